@@ -1,0 +1,171 @@
+/*
+ * surf_b200.h -- C ABI of the B200-native SURF engine (libsurf_b200.so, sm_100a CUDA kernels).
+ *
+ * Drop-in boundary for the OpenCV calls made by stropitek/SurfFeatures:
+ *   cv::SurfFeatureDetector(minHessian).detect(img, kps, mask)
+ *        SurfFeatures/Logic/vtkSlicerSurfFeaturesLogic.cxx:1384-1385
+ *   cv::SurfDescriptorExtractor().compute(img, kps, desc)
+ *        SurfFeatures/Logic/vtkSlicerSurfFeaturesLogic.cxx:1388-1389
+ *   descriptorMatcher->knnMatch(queryDescriptors, matches, k)
+ *        SurfFeatures/Logic/vtkSlicerSurfFeaturesLogic.cxx:640   (+ clear/add at :1402-1403)
+ * Output layouts are those of cv::KeyPoint (28 B), a continuous CV_32F N x D cv::Mat, and
+ * cv::DMatch (16 B): holders at SurfFeatures/Logic/vtkSlicerSurfFeaturesLogic.h:211-237,258-260.
+ *
+ * Conventions: every function returns a SURF_* status (0 = OK); no C++ exception and no exit()
+ * crosses this boundary; there is NO CPU fallback -- without an sm_100 device surf_create fails.
+ * An engine is bound to one device and one CUDA stream and is not thread-safe: use one engine per
+ * host thread / per GPU.  Plain pointers and sizes only; no torch or OpenCV types.
+ */
+#ifndef SURF_B200_H
+#define SURF_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SURF_OK 0
+#define SURF_ERR_BAD_ARG (-1)     /* null pointer, non-positive size, invalid parameter */
+#define SURF_ERR_UNSUPPORTED (-2) /* frame or batch larger than the engine was created for, ... */
+#define SURF_ERR_CAPACITY (-3)    /* output would not fit; surf_required_capacity() tells the need */
+#define SURF_ERR_CUDA (-4)
+#define SURF_ERR_NO_DEVICE (-5)   /* no sm_100 device: there is no CPU path */
+#define SURF_ERR_NCCL (-6)
+
+#define SURF_MEM_HOST 0
+#define SURF_MEM_DEVICE 1
+
+/* cv::KeyPoint field order: Point2f pt; float size, angle, response; int octave, class_id. */
+typedef struct surf_keypoint {
+    float x, y;
+    float size;
+    float angle;
+    float response;
+    int32_t octave;
+    int32_t class_id;
+} surf_keypoint;
+
+/* cv::DMatch field order. */
+typedef struct surf_dmatch {
+    int32_t query_idx;
+    int32_t train_idx;
+    int32_t img_idx;
+    float distance;
+} surf_dmatch;
+
+/* The five public fields of cv::SURF (nonfree/features2d.hpp). */
+typedef struct surf_params {
+    double hessian_threshold;
+    int32_t n_octaves;
+    int32_t n_octave_layers;
+    int32_t extended; /* 0: 64-d, 1: 128-d */
+    int32_t upright;  /* 1: skip orientation, angle = 270 */
+} surf_params;
+
+typedef struct surf_engine surf_engine;
+
+/* Per-stage device times of the last batch call, milliseconds (CUDA events on the engine stream). */
+typedef struct surf_timings {
+    float h2d, integral, hessian, nms, sort, describe, pack, d2h, total;
+    int32_t launches; /* kernels launched by the last call */
+} surf_timings;
+
+/* ---- lifetime ---- */
+
+/* Creates an engine on `device` with workspace for `max_batch` frames of up to max_width x
+ * max_height and `max_keypoints` raw keypoints per frame.  Mirrors `explicit SURF(double
+ * hessianThreshold, int nOctaves, int nOctaveLayers, bool extended, bool upright)`. */
+int surf_create(const surf_params *params, int device, int max_width, int max_height, int max_batch,
+                int max_keypoints, surf_engine **out);
+void surf_destroy(surf_engine *e);
+int surf_set_params(surf_engine *e, const surf_params *params);
+int surf_get_params(const surf_engine *e, surf_params *params);
+const char *surf_last_error(const surf_engine *e);
+/* After SURF_ERR_CAPACITY: the per-frame (or total) count that would have been needed. */
+long surf_required_capacity(const surf_engine *e);
+int surf_descriptor_size(const surf_engine *e); /* SURF::descriptorSize(): 64 or 128 */
+int surf_get_timings(const surf_engine *e, surf_timings *t);
+/* cudaStream_t of the engine, as void* (for callers that time with their own CUDA events). */
+void *surf_stream(const surf_engine *e);
+
+/* ---- single frame: the cv::Feature2D calls ---- */
+
+/* FeatureDetector::detect(image, keypoints, mask).  mask may be NULL (non-zero = keep).
+ * Host pointers.  Writes up to `capacity` keypoints (oriented, sorted, deleted ones removed). */
+int surf_detect(surf_engine *e, const uint8_t *image, int width, int height, size_t pitch, const uint8_t *mask,
+                size_t mask_pitch, surf_keypoint *keypoints, int capacity, int *n_out);
+
+/* DescriptorExtractor::compute(image, keypoints, descriptors); keypoints are in-out and may shrink. */
+int surf_compute(surf_engine *e, const uint8_t *image, int width, int height, size_t pitch,
+                 surf_keypoint *keypoints, int n_in, float *descriptors, int *n_out);
+
+/* SURF::operator()(img, mask, keypoints, descriptors, useProvidedKeypoints=false). */
+int surf_detect_and_compute(surf_engine *e, const uint8_t *image, int width, int height, size_t pitch,
+                            const uint8_t *mask, size_t mask_pitch, surf_keypoint *keypoints, float *descriptors,
+                            int capacity, int *n_out);
+
+/* ---- batches: the frame loop of computeNext (vtkSlicerSurfFeaturesLogic.cxx:1392-1406) ---- */
+
+/* B frames of identical size, frame b at images + b*frame_stride.  Outputs are PACKED in frame
+ * order: frame b owns entries [offsets[b], offsets[b+1]) of keypoints / descriptor rows;
+ * offsets has batch+1 entries (host memory always).  descriptors may be NULL (detect only).
+ * in_mem / out_mem say where images(+mask) and keypoints/descriptors live (SURF_MEM_*).
+ * `capacity` is the total number of keypoint slots in the output arrays. */
+int surf_detect_and_compute_batch(surf_engine *e, const uint8_t *images, int in_mem, int batch, int width,
+                                  int height, size_t pitch, size_t frame_stride, const uint8_t *mask,
+                                  size_t mask_pitch, surf_keypoint *keypoints, float *descriptors, int out_mem,
+                                  long capacity, int32_t *offsets);
+
+/* Asynchronous halves of the call above, for double-buffered streams (two engines, alternate):
+ * submit enqueues upload + all kernels; collect waits and copies the packed results out. */
+int surf_submit_batch(surf_engine *e, const uint8_t *images, int in_mem, int batch, int width, int height,
+                      size_t pitch, size_t frame_stride, const uint8_t *mask, size_t mask_pitch, int want_descriptors);
+int surf_collect_batch(surf_engine *e, surf_keypoint *keypoints, float *descriptors, int out_mem, long capacity,
+                       int32_t *offsets);
+/* Device-resident results of the last submitted batch (valid until the next submit): packed
+ * keypoints, packed descriptors, device int32 offsets[batch+1]. Requires surf_collect_batch or
+ * surf_sync first if the host needs the counts. */
+int surf_device_results(surf_engine *e, const surf_keypoint **keypoints, const float **descriptors,
+                        const int32_t **offsets);
+int surf_sync(surf_engine *e);
+
+/* ---- stage-level exports (parity checks of the per-stage tolerances) ---- */
+
+/* cv::integral(img, sum, CV_32S): sum is (height+1) x (width+1) int32, dense, host. */
+int surf_integral(surf_engine *e, const uint8_t *image, int width, int height, size_t pitch, int clamp01,
+                  int32_t *sum);
+/* det of pyramid layer (octave, layer) for one frame: (height>>octave) x (width>>octave) fp32, host. */
+int surf_hessian_layer(surf_engine *e, const uint8_t *image, int width, int height, size_t pitch, int octave,
+                       int layer, float *det, int *rows, int *cols);
+/* Interpolated, sorted maxima before orientation (angle = -1). */
+int surf_raw_keypoints(surf_engine *e, const uint8_t *image, int width, int height, size_t pitch,
+                       const uint8_t *mask, size_t mask_pitch, surf_keypoint *keypoints, int capacity, int *n_out);
+/* Orientation + descriptor of given keypoints WITHOUT removing deleted ones (size = -1 marks
+ * them); patches (optional) receives the 21 x 21 8-bit window of each keypoint. */
+int surf_describe_keypoints(surf_engine *e, const uint8_t *image, int width, int height, size_t pitch,
+                            surf_keypoint *keypoints, int n, float *descriptors, uint8_t *patches);
+
+/* ---- stage 5: BFMatcher(NORM_L2).knnMatch ---- */
+
+/* k nearest train rows for every query row (k <= 4), ascending distance, ties -> lower train_idx.
+ * out has n_query*k records (img_idx = 0).  mem says where query/train/out live. */
+int surf_match_knn(surf_engine *e, const float *query, int n_query, const float *train, int n_train, int dim,
+                   int k, surf_dmatch *out, int mem);
+/* knnMatch(k=2) + ratio test d1 < ratio*d2; good[i] = 1 if query i passes.  out as above (k=2). */
+int surf_match_ratio(surf_engine *e, const float *query, int n_query, const float *train, int n_train, int dim,
+                     float ratio, surf_dmatch *out, uint8_t *good, int mem);
+
+/* ---- row-sharded keyframe database helpers (multi-GPU, config 5) ---- */
+
+/* Merges per-rank top-k candidate lists: in is n_ranks x n_query x k records (train_idx already
+ * global), out is n_query x k.  Device pointers; runs on the engine stream. */
+int surf_merge_topk(surf_engine *e, const surf_dmatch *in, int n_ranks, int n_query, int k, surf_dmatch *out);
+
+const char *surf_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

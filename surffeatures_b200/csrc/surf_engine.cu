@@ -1,0 +1,840 @@
+// surf_engine.cu -- host side of libsurf_b200.so: the C ABI declared in include/surf_b200.h.
+//
+// Replaces, for the calls at SurfFeatures/Logic/vtkSlicerSurfFeaturesLogic.cxx:1384-1389 and :640,
+// what OpenCV 2.4.5's cv::SURF / BFMatcher do on the CPU.  One engine = one device + one stream +
+// one workspace; every stage is a kernel launch on that stream (surf_kernels.cu, surf_match.cu).
+// There is no CPU path: without an sm_100 device surf_create fails with SURF_ERR_NO_DEVICE.
+#include <cfloat>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "surf_internal.h"
+
+using namespace surfb200;
+
+namespace {
+
+enum Ev { EV_START, EV_H2D, EV_INTEGRAL, EV_HESSIAN_NMS, EV_SORT, EV_DESCRIBE, EV_PACK, EV_END, EV_COUNT };
+
+struct Pending {
+    bool active = false;
+    int batch = 0;
+    bool want_desc = false;
+};
+
+}  // namespace
+
+struct surf_engine {
+    surf_params params{};
+    int device = 0;
+    int max_w = 0, max_h = 0, max_b = 0, cap = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[EV_COUNT]{};
+    bool ev_valid = false;
+
+    // workspace
+    uint8_t *d_img = nullptr;   size_t img_pitch = 0;
+    uint8_t *d_mask = nullptr;
+    uint32_t *d_sum = nullptr, *d_msum = nullptr, *d_bandsum = nullptr;
+    float *d_det = nullptr;     size_t det_words = 0;
+    surf_keypoint *d_kp_a = nullptr, *d_kp_b = nullptr, *d_out_kp = nullptr;
+    float *d_desc = nullptr, *d_out_desc = nullptr;  int desc_dim = 0;
+    uint8_t *d_patches = nullptr;
+    int *d_counts = nullptr, *d_ndel = nullptr, *d_off_in = nullptr, *d_off_out = nullptr, *d_misc = nullptr;
+    int *d_deleted = nullptr;
+    int *h_pin = nullptr;  // pinned: counts[B], ndel[B], off_out[B+1], misc[4]
+    surf_dmatch *d_match_part = nullptr;  size_t match_part_cap = 0;
+    void *d_match_io = nullptr;           size_t match_io_cap = 0;
+
+    surf_keypoint *sorted = nullptr;  // which of d_kp_a / d_kp_b holds the current keypoints
+    Pending pending;
+    surf_timings timings{};
+    int launches = 0;
+    long required = 0;
+    char err[512] = "";
+};
+
+namespace {
+
+int fail(surf_engine *e, int code, const char *fmt, ...)
+{
+    if (e) {
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(e->err, sizeof(e->err), fmt, ap);
+        va_end(ap);
+    }
+    return code;
+}
+
+#define CU(e, call)                                                                                          \
+    do {                                                                                                     \
+        cudaError_t _r = (call);                                                                             \
+        if (_r != cudaSuccess)                                                                               \
+            return fail((e), SURF_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_r), __FILE__, \
+                        __LINE__);                                                                           \
+    } while (0)
+
+inline int cv_round(double v) { return (int)lrint(v); }
+
+// resizeHaarPattern (nonfree/surf.cpp): coordinates rounded half-to-even, fp32 weight.
+void scale_boxes(const int (*src)[5], Box *dst, int n, int old_size, int new_size)
+{
+    const float ratio = (float)new_size / old_size;
+    for (int k = 0; k < n; k++) {
+        dst[k].x1 = cv_round(ratio * src[k][0]);
+        dst[k].y1 = cv_round(ratio * src[k][1]);
+        dst[k].x2 = cv_round(ratio * src[k][2]);
+        dst[k].y2 = cv_round(ratio * src[k][3]);
+        dst[k].w = src[k][4] / ((float)(dst[k].x2 - dst[k].x1) * (dst[k].y2 - dst[k].y1));
+    }
+}
+
+const int kDxx[3][5] = {{0, 2, 3, 7, 1}, {3, 2, 6, 7, -2}, {6, 2, 9, 7, 1}};
+const int kDyy[3][5] = {{2, 0, 7, 3, 1}, {2, 3, 7, 6, -2}, {2, 6, 7, 9, 1}};
+const int kDxy[4][5] = {{1, 1, 4, 4, 1}, {5, 1, 8, 4, -1}, {1, 5, 4, 8, -1}, {5, 5, 8, 8, 1}};
+const int kDm[1][5] = {{0, 0, 9, 9, 1}};
+
+OctavePat make_octave(int octave, int lpo, int W, int H)
+{
+    OctavePat p{};
+    p.step = 1 << octave;
+    p.rows = H / p.step;
+    p.cols = W / p.step;
+    p.lpo = lpo;
+    for (int l = 0; l < lpo; l++) {
+        LayerPat &L = p.L[l];
+        L.size = (9 + 6 * l) << octave;
+        L.m = (L.size / 2) / p.step;
+        L.skip = (L.size > H || L.size > W) ? 1 : 0;
+        L.ni = L.skip ? 0 : 1 + (H - L.size) / p.step;
+        L.nj = L.skip ? 0 : 1 + (W - L.size) / p.step;
+        scale_boxes(kDxx, L.dxx, 3, 9, L.size);
+        scale_boxes(kDyy, L.dyy, 3, 9, L.size);
+        scale_boxes(kDxy, L.dxy, 4, 9, L.size);
+        scale_boxes(kDm, &L.mask, 1, 9, L.size);
+    }
+    return p;
+}
+
+size_t det_octave_words(const surf_params &p, int octave, int W, int H)
+{
+    return (size_t)(p.n_octave_layers + 2) * (size_t)((H >> octave)) * (size_t)((W >> octave));
+}
+
+FrameGeo make_geo(int W, int H)
+{
+    FrameGeo g;
+    g.W = W;
+    g.H = H;
+    g.SP = (W + 1 + 3) & ~3;
+    g.sum_frame = (size_t)(H + 1) * g.SP;
+    return g;
+}
+
+int check_params(surf_engine *e, const surf_params *p)
+{
+    if (!p) return fail(e, SURF_ERR_BAD_ARG, "params is null");
+    if (!(p->hessian_threshold >= 0)) return fail(e, SURF_ERR_BAD_ARG, "hessianThreshold must be >= 0");
+    if (p->n_octaves <= 0 || p->n_octaves > kMaxOctaves)
+        return fail(e, SURF_ERR_BAD_ARG, "nOctaves must be in 1..%d", kMaxOctaves);
+    if (p->n_octave_layers <= 0 || p->n_octave_layers + 2 > kMaxLayersPerOctave)
+        return fail(e, SURF_ERR_BAD_ARG, "nOctaveLayers must be in 1..%d", kMaxLayersPerOctave - 2);
+    return SURF_OK;
+}
+
+void free_workspace(surf_engine *e)
+{
+    cudaFree(e->d_img); cudaFree(e->d_mask); cudaFree(e->d_sum); cudaFree(e->d_msum); cudaFree(e->d_bandsum);
+    cudaFree(e->d_det); cudaFree(e->d_kp_a); cudaFree(e->d_kp_b); cudaFree(e->d_out_kp); cudaFree(e->d_desc);
+    cudaFree(e->d_out_desc); cudaFree(e->d_patches); cudaFree(e->d_counts); cudaFree(e->d_ndel);
+    cudaFree(e->d_off_in); cudaFree(e->d_off_out); cudaFree(e->d_misc); cudaFree(e->d_deleted);
+    cudaFree(e->d_match_part); cudaFree(e->d_match_io);
+    if (e->h_pin) cudaFreeHost(e->h_pin);
+    e->d_img = e->d_mask = nullptr; e->d_sum = e->d_msum = e->d_bandsum = nullptr; e->d_det = nullptr;
+    e->d_kp_a = e->d_kp_b = e->d_out_kp = nullptr; e->d_desc = e->d_out_desc = nullptr; e->d_patches = nullptr;
+    e->d_counts = e->d_ndel = e->d_off_in = e->d_off_out = e->d_misc = e->d_deleted = nullptr;
+    e->d_match_part = nullptr; e->d_match_io = nullptr; e->h_pin = nullptr;
+    e->match_part_cap = e->match_io_cap = 0;
+}
+
+int alloc_det_and_desc(surf_engine *e)
+{
+    // det pyramid and descriptor buffers depend on the parameters; (re)allocate when they change
+    size_t words = 0;
+    for (int o = 0; o < e->params.n_octaves; o++) words += det_octave_words(e->params, o, e->max_w, e->max_h);
+    words *= (size_t)e->max_b;
+    if (words > e->det_words) {
+        cudaFree(e->d_det);
+        e->d_det = nullptr;
+        CU(e, cudaMalloc(&e->d_det, (words ? words : 1) * sizeof(float)));
+        e->det_words = words;
+    }
+    const int D = e->params.extended ? 128 : 64;
+    if (D > e->desc_dim) {
+        cudaFree(e->d_desc);
+        cudaFree(e->d_out_desc);
+        e->d_desc = e->d_out_desc = nullptr;
+        const size_t n = (size_t)e->max_b * e->cap * D;
+        CU(e, cudaMalloc(&e->d_desc, n * sizeof(float)));
+        CU(e, cudaMalloc(&e->d_out_desc, n * sizeof(float)));
+        e->desc_dim = D;
+    }
+    return SURF_OK;
+}
+
+int alloc_workspace(surf_engine *e)
+{
+    const int W = e->max_w, H = e->max_h, B = e->max_b, cap = e->cap;
+    const FrameGeo g = make_geo(W, H);
+    e->img_pitch = (size_t)((W + 15) & ~15);
+    CU(e, cudaMalloc(&e->d_img, e->img_pitch * H * B));
+    CU(e, cudaMalloc(&e->d_mask, e->img_pitch * H));
+    CU(e, cudaMalloc(&e->d_sum, g.sum_frame * sizeof(uint32_t) * B));
+    CU(e, cudaMalloc(&e->d_msum, g.sum_frame * sizeof(uint32_t)));
+    CU(e, cudaMalloc(&e->d_bandsum, integral_bandsum_words(W, H, B) * sizeof(uint32_t)));
+    const size_t nk = (size_t)B * cap;
+    CU(e, cudaMalloc(&e->d_kp_a, nk * sizeof(surf_keypoint)));
+    CU(e, cudaMalloc(&e->d_kp_b, nk * sizeof(surf_keypoint)));
+    CU(e, cudaMalloc(&e->d_out_kp, nk * sizeof(surf_keypoint)));
+    CU(e, cudaMalloc(&e->d_deleted, nk * sizeof(int)));
+    CU(e, cudaMalloc(&e->d_counts, sizeof(int) * B));
+    CU(e, cudaMalloc(&e->d_ndel, sizeof(int) * B));
+    CU(e, cudaMalloc(&e->d_off_in, sizeof(int) * (B + 1)));
+    CU(e, cudaMalloc(&e->d_off_out, sizeof(int) * (B + 1)));
+    CU(e, cudaMalloc(&e->d_misc, sizeof(int) * 4));
+    CU(e, cudaMallocHost(&e->h_pin, sizeof(int) * (3 * (size_t)B + 8)));
+    return alloc_det_and_desc(e);
+}
+
+struct BatchIn {
+    const uint8_t *images;
+    int in_mem, batch, width, height;
+    size_t pitch, frame_stride;
+    const uint8_t *mask;
+    size_t mask_pitch;
+};
+
+int check_frame_args(surf_engine *e, const BatchIn &in)
+{
+    if (!e) return SURF_ERR_BAD_ARG;
+    if (!in.images) return fail(e, SURF_ERR_BAD_ARG, "image pointer is null");
+    if (in.width <= 0 || in.height <= 0 || in.batch <= 0) return fail(e, SURF_ERR_BAD_ARG, "non-positive size");
+    if (in.pitch < (size_t)in.width) return fail(e, SURF_ERR_BAD_ARG, "pitch smaller than width");
+    if (in.batch > 1 && in.frame_stride < in.pitch * (size_t)(in.height - 1) + in.width)
+        return fail(e, SURF_ERR_BAD_ARG, "frame stride smaller than a frame");
+    if (in.width > e->max_w || in.height > e->max_h || in.batch > e->max_b)
+        return fail(e, SURF_ERR_UNSUPPORTED, "%dx%d x%d exceeds the engine's %dx%d x%d workspace", in.width, in.height,
+                    in.batch, e->max_w, e->max_h, e->max_b);
+    if (in.in_mem != SURF_MEM_HOST && in.in_mem != SURF_MEM_DEVICE) return fail(e, SURF_ERR_BAD_ARG, "bad in_mem");
+    if (in.mask && in.mask_pitch < (size_t)in.width) return fail(e, SURF_ERR_BAD_ARG, "mask pitch smaller than width");
+    return SURF_OK;
+}
+
+// Uploads (or references) the frames; returns the device view.
+int stage_images(surf_engine *e, const BatchIn &in, ImageRef *ref)
+{
+    if (in.in_mem == SURF_MEM_DEVICE) {
+        ref->ptr = in.images;
+        ref->pitch = in.pitch;
+        ref->frame_stride = in.frame_stride;
+        return SURF_OK;
+    }
+    const size_t dp = e->img_pitch;
+    if (in.batch == 1 || in.frame_stride == in.pitch * (size_t)in.height) {
+        CU(e, cudaMemcpy2DAsync(e->d_img, dp, in.images, in.pitch, in.width, (size_t)in.height * in.batch,
+                                cudaMemcpyHostToDevice, e->stream));
+    } else {
+        for (int b = 0; b < in.batch; b++)
+            CU(e, cudaMemcpy2DAsync(e->d_img + (size_t)b * dp * in.height, dp, in.images + (size_t)b * in.frame_stride,
+                                    in.pitch, in.width, in.height, cudaMemcpyHostToDevice, e->stream));
+    }
+    ref->ptr = e->d_img;
+    ref->pitch = dp;
+    ref->frame_stride = dp * in.height;
+    return SURF_OK;
+}
+
+int stage_mask(surf_engine *e, const BatchIn &in, const FrameGeo &geo, const uint32_t **msum)
+{
+    *msum = nullptr;
+    if (!in.mask) return SURF_OK;
+    ImageRef m;
+    if (in.in_mem == SURF_MEM_DEVICE) {
+        m.ptr = in.mask;
+        m.pitch = in.mask_pitch;
+    } else {
+        CU(e, cudaMemcpy2DAsync(e->d_mask, e->img_pitch, in.mask, in.mask_pitch, in.width, in.height,
+                                cudaMemcpyHostToDevice, e->stream));
+        m.ptr = e->d_mask;
+        m.pitch = e->img_pitch;
+    }
+    m.frame_stride = 0;
+    launch_integral(m, 1, geo, e->d_msum, e->d_bandsum, 1, e->stream, &e->launches);
+    *msum = e->d_msum;
+    return SURF_OK;
+}
+
+void rec(surf_engine *e, Ev which) { cudaEventRecord(e->ev[which], e->stream); }
+
+// integral -> Hessian pyramid -> maxima -> sort.  Leaves sorted raw keypoints in e->sorted.
+int run_detect(surf_engine *e, const ImageRef &img, const uint32_t *msum, const FrameGeo &geo, int B)
+{
+    const surf_params &p = e->params;
+    CU(e, cudaMemsetAsync(e->d_counts, 0, sizeof(int) * B, e->stream));
+    launch_integral(img, B, geo, e->d_sum, e->d_bandsum, 0, e->stream, &e->launches);
+    rec(e, EV_INTEGRAL);
+    const float thr = (float)p.hessian_threshold;
+    float *det = e->d_det;
+    for (int o = 0; o < p.n_octaves; o++) {
+        const OctavePat pat = make_octave(o, p.n_octave_layers + 2, geo.W, geo.H);
+        const size_t det_frame = (size_t)pat.lpo * pat.rows * pat.cols;
+        launch_hessian(e->d_sum, geo, pat, det, det_frame, B, e->stream, &e->launches);
+        launch_nms(det, det_frame, e->d_sum, msum, geo, pat, o, p.n_octave_layers, thr, e->d_kp_a, e->d_counts, e->cap,
+                   B, e->stream, &e->launches);
+        det += det_frame * B;
+    }
+    rec(e, EV_HESSIAN_NMS);
+    e->sorted = launch_sort(e->d_kp_a, e->d_kp_b, e->d_counts, e->cap, B, e->stream, &e->launches);
+    rec(e, EV_SORT);
+    CU(e, cudaGetLastError());
+    return SURF_OK;
+}
+
+// orientation (+ descriptors) on e->sorted, then removal of deleted keypoints and packing.
+int run_describe_pack(surf_engine *e, const ImageRef &img, const FrameGeo &geo, int B, bool want_desc,
+                      uint8_t *patches, bool pack)
+{
+    const surf_params &p = e->params;
+    CU(e, cudaMemsetAsync(e->d_ndel, 0, sizeof(int) * B, e->stream));
+    CU(e, cudaMemsetAsync(e->d_misc, 0, sizeof(int) * 4, e->stream));
+    launch_offsets(e->d_counts, nullptr, e->cap, B, e->d_off_in, e->stream, &e->launches);
+    DescribeArgs a{};
+    a.img = img;
+    a.sum = e->d_sum;
+    a.geo = geo;
+    a.kps = e->sorted;
+    a.cap = e->cap;
+    a.offsets = e->d_off_in;
+    a.B = B;
+    a.desc = want_desc ? e->d_desc : nullptr;
+    a.patches = patches;
+    a.extended = p.extended;
+    a.upright = p.upright;
+    a.work_counter = e->d_misc;
+    a.status = e->d_misc + 1;
+    a.ndeleted = e->d_ndel;
+    a.deleted_slots = e->d_deleted;
+    launch_describe(a, e->stream, &e->launches);
+    rec(e, EV_DESCRIBE);
+    if (pack) {
+        launch_offsets(e->d_counts, e->d_ndel, e->cap, B, e->d_off_out, e->stream, &e->launches);
+        launch_pack(e->sorted, want_desc ? e->d_desc : nullptr, p.extended ? 128 : 64, e->cap, B, e->d_off_in, e->d_ndel,
+                    e->d_deleted, e->d_off_out, e->d_out_kp, want_desc ? e->d_out_desc : nullptr, e->stream,
+                    &e->launches);
+    }
+    rec(e, EV_PACK);
+    CU(e, cudaGetLastError());
+    return SURF_OK;
+}
+
+int fetch_counts(surf_engine *e, int B)
+{
+    // counts[B] | ndel[B] | off_out[B+1] | misc[4]
+    int *h = e->h_pin;
+    CU(e, cudaMemcpyAsync(h, e->d_counts, sizeof(int) * B, cudaMemcpyDeviceToHost, e->stream));
+    CU(e, cudaMemcpyAsync(h + B, e->d_ndel, sizeof(int) * B, cudaMemcpyDeviceToHost, e->stream));
+    CU(e, cudaMemcpyAsync(h + 2 * B, e->d_off_out, sizeof(int) * (B + 1), cudaMemcpyDeviceToHost, e->stream));
+    CU(e, cudaMemcpyAsync(h + 3 * B + 1, e->d_misc, sizeof(int) * 4, cudaMemcpyDeviceToHost, e->stream));
+    return SURF_OK;
+}
+
+int check_counts(surf_engine *e, int B)
+{
+    const int *h = e->h_pin;
+    int worst = 0;
+    for (int b = 0; b < B; b++) worst = h[b] > worst ? h[b] : worst;
+    if (worst > e->cap) {
+        e->required = worst;
+        return fail(e, SURF_ERR_CAPACITY, "a frame produced %d raw keypoints; the engine was created for %d per frame",
+                    worst, e->cap);
+    }
+    if (h[3 * B + 1 + 1] & 1)
+        return fail(e, SURF_ERR_UNSUPPORTED, "a keypoint needs a descriptor window wider than %d pixels", kMaxWindow);
+    return SURF_OK;
+}
+
+void collect_timings(surf_engine *e)
+{
+    auto ms = [&](Ev a, Ev b) {
+        float t = 0;
+        cudaEventElapsedTime(&t, e->ev[a], e->ev[b]);
+        return t;
+    };
+    surf_timings &t = e->timings;
+    t.h2d = ms(EV_START, EV_H2D);
+    t.integral = ms(EV_H2D, EV_INTEGRAL);
+    t.hessian = ms(EV_INTEGRAL, EV_HESSIAN_NMS);  // Hessian + maxima of all octaves, interleaved
+    t.nms = 0;
+    t.sort = ms(EV_HESSIAN_NMS, EV_SORT);
+    t.describe = ms(EV_SORT, EV_DESCRIBE);
+    t.pack = ms(EV_DESCRIBE, EV_PACK);
+    t.d2h = ms(EV_PACK, EV_END);
+    t.total = ms(EV_START, EV_END);
+    t.launches = e->launches;
+}
+
+int ensure_device(surf_engine *e)
+{
+    CU(e, cudaSetDevice(e->device));
+    return SURF_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *surf_version(void) { return "surf_b200 0.1 (sm_100a)"; }
+
+int surf_create(const surf_params *params, int device, int max_width, int max_height, int max_batch, int max_keypoints,
+                surf_engine **out)
+{
+    if (!out) return SURF_ERR_BAD_ARG;
+    *out = nullptr;
+    if (max_width <= 0 || max_height <= 0 || max_batch <= 0 || max_keypoints <= 0) return SURF_ERR_BAD_ARG;
+    int rc = check_params(nullptr, params);
+    if (rc) return rc;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0 || device < 0 || device >= ndev) {
+        cudaGetLastError();
+        return SURF_ERR_NO_DEVICE;
+    }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return SURF_ERR_NO_DEVICE;
+    if (prop.major != 10) return SURF_ERR_NO_DEVICE;  // kernels are built for sm_100a only
+    surf_engine *e = new (std::nothrow) surf_engine();
+    if (!e) return SURF_ERR_BAD_ARG;
+    e->params = *params;
+    e->device = device;
+    e->max_w = max_width;
+    e->max_h = max_height;
+    e->max_b = max_batch;
+    e->cap = (max_keypoints + 127) & ~127;
+    if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete e;
+        return SURF_ERR_CUDA;
+    }
+    for (int i = 0; i < EV_COUNT; i++) cudaEventCreate(&e->ev[i]);
+    e->ev_valid = true;
+    upload_tables();
+    rc = alloc_workspace(e);
+    if (rc == SURF_OK && cudaGetLastError() != cudaSuccess) rc = SURF_ERR_CUDA;
+    if (rc) {
+        fprintf(stderr, "surf_create: %s\n", e->err);
+        surf_destroy(e);
+        return rc;
+    }
+    *out = e;
+    return SURF_OK;
+}
+
+void surf_destroy(surf_engine *e)
+{
+    if (!e) return;
+    cudaSetDevice(e->device);
+    if (e->stream) cudaStreamSynchronize(e->stream);
+    free_workspace(e);
+    if (e->ev_valid)
+        for (int i = 0; i < EV_COUNT; i++) cudaEventDestroy(e->ev[i]);
+    if (e->stream) cudaStreamDestroy(e->stream);
+    delete e;
+}
+
+int surf_set_params(surf_engine *e, const surf_params *params)
+{
+    if (!e) return SURF_ERR_BAD_ARG;
+    int rc = check_params(e, params);
+    if (rc) return rc;
+    if ((rc = ensure_device(e))) return rc;
+    CU(e, cudaStreamSynchronize(e->stream));
+    e->params = *params;
+    return alloc_det_and_desc(e);
+}
+
+int surf_get_params(const surf_engine *e, surf_params *params)
+{
+    if (!e || !params) return SURF_ERR_BAD_ARG;
+    *params = e->params;
+    return SURF_OK;
+}
+
+const char *surf_last_error(const surf_engine *e) { return e ? e->err : "null engine"; }
+long surf_required_capacity(const surf_engine *e) { return e ? e->required : 0; }
+int surf_descriptor_size(const surf_engine *e) { return e ? (e->params.extended ? 128 : 64) : 0; }
+void *surf_stream(const surf_engine *e) { return e ? (void *)e->stream : nullptr; }
+
+int surf_get_timings(const surf_engine *e, surf_timings *t)
+{
+    if (!e || !t) return SURF_ERR_BAD_ARG;
+    *t = e->timings;
+    return SURF_OK;
+}
+
+int surf_sync(surf_engine *e)
+{
+    if (!e) return SURF_ERR_BAD_ARG;
+    int rc = ensure_device(e);
+    if (rc) return rc;
+    CU(e, cudaStreamSynchronize(e->stream));
+    return SURF_OK;
+}
+
+int surf_submit_batch(surf_engine *e, const uint8_t *images, int in_mem, int batch, int width, int height, size_t pitch,
+                      size_t frame_stride, const uint8_t *mask, size_t mask_pitch, int want_descriptors)
+{
+    BatchIn in{images, in_mem, batch, width, height, pitch, frame_stride, mask, mask_pitch};
+    int rc = check_frame_args(e, in);
+    if (rc) return rc;
+    if ((rc = ensure_device(e))) return rc;
+    e->pending.active = false;
+    e->launches = 0;
+    const FrameGeo geo = make_geo(width, height);
+    rec(e, EV_START);
+    ImageRef img;
+    if ((rc = stage_images(e, in, &img))) return rc;
+    const uint32_t *msum = nullptr;
+    if ((rc = stage_mask(e, in, geo, &msum))) return rc;
+    rec(e, EV_H2D);
+    if ((rc = run_detect(e, img, msum, geo, batch))) return rc;
+    if ((rc = run_describe_pack(e, img, geo, batch, want_descriptors != 0, nullptr, true))) return rc;
+    if ((rc = fetch_counts(e, batch))) return rc;
+    e->pending.active = true;
+    e->pending.batch = batch;
+    e->pending.want_desc = want_descriptors != 0;
+    return SURF_OK;
+}
+
+int surf_collect_batch(surf_engine *e, surf_keypoint *keypoints, float *descriptors, int out_mem, long capacity,
+                       int32_t *offsets)
+{
+    if (!e) return SURF_ERR_BAD_ARG;
+    if (!e->pending.active) return fail(e, SURF_ERR_BAD_ARG, "no submitted batch to collect");
+    if (!offsets) return fail(e, SURF_ERR_BAD_ARG, "offsets is null");
+    int rc = ensure_device(e);
+    if (rc) return rc;
+    const int B = e->pending.batch;
+    CU(e, cudaStreamSynchronize(e->stream));
+    if ((rc = check_counts(e, B))) return rc;
+    const int *off = e->h_pin + 2 * B;
+    const long total = off[B];
+    for (int b = 0; b <= B; b++) offsets[b] = off[b];
+    if (total > capacity) {
+        e->required = total;
+        return fail(e, SURF_ERR_CAPACITY, "%ld keypoints in the batch; the output arrays hold %ld", total, capacity);
+    }
+    const cudaMemcpyKind kind = out_mem == SURF_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+    const int D = e->params.extended ? 128 : 64;
+    if (total > 0 && keypoints)
+        CU(e, cudaMemcpyAsync(keypoints, e->d_out_kp, sizeof(surf_keypoint) * total, kind, e->stream));
+    if (total > 0 && descriptors && e->pending.want_desc)
+        CU(e, cudaMemcpyAsync(descriptors, e->d_out_desc, sizeof(float) * D * total, kind, e->stream));
+    rec(e, EV_END);
+    CU(e, cudaStreamSynchronize(e->stream));
+    collect_timings(e);
+    return SURF_OK;
+}
+
+int surf_device_results(surf_engine *e, const surf_keypoint **keypoints, const float **descriptors,
+                        const int32_t **offsets)
+{
+    if (!e) return SURF_ERR_BAD_ARG;
+    if (!e->pending.active) return fail(e, SURF_ERR_BAD_ARG, "no submitted batch");
+    if (keypoints) *keypoints = e->d_out_kp;
+    if (descriptors) *descriptors = e->pending.want_desc ? e->d_out_desc : nullptr;
+    if (offsets) *offsets = e->d_off_out;
+    return SURF_OK;
+}
+
+int surf_detect_and_compute_batch(surf_engine *e, const uint8_t *images, int in_mem, int batch, int width, int height,
+                                  size_t pitch, size_t frame_stride, const uint8_t *mask, size_t mask_pitch,
+                                  surf_keypoint *keypoints, float *descriptors, int out_mem, long capacity,
+                                  int32_t *offsets)
+{
+    int rc = surf_submit_batch(e, images, in_mem, batch, width, height, pitch, frame_stride, mask, mask_pitch,
+                               descriptors != nullptr);
+    if (rc) return rc;
+    return surf_collect_batch(e, keypoints, descriptors, out_mem, capacity, offsets);
+}
+
+int surf_detect_and_compute(surf_engine *e, const uint8_t *image, int width, int height, size_t pitch,
+                            const uint8_t *mask, size_t mask_pitch, surf_keypoint *keypoints, float *descriptors,
+                            int capacity, int *n_out)
+{
+    if (!e) return SURF_ERR_BAD_ARG;
+    if (!n_out) return fail(e, SURF_ERR_BAD_ARG, "n_out is null");
+    *n_out = 0;
+    // cv::FeatureDetector::detect: an empty image yields no keypoints, not an error
+    if (!image || width == 0 || height == 0) return image ? SURF_OK : fail(e, SURF_ERR_BAD_ARG, "image pointer is null");
+    int32_t off[2] = {0, 0};
+    int rc = surf_detect_and_compute_batch(e, image, SURF_MEM_HOST, 1, width, height, pitch, pitch * (size_t)height, mask,
+                                           mask_pitch, keypoints, descriptors, SURF_MEM_HOST, capacity, off);
+    if (rc) return rc;
+    *n_out = off[1];
+    return SURF_OK;
+}
+
+int surf_detect(surf_engine *e, const uint8_t *image, int width, int height, size_t pitch, const uint8_t *mask,
+                size_t mask_pitch, surf_keypoint *keypoints, int capacity, int *n_out)
+{
+    return surf_detect_and_compute(e, image, width, height, pitch, mask, mask_pitch, keypoints, nullptr, capacity, n_out);
+}
+
+static int describe_given(surf_engine *e, const uint8_t *image, int width, int height, size_t pitch,
+                          surf_keypoint *keypoints, int n, float *descriptors, uint8_t *patches, bool pack, int *n_out)
+{
+    BatchIn in{image, SURF_MEM_HOST, 1, width, height, pitch, pitch * (size_t)height, nullptr, 0};
+    int rc = check_frame_args(e, in);
+    if (rc) return rc;
+    if (!keypoints) return fail(e, SURF_ERR_BAD_ARG, "keypoints is null");
+    if (n > e->cap) {
+        e->required = n;
+        return fail(e, SURF_ERR_CAPACITY, "%d keypoints given; the engine was created for %d per frame", n, e->cap);
+    }
+    if ((rc = ensure_device(e))) return rc;
+    e->pending.active = false;
+    e->launches = 0;
+    const FrameGeo geo = make_geo(width, height);
+    const int D = e->params.extended ? 128 : 64;
+    rec(e, EV_START);
+    ImageRef img;
+    if ((rc = stage_images(e, in, &img))) return rc;
+    CU(e, cudaMemcpyAsync(e->d_kp_a, keypoints, sizeof(surf_keypoint) * n, cudaMemcpyHostToDevice, e->stream));
+    CU(e, cudaMemcpyAsync(e->d_counts, &n, sizeof(int), cudaMemcpyHostToDevice, e->stream));
+    e->sorted = e->d_kp_a;
+    rec(e, EV_H2D);
+    launch_integral(img, 1, geo, e->d_sum, e->d_bandsum, 0, e->stream, &e->launches);
+    rec(e, EV_INTEGRAL);
+    rec(e, EV_HESSIAN_NMS);
+    rec(e, EV_SORT);
+    if (patches && !e->d_patches) CU(e, cudaMalloc(&e->d_patches, (size_t)e->cap * kPatchPx));
+    if ((rc = run_describe_pack(e, img, geo, 1, descriptors != nullptr, patches ? e->d_patches : nullptr, pack))) return rc;
+    if ((rc = fetch_counts(e, 1))) return rc;
+    CU(e, cudaStreamSynchronize(e->stream));
+    if ((rc = check_counts(e, 1))) return rc;
+    if (pack) {
+        const int m = e->h_pin[2 + 1];
+        if (m > 0) {
+            CU(e, cudaMemcpyAsync(keypoints, e->d_out_kp, sizeof(surf_keypoint) * m, cudaMemcpyDeviceToHost, e->stream));
+            if (descriptors)
+                CU(e, cudaMemcpyAsync(descriptors, e->d_out_desc, sizeof(float) * D * m, cudaMemcpyDeviceToHost, e->stream));
+        }
+        if (n_out) *n_out = m;
+    } else {
+        CU(e, cudaMemcpyAsync(keypoints, e->d_kp_a, sizeof(surf_keypoint) * n, cudaMemcpyDeviceToHost, e->stream));
+        if (descriptors)
+            CU(e, cudaMemcpyAsync(descriptors, e->d_desc, sizeof(float) * D * n, cudaMemcpyDeviceToHost, e->stream));
+        if (patches)
+            CU(e, cudaMemcpyAsync(patches, e->d_patches, (size_t)n * kPatchPx, cudaMemcpyDeviceToHost, e->stream));
+        if (n_out) *n_out = n;
+    }
+    rec(e, EV_END);
+    CU(e, cudaStreamSynchronize(e->stream));
+    collect_timings(e);
+    return SURF_OK;
+}
+
+int surf_compute(surf_engine *e, const uint8_t *image, int width, int height, size_t pitch, surf_keypoint *keypoints,
+                 int n_in, float *descriptors, int *n_out)
+{
+    if (!e) return SURF_ERR_BAD_ARG;
+    if (!n_out) return fail(e, SURF_ERR_BAD_ARG, "n_out is null");
+    *n_out = 0;
+    // DescriptorExtractor::compute: empty image or no keypoints -> empty result
+    if (!image || width == 0 || height == 0 || n_in <= 0) return SURF_OK;
+    if (!keypoints || !descriptors) return fail(e, SURF_ERR_BAD_ARG, "null keypoints or descriptors");
+    // KeyPointsFilter::runByKeypointSize(keypoints, FLT_EPSILON): stable removal on the host
+    int m = 0;
+    for (int i = 0; i < n_in; i++)
+        if (!(keypoints[i].size < FLT_EPSILON)) keypoints[m++] = keypoints[i];
+    if (m == 0) return SURF_OK;
+    return describe_given(e, image, width, height, pitch, keypoints, m, descriptors, nullptr, true, n_out);
+}
+
+int surf_describe_keypoints(surf_engine *e, const uint8_t *image, int width, int height, size_t pitch,
+                            surf_keypoint *keypoints, int n, float *descriptors, uint8_t *patches)
+{
+    if (!e) return SURF_ERR_BAD_ARG;
+    if (n <= 0) return SURF_OK;
+    return describe_given(e, image, width, height, pitch, keypoints, n, descriptors, patches, false, nullptr);
+}
+
+int surf_integral(surf_engine *e, const uint8_t *image, int width, int height, size_t pitch, int clamp01, int32_t *sum)
+{
+    BatchIn in{image, SURF_MEM_HOST, 1, width, height, pitch, pitch * (size_t)height, nullptr, 0};
+    int rc = check_frame_args(e, in);
+    if (rc) return rc;
+    if (!sum) return fail(e, SURF_ERR_BAD_ARG, "sum is null");
+    if ((rc = ensure_device(e))) return rc;
+    e->pending.active = false;
+    e->launches = 0;
+    const FrameGeo geo = make_geo(width, height);
+    ImageRef img;
+    if ((rc = stage_images(e, in, &img))) return rc;
+    launch_integral(img, 1, geo, e->d_sum, e->d_bandsum, clamp01, e->stream, &e->launches);
+    CU(e, cudaGetLastError());
+    CU(e, cudaMemcpy2DAsync(sum, sizeof(int32_t) * (width + 1), e->d_sum, sizeof(uint32_t) * geo.SP,
+                            sizeof(int32_t) * (width + 1), height + 1, cudaMemcpyDeviceToHost, e->stream));
+    CU(e, cudaStreamSynchronize(e->stream));
+    return SURF_OK;
+}
+
+int surf_hessian_layer(surf_engine *e, const uint8_t *image, int width, int height, size_t pitch, int octave, int layer,
+                       float *det, int *rows, int *cols)
+{
+    BatchIn in{image, SURF_MEM_HOST, 1, width, height, pitch, pitch * (size_t)height, nullptr, 0};
+    int rc = check_frame_args(e, in);
+    if (rc) return rc;
+    const int lpo = e->params.n_octave_layers + 2;
+    if (!det || octave < 0 || octave >= e->params.n_octaves || layer < 0 || layer >= lpo)
+        return fail(e, SURF_ERR_BAD_ARG, "bad octave/layer or null output");
+    if ((rc = ensure_device(e))) return rc;
+    e->pending.active = false;
+    e->launches = 0;
+    const FrameGeo geo = make_geo(width, height);
+    ImageRef img;
+    if ((rc = stage_images(e, in, &img))) return rc;
+    launch_integral(img, 1, geo, e->d_sum, e->d_bandsum, 0, e->stream, &e->launches);
+    const OctavePat pat = make_octave(octave, lpo, width, height);
+    const size_t det_frame = (size_t)pat.lpo * pat.rows * pat.cols;
+    launch_hessian(e->d_sum, geo, pat, e->d_det, det_frame, 1, e->stream, &e->launches);
+    CU(e, cudaGetLastError());
+    const size_t plane = (size_t)pat.rows * pat.cols;
+    if (plane)
+        CU(e, cudaMemcpyAsync(det, e->d_det + plane * layer, plane * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+    CU(e, cudaStreamSynchronize(e->stream));
+    if (rows) *rows = pat.rows;
+    if (cols) *cols = pat.cols;
+    return SURF_OK;
+}
+
+int surf_raw_keypoints(surf_engine *e, const uint8_t *image, int width, int height, size_t pitch, const uint8_t *mask,
+                       size_t mask_pitch, surf_keypoint *keypoints, int capacity, int *n_out)
+{
+    BatchIn in{image, SURF_MEM_HOST, 1, width, height, pitch, pitch * (size_t)height, mask, mask_pitch};
+    int rc = check_frame_args(e, in);
+    if (rc) return rc;
+    if (!keypoints || !n_out) return fail(e, SURF_ERR_BAD_ARG, "null output");
+    if ((rc = ensure_device(e))) return rc;
+    e->pending.active = false;
+    e->launches = 0;
+    const FrameGeo geo = make_geo(width, height);
+    rec(e, EV_START);
+    ImageRef img;
+    if ((rc = stage_images(e, in, &img))) return rc;
+    const uint32_t *msum = nullptr;
+    if ((rc = stage_mask(e, in, geo, &msum))) return rc;
+    rec(e, EV_H2D);
+    if ((rc = run_detect(e, img, msum, geo, 1))) return rc;
+    CU(e, cudaMemcpyAsync(e->h_pin, e->d_counts, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+    CU(e, cudaStreamSynchronize(e->stream));
+    const int n = e->h_pin[0];
+    *n_out = n;
+    if (n > e->cap || n > capacity) {
+        e->required = n;
+        return fail(e, SURF_ERR_CAPACITY, "%d raw keypoints; capacity %d (engine %d)", n, capacity, e->cap);
+    }
+    if (n > 0) CU(e, cudaMemcpy(keypoints, e->sorted, sizeof(surf_keypoint) * n, cudaMemcpyDeviceToHost));
+    return SURF_OK;
+}
+
+// ---- stage 5 ----
+
+static int match_common(surf_engine *e, const float *query, int n_query, const float *train, int n_train, int dim, int k,
+                        float ratio, surf_dmatch *out, uint8_t *good, int mem)
+{
+    if (!e) return SURF_ERR_BAD_ARG;
+    if (!query || !train || !out) return fail(e, SURF_ERR_BAD_ARG, "null pointer");
+    if (n_query < 0 || n_train < 0) return fail(e, SURF_ERR_BAD_ARG, "negative row count");
+    if (dim != 64 && dim != 128) return fail(e, SURF_ERR_UNSUPPORTED, "descriptor length must be 64 or 128");
+    if (k < 1 || k > 4) return fail(e, SURF_ERR_UNSUPPORTED, "k must be in 1..4");
+    if (n_query == 0) return SURF_OK;
+    int rc = ensure_device(e);
+    if (rc) return rc;
+    e->launches = 0;
+    const float *dq = query, *dt = train;
+    surf_dmatch *dout = out;
+    uint8_t *dgood = good;
+    if (mem == SURF_MEM_HOST) {
+        const size_t bq = sizeof(float) * dim * (size_t)n_query, bt = sizeof(float) * dim * (size_t)n_train;
+        const size_t bo = sizeof(surf_dmatch) * (size_t)k * n_query;
+        const size_t need = ((bq + 255) & ~(size_t)255) + ((bt + 255) & ~(size_t)255) + ((bo + 255) & ~(size_t)255) + n_query;
+        if (need > e->match_io_cap) {
+            cudaFree(e->d_match_io);
+            e->d_match_io = nullptr;
+            e->match_io_cap = 0;
+            CU(e, cudaMalloc(&e->d_match_io, need));
+            e->match_io_cap = need;
+        }
+        char *p = (char *)e->d_match_io;
+        float *q2 = (float *)p;
+        p += (bq + 255) & ~(size_t)255;
+        float *t2 = (float *)p;
+        p += (bt + 255) & ~(size_t)255;
+        dout = (surf_dmatch *)p;
+        p += (bo + 255) & ~(size_t)255;
+        dgood = (uint8_t *)p;
+        CU(e, cudaMemcpyAsync(q2, query, bq, cudaMemcpyHostToDevice, e->stream));
+        if (n_train) CU(e, cudaMemcpyAsync(t2, train, bt, cudaMemcpyHostToDevice, e->stream));
+        dq = q2;
+        dt = t2;
+    }
+    const size_t need_part = match_scratch_records(n_query, n_train > 0 ? n_train : 1, k);
+    if (need_part > e->match_part_cap) {
+        cudaFree(e->d_match_part);
+        e->d_match_part = nullptr;
+        e->match_part_cap = 0;
+        CU(e, cudaMalloc(&e->d_match_part, need_part * sizeof(surf_dmatch)));
+        e->match_part_cap = need_part;
+    }
+    launch_match_knn(dq, n_query, dt, n_train, dim, k, dout, 0, e->d_match_part, e->stream, &e->launches);
+    if (good) launch_ratio_test(dout, n_query, ratio, dgood, e->stream, &e->launches);
+    CU(e, cudaGetLastError());
+    if (mem == SURF_MEM_HOST) {
+        CU(e, cudaMemcpyAsync(out, dout, sizeof(surf_dmatch) * (size_t)k * n_query, cudaMemcpyDeviceToHost, e->stream));
+        if (good) CU(e, cudaMemcpyAsync(good, dgood, n_query, cudaMemcpyDeviceToHost, e->stream));
+        CU(e, cudaStreamSynchronize(e->stream));
+    }
+    return SURF_OK;
+}
+
+int surf_match_knn(surf_engine *e, const float *query, int n_query, const float *train, int n_train, int dim, int k,
+                   surf_dmatch *out, int mem)
+{
+    return match_common(e, query, n_query, train, n_train, dim, k, 0.f, out, nullptr, mem);
+}
+
+int surf_match_ratio(surf_engine *e, const float *query, int n_query, const float *train, int n_train, int dim,
+                     float ratio, surf_dmatch *out, uint8_t *good, int mem)
+{
+    if (e && !good) return fail(e, SURF_ERR_BAD_ARG, "good is null");
+    return match_common(e, query, n_query, train, n_train, dim, 2, ratio, out, good, mem);
+}
+
+int surf_merge_topk(surf_engine *e, const surf_dmatch *in, int n_ranks, int n_query, int k, surf_dmatch *out)
+{
+    if (!e) return SURF_ERR_BAD_ARG;
+    if (!in || !out || n_ranks <= 0 || n_query < 0 || k < 1 || k > 4) return fail(e, SURF_ERR_BAD_ARG, "bad argument");
+    if (n_query == 0) return SURF_OK;
+    int rc = ensure_device(e);
+    if (rc) return rc;
+    launch_merge_topk(in, n_ranks, n_query, k, out, e->stream, &e->launches);
+    CU(e, cudaGetLastError());
+    return SURF_OK;
+}
+
+}  // extern "C"

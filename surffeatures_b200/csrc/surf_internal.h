@@ -1,0 +1,101 @@
+// surf_internal.h -- types shared by the host engine and the sm_100a kernels (not part of the ABI).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "surf_b200.h"
+
+namespace surfb200 {
+
+constexpr int kMaxLayersPerOctave = 8;  // nOctaveLayers + 2 <= 8
+constexpr int kMaxOctaves = 8;
+constexpr int kPatch = 21;              // PATCH_SZ + 1 (OpenCV nonfree/surf.cpp)
+constexpr int kPatchPx = kPatch * kPatch;
+constexpr int kOriSamples = 113;        // integer points with i^2 + j^2 <= 36
+constexpr int kOriWindows = 72;         // 0, 5, ..., 355 degrees
+constexpr int kMaxWindow = 768;         // largest descriptor window side handled (size 264 -> 739)
+constexpr int kWinSmemSide = 128;       // windows up to 128 x 128 are staged in shared memory
+constexpr int kSortChunk = 1024;
+
+// One box of a resized Haar pattern: corner coordinates relative to the filter origin in the
+// integral image and the signed fp32 weight 1/area  (resizeHaarPattern).
+struct Box {
+    int x1, y1, x2, y2;
+    float w;
+};
+
+struct LayerPat {
+    int size;    // filter side in pixels
+    int m;       // (size/2)/step: first written sample row/column
+    int ni, nj;  // written samples: 1 + (H - size)/step, 1 + (W - size)/step
+    int skip;    // size > H or size > W: layer left at zero
+    Box dxx[3], dyy[3], dxy[4];
+    Box mask;    // (0,0,9,9) resized: mean of the mask integral under the filter
+};
+
+struct OctavePat {
+    int step, rows, cols, lpo;  // sampling step 2^o, sample grid, layers in this octave
+    LayerPat L[kMaxLayersPerOctave];
+};
+
+struct FrameGeo {
+    int W, H;
+    int SP;            // integral row pitch in 32-bit words (multiple of 4)
+    size_t sum_frame;  // words per integral frame: (H + 1) * SP
+};
+
+struct ImageRef {
+    const uint8_t *ptr;
+    size_t pitch;         // bytes between rows
+    size_t frame_stride;  // bytes between frames
+};
+
+struct DescribeArgs {
+    ImageRef img;
+    const uint32_t *sum;
+    FrameGeo geo;
+    surf_keypoint *kps;   // [B][cap], updated in place (angle, size = -1 on deletion)
+    int cap;
+    const int *offsets;   // exclusive prefix of the per-frame counts, B + 1 entries
+    int B;
+    float *desc;          // [B][cap][D] or nullptr (orientation only)
+    uint8_t *patches;     // optional [B][cap][441]
+    int extended, upright;
+    int *work_counter;    // dynamic work queue head
+    int *ndeleted;        // [B]
+    int *deleted_slots;   // [B][cap]
+    int *status;          // bit 0: a window larger than kMaxWindow was met
+};
+
+// ---- launchers (surf_kernels.cu) ----
+int integral_band_rows(int W);
+size_t integral_bandsum_words(int W, int H, int B);
+void launch_integral(const ImageRef &img, int B, const FrameGeo &geo, uint32_t *sum, uint32_t *bandsum, int clamp01,
+                     cudaStream_t st, int *launches);
+void launch_hessian(const uint32_t *sum, const FrameGeo &geo, const OctavePat &pat, float *det, size_t det_frame, int B,
+                    cudaStream_t st, int *launches);
+void launch_nms(const float *det, size_t det_frame, const uint32_t *sum, const uint32_t *msum, const FrameGeo &geo,
+                const OctavePat &pat, int octave, int n_mid, float thr, surf_keypoint *raw, int *counts, int cap, int B,
+                cudaStream_t st, int *launches);
+// Sorts every frame's raw keypoints (response desc, size desc, octave desc, y desc, x asc).
+// Returns the buffer (a or b) that holds the sorted result.
+surf_keypoint *launch_sort(surf_keypoint *a, surf_keypoint *b, const int *counts, int cap, int B, cudaStream_t st,
+                           int *launches);
+// offsets[b] = sum_{b' < b} (min(counts[b'], cap) - (ndel ? ndel[b'] : 0)), B + 1 entries.
+void launch_offsets(const int *counts, const int *ndel, int cap, int B, int *offsets, cudaStream_t st, int *launches);
+void launch_describe(const DescribeArgs &a, cudaStream_t st, int *launches);
+void launch_pack(const surf_keypoint *kps, const float *desc, int D, int cap, int B, const int *in_offsets,
+                 const int *ndel, const int *deleted_slots, const int *out_offsets, surf_keypoint *out_kps,
+                 float *out_desc, cudaStream_t st, int *launches);
+void upload_tables();  // orientation sample weights + descriptor Gaussian -> __constant__ (per device)
+
+// ---- launchers (surf_match.cu) ----
+size_t match_scratch_records(int nq, int nt, int k);  // partial top-k records launch_match_knn needs
+void launch_match_knn(const float *q, int nq, const float *t, int nt, int dim, int k, surf_dmatch *out, int train_base,
+                      surf_dmatch *scratch, cudaStream_t st, int *launches);
+void launch_ratio_test(const surf_dmatch *m, int nq, float ratio, uint8_t *good, cudaStream_t st, int *launches);
+void launch_merge_topk(const surf_dmatch *in, int n_ranks, int nq, int k, surf_dmatch *out, cudaStream_t st,
+                       int *launches);
+
+}  // namespace surfb200

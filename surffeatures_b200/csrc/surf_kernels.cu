@@ -1,0 +1,1022 @@
+// surf_kernels.cu -- stages 1-4 of the SURF path as hand-written sm_100a kernels.
+//
+// Compiled with -fmad=false: the reference's OpenCV 2.4.5 is an SSE-only build
+// (/root/reference/SuperBuild/External_OpenCV.cmake:40-45), so none of its fp32 expressions is
+// contracted into an FMA; discrete decisions (threshold, strict maxima, rounding of angles and
+// window pixels) only reproduce when the operation order and rounding do.
+//
+// Stage map:
+//   K1  integral image        cv::integral(8U -> 32S)                    rows a4
+//   K2  Hessian determinant   calcLayerDetAndTrace, all layers/octave    row  a5
+//   K3  maxima + refinement   findMaximaInLayer + interpolateKeypoint    row  a6
+//   K3b sort                  std::sort(KeypointGreater)                 row  a6
+//   K4  orientation+descr.    SURFInvoker                                rows a7, a8
+//   K6  pack                  removal of deleted keypoints               row  a9
+// reached from SurfFeatures/Logic/vtkSlicerSurfFeaturesLogic.cxx:1384-1389.
+#include <cfloat>
+#include <cmath>
+
+#include "surf_internal.h"
+
+namespace surfb200 {
+
+#define FULL_MASK 0xffffffffu
+
+// ------------------------------------------------------------------------------------------------
+// constant tables (fixed by the algorithm, not by engine parameters)
+// ------------------------------------------------------------------------------------------------
+__constant__ signed char c_ori_x[kOriSamples];
+__constant__ signed char c_ori_y[kOriSamples];
+__constant__ float c_ori_w[kOriSamples];
+__constant__ float c_desc_w[400];
+
+static void gaussian_taps(int n, double sigma, float *out)
+{
+    // getGaussianKernel(n, sigma, CV_32F) as OpenCV 2.4.5 builds it.
+    double s2 = -0.5 / (sigma * sigma), acc = 0;
+    for (int i = 0; i < n; i++) {
+        double x = i - (n - 1) * 0.5;
+        out[i] = (float)std::exp(s2 * x * x);
+        acc += out[i];
+    }
+    acc = 1. / acc;
+    for (int i = 0; i < n; i++) out[i] = (float)(out[i] * acc);
+}
+
+void upload_tables()
+{
+    signed char px[kOriSamples], py[kOriSamples];
+    float pw[kOriSamples], dw[400], g[13], gd[20];
+    gaussian_taps(13, 2.5, g);
+    int n = 0;
+    for (int i = -6; i <= 6; i++)
+        for (int j = -6; j <= 6; j++)
+            if (i * i + j * j <= 36) {
+                px[n] = (signed char)i;  // the outer loop variable is the x offset
+                py[n] = (signed char)j;
+                pw[n++] = g[i + 6] * g[j + 6];
+            }
+    gaussian_taps(20, 3.3, gd);
+    for (int i = 0; i < 20; i++)
+        for (int j = 0; j < 20; j++) dw[i * 20 + j] = gd[i] * gd[j];
+    cudaMemcpyToSymbol(c_ori_x, px, sizeof(px));
+    cudaMemcpyToSymbol(c_ori_y, py, sizeof(py));
+    cudaMemcpyToSymbol(c_ori_w, pw, sizeof(pw));
+    cudaMemcpyToSymbol(c_desc_w, dw, sizeof(dw));
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1: integral image.  Two kernels:
+//   k_band_colsum   per band of R rows, the column totals of that band (reads the image once)
+//   k_band_integral per band: warps scan rows with shuffles into a shared tile, a carry row is
+//                   built from the totals of the bands above, then one thread per column walks
+//                   down the tile and writes the final rows (the integral is written exactly once).
+// Output is (H+1) x (W+1) with a zero first row and column, row pitch SP words.
+// ------------------------------------------------------------------------------------------------
+int integral_band_rows(int W)
+{
+    // tile = R rows x TP words + carry row; keep it under ~160 KB
+    int TP = (W + 4) & ~3;
+    int R = (160 * 1024 / 4 - TP) / TP;
+    if (R > 32) R = 32;
+    if (R < 1) R = 1;
+    return R;
+}
+
+size_t integral_bandsum_words(int W, int H, int B)
+{
+    int R = integral_band_rows(W);
+    int nb = (H + R - 1) / R;
+    return (size_t)B * nb * W;
+}
+
+__global__ void __launch_bounds__(256) k_band_colsum(const uint8_t *__restrict__ img, size_t pitch, size_t fstride,
+                                                     int W, int H, int R, int nbands, uint32_t *__restrict__ bandsum,
+                                                     int clamp01, int aligned4)
+{
+    const int band = blockIdx.y, b = blockIdx.z;
+    const int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (x4 >= W) return;
+    const int y0 = band * R, y1 = min(H, y0 + R);
+    const uint8_t *p = img + (size_t)b * fstride + (size_t)y0 * pitch + x4;
+    uint32_t s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+    if (aligned4 && x4 + 3 < W) {
+        for (int y = y0; y < y1; y++, p += pitch) {
+            uint32_t v = __ldg(reinterpret_cast<const uint32_t *>(p));
+            uint32_t a = v & 0xff, c = (v >> 8) & 0xff, d = (v >> 16) & 0xff, e = v >> 24;
+            if (clamp01) { a = min(a, 1u); c = min(c, 1u); d = min(d, 1u); e = min(e, 1u); }
+            s0 += a; s1 += c; s2 += d; s3 += e;
+        }
+    } else {
+        for (int y = y0; y < y1; y++, p += pitch) {
+            uint32_t v[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                v[k] = (x4 + k < W) ? p[k] : 0;
+                if (clamp01) v[k] = min(v[k], 1u);
+            }
+            s0 += v[0]; s1 += v[1]; s2 += v[2]; s3 += v[3];
+        }
+    }
+    uint32_t *o = bandsum + ((size_t)b * nbands + band) * W + x4;
+    o[0] = s0;
+    if (x4 + 1 < W) o[1] = s1;
+    if (x4 + 2 < W) o[2] = s2;
+    if (x4 + 3 < W) o[3] = s3;
+}
+
+// Inclusive scan of one row of W values produced by `load4(x)` (4 consecutive values starting at
+// x, zero past W) into dst[0..W): 4 values per lane, one warp-shuffle scan per 128 columns.
+template <class Load4>
+__device__ __forceinline__ void warp_row_scan(int W, uint32_t *dst, Load4 load4)
+{
+    const int lane = threadIdx.x & 31;
+    uint32_t running = 0;
+    for (int x0 = 0; x0 < W; x0 += 128) {
+        const int x = x0 + lane * 4;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (x < W) v = load4(x);
+        v.y += v.x;
+        v.z += v.y;
+        v.w += v.z;
+        uint32_t incl = v.w;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            uint32_t t = __shfl_up_sync(FULL_MASK, incl, d);
+            if (lane >= d) incl += t;
+        }
+        const uint32_t base = running + incl - v.w;
+        v.x += base; v.y += base; v.z += base; v.w += base;
+        if (x < W) *reinterpret_cast<uint4 *>(dst + x) = v;  // dst rows are padded to a multiple of 4
+        running += __shfl_sync(FULL_MASK, incl, 31);
+    }
+}
+
+__global__ void __launch_bounds__(1024) k_band_integral(const uint8_t *__restrict__ img, size_t pitch, size_t fstride,
+                                                        int W, int H, int R, int nbands,
+                                                        const uint32_t *__restrict__ bandsum, uint32_t *__restrict__ sum,
+                                                        int SP, size_t sum_frame, int clamp01, int aligned4)
+{
+    extern __shared__ __align__(16) uint32_t smem[];
+    const int TP = (W + 4) & ~3;
+    uint32_t *carry = smem;       // TP words: integral row at the top of the band, columns 1..W
+    uint32_t *tile = smem + TP;   // R x TP words: row prefix sums of the band's rows
+    const int band = blockIdx.x, b = blockIdx.y;
+    const int tid = threadIdx.x, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    const int y0 = band * R, rows = min(R, H - y0);
+
+    // column totals of everything above this band
+    for (int x = tid; x < W; x += blockDim.x) {
+        uint32_t c = 0;
+        const uint32_t *bs = bandsum + (size_t)b * nbands * W + x;
+        for (int k = 0; k < band; k++) c += __ldg(bs + (size_t)k * W);
+        carry[x] = c;
+    }
+    __syncthreads();
+
+    const uint8_t *base = img + (size_t)b * fstride + (size_t)y0 * pitch;
+    // warp 0 turns the carry into a row prefix (in place) and then joins the row scans
+    for (int r = warp - 1; r < rows; r += nwarps) {
+        if (r < 0) {
+            warp_row_scan(W, carry, [&](int x) { return *reinterpret_cast<const uint4 *>(carry + x); });
+            // values past W inside the last uint4 are stale: never read (columns < W only)
+            continue;
+        }
+        const uint8_t *row = base + (size_t)r * pitch;
+        warp_row_scan(W, tile + (size_t)r * TP, [&](int x) {
+            uint4 v;
+            if (aligned4 && x + 3 < W) {
+                uint32_t u = __ldg(reinterpret_cast<const uint32_t *>(row + x));
+                v = make_uint4(u & 0xff, (u >> 8) & 0xff, (u >> 16) & 0xff, u >> 24);
+            } else {
+                v.x = row[x];
+                v.y = (x + 1 < W) ? row[x + 1] : 0;
+                v.z = (x + 2 < W) ? row[x + 2] : 0;
+                v.w = (x + 3 < W) ? row[x + 3] : 0;
+            }
+            if (clamp01) { v.x = min(v.x, 1u); v.y = min(v.y, 1u); v.z = min(v.z, 1u); v.w = min(v.w, 1u); }
+            return v;
+        });
+    }
+    __syncthreads();
+
+    uint32_t *out = sum + (size_t)b * sum_frame;
+    for (int x = tid; x <= W; x += blockDim.x) {
+        if (x == W) {
+            // the zero first column of this band's output rows (and of row 0)
+            if (band == 0) out[0] = 0;
+            for (int r = 0; r < rows; r++) out[(size_t)(y0 + r + 1) * SP] = 0;
+        } else {
+            uint32_t acc = carry[x];
+            if (band == 0) out[x + 1] = 0;
+            uint32_t *o = out + (size_t)(y0 + 1) * SP + x + 1;
+            for (int r = 0; r < rows; r++, o += SP) {
+                acc += tile[(size_t)r * TP + x];
+                *o = acc;
+            }
+        }
+    }
+}
+
+void launch_integral(const ImageRef &img, int B, const FrameGeo &geo, uint32_t *sum, uint32_t *bandsum, int clamp01,
+                     cudaStream_t st, int *launches)
+{
+    const int W = geo.W, H = geo.H;
+    const int R = integral_band_rows(W);
+    const int nbands = (H + R - 1) / R;
+    const int aligned4 = ((reinterpret_cast<uintptr_t>(img.ptr) | img.pitch | img.frame_stride) & 3) == 0;
+    dim3 g1((W + 1023) / 1024, nbands, B);
+    k_band_colsum<<<g1, 256, 0, st>>>(img.ptr, img.pitch, img.frame_stride, W, H, R, nbands, bandsum, clamp01, aligned4);
+    const int TP = (W + 4) & ~3;
+    const size_t smem = (size_t)(R + 1) * TP * sizeof(uint32_t);
+    static bool attr_set[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!attr_set[dev & 63]) {
+        cudaFuncSetAttribute(k_band_integral, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        attr_set[dev & 63] = true;
+    }
+    // one warp per band row plus the carry scan: R + 1 warps, at most 32
+    int nwarps = min(32, R + 1);
+    if (nwarps < 2) nwarps = 2;
+    dim3 g2(nbands, B);
+    k_band_integral<<<g2, nwarps * 32, smem, st>>>(img.ptr, img.pitch, img.frame_stride, W, H, R, nbands, bandsum, sum,
+                                                   geo.SP, geo.sum_frame, clamp01, aligned4);
+    *launches += 2;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Box responses (calcHaarPattern): integer corner sum -> fp32 product with the weight ->
+// accumulated in fp64 -> cast to fp32.  SURVEY.md A3.2.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float box_term(const int *__restrict__ o, int SP, const Box &bx)
+{
+    int s = __ldg(o + bx.y1 * SP + bx.x1) + __ldg(o + bx.y2 * SP + bx.x2) - __ldg(o + bx.y2 * SP + bx.x1) -
+            __ldg(o + bx.y1 * SP + bx.x2);
+    return (float)s * bx.w;
+}
+
+__device__ __forceinline__ float resp3(const int *o, int SP, const Box *bx)
+{
+    double d = (double)box_term(o, SP, bx[0]);
+    d += (double)box_term(o, SP, bx[1]);
+    d += (double)box_term(o, SP, bx[2]);
+    return (float)d;
+}
+
+__device__ __forceinline__ float resp4(const int *o, int SP, const Box *bx)
+{
+    double d = (double)box_term(o, SP, bx[0]);
+    d += (double)box_term(o, SP, bx[1]);
+    d += (double)box_term(o, SP, bx[2]);
+    d += (double)box_term(o, SP, bx[3]);
+    return (float)d;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2: Hessian determinant of every layer of one octave.  One thread per sample, looping over the
+// octave's layers; det is written for the whole sample grid (zero outside the written region, as
+// the oracle's zero-filled arrays).  Layout: det[b][layer][row][col].
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_hessian(const uint32_t *__restrict__ sum, int SP, size_t sum_frame,
+                                                 const __grid_constant__ OctavePat pat, float *__restrict__ det,
+                                                 size_t det_frame)
+{
+    const int j = blockIdx.x * 32 + threadIdx.x;
+    const int i = blockIdx.y * 8 + threadIdx.y;
+    const int b = blockIdx.z;
+    if (i >= pat.rows || j >= pat.cols) return;
+    const int *S = reinterpret_cast<const int *>(sum) + (size_t)b * sum_frame;
+    float *out = det + (size_t)b * det_frame + (size_t)i * pat.cols + j;
+    const size_t plane = (size_t)pat.rows * pat.cols;
+    for (int l = 0; l < pat.lpo; l++) {
+        const LayerPat &P = pat.L[l];
+        float v = 0.f;
+        const int ii = i - P.m, jj = j - P.m;
+        if (!P.skip && ii >= 0 && ii < P.ni && jj >= 0 && jj < P.nj) {
+            const int *o = S + (size_t)(ii * pat.step) * SP + jj * pat.step;
+            float dx = resp3(o, SP, P.dxx);
+            float dy = resp3(o, SP, P.dyy);
+            float dc = resp4(o, SP, P.dxy);
+            v = dx * dy - 0.81f * dc * dc;
+        }
+        out[(size_t)l * plane] = v;
+    }
+}
+
+void launch_hessian(const uint32_t *sum, const FrameGeo &geo, const OctavePat &pat, float *det, size_t det_frame, int B,
+                    cudaStream_t st, int *launches)
+{
+    if (pat.rows <= 0 || pat.cols <= 0) return;
+    dim3 grid((pat.cols + 31) / 32, (pat.rows + 7) / 8, B), block(32, 8);
+    k_hessian<<<grid, block, 0, st>>>(sum, geo.SP, geo.sum_frame, pat, det, det_frame);
+    *launches += 1;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3: strict 3x3x3 maxima over the threshold, optional mask test, quadratic refinement, and
+// warp-aggregated append to the frame's raw keypoint list.  SURVEY.md A3.4.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool refine_maximum(const float (&N)[3][9], int step, int ds, surf_keypoint &kp)
+{
+    // interpolateKeypoint: b = -gradient, A = Hessian of the 3x3x3 block; Matx33f::solve closed form.
+    const float b0 = -(N[1][5] - N[1][3]) / 2, b1 = -(N[1][7] - N[1][1]) / 2, b2 = -(N[2][4] - N[0][4]) / 2;
+    const float xy = (N[1][8] - N[1][6] - N[1][2] + N[1][0]) / 4;
+    const float xs = (N[2][5] - N[2][3] - N[0][5] + N[0][3]) / 4;
+    const float ys = (N[2][7] - N[2][1] - N[0][7] + N[0][1]) / 4;
+    const float a00 = N[1][3] - 2 * N[1][4] + N[1][5];
+    const float a11 = N[1][1] - 2 * N[1][4] + N[1][7];
+    const float a22 = N[0][4] - 2 * N[1][4] + N[2][4];
+    const float a01 = xy, a02 = xs, a10 = xy, a12 = ys, a20 = xs, a21 = ys;
+    float d = a00 * (a11 * a22 - a21 * a12) - a01 * (a10 * a22 - a20 * a12) + a02 * (a10 * a21 - a20 * a11);
+    float x0 = 0, x1 = 0, x2 = 0;
+    if (d != 0) {
+        d = 1 / d;
+        x0 = d * (b0 * (a11 * a22 - a12 * a21) - a01 * (b1 * a22 - a12 * b2) + a02 * (b1 * a21 - a11 * b2));
+        x1 = d * (a00 * (b1 * a22 - a12 * b2) - b0 * (a10 * a22 - a12 * a20) + a02 * (a10 * b2 - b1 * a20));
+        x2 = d * (a00 * (a11 * b2 - b1 * a21) - a01 * (a10 * b2 - b1 * a20) + b0 * (a10 * a21 - a11 * a20));
+    }
+    const bool ok = (x0 != 0 || x1 != 0 || x2 != 0) && fabsf(x0) <= 1 && fabsf(x1) <= 1 && fabsf(x2) <= 1;
+    if (ok) {
+        kp.x += x0 * step;
+        kp.y += x1 * step;
+        kp.size = (float)__float2int_rn(kp.size + x2 * ds);
+    }
+    return ok;
+}
+
+__global__ void __launch_bounds__(256) k_nms(const float *__restrict__ det, size_t det_frame,
+                                             const uint32_t *__restrict__ sum, const uint32_t *__restrict__ msum, int SP,
+                                             size_t sum_frame, const __grid_constant__ OctavePat pat, int octave,
+                                             int n_mid, float thr, surf_keypoint *__restrict__ raw,
+                                             int *__restrict__ counts, int cap)
+{
+    const int j = blockIdx.x * 32 + threadIdx.x;
+    const int i = blockIdx.y * 8 + threadIdx.y;
+    const int b = blockIdx.z / n_mid;
+    const int l = 1 + blockIdx.z % n_mid;
+    const int rows = pat.rows, cols = pat.cols, step = pat.step;
+    const LayerPat &P = pat.L[l];
+    const int size = P.size;
+    const int margin = (pat.L[l + 1].size / 2) / step + 1;
+
+    bool found = false;
+    surf_keypoint kp;
+    if (i >= margin && i < rows - margin && j >= margin && j < cols - margin) {
+        const size_t plane = (size_t)rows * cols;
+        const float *d1 = det + (size_t)b * det_frame + (size_t)l * plane + (size_t)i * cols + j;
+        const float v = __ldg(d1);
+        if (v > thr) {
+            float N[3][9];
+#pragma unroll
+            for (int k = 0; k < 3; k++)
+#pragma unroll
+                for (int r = 0; r < 3; r++)
+#pragma unroll
+                    for (int q = 0; q < 3; q++)
+                        N[k][r * 3 + q] = __ldg(d1 + (ptrdiff_t)(k - 1) * (ptrdiff_t)plane + (r - 1) * cols + (q - 1));
+            const int si = step * (i - (size / 2) / step);
+            const int sj = step * (j - (size / 2) / step);
+            bool keep = true;
+            if (msum) {
+                // mean of min(mask,1) over the size x size box must reach 0.5
+                const int *mo = reinterpret_cast<const int *>(msum) + (size_t)si * SP + sj;
+                const float mv = (float)(double)box_term(mo, SP, P.mask);
+                keep = !(mv < 0.5f);
+            }
+            if (keep) {
+                bool is_max = true;
+#pragma unroll
+                for (int k = 0; k < 3; k++)
+#pragma unroll
+                    for (int q = 0; q < 9; q++)
+                        if (!(k == 1 && q == 4)) is_max = is_max && (v > N[k][q]);
+                if (is_max) {
+                    kp.x = sj + (size - 1) * 0.5f;
+                    kp.y = si + (size - 1) * 0.5f;
+                    kp.size = (float)size;
+                    kp.angle = -1.f;
+                    kp.response = v;
+                    kp.octave = octave;
+                    // class_id = sign(trace) = sign(dxx + dyy), recomputed for the few candidates
+                    const int *o = reinterpret_cast<const int *>(sum) + (size_t)b * sum_frame +
+                                   (size_t)((i - P.m) * step) * SP + (j - P.m) * step;
+                    const float tr = resp3(o, SP, P.dxx) + resp3(o, SP, P.dyy);
+                    kp.class_id = (tr > 0) - (tr < 0);
+                    found = refine_maximum(N, step, size - pat.L[l - 1].size, kp);
+                }
+            }
+        }
+    }
+    const unsigned m = __ballot_sync(FULL_MASK, found);
+    if (m) {
+        const int lane = (threadIdx.y * 32 + threadIdx.x) & 31;
+        const int leader = __ffs(m) - 1;
+        int base = 0;
+        if (lane == leader) base = atomicAdd(counts + b, __popc(m));
+        base = __shfl_sync(FULL_MASK, base, leader);
+        const int pos = base + __popc(m & ((1u << lane) - 1));
+        if (found && pos < cap) raw[(size_t)b * cap + pos] = kp;
+    }
+}
+
+void launch_nms(const float *det, size_t det_frame, const uint32_t *sum, const uint32_t *msum, const FrameGeo &geo,
+                const OctavePat &pat, int octave, int n_mid, float thr, surf_keypoint *raw, int *counts, int cap, int B,
+                cudaStream_t st, int *launches)
+{
+    if (pat.rows <= 0 || pat.cols <= 0) return;
+    dim3 grid((pat.cols + 31) / 32, (pat.rows + 7) / 8, B * n_mid), block(32, 8);
+    k_nms<<<grid, block, 0, st>>>(det, det_frame, sum, msum, geo.SP, geo.sum_frame, pat, octave, n_mid, thr, raw, counts,
+                                  cap);
+    *launches += 1;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3b: per-frame sort with the reference's comparator (KeypointGreater): response desc, size desc,
+// octave desc, y desc, x asc.  Bitonic sort of 1024-keypoint chunks in shared memory, then
+// rank-by-binary-search merge passes between sorted runs (ping-pong buffers).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool kp_before(const surf_keypoint &a, const surf_keypoint &b)
+{
+    if (a.response > b.response) return true;
+    if (a.response < b.response) return false;
+    if (a.size > b.size) return true;
+    if (a.size < b.size) return false;
+    if (a.octave > b.octave) return true;
+    if (a.octave < b.octave) return false;
+    if (a.y < b.y) return false;
+    if (a.y > b.y) return true;
+    return a.x < b.x;
+}
+
+__global__ void __launch_bounds__(512) k_sort_chunks(surf_keypoint *__restrict__ kps, const int *__restrict__ counts,
+                                                     int cap)
+{
+    __shared__ surf_keypoint s_kp[kSortChunk];
+    __shared__ unsigned short s_idx[kSortChunk];
+    const int b = blockIdx.y;
+    const int n = min(counts[b], cap);
+    const int c0 = blockIdx.x * kSortChunk;
+    if (c0 >= n) return;
+    const int cnt = min(kSortChunk, n - c0);
+    surf_keypoint *g = kps + (size_t)b * cap + c0;
+    for (int t = threadIdx.x; t < kSortChunk; t += blockDim.x) {
+        if (t < cnt) s_kp[t] = g[t];
+        s_idx[t] = (unsigned short)t;
+    }
+    __syncthreads();
+    // entries >= cnt sort last; ties between real entries fall back to the slot index
+    auto before = [&](unsigned short a, unsigned short c) {
+        if (a >= cnt || c >= cnt) return a < c && a < cnt;
+        if (kp_before(s_kp[a], s_kp[c])) return true;
+        if (kp_before(s_kp[c], s_kp[a])) return false;
+        return a < c;
+    };
+    for (int k = 2; k <= kSortChunk; k <<= 1) {
+        for (int jj = k >> 1; jj > 0; jj >>= 1) {
+            for (int t = threadIdx.x; t < kSortChunk; t += blockDim.x) {
+                const int p = t ^ jj;
+                if (p > t) {
+                    const unsigned short a = s_idx[t], c = s_idx[p];
+                    const bool up = (t & k) == 0;
+                    if (up ? before(c, a) : before(a, c)) {
+                        s_idx[t] = c;
+                        s_idx[p] = a;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    for (int t = threadIdx.x; t < cnt; t += blockDim.x) g[t] = s_kp[s_idx[t]];
+}
+
+__global__ void __launch_bounds__(256) k_merge_pass(const surf_keypoint *__restrict__ in, surf_keypoint *__restrict__ out,
+                                                    const int *__restrict__ counts, int cap, int run)
+{
+    const int b = blockIdx.y;
+    const int n = min(counts[b], cap);
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    const surf_keypoint *src = in + (size_t)b * cap;
+    const surf_keypoint me = src[e];
+    const int pair0 = (e / (2 * run)) * (2 * run);
+    const int mid = min(pair0 + run, n), end = min(pair0 + 2 * run, n);
+    int rank;
+    if (e < mid) {
+        // number of right-run elements strictly before me
+        int lo = mid, hi = end;
+        while (lo < hi) {
+            int m = (lo + hi) >> 1;
+            if (kp_before(src[m], me)) lo = m + 1; else hi = m;
+        }
+        rank = (e - pair0) + (lo - mid);
+    } else {
+        // number of left-run elements not after me (stable: left wins ties)
+        int lo = pair0, hi = mid;
+        while (lo < hi) {
+            int m = (lo + hi) >> 1;
+            if (!kp_before(me, src[m])) lo = m + 1; else hi = m;
+        }
+        rank = (e - mid) + (lo - pair0);
+    }
+    out[(size_t)b * cap + pair0 + rank] = me;
+}
+
+surf_keypoint *launch_sort(surf_keypoint *a, surf_keypoint *b, const int *counts, int cap, int B, cudaStream_t st,
+                           int *launches)
+{
+    dim3 g1((cap + kSortChunk - 1) / kSortChunk, B);
+    k_sort_chunks<<<g1, 512, 0, st>>>(a, counts, cap);
+    *launches += 1;
+    surf_keypoint *src = a, *dst = b;
+    for (int run = kSortChunk; run < cap; run <<= 1) {
+        dim3 g2((cap + 255) / 256, B);
+        k_merge_pass<<<g2, 256, 0, st>>>(src, dst, counts, cap, run);
+        *launches += 1;
+        surf_keypoint *t = src;
+        src = dst;
+        dst = t;
+    }
+    return src;
+}
+
+// ------------------------------------------------------------------------------------------------
+// offsets: exclusive prefix of the per-frame counts (single block; B <= a few thousand).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) k_offsets(const int *__restrict__ counts, const int *__restrict__ ndel, int cap,
+                                                  int B, int *__restrict__ offsets)
+{
+    __shared__ int s_part[1024];
+    const int tid = threadIdx.x;
+    const int per = (B + 1023) / 1024;
+    const int lo = min(B, tid * per), hi = min(B, lo + per);
+    int s = 0;
+    for (int k = lo; k < hi; k++) s += min(counts[k], cap) - (ndel ? ndel[k] : 0);
+    s_part[tid] = s;
+    __syncthreads();
+    for (int d = 1; d < 1024; d <<= 1) {
+        int t = (tid >= d) ? s_part[tid - d] : 0;
+        __syncthreads();
+        s_part[tid] += t;
+        __syncthreads();
+    }
+    int run = s_part[tid] - s;
+    for (int k = lo; k < hi; k++) {
+        offsets[k] = run;
+        run += min(counts[k], cap) - (ndel ? ndel[k] : 0);
+    }
+    if (tid == 1023) offsets[B] = s_part[1023];
+}
+
+void launch_offsets(const int *counts, const int *ndel, int cap, int B, int *offsets, cudaStream_t st, int *launches)
+{
+    k_offsets<<<1, 1024, 0, st>>>(counts, ndel, cap, B, offsets);
+    *launches += 1;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K4: orientation + descriptor, one CTA (128 threads) per keypoint, persistent CTAs pulling
+// keypoints from an atomic queue.  SURVEY.md A4, A5.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float fast_atan2_deg(float y, float x)
+{
+    // fastAtan2 (core/mathfuncs.cpp): 7th-order odd polynomial, degrees in [0, 360].
+    const float k = (float)(180 / 3.1415926535897932384626433832795);
+    const float p1 = 0.9997878412794807f * k, p3 = -0.3258083974640975f * k;
+    const float p5 = 0.1555786518463281f * k, p7 = -0.04432655554792128f * k;
+    const float ax = fabsf(x), ay = fabsf(y);
+    float a, c, c2;
+    if (ax >= ay) {
+        c = ay / (ax + (float)DBL_EPSILON);
+        c2 = c * c;
+        a = (((p7 * c2 + p5) * c2 + p3) * c2 + p1) * c;
+    } else {
+        c = ax / (ay + (float)DBL_EPSILON);
+        c2 = c * c;
+        a = 90.f - (((p7 * c2 + p5) * c2 + p3) * c2 + p1) * c;
+    }
+    if (x < 0) a = 180.f - a;
+    if (y < 0) a = 360.f - a;
+    return a;
+}
+
+__device__ __forceinline__ int sat_u8(float v)
+{
+    int r = __float2int_rn(v);
+    return r < 0 ? 0 : (r > 255 ? 255 : r);
+}
+
+struct WindowGeo {
+    const uint8_t *img;
+    int pitch, W, H;
+    int upright;
+    int x0, y0;       // upright: integer window origin
+    float sd, cd;     // rotated: -sin, cos of the dominant angle
+    const float *rsx; // per-row start coordinates (fp32 sequential chain)
+    const float *rsy;
+};
+
+// One pixel of the win_size x win_size window around the keypoint.
+__device__ __forceinline__ int window_pixel(const WindowGeo &g, int i, int j)
+{
+    if (g.upright) {
+        int x = min(max(g.x0 + i, 0), g.W - 1);
+        int y = min(max(g.y0 - j, 0), g.H - 1);
+        return g.img[(size_t)y * g.pitch + x];
+    }
+    const double fx = (double)g.rsx[i] + (double)j * (double)g.cd;
+    const double fy = (double)g.rsy[i] - (double)j * (double)g.sd;
+    const int ix = __double2int_rd(fx), iy = __double2int_rd(fy);
+    if ((unsigned)ix < (unsigned)(g.W - 1) && (unsigned)iy < (unsigned)(g.H - 1)) {
+        const float a = (float)(fx - ix), b = (float)(fy - iy);
+        const uint8_t *q = g.img + (size_t)iy * g.pitch + ix;
+        const float v = q[0] * (1.f - a) * (1.f - b) + q[1] * a * (1.f - b) + q[g.pitch] * (1.f - a) * b +
+                        q[g.pitch + 1] * a * b;
+        return __float2int_rn(v) & 0xff;
+    }
+    const int x = min(max(__double2int_rn(fx), 0), g.W - 1);
+    const int y = min(max(__double2int_rn(fy), 0), g.H - 1);
+    return g.img[(size_t)y * g.pitch + x];
+}
+
+struct AreaTab {  // one destination cell of the INTER_AREA table (same for x and y: square window)
+    int start[kPatch];
+    int count[kPatch];
+    float a_first[kPatch], a_mid[kPatch], a_last[kPatch];
+    unsigned char has_first[kPatch], has_last[kPatch];
+};
+
+__device__ __forceinline__ float area_alpha(const AreaTab &t, int d, int e)
+{
+    if (e == 0 && t.has_first[d]) return t.a_first[d];
+    if (e == t.count[d] - 1 && t.has_last[d]) return t.a_last[d];
+    return t.a_mid[d];
+}
+
+constexpr int kDescThreads = 128;
+
+__global__ void __launch_bounds__(kDescThreads) k_describe(const __grid_constant__ DescribeArgs A)
+{
+    extern __shared__ __align__(16) unsigned char s_win[];  // kWinSmemSide^2 bytes
+    __shared__ int s_work;
+    __shared__ float s_X[kOriSamples], s_Y[kOriSamples];
+    __shared__ int s_iang[kOriSamples];
+    __shared__ int s_warp_cnt[4];
+    __shared__ float s_wx[kOriWindows], s_wy[kOriWindows];
+    __shared__ float s_dir, s_scale;
+    __shared__ float s_rsx[kMaxWindow], s_rsy[kMaxWindow];
+    __shared__ AreaTab s_tab;
+    __shared__ unsigned char s_patch[kPatchPx + 3];
+    __shared__ float s_dx[400], s_dy[400];
+    __shared__ float s_vec[128];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int W = A.geo.W, H = A.geo.H, SP = A.geo.SP;
+    const int total = A.offsets[A.B];
+    const int D = A.extended ? 128 : 64;
+
+    for (;;) {
+        __syncthreads();  // everyone is done with the previous keypoint's shared state
+        if (tid == 0) s_work = atomicAdd(A.work_counter, 1);
+        __syncthreads();
+        const int w = s_work;
+        if (w >= total) break;
+
+        // frame of work item w: last b with offsets[b] <= w
+        int lo = 0, hi = A.B;
+        while (hi - lo > 1) {
+            int m = (lo + hi) >> 1;
+            if (A.offsets[m] <= w) lo = m; else hi = m;
+        }
+        const int b = lo, slot = w - A.offsets[b];
+        surf_keypoint *kpp = A.kps + (size_t)b * A.cap + slot;
+        const float cx = kpp->x, cy = kpp->y, size = kpp->size;
+        const uint8_t *img = A.img.ptr + (size_t)b * A.img.frame_stride;
+        const int *S = reinterpret_cast<const int *>(A.sum) + (size_t)b * A.geo.sum_frame;
+
+        const float s = size * 1.2f / 9.0f;
+        const int g = 2 * __float2int_rn(2 * s);
+        bool dead = (H + 1 < g) || (W + 1 < g);
+
+        float dir = 360.f - 90.f;
+        if (!dead && !A.upright) {
+            // ---- orientation samples (one per thread), compacted in sample order ----
+            bool valid = false;
+            float X = 0, Y = 0;
+            if (tid < kOriSamples) {
+                const float hg = (float)(g - 1) / 2;
+                const int x = __float2int_rn(cx + c_ori_x[tid] * s - hg);
+                const int y = __float2int_rn(cy + c_ori_y[tid] * s - hg);
+                if (!(y < 0 || y >= (H + 1) - g || x < 0 || x >= (W + 1) - g)) {
+                    valid = true;
+                    const int h = g / 2;
+                    const int *o = S + (size_t)y * SP + x;
+                    const int p00 = __ldg(o), p0h = __ldg(o + h), p0g = __ldg(o + g);
+                    const int *oh = o + (size_t)h * SP, *og = o + (size_t)g * SP;
+                    const int ph0 = __ldg(oh), phg = __ldg(oh + g);
+                    const int pg0 = __ldg(og), pgh = __ldg(og + h), pgg = __ldg(og + g);
+                    const float wa = 1 / ((float)h * g);
+                    const float wn = -1 / ((float)h * g);
+                    // x gradient: right half minus left half; y gradient: top half minus bottom half
+                    const int left = p00 + pgh - pg0 - p0h, right = p0h + pgg - pgh - p0g;
+                    const int top = p00 + phg - ph0 - p0g, bottom = ph0 + pgg - pg0 - phg;
+                    const float vx = (float)((double)((float)left * wn) + (double)((float)right * wa));
+                    const float vy = (float)((double)((float)top * wa) + (double)((float)bottom * wn));
+                    X = vx * c_ori_w[tid];
+                    Y = vy * c_ori_w[tid];
+                }
+            }
+            const unsigned bal = __ballot_sync(FULL_MASK, valid);
+            if (lane == 0) s_warp_cnt[warp] = __popc(bal);
+            __syncthreads();
+            int base = 0;
+            for (int k = 0; k < warp; k++) base += s_warp_cnt[k];
+            const int na = s_warp_cnt[0] + s_warp_cnt[1] + s_warp_cnt[2] + s_warp_cnt[3];
+            if (valid) {
+                const int pos = base + __popc(bal & ((1u << lane) - 1));
+                s_X[pos] = X;
+                s_Y[pos] = Y;
+                s_iang[pos] = __float2int_rn(fast_atan2_deg(Y, X));
+            }
+            __syncthreads();
+            if (na == 0) {
+                dead = true;
+            } else {
+                // ---- 72 sliding 60-degree windows, fp32 sums in sample order ----
+                if (tid < kOriWindows) {
+                    const int ang0 = tid * 5;
+                    float sx = 0, sy = 0;
+                    for (int k = 0; k < na; k++) {
+                        const int d = abs(s_iang[k] - ang0);
+                        if (d < 30 || d > 330) {
+                            sx += s_X[k];
+                            sy += s_Y[k];
+                        }
+                    }
+                    s_wx[tid] = sx;
+                    s_wy[tid] = sy;
+                }
+                __syncthreads();
+                if (tid == 0) {
+                    float bx = 0, by = 0, best = 0;
+                    for (int k = 0; k < kOriWindows; k++) {
+                        const float mod = s_wx[k] * s_wx[k] + s_wy[k] * s_wy[k];
+                        if (mod > best) {
+                            best = mod;
+                            bx = s_wx[k];
+                            by = s_wy[k];
+                        }
+                    }
+                    s_dir = fast_atan2_deg(-by, bx);
+                }
+                __syncthreads();
+                dir = s_dir;
+            }
+        }
+
+        const int n = (int)(21 * s);
+        const bool want_desc = (A.desc != nullptr) || (A.patches != nullptr);
+        if (!dead && want_desc && (n < kPatch || n > kMaxWindow)) {
+            // n < 21: up-scaling INTER_AREA is outside the restated path (oracle deletes it too);
+            // n > kMaxWindow: unsupported window, reported through the status word.
+            if (n > kMaxWindow && tid == 0) atomicOr(A.status, 1);
+            dead = true;
+        }
+        if (dead) {
+            if (tid == 0) {
+                kpp->size = -1.f;
+                const int pos = atomicAdd(A.ndeleted + b, 1);
+                A.deleted_slots[(size_t)b * A.cap + pos] = slot;
+            }
+            continue;
+        }
+        if (tid == 0) kpp->angle = dir;
+        if (!want_desc) continue;
+
+        // ---- window geometry ----
+        WindowGeo wg;
+        wg.img = img;
+        wg.pitch = (int)A.img.pitch;
+        wg.W = W;
+        wg.H = H;
+        wg.upright = A.upright;
+        wg.rsx = s_rsx;
+        wg.rsy = s_rsy;
+        const float off = -(float)(n - 1) / 2;
+        if (A.upright) {
+            wg.x0 = __float2int_rn(cx + off);
+            wg.y0 = __float2int_rn(cy - off);
+            wg.sd = 1.f;
+            wg.cd = 0.f;
+        } else {
+            const float th = dir * (float)(3.1415926535897932384626433832795 / 180);
+            wg.sd = -(float)sin((double)th);
+            wg.cd = (float)cos((double)th);
+            wg.x0 = wg.y0 = 0;
+            if (tid == 0) {
+                // row starts advance by sequential fp32 additions
+                float sx0 = cx + off * wg.cd + off * wg.sd;
+                float sy0 = cy - off * wg.sd + off * wg.cd;
+                for (int i = 0; i < n; i++) {
+                    s_rsx[i] = sx0;
+                    s_rsy[i] = sy0;
+                    sx0 += wg.sd;
+                    sy0 += wg.cd;
+                }
+            }
+        }
+        // ---- INTER_AREA table for this window size (threads 32..52) ----
+        const double inv = (double)kPatch / n;
+        const double scale = 1. / inv;
+        const int isc = __double2int_rn(scale);
+        const bool int_scale = fabs(scale - isc) < DBL_EPSILON;
+        if (!int_scale && tid >= 32 && tid < 32 + kPatch) {
+            const int d = tid - 32;
+            const double f1 = d * scale, f2 = f1 + scale;
+            const double cell = fmin(scale, n - f1);
+            int s1 = __double2int_ru(f1), s2 = __double2int_rd(f2);
+            s2 = min(s2, n - 1);
+            s1 = min(s1, s2);
+            const bool hf = (s1 - f1) > 1e-3, hl = (f2 - s2) > 1e-3;
+            s_tab.start[d] = hf ? s1 - 1 : s1;
+            s_tab.count[d] = (hf ? 1 : 0) + (s2 - s1) + (hl ? 1 : 0);
+            s_tab.has_first[d] = hf;
+            s_tab.has_last[d] = hl;
+            s_tab.a_first[d] = (float)((s1 - f1) / cell);
+            s_tab.a_mid[d] = (float)(1.0 / cell);
+            s_tab.a_last[d] = (float)(fmin(fmin(f2 - s2, 1.), cell) / cell);
+        }
+        __syncthreads();
+
+        // ---- window pixels: staged in shared memory when they fit ----
+        const bool staged = n <= kWinSmemSide;
+        if (staged) {
+            for (int idx = tid; idx < n * n; idx += kDescThreads) {
+                const int i = idx / n, j = idx - i * n;
+                s_win[idx] = (unsigned char)window_pixel(wg, i, j);
+            }
+            __syncthreads();
+        }
+        auto WIN = [&](int i, int j) -> int { return staged ? (int)s_win[i * n + j] : window_pixel(wg, i, j); };
+
+        // ---- resize to 21 x 21 (INTER_AREA), one destination pixel per thread ----
+        for (int p = tid; p < kPatchPx; p += kDescThreads) {
+            const int dy = p / kPatch, dx = p - dy * kPatch;
+            int outv;
+            if (int_scale && isc == 2) {
+                outv = (WIN(2 * dy, 2 * dx) + WIN(2 * dy, 2 * dx + 1) + WIN(2 * dy + 1, 2 * dx) +
+                        WIN(2 * dy + 1, 2 * dx + 1) + 2) >> 2;
+            } else if (int_scale) {
+                int acc = 0;
+                for (int v = 0; v < isc; v++)
+                    for (int u = 0; u < isc; u++) acc += WIN(dy * isc + v, dx * isc + u);
+                const float wgt = 1.f / (isc * isc);
+                outv = sat_u8(acc * wgt);
+            } else {
+                const int ys = s_tab.start[dy], yc = s_tab.count[dy];
+                const int xs = s_tab.start[dx], xc = s_tab.count[dx];
+                float acc = 0;
+                for (int e = 0; e < yc; e++) {
+                    const float beta = area_alpha(s_tab, dy, e);
+                    float buf = 0;
+                    for (int f = 0; f < xc; f++) buf += WIN(ys + e, xs + f) * area_alpha(s_tab, dx, f);
+                    if (e == 0) acc = beta * buf; else acc += beta * buf;
+                }
+                outv = sat_u8(acc);
+            }
+            s_patch[p] = (unsigned char)outv;
+        }
+        __syncthreads();
+        if (A.patches) {
+            unsigned char *po = A.patches + ((size_t)b * A.cap + slot) * kPatchPx;
+            for (int p = tid; p < kPatchPx; p += kDescThreads) po[p] = s_patch[p];
+        }
+        if (!A.desc) continue;
+
+        // ---- 2x2 Haar gradients of the patch, Gaussian weighted ----
+        for (int t = tid; t < 400; t += kDescThreads) {
+            const int i = t / 20, j = t - i * 20;
+            const unsigned char *r0 = s_patch + i * kPatch + j, *r1 = r0 + kPatch;
+            const float wgt = c_desc_w[t];
+            s_dx[t] = (r0[1] - r0[0] + r1[1] - r1[0]) * wgt;
+            s_dy[t] = (r1[0] - r0[0] + r1[1] - r0[1]) * wgt;
+        }
+        __syncthreads();
+        // ---- 4 x 4 sub-regions, one output component per thread, sequential fp32 sums ----
+        const int nb = A.extended ? 8 : 4;
+        for (int t = tid; t < D; t += kDescThreads) {
+            const int region = t / nb, comp = t - region * nb;
+            const int I = region >> 2, J = region & 3;
+            float acc = 0;
+            for (int y = I * 5; y < I * 5 + 5; y++)
+                for (int x = J * 5; x < J * 5 + 5; x++) {
+                    const float tx = s_dx[y * 20 + x], ty = s_dy[y * 20 + x];
+                    if (A.extended) {
+                        switch (comp) {
+                            case 0: if (ty >= 0) acc += tx; break;
+                            case 1: if (ty >= 0) acc += fabsf(tx); break;
+                            case 2: if (!(ty >= 0)) acc += tx; break;
+                            case 3: if (!(ty >= 0)) acc += fabsf(tx); break;
+                            case 4: if (tx >= 0) acc += ty; break;
+                            case 5: if (tx >= 0) acc += fabsf(ty); break;
+                            case 6: if (!(tx >= 0)) acc += ty; break;
+                            default: if (!(tx >= 0)) acc += fabsf(ty); break;
+                        }
+                    } else {
+                        switch (comp) {
+                            case 0: acc += tx; break;
+                            case 1: acc += ty; break;
+                            case 2: acc += fabsf(tx); break;
+                            default: acc += fabsf(ty); break;
+                        }
+                    }
+                }
+            s_vec[t] = acc;
+        }
+        __syncthreads();
+        if (warp == 0) {
+            double mag = 0;
+            for (int t = lane; t < D; t += 32) mag += (double)(s_vec[t] * s_vec[t]);
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) mag += __shfl_xor_sync(FULL_MASK, mag, d);
+            if (lane == 0) s_scale = (float)(1. / (sqrt(mag) + DBL_EPSILON));
+        }
+        __syncthreads();
+        float *vo = A.desc + ((size_t)b * A.cap + slot) * D;
+        for (int t = tid; t < D; t += kDescThreads) vo[t] = s_vec[t] * s_scale;
+    }
+}
+
+void launch_describe(const DescribeArgs &a, cudaStream_t st, int *launches)
+{
+    static int grids[64] = {};
+    const size_t smem = (size_t)kWinSmemSide * kWinSmemSide;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    int &grid = grids[dev & 63];
+    if (!grid) {
+        int sms = 148, per_sm = 4;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaFuncSetAttribute(k_describe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_describe, kDescThreads, smem);
+        if (per_sm < 1) per_sm = 1;
+        grid = sms * per_sm;  // persistent CTAs: a multiple of the SM count
+    }
+    k_describe<<<grid, kDescThreads, smem, st>>>(a);
+    *launches += 1;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K6: stable removal of deleted keypoints and packing of all frames into contiguous outputs.
+// A surviving keypoint at slot e moves to e - #(deleted slots < e); deletions are rare, so the
+// per-frame deleted-slot list is short (usually empty).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_pack(const surf_keypoint *__restrict__ kps, const float *__restrict__ desc,
+                                              int D, int cap, const int *__restrict__ in_offsets,
+                                              const int *__restrict__ ndel, const int *__restrict__ deleted_slots,
+                                              const int *__restrict__ out_offsets, surf_keypoint *__restrict__ out_kps,
+                                              float *__restrict__ out_desc)
+{
+    __shared__ int s_pos[128];
+    const int b = blockIdx.y;
+    const int n = in_offsets[b + 1] - in_offsets[b];
+    const int e0 = blockIdx.x * 128;
+    if (e0 >= n) return;
+    const int e = e0 + threadIdx.x;
+    int pos = -1;
+    if (e < n) {
+        const surf_keypoint kp = kps[(size_t)b * cap + e];
+        if (kp.size > 0) {
+            int before = 0;
+            const int nd = ndel[b];
+            const int *dl = deleted_slots + (size_t)b * cap;
+            for (int k = 0; k < nd; k++) before += (dl[k] < e);
+            pos = out_offsets[b] + e - before;
+            out_kps[pos] = kp;
+        }
+    }
+    s_pos[threadIdx.x] = pos;
+    __syncthreads();
+    if (!desc) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int D4 = D / 4;
+    for (int r = warp; r < 128; r += 4) {
+        const int p = s_pos[r];
+        if (p < 0) continue;
+        const float4 *src = reinterpret_cast<const float4 *>(desc + ((size_t)b * cap + e0 + r) * D);
+        float4 *dst = reinterpret_cast<float4 *>(out_desc + (size_t)p * D);
+        for (int k = lane; k < D4; k += 32) dst[k] = src[k];
+    }
+}
+
+void launch_pack(const surf_keypoint *kps, const float *desc, int D, int cap, int B, const int *in_offsets,
+                 const int *ndel, const int *deleted_slots, const int *out_offsets, surf_keypoint *out_kps,
+                 float *out_desc, cudaStream_t st, int *launches)
+{
+    dim3 grid((cap + 127) / 128, B);
+    k_pack<<<grid, 128, 0, st>>>(kps, desc, D, cap, in_offsets, ndel, deleted_slots, out_offsets, out_kps, out_desc);
+    *launches += 1;
+}
+
+}  // namespace surfb200

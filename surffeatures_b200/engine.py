@@ -1,0 +1,395 @@
+"""Host-side mirror of the OpenCV interface the reference calls, over the C ABI of libsurf_b200.so.
+
+`SURF` mirrors cv::SURF / cv2.Feature2D (detect, compute, detectAndCompute, descriptorSize, the five
+public fields) as used at SurfFeatures/Logic/vtkSlicerSurfFeaturesLogic.cxx:1384-1389; `BFMatcher`
+mirrors DescriptorMatcher::knnMatch as used at :640 (and clear/add at :1402-1403).
+
+Everything here is plumbing: every numerical step runs in the CUDA library.  There is no CPU path --
+if the library or an sm_100 device is missing, construction raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional, Sequence
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsurf_b200.so")
+
+KEYPOINT_DTYPE = np.dtype(
+    [("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"), ("response", "<f4"),
+     ("octave", "<i4"), ("class_id", "<i4")]
+)  # cv::KeyPoint, 28 B
+DMATCH_DTYPE = np.dtype([("queryIdx", "<i4"), ("trainIdx", "<i4"), ("imgIdx", "<i4"), ("distance", "<f4")])  # cv::DMatch
+
+SURF_OK = 0
+ERR_NAMES = {-1: "BAD_ARG", -2: "UNSUPPORTED", -3: "CAPACITY", -4: "CUDA", -5: "NO_DEVICE", -6: "NCCL"}
+MEM_HOST, MEM_DEVICE = 0, 1
+
+# every symbol include/surf_b200.h declares
+ABI_SYMBOLS = [
+    "surf_create", "surf_destroy", "surf_set_params", "surf_get_params", "surf_last_error", "surf_required_capacity",
+    "surf_descriptor_size", "surf_get_timings", "surf_stream", "surf_detect", "surf_compute", "surf_detect_and_compute",
+    "surf_detect_and_compute_batch", "surf_submit_batch", "surf_collect_batch", "surf_device_results", "surf_sync",
+    "surf_integral", "surf_hessian_layer", "surf_raw_keypoints", "surf_describe_keypoints", "surf_match_knn",
+    "surf_match_ratio", "surf_merge_topk", "surf_version",
+]
+
+
+class SurfError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"surf_b200 error {ERR_NAMES.get(code, code)}: {msg}")
+        self.code = code
+
+
+class Params(C.Structure):
+    _fields_ = [("hessian_threshold", C.c_double), ("n_octaves", C.c_int32), ("n_octave_layers", C.c_int32),
+                ("extended", C.c_int32), ("upright", C.c_int32)]
+
+
+class Timings(C.Structure):
+    _fields_ = [(n, C.c_float) for n in ("h2d", "integral", "hessian", "nms", "sort", "describe", "pack", "d2h", "total")]
+    _fields_ += [("launches", C.c_int32)]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+_lib = None
+
+
+def load_library():
+    """Loads libsurf_b200.so; raises if it has not been built (no fallback of any kind)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise SurfError(-5, f"{LIB_PATH} is missing: run `python -m surffeatures_b200.build` (there is no CPU path)")
+    L = C.CDLL(LIB_PATH)
+    vp, i32, sz, lng = C.c_void_p, C.c_int, C.c_size_t, C.c_long
+    pp = C.POINTER(Params)
+    L.surf_create.argtypes = [pp, i32, i32, i32, i32, i32, C.POINTER(vp)]
+    L.surf_destroy.argtypes = [vp]
+    L.surf_destroy.restype = None
+    L.surf_set_params.argtypes = [vp, pp]
+    L.surf_get_params.argtypes = [vp, pp]
+    L.surf_last_error.argtypes = [vp]
+    L.surf_last_error.restype = C.c_char_p
+    L.surf_required_capacity.argtypes = [vp]
+    L.surf_required_capacity.restype = lng
+    L.surf_descriptor_size.argtypes = [vp]
+    L.surf_get_timings.argtypes = [vp, C.POINTER(Timings)]
+    L.surf_stream.argtypes = [vp]
+    L.surf_stream.restype = vp
+    L.surf_detect.argtypes = [vp, vp, i32, i32, sz, vp, sz, vp, i32, C.POINTER(i32)]
+    L.surf_compute.argtypes = [vp, vp, i32, i32, sz, vp, i32, vp, C.POINTER(i32)]
+    L.surf_detect_and_compute.argtypes = [vp, vp, i32, i32, sz, vp, sz, vp, vp, i32, C.POINTER(i32)]
+    L.surf_detect_and_compute_batch.argtypes = [vp, vp, i32, i32, i32, i32, sz, sz, vp, sz, vp, vp, i32, lng, vp]
+    L.surf_submit_batch.argtypes = [vp, vp, i32, i32, i32, i32, sz, sz, vp, sz, i32]
+    L.surf_collect_batch.argtypes = [vp, vp, vp, i32, lng, vp]
+    L.surf_device_results.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
+    L.surf_sync.argtypes = [vp]
+    L.surf_integral.argtypes = [vp, vp, i32, i32, sz, i32, vp]
+    L.surf_hessian_layer.argtypes = [vp, vp, i32, i32, sz, i32, i32, vp, C.POINTER(i32), C.POINTER(i32)]
+    L.surf_raw_keypoints.argtypes = [vp, vp, i32, i32, sz, vp, sz, vp, i32, C.POINTER(i32)]
+    L.surf_describe_keypoints.argtypes = [vp, vp, i32, i32, sz, vp, i32, vp, vp]
+    L.surf_match_knn.argtypes = [vp, vp, i32, vp, i32, i32, i32, vp, i32]
+    L.surf_match_ratio.argtypes = [vp, vp, i32, vp, i32, i32, C.c_float, vp, vp, i32]
+    L.surf_merge_topk.argtypes = [vp, vp, i32, i32, i32, vp]
+    L.surf_version.argtypes = []
+    L.surf_version.restype = C.c_char_p
+    for name in ABI_SYMBOLS:
+        getattr(L, name)  # raises AttributeError if the library does not export a declared symbol
+    _lib = L
+    return L
+
+
+def _u8(a, what="image"):
+    a = np.asarray(a)
+    if a.dtype != np.uint8 or a.ndim != 2:
+        raise SurfError(-1, f"{what} must be a 2-D uint8 array (single channel, depth 8U)")
+    if a.strides[1] != 1:
+        a = np.ascontiguousarray(a)
+    return a
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data
+
+
+class SURF:
+    """cv::SURF(hessianThreshold, nOctaves=4, nOctaveLayers=2, extended=true, upright=false).
+
+    Defaults follow the modern xfeatures2d::SURF::create(100, 4, 3, False, False), which are also the
+    BASELINE config-1 values; pass the reference's (minHessian, 4, 2, ...) explicitly to mirror
+    vtkSlicerSurfFeaturesLogic.cxx:1384.
+    """
+
+    def __init__(self, hessianThreshold: float = 100.0, nOctaves: int = 4, nOctaveLayers: int = 3,
+                 extended: bool = False, upright: bool = False, *, device: int = 0, max_width: int = 1024,
+                 max_height: int = 1024, max_batch: int = 1, max_keypoints: int = 32768):
+        self._lib = load_library()
+        self._h = C.c_void_p()
+        self._p = Params(float(hessianThreshold), int(nOctaves), int(nOctaveLayers), int(bool(extended)),
+                         int(bool(upright)))
+        self.device, self.max_width, self.max_height = device, max_width, max_height
+        self.max_batch, self.max_keypoints = max_batch, max_keypoints
+        rc = self._lib.surf_create(C.byref(self._p), device, max_width, max_height, max_batch, max_keypoints,
+                                   C.byref(self._h))
+        if rc != SURF_OK:
+            self._h = C.c_void_p()
+            raise SurfError(rc, "surf_create failed (an sm_100 GPU is required; there is no CPU fallback)")
+
+    # ---- lifetime ----
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self._lib.surf_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != SURF_OK:
+            raise SurfError(rc, self._lib.surf_last_error(self._h).decode())
+
+    # ---- the five public fields of cv::SURF ----
+    def _set(self, **kw):
+        p = Params(self._p.hessian_threshold, self._p.n_octaves, self._p.n_octave_layers, self._p.extended, self._p.upright)
+        for k, v in kw.items():
+            setattr(p, k, v)
+        self._check(self._lib.surf_set_params(self._h, C.byref(p)))
+        self._p = p
+
+    hessianThreshold = property(lambda s: s._p.hessian_threshold, lambda s, v: s._set(hessian_threshold=float(v)))
+    nOctaves = property(lambda s: s._p.n_octaves, lambda s, v: s._set(n_octaves=int(v)))
+    nOctaveLayers = property(lambda s: s._p.n_octave_layers, lambda s, v: s._set(n_octave_layers=int(v)))
+    extended = property(lambda s: bool(s._p.extended), lambda s, v: s._set(extended=int(bool(v))))
+    upright = property(lambda s: bool(s._p.upright), lambda s, v: s._set(upright=int(bool(v))))
+
+    def descriptorSize(self) -> int:
+        return int(self._lib.surf_descriptor_size(self._h))
+
+    def descriptorType(self) -> int:
+        return 5  # CV_32F
+
+    def timings(self) -> dict:
+        t = Timings()
+        self._check(self._lib.surf_get_timings(self._h, C.byref(t)))
+        return t.as_dict()
+
+    def required_capacity(self) -> int:
+        return int(self._lib.surf_required_capacity(self._h))
+
+    @property
+    def handle(self):
+        return self._h
+
+    @property
+    def cuda_stream(self) -> int:
+        return int(self._lib.surf_stream(self._h) or 0)
+
+    # ---- cv::Feature2D ----
+    def detect(self, image, mask=None) -> np.ndarray:
+        """FeatureDetector::detect: oriented, sorted keypoints as a KEYPOINT_DTYPE array."""
+        kps, _ = self._dac(image, mask, want_desc=False)
+        return kps
+
+    def detectAndCompute(self, image, mask=None):
+        """SURF::operator()(img, mask, keypoints, descriptors): (keypoints, N x D float32)."""
+        return self._dac(image, mask, want_desc=True)
+
+    def _dac(self, image, mask, want_desc):
+        image = np.asarray(image)
+        D = self.descriptorSize()
+        if image.size == 0:
+            return np.zeros(0, KEYPOINT_DTYPE), (np.zeros((0, D), np.float32) if want_desc else None)
+        img = _u8(image)
+        m = None if mask is None else _u8(mask, "mask")
+        if m is not None and m.shape != img.shape:
+            raise SurfError(-1, "mask must have the image's size")
+        cap = self.max_keypoints
+        kps = np.zeros(cap, KEYPOINT_DTYPE)
+        desc = np.zeros((cap, D), np.float32) if want_desc else None
+        n = C.c_int(0)
+        H, W = img.shape
+        rc = self._lib.surf_detect_and_compute(self._h, _ptr(img), W, H, img.strides[0], _ptr(m),
+                                               0 if m is None else m.strides[0], _ptr(kps), _ptr(desc), cap, C.byref(n))
+        self._check(rc)
+        return kps[:n.value].copy(), (desc[:n.value].copy() if want_desc else None)
+
+    def compute(self, image, keypoints):
+        """DescriptorExtractor::compute: returns (surviving keypoints, descriptors)."""
+        D = self.descriptorSize()
+        kps = np.array(keypoints, dtype=KEYPOINT_DTYPE, copy=True).ravel()
+        image = np.asarray(image)
+        if image.size == 0 or len(kps) == 0:
+            return np.zeros(0, KEYPOINT_DTYPE), np.zeros((0, D), np.float32)
+        img = _u8(image)
+        H, W = img.shape
+        desc = np.zeros((len(kps), D), np.float32)
+        n = C.c_int(0)
+        self._check(self._lib.surf_compute(self._h, _ptr(img), W, H, img.strides[0], _ptr(kps), len(kps), _ptr(desc),
+                                           C.byref(n)))
+        return kps[:n.value].copy(), desc[:n.value].copy()
+
+    # ---- batches (the frame loop of computeNext, vtkSlicerSurfFeaturesLogic.cxx:1392-1406) ----
+    def detectAndComputeBatch(self, images, mask=None, want_descriptors=True, capacity: Optional[int] = None):
+        """images: (B, H, W) uint8.  Returns a list of (keypoints, descriptors) per frame."""
+        kps, desc, off = self.detectAndComputeBatchPacked(images, mask, want_descriptors, capacity)
+        return [(kps[off[b]:off[b + 1]], None if desc is None else desc[off[b]:off[b + 1]]) for b in range(len(off) - 1)]
+
+    def detectAndComputeBatchPacked(self, images, mask=None, want_descriptors=True, capacity: Optional[int] = None):
+        images = np.ascontiguousarray(images, dtype=np.uint8)
+        if images.ndim != 3:
+            raise SurfError(-1, "images must be (B, H, W) uint8")
+        B, H, W = images.shape
+        m = None if mask is None else _u8(mask, "mask")
+        D = self.descriptorSize()
+        cap = int(capacity) if capacity else B * self.max_keypoints
+        kps = np.zeros(cap, KEYPOINT_DTYPE)
+        desc = np.zeros((cap, D), np.float32) if want_descriptors else None
+        off = np.zeros(B + 1, np.int32)
+        rc = self._lib.surf_detect_and_compute_batch(self._h, _ptr(images), MEM_HOST, B, W, H, W, W * H, _ptr(m),
+                                                     0 if m is None else m.strides[0], _ptr(kps), _ptr(desc), MEM_HOST,
+                                                     cap, _ptr(off))
+        self._check(rc)
+        n = int(off[B])
+        return kps[:n], (None if desc is None else desc[:n]), off
+
+    # ---- raw pointer batch API (device- or pinned-memory buffers owned by the caller) ----
+    def submit(self, images_ptr: int, in_mem: int, B: int, W: int, H: int, pitch: int, frame_stride: int,
+               want_descriptors: bool = True, mask_ptr: int = 0, mask_pitch: int = 0):
+        self._check(self._lib.surf_submit_batch(self._h, images_ptr, in_mem, B, W, H, pitch, frame_stride,
+                                                mask_ptr or None, mask_pitch, int(want_descriptors)))
+
+    def collect(self, kps_ptr: int, desc_ptr: int, out_mem: int, capacity: int, offsets: np.ndarray):
+        self._check(self._lib.surf_collect_batch(self._h, kps_ptr or None, desc_ptr or None, out_mem, capacity,
+                                                 _ptr(offsets)))
+
+    def device_results(self):
+        k, d, o = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        self._check(self._lib.surf_device_results(self._h, C.byref(k), C.byref(d), C.byref(o)))
+        return k.value or 0, d.value or 0, o.value or 0
+
+    def sync(self):
+        self._check(self._lib.surf_sync(self._h))
+
+    # ---- stage-level exports (parity of the per-stage tolerances) ----
+    def integral(self, image, clamp01=False) -> np.ndarray:
+        img = _u8(image)
+        H, W = img.shape
+        out = np.empty((H + 1, W + 1), np.int32)
+        self._check(self._lib.surf_integral(self._h, _ptr(img), W, H, img.strides[0], int(clamp01), _ptr(out)))
+        return out
+
+    def hessian_layer(self, image, octave: int, layer: int) -> np.ndarray:
+        img = _u8(image)
+        H, W = img.shape
+        out = np.empty((H >> octave, W >> octave), np.float32)
+        r, c = C.c_int(0), C.c_int(0)
+        self._check(self._lib.surf_hessian_layer(self._h, _ptr(img), W, H, img.strides[0], octave, layer, _ptr(out),
+                                                 C.byref(r), C.byref(c)))
+        assert (r.value, c.value) == out.shape
+        return out
+
+    def raw_keypoints(self, image, mask=None) -> np.ndarray:
+        img = _u8(image)
+        m = None if mask is None else _u8(mask, "mask")
+        H, W = img.shape
+        kps = np.zeros(self.max_keypoints, KEYPOINT_DTYPE)
+        n = C.c_int(0)
+        self._check(self._lib.surf_raw_keypoints(self._h, _ptr(img), W, H, img.strides[0], _ptr(m),
+                                                 0 if m is None else m.strides[0], _ptr(kps), len(kps), C.byref(n)))
+        return kps[:n.value].copy()
+
+    def describe_keypoints(self, image, keypoints, want_desc=True, want_patches=False):
+        """Orientation (+descriptor, +21x21 patch) of given keypoints, deleted ones kept with size=-1."""
+        img = _u8(image)
+        H, W = img.shape
+        kps = np.array(keypoints, dtype=KEYPOINT_DTYPE, copy=True).ravel()
+        D = self.descriptorSize()
+        desc = np.zeros((len(kps), D), np.float32) if want_desc else None
+        patches = np.zeros((len(kps), 21, 21), np.uint8) if want_patches else None
+        self._check(self._lib.surf_describe_keypoints(self._h, _ptr(img), W, H, img.strides[0], _ptr(kps), len(kps),
+                                                      _ptr(desc), _ptr(patches)))
+        return kps, desc, patches
+
+    # ---- stage 5 on this engine's stream ----
+    def match_knn(self, query, train, k=2) -> np.ndarray:
+        q = np.ascontiguousarray(query, np.float32)
+        t = np.ascontiguousarray(train, np.float32)
+        if q.ndim != 2 or t.ndim != 2 or (len(t) and q.shape[1] != t.shape[1]):
+            raise SurfError(-1, "query/train must be N x D float32 with equal D")
+        out = np.zeros((q.shape[0], k), DMATCH_DTYPE)
+        self._check(self._lib.surf_match_knn(self._h, _ptr(q), q.shape[0], _ptr(t), t.shape[0], q.shape[1], k, _ptr(out),
+                                             MEM_HOST))
+        return out
+
+    def match_ratio(self, query, train, ratio=0.8):
+        q = np.ascontiguousarray(query, np.float32)
+        t = np.ascontiguousarray(train, np.float32)
+        out = np.zeros((q.shape[0], 2), DMATCH_DTYPE)
+        good = np.zeros(q.shape[0], np.uint8)
+        self._check(self._lib.surf_match_ratio(self._h, _ptr(q), q.shape[0], _ptr(t), t.shape[0], q.shape[1],
+                                               float(ratio), _ptr(out), _ptr(good), MEM_HOST))
+        return out, good.astype(bool)
+
+    def match_ratio_device(self, q_ptr: int, nq: int, t_ptr: int, nt: int, dim: int, ratio: float, out_ptr: int,
+                           good_ptr: int):
+        self._check(self._lib.surf_match_ratio(self._h, q_ptr, nq, t_ptr, nt, dim, float(ratio), out_ptr, good_ptr,
+                                               MEM_DEVICE))
+
+    def merge_topk_device(self, in_ptr: int, n_ranks: int, nq: int, k: int, out_ptr: int):
+        self._check(self._lib.surf_merge_topk(self._h, in_ptr, n_ranks, nq, k, out_ptr))
+
+
+class BFMatcher:
+    """cv::BFMatcher(NORM_L2): add / clear / knnMatch with DMatch records (imgIdx bookkeeping as
+    DescriptorMatcher::add(vector<Mat>) does; vtkSlicerSurfFeaturesLogic.cxx:1402-1403, :640)."""
+
+    def __init__(self, engine: Optional[SURF] = None, **engine_kw):
+        self._engine = engine or SURF(**engine_kw)
+        self._train: list[np.ndarray] = []
+
+    def add(self, descriptors: Sequence[np.ndarray]):
+        for d in descriptors:
+            self._train.append(np.ascontiguousarray(d, np.float32))
+
+    def clear(self):
+        self._train = []
+
+    def getTrainDescriptors(self):
+        return list(self._train)
+
+    def knnMatch(self, queryDescriptors, trainDescriptors=None, k=2) -> np.ndarray:
+        """Returns an (Nq, k) DMATCH_DTYPE array, ascending distance, ties -> lower trainIdx."""
+        if trainDescriptors is not None:
+            return self._engine.match_knn(queryDescriptors, trainDescriptors, k)
+        if not self._train:
+            return np.zeros((len(queryDescriptors), 0), DMATCH_DTYPE)
+        sizes = np.array([len(t) for t in self._train])
+        starts = np.concatenate([[0], np.cumsum(sizes)])
+        m = self._engine.match_knn(queryDescriptors, np.concatenate(self._train, axis=0), k)
+        # map the concatenated row index back to (imgIdx, trainIdx within that image)
+        valid = m["trainIdx"] >= 0
+        img = np.searchsorted(starts, m["trainIdx"], side="right") - 1
+        m["imgIdx"] = np.where(valid, img, -1)
+        m["trainIdx"] = np.where(valid, m["trainIdx"] - starts[np.clip(img, 0, len(sizes) - 1)], -1)
+        return m
+
+    def ratioMatch(self, queryDescriptors, trainDescriptors, ratio=0.8):
+        return self._engine.match_ratio(queryDescriptors, trainDescriptors, ratio)
+
+
+def to_cv2_keypoints(kps: np.ndarray):
+    """KEYPOINT_DTYPE array -> tuple of cv2.KeyPoint (needs cv2; a consumer-side convenience only)."""
+    import cv2
+
+    return tuple(cv2.KeyPoint(float(k["x"]), float(k["y"]), float(k["size"]), float(k["angle"]), float(k["response"]),
+                              int(k["octave"]), int(k["class_id"])) for k in kps)

@@ -1,0 +1,343 @@
+"""GPU parity: the CUDA path, called through the C ABI, against the CPU oracle on the same inputs.
+
+Tolerances are BASELINE.json's: integral bit-exact; Hessian responses within 1e-5 relative; >= 99 % of
+keypoints paired within 0.5 px and 2 % scale; descriptors within 1e-4 L2.  Most stages are in fact
+checked for exact equality, because the kernels reproduce the reference's operation order.
+"""
+import numpy as np
+import pytest
+
+from surffeatures_b200 import speckle
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from surffeatures_b200 import SURF
+
+    e = SURF(100, 4, 3, False, False, max_width=1024, max_height=1024, max_batch=8, max_keypoints=32768)
+    yield e
+    e.close()
+
+
+def _pair_stats(a, b):
+    """Fraction of keypoints of `b` (oracle) with a partner in `a` within 0.5 px and 2 % scale."""
+    if len(b) == 0:
+        return 1.0 if len(a) == 0 else 0.0
+    if len(a) == 0:
+        return 0.0
+    ok = 0
+    ax, ay, asz = a["x"], a["y"], a["size"]
+    for k in b:
+        d2 = (ax - k["x"]) ** 2 + (ay - k["y"]) ** 2
+        near = (d2 <= 0.25) & (np.abs(asz - k["size"]) <= 0.02 * k["size"])
+        ok += bool(near.any())
+    return ok / len(b)
+
+
+# ---------------------------------------------------------------- stage 1
+@pytest.mark.parametrize("shape", [(480, 640), (17, 33), (1, 1), (479, 641), (1024, 1024), (100, 4), (33, 129)])
+def test_integral_bit_exact(eng, oracle, shape):
+    rng = np.random.default_rng(shape[0] * 7919 + shape[1])
+    img = rng.integers(0, 256, shape, dtype=np.uint8)
+    assert np.array_equal(eng.integral(img), oracle.integral(img))
+
+
+def test_integral_saturated_and_mask(eng, oracle):
+    img = np.full((1024, 1024), 255, np.uint8)
+    got = eng.integral(img)
+    assert got[-1, -1] == 255 * 1024 * 1024
+    assert np.array_equal(got, oracle.integral(img))
+    m = np.random.default_rng(3).integers(0, 3, (480, 640), dtype=np.uint8) * 100
+    assert np.array_equal(eng.integral(m, clamp01=True), oracle.integral(m, clamp01=True))
+
+
+def test_integral_strided_input(eng, oracle):
+    big = np.random.default_rng(5).integers(0, 256, (300, 700), dtype=np.uint8)
+    view = big[10:250, 3:643]  # pitch 700, unaligned start
+    assert np.array_equal(eng.integral(view), oracle.integral(np.ascontiguousarray(view)))
+
+
+# ---------------------------------------------------------------- stage 2
+def test_hessian_layers(eng, oracle, frame640):
+    S = oracle.integral(frame640)
+    worst = 0.0
+    exact = total = 0
+    for o in range(4):
+        for l in range(5):
+            size, step = (9 + 6 * l) << o, 1 << o
+            want, _, _ = oracle.hessian_layer(S, size, step)
+            got = eng.hessian_layer(frame640, o, l)
+            assert got.shape == want.shape
+            scale = np.maximum(np.abs(want), 1.0)
+            worst = max(worst, float((np.abs(got - want) / scale).max()))
+            exact += int((got == want).sum())
+            total += want.size
+    assert worst <= 1e-5, worst
+    assert exact == total, f"{total - exact} of {total} Hessian samples not bit-identical"
+
+
+def test_hessian_skips_oversize_layers(eng, oracle):
+    img = speckle.speckle_frame(240, 320, 11)
+    S = oracle.integral(img)
+    want, _, ok = oracle.hessian_layer(S, 264, 8)
+    assert not ok
+    got = eng.hessian_layer(img, 3, 4)
+    assert np.array_equal(got, want) and not got.any()
+
+
+# ---------------------------------------------------------------- stage 3
+@pytest.mark.parametrize("thr,layers", [(100, 3), (400, 2), (1000, 3)])
+def test_raw_keypoints_identical(eng, oracle, frame640, thr, layers):
+    eng.hessianThreshold, eng.nOctaveLayers = thr, layers
+    try:
+        got = eng.raw_keypoints(frame640)
+    finally:
+        eng.hessianThreshold, eng.nOctaveLayers = 100, 3
+    want = oracle.raw_keypoints(frame640, oracle.params(thr, 4, layers))
+    assert len(got) == len(want) > 500
+    for f in ("x", "y", "size", "response", "octave", "class_id", "angle"):
+        assert np.array_equal(got[f], want[f]), f
+
+
+def test_raw_keypoints_blobs_all_octaves(eng, oracle):
+    img = speckle.speckle_frame(480, 640, 21, blobs=8)
+    got = eng.raw_keypoints(img)
+    want = oracle.raw_keypoints(img, oracle.params(100, 4, 3))
+    assert set(np.unique(want["octave"])) >= {0, 1, 2}
+    assert got.tobytes() == want.tobytes()
+
+
+def test_mask_semantics(eng, oracle, frame640):
+    mask = np.zeros_like(frame640)
+    mask[100:400, 150:500] = 255
+    got = eng.raw_keypoints(frame640, mask)
+    want = oracle.raw_keypoints(frame640, oracle.params(100, 4, 3), mask=mask)
+    assert 0 < len(want) < len(oracle.raw_keypoints(frame640, oracle.params(100, 4, 3)))
+    assert got.tobytes() == want.tobytes()
+
+
+# ---------------------------------------------------------------- stage 4
+def test_orientation_patches_descriptors_given_keypoints(eng, oracle, frame640):
+    p = oracle.params(100, 4, 3)
+    raw = oracle.raw_keypoints(frame640, p)
+    okp, odesc, opatch = oracle.describe(frame640, p, raw, want_patches=True)
+    gkp, gdesc, gpatch = eng.describe_keypoints(frame640, raw, want_patches=True)
+    assert np.array_equal(gkp["size"], okp["size"])
+    live = okp["size"] > 0
+    assert np.array_equal(gkp["angle"][live], okp["angle"][live])
+    same_patch = (gpatch[live] == opatch[live]).all(axis=(1, 2))
+    assert same_patch.mean() >= 0.999, f"{(~same_patch).sum()} patches differ"
+    err = np.linalg.norm(gdesc[live] - odesc[live], axis=1)
+    assert err.max() <= 1e-4, float(err.max())
+    assert (err == 0).mean() >= 0.99
+
+
+def test_big_keypoints_unstaged_window_path(eng, oracle):
+    img = speckle.speckle_frame(480, 640, 21, blobs=8)
+    p = oracle.params(100, 4, 3)
+    raw = oracle.raw_keypoints(img, p)
+    big = raw[raw["size"] > 56]  # window side > 128: computed on demand, not staged
+    assert len(big) > 0
+    okp, odesc, opatch = oracle.describe(img, p, big, want_patches=True)
+    gkp, gdesc, gpatch = eng.describe_keypoints(img, big, want_patches=True)
+    assert np.array_equal(gkp["angle"], okp["angle"])
+    assert np.array_equal(gpatch, opatch)
+    assert np.abs(gdesc - odesc).max() <= 1e-6
+
+
+@pytest.mark.parametrize("extended,upright", [(False, False), (True, False), (False, True), (True, True)])
+def test_detect_and_compute_variants(oracle, frame640, extended, upright):
+    from surffeatures_b200 import SURF
+
+    e = SURF(100, 4, 3, extended, upright, max_width=640, max_height=480, max_keypoints=16384)
+    try:
+        kps, desc = e.detectAndCompute(frame640)
+    finally:
+        e.close()
+    okps, odesc = oracle.detect_and_compute(frame640, oracle.params(100, 4, 3, extended, upright))
+    assert desc.shape == odesc.shape == (len(okps), 128 if extended else 64)
+    assert _pair_stats(kps, okps) >= 0.99
+    assert np.array_equal(kps["x"], okps["x"]) and np.array_equal(kps["y"], okps["y"])
+    assert np.array_equal(kps["angle"], okps["angle"])
+    err = np.linalg.norm(desc - odesc, axis=1)
+    assert err.max() <= 1e-4, float(err.max())
+    assert np.allclose(np.linalg.norm(desc, axis=1), 1.0, atol=1e-5)
+
+
+def test_reference_call_sequence_detect_then_compute(oracle, frame640):
+    """The reference's own sequence (vtkSlicerSurfFeaturesLogic.cxx:1384-1389): detect with
+    (minHessian, 4, 2) and a mask, then compute with a default-constructed extractor."""
+    from surffeatures_b200 import SURF
+
+    mask = np.zeros_like(frame640)
+    mask[40:440, 60:600] = 1
+    det = SURF(400, 4, 2, max_width=640, max_height=480)
+    ext = SURF(100, 4, 2, extended=True, max_width=640, max_height=480)
+    try:
+        kps = det.detect(frame640, mask)
+        kps2, desc = ext.compute(frame640, kps)
+    finally:
+        det.close()
+        ext.close()
+    okps = oracle.detect(frame640, oracle.params(400, 4, 2), mask=mask)
+    okps2, odesc = oracle.compute(frame640, oracle.params(100, 4, 2, True, False), okps)
+    assert kps.tobytes() == okps.tobytes()
+    assert kps2.tobytes() == okps2.tobytes()
+    assert np.linalg.norm(desc - odesc, axis=1).max() <= 1e-4
+
+
+def test_batch_equals_single_and_is_ordered(eng, oracle):
+    frames = speckle.speckle_stream(5, 240, 320, seed=1)
+    res = eng.detectAndComputeBatch(frames)
+    assert len(res) == 5
+    for b in range(5):
+        k1, d1 = eng.detectAndCompute(frames[b])
+        assert res[b][0].tobytes() == k1.tobytes()
+        assert np.array_equal(res[b][1], d1)
+    ok, od = oracle.detect_and_compute(frames[3], oracle.params(100, 4, 3))
+    assert np.array_equal(res[3][0]["x"], ok["x"])
+    assert np.linalg.norm(res[3][1] - od, axis=1).max() <= 1e-4
+
+
+def test_full_size_1024_extended_upright(oracle):
+    """BASELINE config 3 shape (1024x1024, 128-d, upright) on one frame against the oracle."""
+    from surffeatures_b200 import SURF
+
+    img = speckle.speckle_frame(1024, 1024, 100)
+    e = SURF(100, 4, 3, True, True, max_width=1024, max_height=1024, max_keypoints=32768)
+    try:
+        kps, desc = e.detectAndCompute(img)
+    finally:
+        e.close()
+    okps, odesc = oracle.detect_and_compute(img, oracle.params(100, 4, 3, True, True))
+    assert len(kps) == len(okps) > 10000
+    assert _pair_stats(kps[:2000], okps[:2000]) >= 0.99
+    assert (kps["angle"] == 270.0).all()
+    assert np.linalg.norm(desc - odesc, axis=1).max() <= 1e-4
+
+
+# ---------------------------------------------------------------- edge cases
+def test_edge_cases(eng, oracle):
+    from surffeatures_b200 import SurfError
+
+    # empty image -> empty outputs, not an error
+    k, d = eng.detectAndCompute(np.zeros((0, 0), np.uint8))
+    assert len(k) == 0 and d.shape == (0, 64)
+    # flat image -> no keypoints
+    k, d = eng.detectAndCompute(np.full((64, 64), 128, np.uint8))
+    assert len(k) == 0 and d.shape == (0, 64)
+    # image smaller than the smallest filter
+    k, d = eng.detectAndCompute(np.random.default_rng(0).integers(0, 255, (8, 8), dtype=np.uint8))
+    assert len(k) == 0
+    # compute with no keypoints
+    k, d = eng.compute(np.zeros((32, 32), np.uint8), np.zeros(0, k.dtype))
+    assert len(k) == 0 and d.shape == (0, 64)
+    # frame larger than the workspace is refused
+    with pytest.raises(SurfError):
+        eng.detectAndCompute(np.zeros((2000, 2000), np.uint8))
+    # multi-channel / wrong depth is refused
+    with pytest.raises(SurfError):
+        eng.detectAndCompute(np.zeros((32, 32, 3), np.uint8))
+
+
+def test_small_image_keypoints_near_border(eng, oracle):
+    img = speckle.speckle_frame(72, 96, 5, blobs=3)
+    p = oracle.params(50, 4, 3)
+    eng.hessianThreshold = 50
+    try:
+        k, d = eng.detectAndCompute(img)
+    finally:
+        eng.hessianThreshold = 100
+    ok, od = oracle.detect_and_compute(img, p)
+    assert k.tobytes() == ok.tobytes()
+    if len(ok):
+        assert np.linalg.norm(d - od, axis=1).max() <= 1e-4
+
+
+def test_provided_keypoints_deletion_and_filter(eng, oracle, frame640):
+    p = oracle.params(100, 4, 3)
+    kps = oracle.raw_keypoints(frame640, p)[:50].copy()
+    kps["size"][3] = 0.0        # dropped by runByKeypointSize
+    kps["size"][7] = 4000.0     # Haar wavelet larger than the image: deleted by the invoker
+    kps["x"][9], kps["y"][9] = -500.0, -500.0  # no orientation sample in bounds: deleted
+    gk, gd = eng.compute(frame640, kps)
+    ok, od = oracle.compute(frame640, p, kps)
+    assert len(gk) == len(ok) == 47
+    assert gk.tobytes() == ok.tobytes()
+    assert np.linalg.norm(gd - od, axis=1).max() <= 1e-4
+
+
+def test_capacity_overflow_is_reported(frame640):
+    from surffeatures_b200 import SURF, SurfError
+
+    e = SURF(100, 4, 3, max_width=640, max_height=480, max_keypoints=128)
+    try:
+        with pytest.raises(SurfError) as ei:
+            e.detectAndCompute(frame640)
+        assert ei.value.code == -3 and e.required_capacity() > 128
+    finally:
+        e.close()
+
+
+# ---------------------------------------------------------------- stage 5
+@pytest.mark.parametrize("nq,nt,dim,k", [(300, 400, 64, 2), (1000, 4243, 64, 3), (257, 129, 128, 2), (5, 3, 64, 4),
+                                         (64, 1, 64, 1)])
+def test_knn_match_equals_oracle(eng, oracle, nq, nt, dim, k):
+    rng = np.random.default_rng(nq + nt)
+    t = np.abs(rng.standard_normal((nt, dim))).astype(np.float32)
+    t /= np.linalg.norm(t, axis=1, keepdims=True)
+    q = t[rng.integers(0, nt, nq)] + 0.05 * rng.standard_normal((nq, dim)).astype(np.float32)
+    q /= np.linalg.norm(q, axis=1, keepdims=True)
+    got = eng.match_knn(q, t, k)
+    want = oracle.knn_match(q, t, k)
+    assert np.array_equal(got["trainIdx"], want["trainIdx"])
+    assert np.array_equal(got["queryIdx"], want["queryIdx"])
+    fin = want["trainIdx"] >= 0
+    assert np.allclose(got["distance"][fin], want["distance"][fin], rtol=2e-6, atol=1e-7)
+    assert (got["trainIdx"][~fin] == -1).all()
+
+
+def test_knn_match_ties_go_to_lower_index(eng):
+    rng = np.random.default_rng(9)
+    t = rng.standard_normal((200, 64)).astype(np.float32)
+    t[150] = t[20]
+    t[77] = t[20]
+    q = t[[20, 20, 5]].copy()
+    m = eng.match_knn(q, t, 3)
+    assert list(m["trainIdx"][0]) == [20, 77, 150]
+    assert list(m["trainIdx"][2][:1]) == [5]
+
+
+def test_frame_to_frame_ratio_match(eng, oracle):
+    """BASELINE config 2 step: descriptors of frame t matched to frame t-1, ratio test 0.8."""
+    frames = speckle.speckle_stream(2, 480, 640, seed=1)
+    (k0, d0), (k1, d1) = eng.detectAndComputeBatch(frames)
+    m, good = eng.match_ratio(d1, d0, 0.8)
+    om = oracle.knn_match(d1, d0, 2)
+    assert np.array_equal(m["trainIdx"], om["trainIdx"])
+    ogood = om["distance"][:, 0] < np.float32(0.8) * om["distance"][:, 1]
+    assert (good == ogood).mean() >= 0.999
+    # matched keypoints move by about the stream's (0.7, 0.3) px shift
+    dx = k1["x"][good] - k0["x"][m["trainIdx"][good, 0]]
+    assert good.sum() > 500 and abs(np.median(dx) + 0.7) < 0.2
+
+
+def test_bfmatcher_add_imgidx(eng, oracle):
+    from surffeatures_b200 import BFMatcher
+
+    rng = np.random.default_rng(4)
+    mats = [rng.standard_normal((n, 64)).astype(np.float32) for n in (30, 50, 20)]
+    q = rng.standard_normal((40, 64)).astype(np.float32)
+    bf = BFMatcher(eng)
+    bf.add(mats)
+    m = bf.knnMatch(q, k=3)
+    allt = np.concatenate(mats)
+    om = oracle.knn_match(q, allt, 3)
+    starts = np.array([0, 30, 80])
+    img = np.searchsorted(starts, om["trainIdx"], side="right") - 1
+    assert np.array_equal(m["imgIdx"], img)
+    assert np.array_equal(m["trainIdx"], om["trainIdx"] - starts[img])
+    bf.clear()
+    assert bf.knnMatch(q, k=3).shape == (40, 0)
