@@ -1,0 +1,370 @@
+#!/usr/bin/env python
+"""bench.py -- SURF detect+describe frames/sec @640x480 (BASELINE.json metric), config 2:
+a stream of 640x480 speckle frames, detect + describe every frame and BF L2 ratio-match it to the
+previous frame.  One step = one batch of BATCH consecutive frames of the stream.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+value   : whole-job frames/s with the frames already resident in HBM (device pointers in/out)
+e2e     : the same through the host-buffer API (pinned host frames -> H2D, packed keypoints,
+          descriptors and matches -> D2H inside the timed region)
+roofline: dominant kernel's algorithmic bytes / its CUDA-event time, against MEASURED_PEAKS.json
+cpu_baseline: the CPU oracle (restatement of OpenCV 2.4.5 SURF + BFMatcher) on the box's host cores
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+W_, H_ = 640, 480
+PARAMS = dict(hessianThreshold=100.0, nOctaves=4, nOctaveLayers=3, extended=False, upright=False)
+RATIO = 0.8
+CAP = 8192          # raw keypoints per frame the workspace holds
+POOL_BATCHES = 4    # distinct batches cycled through; the per-step working set (integral + det pyramid of 64 frames, ~600 MB) exceeds the 126 MB L2
+
+
+def _metric():
+    return "SURF detect+describe frames/sec @640x480 (1/2/4/8 GPU); HBM GB/s vs peak"
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured"
+    return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.rows, self.proc, self.idx = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_stream(n_frames: int, seed: int) -> np.ndarray:
+    from surffeatures_b200 import speckle
+
+    return speckle.speckle_stream(n_frames, H_, W_, seed=seed)
+
+
+def algorithmic_bytes_per_frame(n_kp: float, D: int = 64, L: int = 3, O: int = 4):
+    """B1..B4 per 640x480 frame."""
+    A = 4 * (W_ + 1) * (H_ + 1)
+    P = sum((H_ >> o) * (W_ >> o) for o in range(O))
+    b1 = W_ * H_ + A
+    b2 = O * A + 4 * (L + 2) * P
+    b3 = 4 * (L + 2) * P + 28 * n_kp
+    b4 = W_ * H_ + A + n_kp * (28 + 4 + 4 * D)
+    return {"integral": b1, "hessian": b2, "nms": b3, "describe": b4, "total": b1 + b2 + b3 + b4}
+
+
+# ------------------------------------------------------------------------------------------------
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path.  Genuine OpenCV 2.4.5
+    nonfree cannot be built offline, so this times the oracle port (all host threads, frame-parallel),
+    each step a bounded sample of the same stream."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    from oracle import surf_oracle as so
+
+    threads = so.max_threads()
+    sample = max(threads, 8)
+    frames = make_stream(sample + 1, seed=1)
+    p = so.params(**PARAMS)
+
+    def step():
+        res = so.detect_and_compute_batch(frames[1:], p, cap=CAP, n_threads=threads)
+        prev = so.detect_and_compute(frames[0], p)[1]
+        for _, d in res:
+            so.knn_match(d, prev, 2, n_threads=threads)
+            prev = d
+        return sum(len(k) for k, _ in res)
+
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    nk = 0
+    for _ in range(args.steps):
+        nk += step()
+    dt = time.perf_counter() - t0
+    fps = sample * args.steps / dt
+    line = {
+        "impl": "reference", "metric": _metric(), "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u8/int32/f32", "data": "synthetic",
+        "config": {"workload": "config2: 640x480 speckle stream, detect+describe (thr=100, 4 octaves, 3 layers, 64-d) "
+                               "+ BF L2 k=2 ratio match to previous frame", "frames_per_step": sample},
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port",
+                         "sample": f"{sample} frames/step x {args.steps} steps, oracle port of OpenCV 2.4.5 SURF "
+                                   f"(genuine nonfree not installable offline)"},
+        "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "keypoints_per_frame": nk / (sample * args.steps),
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from surffeatures_b200 import DMATCH_DTYPE, KEYPOINT_DTYPE, MEM_DEVICE, MEM_HOST, SURF
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the engine has no CPU path")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    B = args.batch
+    D = 64
+
+    # ---- synthetic stream: each rank owns its own contiguous shard of the sweep (weak scaling) ----
+    pool = make_stream(POOL_BATCHES * B, seed=1 + rank)
+    h_pool = torch.from_numpy(pool).pin_memory()
+    d_pool = h_pool.to(dev)
+
+    eng = SURF(**PARAMS, device=local, max_width=W_, max_height=H_, max_batch=B, max_keypoints=CAP)
+    stream = torch.cuda.ExternalStream(eng.cuda_stream, device=dev)
+    cap_total = B * CAP
+    d_matches = torch.empty((CAP * 2, 4), dtype=torch.int32, device=dev)
+    d_good = torch.empty((CAP,), dtype=torch.uint8, device=dev)
+    d_prev = torch.zeros((CAP, D), dtype=torch.float32, device=dev)
+    offsets = np.zeros(B + 1, np.int32)
+    launches = [0]
+    kp_seen = [0]
+
+    import ctypes
+    try:
+        cudart = ctypes.CDLL("libcudart.so.12")
+    except OSError:
+        cudart = ctypes.CDLL("/usr/local/cuda/lib64/libcudart.so")
+    cudart.cudaMemcpyAsync.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_void_p]
+
+    def match_stream_device(desc_ptr, n_prev):
+        """Frame t against frame t-1, device-resident; returns the new n_prev."""
+        for b in range(B):
+            nq = int(offsets[b + 1] - offsets[b])
+            qp = desc_ptr + int(offsets[b]) * D * 4
+            if nq and n_prev:
+                eng.match_ratio_device(qp, nq, tp[0], n_prev, D, RATIO, d_matches.data_ptr(), d_good.data_ptr())
+                launches[0] += 3
+            tp[0], n_prev = qp, nq
+        # keep the last frame's descriptors for the next batch (the packed buffer is overwritten)
+        if n_prev:
+            cudart.cudaMemcpyAsync(ctypes.c_void_p(d_prev.data_ptr()), ctypes.c_void_p(tp[0]), n_prev * D * 4, 3,
+                                   ctypes.c_void_p(eng.cuda_stream))
+            tp[0] = d_prev.data_ptr()
+        return n_prev
+
+    tp = [d_prev.data_ptr()]
+
+    def step_device(i, n_prev):
+        src = d_pool[(i % POOL_BATCHES) * B:(i % POOL_BATCHES + 1) * B]
+        eng.submit(src.data_ptr(), MEM_DEVICE, B, W_, H_, W_, W_ * H_, True)
+        eng.collect(0, 0, MEM_DEVICE, cap_total, offsets)   # waits for the counts; copies nothing
+        launches[0] += eng.timings()["launches"]
+        kp_seen[0] += int(offsets[B])
+        _, dptr, _ = eng.device_results()
+        return match_stream_device(dptr, n_prev)
+
+    # host-buffer API: pinned frames in, packed keypoints/descriptors/matches out
+    h_kps = torch.empty((cap_total, 7), dtype=torch.float32).pin_memory()
+    h_desc = torch.empty((cap_total, D), dtype=torch.float32).pin_memory()
+    h_matches = torch.empty((cap_total * 2, 4), dtype=torch.int32).pin_memory()
+    d_matches_all = torch.empty((cap_total * 2, 4), dtype=torch.int32, device=dev)
+    d_good_all = torch.empty((cap_total,), dtype=torch.uint8, device=dev)
+    bytes_io = {"h2d": 0, "d2h": 0}
+
+    def step_e2e(i, n_prev):
+        src = h_pool[(i % POOL_BATCHES) * B:(i % POOL_BATCHES + 1) * B]
+        eng.submit(src.data_ptr(), MEM_HOST, B, W_, H_, W_, W_ * H_, True)
+        eng.collect(h_kps.data_ptr(), h_desc.data_ptr(), MEM_HOST, cap_total, offsets)
+        n = int(offsets[B])
+        _, dptr, _ = eng.device_results()
+        for b in range(B):
+            nq = int(offsets[b + 1] - offsets[b])
+            qp = dptr + int(offsets[b]) * D * 4
+            if nq and n_prev:
+                eng.match_ratio_device(qp, nq, tp[0], n_prev, D, RATIO,
+                                       d_matches_all.data_ptr() + int(offsets[b]) * 2 * 16,
+                                       d_good_all.data_ptr() + int(offsets[b]))
+            tp[0], n_prev = qp, nq
+        if n_prev:
+            cudart.cudaMemcpyAsync(ctypes.c_void_p(d_prev.data_ptr()), ctypes.c_void_p(tp[0]), n_prev * D * 4, 3,
+                                   ctypes.c_void_p(eng.cuda_stream))
+            tp[0] = d_prev.data_ptr()
+        with torch.cuda.stream(stream):
+            h_matches[:2 * n].copy_(d_matches_all[:2 * n], non_blocking=True)
+        stream.synchronize()
+        bytes_io["h2d"] = B * W_ * H_
+        bytes_io["d2h"] = n * (28 + 4 * D) + 2 * n * 16 + (B + 1) * 4
+        return n_prev
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(step_fn, steps, warmup, sample_clocks=False):
+        n_prev = 0
+        tp[0] = d_prev.data_ptr()
+        for i in range(warmup):
+            n_prev = step_fn(i, n_prev)
+        sampler = ClockSampler(local) if sample_clocks else None
+        barrier()
+        if sampler:
+            sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        launches[0] = 0
+        kp_seen[0] = 0
+        stage = {k: 0.0 for k in ("integral", "hessian", "sort", "describe", "pack")}
+        e0.record(stream)
+        for i in range(steps):
+            n_prev = step_fn(warmup + i, n_prev)
+            t = eng.timings()
+            for k in stage:
+                stage[k] += t[k]
+        e1.record(stream)
+        barrier()
+        ms = e0.elapsed_time(e1)
+        clocks = sampler.stop() if sampler else None
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, {k: v / steps for k, v in stage.items()}, clocks
+
+    steps, warmup = args.steps, max(args.warmup, 3)
+    ms_dev, stage_ms, clocks = timed(step_device, steps, warmup, sample_clocks=True)
+    n_launch = launches[0]
+    kp_per_frame = kp_seen[0] / (steps * B)
+    ms_e2e, _, _ = timed(step_e2e, steps, warmup)
+
+    fps = world * B * steps / (ms_dev * 1e-3)
+    fps_e2e = world * B * steps / (ms_e2e * 1e-3)
+
+    # ---- roofline of the dominant kernel (by measured stage time) ----
+    peak, how = _peaks()
+    alg = algorithmic_bytes_per_frame(kp_per_frame, D)
+    stage_key = {"integral": "integral", "hessian": "hessian", "describe": "describe"}
+    dom = max(stage_key, key=lambda k: stage_ms[k])
+    dom_bytes = (alg["hessian"] + alg["nms"] if dom == "hessian" else alg[dom]) * B
+    achieved = dom_bytes / (stage_ms[dom] * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": {"integral": "k_band_integral", "hessian": "k_hessian+k_nms",
+                                           "describe": "k_describe"}[dom],
+                "achieved": achieved, "peak": peak, "peak_source": how + " (MEASURED_PEAKS.json hbm_gbs)",
+                "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "algorithmic_bytes_per_launch": dom_bytes, "ms_per_launch": stage_ms[dom],
+                "stage_ms_per_step": stage_ms,
+                "whole_path_frac": alg["total"] * B * steps / (ms_dev * 1e-3) / 1e9 / peak}
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        from oracle import surf_oracle as so
+
+        threads = so.max_threads()
+        ns = max(threads, 8)
+        p = so.params(**PARAMS)
+        so.detect_and_compute(pool[0], p)
+        t0 = time.perf_counter()
+        res = so.detect_and_compute_batch(pool[:ns], p, cap=CAP, n_threads=threads)
+        for a, b_ in zip(res[1:], res[:-1]):
+            so.knn_match(a[1], b_[1], 2, n_threads=threads)
+        dt = time.perf_counter() - t0
+        cpu_baseline = {"value": ns / dt, "unit": "frames/s", "cores": threads, "kind": "port",
+                        "sample": f"{ns} frames of the same stream, detect+describe+match, oracle port of OpenCV 2.4.5 "
+                                  f"SURF (genuine nonfree not installable offline), {threads} threads frame-parallel"}
+
+    if rank == 0:
+        line = {
+            "metric": _metric(), "value": fps, "unit": "frames/s", "n_gpus": world, "steps": steps, "warmup": warmup,
+            "ms_per_step": ms_dev / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u8/int32/f32", "data": "synthetic",
+            "config": {"workload": "config2: 640x480 speckle stream, detect+describe (thr=100, 4 octaves, 3 layers, "
+                                   "64-d) + BF L2 k=2 ratio(0.8) match to previous frame",
+                       "frames_per_step": B, "frames_per_step_all_gpus": B * world,
+                       "l2": f"inputs cycle through {POOL_BATCHES} batches (no L2 flush needed): per-step working set "
+                             f"(integral+det pyramid, {B} frames) > 126 MB L2",
+                       "sharding": "frames sharded by rank, no data-path collective"},
+            "e2e": {"value": fps_e2e, "unit": "frames/s", "h2d_bytes_per_step": bytes_io["h2d"],
+                    "d2h_bytes_per_step": bytes_io["d2h"], "ms_per_step": ms_e2e / steps},
+            "gpu_launches": n_launch, "keypoints_per_frame": kp_per_frame,
+            "roofline": roofline, "cpu_baseline": cpu_baseline, "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    # the engine's stream is wrapped by a torch ExternalStream: leave both to process teardown
+    sys.stdout.flush()
+    os._exit(0)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=64)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -71,7 +71,7 @@ def speckle_frame(h: int, w: int, seed: int, blobs: int = 0) -> np.ndarray:
     return _quantise(_psf(z))
 
 
-def speckle_stream(n: int, h: int, w: int, seed: int, shift=(0.7, 0.3), fresh: float = 0.1) -> np.ndarray:
+def speckle_stream(n: int, h: int, w: int, seed: int, shift=(0.7, 0.3), fresh: float = 0.02) -> np.ndarray:
     """n correlated frames: one scatterer field translated by shift*t px plus `fresh` new field."""
     rng = np.random.default_rng(seed)
     pad_x = int(np.ceil(abs(shift[0]) * n)) + 2

@@ -312,7 +312,7 @@ def test_knn_match_ties_go_to_lower_index(eng):
 
 def test_frame_to_frame_ratio_match(eng, oracle):
     """BASELINE config 2 step: descriptors of frame t matched to frame t-1, ratio test 0.8."""
-    frames = speckle.speckle_stream(2, 480, 640, seed=1)
+    frames = speckle.speckle_stream(2, 480, 640, seed=1, fresh=0.0)
     (k0, d0), (k1, d1) = eng.detectAndComputeBatch(frames)
     m, good = eng.match_ratio(d1, d0, 0.8)
     om = oracle.knn_match(d1, d0, 2)
