@@ -341,3 +341,45 @@ def test_bfmatcher_add_imgidx(eng, oracle):
     assert np.array_equal(m["trainIdx"], om["trainIdx"] - starts[img])
     bf.clear()
     assert bf.knnMatch(q, k=3).shape == (40, 0)
+
+
+# ---------------------------------------------------------------- committed golden fixtures
+def test_gpu_reproduces_golden_vectors():
+    import json
+    import os
+
+    from surffeatures_b200 import SURF
+
+    gdir = os.path.join(os.path.dirname(__file__), "golden")
+    meta = json.load(open(os.path.join(gdir, "golden.json")))
+    z = np.load(os.path.join(gdir, "golden_surf.npz"))
+    for name, spec in meta["frames"].items():
+        if spec["kind"] == "frame":
+            img = speckle.speckle_frame(spec["h"], spec["w"], spec["seed"], blobs=spec.get("blobs", 0))
+        else:
+            img = speckle.speckle_stream(spec["n"], spec["h"], spec["w"], seed=spec["seed"])[spec["index"]]
+        assert speckle.sha256(img) == spec["sha256"]
+        e = SURF(**spec["params"], max_width=spec["w"], max_height=spec["h"], max_keypoints=4096)
+        try:
+            k, d = e.detectAndCompute(img)
+            assert int(e.integral(img).astype(np.int64).sum()) == spec["integral_checksum"]
+        finally:
+            e.close()
+        gk, gd = z[name + "_kp"], z[name + "_desc"]
+        assert len(k) == len(gk) == spec["n_keypoints"], name
+        for f in ("x", "y", "size", "angle", "response", "octave", "class_id"):
+            assert np.array_equal(k[f], gk[f]), (name, f)
+        assert np.linalg.norm(d - gd, axis=1).max() <= 1e-4, name
+
+
+def test_config1_frame_counts_match_golden(eng):
+    import json
+    import os
+
+    meta = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "golden.json")))["config1"]
+    img = speckle.speckle_frame(480, 640, 0)
+    assert speckle.sha256(img) == meta["sha256"]
+    k, d = eng.detectAndCompute(img)
+    assert len(k) == meta["n_keypoints"]
+    assert np.bincount(k["octave"], minlength=4).tolist() == meta["octave_hist"]
+    assert abs(float(d.astype(np.float64).sum()) - meta["desc_checksum"]) < 1e-2
