@@ -17,6 +17,7 @@ COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-I", os.path
 # (source, extra flags).  Stages 1-4 reproduce the reference's un-contracted fp32 arithmetic.
 UNITS = [
     ("surf_kernels.cu", ["-fmad=false"]),
+    ("surf_describe.cu", ["-fmad=false"]),
     ("surf_match.cu", []),
     ("surf_engine.cu", []),
 ]

@@ -1,0 +1,646 @@
+// surf_describe.cu -- stage 4 of the SURF path (SURFInvoker in OpenCV 2.4.5 nonfree/surf.cpp; SURVEY.md A4,
+// A5; rows a7/a8), reached from SurfFeatures/Logic/vtkSlicerSurfFeaturesLogic.cxx:1384-1389.
+//
+//   k_orient      one warp per keypoint: 113 Haar samples from the integral image, 72 sliding 60-degree
+//                 windows, dominant angle; classifies the keypoint by descriptor-window size and appends
+//                 it to that class's work list.
+//   k_descriptor  one CTA per keypoint, persistent CTAs on an atomic queue per size class.  The rotated
+//                 n x n window's bounding box in the 8-bit image is staged in shared memory, every window
+//                 pixel is a bilinear tap rounded to uchar, the window is reduced to 21 x 21 with
+//                 INTER_AREA, then 2x2 Haar gradients, 4x4 sub-region sums, L2 normalisation.
+//
+// Compiled with -fmad=false: every fp32 expression rounds as in the SSE-only reference build.
+#include <cuda_pipeline.h>
+
+#include <cfloat>
+#include <cmath>
+
+#include "surf_internal.h"
+
+namespace surfb200 {
+
+#define FULL_MASK 0xffffffffu
+
+// ------------------------------------------------------------------------------------------------
+// constant tables (fixed by the algorithm, not by engine parameters)
+// ------------------------------------------------------------------------------------------------
+__constant__ signed char c_ori_x[kOriSamples];
+__constant__ signed char c_ori_y[kOriSamples];
+__constant__ float c_ori_w[kOriSamples];
+__constant__ float c_desc_w[400];
+
+static void gaussian_taps(int n, double sigma, float *out)
+{
+    // getGaussianKernel(n, sigma, CV_32F) as OpenCV 2.4.5 builds it.
+    double s2 = -0.5 / (sigma * sigma), acc = 0;
+    for (int i = 0; i < n; i++) {
+        double x = i - (n - 1) * 0.5;
+        out[i] = (float)std::exp(s2 * x * x);
+        acc += out[i];
+    }
+    acc = 1. / acc;
+    for (int i = 0; i < n; i++) out[i] = (float)(out[i] * acc);
+}
+
+void upload_tables()
+{
+    signed char px[kOriSamples], py[kOriSamples];
+    float pw[kOriSamples], dw[400], g[13], gd[20];
+    gaussian_taps(13, 2.5, g);
+    int n = 0;
+    for (int i = -6; i <= 6; i++)
+        for (int j = -6; j <= 6; j++)
+            if (i * i + j * j <= 36) {
+                px[n] = (signed char)i;  // the outer loop variable is the x offset
+                py[n] = (signed char)j;
+                pw[n++] = g[i + 6] * g[j + 6];
+            }
+    gaussian_taps(20, 3.3, gd);
+    for (int i = 0; i < 20; i++)
+        for (int j = 0; j < 20; j++) dw[i * 20 + j] = gd[i] * gd[j];
+    cudaMemcpyToSymbol(c_ori_x, px, sizeof(px));
+    cudaMemcpyToSymbol(c_ori_y, py, sizeof(py));
+    cudaMemcpyToSymbol(c_ori_w, pw, sizeof(pw));
+    cudaMemcpyToSymbol(c_desc_w, dw, sizeof(dw));
+}
+
+__device__ __forceinline__ float fast_atan2_deg(float y, float x)
+{
+    // fastAtan2 (core/mathfuncs.cpp): 7th-order odd polynomial, degrees in [0, 360].
+    const float k = (float)(180 / 3.1415926535897932384626433832795);
+    const float p1 = 0.9997878412794807f * k, p3 = -0.3258083974640975f * k;
+    const float p5 = 0.1555786518463281f * k, p7 = -0.04432655554792128f * k;
+    const float ax = fabsf(x), ay = fabsf(y);
+    float a, c, c2;
+    if (ax >= ay) {
+        c = ay / (ax + (float)DBL_EPSILON);
+        c2 = c * c;
+        a = (((p7 * c2 + p5) * c2 + p3) * c2 + p1) * c;
+    } else {
+        c = ax / (ay + (float)DBL_EPSILON);
+        c2 = c * c;
+        a = 90.f - (((p7 * c2 + p5) * c2 + p3) * c2 + p1) * c;
+    }
+    if (x < 0) a = 180.f - a;
+    if (y < 0) a = 360.f - a;
+    return a;
+}
+
+// uchar -> float without a conversion instruction: 2^23 + v is exact, minus 2^23 gives v.
+__device__ __forceinline__ float u8f(unsigned v) { return __uint_as_float(0x4B000000u | v) - 8388608.0f; }
+
+// cvRound of a float in [0, 2^22) -> low byte: adding 1.5 * 2^23 rounds to nearest-even at integer
+// granularity in one fp32 addition.
+__device__ __forceinline__ unsigned round_u8(float v) { return __float_as_uint(v + 12582912.0f) & 0xffu; }
+
+__device__ __forceinline__ int sat_u8(float v)
+{
+    int r = __float2int_rn(v);
+    return r < 0 ? 0 : (r > 255 ? 255 : r);
+}
+
+__device__ __forceinline__ void find_frame(const int *offsets, int B, int w, int &b, int &slot)
+{
+    int lo = 0, hi = B;
+    while (hi - lo > 1) {
+        int m = (lo + hi) >> 1;
+        if (offsets[m] <= w) lo = m; else hi = m;
+    }
+    b = lo;
+    slot = w - offsets[lo];
+}
+
+// ------------------------------------------------------------------------------------------------
+// K4a: orientation.  One warp per keypoint.
+// ------------------------------------------------------------------------------------------------
+constexpr int kOriWarps = 8;
+
+struct __align__(16) OriSample {
+    int iang;    // cvRound(fastAtan2(Y, X))
+    float X, Y;  // Gaussian-weighted Haar responses
+    int pad;
+};
+
+__global__ void __launch_bounds__(kOriWarps * 32) k_orient(const __grid_constant__ DescribeArgs A)
+{
+    __shared__ OriSample s_smp[kOriWarps][kOriSamples + 3];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int W = A.geo.W, H = A.geo.H, SP = A.geo.SP;
+    const int total = A.offsets[A.B];
+    const bool want_desc = (A.desc != nullptr) || (A.patches != nullptr);
+    OriSample *smp = s_smp[warp];
+
+    for (int w = blockIdx.x * kOriWarps + warp; w < total; w += gridDim.x * kOriWarps) {
+        int b, slot;
+        find_frame(A.offsets, A.B, w, b, slot);
+        surf_keypoint *kpp = A.kps + (size_t)b * A.cap + slot;
+        const float cx = kpp->x, cy = kpp->y, size = kpp->size;
+        const int *S = reinterpret_cast<const int *>(A.sum) + (size_t)b * A.geo.sum_frame;
+
+        const float s = size * 1.2f / 9.0f;
+        const int g = 2 * __float2int_rn(2 * s);
+        bool dead = (H + 1 < g) || (W + 1 < g);
+        float dir = 360.f - 90.f;
+
+        if (!dead && !A.upright) {
+            // ---- 113 samples, 4 rounds of 32, compacted in sample order ----
+            int na = 0;
+            const float hg = (float)(g - 1) / 2;
+            const int h = g / 2;
+            const float wa = 1 / ((float)h * g), wn = -1 / ((float)h * g);
+            for (int r = 0; r < 4; r++) {
+                const int k = r * 32 + lane;
+                bool valid = false;
+                float X = 0, Y = 0;
+                if (k < kOriSamples) {
+                    const int x = __float2int_rn(cx + c_ori_x[k] * s - hg);
+                    const int y = __float2int_rn(cy + c_ori_y[k] * s - hg);
+                    if (!(y < 0 || y >= (H + 1) - g || x < 0 || x >= (W + 1) - g)) {
+                        valid = true;
+                        const int *o = S + (size_t)y * SP + x;
+                        const int *oh = o + (size_t)h * SP, *og = o + (size_t)g * SP;
+                        const int p00 = __ldg(o), p0h = __ldg(o + h), p0g = __ldg(o + g);
+                        const int ph0 = __ldg(oh), phg = __ldg(oh + g);
+                        const int pg0 = __ldg(og), pgh = __ldg(og + h), pgg = __ldg(og + g);
+                        // x gradient: right half minus left half; y gradient: top half minus bottom half
+                        const int left = p00 + pgh - pg0 - p0h, right = p0h + pgg - pgh - p0g;
+                        const int top = p00 + phg - ph0 - p0g, bottom = ph0 + pgg - pg0 - phg;
+                        const float vx = (float)((double)((float)left * wn) + (double)((float)right * wa));
+                        const float vy = (float)((double)((float)top * wa) + (double)((float)bottom * wn));
+                        X = vx * c_ori_w[k];
+                        Y = vy * c_ori_w[k];
+                    }
+                }
+                const unsigned bal = __ballot_sync(FULL_MASK, valid);
+                if (valid) {
+                    OriSample o;
+                    o.iang = __float2int_rn(fast_atan2_deg(Y, X));
+                    o.X = X;
+                    o.Y = Y;
+                    o.pad = 0;
+                    smp[na + __popc(bal & ((1u << lane) - 1))] = o;
+                }
+                na += __popc(bal);
+            }
+            __syncwarp();
+            if (na == 0) {
+                dead = true;
+            } else {
+                // ---- 72 sliding windows (lane handles windows lane, lane+32, lane+64), fp32 sums in
+                //      sample order; first strict maximum over increasing window index ----
+                float bmod = 0, bx = 0, by = 0;
+                int bi = 1 << 30;
+                for (int wi = lane; wi < kOriWindows; wi += 32) {
+                    const int ang0 = wi * 5;
+                    float sx = 0, sy = 0;
+                    for (int k = 0; k < na; k++) {
+                        const OriSample o = smp[k];
+                        const int d = abs(o.iang - ang0);
+                        if (d < 30 || d > 330) {
+                            sx += o.X;
+                            sy += o.Y;
+                        }
+                    }
+                    const float mod = sx * sx + sy * sy;
+                    if (mod > bmod) {
+                        bmod = mod;
+                        bx = sx;
+                        by = sy;
+                        bi = wi;
+                    }
+                }
+#pragma unroll
+                for (int d = 16; d > 0; d >>= 1) {
+                    const float om = __shfl_xor_sync(FULL_MASK, bmod, d);
+                    const float ox = __shfl_xor_sync(FULL_MASK, bx, d);
+                    const float oy = __shfl_xor_sync(FULL_MASK, by, d);
+                    const int oi = __shfl_xor_sync(FULL_MASK, bi, d);
+                    if (om > bmod || (om == bmod && oi < bi)) {
+                        bmod = om;
+                        bx = ox;
+                        by = oy;
+                        bi = oi;
+                    }
+                }
+                dir = fast_atan2_deg(-by, bx);
+            }
+            __syncwarp();  // the next keypoint overwrites smp
+        }
+
+        const int n = (int)(21 * s);
+        if (!dead && want_desc && (n < kPatch || n > kMaxWindow)) {
+            // n < 21: up-scaling INTER_AREA is outside the restated path (the oracle deletes it too);
+            // n > kMaxWindow: unsupported window, reported through the status word.
+            if (n > kMaxWindow && lane == 0) atomicOr(A.misc + kMiscStatus, 1);
+            dead = true;
+        }
+        if (lane == 0) {
+            if (dead) {
+                kpp->size = -1.f;
+                const int pos = atomicAdd(A.ndeleted + b, 1);
+                A.deleted_slots[(size_t)b * A.cap + pos] = slot;
+            } else {
+                kpp->angle = dir;
+                if (want_desc) {
+                    const int cls = (n > kClassMaxN0) + (n > kClassMaxN1) + (n > kClassMaxN2);
+                    const int pos = atomicAdd(A.misc + kMiscClassCount + cls, 1);
+                    A.class_list[(size_t)cls * A.list_stride + pos] = b * A.cap + slot;
+                }
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K4b: descriptor.
+// ------------------------------------------------------------------------------------------------
+struct AreaTab {  // one destination cell of the INTER_AREA table (same for x and y: square window)
+    int start[kPatch];
+    int count[kPatch];
+    float a_first[kPatch], a_mid[kPatch], a_last[kPatch];
+    unsigned char has_first[kPatch], has_last[kPatch];
+};
+
+template <int THREADS, bool GLOBAL>
+__global__ void __launch_bounds__(THREADS) k_descriptor(const __grid_constant__ DescribeArgs A, int cls, int max_n,
+                                                        int tile_cap)
+{
+    extern __shared__ __align__(16) unsigned char dyn[];
+    // dynamic layout: double rsx[max_n], rsy[max_n]; then (staged classes) uchar win[max_n^2], uchar tile[tile_cap]
+    double *s_rsx = reinterpret_cast<double *>(dyn);
+    double *s_rsy = s_rsx + max_n;
+    unsigned char *s_win = dyn + (size_t)max_n * 16;
+    unsigned char *s_tile = s_win + (((size_t)max_n * max_n + 15) & ~(size_t)15);
+
+    __shared__ int s_work;
+    __shared__ float s_scale;
+    __shared__ AreaTab s_tab;
+    __shared__ __align__(4) unsigned char s_patch[kPatchPx + 3];
+    __shared__ float s_dx[400], s_dy[400];
+    __shared__ float s_vec[128];
+
+    constexpr int NW = THREADS / 32;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int W = A.geo.W, H = A.geo.H;
+    const int D = A.extended ? 128 : 64;
+    const int pitch = (int)A.img.pitch;
+    const int count = A.misc[kMiscClassCount + cls];
+    const int *list = A.class_list + (size_t)cls * A.list_stride;
+    unsigned char *g_win = GLOBAL ? A.win_scratch + (size_t)blockIdx.x * kMaxWindow * kMaxWindow : nullptr;
+
+    for (;;) {
+        __syncthreads();  // everyone is done with the previous keypoint's shared state
+        if (tid == 0) s_work = atomicAdd(A.misc + kMiscClassHead + cls, 1);
+        __syncthreads();
+        const int work = s_work;
+        if (work >= count) break;
+        const int kidx = list[work];
+        const int b = kidx / A.cap;
+        const surf_keypoint *kpp = A.kps + kidx;
+        const float cx = kpp->x, cy = kpp->y, size = kpp->size, dir = kpp->angle;
+        const uint8_t *img = A.img.ptr + (size_t)b * A.img.frame_stride;
+
+        const float s = size * 1.2f / 9.0f;
+        const int n = (int)(21 * s);
+        const float off = -(float)(n - 1) / 2;
+
+        // ---- window geometry ----
+        float sd = 1.f, cd = 0.f;
+        int ux0 = 0, uy0 = 0;  // upright: integer window origin
+        int tx0, tx1, ty0, ty1;
+        if (A.upright) {
+            ux0 = __float2int_rn(cx + off);
+            uy0 = __float2int_rn(cy - off);
+            tx0 = min(max(ux0, 0), W - 1);
+            tx1 = min(max(ux0 + n - 1, 0), W - 1);
+            ty1 = min(max(uy0, 0), H - 1);
+            ty0 = min(max(uy0 - n + 1, 0), H - 1);
+        } else {
+            const float th = dir * (float)(3.1415926535897932384626433832795 / 180);
+            sd = -(float)sin((double)th);
+            cd = (float)cos((double)th);
+            if (tid == 0) {
+                // row starts advance by sequential fp32 additions; stored as doubles for the tap loop
+                float sx0 = cx + off * cd + off * sd;
+                float sy0 = cy - off * sd + off * cd;
+                for (int i = 0; i < n; i++) {
+                    s_rsx[i] = (double)sx0;
+                    s_rsy[i] = (double)sy0;
+                    sx0 += sd;
+                    sy0 += cd;
+                }
+            }
+            __syncthreads();
+            // bounding box of all taps (floor and floor + 1), clamped to the image
+            const double ex = (double)(n - 1) * (double)cd, ey = (double)(n - 1) * (double)sd;
+            const double x00 = s_rsx[0], x10 = s_rsx[n - 1], y00 = s_rsy[0], y10 = s_rsy[n - 1];
+            const double minx = fmin(fmin(x00, x00 + ex), fmin(x10, x10 + ex));
+            const double maxx = fmax(fmax(x00, x00 + ex), fmax(x10, x10 + ex));
+            const double miny = fmin(fmin(y00, y00 - ey), fmin(y10, y10 - ey));
+            const double maxy = fmax(fmax(y00, y00 - ey), fmax(y10, y10 - ey));
+            tx0 = min(max(__double2int_rd(minx), 0), W - 1);
+            tx1 = min(max(__double2int_rd(maxx) + 1, 0), W - 1);
+            ty0 = min(max(__double2int_rd(miny), 0), H - 1);
+            ty1 = min(max(__double2int_rd(maxy) + 1, 0), H - 1);
+        }
+        const int tx0a = tx0 & ~3;                    // word-aligned tile origin
+        const int tp = ((tx1 - tx0a + 1) + 3) & ~3;   // tile pitch in bytes
+        const int th_rows = ty1 - ty0 + 1;
+        // the tile capacity of a staged class is an upper bound by construction (tile_cap_for); a
+        // violation would be a bug, reported through the status word instead of corrupting memory
+        if (!GLOBAL && tp * th_rows > tile_cap) {
+            if (tid == 0) atomicOr(A.misc + kMiscStatus, 2);
+            continue;
+        }
+
+        // ---- INTER_AREA table for this window size (one warp) ----
+        const double inv = (double)kPatch / n;
+        const double scale = 1. / inv;
+        const int isc = __double2int_rn(scale);
+        const bool int_scale = fabs(scale - isc) < DBL_EPSILON;
+        if (!int_scale && warp == NW - 1 && lane < kPatch) {
+            const int d = lane;
+            const double f1 = d * scale, f2 = f1 + scale;
+            const double cell = fmin(scale, n - f1);
+            int s1 = __double2int_ru(f1), s2 = __double2int_rd(f2);
+            s2 = min(s2, n - 1);
+            s1 = min(s1, s2);
+            const bool hf = (s1 - f1) > 1e-3, hl = (f2 - s2) > 1e-3;
+            s_tab.start[d] = hf ? s1 - 1 : s1;
+            s_tab.count[d] = (hf ? 1 : 0) + (s2 - s1) + (hl ? 1 : 0);
+            s_tab.has_first[d] = hf;
+            s_tab.has_last[d] = hl;
+            s_tab.a_first[d] = (float)((s1 - f1) / cell);
+            s_tab.a_mid[d] = (float)(1.0 / cell);
+            s_tab.a_last[d] = (float)(fmin(fmin(f2 - s2, 1.), cell) / cell);
+        }
+
+        // ---- stage the bounding box of the window in shared memory (coalesced word loads) ----
+        if (!GLOBAL) {
+            const int wpr = tp >> 2;
+            const int wfull = A.img_aligned4 ? min(wpr, (W - tx0a) >> 2) : 0;  // words fully inside the row
+            for (int r = warp; r < th_rows; r += NW) {
+                const uint8_t *src = img + (size_t)(ty0 + r) * pitch + tx0a;
+                uint32_t *dst = reinterpret_cast<uint32_t *>(s_tile + r * tp);
+                for (int c = lane; c < wfull; c += 32)  // asynchronous 4-byte copies, no register staging
+                    __pipeline_memcpy_async(dst + c, src + 4 * c, 4);
+                for (int c = wfull + lane; c < wpr; c += 32) {
+                    const int x = tx0a + 4 * c;
+                    uint32_t v = 0;
+#pragma unroll
+                    for (int k = 0; k < 4; k++)
+                        if (x + k < W) v |= (uint32_t)src[4 * c + k] << (8 * k);
+                    dst[c] = v;
+                }
+            }
+            __pipeline_commit();
+            __pipeline_wait_prior(0);
+        }
+        __syncthreads();
+
+        unsigned char *win = GLOBAL ? g_win : s_win;
+
+        // ---- window pixels: one warp per window row, lanes along the row ----
+        const int src_pitch = GLOBAL ? pitch : tp;
+        const int src_x0 = GLOBAL ? 0 : tx0a, src_y0 = GLOBAL ? 0 : ty0;
+        auto SRC = [&](int o) -> unsigned { return GLOBAL ? (unsigned)__ldg(img + o) : (unsigned)s_tile[o]; };
+        if (A.upright) {
+            for (int i = warp; i < n; i += NW) {
+                const int x = min(max(ux0 + i, 0), W - 1) - src_x0;
+                for (int j = lane; j < n; j += 32) {
+                    const int y = min(max(uy0 - j, 0), H - 1) - src_y0;
+                    win[i * n + j] = (unsigned char)SRC(y * src_pitch + x);
+                }
+            }
+        } else {
+            const double kMagic = 6755399441055744.0;  // 1.5 * 2^52: floor via round-down addition
+            const double lane_dx = (double)lane * (double)cd, lane_dy = (double)lane * (double)sd;
+            const double step_x = 32.0 * (double)cd, step_y = 32.0 * (double)sd;
+            for (int i = warp; i < n; i += NW) {
+                double fx = s_rsx[i] + lane_dx;  // start + j * step, exact in fp64
+                double fy = s_rsy[i] - lane_dy;
+                unsigned char *wrow = win + i * n;
+                for (int j = lane; j < n; j += 32, fx += step_x, fy -= step_y) {
+                    const double mx = __dadd_rd(fx, kMagic), my = __dadd_rd(fy, kMagic);
+                    const int ix = __double2loint(mx), iy = __double2loint(my);
+                    unsigned v;
+                    if ((unsigned)ix < (unsigned)(W - 1) && (unsigned)iy < (unsigned)(H - 1)) {
+                        const float a = (float)(fx - (mx - kMagic)), bb = (float)(fy - (my - kMagic));
+                        const int q = (iy - src_y0) * src_pitch + (ix - src_x0);
+                        const float na = 1.f - a, nb = 1.f - bb;
+                        const float p00 = u8f(SRC(q)), p01 = u8f(SRC(q + 1));
+                        const float p10 = u8f(SRC(q + src_pitch)), p11 = u8f(SRC(q + src_pitch + 1));
+                        v = round_u8(p00 * na * nb + p01 * a * nb + p10 * na * bb + p11 * a * bb);
+                    } else {
+                        const int x = min(max(__double2int_rn(fx), 0), W - 1);
+                        const int y = min(max(__double2int_rn(fy), 0), H - 1);
+                        v = SRC((y - src_y0) * src_pitch + (x - src_x0));
+                    }
+                    wrow[j] = (unsigned char)v;
+                }
+            }
+        }
+        __syncthreads();
+
+        // ---- resize to 21 x 21 (INTER_AREA), one destination pixel per thread ----
+        for (int p = tid; p < kPatchPx; p += THREADS) {
+            const int dy = p / kPatch, dx = p - dy * kPatch;
+            int outv;
+            if (int_scale && isc == 2) {
+                const unsigned char *r0 = win + (2 * dy) * n + 2 * dx, *r1 = r0 + n;
+                outv = (r0[0] + r0[1] + r1[0] + r1[1] + 2) >> 2;
+            } else if (int_scale) {
+                int acc = 0;
+                for (int v = 0; v < isc; v++) {
+                    const unsigned char *r0 = win + (dy * isc + v) * n + dx * isc;
+                    for (int u = 0; u < isc; u++) acc += r0[u];
+                }
+                const float wgt = 1.f / (isc * isc);
+                outv = sat_u8(acc * wgt);
+            } else {
+                const int ys = s_tab.start[dy], yc = s_tab.count[dy];
+                const bool yhf = s_tab.has_first[dy], yhl = s_tab.has_last[dy];
+                const float yaf = s_tab.a_first[dy], yam = s_tab.a_mid[dy], yal = s_tab.a_last[dy];
+                const int xs = s_tab.start[dx], xc = s_tab.count[dx];
+                const bool xhf = s_tab.has_first[dx], xhl = s_tab.has_last[dx];
+                const float xaf = s_tab.a_first[dx], xam = s_tab.a_mid[dx], xal = s_tab.a_last[dx];
+                const int fend = xc - (xhl ? 1 : 0);
+                float acc = 0;
+                for (int e = 0; e < yc; e++) {
+                    const float beta = (e == 0 && yhf) ? yaf : ((e == yc - 1 && yhl) ? yal : yam);
+                    const unsigned char *row = win + (ys + e) * n + xs;
+                    float buf = 0;
+                    int f = 0;
+                    if (xhf) {
+                        buf += u8f(row[0]) * xaf;
+                        f = 1;
+                    }
+#pragma unroll 4
+                    for (; f < fend; f++) buf += u8f(row[f]) * xam;
+                    if (xhl) buf += u8f(row[xc - 1]) * xal;
+                    if (e == 0) acc = beta * buf; else acc += beta * buf;
+                }
+                outv = sat_u8(acc);
+            }
+            s_patch[p] = (unsigned char)outv;
+        }
+        __syncthreads();
+        if (A.patches) {
+            unsigned char *po = A.patches + (size_t)kidx * kPatchPx;
+            for (int p = tid; p < kPatchPx; p += THREADS) po[p] = s_patch[p];
+        }
+        if (!A.desc) continue;
+
+        // ---- 2x2 Haar gradients of the patch, Gaussian weighted ----
+        for (int t = tid; t < 400; t += THREADS) {
+            const int i = t / 20, j = t - i * 20;
+            const unsigned char *r0 = s_patch + i * kPatch + j, *r1 = r0 + kPatch;
+            const float wgt = c_desc_w[t];
+            s_dx[t] = (r0[1] - r0[0] + r1[1] - r1[0]) * wgt;
+            s_dy[t] = (r1[0] - r0[0] + r1[1] - r0[1]) * wgt;
+        }
+        __syncthreads();
+        // ---- 4 x 4 sub-regions, one output component per thread, sequential fp32 sums ----
+        const int nb = A.extended ? 8 : 4;
+        for (int t = tid; t < D; t += THREADS) {
+            const int region = t / nb, comp = t - region * nb;
+            const int I = region >> 2, J = region & 3;
+            float acc = 0;
+            for (int y = I * 5; y < I * 5 + 5; y++)
+                for (int x = J * 5; x < J * 5 + 5; x++) {
+                    const float tx = s_dx[y * 20 + x], ty = s_dy[y * 20 + x];
+                    if (A.extended) {
+                        switch (comp) {
+                            case 0: if (ty >= 0) acc += tx; break;
+                            case 1: if (ty >= 0) acc += fabsf(tx); break;
+                            case 2: if (!(ty >= 0)) acc += tx; break;
+                            case 3: if (!(ty >= 0)) acc += fabsf(tx); break;
+                            case 4: if (tx >= 0) acc += ty; break;
+                            case 5: if (tx >= 0) acc += fabsf(ty); break;
+                            case 6: if (!(tx >= 0)) acc += ty; break;
+                            default: if (!(tx >= 0)) acc += fabsf(ty); break;
+                        }
+                    } else {
+                        switch (comp) {
+                            case 0: acc += tx; break;
+                            case 1: acc += ty; break;
+                            case 2: acc += fabsf(tx); break;
+                            default: acc += fabsf(ty); break;
+                        }
+                    }
+                }
+            s_vec[t] = acc;
+        }
+        __syncthreads();
+        if (warp == 0) {
+            double mag = 0;
+            for (int t = lane; t < D; t += 32) mag += (double)(s_vec[t] * s_vec[t]);
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) mag += __shfl_xor_sync(FULL_MASK, mag, d);
+            if (lane == 0) s_scale = (float)(1. / (sqrt(mag) + DBL_EPSILON));
+        }
+        __syncthreads();
+        float *vo = A.desc + (size_t)kidx * D;
+        for (int t = tid; t < D; t += THREADS) vo[t] = s_vec[t] * s_scale;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+struct ClassCfg {
+    int max_n, tile_cap, smem, grid;
+};
+
+int tile_cap_for(int max_n)
+{
+    // bounding box side of a rotated n x n window: n (|cos| + |sin|) + 3 <= 1.4143 n + 3, rows padded to 4
+    int side = (int)(1.4143 * max_n) + 4;
+    int pitch = (side + 3 + 3) & ~3;
+    return pitch * side;
+}
+
+struct DevCfg {
+    bool ready = false;
+    int ori_grid = 0;
+    ClassCfg cls[kNumClasses];
+    cudaStream_t side[3];
+    cudaEvent_t fork, join[3];
+};
+DevCfg g_cfg[64];
+
+template <int THREADS, bool GLOBAL>
+void setup_class(ClassCfg &c, int sms)
+{
+    cudaFuncSetAttribute(k_descriptor<THREADS, GLOBAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, c.smem);
+    int per_sm = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_descriptor<THREADS, GLOBAL>, THREADS, c.smem);
+    if (per_sm < 1) per_sm = 1;
+    if (GLOBAL && per_sm > kClassDGridPerSm) per_sm = kClassDGridPerSm;
+    c.grid = sms * per_sm;  // persistent CTAs: a multiple of the SM count
+}
+
+DevCfg &dev_cfg()
+{
+    int dev = 0;
+    cudaGetDevice(&dev);
+    DevCfg &c = g_cfg[dev & 63];
+    if (!c.ready) {
+        int sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        int per_sm = 4;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_orient, kOriWarps * 32, 0);
+        c.ori_grid = sms * (per_sm < 1 ? 1 : per_sm);
+        for (int k = 0; k < kNumClasses; k++) {
+            ClassCfg &cc = c.cls[k];
+            const int max_ns[kNumClasses] = {kClassMaxN0, kClassMaxN1, kClassMaxN2, kMaxWindow};
+            cc.max_n = max_ns[k];
+            const bool global = (k == kNumClasses - 1);
+            cc.tile_cap = global ? 0 : tile_cap_for(cc.max_n);
+            cc.smem = cc.max_n * 16 + (global ? 0 : ((cc.max_n * cc.max_n + 15) & ~15) + cc.tile_cap);
+        }
+        setup_class<128, false>(c.cls[0], sms);
+        setup_class<256, false>(c.cls[1], sms);
+        setup_class<256, false>(c.cls[2], sms);
+        setup_class<256, true>(c.cls[3], sms);
+        for (int k = 0; k < 3; k++) {
+            cudaStreamCreateWithFlags(&c.side[k], cudaStreamNonBlocking);
+            cudaEventCreateWithFlags(&c.join[k], cudaEventDisableTiming);
+        }
+        cudaEventCreateWithFlags(&c.fork, cudaEventDisableTiming);
+        c.ready = true;
+    }
+    return c;
+}
+
+}  // namespace
+
+size_t describe_scratch_bytes()
+{
+    return (size_t)dev_cfg().cls[kNumClasses - 1].grid * kMaxWindow * kMaxWindow;
+}
+
+void launch_describe(const DescribeArgs &a, cudaStream_t st, int *launches)
+{
+    DevCfg &c = dev_cfg();
+    k_orient<<<c.ori_grid, kOriWarps * 32, 0, st>>>(a);
+    *launches += 1;
+    if (!a.desc && !a.patches) return;
+    // The four size classes are independent: fork them onto side streams so their CTAs share the
+    // GPU and the tails of the short launches overlap the long ones; join back on `st`.
+    cudaEventRecord(c.fork, st);
+    for (int k = 0; k < 3; k++) cudaStreamWaitEvent(c.side[k], c.fork, 0);
+    k_descriptor<256, false><<<c.cls[1].grid, 256, c.cls[1].smem, st>>>(a, 1, c.cls[1].max_n, c.cls[1].tile_cap);
+    k_descriptor<256, true><<<c.cls[3].grid, 256, c.cls[3].smem, c.side[0]>>>(a, 3, c.cls[3].max_n, c.cls[3].tile_cap);
+    k_descriptor<256, false><<<c.cls[2].grid, 256, c.cls[2].smem, c.side[1]>>>(a, 2, c.cls[2].max_n, c.cls[2].tile_cap);
+    k_descriptor<128, false><<<c.cls[0].grid, 128, c.cls[0].smem, c.side[2]>>>(a, 0, c.cls[0].max_n, c.cls[0].tile_cap);
+    for (int k = 0; k < 3; k++) {
+        cudaEventRecord(c.join[k], c.side[k]);
+        cudaStreamWaitEvent(st, c.join[k], 0);
+    }
+    *launches += 4;
+}
+
+}  // namespace surfb200

@@ -46,7 +46,8 @@ struct surf_engine {
     float *d_desc = nullptr, *d_out_desc = nullptr;  int desc_dim = 0;
     uint8_t *d_patches = nullptr;
     int *d_counts = nullptr, *d_ndel = nullptr, *d_off_in = nullptr, *d_off_out = nullptr, *d_misc = nullptr;
-    int *d_deleted = nullptr;
+    int *d_deleted = nullptr, *d_class_list = nullptr;
+    uint8_t *d_win_scratch = nullptr;
     int *h_pin = nullptr;  // pinned: counts[B], ndel[B], off_out[B+1], misc[4]
     surf_dmatch *d_match_part = nullptr;  size_t match_part_cap = 0;
     void *d_match_io = nullptr;           size_t match_io_cap = 0;
@@ -154,12 +155,13 @@ void free_workspace(surf_engine *e)
     cudaFree(e->d_det); cudaFree(e->d_kp_a); cudaFree(e->d_kp_b); cudaFree(e->d_out_kp); cudaFree(e->d_desc);
     cudaFree(e->d_out_desc); cudaFree(e->d_patches); cudaFree(e->d_counts); cudaFree(e->d_ndel);
     cudaFree(e->d_off_in); cudaFree(e->d_off_out); cudaFree(e->d_misc); cudaFree(e->d_deleted);
-    cudaFree(e->d_match_part); cudaFree(e->d_match_io);
+    cudaFree(e->d_match_part); cudaFree(e->d_match_io); cudaFree(e->d_class_list); cudaFree(e->d_win_scratch);
     if (e->h_pin) cudaFreeHost(e->h_pin);
     e->d_img = e->d_mask = nullptr; e->d_sum = e->d_msum = e->d_bandsum = nullptr; e->d_det = nullptr;
     e->d_kp_a = e->d_kp_b = e->d_out_kp = nullptr; e->d_desc = e->d_out_desc = nullptr; e->d_patches = nullptr;
     e->d_counts = e->d_ndel = e->d_off_in = e->d_off_out = e->d_misc = e->d_deleted = nullptr;
-    e->d_match_part = nullptr; e->d_match_io = nullptr; e->h_pin = nullptr;
+    e->d_match_part = nullptr; e->d_match_io = nullptr; e->h_pin = nullptr; e->d_class_list = nullptr;
+    e->d_win_scratch = nullptr;
     e->match_part_cap = e->match_io_cap = 0;
 }
 
@@ -207,8 +209,10 @@ int alloc_workspace(surf_engine *e)
     CU(e, cudaMalloc(&e->d_ndel, sizeof(int) * B));
     CU(e, cudaMalloc(&e->d_off_in, sizeof(int) * (B + 1)));
     CU(e, cudaMalloc(&e->d_off_out, sizeof(int) * (B + 1)));
-    CU(e, cudaMalloc(&e->d_misc, sizeof(int) * 4));
-    CU(e, cudaMallocHost(&e->h_pin, sizeof(int) * (3 * (size_t)B + 8)));
+    CU(e, cudaMalloc(&e->d_misc, sizeof(int) * kMiscWords));
+    CU(e, cudaMalloc(&e->d_class_list, nk * kNumClasses * sizeof(int)));
+    CU(e, cudaMalloc(&e->d_win_scratch, describe_scratch_bytes()));
+    CU(e, cudaMallocHost(&e->h_pin, sizeof(int) * (3 * (size_t)B + 8 + kMiscWords)));
     return alloc_det_and_desc(e);
 }
 
@@ -312,7 +316,7 @@ int run_describe_pack(surf_engine *e, const ImageRef &img, const FrameGeo &geo, 
 {
     const surf_params &p = e->params;
     CU(e, cudaMemsetAsync(e->d_ndel, 0, sizeof(int) * B, e->stream));
-    CU(e, cudaMemsetAsync(e->d_misc, 0, sizeof(int) * 4, e->stream));
+    CU(e, cudaMemsetAsync(e->d_misc, 0, sizeof(int) * kMiscWords, e->stream));
     launch_offsets(e->d_counts, nullptr, e->cap, B, e->d_off_in, e->stream, &e->launches);
     DescribeArgs a{};
     a.img = img;
@@ -326,10 +330,13 @@ int run_describe_pack(surf_engine *e, const ImageRef &img, const FrameGeo &geo, 
     a.patches = patches;
     a.extended = p.extended;
     a.upright = p.upright;
-    a.work_counter = e->d_misc;
-    a.status = e->d_misc + 1;
+    a.img_aligned4 = ((reinterpret_cast<uintptr_t>(img.ptr) | img.pitch | img.frame_stride) & 3) == 0;
+    a.misc = e->d_misc;
     a.ndeleted = e->d_ndel;
     a.deleted_slots = e->d_deleted;
+    a.class_list = e->d_class_list;
+    a.list_stride = (size_t)e->max_b * e->cap;
+    a.win_scratch = e->d_win_scratch;
     launch_describe(a, e->stream, &e->launches);
     rec(e, EV_DESCRIBE);
     if (pack) {
@@ -350,7 +357,7 @@ int fetch_counts(surf_engine *e, int B)
     CU(e, cudaMemcpyAsync(h, e->d_counts, sizeof(int) * B, cudaMemcpyDeviceToHost, e->stream));
     CU(e, cudaMemcpyAsync(h + B, e->d_ndel, sizeof(int) * B, cudaMemcpyDeviceToHost, e->stream));
     CU(e, cudaMemcpyAsync(h + 2 * B, e->d_off_out, sizeof(int) * (B + 1), cudaMemcpyDeviceToHost, e->stream));
-    CU(e, cudaMemcpyAsync(h + 3 * B + 1, e->d_misc, sizeof(int) * 4, cudaMemcpyDeviceToHost, e->stream));
+    CU(e, cudaMemcpyAsync(h + 3 * B + 1, e->d_misc, sizeof(int) * kMiscWords, cudaMemcpyDeviceToHost, e->stream));
     return SURF_OK;
 }
 
@@ -364,7 +371,9 @@ int check_counts(surf_engine *e, int B)
         return fail(e, SURF_ERR_CAPACITY, "a frame produced %d raw keypoints; the engine was created for %d per frame",
                     worst, e->cap);
     }
-    if (h[3 * B + 1 + 1] & 1)
+    if (h[3 * B + 1 + kMiscStatus] & 2)
+        return fail(e, SURF_ERR_CUDA, "internal error: descriptor tile capacity exceeded");
+    if (h[3 * B + 1 + kMiscStatus] & 1)
         return fail(e, SURF_ERR_UNSUPPORTED, "a keypoint needs a descriptor window wider than %d pixels", kMaxWindow);
     return SURF_OK;
 }

@@ -51,8 +51,23 @@ struct ImageRef {
     size_t frame_stride;  // bytes between frames
 };
 
+// Descriptor windows are handled by size class (window side n = (int)(21 * size * 1.2 / 9)):
+// the rotated window's bounding box in the image and the n x n window itself are staged in shared
+// memory for classes A-C; class D (n > 184, about 1 % of keypoints) reads the image from global
+// memory and keeps its window in a per-CTA global scratch buffer.
+constexpr int kNumClasses = 4;
+constexpr int kClassMaxN0 = 64, kClassMaxN1 = 128, kClassMaxN2 = 184;  // class D: up to kMaxWindow
+constexpr int kClassDGridPerSm = 2;
+
+// d_misc word layout
+constexpr int kMiscStatus = 1;
+constexpr int kMiscClassCount = 2;   // [4]
+constexpr int kMiscClassHead = 6;    // [4]
+constexpr int kMiscWords = 16;
+
 struct DescribeArgs {
     ImageRef img;
+    int img_aligned4;     // base, pitch and frame stride are multiples of 4: word loads allowed
     const uint32_t *sum;
     FrameGeo geo;
     surf_keypoint *kps;   // [B][cap], updated in place (angle, size = -1 on deletion)
@@ -62,11 +77,15 @@ struct DescribeArgs {
     float *desc;          // [B][cap][D] or nullptr (orientation only)
     uint8_t *patches;     // optional [B][cap][441]
     int extended, upright;
-    int *work_counter;    // dynamic work queue head
+    int *misc;            // status word, class counters and queue heads (kMisc*)
     int *ndeleted;        // [B]
     int *deleted_slots;   // [B][cap]
-    int *status;          // bit 0: a window larger than kMaxWindow was met
+    int *class_list;      // [kNumClasses][list_stride]: keypoint index b * cap + slot
+    size_t list_stride;
+    uint8_t *win_scratch; // class D windows: [grid][kMaxWindow * kMaxWindow]
 };
+
+size_t describe_scratch_bytes();  // size of win_scratch for the current device
 
 // ---- launchers (surf_kernels.cu) ----
 int integral_band_rows(int W);

@@ -23,49 +23,6 @@ namespace surfb200 {
 #define FULL_MASK 0xffffffffu
 
 // ------------------------------------------------------------------------------------------------
-// constant tables (fixed by the algorithm, not by engine parameters)
-// ------------------------------------------------------------------------------------------------
-__constant__ signed char c_ori_x[kOriSamples];
-__constant__ signed char c_ori_y[kOriSamples];
-__constant__ float c_ori_w[kOriSamples];
-__constant__ float c_desc_w[400];
-
-static void gaussian_taps(int n, double sigma, float *out)
-{
-    // getGaussianKernel(n, sigma, CV_32F) as OpenCV 2.4.5 builds it.
-    double s2 = -0.5 / (sigma * sigma), acc = 0;
-    for (int i = 0; i < n; i++) {
-        double x = i - (n - 1) * 0.5;
-        out[i] = (float)std::exp(s2 * x * x);
-        acc += out[i];
-    }
-    acc = 1. / acc;
-    for (int i = 0; i < n; i++) out[i] = (float)(out[i] * acc);
-}
-
-void upload_tables()
-{
-    signed char px[kOriSamples], py[kOriSamples];
-    float pw[kOriSamples], dw[400], g[13], gd[20];
-    gaussian_taps(13, 2.5, g);
-    int n = 0;
-    for (int i = -6; i <= 6; i++)
-        for (int j = -6; j <= 6; j++)
-            if (i * i + j * j <= 36) {
-                px[n] = (signed char)i;  // the outer loop variable is the x offset
-                py[n] = (signed char)j;
-                pw[n++] = g[i + 6] * g[j + 6];
-            }
-    gaussian_taps(20, 3.3, gd);
-    for (int i = 0; i < 20; i++)
-        for (int j = 0; j < 20; j++) dw[i * 20 + j] = gd[i] * gd[j];
-    cudaMemcpyToSymbol(c_ori_x, px, sizeof(px));
-    cudaMemcpyToSymbol(c_ori_y, py, sizeof(py));
-    cudaMemcpyToSymbol(c_ori_w, pw, sizeof(pw));
-    cudaMemcpyToSymbol(c_desc_w, dw, sizeof(dw));
-}
-
-// ------------------------------------------------------------------------------------------------
 // K1: integral image.  Two kernels:
 //   k_band_colsum   per band of R rows, the column totals of that band (reads the image once)
 //   k_band_integral per band: warps scan rows with shuffles into a shared tile, a carry row is
@@ -572,398 +529,6 @@ __global__ void __launch_bounds__(1024) k_offsets(const int *__restrict__ counts
 void launch_offsets(const int *counts, const int *ndel, int cap, int B, int *offsets, cudaStream_t st, int *launches)
 {
     k_offsets<<<1, 1024, 0, st>>>(counts, ndel, cap, B, offsets);
-    *launches += 1;
-}
-
-// ------------------------------------------------------------------------------------------------
-// K4: orientation + descriptor, one CTA (128 threads) per keypoint, persistent CTAs pulling
-// keypoints from an atomic queue.  SURVEY.md A4, A5.
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ float fast_atan2_deg(float y, float x)
-{
-    // fastAtan2 (core/mathfuncs.cpp): 7th-order odd polynomial, degrees in [0, 360].
-    const float k = (float)(180 / 3.1415926535897932384626433832795);
-    const float p1 = 0.9997878412794807f * k, p3 = -0.3258083974640975f * k;
-    const float p5 = 0.1555786518463281f * k, p7 = -0.04432655554792128f * k;
-    const float ax = fabsf(x), ay = fabsf(y);
-    float a, c, c2;
-    if (ax >= ay) {
-        c = ay / (ax + (float)DBL_EPSILON);
-        c2 = c * c;
-        a = (((p7 * c2 + p5) * c2 + p3) * c2 + p1) * c;
-    } else {
-        c = ax / (ay + (float)DBL_EPSILON);
-        c2 = c * c;
-        a = 90.f - (((p7 * c2 + p5) * c2 + p3) * c2 + p1) * c;
-    }
-    if (x < 0) a = 180.f - a;
-    if (y < 0) a = 360.f - a;
-    return a;
-}
-
-__device__ __forceinline__ int sat_u8(float v)
-{
-    int r = __float2int_rn(v);
-    return r < 0 ? 0 : (r > 255 ? 255 : r);
-}
-
-struct WindowGeo {
-    const uint8_t *img;
-    int pitch, W, H;
-    int upright;
-    int x0, y0;       // upright: integer window origin
-    float sd, cd;     // rotated: -sin, cos of the dominant angle
-    const float *rsx; // per-row start coordinates (fp32 sequential chain)
-    const float *rsy;
-};
-
-// One pixel of the win_size x win_size window around the keypoint.
-__device__ __forceinline__ int window_pixel(const WindowGeo &g, int i, int j)
-{
-    if (g.upright) {
-        int x = min(max(g.x0 + i, 0), g.W - 1);
-        int y = min(max(g.y0 - j, 0), g.H - 1);
-        return g.img[(size_t)y * g.pitch + x];
-    }
-    const double fx = (double)g.rsx[i] + (double)j * (double)g.cd;
-    const double fy = (double)g.rsy[i] - (double)j * (double)g.sd;
-    const int ix = __double2int_rd(fx), iy = __double2int_rd(fy);
-    if ((unsigned)ix < (unsigned)(g.W - 1) && (unsigned)iy < (unsigned)(g.H - 1)) {
-        const float a = (float)(fx - ix), b = (float)(fy - iy);
-        const uint8_t *q = g.img + (size_t)iy * g.pitch + ix;
-        const float v = q[0] * (1.f - a) * (1.f - b) + q[1] * a * (1.f - b) + q[g.pitch] * (1.f - a) * b +
-                        q[g.pitch + 1] * a * b;
-        return __float2int_rn(v) & 0xff;
-    }
-    const int x = min(max(__double2int_rn(fx), 0), g.W - 1);
-    const int y = min(max(__double2int_rn(fy), 0), g.H - 1);
-    return g.img[(size_t)y * g.pitch + x];
-}
-
-struct AreaTab {  // one destination cell of the INTER_AREA table (same for x and y: square window)
-    int start[kPatch];
-    int count[kPatch];
-    float a_first[kPatch], a_mid[kPatch], a_last[kPatch];
-    unsigned char has_first[kPatch], has_last[kPatch];
-};
-
-__device__ __forceinline__ float area_alpha(const AreaTab &t, int d, int e)
-{
-    if (e == 0 && t.has_first[d]) return t.a_first[d];
-    if (e == t.count[d] - 1 && t.has_last[d]) return t.a_last[d];
-    return t.a_mid[d];
-}
-
-constexpr int kDescThreads = 128;
-
-__global__ void __launch_bounds__(kDescThreads) k_describe(const __grid_constant__ DescribeArgs A)
-{
-    extern __shared__ __align__(16) unsigned char s_win[];  // kWinSmemSide^2 bytes
-    __shared__ int s_work;
-    __shared__ float s_X[kOriSamples], s_Y[kOriSamples];
-    __shared__ int s_iang[kOriSamples];
-    __shared__ int s_warp_cnt[4];
-    __shared__ float s_wx[kOriWindows], s_wy[kOriWindows];
-    __shared__ float s_dir, s_scale;
-    __shared__ float s_rsx[kMaxWindow], s_rsy[kMaxWindow];
-    __shared__ AreaTab s_tab;
-    __shared__ unsigned char s_patch[kPatchPx + 3];
-    __shared__ float s_dx[400], s_dy[400];
-    __shared__ float s_vec[128];
-
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int W = A.geo.W, H = A.geo.H, SP = A.geo.SP;
-    const int total = A.offsets[A.B];
-    const int D = A.extended ? 128 : 64;
-
-    for (;;) {
-        __syncthreads();  // everyone is done with the previous keypoint's shared state
-        if (tid == 0) s_work = atomicAdd(A.work_counter, 1);
-        __syncthreads();
-        const int w = s_work;
-        if (w >= total) break;
-
-        // frame of work item w: last b with offsets[b] <= w
-        int lo = 0, hi = A.B;
-        while (hi - lo > 1) {
-            int m = (lo + hi) >> 1;
-            if (A.offsets[m] <= w) lo = m; else hi = m;
-        }
-        const int b = lo, slot = w - A.offsets[b];
-        surf_keypoint *kpp = A.kps + (size_t)b * A.cap + slot;
-        const float cx = kpp->x, cy = kpp->y, size = kpp->size;
-        const uint8_t *img = A.img.ptr + (size_t)b * A.img.frame_stride;
-        const int *S = reinterpret_cast<const int *>(A.sum) + (size_t)b * A.geo.sum_frame;
-
-        const float s = size * 1.2f / 9.0f;
-        const int g = 2 * __float2int_rn(2 * s);
-        bool dead = (H + 1 < g) || (W + 1 < g);
-
-        float dir = 360.f - 90.f;
-        if (!dead && !A.upright) {
-            // ---- orientation samples (one per thread), compacted in sample order ----
-            bool valid = false;
-            float X = 0, Y = 0;
-            if (tid < kOriSamples) {
-                const float hg = (float)(g - 1) / 2;
-                const int x = __float2int_rn(cx + c_ori_x[tid] * s - hg);
-                const int y = __float2int_rn(cy + c_ori_y[tid] * s - hg);
-                if (!(y < 0 || y >= (H + 1) - g || x < 0 || x >= (W + 1) - g)) {
-                    valid = true;
-                    const int h = g / 2;
-                    const int *o = S + (size_t)y * SP + x;
-                    const int p00 = __ldg(o), p0h = __ldg(o + h), p0g = __ldg(o + g);
-                    const int *oh = o + (size_t)h * SP, *og = o + (size_t)g * SP;
-                    const int ph0 = __ldg(oh), phg = __ldg(oh + g);
-                    const int pg0 = __ldg(og), pgh = __ldg(og + h), pgg = __ldg(og + g);
-                    const float wa = 1 / ((float)h * g);
-                    const float wn = -1 / ((float)h * g);
-                    // x gradient: right half minus left half; y gradient: top half minus bottom half
-                    const int left = p00 + pgh - pg0 - p0h, right = p0h + pgg - pgh - p0g;
-                    const int top = p00 + phg - ph0 - p0g, bottom = ph0 + pgg - pg0 - phg;
-                    const float vx = (float)((double)((float)left * wn) + (double)((float)right * wa));
-                    const float vy = (float)((double)((float)top * wa) + (double)((float)bottom * wn));
-                    X = vx * c_ori_w[tid];
-                    Y = vy * c_ori_w[tid];
-                }
-            }
-            const unsigned bal = __ballot_sync(FULL_MASK, valid);
-            if (lane == 0) s_warp_cnt[warp] = __popc(bal);
-            __syncthreads();
-            int base = 0;
-            for (int k = 0; k < warp; k++) base += s_warp_cnt[k];
-            const int na = s_warp_cnt[0] + s_warp_cnt[1] + s_warp_cnt[2] + s_warp_cnt[3];
-            if (valid) {
-                const int pos = base + __popc(bal & ((1u << lane) - 1));
-                s_X[pos] = X;
-                s_Y[pos] = Y;
-                s_iang[pos] = __float2int_rn(fast_atan2_deg(Y, X));
-            }
-            __syncthreads();
-            if (na == 0) {
-                dead = true;
-            } else {
-                // ---- 72 sliding 60-degree windows, fp32 sums in sample order ----
-                if (tid < kOriWindows) {
-                    const int ang0 = tid * 5;
-                    float sx = 0, sy = 0;
-                    for (int k = 0; k < na; k++) {
-                        const int d = abs(s_iang[k] - ang0);
-                        if (d < 30 || d > 330) {
-                            sx += s_X[k];
-                            sy += s_Y[k];
-                        }
-                    }
-                    s_wx[tid] = sx;
-                    s_wy[tid] = sy;
-                }
-                __syncthreads();
-                if (tid == 0) {
-                    float bx = 0, by = 0, best = 0;
-                    for (int k = 0; k < kOriWindows; k++) {
-                        const float mod = s_wx[k] * s_wx[k] + s_wy[k] * s_wy[k];
-                        if (mod > best) {
-                            best = mod;
-                            bx = s_wx[k];
-                            by = s_wy[k];
-                        }
-                    }
-                    s_dir = fast_atan2_deg(-by, bx);
-                }
-                __syncthreads();
-                dir = s_dir;
-            }
-        }
-
-        const int n = (int)(21 * s);
-        const bool want_desc = (A.desc != nullptr) || (A.patches != nullptr);
-        if (!dead && want_desc && (n < kPatch || n > kMaxWindow)) {
-            // n < 21: up-scaling INTER_AREA is outside the restated path (oracle deletes it too);
-            // n > kMaxWindow: unsupported window, reported through the status word.
-            if (n > kMaxWindow && tid == 0) atomicOr(A.status, 1);
-            dead = true;
-        }
-        if (dead) {
-            if (tid == 0) {
-                kpp->size = -1.f;
-                const int pos = atomicAdd(A.ndeleted + b, 1);
-                A.deleted_slots[(size_t)b * A.cap + pos] = slot;
-            }
-            continue;
-        }
-        if (tid == 0) kpp->angle = dir;
-        if (!want_desc) continue;
-
-        // ---- window geometry ----
-        WindowGeo wg;
-        wg.img = img;
-        wg.pitch = (int)A.img.pitch;
-        wg.W = W;
-        wg.H = H;
-        wg.upright = A.upright;
-        wg.rsx = s_rsx;
-        wg.rsy = s_rsy;
-        const float off = -(float)(n - 1) / 2;
-        if (A.upright) {
-            wg.x0 = __float2int_rn(cx + off);
-            wg.y0 = __float2int_rn(cy - off);
-            wg.sd = 1.f;
-            wg.cd = 0.f;
-        } else {
-            const float th = dir * (float)(3.1415926535897932384626433832795 / 180);
-            wg.sd = -(float)sin((double)th);
-            wg.cd = (float)cos((double)th);
-            wg.x0 = wg.y0 = 0;
-            if (tid == 0) {
-                // row starts advance by sequential fp32 additions
-                float sx0 = cx + off * wg.cd + off * wg.sd;
-                float sy0 = cy - off * wg.sd + off * wg.cd;
-                for (int i = 0; i < n; i++) {
-                    s_rsx[i] = sx0;
-                    s_rsy[i] = sy0;
-                    sx0 += wg.sd;
-                    sy0 += wg.cd;
-                }
-            }
-        }
-        // ---- INTER_AREA table for this window size (threads 32..52) ----
-        const double inv = (double)kPatch / n;
-        const double scale = 1. / inv;
-        const int isc = __double2int_rn(scale);
-        const bool int_scale = fabs(scale - isc) < DBL_EPSILON;
-        if (!int_scale && tid >= 32 && tid < 32 + kPatch) {
-            const int d = tid - 32;
-            const double f1 = d * scale, f2 = f1 + scale;
-            const double cell = fmin(scale, n - f1);
-            int s1 = __double2int_ru(f1), s2 = __double2int_rd(f2);
-            s2 = min(s2, n - 1);
-            s1 = min(s1, s2);
-            const bool hf = (s1 - f1) > 1e-3, hl = (f2 - s2) > 1e-3;
-            s_tab.start[d] = hf ? s1 - 1 : s1;
-            s_tab.count[d] = (hf ? 1 : 0) + (s2 - s1) + (hl ? 1 : 0);
-            s_tab.has_first[d] = hf;
-            s_tab.has_last[d] = hl;
-            s_tab.a_first[d] = (float)((s1 - f1) / cell);
-            s_tab.a_mid[d] = (float)(1.0 / cell);
-            s_tab.a_last[d] = (float)(fmin(fmin(f2 - s2, 1.), cell) / cell);
-        }
-        __syncthreads();
-
-        // ---- window pixels: staged in shared memory when they fit ----
-        const bool staged = n <= kWinSmemSide;
-        if (staged) {
-            for (int idx = tid; idx < n * n; idx += kDescThreads) {
-                const int i = idx / n, j = idx - i * n;
-                s_win[idx] = (unsigned char)window_pixel(wg, i, j);
-            }
-            __syncthreads();
-        }
-        auto WIN = [&](int i, int j) -> int { return staged ? (int)s_win[i * n + j] : window_pixel(wg, i, j); };
-
-        // ---- resize to 21 x 21 (INTER_AREA), one destination pixel per thread ----
-        for (int p = tid; p < kPatchPx; p += kDescThreads) {
-            const int dy = p / kPatch, dx = p - dy * kPatch;
-            int outv;
-            if (int_scale && isc == 2) {
-                outv = (WIN(2 * dy, 2 * dx) + WIN(2 * dy, 2 * dx + 1) + WIN(2 * dy + 1, 2 * dx) +
-                        WIN(2 * dy + 1, 2 * dx + 1) + 2) >> 2;
-            } else if (int_scale) {
-                int acc = 0;
-                for (int v = 0; v < isc; v++)
-                    for (int u = 0; u < isc; u++) acc += WIN(dy * isc + v, dx * isc + u);
-                const float wgt = 1.f / (isc * isc);
-                outv = sat_u8(acc * wgt);
-            } else {
-                const int ys = s_tab.start[dy], yc = s_tab.count[dy];
-                const int xs = s_tab.start[dx], xc = s_tab.count[dx];
-                float acc = 0;
-                for (int e = 0; e < yc; e++) {
-                    const float beta = area_alpha(s_tab, dy, e);
-                    float buf = 0;
-                    for (int f = 0; f < xc; f++) buf += WIN(ys + e, xs + f) * area_alpha(s_tab, dx, f);
-                    if (e == 0) acc = beta * buf; else acc += beta * buf;
-                }
-                outv = sat_u8(acc);
-            }
-            s_patch[p] = (unsigned char)outv;
-        }
-        __syncthreads();
-        if (A.patches) {
-            unsigned char *po = A.patches + ((size_t)b * A.cap + slot) * kPatchPx;
-            for (int p = tid; p < kPatchPx; p += kDescThreads) po[p] = s_patch[p];
-        }
-        if (!A.desc) continue;
-
-        // ---- 2x2 Haar gradients of the patch, Gaussian weighted ----
-        for (int t = tid; t < 400; t += kDescThreads) {
-            const int i = t / 20, j = t - i * 20;
-            const unsigned char *r0 = s_patch + i * kPatch + j, *r1 = r0 + kPatch;
-            const float wgt = c_desc_w[t];
-            s_dx[t] = (r0[1] - r0[0] + r1[1] - r1[0]) * wgt;
-            s_dy[t] = (r1[0] - r0[0] + r1[1] - r0[1]) * wgt;
-        }
-        __syncthreads();
-        // ---- 4 x 4 sub-regions, one output component per thread, sequential fp32 sums ----
-        const int nb = A.extended ? 8 : 4;
-        for (int t = tid; t < D; t += kDescThreads) {
-            const int region = t / nb, comp = t - region * nb;
-            const int I = region >> 2, J = region & 3;
-            float acc = 0;
-            for (int y = I * 5; y < I * 5 + 5; y++)
-                for (int x = J * 5; x < J * 5 + 5; x++) {
-                    const float tx = s_dx[y * 20 + x], ty = s_dy[y * 20 + x];
-                    if (A.extended) {
-                        switch (comp) {
-                            case 0: if (ty >= 0) acc += tx; break;
-                            case 1: if (ty >= 0) acc += fabsf(tx); break;
-                            case 2: if (!(ty >= 0)) acc += tx; break;
-                            case 3: if (!(ty >= 0)) acc += fabsf(tx); break;
-                            case 4: if (tx >= 0) acc += ty; break;
-                            case 5: if (tx >= 0) acc += fabsf(ty); break;
-                            case 6: if (!(tx >= 0)) acc += ty; break;
-                            default: if (!(tx >= 0)) acc += fabsf(ty); break;
-                        }
-                    } else {
-                        switch (comp) {
-                            case 0: acc += tx; break;
-                            case 1: acc += ty; break;
-                            case 2: acc += fabsf(tx); break;
-                            default: acc += fabsf(ty); break;
-                        }
-                    }
-                }
-            s_vec[t] = acc;
-        }
-        __syncthreads();
-        if (warp == 0) {
-            double mag = 0;
-            for (int t = lane; t < D; t += 32) mag += (double)(s_vec[t] * s_vec[t]);
-#pragma unroll
-            for (int d = 16; d > 0; d >>= 1) mag += __shfl_xor_sync(FULL_MASK, mag, d);
-            if (lane == 0) s_scale = (float)(1. / (sqrt(mag) + DBL_EPSILON));
-        }
-        __syncthreads();
-        float *vo = A.desc + ((size_t)b * A.cap + slot) * D;
-        for (int t = tid; t < D; t += kDescThreads) vo[t] = s_vec[t] * s_scale;
-    }
-}
-
-void launch_describe(const DescribeArgs &a, cudaStream_t st, int *launches)
-{
-    static int grids[64] = {};
-    const size_t smem = (size_t)kWinSmemSide * kWinSmemSide;
-    int dev = 0;
-    cudaGetDevice(&dev);
-    int &grid = grids[dev & 63];
-    if (!grid) {
-        int sms = 148, per_sm = 4;
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        cudaFuncSetAttribute(k_describe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_describe, kDescThreads, smem);
-        if (per_sm < 1) per_sm = 1;
-        grid = sms * per_sm;  // persistent CTAs: a multiple of the SM count
-    }
-    k_describe<<<grid, kDescThreads, smem, st>>>(a);
     *launches += 1;
 }
 
