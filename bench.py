@@ -176,79 +176,36 @@ def run_ours(args):
     eng = SURF(**PARAMS, device=local, max_width=W_, max_height=H_, max_batch=B, max_keypoints=CAP)
     stream = torch.cuda.ExternalStream(eng.cuda_stream, device=dev)
     cap_total = B * CAP
-    d_matches = torch.empty((CAP * 2, 4), dtype=torch.int32, device=dev)
-    d_good = torch.empty((CAP,), dtype=torch.uint8, device=dev)
-    d_prev = torch.zeros((CAP, D), dtype=torch.float32, device=dev)
     offsets = np.zeros(B + 1, np.int32)
     launches = [0]
     kp_seen = [0]
 
-    import ctypes
-    try:
-        cudart = ctypes.CDLL("libcudart.so.12")
-    except OSError:
-        cudart = ctypes.CDLL("/usr/local/cuda/lib64/libcudart.so")
-    cudart.cudaMemcpyAsync.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_void_p]
-
-    def match_stream_device(desc_ptr, n_prev):
-        """Frame t against frame t-1, device-resident; returns the new n_prev."""
-        for b in range(B):
-            nq = int(offsets[b + 1] - offsets[b])
-            qp = desc_ptr + int(offsets[b]) * D * 4
-            if nq and n_prev:
-                eng.match_ratio_device(qp, nq, tp[0], n_prev, D, RATIO, d_matches.data_ptr(), d_good.data_ptr())
-                launches[0] += 3
-            tp[0], n_prev = qp, nq
-        # keep the last frame's descriptors for the next batch (the packed buffer is overwritten)
-        if n_prev:
-            cudart.cudaMemcpyAsync(ctypes.c_void_p(d_prev.data_ptr()), ctypes.c_void_p(tp[0]), n_prev * D * 4, 3,
-                                   ctypes.c_void_p(eng.cuda_stream))
-            tp[0] = d_prev.data_ptr()
-        return n_prev
-
-    tp = [d_prev.data_ptr()]
-
-    def step_device(i, n_prev):
+    def step_device(i, _):
         src = d_pool[(i % POOL_BATCHES) * B:(i % POOL_BATCHES + 1) * B]
         eng.submit(src.data_ptr(), MEM_DEVICE, B, W_, H_, W_, W_ * H_, True)
         eng.collect(0, 0, MEM_DEVICE, cap_total, offsets)   # waits for the counts; copies nothing
         launches[0] += eng.timings()["launches"]
         kp_seen[0] += int(offsets[B])
-        _, dptr, _ = eng.device_results()
-        return match_stream_device(dptr, n_prev)
+        eng.match_prev_device(RATIO)                         # frame t vs t-1 for the whole batch, on the device
+        launches[0] += 7
+        return 0
 
     # host-buffer API: pinned frames in, packed keypoints/descriptors/matches out
     h_kps = torch.empty((cap_total, 7), dtype=torch.float32).pin_memory()
     h_desc = torch.empty((cap_total, D), dtype=torch.float32).pin_memory()
     h_matches = torch.empty((cap_total * 2, 4), dtype=torch.int32).pin_memory()
-    d_matches_all = torch.empty((cap_total * 2, 4), dtype=torch.int32, device=dev)
-    d_good_all = torch.empty((cap_total,), dtype=torch.uint8, device=dev)
+    h_good = torch.empty((cap_total,), dtype=torch.uint8).pin_memory()
     bytes_io = {"h2d": 0, "d2h": 0}
 
-    def step_e2e(i, n_prev):
+    def step_e2e(i, _):
         src = h_pool[(i % POOL_BATCHES) * B:(i % POOL_BATCHES + 1) * B]
         eng.submit(src.data_ptr(), MEM_HOST, B, W_, H_, W_, W_ * H_, True)
         eng.collect(h_kps.data_ptr(), h_desc.data_ptr(), MEM_HOST, cap_total, offsets)
         n = int(offsets[B])
-        _, dptr, _ = eng.device_results()
-        for b in range(B):
-            nq = int(offsets[b + 1] - offsets[b])
-            qp = dptr + int(offsets[b]) * D * 4
-            if nq and n_prev:
-                eng.match_ratio_device(qp, nq, tp[0], n_prev, D, RATIO,
-                                       d_matches_all.data_ptr() + int(offsets[b]) * 2 * 16,
-                                       d_good_all.data_ptr() + int(offsets[b]))
-            tp[0], n_prev = qp, nq
-        if n_prev:
-            cudart.cudaMemcpyAsync(ctypes.c_void_p(d_prev.data_ptr()), ctypes.c_void_p(tp[0]), n_prev * D * 4, 3,
-                                   ctypes.c_void_p(eng.cuda_stream))
-            tp[0] = d_prev.data_ptr()
-        with torch.cuda.stream(stream):
-            h_matches[:2 * n].copy_(d_matches_all[:2 * n], non_blocking=True)
-        stream.synchronize()
+        eng.match_prev_to(RATIO, h_matches.data_ptr(), h_good.data_ptr(), MEM_HOST, cap_total)
         bytes_io["h2d"] = B * W_ * H_
-        bytes_io["d2h"] = n * (28 + 4 * D) + 2 * n * 16 + (B + 1) * 4
-        return n_prev
+        bytes_io["d2h"] = n * (28 + 4 * D) + 2 * n * 16 + n + (B + 1) * 4
+        return 0
 
     def barrier():
         torch.cuda.synchronize()
@@ -258,7 +215,7 @@ def run_ours(args):
 
     def timed(step_fn, steps, warmup, sample_clocks=False):
         n_prev = 0
-        tp[0] = d_prev.data_ptr()
+        eng.stream_reset()
         for i in range(warmup):
             n_prev = step_fn(i, n_prev)
         sampler = ClockSampler(local) if sample_clocks else None
@@ -302,7 +259,7 @@ def run_ours(args):
     dom_bytes = (alg["hessian"] + alg["nms"] if dom == "hessian" else alg[dom]) * B
     achieved = dom_bytes / (stage_ms[dom] * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": {"integral": "k_band_integral", "hessian": "k_hessian+k_nms",
-                                           "describe": "k_describe"}[dom],
+                                           "describe": "k_orient+k_descriptor<A..D>"}[dom],
                 "achieved": achieved, "peak": peak, "peak_source": how + " (MEASURED_PEAKS.json hbm_gbs)",
                 "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                 "algorithmic_bytes_per_launch": dom_bytes, "ms_per_launch": stage_ms[dom],

@@ -157,6 +157,23 @@ int surf_match_knn(surf_engine *e, const float *query, int n_query, const float 
 int surf_match_ratio(surf_engine *e, const float *query, int n_query, const float *train, int n_train, int dim,
                      float ratio, surf_dmatch *out, uint8_t *good, int mem);
 
+/* Live-stream matching (BASELINE config 2): every frame of the batch last submitted AND collected
+ * on this engine is matched (k = 2 + ratio test) against its predecessor -- the first frame against
+ * the last frame of the previous batch (no matches on the very first call or after
+ * surf_stream_reset).  Results are packed like the keypoints: 2 records per keypoint, row
+ * 2*(offsets[b]+i) for keypoint i of frame b, query_idx / train_idx local to their frames;
+ * good[offsets[b]+i] = ratio test.  out / good may be NULL to leave the results on the device
+ * (surf_device_matches).  One batched launch sequence, no host synchronisation inside. */
+int surf_match_prev(surf_engine *e, float ratio, surf_dmatch *out, uint8_t *good, int out_mem, long capacity);
+int surf_stream_reset(surf_engine *e);
+int surf_device_matches(surf_engine *e, const surf_dmatch **matches, const uint8_t **good);
+/* 0: tensor-core candidate search + exact rescoring (default); 1: exact CUDA-core kernel only.
+ * Both return identical results. */
+int surf_set_match_mode(surf_engine *e, int exact_only);
+/* Number of queries of the last tensor-core match call whose candidate set could not be proven and
+ * that were redone by the exact kernel (diagnostic; synchronises the engine stream). */
+int surf_match_redo_count(surf_engine *e, int *count);
+
 /* ---- row-sharded keyframe database helpers (multi-GPU, config 5) ---- */
 
 /* Merges per-rank top-k candidate lists: in is n_ranks x n_query x k records (train_idx already

@@ -19,6 +19,7 @@ UNITS = [
     ("surf_kernels.cu", ["-fmad=false"]),
     ("surf_describe.cu", ["-fmad=false"]),
     ("surf_match.cu", []),
+    ("surf_match_tc.cu", []),
     ("surf_engine.cu", []),
 ]
 

@@ -51,6 +51,24 @@ struct surf_engine {
     int *h_pin = nullptr;  // pinned: counts[B], ndel[B], off_out[B+1], misc[4]
     surf_dmatch *d_match_part = nullptr;  size_t match_part_cap = 0;
     void *d_match_io = nullptr;           size_t match_io_cap = 0;
+    int match_exact_only = 0;
+    int last_tc_ws = -1;  // workspace used by the last tensor-core match (for surf_match_redo_count)
+
+    // tensor-core matcher workspaces: [0] generic two-operand calls, [1] the frame stream ring
+    struct TcWs {
+        TcPool pool{};
+        int slots = 0, dim = 0;
+        TcCand *cand = nullptr;      size_t cand_cap = 0;
+        int *redo = nullptr;         size_t redo_cap = 0;
+        int *counters = nullptr;
+        TcSegment *segs = nullptr;   TcProblem *probs = nullptr;  int table_cap = 0;
+    } tc[2];
+    float *d_prev_desc = nullptr;    // last frame of the previous batch (fp32 rows) for exact rescoring
+    int *d_prev_off = nullptr;       // {0, n_prev}
+    int tc_prev_slot = 0;
+    bool stream_primed = false;
+    surf_dmatch *d_stream_matches = nullptr;
+    uint8_t *d_stream_good = nullptr;
 
     surf_keypoint *sorted = nullptr;  // which of d_kp_a / d_kp_b holds the current keypoints
     Pending pending;
@@ -156,6 +174,14 @@ void free_workspace(surf_engine *e)
     cudaFree(e->d_out_desc); cudaFree(e->d_patches); cudaFree(e->d_counts); cudaFree(e->d_ndel);
     cudaFree(e->d_off_in); cudaFree(e->d_off_out); cudaFree(e->d_misc); cudaFree(e->d_deleted);
     cudaFree(e->d_match_part); cudaFree(e->d_match_io); cudaFree(e->d_class_list); cudaFree(e->d_win_scratch);
+    for (auto &w : e->tc) {
+        cudaFree(w.pool.hi); cudaFree(w.pool.lo); cudaFree(w.pool.norm); cudaFree(w.pool.max_norm);
+        cudaFree(w.pool.count); cudaFree(w.cand); cudaFree(w.redo); cudaFree(w.counters); cudaFree(w.segs);
+        cudaFree(w.probs);
+        w = surf_engine::TcWs();
+    }
+    cudaFree(e->d_prev_desc); cudaFree(e->d_prev_off); cudaFree(e->d_stream_matches); cudaFree(e->d_stream_good);
+    e->d_prev_desc = nullptr; e->d_prev_off = nullptr; e->d_stream_matches = nullptr; e->d_stream_good = nullptr;
     if (e->h_pin) cudaFreeHost(e->h_pin);
     e->d_img = e->d_mask = nullptr; e->d_sum = e->d_msum = e->d_bandsum = nullptr; e->d_det = nullptr;
     e->d_kp_a = e->d_kp_b = e->d_out_kp = nullptr; e->d_desc = e->d_out_desc = nullptr; e->d_patches = nullptr;
@@ -763,6 +789,67 @@ int surf_raw_keypoints(surf_engine *e, const uint8_t *image, int width, int heig
 
 // ---- stage 5 ----
 
+// (Re)allocates the prepared-descriptor pool of a tensor-core workspace.
+static int tc_reserve(surf_engine *e, surf_engine::TcWs &w, int slots, int slot_rows, int dim)
+{
+    if (w.pool.hi && slots <= w.slots && slot_rows <= w.pool.slot_rows && dim <= w.dim) {
+        return SURF_OK;
+    }
+    CU(e, cudaStreamSynchronize(e->stream));
+    cudaFree(w.pool.hi); cudaFree(w.pool.lo); cudaFree(w.pool.norm); cudaFree(w.pool.max_norm); cudaFree(w.pool.count);
+    w.pool = TcPool();
+    if (slots < w.slots) slots = w.slots;
+    if (slot_rows < w.pool.slot_rows) slot_rows = w.pool.slot_rows;
+    if (dim < w.dim) dim = w.dim;
+    const size_t rows = (size_t)slots * slot_rows;
+    CU(e, cudaMalloc(&w.pool.hi, rows * dim * sizeof(uint16_t)));
+    CU(e, cudaMalloc(&w.pool.lo, rows * dim * sizeof(uint16_t)));
+    CU(e, cudaMalloc(&w.pool.norm, rows * sizeof(float)));
+    CU(e, cudaMalloc(&w.pool.max_norm, slots * sizeof(float)));
+    CU(e, cudaMalloc(&w.pool.count, slots * sizeof(int)));
+    CU(e, cudaMemset(w.pool.count, 0, slots * sizeof(int)));
+    CU(e, cudaMemset(w.pool.max_norm, 0, slots * sizeof(float)));
+    w.pool.slot_rows = slot_rows;
+    w.slots = slots;
+    w.dim = dim;
+    return SURF_OK;
+}
+
+static int tc_reserve_work(surf_engine *e, surf_engine::TcWs &w, int n_probs, int splits, int max_q, int n_segs)
+{
+    const size_t need = (size_t)n_probs * splits * max_q;
+    if (need > w.cand_cap) {
+        CU(e, cudaStreamSynchronize(e->stream));
+        cudaFree(w.cand);
+        w.cand = nullptr;
+        w.cand_cap = 0;
+        CU(e, cudaMalloc(&w.cand, need * sizeof(TcCand)));
+        w.cand_cap = need;
+    }
+    const size_t need_redo = (size_t)n_probs * max_q;
+    if (need_redo > w.redo_cap) {
+        CU(e, cudaStreamSynchronize(e->stream));
+        cudaFree(w.redo);
+        w.redo = nullptr;
+        w.redo_cap = 0;
+        CU(e, cudaMalloc(&w.redo, need_redo * 2 * sizeof(int)));
+        w.redo_cap = need_redo;
+    }
+    if (!w.counters) CU(e, cudaMalloc(&w.counters, 4 * sizeof(int)));
+    const int tab = n_probs > n_segs ? n_probs : n_segs;
+    if (tab > w.table_cap) {
+        CU(e, cudaStreamSynchronize(e->stream));
+        cudaFree(w.segs);
+        cudaFree(w.probs);
+        w.segs = nullptr;
+        w.probs = nullptr;
+        CU(e, cudaMalloc(&w.segs, tab * sizeof(TcSegment)));
+        CU(e, cudaMalloc(&w.probs, tab * sizeof(TcProblem)));
+        w.table_cap = tab;
+    }
+    return SURF_OK;
+}
+
 static int match_common(surf_engine *e, const float *query, int n_query, const float *train, int n_train, int dim, int k,
                         float ratio, surf_dmatch *out, uint8_t *good, int mem)
 {
@@ -802,16 +889,43 @@ static int match_common(surf_engine *e, const float *query, int n_query, const f
         dq = q2;
         dt = t2;
     }
-    const size_t need_part = match_scratch_records(n_query, n_train > 0 ? n_train : 1, k);
-    if (need_part > e->match_part_cap) {
-        cudaFree(e->d_match_part);
-        e->d_match_part = nullptr;
-        e->match_part_cap = 0;
-        CU(e, cudaMalloc(&e->d_match_part, need_part * sizeof(surf_dmatch)));
-        e->match_part_cap = need_part;
+    if (e->match_exact_only || n_train == 0) {
+        const size_t need_part = match_scratch_records(n_query, n_train > 0 ? n_train : 1, k);
+        if (need_part > e->match_part_cap) {
+            cudaFree(e->d_match_part);
+            e->d_match_part = nullptr;
+            e->match_part_cap = 0;
+            CU(e, cudaMalloc(&e->d_match_part, need_part * sizeof(surf_dmatch)));
+            e->match_part_cap = need_part;
+        }
+        launch_match_knn(dq, n_query, dt, n_train, dim, k, dout, 0, e->d_match_part, e->stream, &e->launches);
+        if (good) launch_ratio_test(dout, n_query, ratio, dgood, e->stream, &e->launches);
+    } else {
+        // tensor-core candidate search + exact rescoring: slot 0 = queries, slot 1 = train rows
+        const int rows = ((n_query > n_train ? n_query : n_train) + 255) & ~255;
+        int rc2 = tc_reserve(e, e->tc[0], 2, rows, dim);
+        if (rc2) return rc2;
+        surf_engine::TcWs &w = e->tc[0];
+        const int max_q = (n_query + 127) & ~127;
+        int sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, e->device);
+        const int n_tiles = (n_train + 255) / 256, mt = max_q / 128;
+        int splits = (2 * sms + mt - 1) / mt;
+        if (splits > n_tiles) splits = n_tiles;
+        if (splits < 1) splits = 1;
+        if ((rc2 = tc_reserve_work(e, w, 1, splits, max_q, 2))) return rc2;
+        TcSegment segs[2] = {{dq, nullptr, 0, n_query, 0}, {dt, nullptr, 0, n_train, 1}};
+        TcProblem pr{};
+        pr.q_slot = 0; pr.t_slot = 1; pr.qsrc = dq; pr.tsrc = dt;
+        CU(e, cudaMemcpyAsync(w.segs, segs, sizeof(segs), cudaMemcpyHostToDevice, e->stream));
+        CU(e, cudaMemcpyAsync(w.probs, &pr, sizeof(pr), cudaMemcpyHostToDevice, e->stream));
+        TcMatchArgs a{};
+        a.pool = w.pool; a.segs = w.segs; a.n_segs = 2; a.probs = w.probs; a.n_probs = 1; a.n_splits = splits;
+        a.max_q_rows = max_q; a.cand = w.cand; a.counters = w.counters; a.redo_list = w.redo; a.dim = dim; a.k = k;
+        a.ratio = ratio; a.out = dout; a.good = good ? dgood : nullptr;
+        launch_tc_match(a, e->stream, &e->launches);
+        e->last_tc_ws = 0;
     }
-    launch_match_knn(dq, n_query, dt, n_train, dim, k, dout, 0, e->d_match_part, e->stream, &e->launches);
-    if (good) launch_ratio_test(dout, n_query, ratio, dgood, e->stream, &e->launches);
     CU(e, cudaGetLastError());
     if (mem == SURF_MEM_HOST) {
         CU(e, cudaMemcpyAsync(out, dout, sizeof(surf_dmatch) * (size_t)k * n_query, cudaMemcpyDeviceToHost, e->stream));
@@ -832,6 +946,113 @@ int surf_match_ratio(surf_engine *e, const float *query, int n_query, const floa
 {
     if (e && !good) return fail(e, SURF_ERR_BAD_ARG, "good is null");
     return match_common(e, query, n_query, train, n_train, dim, 2, ratio, out, good, mem);
+}
+
+int surf_set_match_mode(surf_engine *e, int exact_only)
+{
+    if (!e) return SURF_ERR_BAD_ARG;
+    e->match_exact_only = exact_only ? 1 : 0;
+    return SURF_OK;
+}
+
+int surf_match_redo_count(surf_engine *e, int *count)
+{
+    if (!e || !count) return SURF_ERR_BAD_ARG;
+    *count = 0;
+    if (e->last_tc_ws < 0 || !e->tc[e->last_tc_ws].counters) return SURF_OK;
+    int rc = ensure_device(e);
+    if (rc) return rc;
+    CU(e, cudaStreamSynchronize(e->stream));
+    CU(e, cudaMemcpy(count, e->tc[e->last_tc_ws].counters + 1, sizeof(int), cudaMemcpyDeviceToHost));
+    return SURF_OK;
+}
+
+int surf_stream_reset(surf_engine *e)
+{
+    if (!e) return SURF_ERR_BAD_ARG;
+    int rc = ensure_device(e);
+    if (rc) return rc;
+    e->stream_primed = false;
+    return SURF_OK;
+}
+
+int surf_device_matches(surf_engine *e, const surf_dmatch **matches, const uint8_t **good)
+{
+    if (!e) return SURF_ERR_BAD_ARG;
+    if (matches) *matches = e->d_stream_matches;
+    if (good) *good = e->d_stream_good;
+    return SURF_OK;
+}
+
+int surf_match_prev(surf_engine *e, float ratio, surf_dmatch *out, uint8_t *good, int out_mem, long capacity)
+{
+    if (!e) return SURF_ERR_BAD_ARG;
+    if (!e->pending.active || !e->pending.want_desc)
+        return fail(e, SURF_ERR_BAD_ARG, "surf_match_prev needs a submitted and collected batch with descriptors");
+    int rc = ensure_device(e);
+    if (rc) return rc;
+    const int B = e->pending.batch, D = e->params.extended ? 128 : 64;
+    const int slots = e->max_b + 1, rows = (e->cap + 255) & ~255;
+    surf_engine::TcWs &w = e->tc[1];
+    if ((rc = tc_reserve(e, w, slots, rows, D))) return rc;
+    if ((rc = tc_reserve_work(e, w, e->max_b, 1, rows, e->max_b))) return rc;
+    const size_t nk = (size_t)e->max_b * e->cap;
+    if (!e->d_prev_desc) {
+        CU(e, cudaMalloc(&e->d_prev_desc, (size_t)e->cap * 128 * sizeof(float)));
+        CU(e, cudaMalloc(&e->d_prev_off, 2 * sizeof(int)));
+        CU(e, cudaMalloc(&e->d_stream_matches, nk * 2 * sizeof(surf_dmatch)));
+        CU(e, cudaMalloc(&e->d_stream_good, nk));
+    }
+    if (!e->stream_primed) {  // forget the previous frame: an empty predecessor slot
+        CU(e, cudaMemsetAsync(w.pool.count + e->tc_prev_slot, 0, sizeof(int), e->stream));
+        CU(e, cudaMemsetAsync(e->d_prev_off, 0, 2 * sizeof(int), e->stream));
+    }
+    std::vector<TcSegment> segs(B);
+    std::vector<TcProblem> probs(B);
+    int prev = e->tc_prev_slot;
+    for (int i = 0; i < B; i++) {
+        const int slot = (e->tc_prev_slot + 1 + i) % slots;
+        segs[i] = TcSegment{e->d_out_desc, e->d_off_out + i, 0, 0, slot};
+        TcProblem p{};
+        p.q_slot = slot;
+        p.t_slot = prev;
+        p.qsrc = e->d_out_desc;
+        p.q_off = e->d_off_out + i;
+        p.tsrc = i == 0 ? e->d_prev_desc : e->d_out_desc;
+        p.t_off = i == 0 ? e->d_prev_off : e->d_off_out + i - 1;
+        p.out_off = e->d_off_out + i;
+        probs[i] = p;
+        prev = slot;
+    }
+    CU(e, cudaMemcpyAsync(w.segs, segs.data(), sizeof(TcSegment) * B, cudaMemcpyHostToDevice, e->stream));
+    CU(e, cudaMemcpyAsync(w.probs, probs.data(), sizeof(TcProblem) * B, cudaMemcpyHostToDevice, e->stream));
+    TcMatchArgs a{};
+    a.pool = w.pool; a.segs = w.segs; a.n_segs = B; a.probs = w.probs; a.n_probs = B; a.n_splits = 1;
+    a.max_q_rows = rows; a.cand = w.cand; a.counters = w.counters; a.redo_list = w.redo; a.dim = D; a.k = 2;
+    a.ratio = ratio; a.out = e->d_stream_matches; a.good = e->d_stream_good;
+    int launches = 0;
+    launch_tc_match(a, e->stream, &launches);
+    e->last_tc_ws = 1;
+    // keep the last frame (fp32 rows + its slot) as the next batch's predecessor
+    launch_copy_rows(e->d_out_desc, e->d_off_out + B - 1, D, e->d_prev_desc, e->cap, e->d_prev_off, e->stream, &launches);
+    e->launches = launches;
+    e->timings.launches = launches;
+    CU(e, cudaGetLastError());
+    e->tc_prev_slot = prev;
+    e->stream_primed = true;
+    const long total = e->h_pin[2 * B + B];  // offsets[B] fetched by surf_collect_batch
+    if (out || good) {
+        if (total > capacity) {
+            e->required = total;
+            return fail(e, SURF_ERR_CAPACITY, "%ld keypoints in the batch; the match arrays hold %ld", total, capacity);
+        }
+        const cudaMemcpyKind kind = out_mem == SURF_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+        if (out && total)
+            CU(e, cudaMemcpyAsync(out, e->d_stream_matches, sizeof(surf_dmatch) * 2 * total, kind, e->stream));
+        if (good && total) CU(e, cudaMemcpyAsync(good, e->d_stream_good, total, kind, e->stream));
+        CU(e, cudaStreamSynchronize(e->stream));
+    }
+    return SURF_OK;
 }
 
 int surf_merge_topk(surf_engine *e, const surf_dmatch *in, int n_ranks, int n_query, int k, surf_dmatch *out)

@@ -109,6 +109,64 @@ void launch_pack(const surf_keypoint *kps, const float *desc, int D, int cap, in
                  float *out_desc, cudaStream_t st, int *launches);
 void upload_tables();  // orientation sample weights + descriptor Gaussian -> __constant__ (per device)
 
+// ---- tensor-core candidate search (surf_match_tc.cu) ----
+constexpr int kCand = 8;  // approximate candidates kept per query and train split
+
+struct TcCand {
+    float d[kCand];  // approximate |t|^2 - 2 q.t, ascending
+    int i[kCand];    // train row within its slot, -1 = empty
+};
+
+// Descriptor rows prepared for the tensor cores: BF16 hi / lo parts in the UMMA canonical K-major
+// layout, one slot per frame (or per operand), slot_rows rows each (multiple of 256).
+struct TcPool {
+    uint16_t *hi, *lo;
+    float *norm;      // [slots][slot_rows] |row|^2 (INF for padding rows)
+    float *max_norm;  // [slots]
+    int *count;       // [slots] live rows
+    int slot_rows;
+};
+
+// Rows [off[0], off[1]) of `src` (or [row0, row0 + n) when off is null) go to `slot`.
+struct TcSegment {
+    const float *src;
+    const int *off;
+    int row0, n;
+    int slot;
+};
+
+// One knnMatch: queries = slot q_slot, train = slot t_slot; fp32 rows for the exact rescoring at
+// qsrc + (q_off ? q_off[0] : q_row0) * D (same for train); results at out + (out_off ? ... ) * k.
+struct TcProblem {
+    int q_slot, t_slot;
+    const float *qsrc, *tsrc;
+    const int *q_off, *t_off, *out_off;
+    int q_row0, t_row0, out_row0;
+};
+
+struct TcMatchArgs {
+    TcPool pool;
+    const TcSegment *segs;  // device
+    int n_segs;
+    const TcProblem *probs;  // device
+    int n_probs;
+    int n_splits;
+    int max_q_rows;   // upper bound on queries per problem (multiple of 128)
+    TcCand *cand;     // [n_probs][n_splits][max_q_rows]
+    int *counters;    // [0] work-queue head, [1] redo count
+    int *redo_list;   // 2 ints per entry
+    int dim, k;
+    float ratio;
+    surf_dmatch *out;
+    uint8_t *good;    // optional
+};
+
+size_t tc_candidates_smem(int dim);
+void launch_tc_match(const TcMatchArgs &a, cudaStream_t st, int *launches);
+// copies rows [off[0], off[1]) of src (D floats each) to dst and writes {0, n} to dst_off (device-side count)
+void launch_copy_rows(const float *src, const int *off, int dim, float *dst, int max_rows, int *dst_off, cudaStream_t st,
+                      int *launches);
+
 // ---- launchers (surf_match.cu) ----
 size_t match_scratch_records(int nq, int nt, int k);  // partial top-k records launch_match_knn needs
 void launch_match_knn(const float *q, int nq, const float *t, int nt, int dim, int k, surf_dmatch *out, int train_base,

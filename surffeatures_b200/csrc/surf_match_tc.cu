@@ -1,0 +1,582 @@
+// surf_match_tc.cu -- stage 5 on the 5th-generation tensor cores: candidate search for
+// BFMatcher(NORM_L2)::knnMatch (SurfFeatures/Logic/vtkSlicerSurfFeaturesLogic.cxx:640).
+//
+// The one dense contraction of the path is S = Q * T^T.  It runs as tcgen05.mma (kind::f16, BF16
+// operands, FP32 accumulators in TMEM) with a hi/lo BF16 split of the fp32 descriptors
+// (q.t ~ qh.th + qh.tl + ql.th), so the approximate squared distance |t|^2 - 2 q.t is good to ~1e-5.
+// It is used ONLY to pick kCand candidates per query; the reported distances and the final order
+// come from exact fp32 rescoring of those candidates (same arithmetic as the exact kernel in
+// surf_match.cu), and a per-query margin test proves the candidates contain the true top-k;
+// queries that fail the test are redone by the exact kernel, so results equal the exact path.
+//
+//   k_tc_prep        fp32 rows -> BF16 hi / lo in the UMMA canonical K-major layout + |row|^2
+//   k_tc_candidates  128 x 256 output tiles: operands copied to shared memory, one elected thread
+//                    issues tcgen05.mma, accumulators read back with tcgen05.ld, per-row running
+//                    top-kCand kept in registers across the train tiles
+//   k_tc_rescore     exact fp32 distances of the candidates, top-k, margin test
+#include <cuda_bf16.h>
+
+#include <cfloat>
+
+#include "surf_internal.h"
+
+namespace surfb200 {
+
+constexpr int kTM = 128;  // queries per tile  (UMMA M)
+constexpr int kTN = 256;  // train rows per tile (UMMA N)
+constexpr uint32_t kTmemCols = 256;
+
+// ------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+
+// Bounded wait: a barrier that never completes traps instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    uint32_t done = 0;
+    for (uint32_t spin = 0; !done; spin++) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (spin > (1u << 26)) __trap();
+    }
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t cols)
+{
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols)
+{
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// D[tmem] (+)= A[smem] * B[smem]^T, BF16 x BF16 -> FP32, issued by one thread for the CTA.
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+__device__ __forceinline__ void umma_commit(uint32_t bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+// 32 consecutive fp32 columns of this thread's TMEM lane.
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32])
+{
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; i++) v[i] = __uint_as_float(r[i]);
+}
+
+// Shared-memory matrix descriptor, K-major, no swizzle (canonical layout ((8,m),(8,2k)) with 16-byte
+// rows inside an 8 x 16 B core matrix): LBO = byte step between the two core matrices along K,
+// SBO = byte step between 8-row groups.  Bits 46-47 = 1 is the sm_100 descriptor version.
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo)
+{
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+    d |= (uint64_t)((lbo >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;
+    return d;
+}
+
+// Instruction descriptor for kind::f16: D = F32, A = B = BF16, both K-major, M x N tile.
+__host__ __device__ constexpr uint32_t umma_idesc(int M, int N)
+{
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K5a: prep.  Row r, element k of a slot lives at bf16 index ((r/8)*(D/8) + k/8)*64 + (r%8)*8 + k%8,
+// so any 8-aligned block of rows is one contiguous run of core matrices.
+// ------------------------------------------------------------------------------------------------
+template <int D>
+__global__ void __launch_bounds__(256) k_tc_prep(const TcSegment *__restrict__ segs, int n_segs, TcPool pool)
+{
+    constexpr int G = D / 8;  // 8-element groups per row
+    const int seg = blockIdx.y;
+    if (seg >= n_segs) return;
+    const TcSegment sg = segs[seg];
+    const float *src = sg.src;
+    const int n = min(sg.off ? sg.off[1] - sg.off[0] : sg.n, pool.slot_rows);
+    const int src_row0 = sg.off ? sg.off[0] : sg.row0;
+    const int npad = min((n + kTN - 1) / kTN * kTN, pool.slot_rows);
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int r = t / G, g = t - r * G;
+    if (t == 0) pool.count[sg.slot] = n;
+    if (r >= npad) return;  // npad is a multiple of 256 rows: whole blocks leave together
+    float v[8];
+    if (r < n) {
+        const float4 *p = reinterpret_cast<const float4 *>(src + (size_t)(src_row0 + r) * D + g * 8);
+        const float4 a = __ldg(p), b = __ldg(p + 1);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    } else {
+#pragma unroll
+        for (int k = 0; k < 8; k++) v[k] = 0.f;
+    }
+    uint32_t hi[4], lo[4];
+    float nrm = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; k += 2) {
+        const __nv_bfloat16 h0 = __float2bfloat16_rn(v[k]), h1 = __float2bfloat16_rn(v[k + 1]);
+        const __nv_bfloat16 l0 = __float2bfloat16_rn(v[k] - __bfloat162float(h0));
+        const __nv_bfloat16 l1 = __float2bfloat16_rn(v[k + 1] - __bfloat162float(h1));
+        hi[k / 2] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+        lo[k / 2] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+        nrm = fmaf(v[k], v[k], nrm);
+        nrm = fmaf(v[k + 1], v[k + 1], nrm);
+    }
+#pragma unroll
+    for (int d = G / 2; d > 0; d >>= 1) nrm += __shfl_xor_sync(0xffffffffu, nrm, d);
+    const size_t slot_base = (size_t)sg.slot * pool.slot_rows;
+    const size_t e = (slot_base + (size_t)(r & ~7)) * D + (size_t)g * 64 + (size_t)(r & 7) * 8;
+    *reinterpret_cast<uint4 *>(pool.hi + e) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    *reinterpret_cast<uint4 *>(pool.lo + e) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    if (g == 0) {
+        pool.norm[slot_base + r] = r < n ? nrm : INFINITY;
+        if (r < n) atomicMax(reinterpret_cast<int *>(pool.max_norm + sg.slot), __float_as_int(nrm));
+    }
+}
+
+__global__ void k_tc_reset(TcPool pool, const TcSegment *__restrict__ segs, int n_segs)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_segs) pool.max_norm[segs[i].slot] = 0.f;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K5b: candidates.
+// ------------------------------------------------------------------------------------------------
+struct Cand {
+    float d[kCand];
+    int i[kCand];
+};
+
+__device__ __forceinline__ void cand_insert(Cand &c, float dist, int idx)
+{
+    // strictly smaller than the current worst: ties keep the earlier (lower) train index
+    c.d[kCand - 1] = dist;
+    c.i[kCand - 1] = idx;
+#pragma unroll
+    for (int r = kCand - 1; r > 0; r--) {
+        if (c.d[r] < c.d[r - 1]) {
+            const float td = c.d[r]; c.d[r] = c.d[r - 1]; c.d[r - 1] = td;
+            const int ti = c.i[r]; c.i[r] = c.i[r - 1]; c.i[r - 1] = ti;
+        }
+    }
+}
+
+template <int D>
+__global__ void __launch_bounds__(128) k_tc_candidates(TcPool pool, const TcProblem *__restrict__ probs, int n_probs,
+                                                       int mt_per_prob, int n_splits, int cand_stride,
+                                                       TcCand *__restrict__ cand_out, int *__restrict__ work_head)
+{
+    constexpr int KSTEPS = D / 16;
+    constexpr uint32_t SBO = (D / 8) * 128;        // bytes between 8-row groups
+    constexpr uint32_t A_BYTES = kTM * D * 2;      // one of hi / lo
+    constexpr uint32_t B_BYTES = kTN * D * 2;
+    extern __shared__ __align__(1024) unsigned char sm[];
+    unsigned char *sA_hi = sm, *sA_lo = sm + A_BYTES;
+    unsigned char *sB_hi = sm + 2 * A_BYTES, *sB_lo = sB_hi + B_BYTES;
+    float *sTn = reinterpret_cast<float *>(sB_lo + B_BYTES);  // |t|^2 of the current train tile
+    __shared__ __align__(8) uint64_t s_bar;
+    __shared__ uint32_t s_tmem;
+    __shared__ int s_item;
+
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const uint32_t bar = smem_u32(&s_bar);
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    if (warp == 0) tmem_alloc(smem_u32(&s_tmem), kTmemCols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = s_tmem;
+    const uint32_t idesc = umma_idesc(kTM, kTN);
+    uint32_t phase = 0;
+    const int total_items = n_probs * mt_per_prob * n_splits;
+
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) s_item = atomicAdd(work_head, 1);
+        __syncthreads();
+        const int item = s_item;
+        if (item >= total_items) break;
+        const int p = item / (mt_per_prob * n_splits);
+        const int rem = item - p * (mt_per_prob * n_splits);
+        const int mt = rem / n_splits, split = rem - mt * n_splits;
+        const TcProblem pr = probs[p];
+        const int nq = pool.count[pr.q_slot], nt = pool.count[pr.t_slot];
+        const int q0 = mt * kTM;
+        if (q0 >= nq) continue;
+        // train tiles of this split
+        const int n_tiles = (nt + kTN - 1) / kTN;
+        const int per = (n_tiles + n_splits - 1) / n_splits;
+        const int tile0 = split * per, tile1 = min(n_tiles, tile0 + per);
+
+        // ---- query tile (hi, lo): contiguous run of core matrices ----
+        {
+            const size_t e0 = ((size_t)pr.q_slot * pool.slot_rows + q0) * D;
+            const uint4 *gh = reinterpret_cast<const uint4 *>(pool.hi + e0);
+            const uint4 *gl = reinterpret_cast<const uint4 *>(pool.lo + e0);
+            uint4 *dh = reinterpret_cast<uint4 *>(sA_hi), *dl = reinterpret_cast<uint4 *>(sA_lo);
+            for (int k = tid; k < (int)(A_BYTES / 16); k += 128) {
+                dh[k] = __ldg(gh + k);
+                dl[k] = __ldg(gl + k);
+            }
+        }
+        Cand best;
+#pragma unroll
+        for (int r = 0; r < kCand; r++) {
+            best.d[r] = INFINITY;
+            best.i[r] = -1;
+        }
+
+        for (int tile = tile0; tile < tile1; tile++) {
+            const int t0 = tile * kTN;
+            // ---- train tile (hi, lo, norms) ----
+            {
+                const size_t row0 = (size_t)pr.t_slot * pool.slot_rows + t0;
+                const uint4 *gh = reinterpret_cast<const uint4 *>(pool.hi + row0 * D);
+                const uint4 *gl = reinterpret_cast<const uint4 *>(pool.lo + row0 * D);
+                uint4 *dh = reinterpret_cast<uint4 *>(sB_hi), *dl = reinterpret_cast<uint4 *>(sB_lo);
+                for (int k = tid; k < (int)(B_BYTES / 16); k += 128) {
+                    dh[k] = __ldg(gh + k);
+                    dl[k] = __ldg(gl + k);
+                }
+                for (int k = tid; k < kTN; k += 128) sTn[k] = pool.norm[row0 + k];
+            }
+            fence_async_smem();  // generic-proxy stores -> visible to the tensor core's async proxy
+            tc_fence_before();
+            __syncthreads();
+            if (tid == 0) {
+                tc_fence_after();
+                const uint32_t a_hi = smem_u32(sA_hi), a_lo = smem_u32(sA_lo);
+                const uint32_t b_hi = smem_u32(sB_hi), b_lo = smem_u32(sB_lo);
+#pragma unroll
+                for (int ks = 0; ks < KSTEPS; ks++) {
+                    const uint32_t ko = ks * 256;  // two core matrices (16 K-elements) per step
+                    umma_bf16(tmem, umma_desc(a_hi + ko, 128, SBO), umma_desc(b_hi + ko, 128, SBO), idesc, ks > 0);
+                }
+#pragma unroll
+                for (int ks = 0; ks < KSTEPS; ks++) {
+                    const uint32_t ko = ks * 256;
+                    umma_bf16(tmem, umma_desc(a_hi + ko, 128, SBO), umma_desc(b_lo + ko, 128, SBO), idesc, 1);
+                    umma_bf16(tmem, umma_desc(a_lo + ko, 128, SBO), umma_desc(b_hi + ko, 128, SBO), idesc, 1);
+                }
+                umma_commit(bar);
+            }
+            mbar_wait(bar, phase);
+            phase ^= 1;
+            tc_fence_after();
+
+            // ---- epilogue: thread = query row = TMEM lane ----
+            const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);
+            const int lim = min(kTN, nt - t0);
+#pragma unroll 1
+            for (int c0 = 0; c0 < kTN; c0 += 32) {
+                float v[32];
+                tmem_ld32(lane_addr + c0, v);
+                if (c0 < lim) {
+#pragma unroll
+                    for (int c = 0; c < 32; c++) {
+                        const float dist = fmaf(-2.f, v[c], sTn[c0 + c]);  // |t|^2 - 2 q.t  (+ |q|^2 later)
+                        if (dist < best.d[kCand - 1]) cand_insert(best, dist, t0 + c0 + c);
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncthreads();  // TMEM and the train tile are free for the next iteration
+        }
+        if (q0 + tid < nq) {
+            TcCand o;
+#pragma unroll
+            for (int r = 0; r < kCand; r++) {
+                o.d[r] = best.d[r];
+                o.i[r] = best.i[r];
+            }
+            cand_out[((size_t)p * n_splits + split) * cand_stride + q0 + tid] = o;
+        }
+    }
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, kTmemCols);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K5c: exact rescoring of the candidates, top-k, margin test.  kCand lanes per query.
+// ------------------------------------------------------------------------------------------------
+template <int D>
+__global__ void __launch_bounds__(256) k_tc_rescore(TcPool pool, const TcProblem *__restrict__ probs, int n_splits,
+                                                    int cand_stride, const TcCand *__restrict__ cand, int k, float ratio,
+                                                    surf_dmatch *__restrict__ out, uint8_t *__restrict__ good,
+                                                    int *__restrict__ redo_list, int *__restrict__ redo_count)
+{
+    const int p = blockIdx.y;
+    const TcProblem pr = probs[p];
+    const int nq = pool.count[pr.q_slot], nt = pool.count[pr.t_slot];
+    const int gq = (blockIdx.x * blockDim.x + threadIdx.x) / kCand;
+    const int lane_c = threadIdx.x % kCand;
+    if (gq >= nq) return;  // kCand divides the warp: a query's lanes leave together
+    const int q_row0 = pr.q_off ? pr.q_off[0] : pr.q_row0;
+    const int t_row0 = pr.t_off ? pr.t_off[0] : pr.t_row0;
+    const int out_row0 = pr.out_off ? pr.out_off[0] : pr.out_row0;
+    const float *qsrc = pr.qsrc, *tsrc = pr.tsrc;
+    const float *qv = qsrc + (size_t)(q_row0 + gq) * D;
+    const unsigned gmask = ((1u << kCand) - 1u) << ((threadIdx.x & 31) / kCand * kCand);
+
+    // best k over all splits' candidates, by exact distance; each lane owns candidate slot lane_c
+    float bd[4] = {INFINITY, INFINITY, INFINITY, INFINITY};
+    int bi[4] = {-1, -1, -1, -1};
+    float worst_kept = INFINITY;  // smallest "kCand-th approximate value" over the splits
+    for (int s = 0; s < n_splits; s++) {
+        const TcCand &c = cand[((size_t)p * n_splits + s) * cand_stride + gq];
+        const int idx = c.i[lane_c];
+        float dist = INFINITY;
+        if (idx >= 0) {
+            const float *tv = tsrc + (size_t)(t_row0 + idx) * D;
+            float acc = 0.f;
+#pragma unroll 8
+            for (int d = 0; d < D; d++) {
+                const float df = qv[d] - tv[d];
+                acc = fmaf(df, df, acc);  // same order as k_match_exact
+            }
+            dist = acc;
+        }
+        // a split whose list is full bounds every train row it did not keep
+        const float last = c.d[kCand - 1];
+        if (c.i[kCand - 1] >= 0) worst_kept = fminf(worst_kept, last);
+        // merge this split's kCand exact distances into the running top-4 (all lanes keep a copy)
+#pragma unroll
+        for (int r = 0; r < kCand; r++) {
+            const float od = __shfl_sync(gmask, dist, (threadIdx.x & 31) / kCand * kCand + r);
+            const int oi = __shfl_sync(gmask, idx, (threadIdx.x & 31) / kCand * kCand + r);
+            if (oi < 0) continue;
+            if (od < bd[3] || (od == bd[3] && (unsigned)oi < (unsigned)bi[3])) {
+                bd[3] = od;
+                bi[3] = oi;
+#pragma unroll
+                for (int j = 3; j > 0; j--) {
+                    const bool sw = bd[j] < bd[j - 1] || (bd[j] == bd[j - 1] && (unsigned)bi[j] < (unsigned)bi[j - 1]);
+                    if (sw) {
+                        const float td = bd[j]; bd[j] = bd[j - 1]; bd[j - 1] = td;
+                        const int ti = bi[j]; bi[j] = bi[j - 1]; bi[j - 1] = ti;
+                    }
+                }
+            }
+        }
+    }
+    if (lane_c != 0) return;
+    // margin test: every train row outside the candidate lists has approximate value >= worst_kept,
+    // hence exact squared distance >= |q|^2 + worst_kept - eps.  If that clears the k-th best exact
+    // distance, the top-k is proven; otherwise the exact kernel redoes this query.
+    const float qn = pool.norm[(size_t)pr.q_slot * pool.slot_rows + gq];
+    const float tn_max = pool.max_norm[pr.t_slot];
+    const float eps = 1.0e-4f * sqrtf(qn * tn_max) + 4.0e-6f * (qn + tn_max) + 1e-30f;
+    const int kk = min(k, nt);
+    bool proven = true;
+    if (worst_kept < INFINITY && kk > 0) proven = (qn + worst_kept - eps) > bd[kk - 1];
+    surf_dmatch *o = out + ((size_t)out_row0 + gq) * k;
+    for (int r = 0; r < k; r++) {
+        o[r].query_idx = gq;
+        o[r].train_idx = bi[r];
+        o[r].img_idx = bi[r] < 0 ? -1 : 0;
+        o[r].distance = sqrtf(bd[r]);
+    }
+    if (good && k >= 2)
+        good[out_row0 + gq] = (bi[0] >= 0 && bi[1] >= 0 && sqrtf(bd[0]) < ratio * sqrtf(bd[1])) ? 1 : 0;
+    if (!proven) {
+        const int pos = atomicAdd(redo_count, 1);
+        redo_list[2 * pos] = p;
+        redo_list[2 * pos + 1] = gq;
+    }
+}
+
+// Exact redo of the (rare) queries whose candidate set could not be proven: one warp per query.
+template <int D>
+__global__ void __launch_bounds__(256) k_tc_redo(TcPool pool, const TcProblem *__restrict__ probs, int k, float ratio,
+                                                 surf_dmatch *__restrict__ out, uint8_t *__restrict__ good,
+                                                 const int *__restrict__ redo_list, const int *__restrict__ redo_count)
+{
+    const int lane = threadIdx.x & 31;
+    const int n = *redo_count;
+    for (int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < n; w += (gridDim.x * blockDim.x) >> 5) {
+        const int p = redo_list[2 * w], gq = redo_list[2 * w + 1];
+        const TcProblem pr = probs[p];
+        const int nt = pool.count[pr.t_slot];
+        const int q_row0 = pr.q_off ? pr.q_off[0] : pr.q_row0;
+        const int t_row0 = pr.t_off ? pr.t_off[0] : pr.t_row0;
+        const int out_row0 = pr.out_off ? pr.out_off[0] : pr.out_row0;
+        const float *qsrc = pr.qsrc, *tsrc = pr.tsrc;
+        const float *qv = qsrc + (size_t)(q_row0 + gq) * D;
+        float bd[4] = {INFINITY, INFINITY, INFINITY, INFINITY};
+        int bi[4] = {-1, -1, -1, -1};
+        for (int t = lane; t < nt; t += 32) {
+            const float *tv = tsrc + (size_t)(t_row0 + t) * D;
+            float acc = 0.f;
+#pragma unroll 8
+            for (int d = 0; d < D; d++) {
+                const float df = qv[d] - tv[d];
+                acc = fmaf(df, df, acc);
+            }
+            if (acc < bd[3]) {  // increasing t within a lane: ties keep the lower index
+                bd[3] = acc;
+                bi[3] = t;
+#pragma unroll
+                for (int j = 3; j > 0; j--)
+                    if (bd[j] < bd[j - 1]) {
+                        const float td = bd[j]; bd[j] = bd[j - 1]; bd[j - 1] = td;
+                        const int ti = bi[j]; bi[j] = bi[j - 1]; bi[j - 1] = ti;
+                    }
+            }
+        }
+        // warp merge of 32 sorted lists: k rounds of arg-min over the list heads
+        surf_dmatch *o = out + ((size_t)out_row0 + gq) * k;
+        float d0 = INFINITY, d1 = INFINITY;
+        int i0 = -1, i1 = -1;
+        for (int r = 0; r < k; r++) {
+            float hd = bd[0];
+            int hi = bi[0];
+            int src = lane;
+#pragma unroll
+            for (int s = 16; s > 0; s >>= 1) {
+                const float od = __shfl_xor_sync(0xffffffffu, hd, s);
+                const int oi = __shfl_xor_sync(0xffffffffu, hi, s);
+                const int os = __shfl_xor_sync(0xffffffffu, src, s);
+                const bool take = (oi >= 0) && (hi < 0 || od < hd || (od == hd && oi < hi));
+                if (take) { hd = od; hi = oi; src = os; }
+            }
+            if (lane == src && hi >= 0) {  // pop the winner's head
+                bd[0] = bd[1]; bi[0] = bi[1]; bd[1] = bd[2]; bi[1] = bi[2]; bd[2] = bd[3]; bi[2] = bi[3];
+                bd[3] = INFINITY; bi[3] = -1;
+            }
+            if (lane == 0) {
+                o[r].query_idx = gq;
+                o[r].train_idx = hi;
+                o[r].img_idx = hi < 0 ? -1 : 0;
+                o[r].distance = sqrtf(hd);
+            }
+            if (r == 0) { d0 = hd; i0 = hi; }
+            if (r == 1) { d1 = hd; i1 = hi; }
+        }
+        if (lane == 0 && good && k >= 2)
+            good[out_row0 + gq] = (i0 >= 0 && i1 >= 0 && sqrtf(d0) < ratio * sqrtf(d1)) ? 1 : 0;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+size_t tc_candidates_smem(int dim) { return (size_t)(2 * kTM + 2 * kTN) * dim * 2 + kTN * sizeof(float) + 1024; }
+
+void launch_tc_match(const TcMatchArgs &a, cudaStream_t st, int *launches)
+{
+    const int D = a.dim;
+    // ---- prep every segment (rows -> bf16 hi/lo tiles + norms) ----
+    k_tc_reset<<<(a.n_segs + 127) / 128, 128, 0, st>>>(a.pool, a.segs, a.n_segs);
+    const int G = D / 8;
+    dim3 gprep(((size_t)a.pool.slot_rows * G + 255) / 256, a.n_segs);
+    if (D == 64) k_tc_prep<64><<<gprep, 256, 0, st>>>(a.segs, a.n_segs, a.pool);
+    else k_tc_prep<128><<<gprep, 256, 0, st>>>(a.segs, a.n_segs, a.pool);
+    cudaMemsetAsync(a.counters, 0, 2 * sizeof(int), st);  // [0] work head, [1] redo count
+
+    static int grids[64][2] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    int &grid = grids[dev & 63][D == 128];
+    const size_t smem = tc_candidates_smem(D);
+    if (!grid) {
+        int sms = 148, per_sm = 1;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (D == 64) {
+            cudaFuncSetAttribute(k_tc_candidates<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_tc_candidates<64>, 128, smem);
+        } else {
+            cudaFuncSetAttribute(k_tc_candidates<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_tc_candidates<128>, 128, smem);
+        }
+        if (per_sm < 1) per_sm = 1;
+        if (per_sm > 2) per_sm = 2;  // 256 TMEM columns per CTA: at most two CTAs share an SM's 512
+        grid = sms * per_sm;
+    }
+    const int mt_per_prob = a.max_q_rows / kTM;
+    if (D == 64)
+        k_tc_candidates<64><<<grid, 128, smem, st>>>(a.pool, a.probs, a.n_probs, mt_per_prob, a.n_splits, a.max_q_rows,
+                                                     a.cand, a.counters);
+    else
+        k_tc_candidates<128><<<grid, 128, smem, st>>>(a.pool, a.probs, a.n_probs, mt_per_prob, a.n_splits, a.max_q_rows,
+                                                      a.cand, a.counters);
+    dim3 gres(((size_t)a.max_q_rows * kCand + 255) / 256, a.n_probs);
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (D == 64) {
+        k_tc_rescore<64><<<gres, 256, 0, st>>>(a.pool, a.probs, a.n_splits, a.max_q_rows, a.cand, a.k, a.ratio, a.out, a.good,
+                                               a.redo_list, a.counters + 1);
+        k_tc_redo<64><<<sms * 2, 256, 0, st>>>(a.pool, a.probs, a.k, a.ratio, a.out, a.good, a.redo_list, a.counters + 1);
+    } else {
+        k_tc_rescore<128><<<gres, 256, 0, st>>>(a.pool, a.probs, a.n_splits, a.max_q_rows, a.cand, a.k, a.ratio, a.out,
+                                                a.good, a.redo_list, a.counters + 1);
+        k_tc_redo<128><<<sms * 2, 256, 0, st>>>(a.pool, a.probs, a.k, a.ratio, a.out, a.good, a.redo_list, a.counters + 1);
+    }
+    *launches += 6;
+}
+
+__global__ void __launch_bounds__(256) k_copy_rows(const float *__restrict__ src, const int *__restrict__ off, int dim4,
+                                                   float *__restrict__ dst, int max_rows, int *__restrict__ dst_off)
+{
+    const int n = min(off[1] - off[0], max_rows);
+    if (dst_off && blockIdx.x == 0 && threadIdx.x == 0) {
+        dst_off[0] = 0;
+        dst_off[1] = n;
+    }
+    const float4 *s = reinterpret_cast<const float4 *>(src) + (size_t)off[0] * dim4;
+    float4 *d = reinterpret_cast<float4 *>(dst);
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < (size_t)n * dim4; i += (size_t)gridDim.x * blockDim.x)
+        d[i] = s[i];
+}
+
+void launch_copy_rows(const float *src, const int *off, int dim, float *dst, int max_rows, int *dst_off, cudaStream_t st,
+                      int *launches)
+{
+    k_copy_rows<<<148, 256, 0, st>>>(src, off, dim / 4, dst, max_rows, dst_off);
+    *launches += 1;
+}
+
+}  // namespace surfb200

@@ -34,7 +34,8 @@ ABI_SYMBOLS = [
     "surf_descriptor_size", "surf_get_timings", "surf_stream", "surf_detect", "surf_compute", "surf_detect_and_compute",
     "surf_detect_and_compute_batch", "surf_submit_batch", "surf_collect_batch", "surf_device_results", "surf_sync",
     "surf_integral", "surf_hessian_layer", "surf_raw_keypoints", "surf_describe_keypoints", "surf_match_knn",
-    "surf_match_ratio", "surf_merge_topk", "surf_version",
+    "surf_match_ratio", "surf_merge_topk", "surf_version", "surf_match_prev", "surf_stream_reset",
+    "surf_device_matches", "surf_set_match_mode", "surf_match_redo_count",
 ]
 
 
@@ -98,6 +99,11 @@ def load_library():
     L.surf_match_knn.argtypes = [vp, vp, i32, vp, i32, i32, i32, vp, i32]
     L.surf_match_ratio.argtypes = [vp, vp, i32, vp, i32, i32, C.c_float, vp, vp, i32]
     L.surf_merge_topk.argtypes = [vp, vp, i32, i32, i32, vp]
+    L.surf_match_prev.argtypes = [vp, C.c_float, vp, vp, i32, lng]
+    L.surf_stream_reset.argtypes = [vp]
+    L.surf_device_matches.argtypes = [vp, C.POINTER(vp), C.POINTER(vp)]
+    L.surf_set_match_mode.argtypes = [vp, i32]
+    L.surf_match_redo_count.argtypes = [vp, C.POINTER(i32)]
     L.surf_version.argtypes = []
     L.surf_version.restype = C.c_char_p
     for name in ABI_SYMBOLS:
@@ -344,6 +350,39 @@ class SURF:
                            good_ptr: int):
         self._check(self._lib.surf_match_ratio(self._h, q_ptr, nq, t_ptr, nt, dim, float(ratio), out_ptr, good_ptr,
                                                MEM_DEVICE))
+
+    def set_match_mode(self, exact_only: bool):
+        """False (default): tensor-core candidate search + exact rescoring; True: exact CUDA-core kernel."""
+        self._check(self._lib.surf_set_match_mode(self._h, int(bool(exact_only))))
+
+    def match_redo_count(self) -> int:
+        n = C.c_int(0)
+        self._check(self._lib.surf_match_redo_count(self._h, C.byref(n)))
+        return n.value
+
+    def stream_reset(self):
+        self._check(self._lib.surf_stream_reset(self._h))
+
+    def match_prev(self, ratio=0.8, n_total: Optional[int] = None):
+        """After detectAndComputeBatch*/collect: matches every frame of that batch to its predecessor.
+        Returns ((N, 2) DMATCH_DTYPE, (N,) bool) packed like the batch's keypoints."""
+        n = int(n_total)
+        out = np.zeros((n, 2), DMATCH_DTYPE)
+        good = np.zeros(n, np.uint8)
+        self._check(self._lib.surf_match_prev(self._h, float(ratio), _ptr(out), _ptr(good), MEM_HOST, n))
+        return out, good.astype(bool)
+
+    def match_prev_device(self, ratio=0.8):
+        """Same, results left on the device (device_matches())."""
+        self._check(self._lib.surf_match_prev(self._h, float(ratio), None, None, MEM_DEVICE, 0))
+
+    def match_prev_to(self, ratio, out_ptr: int, good_ptr: int, out_mem: int, capacity: int):
+        self._check(self._lib.surf_match_prev(self._h, float(ratio), out_ptr or None, good_ptr or None, out_mem, capacity))
+
+    def device_matches(self):
+        m, g = C.c_void_p(), C.c_void_p()
+        self._check(self._lib.surf_device_matches(self._h, C.byref(m), C.byref(g)))
+        return m.value or 0, g.value or 0
 
     def merge_topk_device(self, in_ptr: int, n_ranks: int, nq: int, k: int, out_ptr: int):
         self._check(self._lib.surf_merge_topk(self._h, in_ptr, n_ranks, nq, k, out_ptr))

@@ -383,3 +383,78 @@ def test_config1_frame_counts_match_golden(eng):
     assert len(k) == meta["n_keypoints"]
     assert np.bincount(k["octave"], minlength=4).tolist() == meta["octave_hist"]
     assert abs(float(d.astype(np.float64).sum()) - meta["desc_checksum"]) < 1e-2
+
+
+# ---------------------------------------------------------------- stage 5 on the tensor cores
+def _unit_rows(rng, n, dim):
+    t = np.abs(rng.standard_normal((n, dim))).astype(np.float32)
+    return t / np.linalg.norm(t, axis=1, keepdims=True)
+
+
+@pytest.mark.parametrize("nq,nt,dim,k", [(4243, 4100, 64, 2), (300, 9000, 64, 3), (513, 777, 128, 2), (40, 300, 128, 4)])
+def test_tensor_core_matcher_equals_exact_and_rarely_redoes(eng, oracle, nq, nt, dim, k):
+    rng = np.random.default_rng(nq * 31 + nt)
+    t = _unit_rows(rng, nt, dim)
+    q = t[rng.integers(0, nt, nq)] + 0.05 * rng.standard_normal((nq, dim)).astype(np.float32)
+    q /= np.linalg.norm(q, axis=1, keepdims=True)
+    eng.set_match_mode(False)
+    got = eng.match_knn(q, t, k)
+    redo = eng.match_redo_count()
+    eng.set_match_mode(True)
+    try:
+        exact = eng.match_knn(q, t, k)
+    finally:
+        eng.set_match_mode(False)
+    assert got.tobytes() == exact.tobytes()       # bit-identical records, incl. distances
+    want = oracle.knn_match(q, t, k)
+    assert np.array_equal(got["trainIdx"], want["trainIdx"])
+    # the tensor-core candidates must be good enough to prove almost every query
+    assert redo <= max(2, nq // 200), f"{redo} of {nq} queries fell back to the exact kernel"
+
+
+def test_tensor_core_matcher_near_ties_fall_back_correctly(eng, oracle):
+    """Train rows that differ by 1e-7 cannot be separated by the BF16 split: the margin test must send
+    those queries to the exact kernel, and the answer must still be the exact one."""
+    rng = np.random.default_rng(77)
+    base = _unit_rows(rng, 20, 64)
+    # 12 distinct near-copies of every base row inside ONE 256-row train tile: more near-ties than the
+    # 8 candidates a tile keeps, so the candidate set cannot be proven
+    t = np.concatenate([base + np.float32(2e-7) * rng.standard_normal(base.shape).astype(np.float32) for _ in range(12)])
+    q = base[np.arange(200) % 20] + np.float32(1e-3) * rng.standard_normal((200, 64)).astype(np.float32)
+    got = eng.match_knn(q, t, 2)
+    assert eng.match_redo_count() == 200
+    want = oracle.knn_match(q, t, 2)
+    assert np.array_equal(got["trainIdx"], want["trainIdx"])
+    assert np.allclose(got["distance"], want["distance"], rtol=2e-6, atol=1e-7)
+
+
+def test_match_prev_stream_equals_pairwise_exact(oracle):
+    from surffeatures_b200 import SURF
+
+    frames = speckle.speckle_stream(7, 240, 320, seed=3, fresh=0.0)
+    e = SURF(100, 4, 3, max_width=320, max_height=240, max_batch=4, max_keypoints=4096)
+    try:
+        prev = None
+        for lo, hi in ((0, 4), (4, 7)):   # two batches: the second one's first frame matches across the call
+            kps, desc, off = e.detectAndComputeBatchPacked(frames[lo:hi])
+            m, good = e.match_prev(0.8, n_total=int(off[-1]))
+            assert e.match_redo_count() <= 3
+            for b in range(hi - lo):
+                d = desc[off[b]:off[b + 1]]
+                mm, gg = m[off[b]:off[b + 1]], good[off[b]:off[b + 1]]
+                if prev is None:
+                    assert (mm["trainIdx"] == -1).all() and not gg.any()
+                else:
+                    om = oracle.knn_match(d, prev, 2)
+                    assert np.array_equal(mm["trainIdx"], om["trainIdx"]), (lo, b)
+                    assert np.array_equal(mm["queryIdx"][:, 0], np.arange(len(d)))
+                    og = om["distance"][:, 0] < np.float32(0.8) * om["distance"][:, 1]
+                    assert (gg == og).mean() > 0.999
+                prev = d
+        e.stream_reset()
+        kps, desc, off = e.detectAndComputeBatchPacked(frames[:2])
+        m, good = e.match_prev(0.8, n_total=int(off[-1]))
+        assert (m["trainIdx"][:off[1]] == -1).all()      # forgotten predecessor after the reset
+        assert (m["trainIdx"][off[1]:off[2], 0] >= 0).all()
+    finally:
+        e.close()
