@@ -817,7 +817,7 @@ static int tc_reserve(surf_engine *e, surf_engine::TcWs &w, int slots, int slot_
 
 static int tc_reserve_work(surf_engine *e, surf_engine::TcWs &w, int n_probs, int splits, int max_q, int n_segs)
 {
-    const size_t need = (size_t)n_probs * splits * max_q;
+    const size_t need = (size_t)n_probs * splits * 2 * max_q;  // two column halves per train split
     if (need > w.cand_cap) {
         CU(e, cudaStreamSynchronize(e->stream));
         cudaFree(w.cand);

@@ -113,8 +113,10 @@ void upload_tables();  // orientation sample weights + descriptor Gaussian -> __
 constexpr int kCand = 8;  // approximate candidates kept per query and train split
 
 struct TcCand {
-    float d[kCand];  // approximate |t|^2 - 2 q.t, ascending
+    float d[kCand];  // approximate |t|^2 - 2 q.t (unsorted)
     int i[kCand];    // train row within its slot, -1 = empty
+    float worst;     // largest kept value once the list is full, else INF
+    float pad[3];
 };
 
 // Descriptor rows prepared for the tensor cores: BF16 hi / lo parts in the UMMA canonical K-major
@@ -152,7 +154,7 @@ struct TcMatchArgs {
     int n_probs;
     int n_splits;
     int max_q_rows;   // upper bound on queries per problem (multiple of 128)
-    TcCand *cand;     // [n_probs][n_splits][max_q_rows]
+    TcCand *cand;     // [n_probs][n_splits][2 column halves][max_q_rows]
     int *counters;    // [0] work-queue head, [1] redo count
     int *redo_list;   // 2 ints per entry
     int dim, k;

@@ -52,6 +52,19 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
     }
 }
 
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+
+// TMA bulk copy (1-D, no tensor map): global -> shared, completion counted in bytes on an mbarrier.
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+
 __device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t cols)
 {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(cols) : "memory");
@@ -182,27 +195,39 @@ __global__ void k_tc_reset(TcPool pool, const TcSegment *__restrict__ segs, int 
 // ------------------------------------------------------------------------------------------------
 // K5b: candidates.
 // ------------------------------------------------------------------------------------------------
+// Running candidate set of one query row: kCand entries, unsorted; `worst` is the largest kept
+// approximate value and `wslot` where it sits.  A new value replaces the worst (strictly smaller
+// only, so equal values keep the earlier train row).  All indexing is by predicated selects so the
+// arrays stay in registers.
 struct Cand {
     float d[kCand];
     int i[kCand];
+    float worst;
+    int wslot;
 };
 
-__device__ __forceinline__ void cand_insert(Cand &c, float dist, int idx)
+__device__ __forceinline__ void cand_replace_worst(Cand &c, float dist, int idx)
 {
-    // strictly smaller than the current worst: ties keep the earlier (lower) train index
-    c.d[kCand - 1] = dist;
-    c.i[kCand - 1] = idx;
 #pragma unroll
-    for (int r = kCand - 1; r > 0; r--) {
-        if (c.d[r] < c.d[r - 1]) {
-            const float td = c.d[r]; c.d[r] = c.d[r - 1]; c.d[r - 1] = td;
-            const int ti = c.i[r]; c.i[r] = c.i[r - 1]; c.i[r - 1] = ti;
-        }
+    for (int r = 0; r < kCand; r++) {
+        const bool hit = (r == c.wslot);
+        c.d[r] = hit ? dist : c.d[r];
+        c.i[r] = hit ? idx : c.i[r];
     }
+    float w = c.d[0];
+    int ws = 0;
+#pragma unroll
+    for (int r = 1; r < kCand; r++) {
+        const bool g = c.d[r] > w;
+        w = g ? c.d[r] : w;
+        ws = g ? r : ws;
+    }
+    c.worst = w;
+    c.wslot = ws;
 }
 
 template <int D>
-__global__ void __launch_bounds__(128) k_tc_candidates(TcPool pool, const TcProblem *__restrict__ probs, int n_probs,
+__global__ void __launch_bounds__(256) k_tc_candidates(TcPool pool, const TcProblem *__restrict__ probs, int n_probs,
                                                        int mt_per_prob, int n_splits, int cand_stride,
                                                        TcCand *__restrict__ cand_out, int *__restrict__ work_head)
 {
@@ -213,15 +238,16 @@ __global__ void __launch_bounds__(128) k_tc_candidates(TcPool pool, const TcProb
     extern __shared__ __align__(1024) unsigned char sm[];
     unsigned char *sA_hi = sm, *sA_lo = sm + A_BYTES;
     unsigned char *sB_hi = sm + 2 * A_BYTES, *sB_lo = sB_hi + B_BYTES;
-    float *sTn = reinterpret_cast<float *>(sB_lo + B_BYTES);  // |t|^2 of the current train tile
-    __shared__ __align__(8) uint64_t s_bar;
+    float *sTn = reinterpret_cast<float *>(sB_lo + B_BYTES);  // |t|^2 of the train tile, two stages
+    __shared__ __align__(8) uint64_t s_bar[2];  // [0] MMA done (tcgen05.commit), [1] operands landed (bulk copies)
     __shared__ uint32_t s_tmem;
     __shared__ int s_item;
 
     const int tid = threadIdx.x, warp = tid >> 5;
-    const uint32_t bar = smem_u32(&s_bar);
+    const uint32_t bar_mma = smem_u32(&s_bar[0]), bar_ld = smem_u32(&s_bar[1]);
     if (tid == 0) {
-        mbar_init(bar, 1);
+        mbar_init(bar_mma, 1);
+        mbar_init(bar_ld, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncwarp();
@@ -231,7 +257,7 @@ __global__ void __launch_bounds__(128) k_tc_candidates(TcPool pool, const TcProb
     tc_fence_after();
     const uint32_t tmem = s_tmem;
     const uint32_t idesc = umma_idesc(kTM, kTN);
-    uint32_t phase = 0;
+    uint32_t ph_mma = 0, ph_ld = 0;
     const int total_items = n_probs * mt_per_prob * n_splits;
 
     for (;;) {
@@ -252,41 +278,36 @@ __global__ void __launch_bounds__(128) k_tc_candidates(TcPool pool, const TcProb
         const int per = (n_tiles + n_splits - 1) / n_splits;
         const int tile0 = split * per, tile1 = min(n_tiles, tile0 + per);
 
-        // ---- query tile (hi, lo): contiguous run of core matrices ----
-        {
-            const size_t e0 = ((size_t)pr.q_slot * pool.slot_rows + q0) * D;
-            const uint4 *gh = reinterpret_cast<const uint4 *>(pool.hi + e0);
-            const uint4 *gl = reinterpret_cast<const uint4 *>(pool.lo + e0);
-            uint4 *dh = reinterpret_cast<uint4 *>(sA_hi), *dl = reinterpret_cast<uint4 *>(sA_lo);
-            for (int k = tid; k < (int)(A_BYTES / 16); k += 128) {
-                dh[k] = __ldg(gh + k);
-                dl[k] = __ldg(gl + k);
-            }
-        }
         Cand best;
 #pragma unroll
         for (int r = 0; r < kCand; r++) {
             best.d[r] = INFINITY;
             best.i[r] = -1;
         }
+        best.worst = INFINITY;
+        best.wslot = 0;
+        const size_t trow_base = (size_t)pr.t_slot * pool.slot_rows;
+        // operands arrive by TMA bulk copies (contiguous runs of core matrices), counted on bar_ld
+        auto load_train_tile = [&](int tile, int stage) {
+            const size_t row0 = trow_base + (size_t)tile * kTN;
+            bulk_g2s(smem_u32(sB_hi), pool.hi + row0 * D, B_BYTES, bar_ld);
+            bulk_g2s(smem_u32(sB_lo), pool.lo + row0 * D, B_BYTES, bar_ld);
+            bulk_g2s(smem_u32(sTn + stage * kTN), pool.norm + row0, kTN * sizeof(float), bar_ld);
+        };
+        if (tid == 0 && tile0 < tile1) {
+            const size_t e0 = ((size_t)pr.q_slot * pool.slot_rows + q0) * D;
+            mbar_expect_tx(bar_ld, 2 * A_BYTES + 2 * B_BYTES + kTN * sizeof(float));
+            bulk_g2s(smem_u32(sA_hi), pool.hi + e0, A_BYTES, bar_ld);
+            bulk_g2s(smem_u32(sA_lo), pool.lo + e0, A_BYTES, bar_ld);
+            load_train_tile(tile0, 0);
+        }
 
         for (int tile = tile0; tile < tile1; tile++) {
             const int t0 = tile * kTN;
-            // ---- train tile (hi, lo, norms) ----
-            {
-                const size_t row0 = (size_t)pr.t_slot * pool.slot_rows + t0;
-                const uint4 *gh = reinterpret_cast<const uint4 *>(pool.hi + row0 * D);
-                const uint4 *gl = reinterpret_cast<const uint4 *>(pool.lo + row0 * D);
-                uint4 *dh = reinterpret_cast<uint4 *>(sB_hi), *dl = reinterpret_cast<uint4 *>(sB_lo);
-                for (int k = tid; k < (int)(B_BYTES / 16); k += 128) {
-                    dh[k] = __ldg(gh + k);
-                    dl[k] = __ldg(gl + k);
-                }
-                for (int k = tid; k < kTN; k += 128) sTn[k] = pool.norm[row0 + k];
-            }
-            fence_async_smem();  // generic-proxy stores -> visible to the tensor core's async proxy
-            tc_fence_before();
-            __syncthreads();
+            const int stage = (tile - tile0) & 1;
+            mbar_wait(bar_ld, ph_ld);  // operands of this tile are in shared memory
+            ph_ld ^= 1;
+            __syncthreads();  // everyone has observed this phase before the next one can be armed
             if (tid == 0) {
                 tc_fence_after();
                 const uint32_t a_hi = smem_u32(sA_hi), a_lo = smem_u32(sA_lo);
@@ -302,38 +323,47 @@ __global__ void __launch_bounds__(128) k_tc_candidates(TcPool pool, const TcProb
                     umma_bf16(tmem, umma_desc(a_hi + ko, 128, SBO), umma_desc(b_lo + ko, 128, SBO), idesc, 1);
                     umma_bf16(tmem, umma_desc(a_lo + ko, 128, SBO), umma_desc(b_hi + ko, 128, SBO), idesc, 1);
                 }
-                umma_commit(bar);
+                umma_commit(bar_mma);
             }
-            mbar_wait(bar, phase);
-            phase ^= 1;
+            mbar_wait(bar_mma, ph_mma);  // accumulators complete; the train tile in shared memory is free
+            ph_mma ^= 1;
             tc_fence_after();
+            if (tid == 0 && tile + 1 < tile1) {  // prefetch the next train tile under this tile's epilogue
+                mbar_expect_tx(bar_ld, 2 * B_BYTES + kTN * sizeof(float));
+                load_train_tile(tile + 1, stage ^ 1);
+            }
 
-            // ---- epilogue: thread = query row = TMEM lane ----
-            const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);
+            // ---- epilogue: 8 warps; warp w reads TMEM lanes 32*(w%4).. (its query rows) and the
+            //      column half w/4, so two threads share a query row and each keeps its own list ----
+            const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+            const float *tn = sTn + stage * kTN;
             const int lim = min(kTN, nt - t0);
+            const int cbeg = (warp >> 2) * (kTN / 2);
 #pragma unroll 1
-            for (int c0 = 0; c0 < kTN; c0 += 32) {
+            for (int c0 = cbeg; c0 < cbeg + kTN / 2; c0 += 32) {
                 float v[32];
                 tmem_ld32(lane_addr + c0, v);
                 if (c0 < lim) {
 #pragma unroll
                     for (int c = 0; c < 32; c++) {
-                        const float dist = fmaf(-2.f, v[c], sTn[c0 + c]);  // |t|^2 - 2 q.t  (+ |q|^2 later)
-                        if (dist < best.d[kCand - 1]) cand_insert(best, dist, t0 + c0 + c);
+                        const float dist = fmaf(-2.f, v[c], tn[c0 + c]);  // |t|^2 - 2 q.t  (+ |q|^2 later)
+                        if (dist < best.worst) cand_replace_worst(best, dist, t0 + c0 + c);
                     }
                 }
             }
             tc_fence_before();
-            __syncthreads();  // TMEM and the train tile are free for the next iteration
+            __syncthreads();  // every warp has drained TMEM before the next tile's MMA overwrites it
         }
-        if (q0 + tid < nq) {
+        const int row = (warp & 3) * 32 + (tid & 31), half = warp >> 2;
+        if (q0 + row < nq) {
             TcCand o;
 #pragma unroll
             for (int r = 0; r < kCand; r++) {
                 o.d[r] = best.d[r];
                 o.i[r] = best.i[r];
             }
-            cand_out[((size_t)p * n_splits + split) * cand_stride + q0 + tid] = o;
+            o.worst = best.worst;
+            cand_out[((size_t)(p * n_splits + split) * 2 + half) * cand_stride + q0 + row] = o;
         }
     }
     __syncthreads();
@@ -366,23 +396,26 @@ __global__ void __launch_bounds__(256) k_tc_rescore(TcPool pool, const TcProblem
     float bd[4] = {INFINITY, INFINITY, INFINITY, INFINITY};
     int bi[4] = {-1, -1, -1, -1};
     float worst_kept = INFINITY;  // smallest "kCand-th approximate value" over the splits
-    for (int s = 0; s < n_splits; s++) {
-        const TcCand &c = cand[((size_t)p * n_splits + s) * cand_stride + gq];
+    for (int s = 0; s < 2 * n_splits; s++) {
+        const TcCand &c = cand[((size_t)p * 2 * n_splits + s) * cand_stride + gq];
         const int idx = c.i[lane_c];
         float dist = INFINITY;
         if (idx >= 0) {
-            const float *tv = tsrc + (size_t)(t_row0 + idx) * D;
+            const float4 *tv = reinterpret_cast<const float4 *>(tsrc + (size_t)(t_row0 + idx) * D);
+            const float4 *qv4 = reinterpret_cast<const float4 *>(qv);
             float acc = 0.f;
-#pragma unroll 8
-            for (int d = 0; d < D; d++) {
-                const float df = qv[d] - tv[d];
-                acc = fmaf(df, df, acc);  // same order as k_match_exact
+#pragma unroll 4
+            for (int d = 0; d < D / 4; d++) {  // same element order as k_match_exact
+                const float4 a = __ldg(qv4 + d), b = __ldg(tv + d);
+                float df = a.x - b.x; acc = fmaf(df, df, acc);
+                df = a.y - b.y; acc = fmaf(df, df, acc);
+                df = a.z - b.z; acc = fmaf(df, df, acc);
+                df = a.w - b.w; acc = fmaf(df, df, acc);
             }
             dist = acc;
         }
-        // a split whose list is full bounds every train row it did not keep
-        const float last = c.d[kCand - 1];
-        if (c.i[kCand - 1] >= 0) worst_kept = fminf(worst_kept, last);
+        // a list that is full bounds every train row it did not keep (an unfilled list kept them all)
+        if (c.worst < INFINITY) worst_kept = fminf(worst_kept, c.worst);
         // merge this split's kCand exact distances into the running top-4 (all lanes keep a copy)
 #pragma unroll
         for (int r = 0; r < kCand; r++) {
@@ -504,7 +537,7 @@ __global__ void __launch_bounds__(256) k_tc_redo(TcPool pool, const TcProblem *_
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
-size_t tc_candidates_smem(int dim) { return (size_t)(2 * kTM + 2 * kTN) * dim * 2 + kTN * sizeof(float) + 1024; }
+size_t tc_candidates_smem(int dim) { return (size_t)(2 * kTM + 2 * kTN) * dim * 2 + 2 * kTN * sizeof(float) + 1024; }
 
 void launch_tc_match(const TcMatchArgs &a, cudaStream_t st, int *launches)
 {
@@ -527,21 +560,22 @@ void launch_tc_match(const TcMatchArgs &a, cudaStream_t st, int *launches)
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         if (D == 64) {
             cudaFuncSetAttribute(k_tc_candidates<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_tc_candidates<64>, 128, smem);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_tc_candidates<64>, 256, smem);
         } else {
             cudaFuncSetAttribute(k_tc_candidates<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_tc_candidates<128>, 128, smem);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_tc_candidates<128>, 256, smem);
         }
         if (per_sm < 1) per_sm = 1;
         if (per_sm > 2) per_sm = 2;  // 256 TMEM columns per CTA: at most two CTAs share an SM's 512
+        if (D == 64) per_sm = 2;     // 2 x 101 KB of shared memory fit one SM
         grid = sms * per_sm;
     }
     const int mt_per_prob = a.max_q_rows / kTM;
     if (D == 64)
-        k_tc_candidates<64><<<grid, 128, smem, st>>>(a.pool, a.probs, a.n_probs, mt_per_prob, a.n_splits, a.max_q_rows,
+        k_tc_candidates<64><<<grid, 256, smem, st>>>(a.pool, a.probs, a.n_probs, mt_per_prob, a.n_splits, a.max_q_rows,
                                                      a.cand, a.counters);
     else
-        k_tc_candidates<128><<<grid, 128, smem, st>>>(a.pool, a.probs, a.n_probs, mt_per_prob, a.n_splits, a.max_q_rows,
+        k_tc_candidates<128><<<grid, 256, smem, st>>>(a.pool, a.probs, a.n_probs, mt_per_prob, a.n_splits, a.max_q_rows,
                                                       a.cand, a.counters);
     dim3 gres(((size_t)a.max_q_rows * kCand + 255) / 256, a.n_probs);
     int sms = 148;
