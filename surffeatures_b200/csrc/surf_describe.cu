@@ -190,24 +190,22 @@ __global__ void __launch_bounds__(kOriWarps * 32) k_orient(const __grid_constant
                 //      sample order; first strict maximum over increasing window index ----
                 float bmod = 0, bx = 0, by = 0;
                 int bi = 1 << 30;
-                for (int wi = lane; wi < kOriWindows; wi += 32) {
-                    const int ang0 = wi * 5;
-                    float sx = 0, sy = 0;
+                if (lane < 24) {
+                    // lane owns windows lane, lane + 24, lane + 48: one pass over the samples feeds all three
+                    const int a0 = lane * 5, a1 = a0 + 120, a2 = a0 + 240;
+                    float sx0 = 0, sy0 = 0, sx1 = 0, sy1 = 0, sx2 = 0, sy2 = 0;
+#pragma unroll 2
                     for (int k = 0; k < na; k++) {
                         const OriSample o = smp[k];
-                        const int d = abs(o.iang - ang0);
-                        if (d < 30 || d > 330) {
-                            sx += o.X;
-                            sy += o.Y;
-                        }
+                        const int d0 = abs(o.iang - a0), d1 = abs(o.iang - a1), d2 = abs(o.iang - a2);
+                        if (d0 < 30 || d0 > 330) { sx0 += o.X; sy0 += o.Y; }
+                        if (d1 < 30 || d1 > 330) { sx1 += o.X; sy1 += o.Y; }
+                        if (d2 < 30 || d2 > 330) { sx2 += o.X; sy2 += o.Y; }
                     }
-                    const float mod = sx * sx + sy * sy;
-                    if (mod > bmod) {
-                        bmod = mod;
-                        bx = sx;
-                        by = sy;
-                        bi = wi;
-                    }
+                    const float m0 = sx0 * sx0 + sy0 * sy0, m1 = sx1 * sx1 + sy1 * sy1, m2 = sx2 * sx2 + sy2 * sy2;
+                    if (m0 > bmod) { bmod = m0; bx = sx0; by = sy0; bi = lane; }
+                    if (m1 > bmod) { bmod = m1; bx = sx1; by = sy1; bi = lane + 24; }
+                    if (m2 > bmod) { bmod = m2; bx = sx2; by = sy2; bi = lane + 48; }
                 }
 #pragma unroll
                 for (int d = 16; d > 0; d >>= 1) {
@@ -241,6 +239,12 @@ __global__ void __launch_bounds__(kOriWarps * 32) k_orient(const __grid_constant
                 A.deleted_slots[(size_t)b * A.cap + pos] = slot;
             } else {
                 kpp->angle = dir;
+                if (want_desc && !A.upright) {
+                    // -sin / cos of the dominant angle, correctly rounded to fp32,
+                    // computed once here instead of by every thread of the descriptor CTA
+                    const float th = dir * (float)(3.1415926535897932384626433832795 / 180);
+                    A.sincos[(size_t)b * A.cap + slot] = make_float2(-(float)sin((double)th), (float)cos((double)th));
+                }
                 if (want_desc) {
                     const int cls = (n > kClassMaxN0) + (n > kClassMaxN1) + (n > kClassMaxN2);
                     const int pos = atomicAdd(A.misc + kMiscClassCount + cls, 1);
@@ -269,7 +273,7 @@ __global__ void __launch_bounds__(THREADS) k_descriptor(const __grid_constant__ 
     // dynamic layout: double rsx[max_n], rsy[max_n]; then (staged classes) uchar win[max_n^2], uchar tile[tile_cap]
     double *s_rsx = reinterpret_cast<double *>(dyn);
     double *s_rsy = s_rsx + max_n;
-    unsigned char *s_win = dyn + (size_t)max_n * 16;
+    unsigned char *s_win = dyn + (size_t)max_n * 16;  // class D: this region holds the row sums instead
     unsigned char *s_tile = s_win + (((size_t)max_n * max_n + 15) & ~(size_t)15);
 
     __shared__ int s_work;
@@ -316,9 +320,9 @@ __global__ void __launch_bounds__(THREADS) k_descriptor(const __grid_constant__ 
             ty1 = min(max(uy0, 0), H - 1);
             ty0 = min(max(uy0 - n + 1, 0), H - 1);
         } else {
-            const float th = dir * (float)(3.1415926535897932384626433832795 / 180);
-            sd = -(float)sin((double)th);
-            cd = (float)cos((double)th);
+            const float2 sc = A.sincos[kidx];
+            sd = sc.x;
+            cd = sc.y;
             if (tid == 0) {
                 // row starts advance by sequential fp32 additions; stored as doubles for the tap loop
                 float sx0 = cx + off * cd + off * sd;
@@ -414,13 +418,17 @@ __global__ void __launch_bounds__(THREADS) k_descriptor(const __grid_constant__ 
             }
         } else {
             const double kMagic = 6755399441055744.0;  // 1.5 * 2^52: floor via round-down addition
-            const double lane_dx = (double)lane * (double)cd, lane_dy = (double)lane * (double)sd;
-            const double step_x = 32.0 * (double)cd, step_y = 32.0 * (double)sd;
-            for (int i = warp; i < n; i += NW) {
+            // a warp covers 1 row x 32 columns of the window (n <= 32) or 4 rows x 8 columns: far fewer
+            // idle lanes at the end of a row than 32-wide strips
+            const int rows_w = n > 32 ? 4 : 1, cols_w = 32 / rows_w;
+            const int lj = lane & (cols_w - 1), li = lane / cols_w;
+            const double lane_dx = (double)lj * (double)cd, lane_dy = (double)lj * (double)sd;
+            const double step_x = (double)cols_w * (double)cd, step_y = (double)cols_w * (double)sd;
+            for (int i = warp * rows_w + li; i < n; i += NW * rows_w) {
                 double fx = s_rsx[i] + lane_dx;  // start + j * step, exact in fp64
                 double fy = s_rsy[i] - lane_dy;
                 unsigned char *wrow = win + i * n;
-                for (int j = lane; j < n; j += 32, fx += step_x, fy -= step_y) {
+                for (int j = lj; j < n; j += cols_w, fx += step_x, fy -= step_y) {
                     const double mx = __dadd_rd(fx, kMagic), my = __dadd_rd(fy, kMagic);
                     const int ix = __double2loint(mx), iy = __double2loint(my);
                     unsigned v;
@@ -442,7 +450,31 @@ __global__ void __launch_bounds__(THREADS) k_descriptor(const __grid_constant__ 
         }
         __syncthreads();
 
-        // ---- resize to 21 x 21 (INTER_AREA), one destination pixel per thread ----
+        // ---- resize to 21 x 21 (INTER_AREA) ----
+        // Fractional scales run the reference's two passes: row sums buf[sy][dx] = sum_x win[sy][x] * alpha
+        // (fp32, table order) for every window row, then the column pass.  Every window pixel is read once.
+        float *s_buf = reinterpret_cast<float *>(GLOBAL ? (s_win) : s_tile);  // the image tile is no longer needed
+        if (!int_scale) {
+            for (int it = tid; it < n * kPatch; it += THREADS) {
+                const int sy = it / kPatch, dx = it - sy * kPatch;
+                const int xs = s_tab.start[dx], xc = s_tab.count[dx];
+                const bool xhf = s_tab.has_first[dx], xhl = s_tab.has_last[dx];
+                const float xam = s_tab.a_mid[dx];
+                const unsigned char *row = win + sy * n + xs;
+                const int fend = xc - (xhl ? 1 : 0);
+                float buf = 0;
+                int f = 0;
+                if (xhf) {
+                    buf += u8f(row[0]) * s_tab.a_first[dx];
+                    f = 1;
+                }
+#pragma unroll 4
+                for (; f < fend; f++) buf += u8f(row[f]) * xam;
+                if (xhl) buf += u8f(row[xc - 1]) * s_tab.a_last[dx];
+                s_buf[it] = buf;
+            }
+            __syncthreads();
+        }
         for (int p = tid; p < kPatchPx; p += THREADS) {
             const int dy = p / kPatch, dx = p - dy * kPatch;
             int outv;
@@ -461,23 +493,11 @@ __global__ void __launch_bounds__(THREADS) k_descriptor(const __grid_constant__ 
                 const int ys = s_tab.start[dy], yc = s_tab.count[dy];
                 const bool yhf = s_tab.has_first[dy], yhl = s_tab.has_last[dy];
                 const float yaf = s_tab.a_first[dy], yam = s_tab.a_mid[dy], yal = s_tab.a_last[dy];
-                const int xs = s_tab.start[dx], xc = s_tab.count[dx];
-                const bool xhf = s_tab.has_first[dx], xhl = s_tab.has_last[dx];
-                const float xaf = s_tab.a_first[dx], xam = s_tab.a_mid[dx], xal = s_tab.a_last[dx];
-                const int fend = xc - (xhl ? 1 : 0);
+                const float *col = s_buf + ys * kPatch + dx;
                 float acc = 0;
                 for (int e = 0; e < yc; e++) {
                     const float beta = (e == 0 && yhf) ? yaf : ((e == yc - 1 && yhl) ? yal : yam);
-                    const unsigned char *row = win + (ys + e) * n + xs;
-                    float buf = 0;
-                    int f = 0;
-                    if (xhf) {
-                        buf += u8f(row[0]) * xaf;
-                        f = 1;
-                    }
-#pragma unroll 4
-                    for (; f < fend; f++) buf += u8f(row[f]) * xam;
-                    if (xhl) buf += u8f(row[xc - 1]) * xal;
+                    const float buf = col[e * kPatch];
                     if (e == 0) acc = beta * buf; else acc += beta * buf;
                 }
                 outv = sat_u8(acc);
@@ -599,7 +619,8 @@ DevCfg &dev_cfg()
             cc.max_n = max_ns[k];
             const bool global = (k == kNumClasses - 1);
             cc.tile_cap = global ? 0 : tile_cap_for(cc.max_n);
-            cc.smem = cc.max_n * 16 + (global ? 0 : ((cc.max_n * cc.max_n + 15) & ~15) + cc.tile_cap);
+            cc.smem = cc.max_n * 16 + (global ? cc.max_n * kPatch * (int)sizeof(float)
+                                              : ((cc.max_n * cc.max_n + 15) & ~15) + cc.tile_cap);
         }
         setup_class<128, false>(c.cls[0], sms);
         setup_class<256, false>(c.cls[1], sms);

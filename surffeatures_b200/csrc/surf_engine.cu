@@ -48,6 +48,7 @@ struct surf_engine {
     int *d_counts = nullptr, *d_ndel = nullptr, *d_off_in = nullptr, *d_off_out = nullptr, *d_misc = nullptr;
     int *d_deleted = nullptr, *d_class_list = nullptr;
     uint8_t *d_win_scratch = nullptr;
+    float2 *d_sincos = nullptr;
     int *h_pin = nullptr;  // pinned: counts[B], ndel[B], off_out[B+1], misc[4]
     surf_dmatch *d_match_part = nullptr;  size_t match_part_cap = 0;
     void *d_match_io = nullptr;           size_t match_io_cap = 0;
@@ -173,7 +174,7 @@ void free_workspace(surf_engine *e)
     cudaFree(e->d_det); cudaFree(e->d_kp_a); cudaFree(e->d_kp_b); cudaFree(e->d_out_kp); cudaFree(e->d_desc);
     cudaFree(e->d_out_desc); cudaFree(e->d_patches); cudaFree(e->d_counts); cudaFree(e->d_ndel);
     cudaFree(e->d_off_in); cudaFree(e->d_off_out); cudaFree(e->d_misc); cudaFree(e->d_deleted);
-    cudaFree(e->d_match_part); cudaFree(e->d_match_io); cudaFree(e->d_class_list); cudaFree(e->d_win_scratch);
+    cudaFree(e->d_match_part); cudaFree(e->d_match_io); cudaFree(e->d_class_list); cudaFree(e->d_win_scratch); cudaFree(e->d_sincos);
     for (auto &w : e->tc) {
         cudaFree(w.pool.hi); cudaFree(w.pool.lo); cudaFree(w.pool.norm); cudaFree(w.pool.max_norm);
         cudaFree(w.pool.count); cudaFree(w.cand); cudaFree(w.redo); cudaFree(w.counters); cudaFree(w.segs);
@@ -187,7 +188,7 @@ void free_workspace(surf_engine *e)
     e->d_kp_a = e->d_kp_b = e->d_out_kp = nullptr; e->d_desc = e->d_out_desc = nullptr; e->d_patches = nullptr;
     e->d_counts = e->d_ndel = e->d_off_in = e->d_off_out = e->d_misc = e->d_deleted = nullptr;
     e->d_match_part = nullptr; e->d_match_io = nullptr; e->h_pin = nullptr; e->d_class_list = nullptr;
-    e->d_win_scratch = nullptr;
+    e->d_win_scratch = nullptr; e->d_sincos = nullptr;
     e->match_part_cap = e->match_io_cap = 0;
 }
 
@@ -238,6 +239,7 @@ int alloc_workspace(surf_engine *e)
     CU(e, cudaMalloc(&e->d_misc, sizeof(int) * kMiscWords));
     CU(e, cudaMalloc(&e->d_class_list, nk * kNumClasses * sizeof(int)));
     CU(e, cudaMalloc(&e->d_win_scratch, describe_scratch_bytes()));
+    CU(e, cudaMalloc(&e->d_sincos, nk * sizeof(float2)));
     CU(e, cudaMallocHost(&e->h_pin, sizeof(int) * (3 * (size_t)B + 8 + kMiscWords)));
     return alloc_det_and_desc(e);
 }
@@ -363,6 +365,7 @@ int run_describe_pack(surf_engine *e, const ImageRef &img, const FrameGeo &geo, 
     a.class_list = e->d_class_list;
     a.list_stride = (size_t)e->max_b * e->cap;
     a.win_scratch = e->d_win_scratch;
+    a.sincos = e->d_sincos;
     launch_describe(a, e->stream, &e->launches);
     rec(e, EV_DESCRIBE);
     if (pack) {

@@ -83,6 +83,7 @@ struct DescribeArgs {
     int *class_list;      // [kNumClasses][list_stride]: keypoint index b * cap + slot
     size_t list_stride;
     uint8_t *win_scratch; // class D windows: [grid][kMaxWindow * kMaxWindow]
+    float2 *sincos;       // [B][cap]: (-sin, cos) of the dominant angle, written by k_orient
 };
 
 size_t describe_scratch_bytes();  // size of win_scratch for the current device
