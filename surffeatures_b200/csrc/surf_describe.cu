@@ -246,7 +246,7 @@ __global__ void __launch_bounds__(kOriWarps * 32) k_orient(const __grid_constant
                     A.sincos[(size_t)b * A.cap + slot] = make_float2(-(float)sin((double)th), (float)cos((double)th));
                 }
                 if (want_desc) {
-                    const int cls = (n > kClassMaxN0) + (n > kClassMaxN1) + (n > kClassMaxN2);
+                    const int cls = (n > kClassMaxN0) + (n > kClassMaxN1) + (n > kClassMaxN2) + (n > kClassMaxN3);
                     const int pos = atomicAdd(A.misc + kMiscClassCount + cls, 1);
                     A.class_list[(size_t)cls * A.list_stride + pos] = b * A.cap + slot;
                 }
@@ -323,32 +323,23 @@ __global__ void __launch_bounds__(THREADS) k_descriptor(const __grid_constant__ 
             const float2 sc = A.sincos[kidx];
             sd = sc.x;
             cd = sc.y;
-            if (tid == 0) {
-                // row starts advance by sequential fp32 additions; stored as doubles for the tap loop
-                float sx0 = cx + off * cd + off * sd;
-                float sy0 = cy - off * sd + off * cd;
-                for (int i = 0; i < n; i++) {
-                    s_rsx[i] = (double)sx0;
-                    s_rsy[i] = (double)sy0;
-                    sx0 += sd;
-                    sy0 += cd;
-                }
-            }
-            __syncthreads();
-            // bounding box of all taps (floor and floor + 1), clamped to the image
-            const double ex = (double)(n - 1) * (double)cd, ey = (double)(n - 1) * (double)sd;
-            const double x00 = s_rsx[0], x10 = s_rsx[n - 1], y00 = s_rsy[0], y10 = s_rsy[n - 1];
-            const double minx = fmin(fmin(x00, x00 + ex), fmin(x10, x10 + ex));
-            const double maxx = fmax(fmax(x00, x00 + ex), fmax(x10, x10 + ex));
-            const double miny = fmin(fmin(y00, y00 - ey), fmin(y10, y10 - ey));
-            const double maxy = fmax(fmax(y00, y00 - ey), fmax(y10, y10 - ey));
-            tx0 = min(max(__double2int_rd(minx), 0), W - 1);
-            tx1 = min(max(__double2int_rd(maxx) + 1, 0), W - 1);
-            ty0 = min(max(__double2int_rd(miny), 0), H - 1);
-            ty1 = min(max(__double2int_rd(maxy) + 1, 0), H - 1);
+            // Bounding box of all taps from the closed-form window corners.  The true row starts come
+            // from sequential fp32 additions (computed below, overlapped with the tile copy) and drift
+            // from the closed form by far less than the 1-pixel margin taken here.
+            const float sx0 = cx + off * cd + off * sd, sy0 = cy - off * sd + off * cd;
+            const float ext = (float)(n - 1);
+            const float xa = sx0, xb = sx0 + ext * sd, xc2 = sx0 + ext * cd, xd = xb + ext * cd;
+            const float ya = sy0, yb = sy0 + ext * cd, yc2 = sy0 - ext * sd, yd = yb - ext * sd;
+            const float minx = fminf(fminf(xa, xb), fminf(xc2, xd)) - 1.f, maxx = fmaxf(fmaxf(xa, xb), fmaxf(xc2, xd)) + 1.f;
+            const float miny = fminf(fminf(ya, yb), fminf(yc2, yd)) - 1.f, maxy = fmaxf(fmaxf(ya, yb), fmaxf(yc2, yd)) + 1.f;
+            tx0 = min(max(__float2int_rd(minx), 0), W - 1);
+            tx1 = min(max(__float2int_rd(maxx) + 1, 0), W - 1);
+            ty0 = min(max(__float2int_rd(miny), 0), H - 1);
+            ty1 = min(max(__float2int_rd(maxy) + 1, 0), H - 1);
         }
-        const int tx0a = tx0 & ~3;                    // word-aligned tile origin
-        const int tp = ((tx1 - tx0a + 1) + 3) & ~3;   // tile pitch in bytes
+        const int amask = A.img_aligned16 ? 15 : 3;
+        const int tx0a = tx0 & ~amask;                          // tile origin aligned for vector copies
+        const int tp = ((tx1 - tx0a + 1) + amask) & ~amask;     // tile pitch in bytes
         const int th_rows = ty1 - ty0 + 1;
         // the tile capacity of a staged class is an upper bound by construction (tile_cap_for); a
         // violation would be a bug, reported through the status word instead of corrupting memory
@@ -381,25 +372,52 @@ __global__ void __launch_bounds__(THREADS) k_descriptor(const __grid_constant__ 
 
         // ---- stage the bounding box of the window in shared memory (coalesced word loads) ----
         if (!GLOBAL) {
-            const int wpr = tp >> 2;
-            const int wfull = A.img_aligned4 ? min(wpr, (W - tx0a) >> 2) : 0;  // words fully inside the row
-            for (int r = warp; r < th_rows; r += NW) {
-                const uint8_t *src = img + (size_t)(ty0 + r) * pitch + tx0a;
-                uint32_t *dst = reinterpret_cast<uint32_t *>(s_tile + r * tp);
-                for (int c = lane; c < wfull; c += 32)  // asynchronous 4-byte copies, no register staging
-                    __pipeline_memcpy_async(dst + c, src + 4 * c, 4);
-                for (int c = wfull + lane; c < wpr; c += 32) {
-                    const int x = tx0a + 4 * c;
-                    uint32_t v = 0;
+            if (A.img_aligned16) {
+                const int cpr = tp >> 4;                                   // 16-byte chunks per tile row
+                const int cfull = min(cpr, (W - tx0a) >> 4);               // chunks fully inside the image row
+                for (int r = warp; r < th_rows; r += NW) {
+                    const uint8_t *src = img + (size_t)(ty0 + r) * pitch + tx0a;
+                    uint4 *dst = reinterpret_cast<uint4 *>(s_tile + r * tp);
+                    for (int c = lane; c < cfull; c += 32) __pipeline_memcpy_async(dst + c, src + 16 * c, 16);
+                    for (int c = cfull + lane; c < cpr; c += 32) {          // chunk straddling the row end
+                        uint32_t v[4] = {0, 0, 0, 0};
+                        for (int k = 0; k < 16; k++)
+                            if (tx0a + 16 * c + k < W) v[k >> 2] |= (uint32_t)src[16 * c + k] << (8 * (k & 3));
+                        dst[c] = make_uint4(v[0], v[1], v[2], v[3]);
+                    }
+                }
+            } else {
+                const int wpr = tp >> 2;
+                const int wfull = A.img_aligned4 ? min(wpr, (W - tx0a) >> 2) : 0;  // words fully inside the row
+                for (int r = warp; r < th_rows; r += NW) {
+                    const uint8_t *src = img + (size_t)(ty0 + r) * pitch + tx0a;
+                    uint32_t *dst = reinterpret_cast<uint32_t *>(s_tile + r * tp);
+                    for (int c = lane; c < wfull; c += 32) __pipeline_memcpy_async(dst + c, src + 4 * c, 4);
+                    for (int c = wfull + lane; c < wpr; c += 32) {
+                        const int x = tx0a + 4 * c;
+                        uint32_t v = 0;
 #pragma unroll
-                    for (int k = 0; k < 4; k++)
-                        if (x + k < W) v |= (uint32_t)src[4 * c + k] << (8 * k);
-                    dst[c] = v;
+                        for (int k = 0; k < 4; k++)
+                            if (x + k < W) v |= (uint32_t)src[4 * c + k] << (8 * k);
+                        dst[c] = v;
+                    }
                 }
             }
             __pipeline_commit();
-            __pipeline_wait_prior(0);
         }
+        if (!A.upright && (tid == 0 || tid == 32)) {
+            // row starts advance by sequential fp32 additions (x chain on warp 0, y chain on warp 1),
+            // stored as doubles for the tap loop; runs while the tile copies are in flight
+            const float off2 = -(float)(n - 1) / 2;
+            if (tid == 0) {
+                float v = cx + off2 * cd + off2 * sd;
+                for (int i = 0; i < n; i++, v += sd) s_rsx[i] = (double)v;
+            } else {
+                float v = cy - off2 * sd + off2 * cd;
+                for (int i = 0; i < n; i++, v += cd) s_rsy[i] = (double)v;
+            }
+        }
+        if (!GLOBAL) __pipeline_wait_prior(0);
         __syncthreads();
 
         unsigned char *win = GLOBAL ? g_win : s_win;
@@ -577,8 +595,8 @@ struct ClassCfg {
 int tile_cap_for(int max_n)
 {
     // bounding box side of a rotated n x n window: n (|cos| + |sin|) + 3 <= 1.4143 n + 3, rows padded to 4
-    int side = (int)(1.4143 * max_n) + 4;
-    int pitch = (side + 3 + 3) & ~3;
+    int side = (int)(1.4143 * max_n) + 4 + 2;  // + the 1-pixel margin on both sides of the closed-form box
+    int pitch = (side + 15 + 15) & ~15;        // origin aligned down and pitch rounded up to 16 bytes
     return pitch * side;
 }
 
@@ -586,8 +604,8 @@ struct DevCfg {
     bool ready = false;
     int ori_grid = 0;
     ClassCfg cls[kNumClasses];
-    cudaStream_t side[3];
-    cudaEvent_t fork, join[3];
+    cudaStream_t side[kNumClasses - 1];
+    cudaEvent_t fork, join[kNumClasses - 1];
 };
 DevCfg g_cfg[64];
 
@@ -615,7 +633,7 @@ DevCfg &dev_cfg()
         c.ori_grid = sms * (per_sm < 1 ? 1 : per_sm);
         for (int k = 0; k < kNumClasses; k++) {
             ClassCfg &cc = c.cls[k];
-            const int max_ns[kNumClasses] = {kClassMaxN0, kClassMaxN1, kClassMaxN2, kMaxWindow};
+            const int max_ns[kNumClasses] = {kClassMaxN0, kClassMaxN1, kClassMaxN2, kClassMaxN3, kMaxWindow};
             cc.max_n = max_ns[k];
             const bool global = (k == kNumClasses - 1);
             cc.tile_cap = global ? 0 : tile_cap_for(cc.max_n);
@@ -625,8 +643,9 @@ DevCfg &dev_cfg()
         setup_class<128, false>(c.cls[0], sms);
         setup_class<256, false>(c.cls[1], sms);
         setup_class<256, false>(c.cls[2], sms);
-        setup_class<256, true>(c.cls[3], sms);
-        for (int k = 0; k < 3; k++) {
+        setup_class<256, false>(c.cls[3], sms);
+        setup_class<256, true>(c.cls[4], sms);
+        for (int k = 0; k < kNumClasses - 1; k++) {
             cudaStreamCreateWithFlags(&c.side[k], cudaStreamNonBlocking);
             cudaEventCreateWithFlags(&c.join[k], cudaEventDisableTiming);
         }
@@ -652,16 +671,17 @@ void launch_describe(const DescribeArgs &a, cudaStream_t st, int *launches)
     // The four size classes are independent: fork them onto side streams so their CTAs share the
     // GPU and the tails of the short launches overlap the long ones; join back on `st`.
     cudaEventRecord(c.fork, st);
-    for (int k = 0; k < 3; k++) cudaStreamWaitEvent(c.side[k], c.fork, 0);
+    for (int k = 0; k < kNumClasses - 1; k++) cudaStreamWaitEvent(c.side[k], c.fork, 0);
     k_descriptor<256, false><<<c.cls[1].grid, 256, c.cls[1].smem, st>>>(a, 1, c.cls[1].max_n, c.cls[1].tile_cap);
-    k_descriptor<256, true><<<c.cls[3].grid, 256, c.cls[3].smem, c.side[0]>>>(a, 3, c.cls[3].max_n, c.cls[3].tile_cap);
-    k_descriptor<256, false><<<c.cls[2].grid, 256, c.cls[2].smem, c.side[1]>>>(a, 2, c.cls[2].max_n, c.cls[2].tile_cap);
-    k_descriptor<128, false><<<c.cls[0].grid, 128, c.cls[0].smem, c.side[2]>>>(a, 0, c.cls[0].max_n, c.cls[0].tile_cap);
-    for (int k = 0; k < 3; k++) {
+    k_descriptor<256, true><<<c.cls[4].grid, 256, c.cls[4].smem, c.side[0]>>>(a, 4, c.cls[4].max_n, c.cls[4].tile_cap);
+    k_descriptor<256, false><<<c.cls[3].grid, 256, c.cls[3].smem, c.side[1]>>>(a, 3, c.cls[3].max_n, c.cls[3].tile_cap);
+    k_descriptor<256, false><<<c.cls[2].grid, 256, c.cls[2].smem, c.side[2]>>>(a, 2, c.cls[2].max_n, c.cls[2].tile_cap);
+    k_descriptor<128, false><<<c.cls[0].grid, 128, c.cls[0].smem, c.side[3]>>>(a, 0, c.cls[0].max_n, c.cls[0].tile_cap);
+    for (int k = 0; k < kNumClasses - 1; k++) {
         cudaEventRecord(c.join[k], c.side[k]);
         cudaStreamWaitEvent(st, c.join[k], 0);
     }
-    *launches += 4;
+    *launches += 5;
 }
 
 }  // namespace surfb200

@@ -359,6 +359,7 @@ int run_describe_pack(surf_engine *e, const ImageRef &img, const FrameGeo &geo, 
     a.extended = p.extended;
     a.upright = p.upright;
     a.img_aligned4 = ((reinterpret_cast<uintptr_t>(img.ptr) | img.pitch | img.frame_stride) & 3) == 0;
+    a.img_aligned16 = ((reinterpret_cast<uintptr_t>(img.ptr) | img.pitch | img.frame_stride) & 15) == 0;
     a.misc = e->d_misc;
     a.ndeleted = e->d_ndel;
     a.deleted_slots = e->d_deleted;

@@ -55,19 +55,20 @@ struct ImageRef {
 // the rotated window's bounding box in the image and the n x n window itself are staged in shared
 // memory for classes A-C; class D (n > 184, about 1 % of keypoints) reads the image from global
 // memory and keeps its window in a per-CTA global scratch buffer.
-constexpr int kNumClasses = 4;
-constexpr int kClassMaxN0 = 64, kClassMaxN1 = 128, kClassMaxN2 = 184;  // class D: up to kMaxWindow
+constexpr int kNumClasses = 5;
+constexpr int kClassMaxN0 = 64, kClassMaxN1 = 96, kClassMaxN2 = 128, kClassMaxN3 = 176;  // last class: up to kMaxWindow
 constexpr int kClassDGridPerSm = 2;
 
 // d_misc word layout
 constexpr int kMiscStatus = 1;
-constexpr int kMiscClassCount = 2;   // [4]
-constexpr int kMiscClassHead = 6;    // [4]
+constexpr int kMiscClassCount = 2;   // [kNumClasses]
+constexpr int kMiscClassHead = 8;    // [kNumClasses]
 constexpr int kMiscWords = 16;
 
 struct DescribeArgs {
     ImageRef img;
-    int img_aligned4;     // base, pitch and frame stride are multiples of 4: word loads allowed
+    int img_aligned4;     // base, pitch and frame stride are multiples of 4: word copies allowed
+    int img_aligned16;    // ... multiples of 16: 16-byte copies allowed
     const uint32_t *sum;
     FrameGeo geo;
     surf_keypoint *kps;   // [B][cap], updated in place (angle, size = -1 on deletion)
