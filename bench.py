@@ -190,19 +190,22 @@ def run_ours(args):
         launches[0] += 7
         return 0
 
-    # host-buffer API: pinned frames in, packed keypoints/descriptors/matches out
-    h_kps = torch.empty((cap_total, 7), dtype=torch.float32).pin_memory()
-    h_desc = torch.empty((cap_total, D), dtype=torch.float32).pin_memory()
-    h_matches = torch.empty((cap_total * 2, 4), dtype=torch.int32).pin_memory()
-    h_good = torch.empty((cap_total,), dtype=torch.uint8).pin_memory()
+    # host-buffer API: pinned frames in, packed keypoints/descriptors/matches out.  Two sets of pinned
+    # output buffers alternate so that the device->host copies of step i overlap the kernels of step i+1.
+    hbuf = [dict(kps=torch.empty((cap_total, 7), dtype=torch.float32).pin_memory(),
+                 desc=torch.empty((cap_total, D), dtype=torch.float32).pin_memory(),
+                 matches=torch.empty((cap_total * 2, 4), dtype=torch.int32).pin_memory(),
+                 good=torch.empty((cap_total,), dtype=torch.uint8).pin_memory()) for _ in range(2)]
     bytes_io = {"h2d": 0, "d2h": 0}
 
     def step_e2e(i, _):
+        hb = hbuf[i & 1]
         src = h_pool[(i % POOL_BATCHES) * B:(i % POOL_BATCHES + 1) * B]
         eng.submit(src.data_ptr(), MEM_HOST, B, W_, H_, W_, W_ * H_, True)
-        eng.collect(h_kps.data_ptr(), h_desc.data_ptr(), MEM_HOST, cap_total, offsets)
+        eng.wait_outputs()      # copies of step i-1 (other buffer set) have landed; this set is free again
+        eng.collect(hb["kps"].data_ptr(), hb["desc"].data_ptr(), MEM_HOST, cap_total, offsets)
         n = int(offsets[B])
-        eng.match_prev_to(RATIO, h_matches.data_ptr(), h_good.data_ptr(), MEM_HOST, cap_total)
+        eng.match_prev_to(RATIO, hb["matches"].data_ptr(), hb["good"].data_ptr(), MEM_HOST, cap_total)
         bytes_io["h2d"] = B * W_ * H_
         bytes_io["d2h"] = n * (28 + 4 * D) + 2 * n * 16 + n + (B + 1) * 4
         return 0
@@ -232,6 +235,7 @@ def run_ours(args):
             t = eng.timings()
             for k in stage:
                 stage[k] += t[k]
+        eng.wait_outputs()
         e1.record(stream)
         barrier()
         ms = e0.elapsed_time(e1)
@@ -246,7 +250,9 @@ def run_ours(args):
     ms_dev, stage_ms, clocks = timed(step_device, steps, warmup, sample_clocks=True)
     n_launch = launches[0]
     kp_per_frame = kp_seen[0] / (steps * B)
+    eng.set_async_outputs(True)
     ms_e2e, _, _ = timed(step_e2e, steps, warmup)
+    eng.set_async_outputs(False)
 
     fps = world * B * steps / (ms_dev * 1e-3)
     fps_e2e = world * B * steps / (ms_e2e * 1e-3)

@@ -130,6 +130,11 @@ int surf_collect_batch(surf_engine *e, surf_keypoint *keypoints, float *descript
 int surf_device_results(surf_engine *e, const surf_keypoint **keypoints, const float **descriptors,
                         const int32_t **offsets);
 int surf_sync(surf_engine *e);
+/* Asynchronous-output mode: surf_collect_batch and surf_match_prev enqueue their device->host copies
+ * on a second stream and return without waiting for them, so the copies overlap the next batch's
+ * kernels.  The host buffers are valid after surf_wait_outputs(); alternate two sets of buffers. */
+int surf_set_async_outputs(surf_engine *e, int enable);
+int surf_wait_outputs(surf_engine *e);
 
 /* ---- stage-level exports (parity checks of the per-stage tolerances) ---- */
 

@@ -10,6 +10,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <ctime>
 #include <new>
 #include <vector>
 
@@ -34,6 +35,11 @@ struct surf_engine {
     int device = 0;
     int max_w = 0, max_h = 0, max_b = 0, cap = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;  // device->host result copies in asynchronous-output mode
+    cudaEvent_t ev_copy_done = nullptr, ev_match_copy_done = nullptr, ev_ready = nullptr;
+    bool match_copies_in_flight = false;
+    int async_outputs = 0;
+    bool copies_in_flight = false;
     cudaEvent_t ev[EV_COUNT]{};
     bool ev_valid = false;
 
@@ -318,7 +324,7 @@ void rec(surf_engine *e, Ev which) { cudaEventRecord(e->ev[which], e->stream); }
 int run_detect(surf_engine *e, const ImageRef &img, const uint32_t *msum, const FrameGeo &geo, int B)
 {
     const surf_params &p = e->params;
-    CU(e, cudaMemsetAsync(e->d_counts, 0, sizeof(int) * B, e->stream));
+    launch_zero(e->d_counts, B, e->stream, &e->launches);
     launch_integral(img, B, geo, e->d_sum, e->d_bandsum, 0, e->stream, &e->launches);
     rec(e, EV_INTEGRAL);
     const float thr = (float)p.hessian_threshold;
@@ -343,8 +349,8 @@ int run_describe_pack(surf_engine *e, const ImageRef &img, const FrameGeo &geo, 
                       uint8_t *patches, bool pack)
 {
     const surf_params &p = e->params;
-    CU(e, cudaMemsetAsync(e->d_ndel, 0, sizeof(int) * B, e->stream));
-    CU(e, cudaMemsetAsync(e->d_misc, 0, sizeof(int) * kMiscWords, e->stream));
+    launch_zero(e->d_ndel, B, e->stream, &e->launches);
+    launch_zero(e->d_misc, kMiscWords, e->stream, &e->launches);
     launch_offsets(e->d_counts, nullptr, e->cap, B, e->d_off_in, e->stream, &e->launches);
     DescribeArgs a{};
     a.img = img;
@@ -370,6 +376,7 @@ int run_describe_pack(surf_engine *e, const ImageRef &img, const FrameGeo &geo, 
     launch_describe(a, e->stream, &e->launches);
     rec(e, EV_DESCRIBE);
     if (pack) {
+        if (e->copies_in_flight) CU(e, cudaStreamWaitEvent(e->stream, e->ev_copy_done, 0));
         launch_offsets(e->d_counts, e->d_ndel, e->cap, B, e->d_off_out, e->stream, &e->launches);
         launch_pack(e->sorted, want_desc ? e->d_desc : nullptr, p.extended ? 128 : 64, e->cap, B, e->d_off_in, e->d_ndel,
                     e->d_deleted, e->d_off_out, e->d_out_kp, want_desc ? e->d_out_desc : nullptr, e->stream,
@@ -470,6 +477,10 @@ int surf_create(const surf_params *params, int device, int max_width, int max_he
     }
     for (int i = 0; i < EV_COUNT; i++) cudaEventCreate(&e->ev[i]);
     e->ev_valid = true;
+    cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking);
+    cudaEventCreateWithFlags(&e->ev_copy_done, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&e->ev_match_copy_done, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&e->ev_ready, cudaEventDisableTiming);
     upload_tables();
     rc = alloc_workspace(e);
     if (rc == SURF_OK && cudaGetLastError() != cudaSuccess) rc = SURF_ERR_CUDA;
@@ -490,6 +501,13 @@ void surf_destroy(surf_engine *e)
     free_workspace(e);
     if (e->ev_valid)
         for (int i = 0; i < EV_COUNT; i++) cudaEventDestroy(e->ev[i]);
+    if (e->copy_stream) {
+        cudaStreamSynchronize(e->copy_stream);
+        cudaStreamDestroy(e->copy_stream);
+    }
+    if (e->ev_copy_done) cudaEventDestroy(e->ev_copy_done);
+    if (e->ev_match_copy_done) cudaEventDestroy(e->ev_match_copy_done);
+    if (e->ev_ready) cudaEventDestroy(e->ev_ready);
     if (e->stream) cudaStreamDestroy(e->stream);
     delete e;
 }
@@ -578,6 +596,22 @@ int surf_collect_batch(surf_engine *e, surf_keypoint *keypoints, float *descript
     }
     const cudaMemcpyKind kind = out_mem == SURF_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
     const int D = e->params.extended ? 128 : 64;
+    // Asynchronous-output mode: the copies go to the copy stream (the compute stream is idle here, so no
+    // event is needed) and overlap the next batch's kernels; surf_wait_outputs() completes them.
+    // EV_END is recorded BEFORE the copies are enqueued: the stream's last operations were small D2H
+    // copies, so a timed event recorded after the big copies would queue behind them on the copy engine.
+    if (e->async_outputs) {
+        rec(e, EV_END);
+        CU(e, cudaEventSynchronize(e->ev[EV_END]));
+        collect_timings(e);
+        if (total > 0 && keypoints)
+            CU(e, cudaMemcpyAsync(keypoints, e->d_out_kp, sizeof(surf_keypoint) * total, kind, e->copy_stream));
+        if (total > 0 && descriptors && e->pending.want_desc)
+            CU(e, cudaMemcpyAsync(descriptors, e->d_out_desc, sizeof(float) * D * total, kind, e->copy_stream));
+        CU(e, cudaEventRecord(e->ev_copy_done, e->copy_stream));
+        e->copies_in_flight = true;
+        return SURF_OK;
+    }
     if (total > 0 && keypoints)
         CU(e, cudaMemcpyAsync(keypoints, e->d_out_kp, sizeof(surf_keypoint) * total, kind, e->stream));
     if (total > 0 && descriptors && e->pending.want_desc)
@@ -585,6 +619,27 @@ int surf_collect_batch(surf_engine *e, surf_keypoint *keypoints, float *descript
     rec(e, EV_END);
     CU(e, cudaStreamSynchronize(e->stream));
     collect_timings(e);
+    return SURF_OK;
+}
+
+int surf_set_async_outputs(surf_engine *e, int enable)
+{
+    if (!e) return SURF_ERR_BAD_ARG;
+    int rc = ensure_device(e);
+    if (rc) return rc;
+    CU(e, cudaStreamSynchronize(e->copy_stream));
+    e->async_outputs = enable ? 1 : 0;
+    return SURF_OK;
+}
+
+int surf_wait_outputs(surf_engine *e)
+{
+    if (!e) return SURF_ERR_BAD_ARG;
+    int rc = ensure_device(e);
+    if (rc) return rc;
+    CU(e, cudaStreamSynchronize(e->copy_stream));
+    e->copies_in_flight = false;
+    e->match_copies_in_flight = false;
     return SURF_OK;
 }
 
@@ -1008,33 +1063,20 @@ int surf_match_prev(surf_engine *e, float ratio, surf_dmatch *out, uint8_t *good
         CU(e, cudaMalloc(&e->d_stream_good, nk));
     }
     if (!e->stream_primed) {  // forget the previous frame: an empty predecessor slot
-        CU(e, cudaMemsetAsync(w.pool.count + e->tc_prev_slot, 0, sizeof(int), e->stream));
-        CU(e, cudaMemsetAsync(e->d_prev_off, 0, 2 * sizeof(int), e->stream));
+        launch_zero(w.pool.count + e->tc_prev_slot, 1, e->stream, nullptr);
+        launch_zero(e->d_prev_off, 2, e->stream, nullptr);
     }
-    std::vector<TcSegment> segs(B);
-    std::vector<TcProblem> probs(B);
-    int prev = e->tc_prev_slot;
-    for (int i = 0; i < B; i++) {
-        const int slot = (e->tc_prev_slot + 1 + i) % slots;
-        segs[i] = TcSegment{e->d_out_desc, e->d_off_out + i, 0, 0, slot};
-        TcProblem p{};
-        p.q_slot = slot;
-        p.t_slot = prev;
-        p.qsrc = e->d_out_desc;
-        p.q_off = e->d_off_out + i;
-        p.tsrc = i == 0 ? e->d_prev_desc : e->d_out_desc;
-        p.t_off = i == 0 ? e->d_prev_off : e->d_off_out + i - 1;
-        p.out_off = e->d_off_out + i;
-        probs[i] = p;
-        prev = slot;
-    }
-    CU(e, cudaMemcpyAsync(w.segs, segs.data(), sizeof(TcSegment) * B, cudaMemcpyHostToDevice, e->stream));
-    CU(e, cudaMemcpyAsync(w.probs, probs.data(), sizeof(TcProblem) * B, cudaMemcpyHostToDevice, e->stream));
+    int launches = 0;
+    launch_tc_stream_tables(w.segs, w.probs, B, slots, e->tc_prev_slot, e->d_out_desc, e->d_off_out, e->d_prev_desc,
+                            e->d_prev_off, e->stream, &launches);
+    const int prev = (e->tc_prev_slot + B) % slots;
+    // the previous step's match results may still be on their way to the host (its own event: the
+    // keypoint/descriptor copies of THIS step, just enqueued by surf_collect_batch, must not hold us up)
+    if (e->match_copies_in_flight) CU(e, cudaStreamWaitEvent(e->stream, e->ev_match_copy_done, 0));
     TcMatchArgs a{};
     a.pool = w.pool; a.segs = w.segs; a.n_segs = B; a.probs = w.probs; a.n_probs = B; a.n_splits = 1;
     a.max_q_rows = rows; a.cand = w.cand; a.counters = w.counters; a.redo_list = w.redo; a.dim = D; a.k = 2;
     a.ratio = ratio; a.out = e->d_stream_matches; a.good = e->d_stream_good;
-    int launches = 0;
     launch_tc_match(a, e->stream, &launches);
     e->last_tc_ws = 1;
     // keep the last frame (fp32 rows + its slot) as the next batch's predecessor
@@ -1051,10 +1093,20 @@ int surf_match_prev(surf_engine *e, float ratio, surf_dmatch *out, uint8_t *good
             return fail(e, SURF_ERR_CAPACITY, "%ld keypoints in the batch; the match arrays hold %ld", total, capacity);
         }
         const cudaMemcpyKind kind = out_mem == SURF_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
-        if (out && total)
-            CU(e, cudaMemcpyAsync(out, e->d_stream_matches, sizeof(surf_dmatch) * 2 * total, kind, e->stream));
-        if (good && total) CU(e, cudaMemcpyAsync(good, e->d_stream_good, total, kind, e->stream));
-        CU(e, cudaStreamSynchronize(e->stream));
+        cudaStream_t cs = e->stream;
+        if (e->async_outputs) {  // copy stream waits for the match kernels, the host does not
+            CU(e, cudaEventRecord(e->ev_ready, e->stream));
+            CU(e, cudaStreamWaitEvent(e->copy_stream, e->ev_ready, 0));
+            cs = e->copy_stream;
+        }
+        if (out && total) CU(e, cudaMemcpyAsync(out, e->d_stream_matches, sizeof(surf_dmatch) * 2 * total, kind, cs));
+        if (good && total) CU(e, cudaMemcpyAsync(good, e->d_stream_good, total, kind, cs));
+        if (e->async_outputs) {
+            CU(e, cudaEventRecord(e->ev_match_copy_done, e->copy_stream));
+            e->match_copies_in_flight = true;
+        } else {
+            CU(e, cudaStreamSynchronize(e->stream));
+        }
     }
     return SURF_OK;
 }

@@ -109,6 +109,7 @@ void launch_describe(const DescribeArgs &a, cudaStream_t st, int *launches);
 void launch_pack(const surf_keypoint *kps, const float *desc, int D, int cap, int B, const int *in_offsets,
                  const int *ndel, const int *deleted_slots, const int *out_offsets, surf_keypoint *out_kps,
                  float *out_desc, cudaStream_t st, int *launches);
+void launch_zero(int *p, int n_words, cudaStream_t st, int *launches);
 void upload_tables();  // orientation sample weights + descriptor Gaussian -> __constant__ (per device)
 
 // ---- tensor-core candidate search (surf_match_tc.cu) ----
@@ -167,6 +168,10 @@ struct TcMatchArgs {
 
 size_t tc_candidates_smem(int dim);
 void launch_tc_match(const TcMatchArgs &a, cudaStream_t st, int *launches);
+// Builds the segment / problem tables of the frame-stream matcher on the device: frame i of the batch goes
+// to ring slot (prev_slot + 1 + i) % slots and is matched against the frame before it.
+void launch_tc_stream_tables(TcSegment *segs, TcProblem *probs, int B, int slots, int prev_slot, const float *desc,
+                             const int *off, const float *prev_desc, const int *prev_off, cudaStream_t st, int *launches);
 // copies rows [off[0], off[1]) of src (D floats each) to dst and writes {0, n} to dst_off (device-side count)
 void launch_copy_rows(const float *src, const int *off, int dim, float *dst, int max_rows, int *dst_off, cudaStream_t st,
                       int *launches);

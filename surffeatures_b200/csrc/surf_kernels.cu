@@ -499,6 +499,23 @@ surf_keypoint *launch_sort(surf_keypoint *a, surf_keypoint *b, const int *counts
 }
 
 // ------------------------------------------------------------------------------------------------
+// Zero-fill of small counter arrays as a kernel: cudaMemsetAsync may be executed by a copy engine, where
+// it would queue behind a large device->host result copy of the previous batch (asynchronous-output mode).
+// ------------------------------------------------------------------------------------------------
+__global__ void k_zero_words(int *__restrict__ p, int n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = 0;
+}
+
+void launch_zero(int *p, int n, cudaStream_t st, int *launches)
+{
+    if (n <= 0) return;
+    k_zero_words<<<(n + 255) / 256, 256, 0, st>>>(p, n);
+    if (launches) *launches += 1;
+}
+
+// ------------------------------------------------------------------------------------------------
 // offsets: exclusive prefix of the per-frame counts (single block; B <= a few thousand).
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024) k_offsets(const int *__restrict__ counts, const int *__restrict__ ndel, int cap,

@@ -548,7 +548,7 @@ void launch_tc_match(const TcMatchArgs &a, cudaStream_t st, int *launches)
     dim3 gprep(((size_t)a.pool.slot_rows * G + 255) / 256, a.n_segs);
     if (D == 64) k_tc_prep<64><<<gprep, 256, 0, st>>>(a.segs, a.n_segs, a.pool);
     else k_tc_prep<128><<<gprep, 256, 0, st>>>(a.segs, a.n_segs, a.pool);
-    cudaMemsetAsync(a.counters, 0, 2 * sizeof(int), st);  // [0] work head, [1] redo count
+    launch_zero(a.counters, 2, st, nullptr);  // [0] work head, [1] redo count
 
     static int grids[64][2] = {};
     int dev = 0;
@@ -590,6 +590,38 @@ void launch_tc_match(const TcMatchArgs &a, cudaStream_t st, int *launches)
         k_tc_redo<128><<<sms * 2, 256, 0, st>>>(a.pool, a.probs, a.k, a.ratio, a.out, a.good, a.redo_list, a.counters + 1);
     }
     *launches += 6;
+}
+
+__global__ void k_tc_stream_tables(TcSegment *segs, TcProblem *probs, int B, int slots, int prev_slot, const float *desc,
+                                   const int *off, const float *prev_desc, const int *prev_off)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B) return;
+    const int slot = (prev_slot + 1 + i) % slots;
+    TcSegment sg;
+    sg.src = desc;
+    sg.off = off + i;
+    sg.row0 = 0;
+    sg.n = 0;
+    sg.slot = slot;
+    segs[i] = sg;
+    TcProblem p;
+    p.q_slot = slot;
+    p.t_slot = (prev_slot + i) % slots;
+    p.qsrc = desc;
+    p.q_off = off + i;
+    p.tsrc = i == 0 ? prev_desc : desc;
+    p.t_off = i == 0 ? prev_off : off + i - 1;
+    p.out_off = off + i;
+    p.q_row0 = p.t_row0 = p.out_row0 = 0;
+    probs[i] = p;
+}
+
+void launch_tc_stream_tables(TcSegment *segs, TcProblem *probs, int B, int slots, int prev_slot, const float *desc,
+                             const int *off, const float *prev_desc, const int *prev_off, cudaStream_t st, int *launches)
+{
+    k_tc_stream_tables<<<(B + 127) / 128, 128, 0, st>>>(segs, probs, B, slots, prev_slot, desc, off, prev_desc, prev_off);
+    *launches += 1;
 }
 
 __global__ void __launch_bounds__(256) k_copy_rows(const float *__restrict__ src, const int *__restrict__ off, int dim4,

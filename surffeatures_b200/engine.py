@@ -35,7 +35,8 @@ ABI_SYMBOLS = [
     "surf_detect_and_compute_batch", "surf_submit_batch", "surf_collect_batch", "surf_device_results", "surf_sync",
     "surf_integral", "surf_hessian_layer", "surf_raw_keypoints", "surf_describe_keypoints", "surf_match_knn",
     "surf_match_ratio", "surf_merge_topk", "surf_version", "surf_match_prev", "surf_stream_reset",
-    "surf_device_matches", "surf_set_match_mode", "surf_match_redo_count",
+    "surf_device_matches", "surf_set_match_mode", "surf_match_redo_count", "surf_set_async_outputs",
+    "surf_wait_outputs",
 ]
 
 
@@ -104,6 +105,8 @@ def load_library():
     L.surf_device_matches.argtypes = [vp, C.POINTER(vp), C.POINTER(vp)]
     L.surf_set_match_mode.argtypes = [vp, i32]
     L.surf_match_redo_count.argtypes = [vp, C.POINTER(i32)]
+    L.surf_set_async_outputs.argtypes = [vp, i32]
+    L.surf_wait_outputs.argtypes = [vp]
     L.surf_version.argtypes = []
     L.surf_version.restype = C.c_char_p
     for name in ABI_SYMBOLS:
@@ -285,6 +288,13 @@ class SURF:
 
     def sync(self):
         self._check(self._lib.surf_sync(self._h))
+
+    def set_async_outputs(self, enable: bool):
+        """collect()/match_prev_to() return before their device->host copies finish; see wait_outputs()."""
+        self._check(self._lib.surf_set_async_outputs(self._h, int(bool(enable))))
+
+    def wait_outputs(self):
+        self._check(self._lib.surf_wait_outputs(self._h))
 
     # ---- stage-level exports (parity of the per-stage tolerances) ----
     def integral(self, image, clamp01=False) -> np.ndarray:

@@ -466,3 +466,53 @@ def test_match_prev_stream_equals_pairwise_exact(oracle):
         assert (m["trainIdx"][off[1]:off[2], 0] >= 0).all()
     finally:
         e.close()
+
+
+def test_async_output_mode_gives_identical_results():
+    """Copies on the second stream (overlapping the next batch) must deliver the same bytes."""
+    import torch
+
+    from surffeatures_b200 import KEYPOINT_DTYPE, MEM_HOST, SURF
+
+    frames = speckle.speckle_stream(6, 240, 320, seed=9, fresh=0.0)
+    e = SURF(100, 4, 3, max_width=320, max_height=240, max_batch=2, max_keypoints=4096)
+    try:
+        ref = []
+        for i in range(3):
+            k, d, off = e.detectAndComputeBatchPacked(frames[2 * i:2 * i + 2])
+            m, g = e.match_prev(0.8, n_total=int(off[-1]))
+            ref.append((k.copy(), d.copy(), off.copy(), m.copy(), g.copy()))
+        e.stream_reset()
+        e.set_async_outputs(True)
+        cap = 2 * 4096
+        pinned = torch.from_numpy(frames).pin_memory()
+        bufs = [dict(k=torch.zeros((cap, 7), dtype=torch.float32).pin_memory(), d=torch.zeros((cap, 64)).pin_memory(),
+                     m=torch.zeros((cap * 2, 4), dtype=torch.int32).pin_memory(),
+                     g=torch.zeros((cap,), dtype=torch.uint8).pin_memory()) for _ in range(2)]
+        offs = [np.zeros(3, np.int32) for _ in range(3)]
+        got = []
+        for i in range(3):
+            hb = bufs[i & 1]
+            e.submit(pinned[2 * i:2 * i + 2].data_ptr(), MEM_HOST, 2, 320, 240, 320, 320 * 240, True)
+            e.wait_outputs()
+            if i >= 1:   # the previous step's buffers are complete now
+                pb, po = bufs[(i - 1) & 1], offs[i - 1]
+                n = int(po[-1])
+                got.append((pb["k"].numpy()[:n].copy().view(np.uint8).reshape(-1), pb["d"].numpy()[:n].copy(),
+                            pb["m"].numpy()[:2 * n].copy(), pb["g"].numpy()[:n].copy()))
+            e.collect(hb["k"].data_ptr(), hb["d"].data_ptr(), MEM_HOST, cap, offs[i])
+            e.match_prev_to(0.8, hb["m"].data_ptr(), hb["g"].data_ptr(), MEM_HOST, cap)
+        e.wait_outputs()
+        n = int(offs[2][-1])
+        pb = bufs[0]
+        got.append((pb["k"].numpy()[:n].copy().view(np.uint8).reshape(-1), pb["d"].numpy()[:n].copy(),
+                    pb["m"].numpy()[:2 * n].copy(), pb["g"].numpy()[:n].copy()))
+        for i in range(3):
+            k, d, off, m, g = ref[i]
+            assert np.array_equal(offs[i], off)
+            assert got[i][0].tobytes() == k.tobytes()
+            assert np.array_equal(got[i][1], d)
+            assert got[i][2].tobytes() == m.tobytes()
+            assert np.array_equal(got[i][3].astype(bool), g)
+    finally:
+        e.close()
