@@ -14,6 +14,8 @@
 #include <new>
 #include <vector>
 
+#include <cuda.h>
+
 #include "surf_internal.h"
 
 using namespace surfb200;
@@ -59,6 +61,11 @@ struct surf_engine {
     surf_dmatch *d_match_part = nullptr;  size_t match_part_cap = 0;
     void *d_match_io = nullptr;           size_t match_io_cap = 0;
     int match_exact_only = 0;
+    int use_tma = 1;                 // fused TMA-staged Hessian + maxima kernel for octaves 0-1
+    CUtensorMap tmap[2];             // integral-image tile maps of octaves 0 and 1
+    TileOctave tile_oct[2];
+    int tmap_w = 0, tmap_h = 0, tmap_b = 0, tmap_layers = 0;
+    bool tmap_ok[2] = {false, false};
     int last_tc_ws = -1;  // workspace used by the last tensor-core match (for surf_match_redo_count)
 
     // tensor-core matcher workspaces: [0] generic two-operand calls, [1] the frame stream ring
@@ -146,6 +153,104 @@ OctavePat make_octave(int octave, int lpo, int W, int H)
         scale_boxes(kDm, &L.mask, 1, 9, L.size);
     }
     return p;
+}
+
+// Shared-memory tile geometry and corner offsets of the fused Hessian + maxima kernel for one octave.
+bool make_tile_octave(const OctavePat &pat, TileOctave *out)
+{
+    TileOctave t{};
+    t.step = pat.step;
+    t.rows = pat.rows;
+    t.cols = pat.cols;
+    t.lpo = pat.lpo;
+    t.m_max = 0;
+    for (int l = 0; l < pat.lpo; l++) t.m_max = pat.L[l].m > t.m_max ? pat.L[l].m : t.m_max;
+    int tw = 0, th = 0;
+    for (int l = 0; l < pat.lpo; l++) {
+        const int ex = (kTileW - 1 + t.m_max - pat.L[l].m) * pat.step + pat.L[l].size + 1;
+        const int ey = (kTileH - 1 + t.m_max - pat.L[l].m) * pat.step + pat.L[l].size + 1;
+        tw = ex > tw ? ex : tw;
+        th = ey > th ? ey : th;
+    }
+    t.tile_p = (tw + 3 + 3) & ~3;  // + up to 3 columns: the TMA start column is aligned down to 16 bytes
+    t.tile_h = th;
+    t.tile_bytes = t.tile_p * t.tile_h * 4;
+    if (t.tile_p > 256 || t.tile_h > 256) return false;  // TMA box limit
+    if ((size_t)t.tile_bytes + (size_t)pat.lpo * kTileW * kTileH * 4 > 190 * 1024) return false;
+    for (int l = 0; l < pat.lpo; l++) {
+        const LayerPat &P = pat.L[l];
+        TileLayer &T = t.L[l];
+        T.size = P.size; T.m = P.m; T.ni = P.ni; T.nj = P.nj; T.skip = P.skip; T.mask = P.mask;
+        // the three patterns share their box edges (same cvRound of the same products)
+        if (P.dxx[1].x1 != P.dxx[0].x2 || P.dxx[2].x1 != P.dxx[1].x2 || P.dyy[1].y1 != P.dyy[0].y2 ||
+            P.dyy[2].y1 != P.dyy[1].y2 || P.dxy[2].x1 != P.dxy[0].x1 || P.dxy[3].x1 != P.dxy[1].x1 ||
+            P.dxy[1].y1 != P.dxy[0].y1 || P.dxy[3].y1 != P.dxy[2].y1 || P.dxy[2].x2 != P.dxy[0].x2 ||
+            P.dxy[3].x2 != P.dxy[1].x2 || P.dxy[1].y2 != P.dxy[0].y2 || P.dxy[3].y2 != P.dxy[2].y2 ||
+            P.dxx[1].y1 != P.dxx[0].y1 || P.dxx[2].y2 != P.dxx[0].y2 || P.dyy[1].x1 != P.dyy[0].x1 ||
+            P.dyy[2].x2 != P.dyy[0].x2)
+            return false;
+        const int xx[4] = {P.dxx[0].x1, P.dxx[0].x2, P.dxx[1].x2, P.dxx[2].x2}, xy[2] = {P.dxx[0].y1, P.dxx[0].y2};
+        for (int r = 0; r < 2; r++)
+            for (int c = 0; c < 4; c++) T.dxx[r * 4 + c] = xy[r] * t.tile_p + xx[c];
+        const int yy[4] = {P.dyy[0].y1, P.dyy[0].y2, P.dyy[1].y2, P.dyy[2].y2}, yx[2] = {P.dyy[0].x1, P.dyy[0].x2};
+        for (int r = 0; r < 4; r++)
+            for (int c = 0; c < 2; c++) T.dyy[r * 2 + c] = yy[r] * t.tile_p + yx[c];
+        const int cx[4] = {P.dxy[0].x1, P.dxy[0].x2, P.dxy[1].x1, P.dxy[1].x2};
+        const int cy[4] = {P.dxy[0].y1, P.dxy[0].y2, P.dxy[2].y1, P.dxy[2].y2};
+        for (int r = 0; r < 4; r++)
+            for (int c = 0; c < 4; c++) T.dxy[r * 4 + c] = cy[r] * t.tile_p + cx[c];
+        for (int k = 0; k < 3; k++) {
+            T.w[k] = P.dxx[k].w;
+            T.w[3 + k] = P.dyy[k].w;
+        }
+        for (int k = 0; k < 4; k++) T.w[6 + k] = P.dxy[k].w;
+    }
+    *out = t;
+    return true;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_tiled_fn()
+{
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+        cudaGetLastError();
+    }
+    return fn;
+}
+
+// (Re)builds the TMA descriptors of the integral image for octaves 0 and 1 (3-D: x, y, frame).
+void ensure_tensor_maps(surf_engine *e, const FrameGeo &geo, int B)
+{
+    const int layers = e->params.n_octave_layers;
+    if (e->tmap_w == geo.W && e->tmap_h == geo.H && e->tmap_b == B && e->tmap_layers == layers) return;
+    e->tmap_w = geo.W; e->tmap_h = geo.H; e->tmap_b = B; e->tmap_layers = layers;
+    e->tmap_ok[0] = e->tmap_ok[1] = false;
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc || !e->use_tma) return;
+    for (int o = 0; o < 2 && o < e->params.n_octaves; o++) {
+        const OctavePat pat = make_octave(o, layers + 2, geo.W, geo.H);
+        if (!make_tile_octave(pat, &e->tile_oct[o])) continue;
+        const TileOctave &t = e->tile_oct[o];
+        cuuint64_t dims[3] = {(cuuint64_t)(geo.W + 1), (cuuint64_t)(geo.H + 1), (cuuint64_t)B};
+        cuuint64_t strides[2] = {(cuuint64_t)geo.SP * 4, (cuuint64_t)geo.sum_frame * 4};
+        cuuint32_t box[3] = {(cuuint32_t)t.tile_p, (cuuint32_t)t.tile_h, 1};
+        cuuint32_t estr[3] = {1, 1, 1};
+        CUresult r = enc(&e->tmap[o], CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, e->d_sum, dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        e->tmap_ok[o] = (r == CUDA_SUCCESS);
+    }
 }
 
 size_t det_octave_words(const surf_params &p, int octave, int W, int H)
@@ -238,7 +343,7 @@ int alloc_workspace(surf_engine *e)
     CU(e, cudaMalloc(&e->d_kp_b, nk * sizeof(surf_keypoint)));
     CU(e, cudaMalloc(&e->d_out_kp, nk * sizeof(surf_keypoint)));
     CU(e, cudaMalloc(&e->d_deleted, nk * sizeof(int)));
-    CU(e, cudaMalloc(&e->d_counts, sizeof(int) * B));
+    CU(e, cudaMalloc(&e->d_counts, sizeof(int) * (B + 1)));  // + status word of the TMA kernel
     CU(e, cudaMalloc(&e->d_ndel, sizeof(int) * B));
     CU(e, cudaMalloc(&e->d_off_in, sizeof(int) * (B + 1)));
     CU(e, cudaMalloc(&e->d_off_out, sizeof(int) * (B + 1)));
@@ -324,14 +429,22 @@ void rec(surf_engine *e, Ev which) { cudaEventRecord(e->ev[which], e->stream); }
 int run_detect(surf_engine *e, const ImageRef &img, const uint32_t *msum, const FrameGeo &geo, int B)
 {
     const surf_params &p = e->params;
-    launch_zero(e->d_counts, B, e->stream, &e->launches);
+    launch_zero(e->d_counts, B + 1, e->stream, &e->launches);  // per-frame counters + status word
     launch_integral(img, B, geo, e->d_sum, e->d_bandsum, 0, e->stream, &e->launches);
     rec(e, EV_INTEGRAL);
     const float thr = (float)p.hessian_threshold;
     float *det = e->d_det;
+    ensure_tensor_maps(e, geo, B);
     for (int o = 0; o < p.n_octaves; o++) {
         const OctavePat pat = make_octave(o, p.n_octave_layers + 2, geo.W, geo.H);
         const size_t det_frame = (size_t)pat.lpo * pat.rows * pat.cols;
+        if (o < 2 && e->tmap_ok[o]) {
+            // fused: integral tile by TMA -> determinants in shared memory -> maxima; no det pyramid in HBM
+            launch_hessian_nms_tma(e->tmap[o], e->tile_oct[o], msum, geo, o, thr, e->d_kp_a, e->d_counts, e->cap, B,
+                                   e->stream, &e->launches);
+            det += det_frame * B;
+            continue;
+        }
         launch_hessian(e->d_sum, geo, pat, det, det_frame, B, e->stream, &e->launches);
         launch_nms(det, det_frame, e->d_sum, msum, geo, pat, o, p.n_octave_layers, thr, e->d_kp_a, e->d_counts, e->cap,
                    B, e->stream, &e->launches);
@@ -395,6 +508,7 @@ int fetch_counts(surf_engine *e, int B)
     CU(e, cudaMemcpyAsync(h + B, e->d_ndel, sizeof(int) * B, cudaMemcpyDeviceToHost, e->stream));
     CU(e, cudaMemcpyAsync(h + 2 * B, e->d_off_out, sizeof(int) * (B + 1), cudaMemcpyDeviceToHost, e->stream));
     CU(e, cudaMemcpyAsync(h + 3 * B + 1, e->d_misc, sizeof(int) * kMiscWords, cudaMemcpyDeviceToHost, e->stream));
+    CU(e, cudaMemcpyAsync(h + 3 * B + 1 + kMiscWords, e->d_counts + B, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
     return SURF_OK;
 }
 
@@ -408,6 +522,8 @@ int check_counts(surf_engine *e, int B)
         return fail(e, SURF_ERR_CAPACITY, "a frame produced %d raw keypoints; the engine was created for %d per frame",
                     worst, e->cap);
     }
+    if (h[3 * B + 1 + kMiscWords] & 1)
+        return fail(e, SURF_ERR_CUDA, "internal error: a TMA tile load of the integral image did not complete");
     if (h[3 * B + 1 + kMiscStatus] & 2)
         return fail(e, SURF_ERR_CUDA, "internal error: descriptor tile capacity exceeded");
     if (h[3 * B + 1 + kMiscStatus] & 1)
@@ -471,6 +587,7 @@ int surf_create(const surf_params *params, int device, int max_width, int max_he
     e->max_h = max_height;
     e->max_b = max_batch;
     e->cap = (max_keypoints + 127) & ~127;
+    if (getenv("SURF_B200_NO_TMA")) e->use_tma = 0;
     if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess) {
         delete e;
         return SURF_ERR_CUDA;
@@ -520,6 +637,7 @@ int surf_set_params(surf_engine *e, const surf_params *params)
     if ((rc = ensure_device(e))) return rc;
     CU(e, cudaStreamSynchronize(e->stream));
     e->params = *params;
+    e->tmap_w = 0;  // layer tables depend on the parameters
     return alloc_det_and_desc(e);
 }
 
@@ -834,8 +952,10 @@ int surf_raw_keypoints(surf_engine *e, const uint8_t *image, int width, int heig
     if ((rc = stage_mask(e, in, geo, &msum))) return rc;
     rec(e, EV_H2D);
     if ((rc = run_detect(e, img, msum, geo, 1))) return rc;
-    CU(e, cudaMemcpyAsync(e->h_pin, e->d_counts, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+    CU(e, cudaMemcpyAsync(e->h_pin, e->d_counts, 2 * sizeof(int), cudaMemcpyDeviceToHost, e->stream));
     CU(e, cudaStreamSynchronize(e->stream));
+    if (e->h_pin[1] & 1)
+        return fail(e, SURF_ERR_CUDA, "internal error: a TMA tile load of the integral image did not complete");
     const int n = e->h_pin[0];
     *n_out = n;
     if (n > e->cap || n > capacity) {

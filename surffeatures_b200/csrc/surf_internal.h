@@ -1,6 +1,7 @@
 // surf_internal.h -- types shared by the host engine and the sm_100a kernels (not part of the ABI).
 #pragma once
 
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -37,6 +38,27 @@ struct LayerPat {
 struct OctavePat {
     int step, rows, cols, lpo;  // sampling step 2^o, sample grid, layers in this octave
     LayerPat L[kMaxLayersPerOctave];
+};
+
+// Fused, TMA-staged Hessian + maxima kernel (octaves whose integral tile fits shared memory).
+constexpr int kTileW = 64, kTileH = 16;      // samples per CTA incl. the 1-sample halo (useful: 62 x 14)
+constexpr int kTileThreads = kTileW * kTileH;
+
+struct TileLayer {
+    int dxx[8];   // word offsets of the 2 x 4 Dxx corners in the tile: row-major (y1: x0..x3, y2: x0..x3)
+    int dyy[8];   // 4 x 2 Dyy corners: (y0: x1, x2), (y1: ...), ...
+    int dxy[16];  // 4 x 4 Dxy corners, row-major
+    float w[10];  // box weights: Dxx[3], Dyy[3], Dxy[4]
+    int size, m, ni, nj, skip;
+    Box mask;
+};
+
+struct TileOctave {
+    int step, rows, cols, lpo;
+    int m_max;               // largest layer margin (samples)
+    int tile_p, tile_h;      // integral tile: pitch in words (multiple of 4) and rows
+    int tile_bytes;
+    TileLayer L[kMaxLayersPerOctave];
 };
 
 struct FrameGeo {
@@ -99,6 +121,9 @@ void launch_hessian(const uint32_t *sum, const FrameGeo &geo, const OctavePat &p
 void launch_nms(const float *det, size_t det_frame, const uint32_t *sum, const uint32_t *msum, const FrameGeo &geo,
                 const OctavePat &pat, int octave, int n_mid, float thr, surf_keypoint *raw, int *counts, int cap, int B,
                 cudaStream_t st, int *launches);
+void launch_hessian_nms_tma(const CUtensorMap &tmap, const TileOctave &oct, const uint32_t *msum, const FrameGeo &geo,
+                            int octave, float thr, surf_keypoint *raw, int *counts, int cap, int B, cudaStream_t st,
+                            int *launches);
 // Sorts every frame's raw keypoints (response desc, size desc, octave desc, y desc, x asc).
 // Returns the buffer (a or b) that holds the sorted result.
 surf_keypoint *launch_sort(surf_keypoint *a, surf_keypoint *b, const int *counts, int cap, int B, cudaStream_t st,

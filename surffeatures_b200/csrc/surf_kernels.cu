@@ -16,6 +16,8 @@
 #include <cfloat>
 #include <cmath>
 
+#include <cuda.h>
+
 #include "surf_internal.h"
 
 namespace surfb200 {
@@ -385,6 +387,203 @@ void launch_nms(const float *det, size_t det_frame, const uint32_t *sum, const u
     dim3 grid((pat.cols + 31) / 32, (pat.rows + 7) / 8, B * n_mid), block(32, 8);
     k_nms<<<grid, block, 0, st>>>(det, det_frame, sum, msum, geo.SP, geo.sum_frame, pat, octave, n_mid, thr, raw, counts,
                                   cap);
+    *launches += 1;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2+K3 fused, TMA-staged (octaves 0 and 1): one CTA computes the Hessian determinant of every layer
+// of the octave for a 16 x 64 tile of samples from an integral-image tile that a single
+// cp.async.bulk.tensor (TMA) load placed in shared memory, keeps the determinants in shared memory,
+// and runs the 3x3x3 maxima search + refinement on the inner 14 x 62 samples.  The determinant
+// pyramid is never written to HBM (B2/B3 of SURVEY.md section 8d shrink to O*A + 28 N).
+// Arithmetic is identical to k_hessian / k_nms (same box sums, same fp32/fp64 steps).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_addr_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ bool tile_mbar_wait(uint32_t bar, uint32_t parity)
+{
+    uint32_t done = 0;
+    for (uint32_t spin = 0; !done; spin++) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (spin > (1u << 24)) return false;  // a load that never lands must not hang the GPU
+    }
+    return true;
+}
+
+// box responses from the shared-memory tile; corner offsets are words relative to the sample's origin
+__device__ __forceinline__ void tile_responses(const int *__restrict__ o, const TileLayer &T, float &dx, float &dy, float &dc)
+{
+    {   // Dxx: 2 rows x 4 columns of corners -> three boxes
+        const int c0 = o[T.dxx[4]] - o[T.dxx[0]], c1 = o[T.dxx[5]] - o[T.dxx[1]];
+        const int c2 = o[T.dxx[6]] - o[T.dxx[2]], c3 = o[T.dxx[7]] - o[T.dxx[3]];
+        double d = (double)((float)(c1 - c0) * T.w[0]);
+        d += (double)((float)(c2 - c1) * T.w[1]);
+        d += (double)((float)(c3 - c2) * T.w[2]);
+        dx = (float)d;
+    }
+    {   // Dyy: 4 rows x 2 columns
+        const int r0 = o[T.dyy[1]] - o[T.dyy[0]], r1 = o[T.dyy[3]] - o[T.dyy[2]];
+        const int r2 = o[T.dyy[5]] - o[T.dyy[4]], r3 = o[T.dyy[7]] - o[T.dyy[6]];
+        double d = (double)((float)(r1 - r0) * T.w[3]);
+        d += (double)((float)(r2 - r1) * T.w[4]);
+        d += (double)((float)(r3 - r2) * T.w[5]);
+        dy = (float)d;
+    }
+    {   // Dxy: 4 x 4 corners, four boxes; dxy[r * 4 + c] = corner (y_r, x_c)
+        const int b0 = o[T.dxy[0]] + o[T.dxy[5]] - o[T.dxy[4]] - o[T.dxy[1]];
+        const int b1 = o[T.dxy[2]] + o[T.dxy[7]] - o[T.dxy[6]] - o[T.dxy[3]];
+        const int b2 = o[T.dxy[8]] + o[T.dxy[13]] - o[T.dxy[12]] - o[T.dxy[9]];
+        const int b3 = o[T.dxy[10]] + o[T.dxy[15]] - o[T.dxy[14]] - o[T.dxy[11]];
+        double d = (double)((float)b0 * T.w[6]);
+        d += (double)((float)b1 * T.w[7]);
+        d += (double)((float)b2 * T.w[8]);
+        d += (double)((float)b3 * T.w[9]);
+        dc = (float)d;
+    }
+}
+
+__global__ void __launch_bounds__(kTileThreads) k_hessian_nms_tma(const __grid_constant__ CUtensorMap tmap,
+                                                                  const __grid_constant__ TileOctave oct,
+                                                                  const uint32_t *__restrict__ msum, int SP, int octave,
+                                                                  float thr, surf_keypoint *__restrict__ raw,
+                                                                  int *__restrict__ counts, int cap)
+{
+    extern __shared__ __align__(128) unsigned char tile_smem_raw[];
+    // TMA tile destinations must be 128-byte aligned: align by hand (the launch reserves the slack)
+    unsigned char *tile_smem = tile_smem_raw + ((128u - (smem_addr_u32(tile_smem_raw) & 127u)) & 127u);
+    int *s_tile = reinterpret_cast<int *>(tile_smem);                        // tile_h x tile_p words
+    float *s_det = reinterpret_cast<float *>(tile_smem + oct.tile_bytes);    // [lpo][16][64]
+    __shared__ __align__(8) uint64_t s_bar;
+
+    const int tid = threadIdx.x;
+    const int tj = tid & (kTileW - 1), ti = tid / kTileW;
+    const int b = blockIdx.z;
+    const int j0 = blockIdx.x * (kTileW - 2), i0 = blockIdx.y * (kTileH - 2);  // first useful sample of the tile
+    const int step = oct.step;
+    const uint32_t bar = smem_addr_u32(&s_bar);
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)oct.tile_bytes) : "memory");
+        // the innermost TMA coordinate must be 16-byte aligned: start at the word-aligned column at or
+        // left of the tile origin (the tile pitch leaves room for the up-to-3-column shift)
+        const int x0 = ((j0 - 1 - oct.m_max) * step) & ~3, y0 = (i0 - 1 - oct.m_max) * step;
+        asm volatile(
+            "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+            ::"r"(smem_addr_u32(s_tile)), "l"(&tmap), "r"(x0), "r"(y0), "r"(b), "r"(bar)
+            : "memory");
+    }
+    const int xshift = ((j0 - 1 - oct.m_max) * step) & 3;
+    if (!tile_mbar_wait(bar, 0)) {  // reported as an error by the host; never silently wrong
+        if (tid == 0) atomicOr(counts + gridDim.z, 1);  // status word right after the per-frame counters
+        return;
+    }
+
+    // ---- determinants of all layers for this thread's sample ----
+    const int i = i0 - 1 + ti, j = j0 - 1 + tj;
+    const bool in_grid = i >= 0 && j >= 0 && i < oct.rows && j < oct.cols;
+    for (int l = 0; l < oct.lpo; l++) {
+        const TileLayer &T = oct.L[l];
+        float v = 0.f;
+        const int ii = i - T.m, jj = j - T.m;
+        if (in_grid && !T.skip && ii >= 0 && ii < T.ni && jj >= 0 && jj < T.nj) {
+            const int *o = s_tile + ((ti + oct.m_max - T.m) * step) * oct.tile_p + (tj + oct.m_max - T.m) * step + xshift;
+            float dx, dy, dc;
+            tile_responses(o, T, dx, dy, dc);
+            v = dx * dy - 0.81f * dc * dc;
+        }
+        s_det[(l * kTileH + ti) * kTileW + tj] = v;
+    }
+    __syncthreads();
+
+    // ---- maxima of the middle layers on the inner samples ----
+    const bool inner = ti >= 1 && ti < kTileH - 1 && tj >= 1 && tj < kTileW - 1 && in_grid;
+    for (int l = 1; l <= oct.lpo - 2; l++) {
+        const TileLayer &T = oct.L[l];
+        const int size = T.size;
+        const int margin = (oct.L[l + 1].size / 2) / step + 1;
+        bool found = false;
+        surf_keypoint kp;
+        if (inner && i >= margin && i < oct.rows - margin && j >= margin && j < oct.cols - margin) {
+            const float *d1 = s_det + (l * kTileH + ti) * kTileW + tj;
+            const float v = *d1;
+            if (v > thr) {
+                float N[3][9];
+#pragma unroll
+                for (int k = 0; k < 3; k++)
+#pragma unroll
+                    for (int r = 0; r < 3; r++)
+#pragma unroll
+                        for (int q = 0; q < 3; q++) N[k][r * 3 + q] = d1[(k - 1) * (kTileH * kTileW) + (r - 1) * kTileW + (q - 1)];
+                const int si = step * (i - (size / 2) / step);
+                const int sj = step * (j - (size / 2) / step);
+                bool keep = true;
+                if (msum) {
+                    const int *mo = reinterpret_cast<const int *>(msum) + (size_t)si * SP + sj;
+                    const float mv = (float)(double)box_term(mo, SP, T.mask);
+                    keep = !(mv < 0.5f);
+                }
+                if (keep) {
+                    bool is_max = true;
+#pragma unroll
+                    for (int k = 0; k < 3; k++)
+#pragma unroll
+                        for (int q = 0; q < 9; q++)
+                            if (!(k == 1 && q == 4)) is_max = is_max && (v > N[k][q]);
+                    if (is_max) {
+                        kp.x = sj + (size - 1) * 0.5f;
+                        kp.y = si + (size - 1) * 0.5f;
+                        kp.size = (float)size;
+                        kp.angle = -1.f;
+                        kp.response = v;
+                        kp.octave = octave;
+                        const int *o = s_tile + ((ti + oct.m_max - T.m) * step) * oct.tile_p + (tj + oct.m_max - T.m) * step + xshift;
+                        float dx, dy, dc;
+                        tile_responses(o, T, dx, dy, dc);
+                        const float tr = dx + dy;
+                        kp.class_id = (tr > 0) - (tr < 0);
+                        found = refine_maximum(N, step, size - oct.L[l - 1].size, kp);
+                    }
+                }
+            }
+        }
+        const unsigned m = __ballot_sync(FULL_MASK, found);
+        if (m) {
+            const int lane = tid & 31;
+            const int leader = __ffs(m) - 1;
+            int base = 0;
+            if (lane == leader) base = atomicAdd(counts + b, __popc(m));
+            base = __shfl_sync(FULL_MASK, base, leader);
+            const int pos = base + __popc(m & ((1u << lane) - 1));
+            if (found && pos < cap) raw[(size_t)b * cap + pos] = kp;
+        }
+    }
+}
+
+void launch_hessian_nms_tma(const CUtensorMap &tmap, const TileOctave &oct, const uint32_t *msum, const FrameGeo &geo,
+                            int octave, float thr, surf_keypoint *raw, int *counts, int cap, int B, cudaStream_t st,
+                            int *launches)
+{
+    if (oct.rows <= 0 || oct.cols <= 0) return;
+    const size_t smem = (size_t)oct.tile_bytes + (size_t)oct.lpo * kTileH * kTileW * sizeof(float) + 128;
+    static size_t attr_set[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (attr_set[dev & 63] < smem) {
+        cudaFuncSetAttribute(k_hessian_nms_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        attr_set[dev & 63] = 200 * 1024;
+    }
+    dim3 grid((oct.cols + kTileW - 3) / (kTileW - 2), (oct.rows + kTileH - 3) / (kTileH - 2), B);
+    k_hessian_nms_tma<<<grid, kTileThreads, smem, st>>>(tmap, oct, msum, geo.SP, octave, thr, raw, counts, cap);
     *launches += 1;
 }
 
