@@ -569,11 +569,223 @@ __global__ void __launch_bounds__(kTileThreads) k_hessian_nms_tma(const __grid_c
     }
 }
 
+// Compile-time variant: octave and layer count are template parameters, the layer loop is fully
+// unrolled and every filter size, box corner and tile offset folds to a constant, so each corner read
+// is one LDS with an immediate offset.  (The weights are the same IEEE fp32 quotients whether the
+// compiler folds them or not.)  Geometry formulas are those of make_octave / make_tile_octave.
+template <int OCT, int LPO>
+struct TileC {
+    static constexpr int step = 1 << OCT;
+    static constexpr int size_max = (9 + 6 * (LPO - 1)) << OCT;
+    static constexpr int m_max = (size_max / 2) >> OCT;
+    static constexpr int tile_w = (kTileW - 1) * step + size_max + 1;
+    static constexpr int tile_h = (kTileH - 1) * step + size_max + 1;
+    static constexpr int tile_p = (tile_w + 3 + 3) & ~3;
+    static constexpr int tile_bytes = tile_p * tile_h * 4;
+};
+
+template <int OCT, int LPO>
+__device__ __forceinline__ void layer_responses_c(const int *__restrict__ o, int l, float &dx, float &dy, float &dc)
+{
+    constexpr int P = TileC<OCT, LPO>::tile_p;
+    const int size = (9 + 6 * l) << OCT;
+    const float ratio = (float)size / 9;
+    const int r0 = __float2int_rn(ratio * 0), r1 = __float2int_rn(ratio * 1), r2 = __float2int_rn(ratio * 2);
+    const int r3 = __float2int_rn(ratio * 3), r4 = __float2int_rn(ratio * 4), r5 = __float2int_rn(ratio * 5);
+    const int r6 = __float2int_rn(ratio * 6), r7 = __float2int_rn(ratio * 7), r8 = __float2int_rn(ratio * 8);
+    const int r9 = __float2int_rn(ratio * 9);
+    {   // Dxx: rows r2, r7; columns r0, r3, r6, r9
+        const int c0 = o[r7 * P + r0] - o[r2 * P + r0], c1 = o[r7 * P + r3] - o[r2 * P + r3];
+        const int c2 = o[r7 * P + r6] - o[r2 * P + r6], c3 = o[r7 * P + r9] - o[r2 * P + r9];
+        const float w0 = 1 / ((float)(r3 - r0) * (r7 - r2)), w1 = -2 / ((float)(r6 - r3) * (r7 - r2));
+        const float w2 = 1 / ((float)(r9 - r6) * (r7 - r2));
+        double d = (double)((float)(c1 - c0) * w0);
+        d += (double)((float)(c2 - c1) * w1);
+        d += (double)((float)(c3 - c2) * w2);
+        dx = (float)d;
+    }
+    {   // Dyy: rows r0, r3, r6, r9; columns r2, r7
+        const int q0 = o[r0 * P + r7] - o[r0 * P + r2], q1 = o[r3 * P + r7] - o[r3 * P + r2];
+        const int q2 = o[r6 * P + r7] - o[r6 * P + r2], q3 = o[r9 * P + r7] - o[r9 * P + r2];
+        const float w0 = 1 / ((float)(r7 - r2) * (r3 - r0)), w1 = -2 / ((float)(r7 - r2) * (r6 - r3));
+        const float w2 = 1 / ((float)(r7 - r2) * (r9 - r6));
+        double d = (double)((float)(q1 - q0) * w0);
+        d += (double)((float)(q2 - q1) * w1);
+        d += (double)((float)(q3 - q2) * w2);
+        dy = (float)d;
+    }
+    {   // Dxy: rows / columns r1, r4, r5, r8
+        const int b0 = o[r1 * P + r1] + o[r4 * P + r4] - o[r4 * P + r1] - o[r1 * P + r4];
+        const int b1 = o[r1 * P + r5] + o[r4 * P + r8] - o[r4 * P + r5] - o[r1 * P + r8];
+        const int b2 = o[r5 * P + r1] + o[r8 * P + r4] - o[r8 * P + r1] - o[r5 * P + r4];
+        const int b3 = o[r5 * P + r5] + o[r8 * P + r8] - o[r8 * P + r5] - o[r5 * P + r8];
+        const float w0 = 1 / ((float)(r4 - r1) * (r4 - r1)), w1 = -1 / ((float)(r8 - r5) * (r4 - r1));
+        const float w2 = -1 / ((float)(r4 - r1) * (r8 - r5)), w3 = 1 / ((float)(r8 - r5) * (r8 - r5));
+        double d = (double)((float)b0 * w0);
+        d += (double)((float)b1 * w1);
+        d += (double)((float)b2 * w2);
+        d += (double)((float)b3 * w3);
+        dc = (float)d;
+    }
+}
+
+template <int OCT, int LPO>
+__global__ void __launch_bounds__(kTileThreads) k_hessian_nms_tma_c(const __grid_constant__ CUtensorMap tmap, int W, int H,
+                                                                    const uint32_t *__restrict__ msum, int SP, float thr,
+                                                                    surf_keypoint *__restrict__ raw,
+                                                                    int *__restrict__ counts, int cap)
+{
+    using C = TileC<OCT, LPO>;
+    constexpr int step = C::step;
+    extern __shared__ __align__(128) unsigned char tile_smem_raw[];
+    unsigned char *tile_smem = tile_smem_raw + ((128u - (smem_addr_u32(tile_smem_raw) & 127u)) & 127u);
+    int *s_tile = reinterpret_cast<int *>(tile_smem);
+    float *s_det = reinterpret_cast<float *>(tile_smem + C::tile_bytes);
+    __shared__ __align__(8) uint64_t s_bar;
+
+    const int tid = threadIdx.x;
+    const int tj = tid & (kTileW - 1), ti = tid / kTileW;
+    const int b = blockIdx.z;
+    const int j0 = blockIdx.x * (kTileW - 2), i0 = blockIdx.y * (kTileH - 2);
+    const int rows = H >> OCT, cols = W >> OCT;
+    const uint32_t bar = smem_addr_u32(&s_bar);
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)C::tile_bytes) : "memory");
+        const int x0 = ((j0 - 1 - C::m_max) * step) & ~3, y0 = (i0 - 1 - C::m_max) * step;
+        asm volatile(
+            "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+            ::"r"(smem_addr_u32(s_tile)), "l"(&tmap), "r"(x0), "r"(y0), "r"(b), "r"(bar)
+            : "memory");
+    }
+    const int xshift = ((j0 - 1 - C::m_max) * step) & 3;
+    if (!tile_mbar_wait(bar, 0)) {
+        if (tid == 0) atomicOr(counts + gridDim.z, 1);
+        return;
+    }
+    const int i = i0 - 1 + ti, j = j0 - 1 + tj;
+    const bool in_grid = i >= 0 && j >= 0 && i < rows && j < cols;
+#pragma unroll
+    for (int l = 0; l < LPO; l++) {
+        const int size = (9 + 6 * l) << OCT;
+        const int m = (size / 2) >> OCT;
+        const int ni = 1 + (H - size) / step, nj = 1 + (W - size) / step;  // only used when the layer fits
+        float v = 0.f;
+        const int ii = i - m, jj = j - m;
+        if (in_grid && size <= H && size <= W && ii >= 0 && ii < ni && jj >= 0 && jj < nj) {
+            const int *o = s_tile + ((ti + C::m_max - m) * step) * C::tile_p + (tj + C::m_max - m) * step + xshift;
+            float dx, dy, dc;
+            layer_responses_c<OCT, LPO>(o, l, dx, dy, dc);
+            v = dx * dy - 0.81f * dc * dc;
+        }
+        s_det[(l * kTileH + ti) * kTileW + tj] = v;
+    }
+    __syncthreads();
+
+    const bool inner = ti >= 1 && ti < kTileH - 1 && tj >= 1 && tj < kTileW - 1 && in_grid;
+#pragma unroll
+    for (int l = 1; l <= LPO - 2; l++) {
+        const int size = (9 + 6 * l) << OCT;
+        const int m = (size / 2) >> OCT;
+        const int size_up = (9 + 6 * (l + 1)) << OCT, size_dn = (9 + 6 * (l - 1)) << OCT;
+        const int margin = (size_up / 2) / step + 1;
+        bool found = false;
+        surf_keypoint kp;
+        if (inner && i >= margin && i < rows - margin && j >= margin && j < cols - margin) {
+            const float *d1 = s_det + (l * kTileH + ti) * kTileW + tj;
+            const float v = *d1;
+            if (v > thr) {
+                float N[3][9];
+#pragma unroll
+                for (int k = 0; k < 3; k++)
+#pragma unroll
+                    for (int r = 0; r < 3; r++)
+#pragma unroll
+                        for (int q = 0; q < 3; q++) N[k][r * 3 + q] = d1[(k - 1) * (kTileH * kTileW) + (r - 1) * kTileW + (q - 1)];
+                const int si = step * (i - (size / 2) / step);
+                const int sj = step * (j - (size / 2) / step);
+                bool keep = true;
+                if (msum) {
+                    // (0,0,9,9) pattern resized: corners at cvRound(ratio * 0) and cvRound(ratio * 9)
+                    const float ratio = (float)size / 9;
+                    const int e = __float2int_rn(ratio * 9);
+                    const int *mo = reinterpret_cast<const int *>(msum) + (size_t)si * SP + sj;
+                    const int sm = __ldg(mo) + __ldg(mo + e * SP + e) - __ldg(mo + e * SP) - __ldg(mo + e);
+                    const float mv = (float)(double)((float)sm * (1 / ((float)e * e)));
+                    keep = !(mv < 0.5f);
+                }
+                if (keep) {
+                    bool is_max = true;
+#pragma unroll
+                    for (int k = 0; k < 3; k++)
+#pragma unroll
+                        for (int q = 0; q < 9; q++)
+                            if (!(k == 1 && q == 4)) is_max = is_max && (v > N[k][q]);
+                    if (is_max) {
+                        kp.x = sj + (size - 1) * 0.5f;
+                        kp.y = si + (size - 1) * 0.5f;
+                        kp.size = (float)size;
+                        kp.angle = -1.f;
+                        kp.response = v;
+                        kp.octave = OCT;
+                        const int *o = s_tile + ((ti + C::m_max - m) * step) * C::tile_p + (tj + C::m_max - m) * step + xshift;
+                        float dx, dy, dc;
+                        layer_responses_c<OCT, LPO>(o, l, dx, dy, dc);
+                        const float tr = dx + dy;
+                        kp.class_id = (tr > 0) - (tr < 0);
+                        found = refine_maximum(N, step, size - size_dn, kp);
+                    }
+                }
+            }
+        }
+        const unsigned mk = __ballot_sync(FULL_MASK, found);
+        if (mk) {
+            const int lane = tid & 31;
+            const int leader = __ffs(mk) - 1;
+            int base = 0;
+            if (lane == leader) base = atomicAdd(counts + b, __popc(mk));
+            base = __shfl_sync(FULL_MASK, base, leader);
+            const int pos = base + __popc(mk & ((1u << lane) - 1));
+            if (found && pos < cap) raw[(size_t)b * cap + pos] = kp;
+        }
+    }
+}
+
+template <int OCT, int LPO>
+static void launch_tma_c(const CUtensorMap &tmap, const TileOctave &oct, const uint32_t *msum, const FrameGeo &geo, float thr,
+                         surf_keypoint *raw, int *counts, int cap, int B, cudaStream_t st)
+{
+    using C = TileC<OCT, LPO>;
+    const size_t smem = (size_t)C::tile_bytes + (size_t)LPO * kTileH * kTileW * sizeof(float) + 128;
+    static bool attr_set[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!attr_set[dev & 63]) {
+        cudaFuncSetAttribute(k_hessian_nms_tma_c<OCT, LPO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        attr_set[dev & 63] = true;
+    }
+    dim3 grid((oct.cols + kTileW - 3) / (kTileW - 2), (oct.rows + kTileH - 3) / (kTileH - 2), B);
+    k_hessian_nms_tma_c<OCT, LPO><<<grid, kTileThreads, smem, st>>>(tmap, geo.W, geo.H, msum, geo.SP, thr, raw, counts, cap);
+}
+
 void launch_hessian_nms_tma(const CUtensorMap &tmap, const TileOctave &oct, const uint32_t *msum, const FrameGeo &geo,
                             int octave, float thr, surf_keypoint *raw, int *counts, int cap, int B, cudaStream_t st,
                             int *launches)
 {
     if (oct.rows <= 0 || oct.cols <= 0) return;
+    // compile-time variants for the common layer counts (nOctaveLayers 2 and 3); tile geometry must agree
+    #define SURF_TRY_C(O, L)                                                                                     \
+        if (octave == O && oct.lpo == L && oct.tile_p == TileC<O, L>::tile_p && oct.tile_h == TileC<O, L>::tile_h) { \
+            launch_tma_c<O, L>(tmap, oct, msum, geo, thr, raw, counts, cap, B, st);                              \
+            *launches += 1;                                                                                      \
+            return;                                                                                              \
+        }
+    SURF_TRY_C(0, 4) SURF_TRY_C(0, 5) SURF_TRY_C(1, 4) SURF_TRY_C(1, 5)
+    #undef SURF_TRY_C
     const size_t smem = (size_t)oct.tile_bytes + (size_t)oct.lpo * kTileH * kTileW * sizeof(float) + 128;
     static size_t attr_set[64] = {};
     int dev = 0;
