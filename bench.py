@@ -264,10 +264,17 @@ def run_ours(args):
     dom = max(stage_key, key=lambda k: stage_ms[k])
     dom_bytes = (alg["hessian"] + alg["nms"] if dom == "hessian" else alg[dom]) * B
     achieved = dom_bytes / (stage_ms[dom] * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": {"integral": "k_band_integral", "hessian": "k_hessian+k_nms",
-                                           "describe": "k_orient+k_descriptor<A..D>"}[dom],
+    # dram__bytes_read+write of the describe-stage kernels from one `ncu --set full` capture of this very
+    # command at batch 64 (profiles/r1/describe_stage_v5_ncu_summary.txt): 225.6 MB read + 19.8 MB written
+    traffic = 245.4e6 if (dom == "describe" and B == 64) else None
+    roofline = {"bound": "hbm", "kernel": {"integral": "k_band_colsum+k_band_integral",
+                                           "hessian": "k_hessian_nms_tma_c<0|1>+k_hessian+k_nms",
+                                           "describe": "k_orient+k_descriptor<5 size classes>"}[dom],
                 "achieved": achieved, "peak": peak, "peak_source": how + " (MEASURED_PEAKS.json hbm_gbs)",
-                "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                "limiter": "instruction issue, not HBM: smsp__issue_active 68-86 % in the descriptor kernels "
+                           "(~6300 exact bilinear taps per keypoint); see profiles/r1/",
+                "peak_kind": "burst copy peak; the stage is timed inside a long step",
                 "algorithmic_bytes_per_launch": dom_bytes, "ms_per_launch": stage_ms[dom],
                 "stage_ms_per_step": stage_ms,
                 "whole_path_frac": alg["total"] * B * steps / (ms_dev * 1e-3) / 1e9 / peak}
