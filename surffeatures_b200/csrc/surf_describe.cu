@@ -265,16 +265,44 @@ struct AreaTab {  // one destination cell of the INTER_AREA table (same for x an
     unsigned char has_first[kPatch], has_last[kPatch];
 };
 
-template <int THREADS, bool GLOBAL>
-__global__ void __launch_bounds__(THREADS) k_descriptor(const __grid_constant__ DescribeArgs A, int cls, int max_n,
-                                                        int tile_cap)
+// Per-class compile-time geometry.  The image tile of a staged class has a FIXED pitch and row count (the
+// largest bounding box the class can need), so it can be fetched by one TMA box load and indexed with
+// constant strides.
+template <int CLS>
+struct ClassT {
+    static constexpr bool global = (CLS == kNumClasses - 1);
+    static constexpr int max_n = CLS == 0 ? kClassMaxN0 : CLS == 1 ? kClassMaxN1 : CLS == 2 ? kClassMaxN2
+                                 : CLS == 3 ? kClassMaxN3 : kMaxWindow;
+    static constexpr int threads = CLS == 0 ? 128 : 256;
+    // bounding box side of a rotated n x n window: n (|cos| + |sin|) + 3 <= 1.4143 n + 3, plus the 1-pixel
+    // margin on both sides of the closed-form box; origin aligned down / pitch rounded up to 16 bytes
+    static constexpr int side = (int)(1.4143 * max_n) + 4 + 2;
+    static constexpr int tp = global ? 16 : ((side + 15 + 15) & ~15);
+    static constexpr int tr = global ? 0 : side;
+    static constexpr int win_bytes = global ? max_n * kPatch * (int)sizeof(float) : ((max_n * max_n + 127) & ~127);
+    static constexpr int smem = 128 + max_n * 16 + win_bytes + tp * tr;
+};
+
+template <int CLS>
+__global__ void __launch_bounds__(ClassT<CLS>::threads) k_descriptor(const __grid_constant__ DescribeArgs A,
+                                                                     const __grid_constant__ CUtensorMap imap, int use_tma)
 {
-    extern __shared__ __align__(16) unsigned char dyn[];
-    // dynamic layout: double rsx[max_n], rsy[max_n]; then (staged classes) uchar win[max_n^2], uchar tile[tile_cap]
-    double *s_rsx = reinterpret_cast<double *>(dyn);
+    using CT = ClassT<CLS>;
+    constexpr int THREADS = CT::threads;
+    constexpr bool GLOBAL = CT::global;
+    constexpr int max_n = CT::max_n;
+    constexpr int cls = CLS;
+    constexpr int tp = CT::tp;  // tile pitch in bytes (constant per class)
+    extern __shared__ __align__(128) unsigned char dyn_raw[];
+    // dynamic layout (128-byte aligned by hand: TMA destinations need it):
+    //   uchar tile[tr][tp] | uchar win[max_n^2] (class D: float rowsum[max_n][21]) | double rsx[max_n], rsy[max_n]
+    unsigned char *dyn = dyn_raw + ((128u - ((uint32_t)__cvta_generic_to_shared(dyn_raw) & 127u)) & 127u);
+    unsigned char *s_tile = dyn;
+    unsigned char *s_win = dyn + tp * CT::tr;
+    double *s_rsx = reinterpret_cast<double *>(s_win + CT::win_bytes);
     double *s_rsy = s_rsx + max_n;
-    unsigned char *s_win = dyn + (size_t)max_n * 16;  // class D: this region holds the row sums instead
-    unsigned char *s_tile = s_win + (((size_t)max_n * max_n + 15) & ~(size_t)15);
+    __shared__ __align__(8) uint64_t s_bar;
+    uint32_t tma_phase = 0;
 
     __shared__ int s_work;
     __shared__ float s_scale;
@@ -291,6 +319,11 @@ __global__ void __launch_bounds__(THREADS) k_descriptor(const __grid_constant__ 
     const int count = A.misc[kMiscClassCount + cls];
     const int *list = A.class_list + (size_t)cls * A.list_stride;
     unsigned char *g_win = GLOBAL ? A.win_scratch + (size_t)blockIdx.x * kMaxWindow * kMaxWindow : nullptr;
+    const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&s_bar);
+    if (!GLOBAL && tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
 
     for (;;) {
         __syncthreads();  // everyone is done with the previous keypoint's shared state
@@ -337,15 +370,23 @@ __global__ void __launch_bounds__(THREADS) k_descriptor(const __grid_constant__ 
             ty0 = min(max(__float2int_rd(miny), 0), H - 1);
             ty1 = min(max(__float2int_rd(maxy) + 1, 0), H - 1);
         }
-        const int amask = A.img_aligned16 ? 15 : 3;
-        const int tx0a = tx0 & ~amask;                          // tile origin aligned for vector copies
-        const int tp = ((tx1 - tx0a + 1) + amask) & ~amask;     // tile pitch in bytes
+        const int tx0a = tx0 & ~15;              // tile origin aligned down to 16 bytes (TMA / vector copies)
         const int th_rows = ty1 - ty0 + 1;
-        // the tile capacity of a staged class is an upper bound by construction (tile_cap_for); a
-        // violation would be a bug, reported through the status word instead of corrupting memory
-        if (!GLOBAL && tp * th_rows > tile_cap) {
+        // the class tile is an upper bound by construction (ClassT); a violation would be a bug, reported
+        // through the status word instead of corrupting memory
+        if (!GLOBAL && (tx1 - tx0a + 1 > tp || th_rows > CT::tr)) {
             if (tid == 0) atomicOr(A.misc + kMiscStatus, 2);
             continue;
+        }
+        // ---- the window's bounding box -> shared memory: one TMA box load (issued now, awaited below) ----
+        const bool tma = !GLOBAL && use_tma;
+        if (tma && tid == 0) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // earlier generic reads of the tile are done
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)(tp * CT::tr)) : "memory");
+            asm volatile(
+                "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                ::"r"((uint32_t)__cvta_generic_to_shared(s_tile)), "l"(&imap), "r"(tx0a), "r"(ty0), "r"(b), "r"(bar)
+                : "memory");
         }
 
         // ---- INTER_AREA table for this window size (one warp) ----
@@ -370,37 +411,21 @@ __global__ void __launch_bounds__(THREADS) k_descriptor(const __grid_constant__ 
             s_tab.a_last[d] = (float)(fmin(fmin(f2 - s2, 1.), cell) / cell);
         }
 
-        // ---- stage the bounding box of the window in shared memory (coalesced word loads) ----
-        if (!GLOBAL) {
-            if (A.img_aligned16) {
-                const int cpr = tp >> 4;                                   // 16-byte chunks per tile row
-                const int cfull = min(cpr, (W - tx0a) >> 4);               // chunks fully inside the image row
-                for (int r = warp; r < th_rows; r += NW) {
-                    const uint8_t *src = img + (size_t)(ty0 + r) * pitch + tx0a;
-                    uint4 *dst = reinterpret_cast<uint4 *>(s_tile + r * tp);
-                    for (int c = lane; c < cfull; c += 32) __pipeline_memcpy_async(dst + c, src + 16 * c, 16);
-                    for (int c = cfull + lane; c < cpr; c += 32) {          // chunk straddling the row end
-                        uint32_t v[4] = {0, 0, 0, 0};
-                        for (int k = 0; k < 16; k++)
-                            if (tx0a + 16 * c + k < W) v[k >> 2] |= (uint32_t)src[16 * c + k] << (8 * (k & 3));
-                        dst[c] = make_uint4(v[0], v[1], v[2], v[3]);
-                    }
-                }
-            } else {
-                const int wpr = tp >> 2;
-                const int wfull = A.img_aligned4 ? min(wpr, (W - tx0a) >> 2) : 0;  // words fully inside the row
-                for (int r = warp; r < th_rows; r += NW) {
-                    const uint8_t *src = img + (size_t)(ty0 + r) * pitch + tx0a;
-                    uint32_t *dst = reinterpret_cast<uint32_t *>(s_tile + r * tp);
-                    for (int c = lane; c < wfull; c += 32) __pipeline_memcpy_async(dst + c, src + 4 * c, 4);
-                    for (int c = wfull + lane; c < wpr; c += 32) {
-                        const int x = tx0a + 4 * c;
-                        uint32_t v = 0;
+        // ---- fallback when the frames are not 16-byte aligned (no TMA): asynchronous 4-byte copies ----
+        if (!GLOBAL && !tma) {
+            const int wpr = (min(tx1 - tx0a + 1 + 3, tp)) >> 2;
+            const int wfull = A.img_aligned4 ? min(wpr, (W - tx0a) >> 2) : 0;  // words fully inside the row
+            for (int r = warp; r < th_rows; r += NW) {
+                const uint8_t *src = img + (size_t)(ty0 + r) * pitch + tx0a;
+                uint32_t *dst = reinterpret_cast<uint32_t *>(s_tile + r * tp);
+                for (int c = lane; c < wfull; c += 32) __pipeline_memcpy_async(dst + c, src + 4 * c, 4);
+                for (int c = wfull + lane; c < wpr; c += 32) {
+                    const int x = tx0a + 4 * c;
+                    uint32_t v = 0;
 #pragma unroll
-                        for (int k = 0; k < 4; k++)
-                            if (x + k < W) v |= (uint32_t)src[4 * c + k] << (8 * k);
-                        dst[c] = v;
-                    }
+                    for (int k = 0; k < 4; k++)
+                        if (x + k < W) v |= (uint32_t)src[4 * c + k] << (8 * k);
+                    dst[c] = v;
                 }
             }
             __pipeline_commit();
@@ -417,7 +442,21 @@ __global__ void __launch_bounds__(THREADS) k_descriptor(const __grid_constant__ 
                 for (int i = 0; i < n; i++, v += cd) s_rsy[i] = (double)v;
             }
         }
-        if (!GLOBAL) __pipeline_wait_prior(0);
+        if (tma) {
+            uint32_t done = 0;
+            for (uint32_t spin = 0; !done && spin < (1u << 24); spin++)
+                asm volatile(
+                    "{\n\t.reg .pred p;\n\t"
+                    "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                    "selp.u32 %0, 1, 0, p;\n\t}"
+                    : "=r"(done)
+                    : "r"(bar), "r"(tma_phase)
+                    : "memory");
+            if (!done && tid == 0) atomicOr(A.misc + kMiscStatus, 4);  // reported by the host, never silent
+            tma_phase ^= 1;
+        } else if (!GLOBAL) {
+            __pipeline_wait_prior(0);
+        }
         __syncthreads();
 
         unsigned char *win = GLOBAL ? g_win : s_win;
@@ -471,7 +510,7 @@ __global__ void __launch_bounds__(THREADS) k_descriptor(const __grid_constant__ 
         // ---- resize to 21 x 21 (INTER_AREA) ----
         // Fractional scales run the reference's two passes: row sums buf[sy][dx] = sum_x win[sy][x] * alpha
         // (fp32, table order) for every window row, then the column pass.  Every window pixel is read once.
-        float *s_buf = reinterpret_cast<float *>(GLOBAL ? (s_win) : s_tile);  // the image tile is no longer needed
+        float *s_buf = reinterpret_cast<float *>(GLOBAL ? s_win : s_tile);  // the image tile is no longer needed
         if (!int_scale) {
             for (int it = tid; it < n * kPatch; it += THREADS) {
                 const int sy = it / kPatch, dx = it - sy * kPatch;
@@ -589,16 +628,8 @@ __global__ void __launch_bounds__(THREADS) k_descriptor(const __grid_constant__ 
 namespace {
 
 struct ClassCfg {
-    int max_n, tile_cap, smem, grid;
+    int smem, grid;
 };
-
-int tile_cap_for(int max_n)
-{
-    // bounding box side of a rotated n x n window: n (|cos| + |sin|) + 3 <= 1.4143 n + 3, rows padded to 4
-    int side = (int)(1.4143 * max_n) + 4 + 2;  // + the 1-pixel margin on both sides of the closed-form box
-    int pitch = (side + 15 + 15) & ~15;        // origin aligned down and pitch rounded up to 16 bytes
-    return pitch * side;
-}
 
 struct DevCfg {
     bool ready = false;
@@ -609,14 +640,16 @@ struct DevCfg {
 };
 DevCfg g_cfg[64];
 
-template <int THREADS, bool GLOBAL>
+template <int CLS>
 void setup_class(ClassCfg &c, int sms)
 {
-    cudaFuncSetAttribute(k_descriptor<THREADS, GLOBAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, c.smem);
+    using CT = ClassT<CLS>;
+    c.smem = CT::smem;
+    cudaFuncSetAttribute(k_descriptor<CLS>, cudaFuncAttributeMaxDynamicSharedMemorySize, c.smem);
     int per_sm = 1;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_descriptor<THREADS, GLOBAL>, THREADS, c.smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_descriptor<CLS>, CT::threads, c.smem);
     if (per_sm < 1) per_sm = 1;
-    if (GLOBAL && per_sm > kClassDGridPerSm) per_sm = kClassDGridPerSm;
+    if (CT::global && per_sm > kClassDGridPerSm) per_sm = kClassDGridPerSm;
     c.grid = sms * per_sm;  // persistent CTAs: a multiple of the SM count
 }
 
@@ -631,20 +664,11 @@ DevCfg &dev_cfg()
         int per_sm = 4;
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_orient, kOriWarps * 32, 0);
         c.ori_grid = sms * (per_sm < 1 ? 1 : per_sm);
-        for (int k = 0; k < kNumClasses; k++) {
-            ClassCfg &cc = c.cls[k];
-            const int max_ns[kNumClasses] = {kClassMaxN0, kClassMaxN1, kClassMaxN2, kClassMaxN3, kMaxWindow};
-            cc.max_n = max_ns[k];
-            const bool global = (k == kNumClasses - 1);
-            cc.tile_cap = global ? 0 : tile_cap_for(cc.max_n);
-            cc.smem = cc.max_n * 16 + (global ? cc.max_n * kPatch * (int)sizeof(float)
-                                              : ((cc.max_n * cc.max_n + 15) & ~15) + cc.tile_cap);
-        }
-        setup_class<128, false>(c.cls[0], sms);
-        setup_class<256, false>(c.cls[1], sms);
-        setup_class<256, false>(c.cls[2], sms);
-        setup_class<256, false>(c.cls[3], sms);
-        setup_class<256, true>(c.cls[4], sms);
+        setup_class<0>(c.cls[0], sms);
+        setup_class<1>(c.cls[1], sms);
+        setup_class<2>(c.cls[2], sms);
+        setup_class<3>(c.cls[3], sms);
+        setup_class<4>(c.cls[4], sms);
         for (int k = 0; k < kNumClasses - 1; k++) {
             cudaStreamCreateWithFlags(&c.side[k], cudaStreamNonBlocking);
             cudaEventCreateWithFlags(&c.join[k], cudaEventDisableTiming);
@@ -657,26 +681,34 @@ DevCfg &dev_cfg()
 
 }  // namespace
 
+void describe_tile_box(int cls, int *pitch_bytes, int *rows)
+{
+    const int tp[kNumClasses] = {ClassT<0>::tp, ClassT<1>::tp, ClassT<2>::tp, ClassT<3>::tp, 0};
+    const int tr[kNumClasses] = {ClassT<0>::tr, ClassT<1>::tr, ClassT<2>::tr, ClassT<3>::tr, 0};
+    *pitch_bytes = tp[cls];
+    *rows = tr[cls];
+}
+
 size_t describe_scratch_bytes()
 {
     return (size_t)dev_cfg().cls[kNumClasses - 1].grid * kMaxWindow * kMaxWindow;
 }
 
-void launch_describe(const DescribeArgs &a, cudaStream_t st, int *launches)
+void launch_describe(const DescribeArgs &a, const CUtensorMap *imaps, int use_tma, cudaStream_t st, int *launches)
 {
     DevCfg &c = dev_cfg();
     k_orient<<<c.ori_grid, kOriWarps * 32, 0, st>>>(a);
     *launches += 1;
     if (!a.desc && !a.patches) return;
-    // The four size classes are independent: fork them onto side streams so their CTAs share the
-    // GPU and the tails of the short launches overlap the long ones; join back on `st`.
+    // The size classes are independent: fork them onto side streams so their CTAs share the GPU and the
+    // tails of the short launches overlap the long ones; join back on `st`.
     cudaEventRecord(c.fork, st);
     for (int k = 0; k < kNumClasses - 1; k++) cudaStreamWaitEvent(c.side[k], c.fork, 0);
-    k_descriptor<256, false><<<c.cls[1].grid, 256, c.cls[1].smem, st>>>(a, 1, c.cls[1].max_n, c.cls[1].tile_cap);
-    k_descriptor<256, true><<<c.cls[4].grid, 256, c.cls[4].smem, c.side[0]>>>(a, 4, c.cls[4].max_n, c.cls[4].tile_cap);
-    k_descriptor<256, false><<<c.cls[3].grid, 256, c.cls[3].smem, c.side[1]>>>(a, 3, c.cls[3].max_n, c.cls[3].tile_cap);
-    k_descriptor<256, false><<<c.cls[2].grid, 256, c.cls[2].smem, c.side[2]>>>(a, 2, c.cls[2].max_n, c.cls[2].tile_cap);
-    k_descriptor<128, false><<<c.cls[0].grid, 128, c.cls[0].smem, c.side[3]>>>(a, 0, c.cls[0].max_n, c.cls[0].tile_cap);
+    k_descriptor<1><<<c.cls[1].grid, ClassT<1>::threads, c.cls[1].smem, st>>>(a, imaps[1], use_tma);
+    k_descriptor<4><<<c.cls[4].grid, ClassT<4>::threads, c.cls[4].smem, c.side[0]>>>(a, imaps[0], 0);
+    k_descriptor<3><<<c.cls[3].grid, ClassT<3>::threads, c.cls[3].smem, c.side[1]>>>(a, imaps[3], use_tma);
+    k_descriptor<2><<<c.cls[2].grid, ClassT<2>::threads, c.cls[2].smem, c.side[2]>>>(a, imaps[2], use_tma);
+    k_descriptor<0><<<c.cls[0].grid, ClassT<0>::threads, c.cls[0].smem, c.side[3]>>>(a, imaps[0], use_tma);
     for (int k = 0; k < kNumClasses - 1; k++) {
         cudaEventRecord(c.join[k], c.side[k]);
         cudaStreamWaitEvent(st, c.join[k], 0);

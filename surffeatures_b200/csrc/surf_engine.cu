@@ -66,6 +66,9 @@ struct surf_engine {
     TileOctave tile_oct[2];
     int tmap_w = 0, tmap_h = 0, tmap_b = 0, tmap_layers = 0;
     bool tmap_ok[2] = {false, false};
+    CUtensorMap imap[kNumClasses];   // 8-bit frame tiles for the descriptor kernels, one box size per class
+    bool imap_ok = false;
+    const void *imap_ptr = nullptr;  size_t imap_pitch = 0, imap_stride = 0;  int imap_w = 0, imap_h = 0, imap_b = 0;
     int last_tc_ws = -1;  // workspace used by the last tensor-core match (for surf_match_redo_count)
 
     // tensor-core matcher workspaces: [0] generic two-operand calls, [1] the frame stream ring
@@ -251,6 +254,35 @@ void ensure_tensor_maps(surf_engine *e, const FrameGeo &geo, int B)
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         e->tmap_ok[o] = (r == CUDA_SUCCESS);
     }
+}
+
+// TMA descriptors of the frames (3-D: x, y, frame; uint8) for the descriptor kernels' image tiles.
+void ensure_image_maps(surf_engine *e, const ImageRef &img, const FrameGeo &geo, int B)
+{
+    if (e->imap_ptr == img.ptr && e->imap_pitch == img.pitch && e->imap_stride == img.frame_stride && e->imap_w == geo.W &&
+        e->imap_h == geo.H && e->imap_b == B)
+        return;
+    e->imap_ptr = img.ptr; e->imap_pitch = img.pitch; e->imap_stride = img.frame_stride;
+    e->imap_w = geo.W; e->imap_h = geo.H; e->imap_b = B;
+    e->imap_ok = false;
+    EncodeTiledFn enc = encode_tiled_fn();
+    const bool aligned16 = ((reinterpret_cast<uintptr_t>(img.ptr) | img.pitch | img.frame_stride) & 15) == 0;
+    if (!enc || !e->use_tma || !aligned16) return;
+    bool ok = true;
+    for (int c = 0; c < kNumClasses - 1; c++) {
+        int tp = 0, tr = 0;
+        describe_tile_box(c, &tp, &tr);
+        cuuint64_t dims[3] = {(cuuint64_t)geo.W, (cuuint64_t)geo.H, (cuuint64_t)B};
+        cuuint64_t strides[2] = {(cuuint64_t)img.pitch, (cuuint64_t)(B > 1 ? img.frame_stride : img.pitch * geo.H)};
+        cuuint32_t box[3] = {(cuuint32_t)tp, (cuuint32_t)tr, 1};
+        cuuint32_t estr[3] = {1, 1, 1};
+        if ((strides[1] & 15) || tp > 256 || tr > 256) { ok = false; break; }
+        CUresult r = enc(&e->imap[c], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<uint8_t *>(img.ptr), dims, strides, box,
+                         estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { ok = false; break; }
+    }
+    e->imap_ok = ok;
 }
 
 size_t det_octave_words(const surf_params &p, int octave, int W, int H)
@@ -486,7 +518,8 @@ int run_describe_pack(surf_engine *e, const ImageRef &img, const FrameGeo &geo, 
     a.list_stride = (size_t)e->max_b * e->cap;
     a.win_scratch = e->d_win_scratch;
     a.sincos = e->d_sincos;
-    launch_describe(a, e->stream, &e->launches);
+    ensure_image_maps(e, img, geo, B);
+    launch_describe(a, e->imap, e->imap_ok ? 1 : 0, e->stream, &e->launches);
     rec(e, EV_DESCRIBE);
     if (pack) {
         if (e->copies_in_flight) CU(e, cudaStreamWaitEvent(e->stream, e->ev_copy_done, 0));
@@ -524,6 +557,8 @@ int check_counts(surf_engine *e, int B)
     }
     if (h[3 * B + 1 + kMiscWords] & 1)
         return fail(e, SURF_ERR_CUDA, "internal error: a TMA tile load of the integral image did not complete");
+    if (h[3 * B + 1 + kMiscStatus] & 4)
+        return fail(e, SURF_ERR_CUDA, "internal error: a TMA tile load of a frame did not complete");
     if (h[3 * B + 1 + kMiscStatus] & 2)
         return fail(e, SURF_ERR_CUDA, "internal error: descriptor tile capacity exceeded");
     if (h[3 * B + 1 + kMiscStatus] & 1)

@@ -78,7 +78,7 @@ struct ImageRef {
 // memory for classes A-C; class D (n > 184, about 1 % of keypoints) reads the image from global
 // memory and keeps its window in a per-CTA global scratch buffer.
 constexpr int kNumClasses = 5;
-constexpr int kClassMaxN0 = 64, kClassMaxN1 = 96, kClassMaxN2 = 128, kClassMaxN3 = 176;  // last class: up to kMaxWindow
+constexpr int kClassMaxN0 = 64, kClassMaxN1 = 96, kClassMaxN2 = 128, kClassMaxN3 = 160;  // last class: up to kMaxWindow
 constexpr int kClassDGridPerSm = 2;
 
 // d_misc word layout
@@ -130,7 +130,9 @@ surf_keypoint *launch_sort(surf_keypoint *a, surf_keypoint *b, const int *counts
                            int *launches);
 // offsets[b] = sum_{b' < b} (min(counts[b'], cap) - (ndel ? ndel[b'] : 0)), B + 1 entries.
 void launch_offsets(const int *counts, const int *ndel, int cap, int B, int *offsets, cudaStream_t st, int *launches);
-void launch_describe(const DescribeArgs &a, cudaStream_t st, int *launches);
+// imaps: TMA descriptors of the 8-bit frames, one per staged size class (box = that class's tile)
+void launch_describe(const DescribeArgs &a, const CUtensorMap *imaps, int use_tma, cudaStream_t st, int *launches);
+void describe_tile_box(int cls, int *pitch_bytes, int *rows);
 void launch_pack(const surf_keypoint *kps, const float *desc, int D, int cap, int B, const int *in_offsets,
                  const int *ndel, const int *deleted_slots, const int *out_offsets, surf_keypoint *out_kps,
                  float *out_desc, cudaStream_t st, int *launches);
