@@ -246,7 +246,7 @@ __global__ void __launch_bounds__(kOriWarps * 32) k_orient(const __grid_constant
                     A.sincos[(size_t)b * A.cap + slot] = make_float2(-(float)sin((double)th), (float)cos((double)th));
                 }
                 if (want_desc) {
-                    const int cls = (n > kClassMaxN0) + (n > kClassMaxN1) + (n > kClassMaxN2) + (n > kClassMaxN3);
+                    const int cls = (n > kClassMaxN0) + (n > kClassMaxN1) + (n > kClassMaxN2);
                     const int pos = atomicAdd(A.misc + kMiscClassCount + cls, 1);
                     A.class_list[(size_t)cls * A.list_stride + pos] = b * A.cap + slot;
                 }
@@ -257,6 +257,11 @@ __global__ void __launch_bounds__(kOriWarps * 32) k_orient(const __grid_constant
 
 // ------------------------------------------------------------------------------------------------
 // K4b: descriptor.
+//   k_descriptor<CLS>   windows up to 128 x 128: the whole bounding box of the rotated window is one TMA tile
+//   k_descriptor_big    larger windows: the window is cut into sub-windows of at most 96 x 96 taps, each with
+//                       its own TMA tile (double-buffered: the next tile lands while the current one is
+//                       tapped); the window itself lives in a per-CTA global scratch buffer
+// Both share the arithmetic below, statement for statement.
 // ------------------------------------------------------------------------------------------------
 struct AreaTab {  // one destination cell of the INTER_AREA table (same for x and y: square window)
     int start[kPatch];
@@ -265,76 +270,298 @@ struct AreaTab {  // one destination cell of the INTER_AREA table (same for x an
     unsigned char has_first[kPatch], has_last[kPatch];
 };
 
-// Per-class compile-time geometry.  The image tile of a staged class has a FIXED pitch and row count (the
-// largest bounding box the class can need), so it can be fetched by one TMA box load and indexed with
-// constant strides.
+struct DescShared {  // static shared state of one descriptor CTA
+    AreaTab tab;
+    __align__(4) unsigned char patch[kPatchPx + 3];
+    float dx[400], dy[400];
+    float vec[128];
+    float scale;
+    int work;
+};
+
+__device__ __forceinline__ void mbar_init1(uint32_t bar)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+}
+
+__device__ __forceinline__ bool mbar_wait_bounded(uint32_t bar, uint32_t parity)
+{
+    uint32_t done = 0;
+    for (uint32_t spin = 0; !done && spin < (1u << 24); spin++)
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    return done != 0;
+}
+
+// One TMA box load of the 8-bit frame b at (x, y) (x 16-byte aligned) into shared memory.
+__device__ __forceinline__ void tma_load_tile(const CUtensorMap *map, uint32_t dst, int x, int y, int b, uint32_t bar, uint32_t bytes)
+{
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // earlier generic accesses of the buffer are done
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+        ::"r"(dst), "l"(map), "r"(x), "r"(y), "r"(b), "r"(bar)
+        : "memory");
+}
+
+// INTER_AREA table entry of destination cell d for an n-pixel source axis (computeResizeAreaTab).
+__device__ __forceinline__ void area_tab_entry(AreaTab &t, int d, int n, double scale)
+{
+    const double f1 = d * scale, f2 = f1 + scale;
+    const double cell = fmin(scale, n - f1);
+    int s1 = __double2int_ru(f1), s2 = __double2int_rd(f2);
+    s2 = min(s2, n - 1);
+    s1 = min(s1, s2);
+    const bool hf = (s1 - f1) > 1e-3, hl = (f2 - s2) > 1e-3;
+    t.start[d] = hf ? s1 - 1 : s1;
+    t.count[d] = (hf ? 1 : 0) + (s2 - s1) + (hl ? 1 : 0);
+    t.has_first[d] = hf;
+    t.has_last[d] = hl;
+    t.a_first[d] = (float)((s1 - f1) / cell);
+    t.a_mid[d] = (float)(1.0 / cell);
+    t.a_last[d] = (float)(fmin(fmin(f2 - s2, 1.), cell) / cell);
+}
+
+// One rotated window pixel: bilinear tap of the frame at (fx, fy), rounded to uchar; nearest with clamping
+// outside the interpolable area.  `tile` holds the frame region starting at (x0, y0) with pitch TP bytes.
+template <class Src>
+__device__ __forceinline__ unsigned rotated_tap(double fx, double fy, int W, int H, int x0, int y0, int TP, Src src)
+{
+    const double kMagic = 6755399441055744.0;  // 1.5 * 2^52: floor via round-down addition
+    const double mx = __dadd_rd(fx, kMagic), my = __dadd_rd(fy, kMagic);
+    const int ix = __double2loint(mx), iy = __double2loint(my);
+    if ((unsigned)ix < (unsigned)(W - 1) && (unsigned)iy < (unsigned)(H - 1)) {
+        const float a = (float)(fx - (mx - kMagic)), bb = (float)(fy - (my - kMagic));
+        const int q = (iy - y0) * TP + (ix - x0);
+        const float na = 1.f - a, nb = 1.f - bb;
+        const float p00 = u8f(src(q)), p01 = u8f(src(q + 1));
+        const float p10 = u8f(src(q + TP)), p11 = u8f(src(q + TP + 1));
+        return round_u8(p00 * na * nb + p01 * a * nb + p10 * na * bb + p11 * a * bb);
+    }
+    const int x = min(max(__double2int_rn(fx), 0), W - 1);
+    const int y = min(max(__double2int_rn(fy), 0), H - 1);
+    return src((y - y0) * TP + (x - x0));
+}
+
+// From the n x n window (`win`, shared or global) to the descriptor: INTER_AREA to 21 x 21, 2x2 Haar gradients,
+// 4x4 sub-region sums, normalisation.  `buf` holds n x 21 floats (row sums of the fractional resize).
+template <int THREADS>
+__device__ __forceinline__ void descriptor_tail(const DescribeArgs &A, int kidx, int n, const unsigned char *win, float *buf,
+                                                DescShared &S, bool int_scale, int isc)
+{
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int D = A.extended ? 128 : 64;
+    // Fractional scales run the reference's two passes: row sums buf[sy][dx] = sum_x win[sy][x] * alpha (fp32,
+    // table order), then the column pass.  Thread = (row group, dx): the dx entry of the table stays in registers.
+    if (!int_scale) {
+        constexpr int G = THREADS / kPatch;
+        if (tid < G * kPatch) {
+            const int g = tid / kPatch, dx = tid - g * kPatch;
+            const int xs = S.tab.start[dx], xc = S.tab.count[dx];
+            const bool xhf = S.tab.has_first[dx], xhl = S.tab.has_last[dx];
+            const float xaf = S.tab.a_first[dx], xam = S.tab.a_mid[dx], xal = S.tab.a_last[dx];
+            const int fend = xc - (xhl ? 1 : 0);
+            for (int sy = g; sy < n; sy += G) {
+                const unsigned char *row = win + sy * n + xs;
+                float b = 0;
+                int f = 0;
+                if (xhf) {
+                    b += u8f(row[0]) * xaf;
+                    f = 1;
+                }
+#pragma unroll 4
+                for (; f < fend; f++) b += u8f(row[f]) * xam;
+                if (xhl) b += u8f(row[xc - 1]) * xal;
+                buf[sy * kPatch + dx] = b;
+            }
+        }
+        __syncthreads();
+    }
+    for (int p = tid; p < kPatchPx; p += THREADS) {
+        const int dy = p / kPatch, dx = p - dy * kPatch;
+        int outv;
+        if (int_scale && isc == 2) {
+            const unsigned char *r0 = win + (2 * dy) * n + 2 * dx, *r1 = r0 + n;
+            outv = (r0[0] + r0[1] + r1[0] + r1[1] + 2) >> 2;
+        } else if (int_scale) {
+            int acc = 0;
+            for (int v = 0; v < isc; v++) {
+                const unsigned char *r0 = win + (dy * isc + v) * n + dx * isc;
+                for (int u = 0; u < isc; u++) acc += r0[u];
+            }
+            const float wgt = 1.f / (isc * isc);
+            outv = sat_u8(acc * wgt);
+        } else {
+            const int ys = S.tab.start[dy], yc = S.tab.count[dy];
+            const bool yhf = S.tab.has_first[dy], yhl = S.tab.has_last[dy];
+            const float yaf = S.tab.a_first[dy], yam = S.tab.a_mid[dy], yal = S.tab.a_last[dy];
+            const float *col = buf + ys * kPatch + dx;
+            float acc = 0;
+            for (int e = 0; e < yc; e++) {
+                const float beta = (e == 0 && yhf) ? yaf : ((e == yc - 1 && yhl) ? yal : yam);
+                const float bv = col[e * kPatch];
+                if (e == 0) acc = beta * bv; else acc += beta * bv;
+            }
+            outv = sat_u8(acc);
+        }
+        S.patch[p] = (unsigned char)outv;
+    }
+    __syncthreads();
+    if (A.patches) {
+        unsigned char *po = A.patches + (size_t)kidx * kPatchPx;
+        for (int p = tid; p < kPatchPx; p += THREADS) po[p] = S.patch[p];
+    }
+    if (!A.desc) return;
+
+    // ---- 2x2 Haar gradients of the patch, Gaussian weighted ----
+    for (int t = tid; t < 400; t += THREADS) {
+        const int i = t / 20, j = t - i * 20;
+        const unsigned char *r0 = S.patch + i * kPatch + j, *r1 = r0 + kPatch;
+        const float wgt = c_desc_w[t];
+        S.dx[t] = (r0[1] - r0[0] + r1[1] - r1[0]) * wgt;
+        S.dy[t] = (r1[0] - r0[0] + r1[1] - r0[1]) * wgt;
+    }
+    __syncthreads();
+    // ---- 4 x 4 sub-regions, one output component per thread, sequential fp32 sums ----
+    const int nb = A.extended ? 8 : 4;
+    for (int t = tid; t < D; t += THREADS) {
+        const int region = t / nb, comp = t - region * nb;
+        const int I = region >> 2, J = region & 3;
+        float acc = 0;
+        for (int y = I * 5; y < I * 5 + 5; y++)
+            for (int x = J * 5; x < J * 5 + 5; x++) {
+                const float tx = S.dx[y * 20 + x], ty = S.dy[y * 20 + x];
+                if (A.extended) {
+                    switch (comp) {
+                        case 0: if (ty >= 0) acc += tx; break;
+                        case 1: if (ty >= 0) acc += fabsf(tx); break;
+                        case 2: if (!(ty >= 0)) acc += tx; break;
+                        case 3: if (!(ty >= 0)) acc += fabsf(tx); break;
+                        case 4: if (tx >= 0) acc += ty; break;
+                        case 5: if (tx >= 0) acc += fabsf(ty); break;
+                        case 6: if (!(tx >= 0)) acc += ty; break;
+                        default: if (!(tx >= 0)) acc += fabsf(ty); break;
+                    }
+                } else {
+                    switch (comp) {
+                        case 0: acc += tx; break;
+                        case 1: acc += ty; break;
+                        case 2: acc += fabsf(tx); break;
+                        default: acc += fabsf(ty); break;
+                    }
+                }
+            }
+        S.vec[t] = acc;
+    }
+    __syncthreads();
+    if (warp == 0) {
+        double mag = 0;
+        for (int t = lane; t < D; t += 32) mag += (double)(S.vec[t] * S.vec[t]);
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) mag += __shfl_xor_sync(FULL_MASK, mag, d);
+        if (lane == 0) S.scale = (float)(1. / (sqrt(mag) + DBL_EPSILON));
+    }
+    __syncthreads();
+    float *vo = A.desc + (size_t)kidx * D;
+    for (int t = tid; t < D; t += THREADS) vo[t] = S.vec[t] * S.scale;
+}
+
+// Per-class compile-time geometry.  The image tile of a class has a FIXED pitch and row count (the largest
+// bounding box the class can need), so it is fetched by one TMA box load and indexed with constant strides.
 template <int CLS>
 struct ClassT {
-    static constexpr bool global = (CLS == kNumClasses - 1);
-    static constexpr int max_n = CLS == 0 ? kClassMaxN0 : CLS == 1 ? kClassMaxN1 : CLS == 2 ? kClassMaxN2
-                                 : CLS == 3 ? kClassMaxN3 : kMaxWindow;
+    static constexpr int max_n = CLS == 0 ? kClassMaxN0 : CLS == 1 ? kClassMaxN1 : kClassMaxN2;
     static constexpr int threads = CLS == 0 ? 128 : 256;
     // bounding box side of a rotated n x n window: n (|cos| + |sin|) + 3 <= 1.4143 n + 3, plus the 1-pixel
     // margin on both sides of the closed-form box; origin aligned down / pitch rounded up to 16 bytes
     static constexpr int side = (int)(1.4143 * max_n) + 4 + 2;
-    static constexpr int tp = global ? 16 : ((side + 15 + 15) & ~15);
-    static constexpr int tr = global ? 0 : side;
-    static constexpr int win_bytes = global ? max_n * kPatch * (int)sizeof(float) : ((max_n * max_n + 127) & ~127);
+    static constexpr int tp = (side + 15 + 15) & ~15;
+    static constexpr int tr = side;
+    static constexpr int win_bytes = (max_n * max_n + 127) & ~127;
     static constexpr int smem = 128 + max_n * 16 + win_bytes + tp * tr;
 };
+
+// Sub-window kernel: tiles sized for sub-windows of at most kSubSide taps per side (the class-1 tile).
+constexpr int kSubSide = kClassMaxN1;
+struct BigT {
+    static constexpr int threads = 256;
+    static constexpr int tp = ClassT<1>::tp, tr = ClassT<1>::tr;
+    static constexpr int tile_bytes = tp * tr;
+    static constexpr int tile_stride = (tile_bytes + 127) & ~127;  // TMA destinations are 128-byte aligned
+    static constexpr int smem = 128 + 2 * tile_stride + kMaxWindow * 16;
+};
+
+// frame-tile fallback when the frames are not 16-byte aligned (no TMA): asynchronous 4-byte copies
+template <int NW, int TP>
+__device__ __forceinline__ void copy_tile_fallback(const DescribeArgs &A, const uint8_t *img, int pitch, unsigned char *tile,
+                                                   int tx0a, int tx1, int ty0, int th_rows)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int W = A.geo.W;
+    const int wpr = min(tx1 - tx0a + 1 + 3, TP) >> 2;
+    const int wfull = A.img_aligned4 ? min(wpr, (W - tx0a) >> 2) : 0;  // words fully inside the row
+    for (int r = warp; r < th_rows; r += NW) {
+        const uint8_t *src = img + (size_t)(ty0 + r) * pitch + tx0a;
+        uint32_t *dst = reinterpret_cast<uint32_t *>(tile + r * TP);
+        for (int c = lane; c < wfull; c += 32) __pipeline_memcpy_async(dst + c, src + 4 * c, 4);
+        for (int c = wfull + lane; c < wpr; c += 32) {
+            const int x = tx0a + 4 * c;
+            uint32_t v = 0;
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+                if (x + k < W) v |= (uint32_t)src[4 * c + k] << (8 * k);
+            dst[c] = v;
+        }
+    }
+    __pipeline_commit();
+    __pipeline_wait_prior(0);
+}
 
 template <int CLS>
 __global__ void __launch_bounds__(ClassT<CLS>::threads) k_descriptor(const __grid_constant__ DescribeArgs A,
                                                                      const __grid_constant__ CUtensorMap imap, int use_tma)
 {
     using CT = ClassT<CLS>;
-    constexpr int THREADS = CT::threads;
-    constexpr bool GLOBAL = CT::global;
-    constexpr int max_n = CT::max_n;
-    constexpr int cls = CLS;
-    constexpr int tp = CT::tp;  // tile pitch in bytes (constant per class)
+    constexpr int THREADS = CT::threads, NW = THREADS / 32;
+    constexpr int max_n = CT::max_n, tp = CT::tp;
     extern __shared__ __align__(128) unsigned char dyn_raw[];
     // dynamic layout (128-byte aligned by hand: TMA destinations need it):
-    //   uchar tile[tr][tp] | uchar win[max_n^2] (class D: float rowsum[max_n][21]) | double rsx[max_n], rsy[max_n]
+    //   uchar tile[tr][tp] | uchar win[max_n^2] | double rsx[max_n], rsy[max_n]
     unsigned char *dyn = dyn_raw + ((128u - ((uint32_t)__cvta_generic_to_shared(dyn_raw) & 127u)) & 127u);
     unsigned char *s_tile = dyn;
     unsigned char *s_win = dyn + tp * CT::tr;
     double *s_rsx = reinterpret_cast<double *>(s_win + CT::win_bytes);
     double *s_rsy = s_rsx + max_n;
     __shared__ __align__(8) uint64_t s_bar;
+    __shared__ DescShared S;
     uint32_t tma_phase = 0;
 
-    __shared__ int s_work;
-    __shared__ float s_scale;
-    __shared__ AreaTab s_tab;
-    __shared__ __align__(4) unsigned char s_patch[kPatchPx + 3];
-    __shared__ float s_dx[400], s_dy[400];
-    __shared__ float s_vec[128];
-
-    constexpr int NW = THREADS / 32;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int W = A.geo.W, H = A.geo.H;
-    const int D = A.extended ? 128 : 64;
     const int pitch = (int)A.img.pitch;
-    const int count = A.misc[kMiscClassCount + cls];
-    const int *list = A.class_list + (size_t)cls * A.list_stride;
-    unsigned char *g_win = GLOBAL ? A.win_scratch + (size_t)blockIdx.x * kMaxWindow * kMaxWindow : nullptr;
+    const int count = A.misc[kMiscClassCount + CLS];
+    const int *list = A.class_list + (size_t)CLS * A.list_stride;
     const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&s_bar);
-    if (!GLOBAL && tid == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+    if (tid == 0) {
+        mbar_init1(bar);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
 
     for (;;) {
         __syncthreads();  // everyone is done with the previous keypoint's shared state
-        if (tid == 0) s_work = atomicAdd(A.misc + kMiscClassHead + cls, 1);
+        if (tid == 0) S.work = atomicAdd(A.misc + kMiscClassHead + CLS, 1);
         __syncthreads();
-        const int work = s_work;
+        const int work = S.work;
         if (work >= count) break;
         const int kidx = list[work];
         const int b = kidx / A.cap;
         const surf_keypoint *kpp = A.kps + kidx;
-        const float cx = kpp->x, cy = kpp->y, size = kpp->size, dir = kpp->angle;
+        const float cx = kpp->x, cy = kpp->y, size = kpp->size;
         const uint8_t *img = A.img.ptr + (size_t)b * A.img.frame_stride;
 
         const float s = size * 1.2f / 9.0f;
@@ -356,9 +583,9 @@ __global__ void __launch_bounds__(ClassT<CLS>::threads) k_descriptor(const __gri
             const float2 sc = A.sincos[kidx];
             sd = sc.x;
             cd = sc.y;
-            // Bounding box of all taps from the closed-form window corners.  The true row starts come
-            // from sequential fp32 additions (computed below, overlapped with the tile copy) and drift
-            // from the closed form by far less than the 1-pixel margin taken here.
+            // Bounding box of all taps from the closed-form window corners.  The true row starts come from
+            // sequential fp32 additions (computed below, overlapped with the tile load) and drift from the
+            // closed form by far less than the 1-pixel margin taken here.
             const float sx0 = cx + off * cd + off * sd, sy0 = cy - off * sd + off * cd;
             const float ext = (float)(n - 1);
             const float xa = sx0, xb = sx0 + ext * sd, xc2 = sx0 + ext * cd, xd = xb + ext * cd;
@@ -374,109 +601,52 @@ __global__ void __launch_bounds__(ClassT<CLS>::threads) k_descriptor(const __gri
         const int th_rows = ty1 - ty0 + 1;
         // the class tile is an upper bound by construction (ClassT); a violation would be a bug, reported
         // through the status word instead of corrupting memory
-        if (!GLOBAL && (tx1 - tx0a + 1 > tp || th_rows > CT::tr)) {
+        if (tx1 - tx0a + 1 > tp || th_rows > CT::tr) {
             if (tid == 0) atomicOr(A.misc + kMiscStatus, 2);
             continue;
         }
         // ---- the window's bounding box -> shared memory: one TMA box load (issued now, awaited below) ----
-        const bool tma = !GLOBAL && use_tma;
-        if (tma && tid == 0) {
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // earlier generic reads of the tile are done
-            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)(tp * CT::tr)) : "memory");
-            asm volatile(
-                "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
-                ::"r"((uint32_t)__cvta_generic_to_shared(s_tile)), "l"(&imap), "r"(tx0a), "r"(ty0), "r"(b), "r"(bar)
-                : "memory");
-        }
+        if (use_tma && tid == 0)
+            tma_load_tile(&imap, (uint32_t)__cvta_generic_to_shared(s_tile), tx0a, ty0, b, bar, (uint32_t)(tp * CT::tr));
 
         // ---- INTER_AREA table for this window size (one warp) ----
         const double inv = (double)kPatch / n;
         const double scale = 1. / inv;
         const int isc = __double2int_rn(scale);
         const bool int_scale = fabs(scale - isc) < DBL_EPSILON;
-        if (!int_scale && warp == NW - 1 && lane < kPatch) {
-            const int d = lane;
-            const double f1 = d * scale, f2 = f1 + scale;
-            const double cell = fmin(scale, n - f1);
-            int s1 = __double2int_ru(f1), s2 = __double2int_rd(f2);
-            s2 = min(s2, n - 1);
-            s1 = min(s1, s2);
-            const bool hf = (s1 - f1) > 1e-3, hl = (f2 - s2) > 1e-3;
-            s_tab.start[d] = hf ? s1 - 1 : s1;
-            s_tab.count[d] = (hf ? 1 : 0) + (s2 - s1) + (hl ? 1 : 0);
-            s_tab.has_first[d] = hf;
-            s_tab.has_last[d] = hl;
-            s_tab.a_first[d] = (float)((s1 - f1) / cell);
-            s_tab.a_mid[d] = (float)(1.0 / cell);
-            s_tab.a_last[d] = (float)(fmin(fmin(f2 - s2, 1.), cell) / cell);
-        }
+        if (!int_scale && warp == NW - 1 && lane < kPatch) area_tab_entry(S.tab, lane, n, scale);
 
-        // ---- fallback when the frames are not 16-byte aligned (no TMA): asynchronous 4-byte copies ----
-        if (!GLOBAL && !tma) {
-            const int wpr = (min(tx1 - tx0a + 1 + 3, tp)) >> 2;
-            const int wfull = A.img_aligned4 ? min(wpr, (W - tx0a) >> 2) : 0;  // words fully inside the row
-            for (int r = warp; r < th_rows; r += NW) {
-                const uint8_t *src = img + (size_t)(ty0 + r) * pitch + tx0a;
-                uint32_t *dst = reinterpret_cast<uint32_t *>(s_tile + r * tp);
-                for (int c = lane; c < wfull; c += 32) __pipeline_memcpy_async(dst + c, src + 4 * c, 4);
-                for (int c = wfull + lane; c < wpr; c += 32) {
-                    const int x = tx0a + 4 * c;
-                    uint32_t v = 0;
-#pragma unroll
-                    for (int k = 0; k < 4; k++)
-                        if (x + k < W) v |= (uint32_t)src[4 * c + k] << (8 * k);
-                    dst[c] = v;
-                }
-            }
-            __pipeline_commit();
-        }
+        if (!use_tma) copy_tile_fallback<NW, tp>(A, img, pitch, s_tile, tx0a, tx1, ty0, th_rows);
         if (!A.upright && (tid == 0 || tid == 32)) {
             // row starts advance by sequential fp32 additions (x chain on warp 0, y chain on warp 1),
-            // stored as doubles for the tap loop; runs while the tile copies are in flight
-            const float off2 = -(float)(n - 1) / 2;
+            // stored as doubles for the tap loop; runs while the tile is in flight
             if (tid == 0) {
-                float v = cx + off2 * cd + off2 * sd;
+                float v = cx + off * cd + off * sd;
                 for (int i = 0; i < n; i++, v += sd) s_rsx[i] = (double)v;
             } else {
-                float v = cy - off2 * sd + off2 * cd;
+                float v = cy - off * sd + off * cd;
                 for (int i = 0; i < n; i++, v += cd) s_rsy[i] = (double)v;
             }
         }
-        if (tma) {
-            uint32_t done = 0;
-            for (uint32_t spin = 0; !done && spin < (1u << 24); spin++)
-                asm volatile(
-                    "{\n\t.reg .pred p;\n\t"
-                    "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-                    "selp.u32 %0, 1, 0, p;\n\t}"
-                    : "=r"(done)
-                    : "r"(bar), "r"(tma_phase)
-                    : "memory");
-            if (!done && tid == 0) atomicOr(A.misc + kMiscStatus, 4);  // reported by the host, never silent
+        if (use_tma) {
+            if (!mbar_wait_bounded(bar, tma_phase) && tid == 0) atomicOr(A.misc + kMiscStatus, 4);  // reported by the host
             tma_phase ^= 1;
-        } else if (!GLOBAL) {
-            __pipeline_wait_prior(0);
         }
         __syncthreads();
 
-        unsigned char *win = GLOBAL ? g_win : s_win;
-
-        // ---- window pixels: one warp per window row, lanes along the row ----
-        const int src_pitch = GLOBAL ? pitch : tp;
-        const int src_x0 = GLOBAL ? 0 : tx0a, src_y0 = GLOBAL ? 0 : ty0;
-        auto SRC = [&](int o) -> unsigned { return GLOBAL ? (unsigned)__ldg(img + o) : (unsigned)s_tile[o]; };
+        // ---- window pixels ----
+        auto SRC = [&](int o) -> unsigned { return (unsigned)s_tile[o]; };
         if (A.upright) {
             for (int i = warp; i < n; i += NW) {
-                const int x = min(max(ux0 + i, 0), W - 1) - src_x0;
+                const int x = min(max(ux0 + i, 0), W - 1) - tx0a;
                 for (int j = lane; j < n; j += 32) {
-                    const int y = min(max(uy0 - j, 0), H - 1) - src_y0;
-                    win[i * n + j] = (unsigned char)SRC(y * src_pitch + x);
+                    const int y = min(max(uy0 - j, 0), H - 1) - ty0;
+                    s_win[i * n + j] = (unsigned char)SRC(y * tp + x);
                 }
             }
         } else {
-            const double kMagic = 6755399441055744.0;  // 1.5 * 2^52: floor via round-down addition
-            // a warp covers 1 row x 32 columns of the window (n <= 32) or 4 rows x 8 columns: far fewer
-            // idle lanes at the end of a row than 32-wide strips
+            // a warp covers 1 row x 32 columns of the window (n <= 32) or 4 rows x 8 columns: far fewer idle
+            // lanes at the end of a row than 32-wide strips
             const int rows_w = n > 32 ? 4 : 1, cols_w = 32 / rows_w;
             const int lj = lane & (cols_w - 1), li = lane / cols_w;
             const double lane_dx = (double)lj * (double)cd, lane_dy = (double)lj * (double)sd;
@@ -484,141 +654,174 @@ __global__ void __launch_bounds__(ClassT<CLS>::threads) k_descriptor(const __gri
             for (int i = warp * rows_w + li; i < n; i += NW * rows_w) {
                 double fx = s_rsx[i] + lane_dx;  // start + j * step, exact in fp64
                 double fy = s_rsy[i] - lane_dy;
-                unsigned char *wrow = win + i * n;
-                for (int j = lj; j < n; j += cols_w, fx += step_x, fy -= step_y) {
-                    const double mx = __dadd_rd(fx, kMagic), my = __dadd_rd(fy, kMagic);
-                    const int ix = __double2loint(mx), iy = __double2loint(my);
-                    unsigned v;
-                    if ((unsigned)ix < (unsigned)(W - 1) && (unsigned)iy < (unsigned)(H - 1)) {
-                        const float a = (float)(fx - (mx - kMagic)), bb = (float)(fy - (my - kMagic));
-                        const int q = (iy - src_y0) * src_pitch + (ix - src_x0);
-                        const float na = 1.f - a, nb = 1.f - bb;
-                        const float p00 = u8f(SRC(q)), p01 = u8f(SRC(q + 1));
-                        const float p10 = u8f(SRC(q + src_pitch)), p11 = u8f(SRC(q + src_pitch + 1));
-                        v = round_u8(p00 * na * nb + p01 * a * nb + p10 * na * bb + p11 * a * bb);
-                    } else {
-                        const int x = min(max(__double2int_rn(fx), 0), W - 1);
-                        const int y = min(max(__double2int_rn(fy), 0), H - 1);
-                        v = SRC((y - src_y0) * src_pitch + (x - src_x0));
-                    }
-                    wrow[j] = (unsigned char)v;
-                }
+                unsigned char *wrow = s_win + i * n;
+                for (int j = lj; j < n; j += cols_w, fx += step_x, fy -= step_y)
+                    wrow[j] = (unsigned char)rotated_tap(fx, fy, W, H, tx0a, ty0, tp, SRC);
             }
         }
         __syncthreads();
+        // the image tile is no longer needed: its space holds the row sums of the resize
+        descriptor_tail<THREADS>(A, kidx, n, s_win, reinterpret_cast<float *>(s_tile), S, int_scale, isc);
+    }
+}
 
-        // ---- resize to 21 x 21 (INTER_AREA) ----
-        // Fractional scales run the reference's two passes: row sums buf[sy][dx] = sum_x win[sy][x] * alpha
-        // (fp32, table order) for every window row, then the column pass.  Every window pixel is read once.
-        float *s_buf = reinterpret_cast<float *>(GLOBAL ? s_win : s_tile);  // the image tile is no longer needed
-        if (!int_scale) {
-            for (int it = tid; it < n * kPatch; it += THREADS) {
-                const int sy = it / kPatch, dx = it - sy * kPatch;
-                const int xs = s_tab.start[dx], xc = s_tab.count[dx];
-                const bool xhf = s_tab.has_first[dx], xhl = s_tab.has_last[dx];
-                const float xam = s_tab.a_mid[dx];
-                const unsigned char *row = win + sy * n + xs;
-                const int fend = xc - (xhl ? 1 : 0);
-                float buf = 0;
-                int f = 0;
-                if (xhf) {
-                    buf += u8f(row[0]) * s_tab.a_first[dx];
-                    f = 1;
-                }
-#pragma unroll 4
-                for (; f < fend; f++) buf += u8f(row[f]) * xam;
-                if (xhl) buf += u8f(row[xc - 1]) * s_tab.a_last[dx];
-                s_buf[it] = buf;
+__global__ void __launch_bounds__(BigT::threads) k_descriptor_big(const __grid_constant__ DescribeArgs A,
+                                                                  const __grid_constant__ CUtensorMap imap, int use_tma)
+{
+    constexpr int THREADS = BigT::threads, NW = THREADS / 32;
+    constexpr int tp = BigT::tp, tr = BigT::tr;
+    constexpr int CLS = kNumClasses - 1;
+    extern __shared__ __align__(128) unsigned char dyn_raw[];
+    unsigned char *dyn = dyn_raw + ((128u - ((uint32_t)__cvta_generic_to_shared(dyn_raw) & 127u)) & 127u);
+    unsigned char *s_tile0 = dyn;                       // two tile buffers
+    double *s_rsx = reinterpret_cast<double *>(dyn + 2 * BigT::tile_stride);
+    double *s_rsy = s_rsx + kMaxWindow;
+    __shared__ __align__(8) uint64_t s_bar[2];
+    __shared__ DescShared S;
+    uint32_t phase[2] = {0, 0};
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int W = A.geo.W, H = A.geo.H;
+    const int pitch = (int)A.img.pitch;
+    const int count = A.misc[kMiscClassCount + CLS];
+    const int *list = A.class_list + (size_t)CLS * A.list_stride;
+    // per-CTA global scratch: the n x n window, then the n x 21 row sums
+    unsigned char *g_win = A.win_scratch + (size_t)blockIdx.x * kBigScratchBytes;
+    float *g_buf = reinterpret_cast<float *>(g_win + (size_t)kMaxWindow * kMaxWindow);
+    const uint32_t bar0 = (uint32_t)__cvta_generic_to_shared(&s_bar[0]);
+    if (tid == 0) {
+        mbar_init1(bar0);
+        mbar_init1(bar0 + 8);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) S.work = atomicAdd(A.misc + kMiscClassHead + CLS, 1);
+        __syncthreads();
+        const int work = S.work;
+        if (work >= count) break;
+        const int kidx = list[work];
+        const int b = kidx / A.cap;
+        const surf_keypoint *kpp = A.kps + kidx;
+        const float cx = kpp->x, cy = kpp->y, size = kpp->size;
+        const uint8_t *img = A.img.ptr + (size_t)b * A.img.frame_stride;
+        const float s = size * 1.2f / 9.0f;
+        const int n = (int)(21 * s);
+        const float off = -(float)(n - 1) / 2;
+
+        float sd = 1.f, cd = 0.f;
+        int ux0 = 0, uy0 = 0;
+        if (A.upright) {
+            ux0 = __float2int_rn(cx + off);
+            uy0 = __float2int_rn(cy - off);
+        } else {
+            const float2 sc = A.sincos[kidx];
+            sd = sc.x;
+            cd = sc.y;
+            if (tid == 0) {
+                float v = cx + off * cd + off * sd;
+                for (int i = 0; i < n; i++, v += sd) s_rsx[i] = (double)v;
+            } else if (tid == 32) {
+                float v = cy - off * sd + off * cd;
+                for (int i = 0; i < n; i++, v += cd) s_rsy[i] = (double)v;
             }
-            __syncthreads();
         }
-        for (int p = tid; p < kPatchPx; p += THREADS) {
-            const int dy = p / kPatch, dx = p - dy * kPatch;
-            int outv;
-            if (int_scale && isc == 2) {
-                const unsigned char *r0 = win + (2 * dy) * n + 2 * dx, *r1 = r0 + n;
-                outv = (r0[0] + r0[1] + r1[0] + r1[1] + 2) >> 2;
-            } else if (int_scale) {
-                int acc = 0;
-                for (int v = 0; v < isc; v++) {
-                    const unsigned char *r0 = win + (dy * isc + v) * n + dx * isc;
-                    for (int u = 0; u < isc; u++) acc += r0[u];
-                }
-                const float wgt = 1.f / (isc * isc);
-                outv = sat_u8(acc * wgt);
+        const double inv = (double)kPatch / n;
+        const double scale = 1. / inv;
+        const int isc = __double2int_rn(scale);
+        const bool int_scale = fabs(scale - isc) < DBL_EPSILON;
+        if (!int_scale && warp == NW - 1 && lane < kPatch) area_tab_entry(S.tab, lane, n, scale);
+        __syncthreads();  // row starts visible
+
+        // ---- sub-windows of at most kSubSide x kSubSide taps, each with its own image tile ----
+        const int q = (n + kSubSide - 1) / kSubSide;
+        const int sw = (n + q - 1) / q;
+        const int n_sub = q * q;
+        // bounding box (tile origin) of sub-window `sub`; exact row starts are known here
+        auto sub_box = [&](int sub, int &i0, int &i1, int &j0, int &j1, int &tx0a, int &ty0, bool &fits) {
+            const int si = sub / q, sj = sub - si * q;
+            i0 = si * sw; i1 = min(n, i0 + sw);
+            j0 = sj * sw; j1 = min(n, j0 + sw);
+            int tx0, tx1, ty1;
+            if (A.upright) {
+                // window pixel (i, j) = frame (clamp(ux0 + i), clamp(uy0 - j))
+                tx0 = min(max(ux0 + i0, 0), W - 1);
+                tx1 = min(max(ux0 + i1 - 1, 0), W - 1);
+                ty1 = min(max(uy0 - j0, 0), H - 1);
+                ty0 = min(max(uy0 - (j1 - 1), 0), H - 1);
             } else {
-                const int ys = s_tab.start[dy], yc = s_tab.count[dy];
-                const bool yhf = s_tab.has_first[dy], yhl = s_tab.has_last[dy];
-                const float yaf = s_tab.a_first[dy], yam = s_tab.a_mid[dy], yal = s_tab.a_last[dy];
-                const float *col = s_buf + ys * kPatch + dx;
-                float acc = 0;
-                for (int e = 0; e < yc; e++) {
-                    const float beta = (e == 0 && yhf) ? yaf : ((e == yc - 1 && yhl) ? yal : yam);
-                    const float buf = col[e * kPatch];
-                    if (e == 0) acc = beta * buf; else acc += beta * buf;
-                }
-                outv = sat_u8(acc);
+                const double xa = s_rsx[i0], xb = s_rsx[i1 - 1], ya = s_rsy[i0], yb = s_rsy[i1 - 1];
+                const double ex0 = (double)j0 * (double)cd, ex1 = (double)(j1 - 1) * (double)cd;
+                const double ey0 = (double)j0 * (double)sd, ey1 = (double)(j1 - 1) * (double)sd;
+                const double minx = fmin(fmin(xa + ex0, xa + ex1), fmin(xb + ex0, xb + ex1));
+                const double maxx = fmax(fmax(xa + ex0, xa + ex1), fmax(xb + ex0, xb + ex1));
+                const double miny = fmin(fmin(ya - ey0, ya - ey1), fmin(yb - ey0, yb - ey1));
+                const double maxy = fmax(fmax(ya - ey0, ya - ey1), fmax(yb - ey0, yb - ey1));
+                tx0 = min(max(__double2int_rd(minx), 0), W - 1);
+                tx1 = min(max(__double2int_rd(maxx) + 1, 0), W - 1);
+                ty0 = min(max(__double2int_rd(miny), 0), H - 1);
+                ty1 = min(max(__double2int_rd(maxy) + 1, 0), H - 1);
             }
-            s_patch[p] = (unsigned char)outv;
+            tx0a = tx0 & ~15;
+            fits = (tx1 - tx0a + 1 <= tp) && (ty1 - ty0 + 1 <= tr);
+        };
+        bool bad = false;
+        if (use_tma && tid == 0) {  // prologue: first tile
+            int i0, i1, j0, j1, tx0a, ty0;
+            bool fits;
+            sub_box(0, i0, i1, j0, j1, tx0a, ty0, fits);
+            tma_load_tile(&imap, (uint32_t)__cvta_generic_to_shared(s_tile0), tx0a, ty0, b, bar0, BigT::tile_bytes);
         }
-        __syncthreads();
-        if (A.patches) {
-            unsigned char *po = A.patches + (size_t)kidx * kPatchPx;
-            for (int p = tid; p < kPatchPx; p += THREADS) po[p] = s_patch[p];
-        }
-        if (!A.desc) continue;
-
-        // ---- 2x2 Haar gradients of the patch, Gaussian weighted ----
-        for (int t = tid; t < 400; t += THREADS) {
-            const int i = t / 20, j = t - i * 20;
-            const unsigned char *r0 = s_patch + i * kPatch + j, *r1 = r0 + kPatch;
-            const float wgt = c_desc_w[t];
-            s_dx[t] = (r0[1] - r0[0] + r1[1] - r1[0]) * wgt;
-            s_dy[t] = (r1[0] - r0[0] + r1[1] - r0[1]) * wgt;
-        }
-        __syncthreads();
-        // ---- 4 x 4 sub-regions, one output component per thread, sequential fp32 sums ----
-        const int nb = A.extended ? 8 : 4;
-        for (int t = tid; t < D; t += THREADS) {
-            const int region = t / nb, comp = t - region * nb;
-            const int I = region >> 2, J = region & 3;
-            float acc = 0;
-            for (int y = I * 5; y < I * 5 + 5; y++)
-                for (int x = J * 5; x < J * 5 + 5; x++) {
-                    const float tx = s_dx[y * 20 + x], ty = s_dy[y * 20 + x];
-                    if (A.extended) {
-                        switch (comp) {
-                            case 0: if (ty >= 0) acc += tx; break;
-                            case 1: if (ty >= 0) acc += fabsf(tx); break;
-                            case 2: if (!(ty >= 0)) acc += tx; break;
-                            case 3: if (!(ty >= 0)) acc += fabsf(tx); break;
-                            case 4: if (tx >= 0) acc += ty; break;
-                            case 5: if (tx >= 0) acc += fabsf(ty); break;
-                            case 6: if (!(tx >= 0)) acc += ty; break;
-                            default: if (!(tx >= 0)) acc += fabsf(ty); break;
-                        }
-                    } else {
-                        switch (comp) {
-                            case 0: acc += tx; break;
-                            case 1: acc += ty; break;
-                            case 2: acc += fabsf(tx); break;
-                            default: acc += fabsf(ty); break;
+        for (int sub = 0; sub < n_sub; sub++) {
+            const int cur = sub & 1;
+            unsigned char *tile = s_tile0 + cur * BigT::tile_stride;
+            int i0, i1, j0, j1, tx0a, ty0;
+            bool fits;
+            sub_box(sub, i0, i1, j0, j1, tx0a, ty0, fits);
+            bad = bad || !fits;
+            if (use_tma) {
+                if (tid == 0 && sub + 1 < n_sub) {  // prefetch the next sub-window's tile into the other buffer
+                    int a0, a1, c0, c1, nx, ny;
+                    bool nf;
+                    sub_box(sub + 1, a0, a1, c0, c1, nx, ny, nf);
+                    tma_load_tile(&imap, (uint32_t)__cvta_generic_to_shared(s_tile0 + (cur ^ 1) * BigT::tile_stride), nx, ny, b,
+                                  bar0 + 8 * (cur ^ 1), BigT::tile_bytes);
+                }
+                if (!mbar_wait_bounded(bar0 + 8 * cur, phase[cur]) && tid == 0) atomicOr(A.misc + kMiscStatus, 4);
+                phase[cur] ^= 1;
+            } else {
+                int tx1 = min(tx0a + tp - 1, W - 1);
+                copy_tile_fallback<NW, tp>(A, img, pitch, tile, tx0a, tx1, ty0, min(tr, H - ty0));
+                __syncthreads();
+            }
+            auto SRC = [&](int o) -> unsigned { return (unsigned)tile[o]; };
+            if (fits) {
+                if (A.upright) {
+                    for (int i = i0 + warp; i < i1; i += NW) {
+                        const int x = min(max(ux0 + i, 0), W - 1) - tx0a;
+                        for (int j = j0 + lane; j < j1; j += 32) {
+                            const int y = min(max(uy0 - j, 0), H - 1) - ty0;
+                            g_win[i * n + j] = (unsigned char)SRC(y * tp + x);
                         }
                     }
+                } else {
+                    const int lj = lane & 7, li = lane >> 3;  // 4 rows x 8 columns per warp
+                    const double lane_dx = (double)(j0 + lj) * (double)cd, lane_dy = (double)(j0 + lj) * (double)sd;
+                    const double step_x = 8.0 * (double)cd, step_y = 8.0 * (double)sd;
+                    for (int i = i0 + warp * 4 + li; i < i1; i += NW * 4) {
+                        double fx = s_rsx[i] + lane_dx;
+                        double fy = s_rsy[i] - lane_dy;
+                        unsigned char *wrow = g_win + (size_t)i * n;
+                        for (int j = j0 + lj; j < j1; j += 8, fx += step_x, fy -= step_y)
+                            wrow[j] = (unsigned char)rotated_tap(fx, fy, W, H, tx0a, ty0, tp, SRC);
+                    }
                 }
-            s_vec[t] = acc;
+            }
+            __syncthreads();  // this buffer may be refilled (two iterations ahead) and g_win rows are complete
         }
-        __syncthreads();
-        if (warp == 0) {
-            double mag = 0;
-            for (int t = lane; t < D; t += 32) mag += (double)(s_vec[t] * s_vec[t]);
-#pragma unroll
-            for (int d = 16; d > 0; d >>= 1) mag += __shfl_xor_sync(FULL_MASK, mag, d);
-            if (lane == 0) s_scale = (float)(1. / (sqrt(mag) + DBL_EPSILON));
-        }
-        __syncthreads();
-        float *vo = A.desc + (size_t)kidx * D;
-        for (int t = tid; t < D; t += THREADS) vo[t] = s_vec[t] * s_scale;
+        if (bad && tid == 0) atomicOr(A.misc + kMiscStatus, 2);
+        descriptor_tail<THREADS>(A, kidx, n, g_win, g_buf, S, int_scale, isc);
     }
 }
 
@@ -649,8 +852,18 @@ void setup_class(ClassCfg &c, int sms)
     int per_sm = 1;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_descriptor<CLS>, CT::threads, c.smem);
     if (per_sm < 1) per_sm = 1;
-    if (CT::global && per_sm > kClassDGridPerSm) per_sm = kClassDGridPerSm;
     c.grid = sms * per_sm;  // persistent CTAs: a multiple of the SM count
+}
+
+void setup_big(ClassCfg &c, int sms)
+{
+    c.smem = BigT::smem;
+    cudaFuncSetAttribute(k_descriptor_big, cudaFuncAttributeMaxDynamicSharedMemorySize, c.smem);
+    int per_sm = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_descriptor_big, BigT::threads, c.smem);
+    if (per_sm < 1) per_sm = 1;
+    if (per_sm > kClassDGridPerSm) per_sm = kClassDGridPerSm;  // bounds the global window scratch
+    c.grid = sms * per_sm;
 }
 
 DevCfg &dev_cfg()
@@ -667,8 +880,7 @@ DevCfg &dev_cfg()
         setup_class<0>(c.cls[0], sms);
         setup_class<1>(c.cls[1], sms);
         setup_class<2>(c.cls[2], sms);
-        setup_class<3>(c.cls[3], sms);
-        setup_class<4>(c.cls[4], sms);
+        setup_big(c.cls[3], sms);
         for (int k = 0; k < kNumClasses - 1; k++) {
             cudaStreamCreateWithFlags(&c.side[k], cudaStreamNonBlocking);
             cudaEventCreateWithFlags(&c.join[k], cudaEventDisableTiming);
@@ -681,18 +893,16 @@ DevCfg &dev_cfg()
 
 }  // namespace
 
+// TMA box (pitch bytes x rows) of the image tile used by size class `cls`
 void describe_tile_box(int cls, int *pitch_bytes, int *rows)
 {
-    const int tp[kNumClasses] = {ClassT<0>::tp, ClassT<1>::tp, ClassT<2>::tp, ClassT<3>::tp, 0};
-    const int tr[kNumClasses] = {ClassT<0>::tr, ClassT<1>::tr, ClassT<2>::tr, ClassT<3>::tr, 0};
+    const int tp[kNumClasses] = {ClassT<0>::tp, ClassT<1>::tp, ClassT<2>::tp, BigT::tp};
+    const int tr[kNumClasses] = {ClassT<0>::tr, ClassT<1>::tr, ClassT<2>::tr, BigT::tr};
     *pitch_bytes = tp[cls];
     *rows = tr[cls];
 }
 
-size_t describe_scratch_bytes()
-{
-    return (size_t)dev_cfg().cls[kNumClasses - 1].grid * kMaxWindow * kMaxWindow;
-}
+size_t describe_scratch_bytes() { return (size_t)dev_cfg().cls[kNumClasses - 1].grid * kBigScratchBytes; }
 
 void launch_describe(const DescribeArgs &a, const CUtensorMap *imaps, int use_tma, cudaStream_t st, int *launches)
 {
@@ -704,16 +914,15 @@ void launch_describe(const DescribeArgs &a, const CUtensorMap *imaps, int use_tm
     // tails of the short launches overlap the long ones; join back on `st`.
     cudaEventRecord(c.fork, st);
     for (int k = 0; k < kNumClasses - 1; k++) cudaStreamWaitEvent(c.side[k], c.fork, 0);
-    k_descriptor<1><<<c.cls[1].grid, ClassT<1>::threads, c.cls[1].smem, st>>>(a, imaps[1], use_tma);
-    k_descriptor<4><<<c.cls[4].grid, ClassT<4>::threads, c.cls[4].smem, c.side[0]>>>(a, imaps[0], 0);
-    k_descriptor<3><<<c.cls[3].grid, ClassT<3>::threads, c.cls[3].smem, c.side[1]>>>(a, imaps[3], use_tma);
-    k_descriptor<2><<<c.cls[2].grid, ClassT<2>::threads, c.cls[2].smem, c.side[2]>>>(a, imaps[2], use_tma);
-    k_descriptor<0><<<c.cls[0].grid, ClassT<0>::threads, c.cls[0].smem, c.side[3]>>>(a, imaps[0], use_tma);
+    k_descriptor_big<<<c.cls[3].grid, BigT::threads, c.cls[3].smem, st>>>(a, imaps[3], use_tma);
+    k_descriptor<1><<<c.cls[1].grid, ClassT<1>::threads, c.cls[1].smem, c.side[0]>>>(a, imaps[1], use_tma);
+    k_descriptor<2><<<c.cls[2].grid, ClassT<2>::threads, c.cls[2].smem, c.side[1]>>>(a, imaps[2], use_tma);
+    k_descriptor<0><<<c.cls[0].grid, ClassT<0>::threads, c.cls[0].smem, c.side[2]>>>(a, imaps[0], use_tma);
     for (int k = 0; k < kNumClasses - 1; k++) {
         cudaEventRecord(c.join[k], c.side[k]);
         cudaStreamWaitEvent(st, c.join[k], 0);
     }
-    *launches += 5;
+    *launches += 4;
 }
 
 }  // namespace surfb200

@@ -269,7 +269,7 @@ void ensure_image_maps(surf_engine *e, const ImageRef &img, const FrameGeo &geo,
     const bool aligned16 = ((reinterpret_cast<uintptr_t>(img.ptr) | img.pitch | img.frame_stride) & 15) == 0;
     if (!enc || !e->use_tma || !aligned16) return;
     bool ok = true;
-    for (int c = 0; c < kNumClasses - 1; c++) {
+    for (int c = 0; c < kNumClasses; c++) {
         int tp = 0, tr = 0;
         describe_tile_box(c, &tp, &tr);
         cuuint64_t dims[3] = {(cuuint64_t)geo.W, (cuuint64_t)geo.H, (cuuint64_t)B};

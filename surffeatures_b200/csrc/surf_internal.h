@@ -73,13 +73,14 @@ struct ImageRef {
     size_t frame_stride;  // bytes between frames
 };
 
-// Descriptor windows are handled by size class (window side n = (int)(21 * size * 1.2 / 9)):
-// the rotated window's bounding box in the image and the n x n window itself are staged in shared
-// memory for classes A-C; class D (n > 184, about 1 % of keypoints) reads the image from global
-// memory and keeps its window in a per-CTA global scratch buffer.
-constexpr int kNumClasses = 5;
-constexpr int kClassMaxN0 = 64, kClassMaxN1 = 96, kClassMaxN2 = 128, kClassMaxN3 = 160;  // last class: up to kMaxWindow
-constexpr int kClassDGridPerSm = 2;
+// Descriptor windows are handled by size class (window side n = (int)(21 * size * 1.2 / 9)).  Classes 0-2
+// (n <= 64 / 96 / 128) stage the rotated window's whole bounding box and the window itself in shared memory;
+// the last class (n > 128) cuts the window into sub-windows of at most 96 x 96 taps, each with its own
+// image tile, and keeps the window in a per-CTA global scratch buffer.
+constexpr int kNumClasses = 4;
+constexpr int kClassMaxN0 = 64, kClassMaxN1 = 96, kClassMaxN2 = 128;  // last class: up to kMaxWindow
+constexpr int kClassDGridPerSm = 3;
+constexpr size_t kBigScratchBytes = (size_t)kMaxWindow * kMaxWindow + (size_t)kMaxWindow * kPatch * sizeof(float);
 
 // d_misc word layout
 constexpr int kMiscStatus = 1;
