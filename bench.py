@@ -236,6 +236,7 @@ def run_ours(args):
             for k in stage:
                 stage[k] += t[k]
         eng.wait_outputs()
+        eng.sync()               # compute stream and the matcher's own stream
         e1.record(stream)
         barrier()
         ms = e0.elapsed_time(e1)

@@ -38,6 +38,9 @@ struct surf_engine {
     int max_w = 0, max_h = 0, max_b = 0, cap = 0;
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;  // device->host result copies in asynchronous-output mode
+    cudaStream_t match_stream = nullptr; // surf_match_prev runs here, concurrently with the next batch's kernels
+    cudaEvent_t ev_batch_done = nullptr, ev_match_done = nullptr;
+    bool match_in_flight = false;
     cudaEvent_t ev_copy_done = nullptr, ev_match_copy_done = nullptr, ev_ready = nullptr;
     bool match_copies_in_flight = false;
     int async_outputs = 0;
@@ -523,6 +526,8 @@ int run_describe_pack(surf_engine *e, const ImageRef &img, const FrameGeo &geo, 
     rec(e, EV_DESCRIBE);
     if (pack) {
         if (e->copies_in_flight) CU(e, cudaStreamWaitEvent(e->stream, e->ev_copy_done, 0));
+        // the stream matcher of the previous batch (on its own stream) still reads the packed descriptors
+        if (e->match_in_flight) CU(e, cudaStreamWaitEvent(e->stream, e->ev_match_done, 0));
         launch_offsets(e->d_counts, e->d_ndel, e->cap, B, e->d_off_out, e->stream, &e->launches);
         launch_pack(e->sorted, want_desc ? e->d_desc : nullptr, p.extended ? 128 : 64, e->cap, B, e->d_off_in, e->d_ndel,
                     e->d_deleted, e->d_off_out, e->d_out_kp, want_desc ? e->d_out_desc : nullptr, e->stream,
@@ -630,6 +635,9 @@ int surf_create(const surf_params *params, int device, int max_width, int max_he
     for (int i = 0; i < EV_COUNT; i++) cudaEventCreate(&e->ev[i]);
     e->ev_valid = true;
     cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking);
+    cudaStreamCreateWithFlags(&e->match_stream, cudaStreamNonBlocking);
+    cudaEventCreateWithFlags(&e->ev_batch_done, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&e->ev_match_done, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&e->ev_copy_done, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&e->ev_match_copy_done, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&e->ev_ready, cudaEventDisableTiming);
@@ -657,6 +665,12 @@ void surf_destroy(surf_engine *e)
         cudaStreamSynchronize(e->copy_stream);
         cudaStreamDestroy(e->copy_stream);
     }
+    if (e->match_stream) {
+        cudaStreamSynchronize(e->match_stream);
+        cudaStreamDestroy(e->match_stream);
+    }
+    if (e->ev_batch_done) cudaEventDestroy(e->ev_batch_done);
+    if (e->ev_match_done) cudaEventDestroy(e->ev_match_done);
     if (e->ev_copy_done) cudaEventDestroy(e->ev_copy_done);
     if (e->ev_match_copy_done) cudaEventDestroy(e->ev_match_copy_done);
     if (e->ev_ready) cudaEventDestroy(e->ev_ready);
@@ -701,6 +715,8 @@ int surf_sync(surf_engine *e)
     int rc = ensure_device(e);
     if (rc) return rc;
     CU(e, cudaStreamSynchronize(e->stream));
+    CU(e, cudaStreamSynchronize(e->match_stream));
+    e->match_in_flight = false;
     return SURF_OK;
 }
 
@@ -1177,6 +1193,7 @@ int surf_match_redo_count(surf_engine *e, int *count)
     int rc = ensure_device(e);
     if (rc) return rc;
     CU(e, cudaStreamSynchronize(e->stream));
+    CU(e, cudaStreamSynchronize(e->match_stream));
     CU(e, cudaMemcpy(count, e->tc[e->last_tc_ws].counters + 1, sizeof(int), cudaMemcpyDeviceToHost));
     return SURF_OK;
 }
@@ -1217,25 +1234,31 @@ int surf_match_prev(surf_engine *e, float ratio, surf_dmatch *out, uint8_t *good
         CU(e, cudaMalloc(&e->d_stream_matches, nk * 2 * sizeof(surf_dmatch)));
         CU(e, cudaMalloc(&e->d_stream_good, nk));
     }
+    // The matcher runs on its own stream: it only depends on the batch just collected, so the caller can
+    // submit the next batch right away and its kernels overlap the (latency-bound) match kernels.
+    cudaStream_t ms = e->match_stream;
+    CU(e, cudaEventRecord(e->ev_batch_done, e->stream));
+    CU(e, cudaStreamWaitEvent(ms, e->ev_batch_done, 0));
     if (!e->stream_primed) {  // forget the previous frame: an empty predecessor slot
-        launch_zero(w.pool.count + e->tc_prev_slot, 1, e->stream, nullptr);
-        launch_zero(e->d_prev_off, 2, e->stream, nullptr);
+        launch_zero(w.pool.count + e->tc_prev_slot, 1, ms, nullptr);
+        launch_zero(e->d_prev_off, 2, ms, nullptr);
     }
     int launches = 0;
     launch_tc_stream_tables(w.segs, w.probs, B, slots, e->tc_prev_slot, e->d_out_desc, e->d_off_out, e->d_prev_desc,
-                            e->d_prev_off, e->stream, &launches);
+                            e->d_prev_off, ms, &launches);
     const int prev = (e->tc_prev_slot + B) % slots;
-    // the previous step's match results may still be on their way to the host (its own event: the
-    // keypoint/descriptor copies of THIS step, just enqueued by surf_collect_batch, must not hold us up)
-    if (e->match_copies_in_flight) CU(e, cudaStreamWaitEvent(e->stream, e->ev_match_copy_done, 0));
+    // the previous step's match results may still be on their way to the host
+    if (e->match_copies_in_flight) CU(e, cudaStreamWaitEvent(ms, e->ev_match_copy_done, 0));
     TcMatchArgs a{};
     a.pool = w.pool; a.segs = w.segs; a.n_segs = B; a.probs = w.probs; a.n_probs = B; a.n_splits = 1;
     a.max_q_rows = rows; a.cand = w.cand; a.counters = w.counters; a.redo_list = w.redo; a.dim = D; a.k = 2;
     a.ratio = ratio; a.out = e->d_stream_matches; a.good = e->d_stream_good;
-    launch_tc_match(a, e->stream, &launches);
+    launch_tc_match(a, ms, &launches);
     e->last_tc_ws = 1;
     // keep the last frame (fp32 rows + its slot) as the next batch's predecessor
-    launch_copy_rows(e->d_out_desc, e->d_off_out + B - 1, D, e->d_prev_desc, e->cap, e->d_prev_off, e->stream, &launches);
+    launch_copy_rows(e->d_out_desc, e->d_off_out + B - 1, D, e->d_prev_desc, e->cap, e->d_prev_off, ms, &launches);
+    CU(e, cudaEventRecord(e->ev_match_done, ms));
+    e->match_in_flight = true;
     e->launches = launches;
     e->timings.launches = launches;
     CU(e, cudaGetLastError());
@@ -1248,10 +1271,9 @@ int surf_match_prev(surf_engine *e, float ratio, surf_dmatch *out, uint8_t *good
             return fail(e, SURF_ERR_CAPACITY, "%ld keypoints in the batch; the match arrays hold %ld", total, capacity);
         }
         const cudaMemcpyKind kind = out_mem == SURF_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
-        cudaStream_t cs = e->stream;
+        cudaStream_t cs = ms;
         if (e->async_outputs) {  // copy stream waits for the match kernels, the host does not
-            CU(e, cudaEventRecord(e->ev_ready, e->stream));
-            CU(e, cudaStreamWaitEvent(e->copy_stream, e->ev_ready, 0));
+            CU(e, cudaStreamWaitEvent(e->copy_stream, e->ev_match_done, 0));
             cs = e->copy_stream;
         }
         if (out && total) CU(e, cudaMemcpyAsync(out, e->d_stream_matches, sizeof(surf_dmatch) * 2 * total, kind, cs));
@@ -1260,7 +1282,7 @@ int surf_match_prev(surf_engine *e, float ratio, surf_dmatch *out, uint8_t *good
             CU(e, cudaEventRecord(e->ev_match_copy_done, e->copy_stream));
             e->match_copies_in_flight = true;
         } else {
-            CU(e, cudaStreamSynchronize(e->stream));
+            CU(e, cudaStreamSynchronize(ms));
         }
     }
     return SURF_OK;
