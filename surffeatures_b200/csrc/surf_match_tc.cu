@@ -195,21 +195,24 @@ __global__ void k_tc_reset(TcPool pool, const TcSegment *__restrict__ segs, int 
 // ------------------------------------------------------------------------------------------------
 // K5b: candidates.
 // ------------------------------------------------------------------------------------------------
-// Running candidate set of one query row: kCand entries, unsorted; `worst` is the largest kept
+// Running candidate set of one query row: KC entries, unsorted; `worst` is the largest kept
 // approximate value and `wslot` where it sits.  A new value replaces the worst (strictly smaller
 // only, so equal values keep the earlier train row).  All indexing is by predicated selects so the
-// arrays stay in registers.
+// arrays stay in registers.  KC = 4 serves k <= 2 (the candidate scan is instruction-bound: every
+// replacement costs the whole warp), KC = 8 serves k = 3, 4.
+template <int KC>
 struct Cand {
-    float d[kCand];
-    int i[kCand];
+    float d[KC];
+    int i[KC];
     float worst;
     int wslot;
 };
 
-__device__ __forceinline__ void cand_replace_worst(Cand &c, float dist, int idx)
+template <int KC>
+__device__ __forceinline__ void cand_replace_worst(Cand<KC> &c, float dist, int idx)
 {
 #pragma unroll
-    for (int r = 0; r < kCand; r++) {
+    for (int r = 0; r < KC; r++) {
         const bool hit = (r == c.wslot);
         c.d[r] = hit ? dist : c.d[r];
         c.i[r] = hit ? idx : c.i[r];
@@ -217,7 +220,7 @@ __device__ __forceinline__ void cand_replace_worst(Cand &c, float dist, int idx)
     float w = c.d[0];
     int ws = 0;
 #pragma unroll
-    for (int r = 1; r < kCand; r++) {
+    for (int r = 1; r < KC; r++) {
         const bool g = c.d[r] > w;
         w = g ? c.d[r] : w;
         ws = g ? r : ws;
@@ -226,7 +229,7 @@ __device__ __forceinline__ void cand_replace_worst(Cand &c, float dist, int idx)
     c.wslot = ws;
 }
 
-template <int D>
+template <int D, int KC>
 __global__ void __launch_bounds__(256) k_tc_candidates(TcPool pool, const TcProblem *__restrict__ probs, int n_probs,
                                                        int mt_per_prob, int n_splits, int cand_stride,
                                                        TcCand *__restrict__ cand_out, int *__restrict__ work_head)
@@ -278,9 +281,9 @@ __global__ void __launch_bounds__(256) k_tc_candidates(TcPool pool, const TcProb
         const int per = (n_tiles + n_splits - 1) / n_splits;
         const int tile0 = split * per, tile1 = min(n_tiles, tile0 + per);
 
-        Cand best;
+        Cand<KC> best;
 #pragma unroll
-        for (int r = 0; r < kCand; r++) {
+        for (int r = 0; r < KC; r++) {
             best.d[r] = INFINITY;
             best.i[r] = -1;
         }
@@ -359,8 +362,8 @@ __global__ void __launch_bounds__(256) k_tc_candidates(TcPool pool, const TcProb
             TcCand o;
 #pragma unroll
             for (int r = 0; r < kCand; r++) {
-                o.d[r] = best.d[r];
-                o.i[r] = best.i[r];
+                o.d[r] = r < KC ? best.d[r < KC ? r : 0] : INFINITY;
+                o.i[r] = r < KC ? best.i[r < KC ? r : 0] : -1;
             }
             o.worst = best.worst;
             cand_out[((size_t)(p * n_splits + split) * 2 + half) * cand_stride + q0 + row] = o;
@@ -556,27 +559,26 @@ void launch_tc_match(const TcMatchArgs &a, cudaStream_t st, int *launches)
     int &grid = grids[dev & 63][D == 128];
     const size_t smem = tc_candidates_smem(D);
     if (!grid) {
-        int sms = 148, per_sm = 1;
+        int sms = 148;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        if (D == 64) {
-            cudaFuncSetAttribute(k_tc_candidates<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_tc_candidates<64>, 256, smem);
-        } else {
-            cudaFuncSetAttribute(k_tc_candidates<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_tc_candidates<128>, 256, smem);
-        }
-        if (per_sm < 1) per_sm = 1;
-        if (per_sm > 2) per_sm = 2;  // 256 TMEM columns per CTA: at most two CTAs share an SM's 512
-        if (D == 64) per_sm = 2;     // 2 x 101 KB of shared memory fit one SM
-        grid = sms * per_sm;
+        cudaFuncSetAttribute(k_tc_candidates<64, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_candidates_smem(64));
+        cudaFuncSetAttribute(k_tc_candidates<64, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_candidates_smem(64));
+        cudaFuncSetAttribute(k_tc_candidates<128, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_candidates_smem(128));
+        cudaFuncSetAttribute(k_tc_candidates<128, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_candidates_smem(128));
+        // 256 TMEM columns per CTA: at most two CTAs share an SM's 512; D = 64 needs 2 x 101 KB of shared memory
+        grid = sms * (D == 64 ? 2 : 1);
     }
     const int mt_per_prob = a.max_q_rows / kTM;
-    if (D == 64)
-        k_tc_candidates<64><<<grid, 256, smem, st>>>(a.pool, a.probs, a.n_probs, mt_per_prob, a.n_splits, a.max_q_rows,
-                                                     a.cand, a.counters);
-    else
-        k_tc_candidates<128><<<grid, 256, smem, st>>>(a.pool, a.probs, a.n_probs, mt_per_prob, a.n_splits, a.max_q_rows,
-                                                      a.cand, a.counters);
+    const bool small_k = a.k <= 2;
+#define SURF_TC_LAUNCH(DD, KK)                                                                                  \
+    k_tc_candidates<DD, KK><<<grid, 256, smem, st>>>(a.pool, a.probs, a.n_probs, mt_per_prob, a.n_splits, a.max_q_rows, \
+                                                     a.cand, a.counters)
+    if (D == 64) {
+        if (small_k) SURF_TC_LAUNCH(64, 4); else SURF_TC_LAUNCH(64, 8);
+    } else {
+        if (small_k) SURF_TC_LAUNCH(128, 4); else SURF_TC_LAUNCH(128, 8);
+    }
+#undef SURF_TC_LAUNCH
     dim3 gres(((size_t)a.max_q_rows * kCand + 255) / 256, a.n_probs);
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
