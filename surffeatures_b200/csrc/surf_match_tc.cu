@@ -465,34 +465,45 @@ __global__ void __launch_bounds__(256) k_tc_rescore(TcPool pool, const TcProblem
     }
 }
 
-// Exact redo of the (rare) queries whose candidate set could not be proven: one warp per query.
+// Exact redo of the (rare) queries whose candidate set could not be proven: one CTA per query, one train
+// row per thread at a time (each distance is the same sequential fp32 sum as in k_match_exact), per-thread
+// top-4, then a merge across the CTA.  A single query is latency-critical: a lone warp scanning thousands of
+// rows would take longer than the whole tensor-core pass.
 template <int D>
 __global__ void __launch_bounds__(256) k_tc_redo(TcPool pool, const TcProblem *__restrict__ probs, int k, float ratio,
                                                  surf_dmatch *__restrict__ out, uint8_t *__restrict__ good,
                                                  const int *__restrict__ redo_list, const int *__restrict__ redo_count)
 {
-    const int lane = threadIdx.x & 31;
+    __shared__ float s_d[8][4];
+    __shared__ int s_i[8][4];
+    __shared__ __align__(16) float s_q[D];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n = *redo_count;
-    for (int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < n; w += (gridDim.x * blockDim.x) >> 5) {
+    for (int w = blockIdx.x; w < n; w += gridDim.x) {
         const int p = redo_list[2 * w], gq = redo_list[2 * w + 1];
         const TcProblem pr = probs[p];
         const int nt = pool.count[pr.t_slot];
         const int q_row0 = pr.q_off ? pr.q_off[0] : pr.q_row0;
         const int t_row0 = pr.t_off ? pr.t_off[0] : pr.t_row0;
         const int out_row0 = pr.out_off ? pr.out_off[0] : pr.out_row0;
-        const float *qsrc = pr.qsrc, *tsrc = pr.tsrc;
-        const float *qv = qsrc + (size_t)(q_row0 + gq) * D;
+        __syncthreads();
+        if (tid < D) s_q[tid] = pr.qsrc[(size_t)(q_row0 + gq) * D + tid];
+        __syncthreads();
         float bd[4] = {INFINITY, INFINITY, INFINITY, INFINITY};
         int bi[4] = {-1, -1, -1, -1};
-        for (int t = lane; t < nt; t += 32) {
-            const float *tv = tsrc + (size_t)(t_row0 + t) * D;
+        for (int t = tid; t < nt; t += 256) {
+            const float4 *tv = reinterpret_cast<const float4 *>(pr.tsrc + (size_t)(t_row0 + t) * D);
             float acc = 0.f;
-#pragma unroll 8
-            for (int d = 0; d < D; d++) {
-                const float df = qv[d] - tv[d];
-                acc = fmaf(df, df, acc);
+#pragma unroll 4
+            for (int d = 0; d < D / 4; d++) {  // same element order as k_match_exact
+                const float4 b4 = __ldg(tv + d);
+                const float4 a4 = *reinterpret_cast<const float4 *>(s_q + 4 * d);
+                float df = a4.x - b4.x; acc = fmaf(df, df, acc);
+                df = a4.y - b4.y; acc = fmaf(df, df, acc);
+                df = a4.z - b4.z; acc = fmaf(df, df, acc);
+                df = a4.w - b4.w; acc = fmaf(df, df, acc);
             }
-            if (acc < bd[3]) {  // increasing t within a lane: ties keep the lower index
+            if (acc < bd[3]) {  // increasing t within a thread: ties keep the lower index
                 bd[3] = acc;
                 bi[3] = t;
 #pragma unroll
@@ -503,19 +514,15 @@ __global__ void __launch_bounds__(256) k_tc_redo(TcPool pool, const TcProblem *_
                     }
             }
         }
-        // warp merge of 32 sorted lists: k rounds of arg-min over the list heads
-        surf_dmatch *o = out + ((size_t)out_row0 + gq) * k;
-        float d0 = INFINITY, d1 = INFINITY;
-        int i0 = -1, i1 = -1;
-        for (int r = 0; r < k; r++) {
+        // warp merge of 32 sorted lists: 4 rounds of arg-min over the list heads (ties -> lower index)
+        for (int r = 0; r < 4; r++) {
             float hd = bd[0];
-            int hi = bi[0];
-            int src = lane;
+            int hi = bi[0], src = lane;
 #pragma unroll
-            for (int s = 16; s > 0; s >>= 1) {
-                const float od = __shfl_xor_sync(0xffffffffu, hd, s);
-                const int oi = __shfl_xor_sync(0xffffffffu, hi, s);
-                const int os = __shfl_xor_sync(0xffffffffu, src, s);
+            for (int s2 = 16; s2 > 0; s2 >>= 1) {
+                const float od = __shfl_xor_sync(0xffffffffu, hd, s2);
+                const int oi = __shfl_xor_sync(0xffffffffu, hi, s2);
+                const int os = __shfl_xor_sync(0xffffffffu, src, s2);
                 const bool take = (oi >= 0) && (hi < 0 || od < hd || (od == hd && oi < hi));
                 if (take) { hd = od; hi = oi; src = os; }
             }
@@ -524,16 +531,37 @@ __global__ void __launch_bounds__(256) k_tc_redo(TcPool pool, const TcProblem *_
                 bd[3] = INFINITY; bi[3] = -1;
             }
             if (lane == 0) {
+                s_d[warp][r] = hd;
+                s_i[warp][r] = hi;
+            }
+        }
+        __syncthreads();
+        if (tid == 0) {  // merge the 8 warps' sorted 4-lists
+            int head[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            surf_dmatch *o = out + ((size_t)out_row0 + gq) * k;
+            float d0 = INFINITY, d1 = INFINITY;
+            int i0 = -1, i1 = -1;
+            for (int r = 0; r < k; r++) {
+                int bw = -1;
+                float hd = INFINITY;
+                int hi = -1;
+                for (int ww = 0; ww < 8; ww++) {
+                    if (head[ww] >= 4) continue;
+                    const float od = s_d[ww][head[ww]];
+                    const int oi = s_i[ww][head[ww]];
+                    if (oi < 0) continue;
+                    if (hi < 0 || od < hd || (od == hd && oi < hi)) { hd = od; hi = oi; bw = ww; }
+                }
+                if (bw >= 0) head[bw]++;
                 o[r].query_idx = gq;
                 o[r].train_idx = hi;
                 o[r].img_idx = hi < 0 ? -1 : 0;
                 o[r].distance = sqrtf(hd);
+                if (r == 0) { d0 = hd; i0 = hi; }
+                if (r == 1) { d1 = hd; i1 = hi; }
             }
-            if (r == 0) { d0 = hd; i0 = hi; }
-            if (r == 1) { d1 = hd; i1 = hi; }
+            if (good && k >= 2) good[out_row0 + gq] = (i0 >= 0 && i1 >= 0 && sqrtf(d0) < ratio * sqrtf(d1)) ? 1 : 0;
         }
-        if (lane == 0 && good && k >= 2)
-            good[out_row0 + gq] = (i0 >= 0 && i1 >= 0 && sqrtf(d0) < ratio * sqrtf(d1)) ? 1 : 0;
     }
 }
 
