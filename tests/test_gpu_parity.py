@@ -516,3 +516,34 @@ def test_async_output_mode_gives_identical_results():
             assert np.array_equal(got[i][3].astype(bool), g)
     finally:
         e.close()
+
+
+def test_device_frames_with_unaligned_pitch_take_the_fallback_path(oracle):
+    """Frames handed over as device pointers with a pitch that is not a multiple of 16 cannot use TMA:
+    the 4-byte cp.async tile path must give the same bytes."""
+    import torch
+
+    from surffeatures_b200 import KEYPOINT_DTYPE, MEM_DEVICE, MEM_HOST, SURF
+
+    frames = speckle.speckle_stream(2, 200, 300, seed=11, fresh=0.0)
+    pitch = 308                                         # multiple of 4, not of 16
+    buf = torch.zeros((2, 200, pitch), dtype=torch.uint8, device="cuda")
+    buf[:, :, :300] = torch.from_numpy(frames).cuda()
+    e = SURF(100, 4, 3, max_width=300, max_height=200, max_batch=2, max_keypoints=8192)
+    try:
+        ref = e.detectAndComputeBatch(frames)
+        cap = 2 * 8192
+        k = torch.zeros((cap, 7), dtype=torch.float32).pin_memory()
+        d = torch.zeros((cap, 64), dtype=torch.float32).pin_memory()
+        off = np.zeros(3, np.int32)
+        torch.cuda.synchronize()
+        e.submit(buf.data_ptr(), MEM_DEVICE, 2, 300, 200, pitch, 200 * pitch, True)
+        e.collect(k.data_ptr(), d.data_ptr(), MEM_HOST, cap, off)
+        for b in range(2):
+            kk = k.numpy()[off[b]:off[b + 1]].copy().view(KEYPOINT_DTYPE).reshape(-1)
+            assert kk.tobytes() == ref[b][0].tobytes()
+            assert np.array_equal(d.numpy()[off[b]:off[b + 1]], ref[b][1])
+        ok, od = oracle.detect_and_compute(frames[1], oracle.params(100, 4, 3))
+        assert len(ok) == off[2] - off[1]
+    finally:
+        e.close()
