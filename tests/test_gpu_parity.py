@@ -547,3 +547,27 @@ def test_device_frames_with_unaligned_pitch_take_the_fallback_path(oracle):
         assert len(ok) == off[2] - off[1]
     finally:
         e.close()
+
+
+@pytest.mark.parametrize("shape,thr,octaves,layers", [((251, 333), 100, 4, 3), ((333, 251), 200, 3, 1),
+                                                      ((480, 640), 300, 4, 4), ((200, 1000), 100, 2, 2),
+                                                      ((640, 480), 100, 5, 2)])
+def test_odd_sizes_and_layer_counts(oracle, shape, thr, octaves, layers):
+    """Frame sizes that are not multiples of the tile / alignment granules and layer counts that take the
+    generic (run-time table) TMA kernel or the non-fused kernels."""
+    from surffeatures_b200 import SURF
+
+    img = speckle.speckle_frame(shape[0], shape[1], seed=shape[0] + layers, blobs=5)
+    e = SURF(thr, octaves, layers, max_width=shape[1], max_height=shape[0], max_keypoints=32768)
+    try:
+        raw = e.raw_keypoints(img)
+        k, d = e.detectAndCompute(img)
+    finally:
+        e.close()
+    p = oracle.params(thr, octaves, layers)
+    assert raw.tobytes() == oracle.raw_keypoints(img, p).tobytes()
+    ok, od = oracle.detect_and_compute(img, p)
+    assert len(k) == len(ok) > 50
+    for f in ("x", "y", "size", "angle", "response", "octave", "class_id"):
+        assert np.array_equal(k[f], ok[f]), f
+    assert np.linalg.norm(d - od, axis=1).max() <= 1e-4
