@@ -116,19 +116,38 @@ __device__ __forceinline__ void find_frame(const int *offsets, int B, int w, int
 constexpr int kOriWarps = 8;
 
 struct __align__(16) OriSample {
-    int iang;    // cvRound(fastAtan2(Y, X))
-    float X, Y;  // Gaussian-weighted Haar responses
-    int pad;
+    float X, Y;          // Gaussian-weighted Haar responses
+    unsigned m0, m1;     // membership of the sample in windows 0..31 / 32..63 (bit w = window w)
 };
+
+// The 72 sliding windows (0, 5, ..., 355 degrees; a sample with rounded angle a belongs to window w iff
+// d = |a - 5w| < 30 or d > 330) that contain angle a form one circular run of 11 or 12 windows:
+// [floor((a-30)/5)+1, ceil((a+30)/5)-1] mod 72.  Returned as a 72-bit mask (m0, m1, m2 = windows 64..71).
+__device__ __forceinline__ void window_mask(int a, unsigned &m0, unsigned &m1, unsigned &m2)
+{
+    const int wmin = (a + 330) / 5 - 71, wmax = (a + 34) / 5 - 1;
+    const int c = wmax - wmin + 1;
+    const int start = wmin < 0 ? wmin + 72 : wmin;
+    const unsigned long long base = (1ull << c) - 1;
+    unsigned long long lo = start < 64 ? base << start : 0ull;
+    unsigned long long hi = start >= 64 ? base << (start - 64) : (start + c > 64 ? base >> (64 - start) : 0ull);
+    lo |= hi >> 8;  // windows 72.. wrap around to 0..
+    m0 = (unsigned)lo;
+    m1 = (unsigned)(lo >> 32);
+    m2 = (unsigned)hi & 0xffu;
+}
 
 __global__ void __launch_bounds__(kOriWarps * 32) k_orient(const __grid_constant__ DescribeArgs A)
 {
     __shared__ OriSample s_smp[kOriWarps][kOriSamples + 3];
+    __shared__ unsigned char s_m2[kOriWarps][kOriSamples + 3];  // membership in windows 64..71
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int W = A.geo.W, H = A.geo.H, SP = A.geo.SP;
     const int total = A.offsets[A.B];
     const bool want_desc = (A.desc != nullptr) || (A.patches != nullptr);
     OriSample *smp = s_smp[warp];
+    unsigned char *smp2 = s_m2[warp];
+    const unsigned lanebit = 1u << lane;
 
     for (int w = blockIdx.x * kOriWarps + warp; w < total; w += gridDim.x * kOriWarps) {
         int b, slot;
@@ -174,11 +193,13 @@ __global__ void __launch_bounds__(kOriWarps * 32) k_orient(const __grid_constant
                 const unsigned bal = __ballot_sync(FULL_MASK, valid);
                 if (valid) {
                     OriSample o;
-                    o.iang = __float2int_rn(fast_atan2_deg(Y, X));
+                    unsigned m2;
+                    window_mask(__float2int_rn(fast_atan2_deg(Y, X)), o.m0, o.m1, m2);
                     o.X = X;
                     o.Y = Y;
-                    o.pad = 0;
-                    smp[na + __popc(bal & ((1u << lane) - 1))] = o;
+                    const int pos = na + __popc(bal & ((1u << lane) - 1));
+                    smp[pos] = o;
+                    smp2[pos] = (unsigned char)m2;
                 }
                 na += __popc(bal);
             }
@@ -188,24 +209,24 @@ __global__ void __launch_bounds__(kOriWarps * 32) k_orient(const __grid_constant
             } else {
                 // ---- 72 sliding windows (lane handles windows lane, lane+32, lane+64), fp32 sums in
                 //      sample order; first strict maximum over increasing window index ----
+                // lane owns windows lane, lane + 32 and (lanes 0..7) lane + 64: one pass over the samples feeds
+                // all three; membership is one bit test per window (masks built with the samples)
                 float bmod = 0, bx = 0, by = 0;
                 int bi = 1 << 30;
-                if (lane < 24) {
-                    // lane owns windows lane, lane + 24, lane + 48: one pass over the samples feeds all three
-                    const int a0 = lane * 5, a1 = a0 + 120, a2 = a0 + 240;
+                {
                     float sx0 = 0, sy0 = 0, sx1 = 0, sy1 = 0, sx2 = 0, sy2 = 0;
-#pragma unroll 2
+#pragma unroll 4
                     for (int k = 0; k < na; k++) {
                         const OriSample o = smp[k];
-                        const int d0 = abs(o.iang - a0), d1 = abs(o.iang - a1), d2 = abs(o.iang - a2);
-                        if (d0 < 30 || d0 > 330) { sx0 += o.X; sy0 += o.Y; }
-                        if (d1 < 30 || d1 > 330) { sx1 += o.X; sy1 += o.Y; }
-                        if (d2 < 30 || d2 > 330) { sx2 += o.X; sy2 += o.Y; }
+                        const unsigned m2 = smp2[k];
+                        if (o.m0 & lanebit) { sx0 += o.X; sy0 += o.Y; }
+                        if (o.m1 & lanebit) { sx1 += o.X; sy1 += o.Y; }
+                        if (m2 & lanebit) { sx2 += o.X; sy2 += o.Y; }
                     }
-                    const float m0 = sx0 * sx0 + sy0 * sy0, m1 = sx1 * sx1 + sy1 * sy1, m2 = sx2 * sx2 + sy2 * sy2;
-                    if (m0 > bmod) { bmod = m0; bx = sx0; by = sy0; bi = lane; }
-                    if (m1 > bmod) { bmod = m1; bx = sx1; by = sy1; bi = lane + 24; }
-                    if (m2 > bmod) { bmod = m2; bx = sx2; by = sy2; bi = lane + 48; }
+                    const float q0 = sx0 * sx0 + sy0 * sy0, q1 = sx1 * sx1 + sy1 * sy1, q2 = sx2 * sx2 + sy2 * sy2;
+                    if (q0 > bmod) { bmod = q0; bx = sx0; by = sy0; bi = lane; }
+                    if (q1 > bmod) { bmod = q1; bx = sx1; by = sy1; bi = lane + 32; }
+                    if (lane < 8 && q2 > bmod) { bmod = q2; bx = sx2; by = sy2; bi = lane + 64; }
                 }
 #pragma unroll
                 for (int d = 16; d > 0; d >>= 1) {
