@@ -276,6 +276,11 @@ def run_ours(args):
                 "limiter": "instruction issue, not HBM: smsp__issue_active 68-86 % in the descriptor kernels "
                            "(~6300 exact bilinear taps per keypoint); see profiles/r1/",
                 "peak_kind": "burst copy peak; the stage is timed inside a long step",
+                # the stage's real limiter: warp instructions issued (ncu smsp__inst_executed.sum of the describe
+                # kernels at batch 64, profiles/r1/) / stage time, against 148 SMs x 4 schedulers x SM clock
+                "issue_slots": ({"warp_inst_per_step": 6.9e9, "achieved_ginst_s": 6.9e9 / (stage_ms[dom] * 1e-3) / 1e9,
+                                 "peak_ginst_s": 148 * 4 * 1.965, "frac": 6.9e9 / (stage_ms[dom] * 1e-3) / (148 * 4 * 1.965e9)}
+                                if (dom == "describe" and B == 64) else None),
                 "algorithmic_bytes_per_launch": dom_bytes, "ms_per_launch": stage_ms[dom],
                 "stage_ms_per_step": stage_ms,
                 "whole_path_frac": alg["total"] * B * steps / (ms_dev * 1e-3) / 1e9 / peak}

@@ -638,16 +638,14 @@ __global__ void __launch_bounds__(ClassT<CLS>::threads) k_descriptor(const __gri
         if (!int_scale && warp == NW - 1 && lane < kPatch) area_tab_entry(S.tab, lane, n, scale);
 
         if (!use_tma) copy_tile_fallback<NW, tp>(A, img, pitch, s_tile, tx0a, tx1, ty0, th_rows);
-        if (!A.upright && (tid == 0 || tid == 32)) {
-            // row starts advance by sequential fp32 additions (x chain on warp 0, y chain on warp 1),
-            // stored as doubles for the tap loop; runs while the tile is in flight
-            if (tid == 0) {
-                float v = cx + off * cd + off * sd;
-                for (int i = 0; i < n; i++, v += sd) s_rsx[i] = (double)v;
-            } else {
-                float v = cy - off * sd + off * cd;
-                for (int i = 0; i < n; i++, v += cd) s_rsy[i] = (double)v;
-            }
+        if (!A.upright && tid < 2) {
+            // row starts advance by sequential fp32 additions (x chain on lane 0, y chain on lane 1 of the same
+            // warp: one instruction stream for both), stored as doubles for the tap loop; runs while the tile
+            // is in flight
+            float v = tid == 0 ? cx + off * cd + off * sd : cy - off * sd + off * cd;
+            const float inc = tid == 0 ? sd : cd;
+            double *dst = tid == 0 ? s_rsx : s_rsy;
+            for (int i = 0; i < n; i++, v += inc) dst[i] = (double)v;
         }
         if (use_tma) {
             if (!mbar_wait_bounded(bar, tma_phase) && tid == 0) atomicOr(A.misc + kMiscStatus, 4);  // reported by the host
@@ -740,12 +738,11 @@ __global__ void __launch_bounds__(BigT::threads) k_descriptor_big(const __grid_c
             const float2 sc = A.sincos[kidx];
             sd = sc.x;
             cd = sc.y;
-            if (tid == 0) {
-                float v = cx + off * cd + off * sd;
-                for (int i = 0; i < n; i++, v += sd) s_rsx[i] = (double)v;
-            } else if (tid == 32) {
-                float v = cy - off * sd + off * cd;
-                for (int i = 0; i < n; i++, v += cd) s_rsy[i] = (double)v;
+            if (tid < 2) {  // x chain on lane 0, y chain on lane 1
+                float v = tid == 0 ? cx + off * cd + off * sd : cy - off * sd + off * cd;
+                const float inc = tid == 0 ? sd : cd;
+                double *dst = tid == 0 ? s_rsx : s_rsy;
+                for (int i = 0; i < n; i++, v += inc) dst[i] = (double)v;
             }
         }
         const double inv = (double)kPatch / n;
