@@ -199,7 +199,8 @@ __global__ void k_tc_reset(TcPool pool, const TcSegment *__restrict__ segs, int 
 // approximate value and `wslot` where it sits.  A new value replaces the worst (strictly smaller
 // only, so equal values keep the earlier train row).  All indexing is by predicated selects so the
 // arrays stay in registers.  KC = 4 serves k <= 2 (the candidate scan is instruction-bound: every
-// replacement costs the whole warp), KC = 8 serves k = 3, 4.
+// replacement costs the whole warp; KC = 3 was measured and sends ~0.7 % of the queries to the redo
+// kernel because the bound is then the third neighbour itself), KC = 8 serves k = 3, 4.
 template <int KC>
 struct Cand {
     float d[KC];
@@ -245,8 +246,11 @@ __global__ void __launch_bounds__(256) k_tc_candidates(TcPool pool, const TcProb
     __shared__ __align__(8) uint64_t s_bar[2];  // [0] MMA done (tcgen05.commit), [1] operands landed (bulk copies)
     __shared__ uint32_t s_tmem;
     __shared__ int s_item;
+    __shared__ float s_thr[2][kTM];  // filter threshold published by each column half of a query row
 
     const int tid = threadIdx.x, warp = tid >> 5;
+    volatile float *my_thr = &s_thr[warp >> 2][(warp & 3) * 32 + (tid & 31)];
+    const volatile float *partner_thr = &s_thr[(warp >> 2) ^ 1][(warp & 3) * 32 + (tid & 31)];
     const uint32_t bar_mma = smem_u32(&s_bar[0]), bar_ld = smem_u32(&s_bar[1]);
     if (tid == 0) {
         mbar_init(bar_mma, 1);
@@ -289,6 +293,8 @@ __global__ void __launch_bounds__(256) k_tc_candidates(TcPool pool, const TcProb
         }
         best.worst = INFINITY;
         best.wslot = 0;
+        float thr = INFINITY;
+        *my_thr = INFINITY;  // read by the partner only after the tile loop's first __syncthreads
         const size_t trow_base = (size_t)pr.t_slot * pool.slot_rows;
         // operands arrive by TMA bulk copies (contiguous runs of core matrices), counted on bar_ld
         auto load_train_tile = [&](int tile, int stage) {
@@ -337,7 +343,11 @@ __global__ void __launch_bounds__(256) k_tc_candidates(TcPool pool, const TcProb
             }
 
             // ---- epilogue: 8 warps; warp w reads TMEM lanes 32*(w%4).. (its query rows) and the
-            //      column half w/4, so two threads share a query row and each keeps its own list ----
+            //      column half w/4, so two threads share a query row and each keeps its own list.
+            //      The filter threshold `thr` is the smaller of this list's worst kept value and the
+            //      partner's published one: both are >= the KC-th smallest value of the whole row, so
+            //      nothing that belongs to the row's KC smallest is ever rejected, and every value
+            //      either list rejects or evicts is >= the final thr (the bound the margin test uses).
             const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16);
             const float *tn = sTn + stage * kTN;
             const int lim = min(kTN, nt - t0);
@@ -346,13 +356,24 @@ __global__ void __launch_bounds__(256) k_tc_candidates(TcPool pool, const TcProb
             for (int c0 = cbeg; c0 < cbeg + kTN / 2; c0 += 32) {
                 float v[32];
                 tmem_ld32(lane_addr + c0, v);
+                thr = fminf(thr, *partner_thr);
                 if (c0 < lim) {
 #pragma unroll
-                    for (int c = 0; c < 32; c++) {
-                        const float dist = fmaf(-2.f, v[c], tn[c0 + c]);  // |t|^2 - 2 q.t  (+ |q|^2 later)
-                        if (dist < best.worst) cand_replace_worst(best, dist, t0 + c0 + c);
+                    for (int c = 0; c < 32; c += 4) {
+                        const float4 t4 = *reinterpret_cast<const float4 *>(tn + c0 + c);
+                        // |t|^2 - 2 q.t  (+ |q|^2 later); padded train rows carry |t|^2 = inf
+                        const float d0 = fmaf(-2.f, v[c], t4.x), d1 = fmaf(-2.f, v[c + 1], t4.y);
+                        const float d2 = fmaf(-2.f, v[c + 2], t4.z), d3 = fmaf(-2.f, v[c + 3], t4.w);
+                        if (fminf(fminf(d0, d1), fminf(d2, d3)) < thr) {  // one test per four columns
+                            const int idx = t0 + c0 + c;
+                            if (d0 < thr) { cand_replace_worst(best, d0, idx); thr = fminf(thr, best.worst); }
+                            if (d1 < thr) { cand_replace_worst(best, d1, idx + 1); thr = fminf(thr, best.worst); }
+                            if (d2 < thr) { cand_replace_worst(best, d2, idx + 2); thr = fminf(thr, best.worst); }
+                            if (d3 < thr) { cand_replace_worst(best, d3, idx + 3); thr = fminf(thr, best.worst); }
+                        }
                     }
                 }
+                *my_thr = thr;
             }
             tc_fence_before();
             __syncthreads();  // every warp has drained TMEM before the next tile's MMA overwrites it
@@ -365,7 +386,7 @@ __global__ void __launch_bounds__(256) k_tc_candidates(TcPool pool, const TcProb
                 o.d[r] = r < KC ? best.d[r < KC ? r : 0] : INFINITY;
                 o.i[r] = r < KC ? best.i[r < KC ? r : 0] : -1;
             }
-            o.worst = best.worst;
+            o.worst = thr;  // lower bound of every value this list did not keep
             cand_out[((size_t)(p * n_splits + split) * 2 + half) * cand_stride + q0 + row] = o;
         }
     }
