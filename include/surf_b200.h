@@ -185,6 +185,54 @@ int surf_match_redo_count(surf_engine *e, int *count);
  * global), out is n_query x k.  Device pointers; runs on the engine stream. */
 int surf_merge_topk(surf_engine *e, const surf_dmatch *in, int n_ranks, int n_query, int k, surf_dmatch *out);
 
+/* ---- "next" row f2: the train database behind DescriptorMatcher::add / clear / knnMatch ----
+ * Reference: computeNext() hands all descriptor Mats of a sweep to the matcher,
+ * vtkSlicerSurfFeaturesLogic.cxx:1402-1403 (clear + add(vector<Mat>)), and
+ * matchDescriptorsKNN :635-643 queries it; DMatch.imgIdx / trainIdx follow the add() order.
+ * The database lives on the device: fp32 rows (exact rescoring), their BF16 hi/lo tensor-core
+ * form (prepared once per add), |row|^2, the keypoints of the rows (for the Hough vote below) and
+ * the image row offsets.  Exact brute-force L2 like surf_match_knn; ties -> lower image, lower row. */
+typedef struct surf_db surf_db;
+
+int surf_db_create(surf_engine *e, int dim, long max_rows, int max_images, surf_db **out);
+void surf_db_destroy(surf_db *db);
+int surf_db_clear(surf_db *db);                                   /* DescriptorMatcher::clear() */
+/* DescriptorMatcher::add(): n_images more train images; image i owns rows
+ * [offsets[i], offsets[i+1]) of descriptors (offsets: host array of n_images+1, offsets[0] may be
+ * non-zero).  keypoints (optional, same rows) are kept for surf_correspond.  mem tells where
+ * descriptors / keypoints live (e.g. SURF_MEM_DEVICE with the pointers of surf_device_results). */
+int surf_db_add(surf_db *db, const float *descriptors, const surf_keypoint *keypoints, const int32_t *offsets,
+                int n_images, int mem);
+int surf_db_size(const surf_db *db, long *rows, int *images);
+/* knnMatch(query, k) against the whole database (k <= 4): out[n_query*k], img_idx = train image,
+ * train_idx = row within that image (-1 / -1 when the database has fewer than k rows). */
+int surf_db_knn(surf_db *db, const float *query, int n_query, int k, surf_dmatch *out, int mem);
+
+/* ---- "next" row f3: inter-slice correspondence, computeNextInterSliceCorrespondence :1434-1571 ----
+ * For every query image: knnMatch(k=3) against the train database and knnMatch(k=1) against the
+ * bogus database (:1457-1458); drop a query keypoint when d_train / d_bogus > bogus_ratio (0.95,
+ * :1463-1480); Hough pose-consistency vote over the surviving matches (houghTransform :241-345 with
+ * the poll booth of :86-164, reference point = mask centroid); per-train-image vote count and the
+ * best image (first maximum, :1485-1512).
+ * matches of query image i start at matches[q_offsets[i]] (results[i].n_matches of them, in query
+ * order); entries the Hough vote rejects are kept with query/train/img index -1 exactly as the
+ * reference leaves them in afterHoughMatches. */
+typedef struct surf_vote_params {
+    float bogus_ratio; /* 0.95 */
+    int32_t ref_x, ref_y; /* xcentroid, ycentroid of the cropped mask (computeCentroid :839-860) */
+} surf_vote_params;
+
+typedef struct surf_vote_result {
+    int32_t n_matches;   /* matches that passed the bogus filter (size of afterHoughMatches[i]) */
+    int32_t hough_count; /* votes of the winning poll booth (iMatchCount) */
+    int32_t best_image;  /* bestMatches[i]: train image with most surviving matches, -1 if no train image */
+    int32_t best_count;  /* bestMatchesCount[i] */
+} surf_vote_result;
+
+int surf_correspond(surf_db *train, surf_db *bogus, const float *query_descriptors,
+                    const surf_keypoint *query_keypoints, const int32_t *q_offsets, int n_query_images,
+                    const surf_vote_params *params, surf_dmatch *matches, surf_vote_result *results, int mem);
+
 const char *surf_version(void);
 
 #ifdef __cplusplus

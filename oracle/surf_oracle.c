@@ -784,3 +784,147 @@ void orc_knn_match(const float *q, int nq, const float *t, int nt, int d, int k,
         }
     }
 }
+
+/* =====================================================================================================
+ * "Next" rows f2 / f3: train database localisation, bogus filter, Hough pose vote, per-image votes.
+ * Restates SurfFeatures/Logic/vtkSlicerSurfFeaturesLogic.cxx:73-345 (HoughCodeSimilarity, angle_radians,
+ * compatible_poll_booths_line_segment, houghTransform) and :1434-1571 (computeNextInterSliceCorrespondence).
+ *
+ * Arithmetic model.  The reference file says `using namespace std;`, so sin / cos / atan2 / log / sqrt on
+ * float arguments resolve to the float overloads, and every product-sum is separate fp32 operations (x86-64
+ * SSE, no contraction).  Which float libm produced the reference's numbers is platform-dependent (it was built
+ * on Windows and macOS); this restatement therefore defines the float functions as CORRECTLY ROUNDED
+ * (evaluate in double, round once) -- libm_float != 0 switches to this machine's sinf/cosf/atan2f/logf so a
+ * test can measure how often that choice matters.  angle_radians() deliberately keeps the reference's factor
+ * 2 (it maps degrees to 2*pi*a/180) and is applied a second time inside the compatibility test, as upstream.
+ * ===================================================================================================== */
+#define ORC_PI 3.141592653589793
+
+static float h_sin(float x, int lf) { return lf ? sinf(x) : (float)sin((double)x); }
+static float h_cos(float x, int lf) { return lf ? cosf(x) : (float)cos((double)x); }
+static float h_atan2(float y, float x, int lf) { return lf ? atan2f(y, x) : (float)atan2((double)y, (double)x); }
+static float h_log(float x, int lf) { return lf ? logf(x) : (float)log((double)x); }
+
+/* angle_radians (:196-201): double arithmetic, result returned as float */
+static float h_angle_radians(float a) { return (float)((2.0f * ORC_PI * a) / 180.0f); }
+
+typedef struct { float row, col, ori, scl; } orc_booth;
+
+/* HoughCodeSimilarity::SetHoughCode (:86-110) + FindPollBooth (:112-141, non-mirrored branch) for one match */
+static orc_booth h_poll_booth(const orc_keypoint *q, const orc_keypoint *t, int refx, int refy, int lf)
+{
+    const float key_row = q->y, key_col = q->x, key_ori = h_angle_radians(q->angle), key_scl = q->size;
+    const float poll_row = (float)refy, poll_col = (float)refx;
+    const float diff_row = poll_row - key_row, diff_col = poll_col - key_col;
+    const float dist_sqr = diff_col * diff_col + diff_row * diff_row;
+    const float dist_to_booth = sqrtf(dist_sqr);
+    const float angle_to_booth = h_atan2(diff_row, diff_col, lf);
+    const float angle_diff = 0.0f - key_ori;
+    const float scale_diff = 10.0f / key_scl;
+    const float f_row = t->y, f_col = t->x, f_ori = h_angle_radians(t->angle), f_scl = t->size;
+    const float ori_diff = f_ori - key_ori;
+    const float scl_ratio = f_scl / key_scl;
+    const float dist = dist_to_booth * scl_ratio;
+    const float angle = angle_to_booth + ori_diff;
+    orc_booth b;
+    b.row = h_sin(angle, lf) * dist + f_row;
+    b.col = h_cos(angle, lf) * dist + f_col;
+    b.ori = f_ori + angle_diff;
+    b.scl = scale_diff * f_scl;
+    return b;
+}
+
+/* compatible_poll_booths_line_segment (:207-260) with its default thresholds; a = "training", b = "poll" */
+static int h_compatible(const orc_booth *a, const orc_booth *b, int lf)
+{
+    const float thr_trans = 30.0f / 43.0f, thr_scale = h_log(1.5f, lf), thr_ori = (float)(20.0f * ORC_PI / 180.0F);
+    const float a_ori = h_angle_radians(a->ori), b_ori = h_angle_radians(b->ori);
+    const float log_diff = fabsf(h_log(a->scl, lf) - h_log(b->scl, lf));
+    const float dc = b->col - a->col, dr = b->row - a->row;
+    const float dist = sqrtf(dc * dc + dr * dr);
+    float od = b_ori > a_ori ? b_ori - a_ori : a_ori - b_ori;
+    if (od > (2 * ORC_PI - od)) od = (float)(2 * ORC_PI - od);
+    return dist < thr_trans * a->scl && log_diff < thr_scale && od < thr_ori;
+}
+
+/* houghTransform(queryKeypoints, trainKeypoints (per image), matches, refx, refy) (:262-345).  train keypoints
+ * are one packed array with img_off[n_img + 1].  Entries with negative train / image index are skipped when
+ * the booths are built; the rejection loop then indexes `matches` by booth index, as upstream does.  Returns
+ * the vote count of the winning booth (0 when there is no valid match). */
+int orc_hough_transform(const orc_keypoint *qk, const orc_keypoint *tk, const int32_t *img_off, orc_dmatch *matches,
+                        int n, int refx, int refy, int libm_float)
+{
+    orc_booth *kg = (orc_booth *)malloc(sizeof(orc_booth) * (size_t)(n > 0 ? n : 1));
+    int m = 0;
+    for (int i = 0; i < n; i++) {
+        if (matches[i].train_idx < 0 || matches[i].img_idx < 0) continue;
+        kg[m++] = h_poll_booth(qk + matches[i].query_idx, tk + img_off[matches[i].img_idx] + matches[i].train_idx, refx,
+                               refy, libm_float);
+    }
+    int best = -1, best_count = 0;
+    for (int i = 0; i < m; i++) {
+        int c = 0;
+        for (int j = 0; j < m; j++) c += h_compatible(kg + i, kg + j, libm_float);
+        if (c > best_count) {
+            best = i;
+            best_count = c;
+        }
+    }
+    if (best >= 0)
+        for (int j = 0; j < m; j++)
+            if (!h_compatible(kg + best, kg + j, libm_float)) {
+                matches[j].img_idx = -1;
+                matches[j].query_idx = -1;
+                matches[j].train_idx = -1;
+            }
+    free(kg);
+    return best_count;
+}
+
+/* One query image of computeNextInterSliceCorrespondence (:1457-1558): m_train = best train match per query
+ * keypoint (first column of knnMatch k=3), m_bogus = best bogus match (k=1).  out receives the surviving
+ * matches (afterHoughMatches[i]); result = {n_matches, hough_count, best_image, best_count}. */
+void orc_correspond(const orc_keypoint *qk, int nq, const orc_dmatch *m_train, const orc_dmatch *m_bogus,
+                    const orc_keypoint *tk, const int32_t *img_off, int n_img, float bogus_ratio, int refx, int refy,
+                    orc_dmatch *out, int32_t *result, int libm_float)
+{
+    int m = 0;
+    for (int j = 0; j < nq; j++) {
+        const float ratio = m_train[j].distance / m_bogus[j].distance;
+        if (ratio > bogus_ratio) continue;
+        out[m++] = m_train[j];
+    }
+    const int hough = orc_hough_transform(qk, tk, img_off, out, m, refx, refy, libm_float);
+    int32_t *votes = (int32_t *)calloc((size_t)(n_img > 0 ? n_img : 1), sizeof(int32_t));
+    for (int j = 0; j < m; j++)
+        if (out[j].img_idx >= 0) votes[out[j].img_idx]++;
+    int best = -1, best_count = -1;
+    for (int j = 0; j < n_img; j++)
+        if (votes[j] > best_count) {
+            best_count = votes[j];
+            best = j;
+        }
+    free(votes);
+    result[0] = m;
+    result[1] = hough;
+    result[2] = best;
+    result[3] = best_count;
+}
+
+/* computeCentroid (:839-860): fp32 running sums of the row / column indices of non-zero mask pixels */
+void orc_mask_centroid(const uint8_t *mask, int H, int W, int pitch, int *x, int *y)
+{
+    float rowc = 0, colc = 0;
+    int count = 0;
+    for (int i = 0; i < H; i++)
+        for (int j = 0; j < W; j++)
+            if (mask[(size_t)i * pitch + j] > 0) {
+                rowc += i;
+                colc += j;
+                count += 1;
+            }
+    rowc /= count;
+    colc /= count;
+    *y = (int)rowc;
+    *x = (int)colc;
+}

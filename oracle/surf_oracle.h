@@ -103,6 +103,14 @@ long orc_detect_and_compute_batch(const uint8_t *imgs, int B, int H, int W,
 void orc_knn_match(const float *q, int nq, const float *t, int nt, int d, int k,
                    orc_dmatch *out, int n_threads);
 
+/* ---- "next" rows f2 / f3 (vtkSlicerSurfFeaturesLogic.cxx:73-345, :1434-1571, :839-860) ---- */
+int orc_hough_transform(const orc_keypoint *qk, const orc_keypoint *tk, const int32_t *img_off, orc_dmatch *matches,
+                        int n, int refx, int refy, int libm_float);
+void orc_correspond(const orc_keypoint *qk, int nq, const orc_dmatch *m_train, const orc_dmatch *m_bogus,
+                    const orc_keypoint *tk, const int32_t *img_off, int n_img, float bogus_ratio, int refx, int refy,
+                    orc_dmatch *out, int32_t *result, int libm_float);
+void orc_mask_centroid(const uint8_t *mask, int H, int W, int pitch, int *x, int *y);
+
 int orc_max_threads(void);
 
 #ifdef __cplusplus

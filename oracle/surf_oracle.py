@@ -74,6 +74,11 @@ def lib():
         L.orc_detect_and_compute_batch.restype = C.c_long
         L.orc_knn_match.argtypes = [vp, i32, vp, i32, i32, i32, vp, i32]
         L.orc_knn_match.restype = None
+        L.orc_hough_transform.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32]
+        L.orc_correspond.argtypes = [vp, i32, vp, vp, vp, vp, i32, C.c_float, i32, i32, vp, vp, i32]
+        L.orc_correspond.restype = None
+        L.orc_mask_centroid.argtypes = [vp, i32, i32, i32, C.POINTER(i32), C.POINTER(i32)]
+        L.orc_mask_centroid.restype = None
         L.orc_max_threads.argtypes = []
         L.orc_max_threads.restype = i32
         _lib = L
@@ -207,3 +212,52 @@ def knn_match(q, t, k=2, n_threads=0):
 
 def max_threads():
     return int(lib().orc_max_threads())
+
+
+def db_knn(query, train_list, k=2, n_threads=0):
+    """DescriptorMatcher::add(train_list) + knnMatch(query, k): exact L2 over the concatenation, then
+    (imgIdx, trainIdx within the image); ties -> lower image, lower row (BFMatcher's scan order)."""
+    sizes = np.array([len(t) for t in train_list], np.int64)
+    starts = np.concatenate([[0], np.cumsum(sizes)])
+    d = np.asarray(query).shape[1]
+    allt = np.concatenate([np.asarray(t, np.float32).reshape(-1, d) for t in train_list], axis=0) if len(train_list) else \
+        np.zeros((0, d), np.float32)
+    m = knn_match(query, allt, k, n_threads)
+    valid = m["trainIdx"] >= 0
+    img = np.searchsorted(starts, m["trainIdx"], side="right") - 1
+    m["imgIdx"] = np.where(valid, img, -1)
+    m["trainIdx"] = np.where(valid, m["trainIdx"] - starts[np.clip(img, 0, max(len(sizes) - 1, 0))], -1)
+    return m
+
+
+def hough_transform(query_kps, train_kps_list, matches, refx, refy, libm_float=False):
+    """houghTransform(): returns (vote count of the winning booth, matches with rejected entries set to -1)."""
+    qk = np.ascontiguousarray(query_kps, KEYPOINT_DTYPE)
+    off = np.concatenate([[0], np.cumsum([len(t) for t in train_kps_list])]).astype(np.int32)
+    tk = np.ascontiguousarray(np.concatenate([np.asarray(t, KEYPOINT_DTYPE) for t in train_kps_list])) \
+        if len(train_kps_list) else np.zeros(0, KEYPOINT_DTYPE)
+    m = np.ascontiguousarray(matches, DMATCH_DTYPE).copy()
+    c = lib().orc_hough_transform(_ptr(qk), _ptr(tk), _ptr(off), _ptr(m), len(m), int(refx), int(refy), int(libm_float))
+    return int(c), m
+
+
+def correspond(query_kps, query_desc, train_kps_list, train_desc_list, bogus_desc_list, refx, refy, bogus_ratio=0.95,
+               libm_float=False, n_threads=0):
+    """computeNextInterSliceCorrespondence for one query image.  Returns (after_hough matches, result[4])."""
+    qk = np.ascontiguousarray(query_kps, KEYPOINT_DTYPE)
+    mt = np.ascontiguousarray(db_knn(query_desc, train_desc_list, 3, n_threads)[:, 0])
+    mb = np.ascontiguousarray(db_knn(query_desc, bogus_desc_list, 1, n_threads)[:, 0])
+    off = np.concatenate([[0], np.cumsum([len(t) for t in train_kps_list])]).astype(np.int32)
+    tk = np.ascontiguousarray(np.concatenate([np.asarray(t, KEYPOINT_DTYPE) for t in train_kps_list]))
+    out = np.zeros(max(len(qk), 1), DMATCH_DTYPE)
+    res = np.zeros(4, np.int32)
+    lib().orc_correspond(_ptr(qk), len(qk), _ptr(mt), _ptr(mb), _ptr(tk), _ptr(off), len(train_kps_list),
+                         float(bogus_ratio), int(refx), int(refy), _ptr(out), _ptr(res), int(libm_float))
+    return out[:res[0]].copy(), res
+
+
+def mask_centroid(mask):
+    m = np.ascontiguousarray(mask, np.uint8)
+    x, y = C.c_int(0), C.c_int(0)
+    lib().orc_mask_centroid(_ptr(m), m.shape[0], m.shape[1], m.strides[0], C.byref(x), C.byref(y))
+    return x.value, y.value

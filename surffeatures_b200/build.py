@@ -21,6 +21,8 @@ UNITS = [
     ("surf_match.cu", []),
     ("surf_match_tc.cu", []),
     ("surf_engine.cu", []),
+    ("surf_db.cu", []),
+    ("surf_vote.cu", ["-fmad=false"]),
 ]
 
 

@@ -16,89 +16,11 @@
 
 #include <cuda.h>
 
-#include "surf_internal.h"
+#include "surf_engine_priv.h"
 
 using namespace surfb200;
 
-namespace {
-
-enum Ev { EV_START, EV_H2D, EV_INTEGRAL, EV_HESSIAN_NMS, EV_SORT, EV_DESCRIBE, EV_PACK, EV_END, EV_COUNT };
-
-struct Pending {
-    bool active = false;
-    int batch = 0;
-    bool want_desc = false;
-};
-
-}  // namespace
-
-struct surf_engine {
-    surf_params params{};
-    int device = 0;
-    int max_w = 0, max_h = 0, max_b = 0, cap = 0;
-    cudaStream_t stream = nullptr;
-    cudaStream_t copy_stream = nullptr;  // device->host result copies in asynchronous-output mode
-    cudaStream_t match_stream = nullptr; // surf_match_prev runs here, concurrently with the next batch's kernels
-    cudaEvent_t ev_batch_done = nullptr, ev_match_done = nullptr;
-    bool match_in_flight = false;
-    cudaEvent_t ev_copy_done = nullptr, ev_match_copy_done = nullptr, ev_ready = nullptr;
-    bool match_copies_in_flight = false;
-    int async_outputs = 0;
-    bool copies_in_flight = false;
-    cudaEvent_t ev[EV_COUNT]{};
-    bool ev_valid = false;
-
-    // workspace
-    uint8_t *d_img = nullptr;   size_t img_pitch = 0;
-    uint8_t *d_mask = nullptr;
-    uint32_t *d_sum = nullptr, *d_msum = nullptr, *d_bandsum = nullptr;
-    float *d_det = nullptr;     size_t det_words = 0;
-    surf_keypoint *d_kp_a = nullptr, *d_kp_b = nullptr, *d_out_kp = nullptr;
-    float *d_desc = nullptr, *d_out_desc = nullptr;  int desc_dim = 0;
-    uint8_t *d_patches = nullptr;
-    int *d_counts = nullptr, *d_ndel = nullptr, *d_off_in = nullptr, *d_off_out = nullptr, *d_misc = nullptr;
-    int *d_deleted = nullptr, *d_class_list = nullptr;
-    uint8_t *d_win_scratch = nullptr;
-    float2 *d_sincos = nullptr;
-    int *h_pin = nullptr;  // pinned: counts[B], ndel[B], off_out[B+1], misc[4]
-    surf_dmatch *d_match_part = nullptr;  size_t match_part_cap = 0;
-    void *d_match_io = nullptr;           size_t match_io_cap = 0;
-    int match_exact_only = 0;
-    int use_tma = 1;                 // fused TMA-staged Hessian + maxima kernel for octaves 0-1
-    CUtensorMap tmap[2];             // integral-image tile maps of octaves 0 and 1
-    TileOctave tile_oct[2];
-    int tmap_w = 0, tmap_h = 0, tmap_b = 0, tmap_layers = 0;
-    bool tmap_ok[2] = {false, false};
-    CUtensorMap imap[kNumClasses];   // 8-bit frame tiles for the descriptor kernels, one box size per class
-    bool imap_ok = false;
-    const void *imap_ptr = nullptr;  size_t imap_pitch = 0, imap_stride = 0;  int imap_w = 0, imap_h = 0, imap_b = 0;
-    int last_tc_ws = -1;  // workspace used by the last tensor-core match (for surf_match_redo_count)
-
-    // tensor-core matcher workspaces: [0] generic two-operand calls, [1] the frame stream ring
-    struct TcWs {
-        TcPool pool{};
-        int slots = 0, dim = 0;
-        TcCand *cand = nullptr;      size_t cand_cap = 0;
-        int *redo = nullptr;         size_t redo_cap = 0;
-        int *counters = nullptr;
-        TcSegment *segs = nullptr;   TcProblem *probs = nullptr;  int table_cap = 0;
-    } tc[2];
-    float *d_prev_desc = nullptr;    // last frame of the previous batch (fp32 rows) for exact rescoring
-    int *d_prev_off = nullptr;       // {0, n_prev}
-    int tc_prev_slot = 0;
-    bool stream_primed = false;
-    surf_dmatch *d_stream_matches = nullptr;
-    uint8_t *d_stream_good = nullptr;
-
-    surf_keypoint *sorted = nullptr;  // which of d_kp_a / d_kp_b holds the current keypoints
-    Pending pending;
-    surf_timings timings{};
-    int launches = 0;
-    long required = 0;
-    char err[512] = "";
-};
-
-namespace {
+namespace surfb200 {
 
 int fail(surf_engine *e, int code, const char *fmt, ...)
 {
@@ -111,13 +33,90 @@ int fail(surf_engine *e, int code, const char *fmt, ...)
     return code;
 }
 
-#define CU(e, call)                                                                                          \
-    do {                                                                                                     \
-        cudaError_t _r = (call);                                                                             \
-        if (_r != cudaSuccess)                                                                               \
-            return fail((e), SURF_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_r), __FILE__, \
-                        __LINE__);                                                                           \
-    } while (0)
+int ensure_device(surf_engine *e)
+{
+    CU(e, cudaSetDevice(e->device));
+    return SURF_OK;
+}
+
+// (Re)allocates the prepared-descriptor pool of a tensor-core workspace.
+int tc_reserve(surf_engine *e, surf_engine::TcWs &w, int slots, int slot_rows, int dim)
+{
+    if (w.pool.hi && slots <= w.slots && slot_rows <= w.pool.slot_rows && dim <= w.dim) {
+        return SURF_OK;
+    }
+    CU(e, cudaStreamSynchronize(e->stream));
+    cudaFree(w.pool.hi); cudaFree(w.pool.lo); cudaFree(w.pool.norm); cudaFree(w.pool.max_norm); cudaFree(w.pool.count);
+    w.pool = TcPool();
+    if (slots < w.slots) slots = w.slots;
+    if (slot_rows < w.pool.slot_rows) slot_rows = w.pool.slot_rows;
+    if (dim < w.dim) dim = w.dim;
+    const size_t rows = (size_t)slots * slot_rows;
+    CU(e, cudaMalloc(&w.pool.hi, rows * dim * sizeof(uint16_t)));
+    CU(e, cudaMalloc(&w.pool.lo, rows * dim * sizeof(uint16_t)));
+    CU(e, cudaMalloc(&w.pool.norm, rows * sizeof(float)));
+    CU(e, cudaMalloc(&w.pool.max_norm, slots * sizeof(float)));
+    CU(e, cudaMalloc(&w.pool.count, slots * sizeof(int)));
+    CU(e, cudaMemset(w.pool.count, 0, slots * sizeof(int)));
+    CU(e, cudaMemset(w.pool.max_norm, 0, slots * sizeof(float)));
+    w.pool.slot_rows = slot_rows;
+    w.slots = slots;
+    w.dim = dim;
+    return SURF_OK;
+}
+
+int tc_reserve_work(surf_engine *e, surf_engine::TcWs &w, int n_probs, int splits, int max_q, int n_segs)
+{
+    const size_t need = (size_t)n_probs * splits * 2 * max_q;  // two column halves per train split
+    if (need > w.cand_cap) {
+        CU(e, cudaStreamSynchronize(e->stream));
+        cudaFree(w.cand);
+        w.cand = nullptr;
+        w.cand_cap = 0;
+        CU(e, cudaMalloc(&w.cand, need * sizeof(TcCand)));
+        w.cand_cap = need;
+    }
+    const size_t need_redo = (size_t)n_probs * max_q;
+    if (need_redo > w.redo_cap) {
+        CU(e, cudaStreamSynchronize(e->stream));
+        cudaFree(w.redo);
+        w.redo = nullptr;
+        w.redo_cap = 0;
+        CU(e, cudaMalloc(&w.redo, need_redo * 2 * sizeof(int)));
+        w.redo_cap = need_redo;
+    }
+    if (!w.counters) CU(e, cudaMalloc(&w.counters, 4 * sizeof(int)));
+    const int tab = n_probs > n_segs ? n_probs : n_segs;
+    if (tab > w.table_cap) {
+        CU(e, cudaStreamSynchronize(e->stream));
+        cudaFree(w.segs);
+        cudaFree(w.probs);
+        w.segs = nullptr;
+        w.probs = nullptr;
+        CU(e, cudaMalloc(&w.segs, tab * sizeof(TcSegment)));
+        CU(e, cudaMalloc(&w.probs, tab * sizeof(TcProblem)));
+        w.table_cap = tab;
+    }
+    return SURF_OK;
+}
+
+int reserve_match_part(surf_engine *e, int n_query, int n_train, int k)
+{
+    const size_t need_part = match_scratch_records(n_query, n_train > 0 ? n_train : 1, k);
+    if (need_part > e->match_part_cap) {
+        CU(e, cudaStreamSynchronize(e->stream));
+        cudaFree(e->d_match_part);
+        e->d_match_part = nullptr;
+        e->match_part_cap = 0;
+        CU(e, cudaMalloc(&e->d_match_part, need_part * sizeof(surf_dmatch)));
+        e->match_part_cap = need_part;
+    }
+    return SURF_OK;
+}
+
+}  // namespace surfb200
+
+namespace {
 
 inline int cv_round(double v) { return (int)lrint(v); }
 
@@ -591,12 +590,6 @@ void collect_timings(surf_engine *e)
     t.launches = e->launches;
 }
 
-int ensure_device(surf_engine *e)
-{
-    CU(e, cudaSetDevice(e->device));
-    return SURF_OK;
-}
-
 }  // namespace
 
 extern "C" {
@@ -1019,67 +1012,6 @@ int surf_raw_keypoints(surf_engine *e, const uint8_t *image, int width, int heig
 
 // ---- stage 5 ----
 
-// (Re)allocates the prepared-descriptor pool of a tensor-core workspace.
-static int tc_reserve(surf_engine *e, surf_engine::TcWs &w, int slots, int slot_rows, int dim)
-{
-    if (w.pool.hi && slots <= w.slots && slot_rows <= w.pool.slot_rows && dim <= w.dim) {
-        return SURF_OK;
-    }
-    CU(e, cudaStreamSynchronize(e->stream));
-    cudaFree(w.pool.hi); cudaFree(w.pool.lo); cudaFree(w.pool.norm); cudaFree(w.pool.max_norm); cudaFree(w.pool.count);
-    w.pool = TcPool();
-    if (slots < w.slots) slots = w.slots;
-    if (slot_rows < w.pool.slot_rows) slot_rows = w.pool.slot_rows;
-    if (dim < w.dim) dim = w.dim;
-    const size_t rows = (size_t)slots * slot_rows;
-    CU(e, cudaMalloc(&w.pool.hi, rows * dim * sizeof(uint16_t)));
-    CU(e, cudaMalloc(&w.pool.lo, rows * dim * sizeof(uint16_t)));
-    CU(e, cudaMalloc(&w.pool.norm, rows * sizeof(float)));
-    CU(e, cudaMalloc(&w.pool.max_norm, slots * sizeof(float)));
-    CU(e, cudaMalloc(&w.pool.count, slots * sizeof(int)));
-    CU(e, cudaMemset(w.pool.count, 0, slots * sizeof(int)));
-    CU(e, cudaMemset(w.pool.max_norm, 0, slots * sizeof(float)));
-    w.pool.slot_rows = slot_rows;
-    w.slots = slots;
-    w.dim = dim;
-    return SURF_OK;
-}
-
-static int tc_reserve_work(surf_engine *e, surf_engine::TcWs &w, int n_probs, int splits, int max_q, int n_segs)
-{
-    const size_t need = (size_t)n_probs * splits * 2 * max_q;  // two column halves per train split
-    if (need > w.cand_cap) {
-        CU(e, cudaStreamSynchronize(e->stream));
-        cudaFree(w.cand);
-        w.cand = nullptr;
-        w.cand_cap = 0;
-        CU(e, cudaMalloc(&w.cand, need * sizeof(TcCand)));
-        w.cand_cap = need;
-    }
-    const size_t need_redo = (size_t)n_probs * max_q;
-    if (need_redo > w.redo_cap) {
-        CU(e, cudaStreamSynchronize(e->stream));
-        cudaFree(w.redo);
-        w.redo = nullptr;
-        w.redo_cap = 0;
-        CU(e, cudaMalloc(&w.redo, need_redo * 2 * sizeof(int)));
-        w.redo_cap = need_redo;
-    }
-    if (!w.counters) CU(e, cudaMalloc(&w.counters, 4 * sizeof(int)));
-    const int tab = n_probs > n_segs ? n_probs : n_segs;
-    if (tab > w.table_cap) {
-        CU(e, cudaStreamSynchronize(e->stream));
-        cudaFree(w.segs);
-        cudaFree(w.probs);
-        w.segs = nullptr;
-        w.probs = nullptr;
-        CU(e, cudaMalloc(&w.segs, tab * sizeof(TcSegment)));
-        CU(e, cudaMalloc(&w.probs, tab * sizeof(TcProblem)));
-        w.table_cap = tab;
-    }
-    return SURF_OK;
-}
-
 static int match_common(surf_engine *e, const float *query, int n_query, const float *train, int n_train, int dim, int k,
                         float ratio, surf_dmatch *out, uint8_t *good, int mem)
 {
@@ -1120,14 +1052,7 @@ static int match_common(surf_engine *e, const float *query, int n_query, const f
         dt = t2;
     }
     if (e->match_exact_only || n_train == 0) {
-        const size_t need_part = match_scratch_records(n_query, n_train > 0 ? n_train : 1, k);
-        if (need_part > e->match_part_cap) {
-            cudaFree(e->d_match_part);
-            e->d_match_part = nullptr;
-            e->match_part_cap = 0;
-            CU(e, cudaMalloc(&e->d_match_part, need_part * sizeof(surf_dmatch)));
-            e->match_part_cap = need_part;
-        }
+        if ((rc = reserve_match_part(e, n_query, n_train, k))) return rc;
         launch_match_knn(dq, n_query, dt, n_train, dim, k, dout, 0, e->d_match_part, e->stream, &e->launches);
         if (good) launch_ratio_test(dout, n_query, ratio, dgood, e->stream, &e->launches);
     } else {

@@ -1,0 +1,110 @@
+// surf_engine_priv.h -- the engine object and the helpers shared by the host-side translation units
+// (surf_engine.cu: stages 1-5 behind the C ABI; surf_db.cu: descriptor database, correspondence votes).
+// Private to libsurf_b200.so; the public boundary is include/surf_b200.h.
+#pragma once
+
+#include <cstdarg>
+#include <cstdio>
+#include <vector>
+
+#include <cuda.h>
+
+#include "surf_internal.h"
+
+using namespace surfb200;  // private header of the library's own translation units
+
+enum Ev { EV_START, EV_H2D, EV_INTEGRAL, EV_HESSIAN_NMS, EV_SORT, EV_DESCRIBE, EV_PACK, EV_END, EV_COUNT };
+
+struct Pending {
+    bool active = false;
+    int batch = 0;
+    bool want_desc = false;
+};
+
+struct surf_engine {
+    surf_params params{};
+    int device = 0;
+    int max_w = 0, max_h = 0, max_b = 0, cap = 0;
+    cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;  // device->host result copies in asynchronous-output mode
+    cudaStream_t match_stream = nullptr; // surf_match_prev runs here, concurrently with the next batch's kernels
+    cudaEvent_t ev_batch_done = nullptr, ev_match_done = nullptr;
+    bool match_in_flight = false;
+    cudaEvent_t ev_copy_done = nullptr, ev_match_copy_done = nullptr, ev_ready = nullptr;
+    bool match_copies_in_flight = false;
+    int async_outputs = 0;
+    bool copies_in_flight = false;
+    cudaEvent_t ev[EV_COUNT]{};
+    bool ev_valid = false;
+
+    // workspace
+    uint8_t *d_img = nullptr;   size_t img_pitch = 0;
+    uint8_t *d_mask = nullptr;
+    uint32_t *d_sum = nullptr, *d_msum = nullptr, *d_bandsum = nullptr;
+    float *d_det = nullptr;     size_t det_words = 0;
+    surf_keypoint *d_kp_a = nullptr, *d_kp_b = nullptr, *d_out_kp = nullptr;
+    float *d_desc = nullptr, *d_out_desc = nullptr;  int desc_dim = 0;
+    uint8_t *d_patches = nullptr;
+    int *d_counts = nullptr, *d_ndel = nullptr, *d_off_in = nullptr, *d_off_out = nullptr, *d_misc = nullptr;
+    int *d_deleted = nullptr, *d_class_list = nullptr;
+    uint8_t *d_win_scratch = nullptr;
+    float2 *d_sincos = nullptr;
+    int *h_pin = nullptr;  // pinned: counts[B], ndel[B], off_out[B+1], misc[4]
+    surf_dmatch *d_match_part = nullptr;  size_t match_part_cap = 0;
+    void *d_match_io = nullptr;           size_t match_io_cap = 0;
+    int match_exact_only = 0;
+    int use_tma = 1;                 // fused TMA-staged Hessian + maxima kernel for octaves 0-1
+    CUtensorMap tmap[2];             // integral-image tile maps of octaves 0 and 1
+    TileOctave tile_oct[2];
+    int tmap_w = 0, tmap_h = 0, tmap_b = 0, tmap_layers = 0;
+    bool tmap_ok[2] = {false, false};
+    CUtensorMap imap[kNumClasses];   // 8-bit frame tiles for the descriptor kernels, one box size per class
+    bool imap_ok = false;
+    const void *imap_ptr = nullptr;  size_t imap_pitch = 0, imap_stride = 0;  int imap_w = 0, imap_h = 0, imap_b = 0;
+    int last_tc_ws = -1;  // workspace used by the last tensor-core match (for surf_match_redo_count)
+
+    // tensor-core matcher workspaces: [0] generic two-operand calls, [1] the frame stream ring,
+    // [2] queries against a descriptor database (surf_db.cu)
+    struct TcWs {
+        TcPool pool{};
+        int slots = 0, dim = 0;
+        TcCand *cand = nullptr;      size_t cand_cap = 0;
+        int *redo = nullptr;         size_t redo_cap = 0;
+        int *counters = nullptr;
+        TcSegment *segs = nullptr;   TcProblem *probs = nullptr;  int table_cap = 0;
+    } tc[3];
+    float *d_prev_desc = nullptr;    // last frame of the previous batch (fp32 rows) for exact rescoring
+    int *d_prev_off = nullptr;       // {0, n_prev}
+    int tc_prev_slot = 0;
+    bool stream_primed = false;
+    surf_dmatch *d_stream_matches = nullptr;
+    uint8_t *d_stream_good = nullptr;
+
+    surf_keypoint *sorted = nullptr;  // which of d_kp_a / d_kp_b holds the current keypoints
+    Pending pending;
+    surf_timings timings{};
+    int launches = 0;
+    long required = 0;
+    char err[512] = "";
+};
+
+
+namespace surfb200 {
+
+int fail(surf_engine *e, int code, const char *fmt, ...);
+int ensure_device(surf_engine *e);
+// (re)allocate the prepared-descriptor pool / the candidate, redo and table buffers of a matcher workspace
+int tc_reserve(surf_engine *e, surf_engine::TcWs &w, int slots, int slot_rows, int dim);
+int tc_reserve_work(surf_engine *e, surf_engine::TcWs &w, int n_probs, int splits, int max_q, int n_segs);
+// scratch of the exact CUDA-core matcher (partial top-k records)
+int reserve_match_part(surf_engine *e, int n_query, int n_train, int k);
+
+}  // namespace surfb200
+
+#define CU(e, call)                                                                                          \
+    do {                                                                                                     \
+        cudaError_t _r = (call);                                                                             \
+        if (_r != cudaSuccess)                                                                               \
+            return surfb200::fail((e), SURF_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_r), \
+                                  __FILE__, __LINE__);                                                       \
+    } while (0)

@@ -160,12 +160,14 @@ struct TcPool {
     int slot_rows;
 };
 
-// Rows [off[0], off[1]) of `src` (or [row0, row0 + n) when off is null) go to `slot`.
+// Rows [off[0], off[1]) of `src` (or [row0, row0 + n) when off is null) go to `slot`, starting at row
+// dst_row0 of the slot (append to a database slot); the slot then holds dst_row0 + n live rows.
 struct TcSegment {
     const float *src;
     const int *off;
     int row0, n;
     int slot;
+    int dst_row0;
 };
 
 // One knnMatch: queries = slot q_slot, train = slot t_slot; fp32 rows for the exact rescoring at
@@ -178,8 +180,9 @@ struct TcProblem {
 };
 
 struct TcMatchArgs {
-    TcPool pool;
-    const TcSegment *segs;  // device
+    TcPool pool;            // query slots (and train slots when tpool.hi is null)
+    TcPool tpool;           // train slots living in another pool (a descriptor database), else zeroed
+    const TcSegment *segs;  // device; rows to prepare into `pool` before matching (n_segs may be 0)
     int n_segs;
     const TcProblem *probs;  // device
     int n_probs;
@@ -196,6 +199,11 @@ struct TcMatchArgs {
 
 size_t tc_candidates_smem(int dim);
 void launch_tc_match(const TcMatchArgs &a, cudaStream_t st, int *launches);
+// prepares the rows of `segs` (device table) into `pool` without matching (database append)
+void launch_tc_prep(const TcPool &pool, const TcSegment *segs, int n_segs, int max_rows, int dim, bool reset_norms,
+                    cudaStream_t st, int *launches);
+// rewrites global train rows of a multi-image database as (img_idx, row within the image): img_off[n_img + 1]
+void launch_db_localize(surf_dmatch *m, long n, const int *img_off, int n_img, cudaStream_t st, int *launches);
 // Builds the segment / problem tables of the frame-stream matcher on the device: frame i of the batch goes
 // to ring slot (prev_slot + 1 + i) % slots and is matched against the frame before it.
 void launch_tc_stream_tables(TcSegment *segs, TcProblem *probs, int B, int slots, int prev_slot, const float *desc,
@@ -211,5 +219,27 @@ void launch_match_knn(const float *q, int nq, const float *t, int nt, int dim, i
 void launch_ratio_test(const surf_dmatch *m, int nq, float ratio, uint8_t *good, cudaStream_t st, int *launches);
 void launch_merge_topk(const surf_dmatch *in, int n_ranks, int nq, int k, surf_dmatch *out, cudaStream_t st,
                        int *launches);
+
+// ---- inter-slice correspondence votes (surf_vote.cu) ----
+struct VoteArgs {
+    const surf_dmatch *m_train;   // [rows][3] knnMatch(k=3) against the train database (image-local indices)
+    const surf_dmatch *m_bogus;   // [rows][1] knnMatch(k=1) against the bogus database
+    const surf_keypoint *qk;      // [rows] query keypoints, all query images packed
+    const surf_keypoint *tk;      // train database keypoints
+    const int *t_img_off;         // train database image offsets (device)
+    const int *q_off;             // [n_query_images + 1] (device)
+    int n_query_images, n_train_images, max_rows_per_image;
+    float bogus_ratio;
+    int ref_x, ref_y;
+    float thr_scale, thr_ori;     // (float)log(1.5f), (float)(20 pi / 180)
+    surf_dmatch *out;             // [rows] surviving matches of image i from q_off[i]
+    float4 *booth;                // [rows]
+    float *booth_thr;             // [rows]
+    int *n_matches;               // [n_query_images]
+    unsigned long long *keys;     // [n_query_images]
+    int *votes;                   // [n_query_images][n_train_images]
+    surf_vote_result *results;    // [n_query_images]
+};
+void launch_vote(const VoteArgs &a, cudaStream_t st, int *launches);
 
 }  // namespace surfb200

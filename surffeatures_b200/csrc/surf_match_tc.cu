@@ -146,13 +146,15 @@ __global__ void __launch_bounds__(256) k_tc_prep(const TcSegment *__restrict__ s
     if (seg >= n_segs) return;
     const TcSegment sg = segs[seg];
     const float *src = sg.src;
-    const int n = min(sg.off ? sg.off[1] - sg.off[0] : sg.n, pool.slot_rows);
+    const int base = sg.dst_row0;  // live rows already in the slot (append); 0 for a fresh slot
+    const int n = min(sg.off ? sg.off[1] - sg.off[0] : sg.n, pool.slot_rows - base);
     const int src_row0 = sg.off ? sg.off[0] : sg.row0;
-    const int npad = min((n + kTN - 1) / kTN * kTN, pool.slot_rows);
+    // rows base + [0, npad) are written; base + npad is the next multiple of 256 (padding rows get |t|^2 = inf)
+    const int npad = min((base + n + kTN - 1) / kTN * kTN, pool.slot_rows) - base;
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     const int r = t / G, g = t - r * G;
-    if (t == 0) pool.count[sg.slot] = n;
-    if (r >= npad) return;  // npad is a multiple of 256 rows: whole blocks leave together
+    if (t == 0) pool.count[sg.slot] = base + n;
+    if (r >= npad) return;  // G divides the warp: the lanes of a row leave together
     float v[8];
     if (r < n) {
         const float4 *p = reinterpret_cast<const float4 *>(src + (size_t)(src_row0 + r) * D + g * 8);
@@ -174,14 +176,17 @@ __global__ void __launch_bounds__(256) k_tc_prep(const TcSegment *__restrict__ s
         nrm = fmaf(v[k], v[k], nrm);
         nrm = fmaf(v[k + 1], v[k + 1], nrm);
     }
+    // the G lanes of a row are consecutive lanes of one warp (G = 8 or 16)
+    const unsigned gm = (G == 32 ? 0xffffffffu : ((1u << G) - 1u) << ((threadIdx.x & 31) / G * G));
 #pragma unroll
-    for (int d = G / 2; d > 0; d >>= 1) nrm += __shfl_xor_sync(0xffffffffu, nrm, d);
+    for (int d = G / 2; d > 0; d >>= 1) nrm += __shfl_xor_sync(gm, nrm, d);
     const size_t slot_base = (size_t)sg.slot * pool.slot_rows;
-    const size_t e = (slot_base + (size_t)(r & ~7)) * D + (size_t)g * 64 + (size_t)(r & 7) * 8;
+    const int R = base + r;
+    const size_t e = (slot_base + (size_t)(R & ~7)) * D + (size_t)g * 64 + (size_t)(R & 7) * 8;
     *reinterpret_cast<uint4 *>(pool.hi + e) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
     *reinterpret_cast<uint4 *>(pool.lo + e) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
     if (g == 0) {
-        pool.norm[slot_base + r] = r < n ? nrm : INFINITY;
+        pool.norm[slot_base + R] = r < n ? nrm : INFINITY;
         if (r < n) atomicMax(reinterpret_cast<int *>(pool.max_norm + sg.slot), __float_as_int(nrm));
     }
 }
@@ -231,8 +236,8 @@ __device__ __forceinline__ void cand_replace_worst(Cand<KC> &c, float dist, int 
 }
 
 template <int D, int KC>
-__global__ void __launch_bounds__(256) k_tc_candidates(TcPool pool, const TcProblem *__restrict__ probs, int n_probs,
-                                                       int mt_per_prob, int n_splits, int cand_stride,
+__global__ void __launch_bounds__(256) k_tc_candidates(TcPool pool, TcPool tpool, const TcProblem *__restrict__ probs,
+                                                       int n_probs, int mt_per_prob, int n_splits, int cand_stride,
                                                        TcCand *__restrict__ cand_out, int *__restrict__ work_head)
 {
     constexpr int KSTEPS = D / 16;
@@ -277,7 +282,7 @@ __global__ void __launch_bounds__(256) k_tc_candidates(TcPool pool, const TcProb
         const int rem = item - p * (mt_per_prob * n_splits);
         const int mt = rem / n_splits, split = rem - mt * n_splits;
         const TcProblem pr = probs[p];
-        const int nq = pool.count[pr.q_slot], nt = pool.count[pr.t_slot];
+        const int nq = pool.count[pr.q_slot], nt = tpool.count[pr.t_slot];
         const int q0 = mt * kTM;
         if (q0 >= nq) continue;
         // train tiles of this split
@@ -295,13 +300,13 @@ __global__ void __launch_bounds__(256) k_tc_candidates(TcPool pool, const TcProb
         best.wslot = 0;
         float thr = INFINITY;
         *my_thr = INFINITY;  // read by the partner only after the tile loop's first __syncthreads
-        const size_t trow_base = (size_t)pr.t_slot * pool.slot_rows;
+        const size_t trow_base = (size_t)pr.t_slot * tpool.slot_rows;
         // operands arrive by TMA bulk copies (contiguous runs of core matrices), counted on bar_ld
         auto load_train_tile = [&](int tile, int stage) {
             const size_t row0 = trow_base + (size_t)tile * kTN;
-            bulk_g2s(smem_u32(sB_hi), pool.hi + row0 * D, B_BYTES, bar_ld);
-            bulk_g2s(smem_u32(sB_lo), pool.lo + row0 * D, B_BYTES, bar_ld);
-            bulk_g2s(smem_u32(sTn + stage * kTN), pool.norm + row0, kTN * sizeof(float), bar_ld);
+            bulk_g2s(smem_u32(sB_hi), tpool.hi + row0 * D, B_BYTES, bar_ld);
+            bulk_g2s(smem_u32(sB_lo), tpool.lo + row0 * D, B_BYTES, bar_ld);
+            bulk_g2s(smem_u32(sTn + stage * kTN), tpool.norm + row0, kTN * sizeof(float), bar_ld);
         };
         if (tid == 0 && tile0 < tile1) {
             const size_t e0 = ((size_t)pr.q_slot * pool.slot_rows + q0) * D;
@@ -398,14 +403,14 @@ __global__ void __launch_bounds__(256) k_tc_candidates(TcPool pool, const TcProb
 // K5c: exact rescoring of the candidates, top-k, margin test.  kCand lanes per query.
 // ------------------------------------------------------------------------------------------------
 template <int D>
-__global__ void __launch_bounds__(256) k_tc_rescore(TcPool pool, const TcProblem *__restrict__ probs, int n_splits,
+__global__ void __launch_bounds__(256) k_tc_rescore(TcPool pool, TcPool tpool, const TcProblem *__restrict__ probs, int n_splits,
                                                     int cand_stride, const TcCand *__restrict__ cand, int k, float ratio,
                                                     surf_dmatch *__restrict__ out, uint8_t *__restrict__ good,
                                                     int *__restrict__ redo_list, int *__restrict__ redo_count)
 {
     const int p = blockIdx.y;
     const TcProblem pr = probs[p];
-    const int nq = pool.count[pr.q_slot], nt = pool.count[pr.t_slot];
+    const int nq = pool.count[pr.q_slot], nt = tpool.count[pr.t_slot];
     const int gq = (blockIdx.x * blockDim.x + threadIdx.x) / kCand;
     const int lane_c = threadIdx.x % kCand;
     if (gq >= nq) return;  // kCand divides the warp: a query's lanes leave together
@@ -465,7 +470,7 @@ __global__ void __launch_bounds__(256) k_tc_rescore(TcPool pool, const TcProblem
     // hence exact squared distance >= |q|^2 + worst_kept - eps.  If that clears the k-th best exact
     // distance, the top-k is proven; otherwise the exact kernel redoes this query.
     const float qn = pool.norm[(size_t)pr.q_slot * pool.slot_rows + gq];
-    const float tn_max = pool.max_norm[pr.t_slot];
+    const float tn_max = tpool.max_norm[pr.t_slot];
     const float eps = 1.0e-4f * sqrtf(qn * tn_max) + 4.0e-6f * (qn + tn_max) + 1e-30f;
     const int kk = min(k, nt);
     bool proven = true;
@@ -491,7 +496,7 @@ __global__ void __launch_bounds__(256) k_tc_rescore(TcPool pool, const TcProblem
 // top-4, then a merge across the CTA.  A single query is latency-critical: a lone warp scanning thousands of
 // rows would take longer than the whole tensor-core pass.
 template <int D>
-__global__ void __launch_bounds__(256) k_tc_redo(TcPool pool, const TcProblem *__restrict__ probs, int k, float ratio,
+__global__ void __launch_bounds__(256) k_tc_redo(TcPool tpool, const TcProblem *__restrict__ probs, int k, float ratio,
                                                  surf_dmatch *__restrict__ out, uint8_t *__restrict__ good,
                                                  const int *__restrict__ redo_list, const int *__restrict__ redo_count)
 {
@@ -503,7 +508,7 @@ __global__ void __launch_bounds__(256) k_tc_redo(TcPool pool, const TcProblem *_
     for (int w = blockIdx.x; w < n; w += gridDim.x) {
         const int p = redo_list[2 * w], gq = redo_list[2 * w + 1];
         const TcProblem pr = probs[p];
-        const int nt = pool.count[pr.t_slot];
+        const int nt = tpool.count[pr.t_slot];
         const int q_row0 = pr.q_off ? pr.q_off[0] : pr.q_row0;
         const int t_row0 = pr.t_off ? pr.t_off[0] : pr.t_row0;
         const int out_row0 = pr.out_off ? pr.out_off[0] : pr.out_row0;
@@ -591,15 +596,25 @@ __global__ void __launch_bounds__(256) k_tc_redo(TcPool pool, const TcProblem *_
 // ------------------------------------------------------------------------------------------------
 size_t tc_candidates_smem(int dim) { return (size_t)(2 * kTM + 2 * kTN) * dim * 2 + 2 * kTN * sizeof(float) + 1024; }
 
+void launch_tc_prep(const TcPool &pool, const TcSegment *segs, int n_segs, int max_rows, int dim, bool reset_norms,
+                    cudaStream_t st, int *launches)
+{
+    if (n_segs <= 0) return;
+    if (reset_norms) k_tc_reset<<<(n_segs + 127) / 128, 128, 0, st>>>(pool, segs, n_segs);
+    const int G = dim / 8;
+    // every row of a segment plus its padding up to the next multiple of 256
+    dim3 gprep(((size_t)(max_rows + 2 * kTN) * G + 255) / 256, n_segs);
+    if (dim == 64) k_tc_prep<64><<<gprep, 256, 0, st>>>(segs, n_segs, pool);
+    else k_tc_prep<128><<<gprep, 256, 0, st>>>(segs, n_segs, pool);
+    if (launches) *launches += reset_norms ? 2 : 1;
+}
+
 void launch_tc_match(const TcMatchArgs &a, cudaStream_t st, int *launches)
 {
     const int D = a.dim;
+    const TcPool &tp = a.tpool.hi ? a.tpool : a.pool;
     // ---- prep every segment (rows -> bf16 hi/lo tiles + norms) ----
-    k_tc_reset<<<(a.n_segs + 127) / 128, 128, 0, st>>>(a.pool, a.segs, a.n_segs);
-    const int G = D / 8;
-    dim3 gprep(((size_t)a.pool.slot_rows * G + 255) / 256, a.n_segs);
-    if (D == 64) k_tc_prep<64><<<gprep, 256, 0, st>>>(a.segs, a.n_segs, a.pool);
-    else k_tc_prep<128><<<gprep, 256, 0, st>>>(a.segs, a.n_segs, a.pool);
+    launch_tc_prep(a.pool, a.segs, a.n_segs, a.pool.slot_rows, D, true, st, nullptr);
     launch_zero(a.counters, 2, st, nullptr);  // [0] work head, [1] redo count
 
     static int grids[64][2] = {};
@@ -619,9 +634,9 @@ void launch_tc_match(const TcMatchArgs &a, cudaStream_t st, int *launches)
     }
     const int mt_per_prob = a.max_q_rows / kTM;
     const bool small_k = a.k <= 2;
-#define SURF_TC_LAUNCH(DD, KK)                                                                                  \
-    k_tc_candidates<DD, KK><<<grid, 256, smem, st>>>(a.pool, a.probs, a.n_probs, mt_per_prob, a.n_splits, a.max_q_rows, \
-                                                     a.cand, a.counters)
+#define SURF_TC_LAUNCH(DD, KK)                                                                                      \
+    k_tc_candidates<DD, KK><<<grid, 256, smem, st>>>(a.pool, tp, a.probs, a.n_probs, mt_per_prob, a.n_splits,       \
+                                                     a.max_q_rows, a.cand, a.counters)
     if (D == 64) {
         if (small_k) SURF_TC_LAUNCH(64, 4); else SURF_TC_LAUNCH(64, 8);
     } else {
@@ -632,15 +647,42 @@ void launch_tc_match(const TcMatchArgs &a, cudaStream_t st, int *launches)
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (D == 64) {
-        k_tc_rescore<64><<<gres, 256, 0, st>>>(a.pool, a.probs, a.n_splits, a.max_q_rows, a.cand, a.k, a.ratio, a.out, a.good,
-                                               a.redo_list, a.counters + 1);
-        k_tc_redo<64><<<sms * 2, 256, 0, st>>>(a.pool, a.probs, a.k, a.ratio, a.out, a.good, a.redo_list, a.counters + 1);
+        k_tc_rescore<64><<<gres, 256, 0, st>>>(a.pool, tp, a.probs, a.n_splits, a.max_q_rows, a.cand, a.k, a.ratio, a.out,
+                                               a.good, a.redo_list, a.counters + 1);
+        k_tc_redo<64><<<sms * 2, 256, 0, st>>>(tp, a.probs, a.k, a.ratio, a.out, a.good, a.redo_list, a.counters + 1);
     } else {
-        k_tc_rescore<128><<<gres, 256, 0, st>>>(a.pool, a.probs, a.n_splits, a.max_q_rows, a.cand, a.k, a.ratio, a.out,
+        k_tc_rescore<128><<<gres, 256, 0, st>>>(a.pool, tp, a.probs, a.n_splits, a.max_q_rows, a.cand, a.k, a.ratio, a.out,
                                                 a.good, a.redo_list, a.counters + 1);
-        k_tc_redo<128><<<sms * 2, 256, 0, st>>>(a.pool, a.probs, a.k, a.ratio, a.out, a.good, a.redo_list, a.counters + 1);
+        k_tc_redo<128><<<sms * 2, 256, 0, st>>>(tp, a.probs, a.k, a.ratio, a.out, a.good, a.redo_list, a.counters + 1);
     }
     *launches += 6;
+}
+
+// Multi-image database: global train row -> (image, row within the image).  img_off is ascending with
+// img_off[0] = 0; rows of image i are [img_off[i], img_off[i + 1]).
+__global__ void k_db_localize(surf_dmatch *__restrict__ m, long n, const int *__restrict__ img_off, int n_img)
+{
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int g = m[i].train_idx;
+    if (g < 0) {
+        m[i].img_idx = -1;
+        return;
+    }
+    int lo = 0, hi = n_img;  // last image whose first row is <= g
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (img_off[mid] <= g) lo = mid; else hi = mid;
+    }
+    m[i].img_idx = lo;
+    m[i].train_idx = g - img_off[lo];
+}
+
+void launch_db_localize(surf_dmatch *m, long n, const int *img_off, int n_img, cudaStream_t st, int *launches)
+{
+    if (n <= 0) return;
+    k_db_localize<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(m, n, img_off, n_img);
+    if (launches) (*launches)++;
 }
 
 __global__ void k_tc_stream_tables(TcSegment *segs, TcProblem *probs, int B, int slots, int prev_slot, const float *desc,
@@ -655,6 +697,7 @@ __global__ void k_tc_stream_tables(TcSegment *segs, TcProblem *probs, int B, int
     sg.row0 = 0;
     sg.n = 0;
     sg.slot = slot;
+    sg.dst_row0 = 0;
     segs[i] = sg;
     TcProblem p;
     p.q_slot = slot;

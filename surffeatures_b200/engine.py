@@ -36,7 +36,8 @@ ABI_SYMBOLS = [
     "surf_integral", "surf_hessian_layer", "surf_raw_keypoints", "surf_describe_keypoints", "surf_match_knn",
     "surf_match_ratio", "surf_merge_topk", "surf_version", "surf_match_prev", "surf_stream_reset",
     "surf_device_matches", "surf_set_match_mode", "surf_match_redo_count", "surf_set_async_outputs",
-    "surf_wait_outputs",
+    "surf_wait_outputs", "surf_db_create", "surf_db_destroy", "surf_db_clear", "surf_db_add", "surf_db_size",
+    "surf_db_knn", "surf_correspond",
 ]
 
 
@@ -58,6 +59,13 @@ class Timings(C.Structure):
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
 
+
+class VoteParams(C.Structure):
+    _fields_ = [("bogus_ratio", C.c_float), ("ref_x", C.c_int32), ("ref_y", C.c_int32)]
+
+
+VOTE_RESULT_DTYPE = np.dtype([("n_matches", "<i4"), ("hough_count", "<i4"), ("best_image", "<i4"),
+                              ("best_count", "<i4")])
 
 _lib = None
 
@@ -107,6 +115,14 @@ def load_library():
     L.surf_match_redo_count.argtypes = [vp, C.POINTER(i32)]
     L.surf_set_async_outputs.argtypes = [vp, i32]
     L.surf_wait_outputs.argtypes = [vp]
+    L.surf_db_create.argtypes = [vp, i32, lng, i32, C.POINTER(vp)]
+    L.surf_db_destroy.argtypes = [vp]
+    L.surf_db_destroy.restype = None
+    L.surf_db_clear.argtypes = [vp]
+    L.surf_db_add.argtypes = [vp, vp, vp, vp, i32, i32]
+    L.surf_db_size.argtypes = [vp, C.POINTER(lng), C.POINTER(i32)]
+    L.surf_db_knn.argtypes = [vp, vp, i32, i32, vp, i32]
+    L.surf_correspond.argtypes = [vp, vp, vp, vp, vp, i32, C.POINTER(VoteParams), vp, vp, i32]
     L.surf_version.argtypes = []
     L.surf_version.restype = C.c_char_p
     for name in ABI_SYMBOLS:
@@ -398,39 +414,116 @@ class SURF:
         self._check(self._lib.surf_merge_topk(self._h, in_ptr, n_ranks, nq, k, out_ptr))
 
 
+class DescriptorDB:
+    """Device-resident train database (surf_db_*): what cv::DescriptorMatcher::add(vector<Mat>) builds at
+    vtkSlicerSurfFeaturesLogic.cxx:1402-1403.  Rows are prepared for the tensor-core matcher once per add()."""
+
+    def __init__(self, engine: SURF, dim: int = 64, max_rows: int = 1 << 20, max_images: int = 4096):
+        self._engine = engine
+        self._lib = engine._lib
+        self.dim = dim
+        h = C.c_void_p()
+        engine._check(self._lib.surf_db_create(engine._h, dim, max_rows, max_images, C.byref(h)))
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None) and getattr(self._engine, "_h", None):
+            self._lib.surf_db_destroy(self._h)
+        self._h = None
+
+    __del__ = close
+
+    def clear(self):
+        self._engine._check(self._lib.surf_db_clear(self._h))
+
+    def add(self, descriptors: Sequence[np.ndarray], keypoints: Optional[Sequence[np.ndarray]] = None):
+        """One entry per train image (imgIdx = position in the add() order)."""
+        descs = [np.ascontiguousarray(d, np.float32).reshape(-1, self.dim) for d in descriptors]
+        if not descs:
+            return
+        off = np.concatenate([[0], np.cumsum([len(d) for d in descs])]).astype(np.int32)
+        allrows = np.ascontiguousarray(np.concatenate(descs, axis=0))
+        kp = None
+        if keypoints is not None:
+            kp = np.ascontiguousarray(np.concatenate([np.asarray(k, KEYPOINT_DTYPE) for k in keypoints]))
+            if len(kp) != len(allrows):
+                raise SurfError(-1, "keypoints and descriptors must have the same number of rows")
+        self._engine._check(self._lib.surf_db_add(self._h, _ptr(allrows), _ptr(kp), _ptr(off), len(descs), MEM_HOST))
+
+    def add_device(self, desc_ptr: int, kps_ptr: int, offsets: np.ndarray):
+        """Rows already on the device (e.g. SURF.device_results() of a collected batch)."""
+        off = np.ascontiguousarray(offsets, np.int32)
+        self._engine._check(self._lib.surf_db_add(self._h, desc_ptr, kps_ptr or None, _ptr(off), len(off) - 1, MEM_DEVICE))
+
+    def size(self):
+        rows, images = C.c_long(0), C.c_int(0)
+        self._engine._check(self._lib.surf_db_size(self._h, C.byref(rows), C.byref(images)))
+        return rows.value, images.value
+
+    def knnMatch(self, queryDescriptors, k=2) -> np.ndarray:
+        q = np.ascontiguousarray(queryDescriptors, np.float32)
+        out = np.zeros((q.shape[0], k), DMATCH_DTYPE)
+        self._engine._check(self._lib.surf_db_knn(self._h, _ptr(q), q.shape[0], k, _ptr(out), MEM_HOST))
+        return out
+
+
+def correspond(train: DescriptorDB, bogus: DescriptorDB, query_descriptors: Sequence[np.ndarray],
+               query_keypoints: Sequence[np.ndarray], ref_x: int, ref_y: int, bogus_ratio: float = 0.95):
+    """computeNextInterSliceCorrespondence (vtkSlicerSurfFeaturesLogic.cxx:1434-1571) for all query images.
+
+    Returns (after_hough, results): after_hough[i] is the DMATCH array of query image i after the bogus filter
+    (entries the Hough vote rejected carry -1 indices, as afterHoughMatches does); results is a
+    VOTE_RESULT_DTYPE array (n_matches, hough_count, best_image, best_count)."""
+    eng = train._engine
+    descs = [np.ascontiguousarray(d, np.float32).reshape(-1, train.dim) for d in query_descriptors]
+    off = np.concatenate([[0], np.cumsum([len(d) for d in descs])]).astype(np.int32)
+    n = int(off[-1])
+    allq = np.ascontiguousarray(np.concatenate(descs, axis=0)) if n else np.zeros((0, train.dim), np.float32)
+    kp = np.ascontiguousarray(np.concatenate([np.asarray(k, KEYPOINT_DTYPE) for k in query_keypoints])) if n else \
+        np.zeros(0, KEYPOINT_DTYPE)
+    matches = np.zeros(max(n, 1), DMATCH_DTYPE)
+    results = np.zeros(len(descs), VOTE_RESULT_DTYPE)
+    vp = VoteParams(float(bogus_ratio), int(ref_x), int(ref_y))
+    eng._check(eng._lib.surf_correspond(train._h, bogus._h, _ptr(allq), _ptr(kp), _ptr(off), len(descs), C.byref(vp),
+                                        _ptr(matches), _ptr(results), MEM_HOST))
+    return [matches[off[i]:off[i] + results["n_matches"][i]].copy() for i in range(len(descs))], results
+
+
 class BFMatcher:
     """cv::BFMatcher(NORM_L2): add / clear / knnMatch with DMatch records (imgIdx bookkeeping as
-    DescriptorMatcher::add(vector<Mat>) does; vtkSlicerSurfFeaturesLogic.cxx:1402-1403, :640)."""
+    DescriptorMatcher::add(vector<Mat>) does; vtkSlicerSurfFeaturesLogic.cxx:1402-1403, :640).
+    The added train images live in a device-resident DescriptorDB."""
 
-    def __init__(self, engine: Optional[SURF] = None, **engine_kw):
+    def __init__(self, engine: Optional[SURF] = None, *, max_rows: int = 1 << 18, max_images: int = 1024, **engine_kw):
         self._engine = engine or SURF(**engine_kw)
         self._train: list[np.ndarray] = []
+        self._db: Optional[DescriptorDB] = None
+        self._cap = (max_rows, max_images)
 
     def add(self, descriptors: Sequence[np.ndarray]):
-        for d in descriptors:
-            self._train.append(np.ascontiguousarray(d, np.float32))
+        new = [np.ascontiguousarray(d, np.float32) for d in descriptors]
+        if not new:
+            return
+        if self._db is None:
+            self._db = DescriptorDB(self._engine, new[0].shape[1], *self._cap)
+        self._db.add(new)
+        self._train.extend(new)
 
     def clear(self):
         self._train = []
+        if self._db is not None:
+            self._db.clear()
 
     def getTrainDescriptors(self):
         return list(self._train)
 
     def knnMatch(self, queryDescriptors, trainDescriptors=None, k=2) -> np.ndarray:
-        """Returns an (Nq, k) DMATCH_DTYPE array, ascending distance, ties -> lower trainIdx."""
+        """Returns an (Nq, k) DMATCH_DTYPE array, ascending distance, ties -> lower imgIdx, lower trainIdx."""
         if trainDescriptors is not None:
             return self._engine.match_knn(queryDescriptors, trainDescriptors, k)
         if not self._train:
             return np.zeros((len(queryDescriptors), 0), DMATCH_DTYPE)
-        sizes = np.array([len(t) for t in self._train])
-        starts = np.concatenate([[0], np.cumsum(sizes)])
-        m = self._engine.match_knn(queryDescriptors, np.concatenate(self._train, axis=0), k)
-        # map the concatenated row index back to (imgIdx, trainIdx within that image)
-        valid = m["trainIdx"] >= 0
-        img = np.searchsorted(starts, m["trainIdx"], side="right") - 1
-        m["imgIdx"] = np.where(valid, img, -1)
-        m["trainIdx"] = np.where(valid, m["trainIdx"] - starts[np.clip(img, 0, len(sizes) - 1)], -1)
-        return m
+        return self._db.knnMatch(queryDescriptors, k)
 
     def ratioMatch(self, queryDescriptors, trainDescriptors, ratio=0.8):
         return self._engine.match_ratio(queryDescriptors, trainDescriptors, ratio)
