@@ -233,6 +233,47 @@ int surf_correspond(surf_db *train, surf_db *bogus, const float *query_descripto
                     const surf_keypoint *query_keypoints, const int32_t *q_offsets, int n_query_images,
                     const surf_vote_params *params, surf_dmatch *matches, surf_vote_result *results, int mem);
 
+/* ---- "next" row f1: MHA sequence ingest + crop + mask, readAndComputeFeaturesOnMhaFile :1337-1379 ----
+ * Host-side reader of the PLUS MetaImage sequences the reference loads (readImageDimensions_mha :444-476,
+ * readImageTransforms_mha :478-541, readImages_mha :543-595, read_mha :598-632) and the driver that pushes
+ * a whole file through the engine in batches (computeNext :1392-1406), reading the next batch from disk into
+ * pinned memory while the current one is on the GPU.  The crop (cropData :745-752) is applied during the
+ * host->device copy: only the rectangle's bytes are uploaded. */
+typedef struct surf_mha surf_mha;
+
+typedef struct surf_mha_info {
+    int32_t width, height, frames_in_file; /* DimSize */
+    int32_t first_frame, last_frame;       /* requested range after the reference's clamping */
+    int32_t n_frames;                      /* frames kept: in range and tracking status OK */
+    int32_t n_transforms;                  /* transforms / names kept by the same filter */
+} surf_mha_info;
+
+/* By default a frame with status INVALID is not read and its bytes are NOT skipped (what readImages_mha
+ * does: every later frame then comes from one frame earlier in the file).  This flag skips them. */
+#define SURF_MHA_SKIP_INVALID_BYTES 1
+
+int surf_mha_open(const char *path, int first_frame, int last_frame, int flags, surf_mha **out, surf_mha_info *info);
+void surf_mha_close(surf_mha *m);
+const char *surf_mha_last_error(const surf_mha *m);
+/* n_transforms x 12 floats (rows of the 3x4 tracker transform), kept frames only */
+int surf_mha_transforms(const surf_mha *m, float *transforms, int capacity);
+/* validity flags of frames first_frame..last_frame (what read_mha leaves in transformsValidity) */
+int surf_mha_validity(const surf_mha *m, uint8_t *valid, int capacity);
+/* "<directory of the file><frame field name>.png" of kept frame i */
+int surf_mha_frame_name(const surf_mha *m, int i, char *buf, int capacity);
+/* kept frames [start, start+count) -> dst (width*height bytes each, frame_stride apart) */
+int surf_mha_read(surf_mha *m, int start, int count, uint8_t *dst, size_t frame_stride);
+/* cropData's cv::Rect(x, y, w, h) for crop_ratios = {x0, x1, y0, y1} (fp32 arithmetic, truncation) */
+int surf_crop_rect(int width, int height, const float crop_ratios[4], int32_t rect[4]);
+/* computeCentroid :839-860 of a (cropped) mask */
+int surf_mask_centroid(const uint8_t *mask, int width, int height, size_t pitch, int32_t *x, int32_t *y);
+/* Every kept frame of the file: crop (NULL = whole frame), detect with the full-size mask's same rectangle
+ * (NULL = no mask), describe.  Results go to the optional host arrays (packed, offsets[n_frames+1]) and /
+ * or are appended to db on the device (matcher->add).  The engine's max_batch sets the batch size. */
+int surf_sweep_mha(surf_engine *e, surf_mha *m, const float crop_ratios[4], const uint8_t *mask, size_t mask_pitch,
+                   surf_db *db, surf_keypoint *keypoints, float *descriptors, int32_t *offsets, long capacity,
+                   int32_t *n_frames_out);
+
 const char *surf_version(void);
 
 #ifdef __cplusplus

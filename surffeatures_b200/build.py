@@ -23,6 +23,7 @@ UNITS = [
     ("surf_engine.cu", []),
     ("surf_db.cu", []),
     ("surf_vote.cu", ["-fmad=false"]),
+    ("surf_mha.cu", ["-fmad=false"]),
 ]
 
 

@@ -426,6 +426,14 @@ int stage_images(surf_engine *e, const BatchIn &in, ImageRef *ref)
     if (in.batch == 1 || in.frame_stride == in.pitch * (size_t)in.height) {
         CU(e, cudaMemcpy2DAsync(e->d_img, dp, in.images, in.pitch, in.width, (size_t)in.height * in.batch,
                                 cudaMemcpyHostToDevice, e->stream));
+    } else if (in.frame_stride % in.pitch == 0) {
+        // a rectangle of every frame of a strided stack (e.g. the crop of an MHA sweep): one 3-D copy
+        cudaMemcpy3DParms p3{};
+        p3.srcPtr = make_cudaPitchedPtr((void *)in.images, in.pitch, in.width, in.frame_stride / in.pitch);
+        p3.dstPtr = make_cudaPitchedPtr(e->d_img, dp, in.width, in.height);
+        p3.extent = make_cudaExtent(in.width, in.height, in.batch);
+        p3.kind = cudaMemcpyHostToDevice;
+        CU(e, cudaMemcpy3DAsync(&p3, e->stream));
     } else {
         for (int b = 0; b < in.batch; b++)
             CU(e, cudaMemcpy2DAsync(e->d_img + (size_t)b * dp * in.height, dp, in.images + (size_t)b * in.frame_stride,
