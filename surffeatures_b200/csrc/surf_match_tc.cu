@@ -491,59 +491,73 @@ __global__ void __launch_bounds__(256) k_tc_rescore(TcPool pool, TcPool tpool, c
     }
 }
 
-// Exact redo of the (rare) queries whose candidate set could not be proven: one CTA per query, one train
-// row per thread at a time (each distance is the same sequential fp32 sum as in k_match_exact), per-thread
-// top-4, then a merge across the CTA.  A single query is latency-critical: a lone warp scanning thousands of
-// rows would take longer than the whole tensor-core pass.
-template <int D>
-__global__ void __launch_bounds__(256) k_tc_redo(TcPool tpool, const TcProblem *__restrict__ probs, int k, float ratio,
-                                                 surf_dmatch *__restrict__ out, uint8_t *__restrict__ good,
-                                                 const int *__restrict__ redo_list, const int *__restrict__ redo_count)
+// Exact redo of the queries whose candidate set could not be proven.  A CTA takes NG consecutive entries of
+// the redo list; when they belong to one problem (always, for a database query) every train row is loaded once
+// and scored against all NG queries, otherwise the entries are scanned one by one.  One train row per thread at
+// a time, each distance the same sequential fp32 sum as in k_match_exact, per-thread top-4 per query, then a
+// merge across the CTA.  Rare in practice (a handful per 10^5 queries); common only when the train set holds
+// many exact duplicates of a descriptor (more tied rows than the candidate lists keep).
+template <int D, int NG>
+__device__ void redo_scan(const TcProblem &pr, int nt, const int *__restrict__ entries, int ng, int k, float ratio,
+                          surf_dmatch *__restrict__ out, uint8_t *__restrict__ good, float (*s_q)[D], float (*s_d)[8][4],
+                          int (*s_i)[8][4])
 {
-    __shared__ float s_d[8][4];
-    __shared__ int s_i[8][4];
-    __shared__ __align__(16) float s_q[D];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int n = *redo_count;
-    for (int w = blockIdx.x; w < n; w += gridDim.x) {
-        const int p = redo_list[2 * w], gq = redo_list[2 * w + 1];
-        const TcProblem pr = probs[p];
-        const int nt = tpool.count[pr.t_slot];
-        const int q_row0 = pr.q_off ? pr.q_off[0] : pr.q_row0;
-        const int t_row0 = pr.t_off ? pr.t_off[0] : pr.t_row0;
-        const int out_row0 = pr.out_off ? pr.out_off[0] : pr.out_row0;
-        __syncthreads();
-        if (tid < D) s_q[tid] = pr.qsrc[(size_t)(q_row0 + gq) * D + tid];
-        __syncthreads();
-        float bd[4] = {INFINITY, INFINITY, INFINITY, INFINITY};
-        int bi[4] = {-1, -1, -1, -1};
-        for (int t = tid; t < nt; t += 256) {
-            const float4 *tv = reinterpret_cast<const float4 *>(pr.tsrc + (size_t)(t_row0 + t) * D);
-            float acc = 0.f;
+    const int q_row0 = pr.q_off ? pr.q_off[0] : pr.q_row0;
+    const int t_row0 = pr.t_off ? pr.t_off[0] : pr.t_row0;
+    const int out_row0 = pr.out_off ? pr.out_off[0] : pr.out_row0;
+    __syncthreads();
+    for (int i = tid; i < NG * D; i += 256) {
+        const int g = i / D, d = i - g * D;
+        s_q[g][d] = g < ng ? pr.qsrc[(size_t)(q_row0 + entries[2 * g + 1]) * D + d] : 0.f;
+    }
+    __syncthreads();
+    float bd[NG][4];
+    int bi[NG][4];
+#pragma unroll
+    for (int g = 0; g < NG; g++)
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            bd[g][r] = INFINITY;
+            bi[g][r] = -1;
+        }
+    for (int t = tid; t < nt; t += 256) {
+        const float4 *tv = reinterpret_cast<const float4 *>(pr.tsrc + (size_t)(t_row0 + t) * D);
+        float acc[NG];
+#pragma unroll
+        for (int g = 0; g < NG; g++) acc[g] = 0.f;
 #pragma unroll 4
-            for (int d = 0; d < D / 4; d++) {  // same element order as k_match_exact
-                const float4 b4 = __ldg(tv + d);
-                const float4 a4 = *reinterpret_cast<const float4 *>(s_q + 4 * d);
-                float df = a4.x - b4.x; acc = fmaf(df, df, acc);
-                df = a4.y - b4.y; acc = fmaf(df, df, acc);
-                df = a4.z - b4.z; acc = fmaf(df, df, acc);
-                df = a4.w - b4.w; acc = fmaf(df, df, acc);
+        for (int d = 0; d < D / 4; d++) {  // same element order as k_match_exact
+            const float4 b4 = __ldg(tv + d);
+#pragma unroll
+            for (int g = 0; g < NG; g++) {
+                const float4 a4 = *reinterpret_cast<const float4 *>(&s_q[g][4 * d]);
+                float df = a4.x - b4.x; acc[g] = fmaf(df, df, acc[g]);
+                df = a4.y - b4.y; acc[g] = fmaf(df, df, acc[g]);
+                df = a4.z - b4.z; acc[g] = fmaf(df, df, acc[g]);
+                df = a4.w - b4.w; acc[g] = fmaf(df, df, acc[g]);
             }
-            if (acc < bd[3]) {  // increasing t within a thread: ties keep the lower index
-                bd[3] = acc;
-                bi[3] = t;
+        }
+#pragma unroll
+        for (int g = 0; g < NG; g++) {
+            if (acc[g] < bd[g][3]) {  // increasing t within a thread: ties keep the lower index
+                bd[g][3] = acc[g];
+                bi[g][3] = t;
 #pragma unroll
                 for (int j = 3; j > 0; j--)
-                    if (bd[j] < bd[j - 1]) {
-                        const float td = bd[j]; bd[j] = bd[j - 1]; bd[j - 1] = td;
-                        const int ti = bi[j]; bi[j] = bi[j - 1]; bi[j - 1] = ti;
+                    if (bd[g][j] < bd[g][j - 1]) {
+                        const float td = bd[g][j]; bd[g][j] = bd[g][j - 1]; bd[g][j - 1] = td;
+                        const int ti = bi[g][j]; bi[g][j] = bi[g][j - 1]; bi[g][j - 1] = ti;
                     }
             }
         }
-        // warp merge of 32 sorted lists: 4 rounds of arg-min over the list heads (ties -> lower index)
+    }
+    // warp merge of 32 sorted lists per query: 4 rounds of arg-min over the list heads (ties -> lower index)
+#pragma unroll
+    for (int g = 0; g < NG; g++) {
         for (int r = 0; r < 4; r++) {
-            float hd = bd[0];
-            int hi = bi[0], src = lane;
+            float hd = bd[g][0];
+            int hi = bi[g][0], src = lane;
 #pragma unroll
             for (int s2 = 16; s2 > 0; s2 >>= 1) {
                 const float od = __shfl_xor_sync(0xffffffffu, hd, s2);
@@ -553,40 +567,72 @@ __global__ void __launch_bounds__(256) k_tc_redo(TcPool tpool, const TcProblem *
                 if (take) { hd = od; hi = oi; src = os; }
             }
             if (lane == src && hi >= 0) {  // pop the winner's head
-                bd[0] = bd[1]; bi[0] = bi[1]; bd[1] = bd[2]; bi[1] = bi[2]; bd[2] = bd[3]; bi[2] = bi[3];
-                bd[3] = INFINITY; bi[3] = -1;
+                bd[g][0] = bd[g][1]; bi[g][0] = bi[g][1]; bd[g][1] = bd[g][2]; bi[g][1] = bi[g][2];
+                bd[g][2] = bd[g][3]; bi[g][2] = bi[g][3];
+                bd[g][3] = INFINITY; bi[g][3] = -1;
             }
             if (lane == 0) {
-                s_d[warp][r] = hd;
-                s_i[warp][r] = hi;
+                s_d[g][warp][r] = hd;
+                s_i[g][warp][r] = hi;
             }
         }
-        __syncthreads();
-        if (tid == 0) {  // merge the 8 warps' sorted 4-lists
-            int head[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-            surf_dmatch *o = out + ((size_t)out_row0 + gq) * k;
-            float d0 = INFINITY, d1 = INFINITY;
-            int i0 = -1, i1 = -1;
-            for (int r = 0; r < k; r++) {
-                int bw = -1;
-                float hd = INFINITY;
-                int hi = -1;
-                for (int ww = 0; ww < 8; ww++) {
-                    if (head[ww] >= 4) continue;
-                    const float od = s_d[ww][head[ww]];
-                    const int oi = s_i[ww][head[ww]];
-                    if (oi < 0) continue;
-                    if (hi < 0 || od < hd || (od == hd && oi < hi)) { hd = od; hi = oi; bw = ww; }
-                }
-                if (bw >= 0) head[bw]++;
-                o[r].query_idx = gq;
-                o[r].train_idx = hi;
-                o[r].img_idx = hi < 0 ? -1 : 0;
-                o[r].distance = sqrtf(hd);
-                if (r == 0) { d0 = hd; i0 = hi; }
-                if (r == 1) { d1 = hd; i1 = hi; }
+    }
+    __syncthreads();
+    if (tid < ng) {  // thread g merges the 8 warps' sorted 4-lists of query g
+        const int g = tid, gq = entries[2 * g + 1];
+        int head[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        surf_dmatch *o = out + ((size_t)out_row0 + gq) * k;
+        float d0 = INFINITY, d1 = INFINITY;
+        int i0 = -1, i1 = -1;
+        for (int r = 0; r < k; r++) {
+            int bw = -1;
+            float hd = INFINITY;
+            int hi = -1;
+            for (int ww = 0; ww < 8; ww++) {
+                if (head[ww] >= 4) continue;
+                const float od = s_d[g][ww][head[ww]];
+                const int oi = s_i[g][ww][head[ww]];
+                if (oi < 0) continue;
+                if (hi < 0 || od < hd || (od == hd && oi < hi)) { hd = od; hi = oi; bw = ww; }
             }
-            if (good && k >= 2) good[out_row0 + gq] = (i0 >= 0 && i1 >= 0 && sqrtf(d0) < ratio * sqrtf(d1)) ? 1 : 0;
+            if (bw >= 0) head[bw]++;
+            o[r].query_idx = gq;
+            o[r].train_idx = hi;
+            o[r].img_idx = hi < 0 ? -1 : 0;
+            o[r].distance = sqrtf(hd);
+            if (r == 0) { d0 = hd; i0 = hi; }
+            if (r == 1) { d1 = hd; i1 = hi; }
+        }
+        if (good && k >= 2) good[out_row0 + gq] = (i0 >= 0 && i1 >= 0 && sqrtf(d0) < ratio * sqrtf(d1)) ? 1 : 0;
+    }
+}
+
+constexpr int kRedoGroup = 8;
+
+template <int D>
+__global__ void __launch_bounds__(256) k_tc_redo(TcPool tpool, const TcProblem *__restrict__ probs, int k, float ratio,
+                                                 surf_dmatch *__restrict__ out, uint8_t *__restrict__ good,
+                                                 const int *__restrict__ redo_list, const int *__restrict__ redo_count)
+{
+    __shared__ float s_d[kRedoGroup][8][4];
+    __shared__ int s_i[kRedoGroup][8][4];
+    __shared__ __align__(16) float s_q[kRedoGroup][D];
+    const int n = *redo_count;
+    // few entries: one per CTA (a lone query is latency-critical); many: groups of kRedoGroup share every train row
+    const int group = n > (int)gridDim.x ? kRedoGroup : 1;
+    for (int w0 = blockIdx.x * group; w0 < n; w0 += gridDim.x * group) {
+        const int ng = min(group, n - w0);
+        const int *entries = redo_list + 2 * w0;
+        bool same = ng > 1;
+        for (int g = 1; g < ng; g++) same = same && entries[2 * g] == entries[0];
+        if (same) {
+            const TcProblem pr = probs[entries[0]];
+            redo_scan<D, kRedoGroup>(pr, tpool.count[pr.t_slot], entries, ng, k, ratio, out, good, s_q, s_d, s_i);
+        } else {
+            for (int g = 0; g < ng; g++) {
+                const TcProblem pr = probs[entries[2 * g]];
+                redo_scan<D, 1>(pr, tpool.count[pr.t_slot], entries + 2 * g, 1, k, ratio, out, good, s_q, s_d, s_i);
+            }
         }
     }
 }

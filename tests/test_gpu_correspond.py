@@ -186,3 +186,29 @@ def test_correspond_rejects_empty_databases(eng):
     finally:
         tdb.close()
         bdb.close()
+
+
+@pytest.mark.parametrize("dim,k", [(64, 2), (128, 3)])
+def test_db_many_exact_duplicates_take_the_grouped_redo_path(eng, oracle, dim, k):
+    """More tied rows inside one train tile than the candidate lists hold: the tensor-core proof fails for every
+    query and the exact redo (groups of queries sharing each train row) must still return the lowest-index rows,
+    like BFMatcher."""
+    from surffeatures_b200.engine import DescriptorDB
+
+    rng = np.random.default_rng(5 + dim)
+    base = _unit_rows(rng, 50, dim)
+    rows = np.repeat(base, 100, axis=0)                              # descriptor j = rows 100 j .. 100 j + 99
+    mats = [rows[:1234], rows[1234:3000], rows[3000:]]
+    q = base[np.arange(400) % 50]
+    db = DescriptorDB(eng, dim, max_rows=1 << 14, max_images=32)
+    try:
+        db.add(mats)
+        got = db.knnMatch(q, k)
+        assert eng.match_redo_count() == 400                         # every query was redone, in groups
+        want = oracle.db_knn(q, mats, k)
+        assert np.array_equal(got["imgIdx"], want["imgIdx"]) and np.array_equal(got["trainIdx"], want["trainIdx"])
+        assert (got["distance"] == 0).all()
+        few = db.knnMatch(q[:7], k)                                  # fewer entries than CTAs: one query per CTA
+        assert eng.match_redo_count() == 7 and few.tobytes() == got[:7].tobytes()
+    finally:
+        db.close()
