@@ -46,7 +46,9 @@ def _peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock and throttle reasons DURING the timed region.  NVML (nvidia_ml_py) is sampled from a thread every
+    10 ms -- the timed region of a short run is well under a second, less than nvidia-smi needs to start on an
+    8-GPU box; `nvidia-smi -lms` (the B200_PROFILING.md recipe) is the fallback when NVML cannot be imported."""
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -54,8 +56,46 @@ class ClockSampler:
 
     def __init__(self, gpu_index: int):
         self.rows, self.proc, self.idx = [], None, gpu_index
+        self.sm, self.reasons, self.mx, self.stop_flag, self.thread, self.nvml = [], set(), None, False, None, None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            # CUDA_VISIBLE_DEVICES may renumber: resolve through the PCI bus id of the torch device
+            import torch
+
+            props = torch.cuda.get_device_properties(gpu_index)
+            try:
+                self.handle = pynvml.nvmlDeviceGetHandleByPciBusId(
+                    f"{props.pci_domain_id:08x}:{props.pci_bus_id:02x}:{props.pci_device_id:02x}.0".encode())
+            except Exception:
+                self.handle = pynvml.nvmlDeviceGetHandleByUUID(f"GPU-{props.uuid}".encode())
+            self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
+
+    def _nvml_loop(self):
+        n = self.nvml
+        bits = {"hw_slowdown": n.nvmlClocksEventReasonHwSlowdown, "hw_thermal_slowdown": n.nvmlClocksEventReasonHwThermalSlowdown,
+                "sw_thermal_slowdown": n.nvmlClocksEventReasonSwThermalSlowdown, "sw_power_cap": n.nvmlClocksEventReasonSwPowerCap}
+        get_reasons = getattr(n, "nvmlDeviceGetCurrentClocksEventReasons", None) or n.nvmlDeviceGetCurrentClocksThrottleReasons
+        while not self.stop_flag:
+            try:
+                self.sm.append(float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)))
+                r = int(get_reasons(self.handle))
+                for name, b in bits.items():
+                    if r & b:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.01)
 
     def start(self):
+        if self.nvml is not None:
+            self.thread = threading.Thread(target=self._nvml_loop, daemon=True)
+            self.thread.start()
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                           "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE,
@@ -69,6 +109,13 @@ class ClockSampler:
             self.rows.append([c.strip() for c in line.split(",")])
 
     def stop(self):
+        if self.nvml is not None:
+            self.stop_flag = True
+            self.thread.join(timeout=1.0)
+            if not self.sm:
+                return {"sm_mhz": None, "sm_max_mhz": self.mx, "reasons": ["no NVML sample"], "source": "nvml"}
+            return {"sm_mhz": float(np.median(self.sm)), "sm_max_mhz": self.mx, "reasons": sorted(self.reasons),
+                    "samples": len(self.sm), "source": "nvml"}
         if self.proc:
             self.proc.terminate()
         sm, mx, reasons = [], [], set()
@@ -82,7 +129,8 @@ class ClockSampler:
                 pass
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm),
+                "source": "nvidia-smi"}
 
 
 def make_stream(n_frames: int, seed: int) -> np.ndarray:
