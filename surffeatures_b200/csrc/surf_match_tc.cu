@@ -400,9 +400,10 @@ __global__ void __launch_bounds__(256) k_tc_candidates(TcPool pool, TcPool tpool
 }
 
 // ------------------------------------------------------------------------------------------------
-// K5c: exact rescoring of the candidates, top-k, margin test.  kCand lanes per query.
+// K5c: exact rescoring of the candidates, top-k, margin test.  LPQ lanes per query, one per
+// candidate slot of a list (4 when the lists keep 4 entries, else 8).
 // ------------------------------------------------------------------------------------------------
-template <int D>
+template <int D, int LPQ>
 __global__ void __launch_bounds__(256) k_tc_rescore(TcPool pool, TcPool tpool, const TcProblem *__restrict__ probs, int n_splits,
                                                     int cand_stride, const TcCand *__restrict__ cand, int k, float ratio,
                                                     surf_dmatch *__restrict__ out, uint8_t *__restrict__ good,
@@ -411,20 +412,20 @@ __global__ void __launch_bounds__(256) k_tc_rescore(TcPool pool, TcPool tpool, c
     const int p = blockIdx.y;
     const TcProblem pr = probs[p];
     const int nq = pool.count[pr.q_slot], nt = tpool.count[pr.t_slot];
-    const int gq = (blockIdx.x * blockDim.x + threadIdx.x) / kCand;
-    const int lane_c = threadIdx.x % kCand;
-    if (gq >= nq) return;  // kCand divides the warp: a query's lanes leave together
+    const int gq = (blockIdx.x * blockDim.x + threadIdx.x) / LPQ;
+    const int lane_c = threadIdx.x % LPQ;
+    if (gq >= nq) return;  // LPQ divides the warp: a query's lanes leave together
     const int q_row0 = pr.q_off ? pr.q_off[0] : pr.q_row0;
     const int t_row0 = pr.t_off ? pr.t_off[0] : pr.t_row0;
     const int out_row0 = pr.out_off ? pr.out_off[0] : pr.out_row0;
     const float *qsrc = pr.qsrc, *tsrc = pr.tsrc;
     const float *qv = qsrc + (size_t)(q_row0 + gq) * D;
-    const unsigned gmask = ((1u << kCand) - 1u) << ((threadIdx.x & 31) / kCand * kCand);
+    const unsigned gmask = ((1u << LPQ) - 1u) << ((threadIdx.x & 31) / LPQ * LPQ);
 
     // best k over all splits' candidates, by exact distance; each lane owns candidate slot lane_c
     float bd[4] = {INFINITY, INFINITY, INFINITY, INFINITY};
     int bi[4] = {-1, -1, -1, -1};
-    float worst_kept = INFINITY;  // smallest "kCand-th approximate value" over the splits
+    float worst_kept = INFINITY;  // smallest "LPQ-th approximate value" over the splits
     for (int s = 0; s < 2 * n_splits; s++) {
         const TcCand &c = cand[((size_t)p * 2 * n_splits + s) * cand_stride + gq];
         const int idx = c.i[lane_c];
@@ -445,11 +446,11 @@ __global__ void __launch_bounds__(256) k_tc_rescore(TcPool pool, TcPool tpool, c
         }
         // a list that is full bounds every train row it did not keep (an unfilled list kept them all)
         if (c.worst < INFINITY) worst_kept = fminf(worst_kept, c.worst);
-        // merge this split's kCand exact distances into the running top-4 (all lanes keep a copy)
+        // merge this split's LPQ exact distances into the running top-4 (all lanes keep a copy)
 #pragma unroll
-        for (int r = 0; r < kCand; r++) {
-            const float od = __shfl_sync(gmask, dist, (threadIdx.x & 31) / kCand * kCand + r);
-            const int oi = __shfl_sync(gmask, idx, (threadIdx.x & 31) / kCand * kCand + r);
+        for (int r = 0; r < LPQ; r++) {
+            const float od = __shfl_sync(gmask, dist, (threadIdx.x & 31) / LPQ * LPQ + r);
+            const int oi = __shfl_sync(gmask, idx, (threadIdx.x & 31) / LPQ * LPQ + r);
             if (oi < 0) continue;
             if (od < bd[3] || (od == bd[3] && (unsigned)oi < (unsigned)bi[3])) {
                 bd[3] = od;
@@ -689,18 +690,21 @@ void launch_tc_match(const TcMatchArgs &a, cudaStream_t st, int *launches)
         if (small_k) SURF_TC_LAUNCH(128, 4); else SURF_TC_LAUNCH(128, 8);
     }
 #undef SURF_TC_LAUNCH
-    dim3 gres(((size_t)a.max_q_rows * kCand + 255) / 256, a.n_probs);
+    const int lpq = small_k ? 4 : kCand;  // lists of the small-k candidate kernel hold 4 entries
+    dim3 gres(((size_t)a.max_q_rows * lpq + 255) / 256, a.n_probs);
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+#define SURF_TC_RESCORE(DD, LL)                                                                                        \
+    k_tc_rescore<DD, LL><<<gres, 256, 0, st>>>(a.pool, tp, a.probs, a.n_splits, a.max_q_rows, a.cand, a.k, a.ratio, a.out, \
+                                               a.good, a.redo_list, a.counters + 1)
     if (D == 64) {
-        k_tc_rescore<64><<<gres, 256, 0, st>>>(a.pool, tp, a.probs, a.n_splits, a.max_q_rows, a.cand, a.k, a.ratio, a.out,
-                                               a.good, a.redo_list, a.counters + 1);
+        if (small_k) SURF_TC_RESCORE(64, 4); else SURF_TC_RESCORE(64, kCand);
         k_tc_redo<64><<<sms * 2, 256, 0, st>>>(tp, a.probs, a.k, a.ratio, a.out, a.good, a.redo_list, a.counters + 1);
     } else {
-        k_tc_rescore<128><<<gres, 256, 0, st>>>(a.pool, tp, a.probs, a.n_splits, a.max_q_rows, a.cand, a.k, a.ratio, a.out,
-                                                a.good, a.redo_list, a.counters + 1);
+        if (small_k) SURF_TC_RESCORE(128, 4); else SURF_TC_RESCORE(128, kCand);
         k_tc_redo<128><<<sms * 2, 256, 0, st>>>(tp, a.probs, a.k, a.ratio, a.out, a.good, a.redo_list, a.counters + 1);
     }
+#undef SURF_TC_RESCORE
     *launches += 6;
 }
 
