@@ -67,7 +67,7 @@ int tc_reserve(surf_engine *e, surf_engine::TcWs &w, int slots, int slot_rows, i
 
 int tc_reserve_work(surf_engine *e, surf_engine::TcWs &w, int n_probs, int splits, int max_q, int n_segs)
 {
-    const size_t need = (size_t)n_probs * splits * 2 * max_q;  // two column halves per train split
+    const size_t need = (size_t)n_probs * splits * max_q;  // one merged candidate list per query and train split
     if (need > w.cand_cap) {
         CU(e, cudaStreamSynchronize(e->stream));
         cudaFree(w.cand);

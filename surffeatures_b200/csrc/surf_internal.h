@@ -188,7 +188,7 @@ struct TcMatchArgs {
     int n_probs;
     int n_splits;
     int max_q_rows;   // upper bound on queries per problem (multiple of 128)
-    TcCand *cand;     // [n_probs][n_splits][2 column halves][max_q_rows]
+    TcCand *cand;     // [n_probs][n_splits][max_q_rows]: the KC smallest approximate values of each train split
     int *counters;    // [0] work-queue head, [1] redo count
     int *redo_list;   // 2 ints per entry
     int dim, k;

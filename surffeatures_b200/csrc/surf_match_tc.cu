@@ -235,8 +235,10 @@ __device__ __forceinline__ void cand_replace_worst(Cand<KC> &c, float dist, int 
     c.wslot = ws;
 }
 
+constexpr int kCandThreads = 512;  // 16 warps: warp w owns TMEM lanes 32*(w%4).. and the column quarter w/4
+
 template <int D, int KC>
-__global__ void __launch_bounds__(256) k_tc_candidates(TcPool pool, TcPool tpool, const TcProblem *__restrict__ probs,
+__global__ void __launch_bounds__(kCandThreads, (D == 64 && KC <= 4) ? 2 : 1) k_tc_candidates(TcPool pool, TcPool tpool, const TcProblem *__restrict__ probs,
                                                        int n_probs, int mt_per_prob, int n_splits, int cand_stride,
                                                        TcCand *__restrict__ cand_out, int *__restrict__ work_head)
 {
@@ -251,11 +253,12 @@ __global__ void __launch_bounds__(256) k_tc_candidates(TcPool pool, TcPool tpool
     __shared__ __align__(8) uint64_t s_bar[2];  // [0] MMA done (tcgen05.commit), [1] operands landed (bulk copies)
     __shared__ uint32_t s_tmem;
     __shared__ int s_item;
-    __shared__ float s_thr[2][kTM];  // filter threshold published by each column half of a query row
+    __shared__ float s_thr[4][kTM];  // filter threshold published by each column quarter of a query row
 
     const int tid = threadIdx.x, warp = tid >> 5;
-    volatile float *my_thr = &s_thr[warp >> 2][(warp & 3) * 32 + (tid & 31)];
-    const volatile float *partner_thr = &s_thr[(warp >> 2) ^ 1][(warp & 3) * 32 + (tid & 31)];
+    const int quarter = warp >> 2, qrow = (warp & 3) * 32 + (tid & 31);
+    volatile float *my_thr = &s_thr[quarter][qrow];
+    const volatile float *row_thr = &s_thr[0][qrow];  // the four quarters' thresholds of this row, kTM apart
     const uint32_t bar_mma = smem_u32(&s_bar[0]), bar_ld = smem_u32(&s_bar[1]);
     if (tid == 0) {
         mbar_init(bar_mma, 1);
@@ -347,21 +350,20 @@ __global__ void __launch_bounds__(256) k_tc_candidates(TcPool pool, TcPool tpool
                 load_train_tile(tile + 1, stage ^ 1);
             }
 
-            // ---- epilogue: 8 warps; warp w reads TMEM lanes 32*(w%4).. (its query rows) and the
-            //      column half w/4, so two threads share a query row and each keeps its own list.
-            //      The filter threshold `thr` is the smaller of this list's worst kept value and the
-            //      partner's published one: both are >= the KC-th smallest value of the whole row, so
-            //      nothing that belongs to the row's KC smallest is ever rejected, and every value
-            //      either list rejects or evicts is >= the final thr (the bound the margin test uses).
+            // ---- epilogue: 16 warps; warp w reads TMEM lanes 32*(w%4).. (its query rows) and the column
+            //      quarter w/4, so four threads share a query row and each keeps its own list.  The filter
+            //      threshold `thr` is the smallest of the four lists' worst kept values: each of them is >= the
+            //      KC-th smallest value of the whole row, so nothing that belongs to the row's KC smallest is
+            //      ever rejected, and every value a list rejects or evicts is >= the final thr.
             const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16);
             const float *tn = sTn + stage * kTN;
             const int lim = min(kTN, nt - t0);
-            const int cbeg = (warp >> 2) * (kTN / 2);
+            const int cbeg = quarter * (kTN / 4);
 #pragma unroll 1
-            for (int c0 = cbeg; c0 < cbeg + kTN / 2; c0 += 32) {
+            for (int c0 = cbeg; c0 < cbeg + kTN / 4; c0 += 32) {
                 float v[32];
                 tmem_ld32(lane_addr + c0, v);
-                thr = fminf(thr, *partner_thr);
+                thr = fminf(fminf(thr, row_thr[0]), fminf(row_thr[kTM], fminf(row_thr[2 * kTM], row_thr[3 * kTM])));
                 if (c0 < lim) {
 #pragma unroll
                     for (int c = 0; c < 32; c += 4) {
@@ -383,17 +385,48 @@ __global__ void __launch_bounds__(256) k_tc_candidates(TcPool pool, TcPool tpool
             tc_fence_before();
             __syncthreads();  // every warp has drained TMEM before the next tile's MMA overwrites it
         }
-        const int row = (warp & 3) * 32 + (tid & 31), half = warp >> 2;
-        if (q0 + row < nq) {
-            TcCand o;
+        // ---- merge the four quarter lists of every query row into one list of the KC smallest values.  The
+        //      scratch aliases the train-tile buffer: every MMA that read it has completed (bar_mma), and the
+        //      next item's bulk copies are issued only after the proxy fence and the barrier at the loop top.
+        struct Ent {
+            float d;
+            int i;
+        };
+        static_assert(sizeof(Ent) * kTM * 4 * KC <= B_BYTES, "merge scratch must fit the train-tile buffer");
+        Ent *s_merge = reinterpret_cast<Ent *>(sB_hi);  // [row][quarter][KC]
 #pragma unroll
-            for (int r = 0; r < kCand; r++) {
-                o.d[r] = r < KC ? best.d[r < KC ? r : 0] : INFINITY;
-                o.i[r] = r < KC ? best.i[r < KC ? r : 0] : -1;
+        for (int r = 0; r < KC; r++) s_merge[(qrow * 4 + quarter) * KC + r] = Ent{best.d[r], best.i[r]};
+        *my_thr = thr;
+        __syncthreads();
+        if (tid < kTM) {
+            const int row = tid;
+            Cand<KC> m;
+#pragma unroll
+            for (int r = 0; r < KC; r++) {
+                m.d[r] = INFINITY;
+                m.i[r] = -1;
             }
-            o.worst = thr;  // lower bound of every value this list did not keep
-            cand_out[((size_t)(p * n_splits + split) * 2 + half) * cand_stride + q0 + row] = o;
+            m.worst = INFINITY;
+            m.wslot = 0;
+            for (int e = 0; e < 4 * KC; e++) {
+                const Ent en = s_merge[row * 4 * KC + e];
+                if (en.i >= 0 && en.d < m.worst) cand_replace_worst(m, en.d, en.i);
+            }
+            if (q0 + row < nq) {
+                TcCand o;
+#pragma unroll
+                for (int r = 0; r < kCand; r++) {
+                    o.d[r] = r < KC ? m.d[r < KC ? r : 0] : INFINITY;
+                    o.i[r] = r < KC ? m.i[r < KC ? r : 0] : -1;
+                }
+                // lower bound of every value of this split that is not in the list: what the quarter lists
+                // rejected or evicted (>= their final thresholds) and what the merge dropped (>= the list's worst)
+                const float bound = fminf(fminf(s_thr[0][row], s_thr[1][row]), fminf(s_thr[2][row], s_thr[3][row]));
+                o.worst = fminf(bound, m.worst);
+                cand_out[(size_t)(p * n_splits + split) * cand_stride + q0 + row] = o;
+            }
         }
+        fence_async_smem();  // generic-proxy accesses to the tile buffer before the next bulk copy overwrites it
     }
     __syncthreads();
     if (warp == 0) tmem_dealloc(tmem, kTmemCols);
@@ -426,8 +459,8 @@ __global__ void __launch_bounds__(256) k_tc_rescore(TcPool pool, TcPool tpool, c
     float bd[4] = {INFINITY, INFINITY, INFINITY, INFINITY};
     int bi[4] = {-1, -1, -1, -1};
     float worst_kept = INFINITY;  // smallest "LPQ-th approximate value" over the splits
-    for (int s = 0; s < 2 * n_splits; s++) {
-        const TcCand &c = cand[((size_t)p * 2 * n_splits + s) * cand_stride + gq];
+    for (int s = 0; s < n_splits; s++) {
+        const TcCand &c = cand[((size_t)p * n_splits + s) * cand_stride + gq];
         const int idx = c.i[lane_c];
         float dist = INFINITY;
         if (idx >= 0) {
@@ -664,26 +697,26 @@ void launch_tc_match(const TcMatchArgs &a, cudaStream_t st, int *launches)
     launch_tc_prep(a.pool, a.segs, a.n_segs, a.pool.slot_rows, D, true, st, nullptr);
     launch_zero(a.counters, 2, st, nullptr);  // [0] work head, [1] redo count
 
-    static int grids[64][2] = {};
+    static bool attr_set[64] = {};
     int dev = 0;
     cudaGetDevice(&dev);
-    int &grid = grids[dev & 63][D == 128];
     const size_t smem = tc_candidates_smem(D);
-    if (!grid) {
-        int sms = 148;
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (!attr_set[dev & 63]) {
         cudaFuncSetAttribute(k_tc_candidates<64, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_candidates_smem(64));
         cudaFuncSetAttribute(k_tc_candidates<64, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_candidates_smem(64));
         cudaFuncSetAttribute(k_tc_candidates<128, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_candidates_smem(128));
         cudaFuncSetAttribute(k_tc_candidates<128, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_candidates_smem(128));
-        // 256 TMEM columns per CTA: at most two CTAs share an SM's 512; D = 64 needs 2 x 101 KB of shared memory
-        grid = sms * (D == 64 ? 2 : 1);
+        attr_set[dev & 63] = true;
     }
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int mt_per_prob = a.max_q_rows / kTM;
     const bool small_k = a.k <= 2;
-#define SURF_TC_LAUNCH(DD, KK)                                                                                      \
-    k_tc_candidates<DD, KK><<<grid, 256, smem, st>>>(a.pool, tp, a.probs, a.n_probs, mt_per_prob, a.n_splits,       \
-                                                     a.max_q_rows, a.cand, a.counters)
+// persistent CTAs: 256 TMEM columns each, so at most two share an SM's 512; the D = 64 / 4-entry variant fits two
+// (2 x 101 KB of shared memory, 64 registers x 512 threads), the others run one per SM
+#define SURF_TC_LAUNCH(DD, KK)                                                                              \
+    k_tc_candidates<DD, KK><<<((DD) == 64 && (KK) <= 4) ? 2 * sms : sms, kCandThreads, smem, st>>>(         \
+        a.pool, tp, a.probs, a.n_probs, mt_per_prob, a.n_splits, a.max_q_rows, a.cand, a.counters)
     if (D == 64) {
         if (small_k) SURF_TC_LAUNCH(64, 4); else SURF_TC_LAUNCH(64, 8);
     } else {
@@ -692,8 +725,6 @@ void launch_tc_match(const TcMatchArgs &a, cudaStream_t st, int *launches)
 #undef SURF_TC_LAUNCH
     const int lpq = small_k ? 4 : kCand;  // lists of the small-k candidate kernel hold 4 entries
     dim3 gres(((size_t)a.max_q_rows * lpq + 255) / 256, a.n_probs);
-    int sms = 148;
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
 #define SURF_TC_RESCORE(DD, LL)                                                                                        \
     k_tc_rescore<DD, LL><<<gres, 256, 0, st>>>(a.pool, tp, a.probs, a.n_splits, a.max_q_rows, a.cand, a.k, a.ratio, a.out, \
                                                a.good, a.redo_list, a.counters + 1)
