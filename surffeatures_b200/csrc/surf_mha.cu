@@ -14,6 +14,7 @@
 //     comes from one frame earlier in the file (readImages_mha has no seek on that branch).  Flag
 //     SURF_MHA_SKIP_INVALID_BYTES selects the evidently intended behaviour instead.
 #include <cerrno>
+#include <unistd.h>
 #include <cstdlib>
 #include <cstring>
 #include <future>
@@ -286,6 +287,9 @@ int surf_sweep_mha(surf_engine *e, surf_mha *m, const float crop_ratios[4], cons
     if (mask && mask_pitch < (size_t)m->width) return fail(e, SURF_ERR_BAD_ARG, "mask must be as large as the frames");
     const int n = (int)m->frame_offset.size(), B = e->max_b, D = surf_descriptor_size(e);
     const size_t frame_bytes = (size_t)m->width * m->height;
+    // only the rows of the crop rectangle are read from the file (full width: one contiguous run per frame)
+    const size_t band_bytes = (size_t)m->width * rect[3];
+    const long band_off = (long)rect[1] * m->width;
     int rc = ensure_device(e);
     if (rc) return rc;
     if (m->stage_bytes < frame_bytes * B) {
@@ -301,22 +305,46 @@ int surf_sweep_mha(surf_engine *e, surf_mha *m, const float crop_ratios[4], cons
     offsets[0] = 0;
     if (n_frames_out) *n_frames_out = n;
     long total = 0;
-    auto read_chunk = [m, frame_bytes](int start, int count, uint8_t *dst) {
-        return surf_mha_read(m, start, count, dst, frame_bytes);
+    // kReaders threads pread() interleaved frames of a chunk (page-cache reads are memcpy-bound per thread)
+    constexpr int kReaders = 4;
+    const int fd = fileno(m->fp);
+    auto read_part = [m, fd, band_bytes, band_off](int start, int count, int part, uint8_t *dst) {
+        for (int i = part; i < count; i += kReaders) {
+            uint8_t *d = dst + (size_t)i * band_bytes;
+            size_t got = 0;
+            while (got < band_bytes) {
+                const ssize_t r = pread(fd, d + got, band_bytes - got, m->frame_offset[start + i] + band_off + (long)got);
+                if (r < 0 && errno == EINTR) continue;
+                if (r <= 0) break;
+                got += (size_t)r;
+            }
+            // a short file leaves the rest of the frame zero (the reference's fread is unchecked)
+            if (got < band_bytes) memset(d + got, 0, band_bytes - got);
+        }
+        return 0;
+    };
+    std::vector<std::future<int> > pending;
+    auto start_chunk = [&](int start, int count, uint8_t *dst) {
+        pending.clear();
+        for (int t = 0; t < kReaders; t++) pending.push_back(std::async(std::launch::async, read_part, start, count, t, dst));
+    };
+    auto wait_chunk = [&]() {
+        for (auto &f : pending)
+            if (f.valid()) f.get();
+        pending.clear();
     };
     // chunk c is read from the file while chunk c-1 is on the GPU (two pinned buffers)
-    std::future<int> pending;
-    if (n > 0) pending = std::async(std::launch::async, read_chunk, 0, n < B ? n : B, m->stage[0]);
+    if (n > 0) start_chunk(0, n < B ? n : B, m->stage[0]);
     std::vector<int32_t> off((size_t)B + 1);
     for (int start = 0, c = 0; start < n; start += B, c++) {
         const int cnt = n - start < B ? n - start : B;
-        if ((rc = pending.get())) return fail(e, rc, "reading frames %d..%d failed: %s", start, start + cnt - 1, m->err);
+        wait_chunk();
         if (start + B < n) {
             const int nxt = n - (start + B) < B ? n - (start + B) : B;
-            pending = std::async(std::launch::async, read_chunk, start + B, nxt, m->stage[(c + 1) & 1]);
+            start_chunk(start + B, nxt, m->stage[(c + 1) & 1]);
         }
-        const uint8_t *view = m->stage[c & 1] + (size_t)rect[1] * m->width + rect[0];  // cropData: the roi of every frame
-        rc = surf_submit_batch(e, view, SURF_MEM_HOST, cnt, rect[2], rect[3], (size_t)m->width, frame_bytes, cmask, mask_pitch, 1);
+        const uint8_t *view = m->stage[c & 1] + rect[0];  // cropData: the roi of every frame (rows already selected)
+        rc = surf_submit_batch(e, view, SURF_MEM_HOST, cnt, rect[2], rect[3], (size_t)m->width, band_bytes, cmask, mask_pitch, 1);
         if (!rc) {
             if (keypoints || descriptors)
                 rc = surf_collect_batch(e, keypoints ? keypoints + total : nullptr, descriptors ? descriptors + (size_t)total * D : nullptr,
@@ -331,7 +359,7 @@ int surf_sweep_mha(surf_engine *e, surf_mha *m, const float crop_ratios[4], cons
             if (!rc) rc = surf_db_add(db, dd, dk, off.data(), cnt, SURF_MEM_DEVICE);
         }
         if (rc) {
-            if (pending.valid()) pending.wait();
+            wait_chunk();
             return rc;
         }
         for (int b = 0; b < cnt; b++) offsets[start + b + 1] = (int32_t)(total + off[b + 1]);
