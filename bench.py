@@ -314,8 +314,8 @@ def run_ours(args):
     dom_bytes = (alg["hessian"] + alg["nms"] if dom == "hessian" else alg[dom]) * B
     achieved = dom_bytes / (stage_ms[dom] * 1e-3) / 1e9
     # dram__bytes_read+write of the describe-stage kernels from one `ncu --set full` capture of this very
-    # command at batch 64 (profiles/r1/describe_stage_v5_ncu_summary.txt): 225.6 MB read + 19.8 MB written
-    traffic = 245.4e6 if (dom == "describe" and B == 64) else None
+    # command at batch 64 (profiles/r1/describe_stage_v10_ncu_summary.txt): 189.9 MB read + 38.9 MB written
+    traffic = 228.8e6 if (dom == "describe" and B == 64) else None
     roofline = {"bound": "hbm", "kernel": {"integral": "k_band_colsum+k_band_integral",
                                            "hessian": "k_hessian_nms_tma_c<0|1>+k_hessian+k_nms",
                                            "describe": "k_orient+k_descriptor<5 size classes>"}[dom],
@@ -326,8 +326,8 @@ def run_ours(args):
                 "peak_kind": "burst copy peak; the stage is timed inside a long step",
                 # the stage's real limiter: warp instructions issued (ncu smsp__inst_executed.sum of the describe
                 # kernels at batch 64, profiles/r1/) / stage time, against 148 SMs x 4 schedulers x SM clock
-                "issue_slots": ({"warp_inst_per_step": 6.9e9, "achieved_ginst_s": 6.9e9 / (stage_ms[dom] * 1e-3) / 1e9,
-                                 "peak_ginst_s": 148 * 4 * 1.965, "frac": 6.9e9 / (stage_ms[dom] * 1e-3) / (148 * 4 * 1.965e9)}
+                "issue_slots": ({"warp_inst_per_step": 6.52e9, "achieved_ginst_s": 6.52e9 / (stage_ms[dom] * 1e-3) / 1e9,
+                                 "peak_ginst_s": 148 * 4 * 1.965, "frac": 6.52e9 / (stage_ms[dom] * 1e-3) / (148 * 4 * 1.965e9)}
                                 if (dom == "describe" and B == 64) else None),
                 "algorithmic_bytes_per_launch": dom_bytes, "ms_per_launch": stage_ms[dom],
                 "stage_ms_per_step": stage_ms,
