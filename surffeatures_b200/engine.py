@@ -37,7 +37,8 @@ ABI_SYMBOLS = [
     "surf_match_ratio", "surf_merge_topk", "surf_version", "surf_match_prev", "surf_stream_reset",
     "surf_device_matches", "surf_set_match_mode", "surf_match_redo_count", "surf_set_async_outputs",
     "surf_wait_outputs", "surf_db_create", "surf_db_destroy", "surf_db_clear", "surf_db_add", "surf_db_size",
-    "surf_db_knn", "surf_correspond",
+    "surf_db_knn", "surf_correspond", "surf_mha_open", "surf_mha_close", "surf_mha_last_error", "surf_mha_transforms",
+    "surf_mha_validity", "surf_mha_frame_name", "surf_mha_read", "surf_crop_rect", "surf_mask_centroid", "surf_sweep_mha",
 ]
 
 
