@@ -16,6 +16,7 @@
 #include <cmath>
 
 #include "surf_internal.h"
+#include "surf_ptx.cuh"
 
 namespace surfb200 {
 
@@ -300,34 +301,12 @@ struct DescShared {  // static shared state of one descriptor CTA
     int work;
 };
 
-__device__ __forceinline__ void mbar_init1(uint32_t bar)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
-}
-
-__device__ __forceinline__ bool mbar_wait_bounded(uint32_t bar, uint32_t parity)
-{
-    uint32_t done = 0;
-    for (uint32_t spin = 0; !done && spin < (1u << 24); spin++)
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done)
-            : "r"(bar), "r"(parity)
-            : "memory");
-    return done != 0;
-}
-
 // One TMA box load of the 8-bit frame b at (x, y) (x 16-byte aligned) into shared memory.
 __device__ __forceinline__ void tma_load_tile(const CUtensorMap *map, uint32_t dst, int x, int y, int b, uint32_t bar, uint32_t bytes)
 {
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // earlier generic accesses of the buffer are done
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-    asm volatile(
-        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
-        ::"r"(dst), "l"(map), "r"(x), "r"(y), "r"(b), "r"(bar)
-        : "memory");
+    fence_async_smem();  // earlier generic accesses of the buffer are done
+    mbar_expect_tx(bar, bytes);
+    tma_load_3d(map, dst, x, y, b, bar);
 }
 
 // INTER_AREA table entry of destination cell d for an n-pixel source axis (computeResizeAreaTab).
@@ -569,8 +548,8 @@ __global__ void __launch_bounds__(ClassT<CLS>::threads) k_descriptor(const __gri
     const int *list = A.class_list + (size_t)CLS * A.list_stride;
     const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&s_bar);
     if (tid == 0) {
-        mbar_init1(bar);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        mbar_init(bar, 1);
+        mbar_init_fence();
     }
 
     for (;;) {
@@ -709,9 +688,9 @@ __global__ void __launch_bounds__(BigT::threads) k_descriptor_big(const __grid_c
     float *g_buf = reinterpret_cast<float *>(g_win + (size_t)kMaxWindow * kMaxWindow);
     const uint32_t bar0 = (uint32_t)__cvta_generic_to_shared(&s_bar[0]);
     if (tid == 0) {
-        mbar_init1(bar0);
-        mbar_init1(bar0 + 8);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        mbar_init(bar0, 1);
+        mbar_init(bar0 + 8, 1);
+        mbar_init_fence();
     }
 
     for (;;) {

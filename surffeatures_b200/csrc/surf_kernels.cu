@@ -19,6 +19,7 @@
 #include <cuda.h>
 
 #include "surf_internal.h"
+#include "surf_ptx.cuh"
 
 namespace surfb200 {
 
@@ -398,24 +399,6 @@ void launch_nms(const float *det, size_t det_frame, const uint32_t *sum, const u
 // pyramid is never written to HBM (B2/B3 of SURVEY.md section 8d shrink to O*A + 28 N).
 // Arithmetic is identical to k_hessian / k_nms (same box sums, same fp32/fp64 steps).
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_addr_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ bool tile_mbar_wait(uint32_t bar, uint32_t parity)
-{
-    uint32_t done = 0;
-    for (uint32_t spin = 0; !done; spin++) {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done)
-            : "r"(bar), "r"(parity)
-            : "memory");
-        if (spin > (1u << 24)) return false;  // a load that never lands must not hang the GPU
-    }
-    return true;
-}
-
 // box responses from the shared-memory tile; corner offsets are words relative to the sample's origin
 __device__ __forceinline__ void tile_responses(const int *__restrict__ o, const TileLayer &T, float &dx, float &dy, float &dc)
 {
@@ -456,7 +439,7 @@ __global__ void __launch_bounds__(kTileThreads) k_hessian_nms_tma(const __grid_c
 {
     extern __shared__ __align__(128) unsigned char tile_smem_raw[];
     // TMA tile destinations must be 128-byte aligned: align by hand (the launch reserves the slack)
-    unsigned char *tile_smem = tile_smem_raw + ((128u - (smem_addr_u32(tile_smem_raw) & 127u)) & 127u);
+    unsigned char *tile_smem = tile_smem_raw + ((128u - (smem_u32(tile_smem_raw) & 127u)) & 127u);
     int *s_tile = reinterpret_cast<int *>(tile_smem);                        // tile_h x tile_p words
     float *s_det = reinterpret_cast<float *>(tile_smem + oct.tile_bytes);    // [lpo][16][64]
     __shared__ __align__(8) uint64_t s_bar;
@@ -466,24 +449,21 @@ __global__ void __launch_bounds__(kTileThreads) k_hessian_nms_tma(const __grid_c
     const int b = blockIdx.z;
     const int j0 = blockIdx.x * (kTileW - 2), i0 = blockIdx.y * (kTileH - 2);  // first useful sample of the tile
     const int step = oct.step;
-    const uint32_t bar = smem_addr_u32(&s_bar);
+    const uint32_t bar = smem_u32(&s_bar);
     if (tid == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        mbar_init(bar, 1);
+        mbar_init_fence();
     }
     __syncthreads();
     if (tid == 0) {
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)oct.tile_bytes) : "memory");
+        mbar_expect_tx(bar, (uint32_t)oct.tile_bytes);
         // the innermost TMA coordinate must be 16-byte aligned: start at the word-aligned column at or
         // left of the tile origin (the tile pitch leaves room for the up-to-3-column shift)
         const int x0 = ((j0 - 1 - oct.m_max) * step) & ~3, y0 = (i0 - 1 - oct.m_max) * step;
-        asm volatile(
-            "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
-            ::"r"(smem_addr_u32(s_tile)), "l"(&tmap), "r"(x0), "r"(y0), "r"(b), "r"(bar)
-            : "memory");
+        tma_load_3d(&tmap, smem_u32(s_tile), x0, y0, b, bar);
     }
     const int xshift = ((j0 - 1 - oct.m_max) * step) & 3;
-    if (!tile_mbar_wait(bar, 0)) {  // reported as an error by the host; never silently wrong
+    if (!mbar_wait_bounded(bar, 0)) {  // reported as an error by the host; never silently wrong
         if (tid == 0) atomicOr(counts + gridDim.z, 1);  // status word right after the per-frame counters
         return;
     }
@@ -638,7 +618,7 @@ __global__ void __launch_bounds__(kTileThreads) k_hessian_nms_tma_c(const __grid
     using C = TileC<OCT, LPO>;
     constexpr int step = C::step;
     extern __shared__ __align__(128) unsigned char tile_smem_raw[];
-    unsigned char *tile_smem = tile_smem_raw + ((128u - (smem_addr_u32(tile_smem_raw) & 127u)) & 127u);
+    unsigned char *tile_smem = tile_smem_raw + ((128u - (smem_u32(tile_smem_raw) & 127u)) & 127u);
     int *s_tile = reinterpret_cast<int *>(tile_smem);
     float *s_det = reinterpret_cast<float *>(tile_smem + C::tile_bytes);
     __shared__ __align__(8) uint64_t s_bar;
@@ -648,22 +628,19 @@ __global__ void __launch_bounds__(kTileThreads) k_hessian_nms_tma_c(const __grid
     const int b = blockIdx.z;
     const int j0 = blockIdx.x * (kTileW - 2), i0 = blockIdx.y * (kTileH - 2);
     const int rows = H >> OCT, cols = W >> OCT;
-    const uint32_t bar = smem_addr_u32(&s_bar);
+    const uint32_t bar = smem_u32(&s_bar);
     if (tid == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        mbar_init(bar, 1);
+        mbar_init_fence();
     }
     __syncthreads();
     if (tid == 0) {
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)C::tile_bytes) : "memory");
+        mbar_expect_tx(bar, (uint32_t)C::tile_bytes);
         const int x0 = ((j0 - 1 - C::m_max) * step) & ~3, y0 = (i0 - 1 - C::m_max) * step;
-        asm volatile(
-            "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
-            ::"r"(smem_addr_u32(s_tile)), "l"(&tmap), "r"(x0), "r"(y0), "r"(b), "r"(bar)
-            : "memory");
+        tma_load_3d(&tmap, smem_u32(s_tile), x0, y0, b, bar);
     }
     const int xshift = ((j0 - 1 - C::m_max) * step) & 3;
-    if (!tile_mbar_wait(bar, 0)) {
+    if (!mbar_wait_bounded(bar, 0)) {
         if (tid == 0) atomicOr(counts + gridDim.z, 1);
         return;
     }

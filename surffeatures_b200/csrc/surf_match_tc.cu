@@ -19,6 +19,7 @@
 #include <cfloat>
 
 #include "surf_internal.h"
+#include "surf_ptx.cuh"
 
 namespace surfb200 {
 
@@ -29,40 +30,10 @@ constexpr uint32_t kTmemCols = 256;
 // ------------------------------------------------------------------------------------------------
 // PTX wrappers
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-
 // Bounded wait: a barrier that never completes traps instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
 {
-    uint32_t done = 0;
-    for (uint32_t spin = 0; !done; spin++) {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done)
-            : "r"(bar), "r"(parity)
-            : "memory");
-        if (spin > (1u << 26)) __trap();
-    }
-}
-
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-
-// TMA bulk copy (1-D, no tensor map): global -> shared, completion counted in bytes on an mbarrier.
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
-{
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
-                 : "memory");
+    if (!mbar_wait_bounded(bar, parity)) __trap();
 }
 
 __device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t cols)
@@ -78,7 +49,6 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols)
 
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // D[tmem] (+)= A[smem] * B[smem]^T, BF16 x BF16 -> FP32, issued by one thread for the CTA.
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
@@ -263,7 +233,7 @@ __global__ void __launch_bounds__(kCandThreads, (D == 64 && KC <= 4) ? 2 : 1) k_
     if (tid == 0) {
         mbar_init(bar_mma, 1);
         mbar_init(bar_ld, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        mbar_init_fence();
     }
     __syncwarp();
     if (warp == 0) tmem_alloc(smem_u32(&s_tmem), kTmemCols);

@@ -212,3 +212,36 @@ def test_db_many_exact_duplicates_take_the_grouped_redo_path(eng, oracle, dim, k
         assert eng.match_redo_count() == 7 and few.tobytes() == got[:7].tobytes()
     finally:
         db.close()
+
+
+def test_config5_full_size_database(eng, oracle):
+    """BASELINE config 5 at its full size on one GPU: 1 048 576 x 64 unit rows (added as 8 images of 131 072 rows,
+    the per-GPU shards of the multi-GPU layout), 4 096 queries = database rows + noise.  Size-independent
+    properties: every query's nearest row is its source row, the records are ascending, and a sample of queries
+    equals the oracle's exact scan of the whole database."""
+    from surffeatures_b200.engine import DescriptorDB
+
+    rng = np.random.default_rng(3)
+    n, shard = 1 << 20, 1 << 17
+    rows = np.abs(rng.standard_normal((n, 64), dtype=np.float32))
+    rows /= np.linalg.norm(rows, axis=1, keepdims=True)
+    src = rng.integers(0, n, 4096)
+    q = rows[src] + 0.05 * rng.standard_normal((4096, 64), dtype=np.float32)
+    q /= np.linalg.norm(q, axis=1, keepdims=True)
+    db = DescriptorDB(eng, 64, max_rows=n, max_images=8)
+    try:
+        db.add([rows[i * shard:(i + 1) * shard] for i in range(8)])
+        assert db.size() == (n, 8)
+        m = db.knnMatch(q, 2)
+        assert eng.match_redo_count() <= 8
+        g = m["imgIdx"].astype(np.int64) * shard + m["trainIdx"]
+        assert (g[:, 0] == src).all()
+        assert (m["distance"][:, 0] <= m["distance"][:, 1]).all()
+        good = m["distance"][:, 0] < np.float32(0.8) * m["distance"][:, 1]
+        assert good.mean() > 0.99                                   # the ratio test has its true positives
+        sel = np.arange(0, 4096, 128)
+        want = oracle.knn_match(q[sel], rows, 2)
+        assert np.array_equal(g[sel], want["trainIdx"])
+        assert np.allclose(m["distance"][sel], want["distance"], rtol=2e-6, atol=1e-7)
+    finally:
+        db.close()

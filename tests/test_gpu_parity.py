@@ -571,3 +571,30 @@ def test_odd_sizes_and_layer_counts(oracle, shape, thr, octaves, layers):
     for f in ("x", "y", "size", "angle", "response", "octave", "class_id"):
         assert np.array_equal(k[f], ok[f]), f
     assert np.linalg.norm(d - od, axis=1).max() <= 1e-4
+
+
+def test_config3_batched_1024_extended_upright(oracle):
+    """BASELINE config 3 shape (1024 x 1024, extended + upright, one batched call), at a batch the test box holds
+    in seconds: 8 distinct frames, each submitted twice.  Repeats must be byte-identical (frames are independent),
+    two frames are checked against the oracle, every angle is 270 and every descriptor has 128 unit-norm values."""
+    from surffeatures_b200 import SURF
+
+    frames = speckle.speckle_batch(8, 1024, 1024, 100)
+    batch = np.concatenate([frames, frames])
+    e = SURF(100, 4, 3, True, True, max_width=1024, max_height=1024, max_batch=16, max_keypoints=32768)
+    try:
+        kps, desc, off = e.detectAndComputeBatchPacked(batch)
+    finally:
+        e.close()
+    assert len(off) == 17 and desc.shape[1] == 128
+    for b in range(8):
+        a0, a1, b0, b1 = off[b], off[b + 1], off[b + 8], off[b + 9]
+        assert kps[a0:a1].tobytes() == kps[b0:b1].tobytes() and desc[a0:a1].tobytes() == desc[b0:b1].tobytes()
+    assert (kps["angle"] == 270.0).all()
+    assert np.allclose(np.linalg.norm(desc, axis=1), 1.0, atol=1e-5)
+    assert (off[1:] - off[:-1]).min() > 10000                       # ~17 k keypoints per 1024^2 speckle frame
+    P = oracle.params(100, 4, 3, True, True)
+    for b in (0, 7):
+        ok, od = oracle.detect_and_compute(frames[b], P)
+        assert kps[off[b]:off[b + 1]].tobytes() == ok.tobytes()
+        assert np.linalg.norm(desc[off[b]:off[b + 1]] - od, axis=1).max() <= 1e-4
