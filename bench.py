@@ -250,6 +250,8 @@ def run_ours(args):
         hb = hbuf[i & 1]
         src = h_pool[(i % POOL_BATCHES) * B:(i % POOL_BATCHES + 1) * B]
         eng.submit(src.data_ptr(), MEM_HOST, B, W_, H_, W_, W_ * H_, True)
+        nxt = h_pool[((i + 1) % POOL_BATCHES) * B:((i + 1) % POOL_BATCHES + 1) * B]
+        eng.prefetch(nxt.data_ptr(), B, W_, H_, W_, W_ * H_)   # next step's H2D runs under this step's kernels
         eng.wait_outputs()      # copies of step i-1 (other buffer set) have landed; this set is free again
         eng.collect(hb["kps"].data_ptr(), hb["desc"].data_ptr(), MEM_HOST, cap_total, offsets)
         n = int(offsets[B])

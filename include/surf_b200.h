@@ -124,6 +124,12 @@ int surf_submit_batch(surf_engine *e, const uint8_t *images, int in_mem, int bat
                       size_t pitch, size_t frame_stride, const uint8_t *mask, size_t mask_pitch, int want_descriptors);
 int surf_collect_batch(surf_engine *e, surf_keypoint *keypoints, float *descriptors, int out_mem, long capacity,
                        int32_t *offsets);
+/* Optional: starts the host->device copy of the NEXT batch's frames on its own stream, into a second frame
+ * buffer, while the batch in flight computes.  A following surf_submit_batch with the same host pointer and
+ * geometry (in_mem = SURF_MEM_HOST) uses those frames instead of uploading again; anything else discards
+ * them.  The host frames must stay unchanged until that submit's kernels have started. */
+int surf_prefetch_batch(surf_engine *e, const uint8_t *images, int batch, int width, int height, size_t pitch,
+                        size_t frame_stride);
 /* Device-resident results of the last submitted batch (valid until the next submit): packed
  * keypoints, packed descriptors, device int32 offsets[batch+1]. Requires surf_collect_batch or
  * surf_sync first if the host needs the counts. */

@@ -315,7 +315,7 @@ int check_params(surf_engine *e, const surf_params *p)
 
 void free_workspace(surf_engine *e)
 {
-    cudaFree(e->d_img); cudaFree(e->d_mask); cudaFree(e->d_sum); cudaFree(e->d_msum); cudaFree(e->d_bandsum);
+    cudaFree(e->d_img); cudaFree(e->d_img_next); cudaFree(e->d_mask); cudaFree(e->d_sum); cudaFree(e->d_msum); cudaFree(e->d_bandsum);
     cudaFree(e->d_det); cudaFree(e->d_kp_a); cudaFree(e->d_kp_b); cudaFree(e->d_out_kp); cudaFree(e->d_desc);
     cudaFree(e->d_out_desc); cudaFree(e->d_patches); cudaFree(e->d_counts); cudaFree(e->d_ndel);
     cudaFree(e->d_off_in); cudaFree(e->d_off_out); cudaFree(e->d_misc); cudaFree(e->d_deleted);
@@ -329,7 +329,7 @@ void free_workspace(surf_engine *e)
     cudaFree(e->d_prev_desc); cudaFree(e->d_prev_off); cudaFree(e->d_stream_matches); cudaFree(e->d_stream_good);
     e->d_prev_desc = nullptr; e->d_prev_off = nullptr; e->d_stream_matches = nullptr; e->d_stream_good = nullptr;
     if (e->h_pin) cudaFreeHost(e->h_pin);
-    e->d_img = e->d_mask = nullptr; e->d_sum = e->d_msum = e->d_bandsum = nullptr; e->d_det = nullptr;
+    e->d_img = e->d_img_next = e->d_mask = nullptr; e->prefetched.valid = false; e->d_sum = e->d_msum = e->d_bandsum = nullptr; e->d_det = nullptr;
     e->d_kp_a = e->d_kp_b = e->d_out_kp = nullptr; e->d_desc = e->d_out_desc = nullptr; e->d_patches = nullptr;
     e->d_counts = e->d_ndel = e->d_off_in = e->d_off_out = e->d_misc = e->d_deleted = nullptr;
     e->d_match_part = nullptr; e->d_match_io = nullptr; e->h_pin = nullptr; e->d_class_list = nullptr;
@@ -413,6 +413,28 @@ int check_frame_args(surf_engine *e, const BatchIn &in)
     return SURF_OK;
 }
 
+// Copies B host frames (any pitch / frame stride) into a dense device stack of pitch e->img_pitch.
+int upload_frames(surf_engine *e, const BatchIn &in, uint8_t *dst, cudaStream_t st)
+{
+    const size_t dp = e->img_pitch;
+    if (in.batch == 1 || in.frame_stride == in.pitch * (size_t)in.height) {
+        CU(e, cudaMemcpy2DAsync(dst, dp, in.images, in.pitch, in.width, (size_t)in.height * in.batch, cudaMemcpyHostToDevice, st));
+    } else if (in.frame_stride % in.pitch == 0) {
+        // a rectangle of every frame of a strided stack (e.g. the crop of an MHA sweep): one 3-D copy
+        cudaMemcpy3DParms p3{};
+        p3.srcPtr = make_cudaPitchedPtr((void *)in.images, in.pitch, in.width, in.frame_stride / in.pitch);
+        p3.dstPtr = make_cudaPitchedPtr(dst, dp, in.width, in.height);
+        p3.extent = make_cudaExtent(in.width, in.height, in.batch);
+        p3.kind = cudaMemcpyHostToDevice;
+        CU(e, cudaMemcpy3DAsync(&p3, st));
+    } else {
+        for (int b = 0; b < in.batch; b++)
+            CU(e, cudaMemcpy2DAsync(dst + (size_t)b * dp * in.height, dp, in.images + (size_t)b * in.frame_stride, in.pitch,
+                                    in.width, in.height, cudaMemcpyHostToDevice, st));
+    }
+    return SURF_OK;
+}
+
 // Uploads (or references) the frames; returns the device view.
 int stage_images(surf_engine *e, const BatchIn &in, ImageRef *ref)
 {
@@ -422,26 +444,28 @@ int stage_images(surf_engine *e, const BatchIn &in, ImageRef *ref)
         ref->frame_stride = in.frame_stride;
         return SURF_OK;
     }
-    const size_t dp = e->img_pitch;
-    if (in.batch == 1 || in.frame_stride == in.pitch * (size_t)in.height) {
-        CU(e, cudaMemcpy2DAsync(e->d_img, dp, in.images, in.pitch, in.width, (size_t)in.height * in.batch,
-                                cudaMemcpyHostToDevice, e->stream));
-    } else if (in.frame_stride % in.pitch == 0) {
-        // a rectangle of every frame of a strided stack (e.g. the crop of an MHA sweep): one 3-D copy
-        cudaMemcpy3DParms p3{};
-        p3.srcPtr = make_cudaPitchedPtr((void *)in.images, in.pitch, in.width, in.frame_stride / in.pitch);
-        p3.dstPtr = make_cudaPitchedPtr(e->d_img, dp, in.width, in.height);
-        p3.extent = make_cudaExtent(in.width, in.height, in.batch);
-        p3.kind = cudaMemcpyHostToDevice;
-        CU(e, cudaMemcpy3DAsync(&p3, e->stream));
+    surf_engine::Prefetched &pf = e->prefetched;
+    if (pf.valid && pf.images == in.images && pf.batch == in.batch && pf.width == in.width && pf.height == in.height &&
+        pf.pitch == in.pitch && pf.frame_stride == in.frame_stride) {
+        // these frames are already on their way (surf_prefetch_batch): swap the buffers, wait on the device only
+        uint8_t *t = e->d_img;
+        e->d_img = e->d_img_next;
+        e->d_img_next = t;
+        cudaEvent_t te = e->ev_free_cur;
+        e->ev_free_cur = e->ev_free_next;
+        e->ev_free_next = te;
+        const bool tr = e->free_cur_recorded;
+        e->free_cur_recorded = e->free_next_recorded;
+        e->free_next_recorded = tr;
+        CU(e, cudaStreamWaitEvent(e->stream, e->ev_upload_done, 0));
     } else {
-        for (int b = 0; b < in.batch; b++)
-            CU(e, cudaMemcpy2DAsync(e->d_img + (size_t)b * dp * in.height, dp, in.images + (size_t)b * in.frame_stride,
-                                    in.pitch, in.width, in.height, cudaMemcpyHostToDevice, e->stream));
+        int rc = upload_frames(e, in, e->d_img, e->stream);
+        if (rc) return rc;
     }
+    pf.valid = false;
     ref->ptr = e->d_img;
-    ref->pitch = dp;
-    ref->frame_stride = dp * in.height;
+    ref->pitch = e->img_pitch;
+    ref->frame_stride = e->img_pitch * in.height;
     return SURF_OK;
 }
 
@@ -642,6 +666,10 @@ int surf_create(const surf_params *params, int device, int max_width, int max_he
     cudaEventCreateWithFlags(&e->ev_copy_done, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&e->ev_match_copy_done, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&e->ev_ready, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&e->ev_upload_done, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&e->ev_free_cur, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&e->ev_free_next, cudaEventDisableTiming);
+    cudaStreamCreateWithFlags(&e->upload_stream, cudaStreamNonBlocking);
     upload_tables();
     rc = alloc_workspace(e);
     if (rc == SURF_OK && cudaGetLastError() != cudaSuccess) rc = SURF_ERR_CUDA;
@@ -675,6 +703,13 @@ void surf_destroy(surf_engine *e)
     if (e->ev_copy_done) cudaEventDestroy(e->ev_copy_done);
     if (e->ev_match_copy_done) cudaEventDestroy(e->ev_match_copy_done);
     if (e->ev_ready) cudaEventDestroy(e->ev_ready);
+    if (e->ev_upload_done) cudaEventDestroy(e->ev_upload_done);
+    if (e->ev_free_cur) cudaEventDestroy(e->ev_free_cur);
+    if (e->ev_free_next) cudaEventDestroy(e->ev_free_next);
+    if (e->upload_stream) {
+        cudaStreamSynchronize(e->upload_stream);
+        cudaStreamDestroy(e->upload_stream);
+    }
     if (e->stream) cudaStreamDestroy(e->stream);
     delete e;
 }
@@ -740,9 +775,32 @@ int surf_submit_batch(surf_engine *e, const uint8_t *images, int in_mem, int bat
     if ((rc = run_detect(e, img, msum, geo, batch))) return rc;
     if ((rc = run_describe_pack(e, img, geo, batch, want_descriptors != 0, nullptr, true))) return rc;
     if ((rc = fetch_counts(e, batch))) return rc;
+    if (in_mem == SURF_MEM_HOST) {  // the staged frames (d_img) are free again after these kernels
+        CU(e, cudaEventRecord(e->ev_free_cur, e->stream));
+        e->free_cur_recorded = true;
+    }
     e->pending.active = true;
     e->pending.batch = batch;
     e->pending.want_desc = want_descriptors != 0;
+    return SURF_OK;
+}
+
+int surf_prefetch_batch(surf_engine *e, const uint8_t *images, int batch, int width, int height, size_t pitch,
+                        size_t frame_stride)
+{
+    BatchIn in{images, SURF_MEM_HOST, batch, width, height, pitch, frame_stride, nullptr, 0};
+    int rc = check_frame_args(e, in);
+    if (rc) return rc;
+    if ((rc = ensure_device(e))) return rc;
+    if (!e->d_img_next) CU(e, cudaMalloc(&e->d_img_next, e->img_pitch * e->max_h * e->max_b));
+    // the upload may start as soon as the last kernels that read this buffer (two batches ago) have ended; it
+    // overlaps the kernels of the batch in flight, which read the other buffer.  The host does not wait.
+    if (e->free_next_recorded) CU(e, cudaStreamWaitEvent(e->upload_stream, e->ev_free_next, 0));
+    if ((rc = upload_frames(e, in, e->d_img_next, e->upload_stream))) return rc;
+    CU(e, cudaEventRecord(e->ev_upload_done, e->upload_stream));
+    surf_engine::Prefetched &pf = e->prefetched;
+    pf.images = images; pf.batch = batch; pf.width = width; pf.height = height; pf.pitch = pitch;
+    pf.frame_stride = frame_stride; pf.valid = true;
     return SURF_OK;
 }
 

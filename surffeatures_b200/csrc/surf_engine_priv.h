@@ -39,6 +39,20 @@ struct surf_engine {
 
     // workspace
     uint8_t *d_img = nullptr;   size_t img_pitch = 0;
+    // surf_prefetch_batch: the next batch's frames are uploaded on their own stream into the second frame buffer
+    // while the current batch computes; surf_submit_batch of the same host frames then swaps the buffers
+    uint8_t *d_img_next = nullptr;
+    cudaStream_t upload_stream = nullptr;
+    cudaEvent_t ev_upload_done = nullptr;
+    // end of the last kernels that read d_img / d_img_next (swapped together with the buffers)
+    cudaEvent_t ev_free_cur = nullptr, ev_free_next = nullptr;
+    bool free_cur_recorded = false, free_next_recorded = false;
+    struct Prefetched {
+        const uint8_t *images = nullptr;
+        int batch = 0, width = 0, height = 0;
+        size_t pitch = 0, frame_stride = 0;
+        bool valid = false;
+    } prefetched;
     uint8_t *d_mask = nullptr;
     uint32_t *d_sum = nullptr, *d_msum = nullptr, *d_bandsum = nullptr;
     float *d_det = nullptr;     size_t det_words = 0;

@@ -32,7 +32,7 @@ MEM_HOST, MEM_DEVICE = 0, 1
 ABI_SYMBOLS = [
     "surf_create", "surf_destroy", "surf_set_params", "surf_get_params", "surf_last_error", "surf_required_capacity",
     "surf_descriptor_size", "surf_get_timings", "surf_stream", "surf_detect", "surf_compute", "surf_detect_and_compute",
-    "surf_detect_and_compute_batch", "surf_submit_batch", "surf_collect_batch", "surf_device_results", "surf_sync",
+    "surf_detect_and_compute_batch", "surf_submit_batch", "surf_prefetch_batch", "surf_collect_batch", "surf_device_results", "surf_sync",
     "surf_integral", "surf_hessian_layer", "surf_raw_keypoints", "surf_describe_keypoints", "surf_match_knn",
     "surf_match_ratio", "surf_merge_topk", "surf_version", "surf_match_prev", "surf_stream_reset",
     "surf_device_matches", "surf_set_match_mode", "surf_match_redo_count", "surf_set_async_outputs",
@@ -100,6 +100,7 @@ def load_library():
     L.surf_detect_and_compute_batch.argtypes = [vp, vp, i32, i32, i32, i32, sz, sz, vp, sz, vp, vp, i32, lng, vp]
     L.surf_submit_batch.argtypes = [vp, vp, i32, i32, i32, i32, sz, sz, vp, sz, i32]
     L.surf_collect_batch.argtypes = [vp, vp, vp, i32, lng, vp]
+    L.surf_prefetch_batch.argtypes = [vp, vp, i32, i32, i32, sz, sz]
     L.surf_device_results.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
     L.surf_sync.argtypes = [vp]
     L.surf_integral.argtypes = [vp, vp, i32, i32, sz, i32, vp]
@@ -293,6 +294,11 @@ class SURF:
                want_descriptors: bool = True, mask_ptr: int = 0, mask_pitch: int = 0):
         self._check(self._lib.surf_submit_batch(self._h, images_ptr, in_mem, B, W, H, pitch, frame_stride,
                                                 mask_ptr or None, mask_pitch, int(want_descriptors)))
+
+    def prefetch(self, images_ptr: int, B: int, W: int, H: int, pitch: int, frame_stride: int):
+        """Starts the upload of the NEXT batch's host frames while the submitted batch computes; the following
+        submit() of the same pointer and geometry uses them (surf_prefetch_batch)."""
+        self._check(self._lib.surf_prefetch_batch(self._h, images_ptr, B, W, H, pitch, frame_stride))
 
     def collect(self, kps_ptr: int, desc_ptr: int, out_mem: int, capacity: int, offsets: np.ndarray):
         self._check(self._lib.surf_collect_batch(self._h, kps_ptr or None, desc_ptr or None, out_mem, capacity,

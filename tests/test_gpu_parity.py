@@ -549,6 +549,43 @@ def test_device_frames_with_unaligned_pitch_take_the_fallback_path(oracle):
         e.close()
 
 
+def test_prefetched_upload_gives_identical_results():
+    """surf_prefetch_batch uploads batch i+1 on its own stream while batch i computes; the results must be the
+    bytes of the plain path, and a submit of OTHER frames must discard the prefetched ones."""
+    import torch
+
+    from surffeatures_b200 import KEYPOINT_DTYPE, MEM_HOST, SURF
+
+    frames = speckle.speckle_stream(8, 240, 320, seed=21, fresh=0.0)
+    e = SURF(100, 4, 3, max_width=320, max_height=240, max_batch=2, max_keypoints=4096)
+    try:
+        ref = [e.detectAndComputeBatchPacked(frames[2 * i:2 * i + 2]) for i in range(4)]
+        ref = [(k.copy(), d.copy(), o.copy()) for k, d, o in ref]
+        pinned = torch.from_numpy(frames).pin_memory()
+        cap = 2 * 4096
+        k = torch.zeros((cap, 7), dtype=torch.float32).pin_memory()
+        d = torch.zeros((cap, 64), dtype=torch.float32).pin_memory()
+        off = np.zeros(3, np.int32)
+
+        def batch_ptr(i):
+            return pinned[2 * i:2 * i + 2].data_ptr()
+
+        # order 0, 1, 2 with every next batch prefetched; then prefetch 0 but submit 3 (must discard)
+        plan = [(0, 1), (1, 2), (2, 0), (3, None)]
+        for cur, nxt in plan:
+            e.submit(batch_ptr(cur), MEM_HOST, 2, 320, 240, 320, 320 * 240, True)
+            if nxt is not None:
+                e.prefetch(batch_ptr(nxt), 2, 320, 240, 320, 320 * 240)
+            e.collect(k.data_ptr(), d.data_ptr(), MEM_HOST, cap, off)
+            rk, rd, ro = ref[cur]
+            n = int(off[-1])
+            assert np.array_equal(off, ro)
+            assert k.numpy()[:n].copy().view(KEYPOINT_DTYPE).reshape(-1).tobytes() == rk.tobytes()
+            assert np.array_equal(d.numpy()[:n], rd)
+    finally:
+        e.close()
+
+
 @pytest.mark.parametrize("shape,thr,octaves,layers", [((251, 333), 100, 4, 3), ((333, 251), 200, 3, 1),
                                                       ((480, 640), 300, 4, 4), ((200, 1000), 100, 2, 2),
                                                       ((640, 480), 100, 5, 2)])
