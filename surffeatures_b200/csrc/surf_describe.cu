@@ -299,6 +299,7 @@ struct DescShared {  // static shared state of one descriptor CTA
     float vec[128];
     float scale;
     int work;
+    int inexact;  // a row start of this window is not a multiple of 2^-32: fp64 tap coordinates
 };
 
 // One TMA box load of the 8-bit frame b at (x, y) (x 16-byte aligned) into shared memory.
@@ -348,17 +349,177 @@ __device__ __forceinline__ unsigned rotated_tap(double fx, double fy, int W, int
     return src((y - y0) * TP + (x - x0));
 }
 
+// ------------------------------------------------------------------------------------------------
+// Fixed-point taps.  The reference walks a window row as `double pixel_x = start_x; pixel_x += cos_dir` with
+// float start_x / cos_dir.  When both are multiples of 2^-32 (|v| >= 2^-9 or v == 0: every keypoint except
+// the ~0.3 % whose direction is within 0.11 degrees of an axis) that sum is exact in fp64 AND in a 64-bit
+// integer with 32 fraction bits.  In the integer form floor() is the high word, and the fraction's
+// conversion to float (one round-to-nearest of a 32-bit integer) is the reference's `(float)(pixel_x - ix)`
+// scaled by 2^32.  The scale is a power of two, so every product and sum below rounds exactly as the
+// reference's; it is removed by the final fused multiply-add with 1.5 * 2^23 (cvRound to the low byte).
+// Cost per tap: 4 integer adds + 2 conversions instead of 8 fp64 additions and 2 fp64->fp32 conversions.
+// Shared memory is addressed with raw 32-bit shared-window addresses (ld/st.shared through inline PTX):
+// with generic pointers into the dynamic allocation the compiler re-derives the window base inside the loop.
+// ------------------------------------------------------------------------------------------------
+template <int OFF>
+__device__ __forceinline__ uint32_t lds_u8(uint32_t addr)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1+%2];" : "=r"(v) : "r"(addr), "n"(OFF));
+    return v;
+}
+__device__ __forceinline__ float lds_f32(uint32_t addr)
+{
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts_u8(uint32_t addr, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(addr), "r"(v)); }
+__device__ __forceinline__ void sts_f32(uint32_t addr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v)); }
+// keeps a loop-invariant value in a register (the compiler would otherwise rematerialise it per use)
+__device__ __forceinline__ uint32_t pin_reg(uint32_t v)
+{
+    asm volatile("" : "+r"(v));
+    return v;
+}
+
+// uchar -> float as one I2FP instruction (measured: 6.43 ms per 64 frames against 6.61 ms with the two-instruction
+// 2^23 trick of u8f)
+__device__ __forceinline__ float tap_u8f(uint32_t v) { return __uint2float_rn(v); }
+
+// float (multiple of 2^-32, |v| < 2^31) -> signed 32.32 fixed point, exact
+__device__ __forceinline__ long long fix32(float v) { return __double2ll_rn((double)v * 4294967296.0); }
+__device__ __forceinline__ bool fix32_exact(float v) { return v == 0.f || fabsf(v) >= 0.001953125f; }
+
+// Interior tap: X's high word already carries (tile address - x0), Y's high word (-y0).
+template <int TP>
+__device__ __forceinline__ uint32_t tap_fixed(long long X, long long Y)
+{
+    const float a = __uint2float_rn((uint32_t)X), b = __uint2float_rn((uint32_t)Y);  // fractions * 2^32
+    const float na = 4294967296.f - a, nb = 4294967296.f - b;
+    const uint32_t q = (uint32_t)((int)(Y >> 32) * TP + (int)(X >> 32));
+    const float p00 = tap_u8f(lds_u8<0>(q)), p01 = tap_u8f(lds_u8<1>(q));
+    const float p10 = tap_u8f(lds_u8<TP>(q)), p11 = tap_u8f(lds_u8<TP + 1>(q));
+    const float t = p00 * na * nb + p01 * a * nb + p10 * na * b + p11 * a * b;  // value * 2^64
+    return __float_as_uint(__fmaf_rn(t, 5.421010862427522e-20f, 12582912.0f));  // low byte = cvRound(value)
+}
+
+// Tap of a window that may leave the interpolable area: X, Y are the true coordinates.
+template <int TP>
+__device__ __forceinline__ uint32_t tap_fixed_checked(long long X, long long Y, int W1, int H1, int x0, int y0, uint32_t tile)
+{
+    const int ix = (int)(X >> 32), iy = (int)(Y >> 32);
+    const uint32_t xl = (uint32_t)X, yl = (uint32_t)Y;
+    if ((unsigned)ix < (unsigned)W1 && (unsigned)iy < (unsigned)H1) {
+        const float a = __uint2float_rn(xl), b = __uint2float_rn(yl);
+        const float na = 4294967296.f - a, nb = 4294967296.f - b;
+        const uint32_t q = tile + (uint32_t)((iy - y0) * TP + (ix - x0));
+        const float p00 = tap_u8f(lds_u8<0>(q)), p01 = tap_u8f(lds_u8<1>(q));
+        const float p10 = tap_u8f(lds_u8<TP>(q)), p11 = tap_u8f(lds_u8<TP + 1>(q));
+        const float t = p00 * na * nb + p01 * a * nb + p10 * na * b + p11 * a * b;
+        return __float_as_uint(__fmaf_rn(t, 5.421010862427522e-20f, 12582912.0f));
+    }
+    // cvRound (nearest, ties to even) of the coordinate, clamped into the frame
+    const int rx = ix + (int)(xl > 0x80000000u || (xl == 0x80000000u && (ix & 1)));
+    const int ry = iy + (int)(yl > 0x80000000u || (yl == 0x80000000u && (iy & 1)));
+    const int x = min(max(rx, 0), W1), y = min(max(ry, 0), H1);
+    return lds_u8<0>(tile + (uint32_t)((y - y0) * TP + (x - x0)));
+}
+
+// Rows [i0, i1) x columns [j0, j1) of the rotated window from the shared-memory frame tile at `tile`
+// (origin (x0, y0), pitch TP).  A warp covers 4 rows x 8 columns per step.  The window goes to shared memory
+// (win_s, GLOBAL = false) or to the per-CTA global scratch (win_g).
+template <int TP, int NW, bool CHECK, bool GLOBAL>
+__device__ __forceinline__ void window_taps_fixed(int n, int i0, int i1, int j0, int j1, const float *rsx, const float *rsy,
+                                                  long long cdq, long long sdq, uint32_t tile, int x0, int y0, int W, int H,
+                                                  uint32_t win_s, unsigned char *win_g)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lj = lane & 7, li = lane >> 3;
+    const long long sx8 = 8 * cdq, sy8 = 8 * sdq;
+    const long long xbias = CHECK ? 0ll : ((long long)(int)(tile - (uint32_t)x0)) << 32;
+    const long long ybias = CHECK ? 0ll : ((long long)(-y0)) << 32;
+    const long long lane_x = (long long)(j0 + lj) * cdq + xbias, lane_y = (long long)(j0 + lj) * sdq - ybias;
+    const int W1 = W - 1, H1 = H - 1;
+    for (int i = i0 + warp * 4 + li; i < i1; i += NW * 4) {
+        long long X = fix32(rsx[i]) + lane_x, Y = fix32(rsy[i]) - lane_y;
+        int j = j0 + lj;
+        const int o = i * n;
+        for (; j + 8 < j1; j += 16, X += 2 * sx8, Y -= 2 * sy8) {
+            uint32_t v0, v1;
+            if (CHECK) {
+                v0 = tap_fixed_checked<TP>(X, Y, W1, H1, x0, y0, tile);
+                v1 = tap_fixed_checked<TP>(X + sx8, Y - sy8, W1, H1, x0, y0, tile);
+            } else {
+                v0 = tap_fixed<TP>(X, Y);
+                v1 = tap_fixed<TP>(X + sx8, Y - sy8);
+            }
+            if (GLOBAL) {
+                win_g[o + j] = (unsigned char)v0;
+                win_g[o + j + 8] = (unsigned char)v1;
+            } else {
+                sts_u8(win_s + o + j, v0);
+                sts_u8(win_s + o + j + 8, v1);
+            }
+        }
+        if (j < j1) {
+            const uint32_t v0 = CHECK ? tap_fixed_checked<TP>(X, Y, W1, H1, x0, y0, tile) : tap_fixed<TP>(X, Y);
+            if (GLOBAL) win_g[o + j] = (unsigned char)v0; else sts_u8(win_s + o + j, v0);
+        }
+    }
+}
+
 // From the n x n window (`win`, shared or global) to the descriptor: INTER_AREA to 21 x 21, 2x2 Haar gradients,
 // 4x4 sub-region sums, normalisation.  `buf` holds n x 21 floats (row sums of the fractional resize).
-template <int THREADS>
+// One weight per source pixel of INTER_AREA cell d: first / middle / last as the table says, 0 past the end.
+template <int MAXC>
+__device__ __forceinline__ void cell_weights(const AreaTab &t, int d, float (&w)[MAXC])
+{
+    const int c = t.count[d];
+    const bool hf = t.has_first[d], hl = t.has_last[d];
+    const float af = t.a_first[d], am = t.a_mid[d], al = t.a_last[d];
+#pragma unroll
+    for (int k = 0; k < MAXC; k++) w[k] = k >= c ? 0.f : ((k == 0 && hf) ? af : ((k == c - 1 && hl) ? al : am));
+}
+
+// MAXC > 0: the window and the row sums live in shared memory (addresses win_addr / buf_addr) and no cell of
+// the resize table touches more than MAXC source pixels; MAXC == 0: any window (global scratch), generic loops.
+template <int THREADS, int MAXC>
 __device__ __forceinline__ void descriptor_tail(const DescribeArgs &A, int kidx, int n, const unsigned char *win, float *buf,
-                                                DescShared &S, bool int_scale, int isc)
+                                                uint32_t win_addr, uint32_t buf_addr, DescShared &S, bool int_scale, int isc)
 {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int D = A.extended ? 128 : 64;
     // Fractional scales run the reference's two passes: row sums buf[sy][dx] = sum_x win[sy][x] * alpha (fp32,
     // table order), then the column pass.  Thread = (row group, dx): the dx entry of the table stays in registers.
-    if (!int_scale) {
+    if (!int_scale && MAXC > 0) {
+        // Fixed trip count: weights beyond the cell's pixel count are 0 and `b + p * 0 == b` exactly (the extra
+        // reads stay inside the CTA's shared memory; any byte is a finite number).
+        constexpr int G = THREADS / kPatch;
+        constexpr int M = MAXC > 0 ? MAXC : 1;
+        if (tid < G * kPatch) {
+            const int g = tid / kPatch, dx = tid - g * kPatch;
+            if (S.tab.count[dx] > M) atomicOr(A.misc + kMiscStatus, 2);  // table bound violated: reported by the host
+            float w[M];
+            cell_weights<M>(S.tab, dx, w);
+            uint32_t ra = win_addr + g * n + S.tab.start[dx], ba = buf_addr + (g * kPatch + dx) * 4;
+            const uint32_t rstep = G * n;
+#pragma unroll 2
+            for (int sy = g; sy < n; sy += G, ra += rstep, ba += G * kPatch * 4) {
+                float b = tap_u8f(lds_u8<0>(ra)) * w[0];
+                if (M > 1) b += tap_u8f(lds_u8<1 % M>(ra)) * w[1 % M];
+                if (M > 2) b += tap_u8f(lds_u8<2 % M>(ra)) * w[2 % M];
+                if (M > 3) b += tap_u8f(lds_u8<3 % M>(ra)) * w[3 % M];
+                if (M > 4) b += tap_u8f(lds_u8<4 % M>(ra)) * w[4 % M];
+                if (M > 5) b += tap_u8f(lds_u8<5 % M>(ra)) * w[5 % M];
+                if (M > 6) b += tap_u8f(lds_u8<6 % M>(ra)) * w[6 % M];
+                if (M > 7) b += tap_u8f(lds_u8<7 % M>(ra)) * w[7 % M];
+                static_assert(M <= 8, "extend the unrolled row pass");
+                sts_f32(ba, b);
+            }
+        }
+        __syncthreads();
+    } else if (!int_scale) {
         constexpr int G = THREADS / kPatch;
         if (tid < G * kPatch) {
             const int g = tid / kPatch, dx = tid - g * kPatch;
@@ -396,6 +557,16 @@ __device__ __forceinline__ void descriptor_tail(const DescribeArgs &A, int kidx,
             }
             const float wgt = 1.f / (isc * isc);
             outv = sat_u8(acc * wgt);
+        } else if (MAXC > 0) {
+            constexpr int M = MAXC > 0 ? MAXC : 1;
+            float v[M];
+            cell_weights<M>(S.tab, dy, v);
+            const int ys = S.tab.start[dy];
+            float acc = 0;
+#pragma unroll
+            for (int e = 0; e < M; e++)  // rows past the window are clamped: their weight is 0, the value finite
+                acc += v[e] * lds_f32(buf_addr + (min(ys + e, n - 1) * kPatch + dx) * 4);
+            outv = sat_u8(acc);
         } else {
             const int ys = S.tab.start[dy], yc = S.tab.count[dy];
             const bool yhf = S.tab.has_first[dy], yhl = S.tab.has_last[dy];
@@ -483,7 +654,9 @@ struct ClassT {
     static constexpr int tp = (side + 15 + 15) & ~15;
     static constexpr int tr = side;
     static constexpr int win_bytes = (max_n * max_n + 127) & ~127;
-    static constexpr int smem = 128 + max_n * 16 + win_bytes + tp * tr;
+    static constexpr int smem = 128 + max_n * 8 + win_bytes + tp * tr;
+    // most source pixels one INTER_AREA cell can touch (table maximum over every n of the class; checked on the device)
+    static constexpr int max_cell = CLS == 0 ? 4 : CLS == 1 ? 6 : 8;
 };
 
 // Sub-window kernel: tiles sized for sub-windows of at most kSubSide taps per side (the class-1 tile).
@@ -493,7 +666,7 @@ struct BigT {
     static constexpr int tp = ClassT<1>::tp, tr = ClassT<1>::tr;
     static constexpr int tile_bytes = tp * tr;
     static constexpr int tile_stride = (tile_bytes + 127) & ~127;  // TMA destinations are 128-byte aligned
-    static constexpr int smem = 128 + 2 * tile_stride + kMaxWindow * 16;
+    static constexpr int smem = 128 + 2 * tile_stride + kMaxWindow * 8;
 };
 
 // frame-tile fallback when the frames are not 16-byte aligned (no TMA): asynchronous 4-byte copies
@@ -531,12 +704,13 @@ __global__ void __launch_bounds__(ClassT<CLS>::threads) k_descriptor(const __gri
     constexpr int max_n = CT::max_n, tp = CT::tp;
     extern __shared__ __align__(128) unsigned char dyn_raw[];
     // dynamic layout (128-byte aligned by hand: TMA destinations need it):
-    //   uchar tile[tr][tp] | uchar win[max_n^2] | double rsx[max_n], rsy[max_n]
+    //   uchar tile[tr][tp] | uchar win[max_n^2] | float rsx[max_n], rsy[max_n]
     unsigned char *dyn = dyn_raw + ((128u - ((uint32_t)__cvta_generic_to_shared(dyn_raw) & 127u)) & 127u);
     unsigned char *s_tile = dyn;
     unsigned char *s_win = dyn + tp * CT::tr;
-    double *s_rsx = reinterpret_cast<double *>(s_win + CT::win_bytes);
-    double *s_rsy = s_rsx + max_n;
+    float *s_rsx = reinterpret_cast<float *>(s_win + CT::win_bytes);
+    float *s_rsy = s_rsx + max_n;
+    const uint32_t tile_addr = pin_reg(smem_u32(s_tile)), win_addr = pin_reg(smem_u32(s_win));
     __shared__ __align__(8) uint64_t s_bar;
     __shared__ DescShared S;
     uint32_t tma_phase = 0;
@@ -554,7 +728,10 @@ __global__ void __launch_bounds__(ClassT<CLS>::threads) k_descriptor(const __gri
 
     for (;;) {
         __syncthreads();  // everyone is done with the previous keypoint's shared state
-        if (tid == 0) S.work = atomicAdd(A.misc + kMiscClassHead + CLS, 1);
+        if (tid == 0) {
+            S.work = atomicAdd(A.misc + kMiscClassHead + CLS, 1);
+            S.inexact = 0;
+        }
         __syncthreads();
         const int work = S.work;
         if (work >= count) break;
@@ -572,6 +749,7 @@ __global__ void __launch_bounds__(ClassT<CLS>::threads) k_descriptor(const __gri
         float sd = 1.f, cd = 0.f;
         int ux0 = 0, uy0 = 0;  // upright: integer window origin
         int tx0, tx1, ty0, ty1;
+        bool interior = false;  // every tap has its four neighbours inside the frame
         if (A.upright) {
             ux0 = __float2int_rn(cx + off);
             uy0 = __float2int_rn(cy - off);
@@ -592,10 +770,13 @@ __global__ void __launch_bounds__(ClassT<CLS>::threads) k_descriptor(const __gri
             const float ya = sy0, yb = sy0 + ext * cd, yc2 = sy0 - ext * sd, yd = yb - ext * sd;
             const float minx = fminf(fminf(xa, xb), fminf(xc2, xd)) - 1.f, maxx = fmaxf(fmaxf(xa, xb), fmaxf(xc2, xd)) + 1.f;
             const float miny = fminf(fminf(ya, yb), fminf(yc2, yd)) - 1.f, maxy = fmaxf(fmaxf(ya, yb), fmaxf(yc2, yd)) + 1.f;
-            tx0 = min(max(__float2int_rd(minx), 0), W - 1);
-            tx1 = min(max(__float2int_rd(maxx) + 1, 0), W - 1);
-            ty0 = min(max(__float2int_rd(miny), 0), H - 1);
-            ty1 = min(max(__float2int_rd(maxy) + 1, 0), H - 1);
+            const int bx0 = __float2int_rd(minx), bx1 = __float2int_rd(maxx) + 1;
+            const int by0 = __float2int_rd(miny), by1 = __float2int_rd(maxy) + 1;
+            interior = bx0 >= 0 && by0 >= 0 && bx1 <= W - 1 && by1 <= H - 1;
+            tx0 = min(max(bx0, 0), W - 1);
+            tx1 = min(max(bx1, 0), W - 1);
+            ty0 = min(max(by0, 0), H - 1);
+            ty1 = min(max(by1, 0), H - 1);
         }
         const int tx0a = tx0 & ~15;              // tile origin aligned down to 16 bytes (TMA / vector copies)
         const int th_rows = ty1 - ty0 + 1;
@@ -623,8 +804,13 @@ __global__ void __launch_bounds__(ClassT<CLS>::threads) k_descriptor(const __gri
             // is in flight
             float v = tid == 0 ? cx + off * cd + off * sd : cy - off * sd + off * cd;
             const float inc = tid == 0 ? sd : cd;
-            double *dst = tid == 0 ? s_rsx : s_rsy;
-            for (int i = 0; i < n; i++, v += inc) dst[i] = (double)v;
+            float *dst = tid == 0 ? s_rsx : s_rsy;
+            bool exact = true;  // every row start is a multiple of 2^-32 (fixed-point taps apply)
+            for (int i = 0; i < n; i++, v += inc) {
+                dst[i] = v;
+                exact = exact && fix32_exact(v);
+            }
+            if (!exact) S.inexact = 1;
         }
         if (use_tma) {
             if (!mbar_wait_bounded(bar, tma_phase) && tid == 0) atomicOr(A.misc + kMiscStatus, 4);  // reported by the host
@@ -642,24 +828,30 @@ __global__ void __launch_bounds__(ClassT<CLS>::threads) k_descriptor(const __gri
                     s_win[i * n + j] = (unsigned char)SRC(y * tp + x);
                 }
             }
+        } else if (!S.inexact && fix32_exact(cd) && fix32_exact(sd)) {
+            // 32.32 fixed-point coordinates (exact here); interior windows skip the per-tap frame test
+            const long long cdq = fix32(cd), sdq = fix32(sd);
+            if (interior)
+                window_taps_fixed<tp, NW, false, false>(n, 0, n, 0, n, s_rsx, s_rsy, cdq, sdq, tile_addr, tx0a, ty0, W, H, win_addr, nullptr);
+            else
+                window_taps_fixed<tp, NW, true, false>(n, 0, n, 0, n, s_rsx, s_rsy, cdq, sdq, tile_addr, tx0a, ty0, W, H, win_addr, nullptr);
         } else {
-            // a warp covers 1 row x 32 columns of the window (n <= 32) or 4 rows x 8 columns: far fewer idle
-            // lanes at the end of a row than 32-wide strips
-            const int rows_w = n > 32 ? 4 : 1, cols_w = 32 / rows_w;
-            const int lj = lane & (cols_w - 1), li = lane / cols_w;
+            // direction within 0.11 degrees of an axis, or a row start inside (-2^-9, 2^-9): fp64 coordinates.
+            // A warp covers 4 rows x 8 columns of the window.
+            const int lj = lane & 7, li = lane >> 3;
             const double lane_dx = (double)lj * (double)cd, lane_dy = (double)lj * (double)sd;
-            const double step_x = (double)cols_w * (double)cd, step_y = (double)cols_w * (double)sd;
-            for (int i = warp * rows_w + li; i < n; i += NW * rows_w) {
-                double fx = s_rsx[i] + lane_dx;  // start + j * step, exact in fp64
-                double fy = s_rsy[i] - lane_dy;
+            const double step_x = 8.0 * (double)cd, step_y = 8.0 * (double)sd;
+            for (int i = warp * 4 + li; i < n; i += NW * 4) {
+                double fx = (double)s_rsx[i] + lane_dx;  // start + j * step, exact in fp64
+                double fy = (double)s_rsy[i] - lane_dy;
                 unsigned char *wrow = s_win + i * n;
-                for (int j = lj; j < n; j += cols_w, fx += step_x, fy -= step_y)
+                for (int j = lj; j < n; j += 8, fx += step_x, fy -= step_y)
                     wrow[j] = (unsigned char)rotated_tap(fx, fy, W, H, tx0a, ty0, tp, SRC);
             }
         }
         __syncthreads();
         // the image tile is no longer needed: its space holds the row sums of the resize
-        descriptor_tail<THREADS>(A, kidx, n, s_win, reinterpret_cast<float *>(s_tile), S, int_scale, isc);
+        descriptor_tail<THREADS, CT::max_cell>(A, kidx, n, s_win, reinterpret_cast<float *>(s_tile), win_addr, tile_addr, S, int_scale, isc);
     }
 }
 
@@ -672,8 +864,9 @@ __global__ void __launch_bounds__(BigT::threads) k_descriptor_big(const __grid_c
     extern __shared__ __align__(128) unsigned char dyn_raw[];
     unsigned char *dyn = dyn_raw + ((128u - ((uint32_t)__cvta_generic_to_shared(dyn_raw) & 127u)) & 127u);
     unsigned char *s_tile0 = dyn;                       // two tile buffers
-    double *s_rsx = reinterpret_cast<double *>(dyn + 2 * BigT::tile_stride);
-    double *s_rsy = s_rsx + kMaxWindow;
+    float *s_rsx = reinterpret_cast<float *>(dyn + 2 * BigT::tile_stride);
+    float *s_rsy = s_rsx + kMaxWindow;
+    const uint32_t tile0_addr = pin_reg(smem_u32(s_tile0));
     __shared__ __align__(8) uint64_t s_bar[2];
     __shared__ DescShared S;
     uint32_t phase[2] = {0, 0};
@@ -695,7 +888,10 @@ __global__ void __launch_bounds__(BigT::threads) k_descriptor_big(const __grid_c
 
     for (;;) {
         __syncthreads();
-        if (tid == 0) S.work = atomicAdd(A.misc + kMiscClassHead + CLS, 1);
+        if (tid == 0) {
+            S.work = atomicAdd(A.misc + kMiscClassHead + CLS, 1);
+            S.inexact = 0;
+        }
         __syncthreads();
         const int work = S.work;
         if (work >= count) break;
@@ -720,8 +916,13 @@ __global__ void __launch_bounds__(BigT::threads) k_descriptor_big(const __grid_c
             if (tid < 2) {  // x chain on lane 0, y chain on lane 1
                 float v = tid == 0 ? cx + off * cd + off * sd : cy - off * sd + off * cd;
                 const float inc = tid == 0 ? sd : cd;
-                double *dst = tid == 0 ? s_rsx : s_rsy;
-                for (int i = 0; i < n; i++, v += inc) dst[i] = (double)v;
+                float *dst = tid == 0 ? s_rsx : s_rsy;
+                bool exact = true;
+                for (int i = 0; i < n; i++, v += inc) {
+                    dst[i] = v;
+                    exact = exact && fix32_exact(v);
+                }
+                if (!exact) S.inexact = 1;
             }
         }
         const double inv = (double)kPatch / n;
@@ -736,11 +937,14 @@ __global__ void __launch_bounds__(BigT::threads) k_descriptor_big(const __grid_c
         const int sw = (n + q - 1) / q;
         const int n_sub = q * q;
         // bounding box (tile origin) of sub-window `sub`; exact row starts are known here
-        auto sub_box = [&](int sub, int &i0, int &i1, int &j0, int &j1, int &tx0a, int &ty0, bool &fits) {
+        const bool fixed_ok = !A.upright && !S.inexact && fix32_exact(cd) && fix32_exact(sd);
+        const long long cdq = fixed_ok ? fix32(cd) : 0, sdq = fixed_ok ? fix32(sd) : 0;
+        auto sub_box = [&](int sub, int &i0, int &i1, int &j0, int &j1, int &tx0a, int &ty0, bool &fits, bool &interior) {
             const int si = sub / q, sj = sub - si * q;
             i0 = si * sw; i1 = min(n, i0 + sw);
             j0 = sj * sw; j1 = min(n, j0 + sw);
             int tx0, tx1, ty1;
+            interior = false;
             if (A.upright) {
                 // window pixel (i, j) = frame (clamp(ux0 + i), clamp(uy0 - j))
                 tx0 = min(max(ux0 + i0, 0), W - 1);
@@ -755,10 +959,15 @@ __global__ void __launch_bounds__(BigT::threads) k_descriptor_big(const __grid_c
                 const double maxx = fmax(fmax(xa + ex0, xa + ex1), fmax(xb + ex0, xb + ex1));
                 const double miny = fmin(fmin(ya - ey0, ya - ey1), fmin(yb - ey0, yb - ey1));
                 const double maxy = fmax(fmax(ya - ey0, ya - ey1), fmax(yb - ey0, yb - ey1));
-                tx0 = min(max(__double2int_rd(minx), 0), W - 1);
-                tx1 = min(max(__double2int_rd(maxx) + 1, 0), W - 1);
-                ty0 = min(max(__double2int_rd(miny), 0), H - 1);
-                ty1 = min(max(__double2int_rd(maxy) + 1, 0), H - 1);
+                // exact extremes of the taps: floor(min) >= 0 and floor(max) + 1 <= limit means every tap has its
+                // four neighbours inside the frame
+                const int bx0 = __double2int_rd(minx), bx1 = __double2int_rd(maxx) + 1;
+                const int by0 = __double2int_rd(miny), by1 = __double2int_rd(maxy) + 1;
+                interior = bx0 >= 0 && by0 >= 0 && bx1 <= W - 1 && by1 <= H - 1;
+                tx0 = min(max(bx0, 0), W - 1);
+                tx1 = min(max(bx1, 0), W - 1);
+                ty0 = min(max(by0, 0), H - 1);
+                ty1 = min(max(by1, 0), H - 1);
             }
             tx0a = tx0 & ~15;
             fits = (tx1 - tx0a + 1 <= tp) && (ty1 - ty0 + 1 <= tr);
@@ -766,22 +975,22 @@ __global__ void __launch_bounds__(BigT::threads) k_descriptor_big(const __grid_c
         bool bad = false;
         if (use_tma && tid == 0) {  // prologue: first tile
             int i0, i1, j0, j1, tx0a, ty0;
-            bool fits;
-            sub_box(0, i0, i1, j0, j1, tx0a, ty0, fits);
+            bool fits, inside;
+            sub_box(0, i0, i1, j0, j1, tx0a, ty0, fits, inside);
             tma_load_tile(&imap, (uint32_t)__cvta_generic_to_shared(s_tile0), tx0a, ty0, b, bar0, BigT::tile_bytes);
         }
         for (int sub = 0; sub < n_sub; sub++) {
             const int cur = sub & 1;
             unsigned char *tile = s_tile0 + cur * BigT::tile_stride;
             int i0, i1, j0, j1, tx0a, ty0;
-            bool fits;
-            sub_box(sub, i0, i1, j0, j1, tx0a, ty0, fits);
+            bool fits, interior;
+            sub_box(sub, i0, i1, j0, j1, tx0a, ty0, fits, interior);
             bad = bad || !fits;
             if (use_tma) {
                 if (tid == 0 && sub + 1 < n_sub) {  // prefetch the next sub-window's tile into the other buffer
                     int a0, a1, c0, c1, nx, ny;
-                    bool nf;
-                    sub_box(sub + 1, a0, a1, c0, c1, nx, ny, nf);
+                    bool nf, ni;
+                    sub_box(sub + 1, a0, a1, c0, c1, nx, ny, nf, ni);
                     tma_load_tile(&imap, (uint32_t)__cvta_generic_to_shared(s_tile0 + (cur ^ 1) * BigT::tile_stride), nx, ny, b,
                                   bar0 + 8 * (cur ^ 1), BigT::tile_bytes);
                 }
@@ -802,13 +1011,19 @@ __global__ void __launch_bounds__(BigT::threads) k_descriptor_big(const __grid_c
                             g_win[i * n + j] = (unsigned char)SRC(y * tp + x);
                         }
                     }
+                } else if (fixed_ok) {
+                    const uint32_t tile_addr = tile0_addr + cur * BigT::tile_stride;
+                    if (interior)
+                        window_taps_fixed<tp, NW, false, true>(n, i0, i1, j0, j1, s_rsx, s_rsy, cdq, sdq, tile_addr, tx0a, ty0, W, H, 0, g_win);
+                    else
+                        window_taps_fixed<tp, NW, true, true>(n, i0, i1, j0, j1, s_rsx, s_rsy, cdq, sdq, tile_addr, tx0a, ty0, W, H, 0, g_win);
                 } else {
                     const int lj = lane & 7, li = lane >> 3;  // 4 rows x 8 columns per warp
                     const double lane_dx = (double)(j0 + lj) * (double)cd, lane_dy = (double)(j0 + lj) * (double)sd;
                     const double step_x = 8.0 * (double)cd, step_y = 8.0 * (double)sd;
                     for (int i = i0 + warp * 4 + li; i < i1; i += NW * 4) {
-                        double fx = s_rsx[i] + lane_dx;
-                        double fy = s_rsy[i] - lane_dy;
+                        double fx = (double)s_rsx[i] + lane_dx;
+                        double fy = (double)s_rsy[i] - lane_dy;
                         unsigned char *wrow = g_win + (size_t)i * n;
                         for (int j = j0 + lj; j < j1; j += 8, fx += step_x, fy -= step_y)
                             wrow[j] = (unsigned char)rotated_tap(fx, fy, W, H, tx0a, ty0, tp, SRC);
@@ -818,7 +1033,7 @@ __global__ void __launch_bounds__(BigT::threads) k_descriptor_big(const __grid_c
             __syncthreads();  // this buffer may be refilled (two iterations ahead) and g_win rows are complete
         }
         if (bad && tid == 0) atomicOr(A.misc + kMiscStatus, 2);
-        descriptor_tail<THREADS>(A, kidx, n, g_win, g_buf, S, int_scale, isc);
+        descriptor_tail<THREADS, 0>(A, kidx, n, g_win, g_buf, 0, 0, S, int_scale, isc);
     }
 }
 

@@ -76,9 +76,10 @@ def load_library():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
-        raise SurfError(-5, f"{LIB_PATH} is missing: run `python -m surffeatures_b200.build` (there is no CPU path)")
-    L = C.CDLL(LIB_PATH)
+    path = os.environ.get("SURF_B200_LIB", LIB_PATH)  # development knob: A/B builds of the same library
+    if not os.path.exists(path):
+        raise SurfError(-5, f"{path} is missing: run `python -m surffeatures_b200.build` (there is no CPU path)")
+    L = C.CDLL(path)
     vp, i32, sz, lng = C.c_void_p, C.c_int, C.c_size_t, C.c_long
     pp = C.POINTER(Params)
     L.surf_create.argtypes = [pp, i32, i32, i32, i32, i32, C.POINTER(vp)]
