@@ -295,9 +295,6 @@ struct AreaTab {  // one destination cell of the INTER_AREA table (same for x an
 struct DescShared {  // static shared state of one descriptor CTA
     AreaTab tab;
     __align__(4) unsigned char patch[kPatchPx + 3];
-    float dx[400], dy[400];
-    float vec[128];
-    float scale;
     int work;
     int inexact;  // a row start of this window is not a multiple of 2^-32: fp64 tap coordinates
 };
@@ -588,58 +585,79 @@ __device__ __forceinline__ void descriptor_tail(const DescribeArgs &A, int kidx,
         for (int p = tid; p < kPatchPx; p += THREADS) po[p] = S.patch[p];
     }
     if (!A.desc) return;
+    // the patch goes to the workspace slot of this keypoint (16-byte aligned); k_patch_descriptor finishes it
+    uint32_t *pw = reinterpret_cast<uint32_t *>(A.patch_ws + (size_t)kidx * kPatchStride);
+    const uint32_t *ps = reinterpret_cast<const uint32_t *>(S.patch);
+    for (int t = tid; t < (kPatchPx + 3) / 4; t += THREADS) pw[t] = ps[t];
+}
 
-    // ---- 2x2 Haar gradients of the patch, Gaussian weighted ----
-    for (int t = tid; t < 400; t += THREADS) {
-        const int i = t / 20, j = t - i * 20;
-        const unsigned char *r0 = S.patch + i * kPatch + j, *r1 = r0 + kPatch;
-        const float wgt = c_desc_w[t];
-        S.dx[t] = (r0[1] - r0[0] + r1[1] - r1[0]) * wgt;
-        S.dy[t] = (r1[0] - r0[0] + r1[1] - r0[1]) * wgt;
-    }
+// ------------------------------------------------------------------------------------------------
+// K4c: from the 21 x 21 patch to the descriptor.  One warp per keypoint of a size class's work list, no block
+// barriers: lane = (sub-region, dx-or-dy half).  Every output component is one sequential fp32 sum over the
+// sub-region's 5 x 5 samples in (y, x) order, as the reference accumulates it.
+//   64-d : half 0 -> sum dx, sum |dx| (components 0, 2 of the region); half 1 -> sum dy, sum |dy| (1, 3)
+//   128-d: half 0 -> dx and |dx| split by the sign of dy (0..3);       half 1 -> dy and |dy| split by the sign of dx (4..7)
+// ------------------------------------------------------------------------------------------------
+constexpr int kPdWarps = 8;
+
+__global__ void __launch_bounds__(kPdWarps * 32) k_patch_descriptor(const __grid_constant__ DescribeArgs A, int cls)
+{
+    __shared__ __align__(16) unsigned char s_patch[kPdWarps][kPatchStride];
+    __shared__ float s_w[400];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int t = threadIdx.x; t < 400; t += kPdWarps * 32) s_w[t] = c_desc_w[t];
     __syncthreads();
-    // ---- 4 x 4 sub-regions, one output component per thread, sequential fp32 sums ----
-    const int nb = A.extended ? 8 : 4;
-    for (int t = tid; t < D; t += THREADS) {
-        const int region = t / nb, comp = t - region * nb;
-        const int I = region >> 2, J = region & 3;
-        float acc = 0;
-        for (int y = I * 5; y < I * 5 + 5; y++)
-            for (int x = J * 5; x < J * 5 + 5; x++) {
-                const float tx = S.dx[y * 20 + x], ty = S.dy[y * 20 + x];
+    const int count = A.misc[kMiscClassCount + cls];
+    const int *list = A.class_list + (size_t)cls * A.list_stride;
+    const int region = lane >> 1, half = lane & 1;
+    const int y0 = (region >> 2) * 5, x0 = (region & 3) * 5;
+    unsigned char *P = s_patch[warp];
+    for (int w = blockIdx.x * kPdWarps + warp; w < count; w += gridDim.x * kPdWarps) {
+        const int kidx = list[w];
+        const uint4 *src = reinterpret_cast<const uint4 *>(A.patch_ws + (size_t)kidx * kPatchStride);
+        if (lane < kPatchStride / 16) reinterpret_cast<uint4 *>(P)[lane] = src[lane];
+        __syncwarp();
+        float a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+        for (int y = y0; y < y0 + 5; y++) {
+            const unsigned char *r0 = P + y * kPatch + x0, *r1 = r0 + kPatch;
+            int p00 = r0[0], p10 = r1[0];
+#pragma unroll
+            for (int x = 0; x < 5; x++) {
+                const int p01 = r0[x + 1], p11 = r1[x + 1];
+                const float wgt = s_w[y * 20 + x0 + x];
+                const float tx = (p01 - p00 + p11 - p10) * wgt, ty = (p10 - p00 + p11 - p01) * wgt;
+                const float u = half ? ty : tx, o = half ? tx : ty;
                 if (A.extended) {
-                    switch (comp) {
-                        case 0: if (ty >= 0) acc += tx; break;
-                        case 1: if (ty >= 0) acc += fabsf(tx); break;
-                        case 2: if (!(ty >= 0)) acc += tx; break;
-                        case 3: if (!(ty >= 0)) acc += fabsf(tx); break;
-                        case 4: if (tx >= 0) acc += ty; break;
-                        case 5: if (tx >= 0) acc += fabsf(ty); break;
-                        case 6: if (!(tx >= 0)) acc += ty; break;
-                        default: if (!(tx >= 0)) acc += fabsf(ty); break;
+                    if (o >= 0) {
+                        a0 += u;
+                        a1 += fabsf(u);
+                    } else {
+                        a2 += u;
+                        a3 += fabsf(u);
                     }
                 } else {
-                    switch (comp) {
-                        case 0: acc += tx; break;
-                        case 1: acc += ty; break;
-                        case 2: acc += fabsf(tx); break;
-                        default: acc += fabsf(ty); break;
-                    }
+                    a0 += u;
+                    a1 += fabsf(u);
                 }
+                p00 = p01;
+                p10 = p11;
             }
-        S.vec[t] = acc;
-    }
-    __syncthreads();
-    if (warp == 0) {
-        double mag = 0;
-        for (int t = lane; t < D; t += 32) mag += (double)(S.vec[t] * S.vec[t]);
+        }
+        double mag = (double)(a0 * a0) + (double)(a1 * a1);
+        if (A.extended) mag += (double)(a2 * a2) + (double)(a3 * a3);
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) mag += __shfl_xor_sync(FULL_MASK, mag, d);
-        if (lane == 0) S.scale = (float)(1. / (sqrt(mag) + DBL_EPSILON));
+        const float scale = (float)(1. / (sqrt(mag) + DBL_EPSILON));
+        if (A.extended) {
+            float4 *vo = reinterpret_cast<float4 *>(A.desc + (size_t)kidx * 128 + region * 8 + half * 4);
+            *vo = make_float4(a0 * scale, a1 * scale, a2 * scale, a3 * scale);
+        } else {
+            float *vo = A.desc + (size_t)kidx * 64 + region * 4 + half;
+            vo[0] = a0 * scale;
+            vo[2] = a1 * scale;
+        }
+        __syncwarp();  // the next keypoint overwrites the patch
     }
-    __syncthreads();
-    float *vo = A.desc + (size_t)kidx * D;
-    for (int t = tid; t < D; t += THREADS) vo[t] = S.vec[t] * S.scale;
 }
 
 // Per-class compile-time geometry.  The image tile of a class has a FIXED pitch and row count (the largest
@@ -647,7 +665,8 @@ __device__ __forceinline__ void descriptor_tail(const DescribeArgs &A, int kidx,
 template <int CLS>
 struct ClassT {
     static constexpr int max_n = CLS == 0 ? kClassMaxN0 : CLS == 1 ? kClassMaxN1 : kClassMaxN2;
-    static constexpr int threads = CLS == 0 ? 128 : 256;
+    // measured (describe stage, 64 frames): 128/256/256 threads 6.43 ms, 128/128/256 6.28 ms, 256/256/256 7.46 ms
+    static constexpr int threads = CLS == 2 ? 256 : 128;
     // bounding box side of a rotated n x n window: n (|cos| + |sin|) + 3 <= 1.4143 n + 3, plus the 1-pixel
     // margin on both sides of the closed-form box; origin aligned down / pitch rounded up to 16 bytes
     static constexpr int side = (int)(1.4143 * max_n) + 4 + 2;
@@ -1048,7 +1067,7 @@ struct ClassCfg {
 
 struct DevCfg {
     bool ready = false;
-    int ori_grid = 0;
+    int ori_grid = 0, pd_grid = 0;
     ClassCfg cls[kNumClasses];
     cudaStream_t side[kNumClasses - 1];
     cudaEvent_t fork, join[kNumClasses - 1];
@@ -1089,6 +1108,7 @@ DevCfg &dev_cfg()
         int per_sm = 4;
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_orient, kOriWarps * 32, 0);
         c.ori_grid = sms * (per_sm < 1 ? 1 : per_sm);
+        c.pd_grid = sms * 4;
         setup_class<0>(c.cls[0], sms);
         setup_class<1>(c.cls[1], sms);
         setup_class<2>(c.cls[2], sms);
@@ -1126,15 +1146,21 @@ void launch_describe(const DescribeArgs &a, const CUtensorMap *imaps, int use_tm
     // tails of the short launches overlap the long ones; join back on `st`.
     cudaEventRecord(c.fork, st);
     for (int k = 0; k < kNumClasses - 1; k++) cudaStreamWaitEvent(c.side[k], c.fork, 0);
+    // each class: windows -> 21 x 21 patches, then (same stream) patches -> descriptors, one warp per keypoint
+    const int pd_grid = c.pd_grid;
     k_descriptor_big<<<c.cls[3].grid, BigT::threads, c.cls[3].smem, st>>>(a, imaps[3], use_tma);
+    if (a.desc) k_patch_descriptor<<<pd_grid / 4, kPdWarps * 32, 0, st>>>(a, 3);
     k_descriptor<1><<<c.cls[1].grid, ClassT<1>::threads, c.cls[1].smem, c.side[0]>>>(a, imaps[1], use_tma);
+    if (a.desc) k_patch_descriptor<<<pd_grid, kPdWarps * 32, 0, c.side[0]>>>(a, 1);
     k_descriptor<2><<<c.cls[2].grid, ClassT<2>::threads, c.cls[2].smem, c.side[1]>>>(a, imaps[2], use_tma);
+    if (a.desc) k_patch_descriptor<<<pd_grid / 2, kPdWarps * 32, 0, c.side[1]>>>(a, 2);
     k_descriptor<0><<<c.cls[0].grid, ClassT<0>::threads, c.cls[0].smem, c.side[2]>>>(a, imaps[0], use_tma);
+    if (a.desc) k_patch_descriptor<<<pd_grid, kPdWarps * 32, 0, c.side[2]>>>(a, 0);
     for (int k = 0; k < kNumClasses - 1; k++) {
         cudaEventRecord(c.join[k], c.side[k]);
         cudaStreamWaitEvent(st, c.join[k], 0);
     }
-    *launches += 4;
+    *launches += a.desc ? 8 : 4;
 }
 
 }  // namespace surfb200

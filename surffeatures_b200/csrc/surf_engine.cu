@@ -319,7 +319,7 @@ void free_workspace(surf_engine *e)
     cudaFree(e->d_det); cudaFree(e->d_kp_a); cudaFree(e->d_kp_b); cudaFree(e->d_out_kp); cudaFree(e->d_desc);
     cudaFree(e->d_out_desc); cudaFree(e->d_patches); cudaFree(e->d_counts); cudaFree(e->d_ndel);
     cudaFree(e->d_off_in); cudaFree(e->d_off_out); cudaFree(e->d_misc); cudaFree(e->d_deleted);
-    cudaFree(e->d_match_part); cudaFree(e->d_match_io); cudaFree(e->d_class_list); cudaFree(e->d_win_scratch); cudaFree(e->d_sincos);
+    cudaFree(e->d_match_part); cudaFree(e->d_match_io); cudaFree(e->d_class_list); cudaFree(e->d_win_scratch); cudaFree(e->d_sincos); cudaFree(e->d_patch_ws);
     for (auto &w : e->tc) {
         cudaFree(w.pool.hi); cudaFree(w.pool.lo); cudaFree(w.pool.norm); cudaFree(w.pool.max_norm);
         cudaFree(w.pool.count); cudaFree(w.cand); cudaFree(w.redo); cudaFree(w.counters); cudaFree(w.segs);
@@ -333,7 +333,7 @@ void free_workspace(surf_engine *e)
     e->d_kp_a = e->d_kp_b = e->d_out_kp = nullptr; e->d_desc = e->d_out_desc = nullptr; e->d_patches = nullptr;
     e->d_counts = e->d_ndel = e->d_off_in = e->d_off_out = e->d_misc = e->d_deleted = nullptr;
     e->d_match_part = nullptr; e->d_match_io = nullptr; e->h_pin = nullptr; e->d_class_list = nullptr;
-    e->d_win_scratch = nullptr; e->d_sincos = nullptr;
+    e->d_win_scratch = nullptr; e->d_sincos = nullptr; e->d_patch_ws = nullptr;
     e->match_part_cap = e->match_io_cap = 0;
 }
 
@@ -385,6 +385,7 @@ int alloc_workspace(surf_engine *e)
     CU(e, cudaMalloc(&e->d_class_list, nk * kNumClasses * sizeof(int)));
     CU(e, cudaMalloc(&e->d_win_scratch, describe_scratch_bytes()));
     CU(e, cudaMalloc(&e->d_sincos, nk * sizeof(float2)));
+    CU(e, cudaMalloc(&e->d_patch_ws, nk * (size_t)kPatchStride));
     CU(e, cudaMallocHost(&e->h_pin, sizeof(int) * (3 * (size_t)B + 8 + kMiscWords)));
     return alloc_det_and_desc(e);
 }
@@ -541,6 +542,7 @@ int run_describe_pack(surf_engine *e, const ImageRef &img, const FrameGeo &geo, 
     a.B = B;
     a.desc = want_desc ? e->d_desc : nullptr;
     a.patches = patches;
+    a.patch_ws = e->d_patch_ws;
     a.extended = p.extended;
     a.upright = p.upright;
     a.img_aligned4 = ((reinterpret_cast<uintptr_t>(img.ptr) | img.pitch | img.frame_stride) & 3) == 0;

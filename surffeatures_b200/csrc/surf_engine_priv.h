@@ -63,6 +63,7 @@ struct surf_engine {
     int *d_deleted = nullptr, *d_class_list = nullptr;
     uint8_t *d_win_scratch = nullptr;
     float2 *d_sincos = nullptr;
+    uint8_t *d_patch_ws = nullptr;  // [max_b][cap][kPatchStride]
     int *h_pin = nullptr;  // pinned: counts[B], ndel[B], off_out[B+1], misc[4]
     surf_dmatch *d_match_part = nullptr;  size_t match_part_cap = 0;
     void *d_match_io = nullptr;           size_t match_io_cap = 0;
