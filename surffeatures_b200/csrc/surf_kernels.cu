@@ -431,7 +431,7 @@ __device__ __forceinline__ void tile_responses(const int *__restrict__ o, const 
     }
 }
 
-__global__ void __launch_bounds__(kTileThreads) k_hessian_nms_tma(const __grid_constant__ CUtensorMap tmap,
+__global__ void __launch_bounds__(kTileThreads, 1024 / kTileThreads) k_hessian_nms_tma(const __grid_constant__ CUtensorMap tmap,
                                                                   const __grid_constant__ TileOctave oct,
                                                                   const uint32_t *__restrict__ msum, int SP, int octave,
                                                                   float thr, surf_keypoint *__restrict__ raw,
@@ -610,7 +610,7 @@ __device__ __forceinline__ void layer_responses_c(const int *__restrict__ o, int
 }
 
 template <int OCT, int LPO>
-__global__ void __launch_bounds__(kTileThreads) k_hessian_nms_tma_c(const __grid_constant__ CUtensorMap tmap, int W, int H,
+__global__ void __launch_bounds__(kTileThreads, 1024 / kTileThreads) k_hessian_nms_tma_c(const __grid_constant__ CUtensorMap tmap, int W, int H,
                                                                     const uint32_t *__restrict__ msum, int SP, float thr,
                                                                     surf_keypoint *__restrict__ raw,
                                                                     int *__restrict__ counts, int cap)
