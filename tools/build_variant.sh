@@ -1,5 +1,6 @@
 #!/bin/bash
-# usage: build_variant.sh NAME [nvcc flags...]  -> scratch_ab/lib_NAME.so
+# usage: tools/build_variant.sh NAME [nvcc flags...]  -> scratch_ab/lib_NAME.so
+# A/B builds of the whole library with extra nvcc flags; select one at run time with SURF_B200_LIB=/root/repo/scratch_ab/lib_NAME.so
 set -e
 name=$1; shift
 cd /root/repo/surffeatures_b200
