@@ -387,6 +387,9 @@ __device__ __forceinline__ float tap_u8f(uint32_t v) { return __uint2float_rn(v)
 // float (multiple of 2^-32, |v| < 2^31) -> signed 32.32 fixed point, exact
 __device__ __forceinline__ long long fix32(float v) { return __double2ll_rn((double)v * 4294967296.0); }
 __device__ __forceinline__ bool fix32_exact(float v) { return v == 0.f || fabsf(v) >= 0.001953125f; }
+// the same test as an order-preserving key: (bits << 1) - 2 wraps 0 to the top, so fix32_exact(v) <=> key >= kFix32KeyMin
+__device__ __forceinline__ uint32_t fix32_key(float v) { return (__float_as_uint(v) << 1) - 2u; }
+constexpr uint32_t kFix32KeyMin = (0x3b000000u << 1) - 2u;  // 2^-9
 
 // Interior tap: X's high word already carries (tile address - x0), Y's high word (-y0).
 template <int TP>
@@ -824,12 +827,14 @@ __global__ void __launch_bounds__(ClassT<CLS>::threads) k_descriptor(const __gri
             float v = tid == 0 ? cx + off * cd + off * sd : cy - off * sd + off * cd;
             const float inc = tid == 0 ? sd : cd;
             float *dst = tid == 0 ? s_rsx : s_rsy;
-            bool exact = true;  // every row start is a multiple of 2^-32 (fixed-point taps apply)
+            // every row start must be a multiple of 2^-32 for the fixed-point taps: branch-free running minimum
+            // of fix32_key (see there)
+            uint32_t key = 0xffffffffu;
             for (int i = 0; i < n; i++, v += inc) {
                 dst[i] = v;
-                exact = exact && fix32_exact(v);
+                key = min(key, fix32_key(v));
             }
-            if (!exact) S.inexact = 1;
+            if (key < kFix32KeyMin) S.inexact = 1;
         }
         if (use_tma) {
             if (!mbar_wait_bounded(bar, tma_phase) && tid == 0) atomicOr(A.misc + kMiscStatus, 4);  // reported by the host
@@ -936,12 +941,12 @@ __global__ void __launch_bounds__(BigT::threads) k_descriptor_big(const __grid_c
                 float v = tid == 0 ? cx + off * cd + off * sd : cy - off * sd + off * cd;
                 const float inc = tid == 0 ? sd : cd;
                 float *dst = tid == 0 ? s_rsx : s_rsy;
-                bool exact = true;
+                uint32_t key = 0xffffffffu;
                 for (int i = 0; i < n; i++, v += inc) {
                     dst[i] = v;
-                    exact = exact && fix32_exact(v);
+                    key = min(key, fix32_key(v));
                 }
-                if (!exact) S.inexact = 1;
+                if (key < kFix32KeyMin) S.inexact = 1;
             }
         }
         const double inv = (double)kPatch / n;
