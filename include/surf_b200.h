@@ -280,6 +280,34 @@ int surf_sweep_mha(surf_engine *e, surf_mha *m, const float crop_ratios[4], cons
                    surf_db *db, surf_keypoint *keypoints, float *descriptors, int32_t *offsets, long capacity,
                    int32_t *n_frames_out);
 
+/* ---- "next" row f4: plane fit by RANSAC and pose estimate (ransac :2085-2188, updateMatchNodeRansac :1655-1851) ----
+ * rand(): the reference draws from the process-global rand(), never seeded (= srand(1)).  surf_rand is that
+ * generator (glibc TYPE_3) as an explicit state; create it with seed 1 and pass it to the calls below in the
+ * reference's call order to reproduce its draws. */
+typedef struct surf_rand surf_rand;
+int surf_rand_create(uint32_t seed, surf_rand **out);
+void surf_rand_destroy(surf_rand *r);
+int surf_rand_next(surf_rand *r); /* rand() */
+/* trainPoints / queryPoints :1672-1703: one pair per match whose imgIdx is not -1 (afterHoughMatches keeps rejected
+ * entries with -1).  train_transforms: 16 floats per train image (trainImagesTransform), image_to_probe: 16 doubles,
+ * both row-major.  Outputs: n_points x 3 doubles each (capacity n_matches). */
+int surf_match_points(const surf_dmatch *matches, int n_matches, const surf_keypoint *query_keypoints,
+                      const surf_keypoint *train_keypoints, const int32_t *train_offsets, int n_train_images,
+                      const float *train_transforms, const double image_to_probe[16], double *train_points,
+                      double *query_points, int32_t *n_points);
+/* ransac(points, inliersIdx, planePointsIdx) :2085-2188 with threshold = ransacMargin (default 1.0, :1002) and 1000
+ * iterations in the reference.  The hypotheses are scored on the device.  inliers: capacity n; order as the reference
+ * leaves it (fitted inliers in point order, then the three plane points).  n < 3 is SURF_ERR_BAD_ARG (reference: returns 1). */
+int surf_ransac_plane(surf_engine *e, surf_rand *rng, const double *points, int n, float margin, int iterations,
+                      int32_t *inliers, int32_t *n_inliers, int32_t plane_idx[3], double *best_error, int32_t *n_outliers);
+/* The estimate matrix of updateMatchNodeRansac :1714-1808 (row-major 4x4, IJK to RAS) and the mean match distance
+ * :1811-1823.  Host arithmetic (about 2 MFLOP of dependent fp64 with libm calls). */
+int surf_estimate_pose(surf_rand *rng, const double *query_points, const double *train_points, int n, const int32_t *inliers,
+                       int n_inliers, const int32_t plane_idx[3], double estimate[16], double *mean_match_distance);
+/* Mean plane-to-plane distance :1826-1846 over every step-th non-zero mask pixel (step 4 in the reference). */
+int surf_mean_plane_distance(const uint8_t *mask, int rows, int cols, size_t pitch, int step, const double ground_truth[16],
+                             const double estimate[16], double *out);
+
 const char *surf_version(void);
 
 #ifdef __cplusplus

@@ -35,7 +35,7 @@ public:
     // max_width / max_height bound the CROPPED frame size; batch = frames per computeNext*() call
     explicit SurfFeaturesLogic(int device = 0, int max_width = 1024, int max_height = 1024, int batch = 32,
                                int max_keypoints = 16384, long db_rows = 1L << 21, int db_images = 8192)
-        : minHessian(400), xcentroid(0), ycentroid(0), correspondenceProgress(0), e_(0), trainDb_(0), bogusDb_(0),
+        : minHessian(400), xcentroid(0), ycentroid(0), correspondenceProgress(0), ransacMargin(1.0f), e_(0), trainDb_(0), bogusDb_(0), rand_(0),
           maskData_(0), maskW_(0), maskH_(0), maskStep_(0), batch_(batch), dbRows_(db_rows), dbImages_(db_images)
     {
         cropRatios[0] = 1 / 5.; cropRatios[1] = 3. / 3.9; cropRatios[2] = 1 / 6.; cropRatios[3] = 3. / 4.;  // .cxx:1008-1009
@@ -61,6 +61,7 @@ public:
             if (sweep_[s].seq) surf_mha_close(sweep_[s].seq);
         surf_db_destroy(trainDb_);
         surf_db_destroy(bogusDb_);
+        surf_rand_destroy(rand_);
         surf_destroy(e_);
     }
 
@@ -139,6 +140,26 @@ public:
         correspondenceProgress = 100;
     }
 
+    // ---- plane fit of the matched train keypoints (row f4) ----
+    struct Point3 { double v[3]; };   // vnl_double_3
+    void setRansacMargin(float m) { ransacMargin = m; }                                   // .h setter, default 1.0 (.cxx:1002)
+    float getRansacMargin() const { return ransacMargin; }
+    // ransac(points, inliersIdx, planePointsIdx) .cxx:2085-2188: 0 on success, 1 with fewer than three points.
+    // rand() is the logic's own stream: glibc's generator, never seeded, as in the reference's process.
+    int ransac(const std::vector<Point3> &points, std::vector<int> &inliersIdx, std::vector<int> &planePointsIdx)
+    {
+        inliersIdx.clear();
+        planePointsIdx.clear();
+        if (points.size() < 3) return 1;
+        if (!rand_) check(surf_rand_create(1, &rand_));
+        std::vector<int32_t> inl(points.size() + 3);
+        int32_t n = 0, plane[3];
+        check(surf_ransac_plane(e_, rand_, &points[0].v[0], (int)points.size(), ransacMargin, 1000, inl.data(), &n, plane, 0, 0));
+        inliersIdx.assign(inl.begin(), inl.begin() + n);
+        planePointsIdx.assign(plane, plane + 3);
+        return 0;
+    }
+
     // results (public members in the reference, .h:258-262)
     std::vector<int> bestMatches, bestMatchesCount, houghCounts;
     std::vector<std::vector<DMatch> > afterHoughMatches, matchesWithBestTrainImage;
@@ -152,6 +173,7 @@ public:
     int trainStartFrame, trainStopFrame, bogusStartFrame, bogusStopFrame, queryStartFrame, queryStopFrame;
     int xcentroid, ycentroid;
     int correspondenceProgress;
+    float ransacMargin;
 
 private:
     enum { BOGUS = 0, TRAIN = 1, QUERY = 2 };
@@ -238,6 +260,7 @@ private:
 
     surf_engine *e_;
     surf_db *trainDb_, *bogusDb_;
+    surf_rand *rand_;
     const unsigned char *maskData_;
     int maskW_, maskH_;
     size_t maskStep_;

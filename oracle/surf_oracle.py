@@ -33,8 +33,8 @@ def params(hessianThreshold=100.0, nOctaves=4, nOctaveLayers=3, extended=False, 
 
 def build(force: bool = False) -> str:
     """Compile the oracle with the committed Makefile (gcc, no FMA contraction)."""
-    src = os.path.join(_HERE, "surf_oracle.c")
-    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < os.path.getmtime(src):
+    srcs = [os.path.join(_HERE, f) for f in ("surf_oracle.c", "surf_oracle.h", "pose_oracle.c", "Makefile")]
+    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < max(os.path.getmtime(f) for f in srcs):
         env = dict(os.environ)
         env.pop("CC", None)
         subprocess.check_call(["make", "-s", "-C", _HERE, "libsurf_oracle.so"], env=env)

@@ -24,6 +24,7 @@ UNITS = [
     ("surf_db.cu", []),
     ("surf_vote.cu", ["-fmad=false"]),
     ("surf_mha.cu", ["-fmad=false"]),
+    ("surf_pose.cu", ["-fmad=false"]),
 ]
 
 

@@ -36,6 +36,8 @@ ABI_SYMBOLS = [
     "surf_integral", "surf_hessian_layer", "surf_raw_keypoints", "surf_describe_keypoints", "surf_match_knn",
     "surf_match_ratio", "surf_merge_topk", "surf_version", "surf_match_prev", "surf_stream_reset",
     "surf_device_matches", "surf_set_match_mode", "surf_match_redo_count", "surf_set_async_outputs",
+    "surf_rand_create", "surf_rand_destroy", "surf_rand_next", "surf_match_points", "surf_ransac_plane",
+    "surf_estimate_pose", "surf_mean_plane_distance",
     "surf_wait_outputs", "surf_db_create", "surf_db_destroy", "surf_db_clear", "surf_db_add", "surf_db_size",
     "surf_db_knn", "surf_correspond", "surf_mha_open", "surf_mha_close", "surf_mha_last_error", "surf_mha_transforms",
     "surf_mha_validity", "surf_mha_frame_name", "surf_mha_read", "surf_crop_rect", "surf_mask_centroid", "surf_sweep_mha",
@@ -102,6 +104,14 @@ def load_library():
     L.surf_submit_batch.argtypes = [vp, vp, i32, i32, i32, i32, sz, sz, vp, sz, i32]
     L.surf_collect_batch.argtypes = [vp, vp, vp, i32, lng, vp]
     L.surf_prefetch_batch.argtypes = [vp, vp, i32, i32, i32, sz, sz]
+    L.surf_rand_create.argtypes = [C.c_uint32, C.POINTER(vp)]
+    L.surf_rand_destroy.argtypes = [vp]
+    L.surf_rand_destroy.restype = None
+    L.surf_rand_next.argtypes = [vp]
+    L.surf_match_points.argtypes = [vp, i32, vp, vp, vp, i32, vp, vp, vp, vp, vp]
+    L.surf_ransac_plane.argtypes = [vp, vp, vp, i32, C.c_float, i32, vp, vp, vp, vp, vp]
+    L.surf_estimate_pose.argtypes = [vp, vp, vp, i32, vp, i32, vp, vp, vp]
+    L.surf_mean_plane_distance.argtypes = [vp, i32, i32, sz, i32, vp, vp, vp]
     L.surf_device_results.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
     L.surf_sync.argtypes = [vp]
     L.surf_integral.argtypes = [vp, vp, i32, i32, sz, i32, vp]

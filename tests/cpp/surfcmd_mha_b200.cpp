@@ -97,6 +97,21 @@ int main(int argc, char **argv)
                         surf.queryOffsets()[i + 1] - surf.queryOffsets()[i], surf.afterHoughMatches[i].size(), surf.houghCounts[i],
                         alive, surf.bestMatches[i], surf.bestMatchesCount[i], surf.matchesWithBestTrainImage[i].size());
         }
+        // row f4: the logic's ransac() on a synthetic tilted plane through query frame 0's keypoints
+        {
+            const int nk = surf.queryOffsets()[1] < 200 ? surf.queryOffsets()[1] : 200;
+            std::vector<surfb200::SurfFeaturesLogic::Point3> pts(nk);
+            for (int j = 0; j < nk; j++) {
+                const surfb200::KeyPoint &k = surf.queryKeypoints()[j];
+                pts[j].v[0] = k.x;
+                pts[j].v[1] = k.y;
+                pts[j].v[2] = 0.05 * k.x - 0.02 * k.y + (j % 5 == 0 ? 30.0 : 0.0);
+            }
+            std::vector<int> inl, plane;
+            const int rc = surf.ransac(pts, inl, plane);
+            std::printf("ransac rc %d points %d inliers %zu plane %d %d %d\n", rc, nk, inl.size(), plane.size() == 3 ? plane[0] : -1,
+                        plane.size() == 3 ? plane[1] : -1, plane.size() == 3 ? plane[2] : -1);
+        }
     } catch (const surfb200::Error &e) {
         std::fprintf(stderr, "surf_b200 error %d: %s\n", e.code, e.what());
         return e.code == SURF_ERR_NO_DEVICE ? 3 : 1;

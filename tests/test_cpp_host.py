@@ -119,7 +119,19 @@ def test_cpp_surfcmd_flow_matches_oracle(tmp_path, oracle):
     head = lines[0].split()
     assert (int(head[1]), int(head[2])) == (cx, cy)
     assert int(head[4]) == sum(len(k) for k, _ in feats["train"])
-    assert len(lines) == 1 + len(feats["query"])
+    assert len(lines) == 2 + len(feats["query"])
+    # last line: SurfFeaturesLogic::ransac on a plane through query frame 0's keypoints (row f4)
+    from oracle import pose_oracle as po
+
+    qk0 = feats["query"][0][0][:200]
+    pts = np.column_stack([qk0["x"].astype(np.float64), qk0["y"].astype(np.float64),
+                           0.05 * qk0["x"].astype(np.float64) - 0.02 * qk0["y"].astype(np.float64)
+                           + np.where(np.arange(len(qk0)) % 5 == 0, 30.0, 0.0)])
+    rc, oinl, oplane, _, _ = po.ransac_plane(po.Rand(1), pts, margin=1.0, iterations=1000)
+    tok = lines[-1].split()
+    assert tok[0] == "ransac" and int(tok[2]) == rc == 0 and int(tok[4]) == len(qk0)
+    assert int(tok[6]) == len(oinl) and [int(t) for t in tok[8:11]] == oplane.tolist()
+    lines = lines[:-1]
     for i, (qk, qd) in enumerate(feats["query"]):
         want, res = oracle.correspond(qk, qd, [k for k, _ in feats["train"]], [d for _, d in feats["train"]],
                                       [d for _, d in feats["bogus"]], cx, cy)
