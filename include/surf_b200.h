@@ -130,6 +130,13 @@ int surf_collect_batch(surf_engine *e, surf_keypoint *keypoints, float *descript
  * them.  The host frames must stay unchanged until that submit's kernels have started. */
 int surf_prefetch_batch(surf_engine *e, const uint8_t *images, int batch, int width, int height, size_t pitch,
                         size_t frame_stride);
+/* Optional, stronger than surf_prefetch_batch: uploads the NEXT batch's frames (host input) and runs stages 1-3 on
+ * them (integral, Hessian, maxima, sort) on a separate stream and a second set of buffers, while the submitted
+ * batch is in its descriptor stage; the two stages stress different units of the SM and overlap well.  A following
+ * surf_submit_batch with the same arguments (pointers, geometry, mask) continues with stage 4; anything else discards
+ * the look-ahead.  Frames and mask must stay unchanged until that submit's results are collected. */
+int surf_lookahead_batch(surf_engine *e, const uint8_t *images, int in_mem, int batch, int width, int height, size_t pitch,
+                         size_t frame_stride, const uint8_t *mask, size_t mask_pitch);
 /* Device-resident results of the last submitted batch (valid until the next submit): packed
  * keypoints, packed descriptors, device int32 offsets[batch+1]. Requires surf_collect_batch or
  * surf_sync first if the host needs the counts. */

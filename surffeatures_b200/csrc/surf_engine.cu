@@ -10,6 +10,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <utility>
 #include <ctime>
 #include <new>
 #include <vector>
@@ -328,6 +329,10 @@ void free_workspace(surf_engine *e)
     }
     cudaFree(e->d_prev_desc); cudaFree(e->d_prev_off); cudaFree(e->d_stream_matches); cudaFree(e->d_stream_good);
     e->d_prev_desc = nullptr; e->d_prev_off = nullptr; e->d_stream_matches = nullptr; e->d_stream_good = nullptr;
+    cudaFree(e->alt.d_sum); cudaFree(e->alt.d_kp_a); cudaFree(e->alt.d_kp_b); cudaFree(e->alt.d_counts);
+    e->alt.d_sum = nullptr; e->alt.d_kp_a = e->alt.d_kp_b = e->alt.sorted = nullptr; e->alt.d_counts = nullptr;
+    e->alt.tmap_w = 0; e->alt.free_recorded = false;
+    e->la.valid = false;
     if (e->h_pin) cudaFreeHost(e->h_pin);
     e->d_img = e->d_img_next = e->d_mask = nullptr; e->prefetched.valid = false; e->d_sum = e->d_msum = e->d_bandsum = nullptr; e->d_det = nullptr;
     e->d_kp_a = e->d_kp_b = e->d_out_kp = nullptr; e->d_desc = e->d_out_desc = nullptr; e->d_patches = nullptr;
@@ -436,9 +441,43 @@ int upload_frames(surf_engine *e, const BatchIn &in, uint8_t *dst, cudaStream_t 
     return SURF_OK;
 }
 
+// Exchanges the current detect set with the alternate one.
+void swap_detect_sets(surf_engine *e)
+{
+    surf_engine::DetectSet &a = e->alt;
+    std::swap(e->d_sum, a.d_sum);
+    std::swap(e->d_kp_a, a.d_kp_a);
+    std::swap(e->d_kp_b, a.d_kp_b);
+    std::swap(e->sorted, a.sorted);
+    std::swap(e->d_counts, a.d_counts);
+    std::swap(e->tmap[0], a.tmap[0]);
+    std::swap(e->tmap[1], a.tmap[1]);
+    std::swap(e->tile_oct[0], a.tile_oct[0]);
+    std::swap(e->tile_oct[1], a.tile_oct[1]);
+    std::swap(e->tmap_w, a.tmap_w);
+    std::swap(e->tmap_h, a.tmap_h);
+    std::swap(e->tmap_b, a.tmap_b);
+    std::swap(e->tmap_layers, a.tmap_layers);
+    std::swap(e->tmap_ok[0], a.tmap_ok[0]);
+    std::swap(e->tmap_ok[1], a.tmap_ok[1]);
+    std::swap(e->ev_set_free, a.ev_free);
+    std::swap(e->set_free_recorded, a.free_recorded);
+}
+
+// A look-ahead that will not be consumed: later work on the main stream must still come after it (the two share the
+// determinant pyramid, the band sums and the mask integral).
+int discard_lookahead(surf_engine *e)
+{
+    if (!e->la.valid) return SURF_OK;
+    e->la.valid = false;
+    CU(e, cudaStreamWaitEvent(e->stream, e->ev_la_done, 0));
+    return SURF_OK;
+}
+
 // Uploads (or references) the frames; returns the device view.
 int stage_images(surf_engine *e, const BatchIn &in, ImageRef *ref)
 {
+    if (int rc = discard_lookahead(e)) return rc;
     if (in.in_mem == SURF_MEM_DEVICE) {
         ref->ptr = in.images;
         ref->pitch = in.pitch;
@@ -520,6 +559,8 @@ int run_detect(surf_engine *e, const ImageRef &img, const uint32_t *msum, const 
     rec(e, EV_HESSIAN_NMS);
     e->sorted = launch_sort(e->d_kp_a, e->d_kp_b, e->d_counts, e->cap, B, e->stream, &e->launches);
     rec(e, EV_SORT);
+    CU(e, cudaEventRecord(e->ev_detect_done, e->stream));
+    e->detect_done_recorded = true;
     CU(e, cudaGetLastError());
     return SURF_OK;
 }
@@ -529,6 +570,7 @@ int run_describe_pack(surf_engine *e, const ImageRef &img, const FrameGeo &geo, 
                       uint8_t *patches, bool pack)
 {
     const surf_params &p = e->params;
+    rec(e, EV_DESC_START);
     launch_zero(e->d_ndel, B, e->stream, &e->launches);
     launch_zero(e->d_misc, kMiscWords, e->stream, &e->launches);
     launch_offsets(e->d_counts, nullptr, e->cap, B, e->d_off_in, e->stream, &e->launches);
@@ -567,6 +609,9 @@ int run_describe_pack(surf_engine *e, const ImageRef &img, const FrameGeo &geo, 
                     &e->launches);
     }
     rec(e, EV_PACK);
+    // the detect set (integral images, keypoints, counters) is free for a look-ahead once these kernels end
+    CU(e, cudaEventRecord(e->ev_set_free, e->stream));
+    e->set_free_recorded = true;
     CU(e, cudaGetLastError());
     return SURF_OK;
 }
@@ -617,7 +662,7 @@ void collect_timings(surf_engine *e)
     t.hessian = ms(EV_INTEGRAL, EV_HESSIAN_NMS);  // Hessian + maxima of all octaves, interleaved
     t.nms = 0;
     t.sort = ms(EV_HESSIAN_NMS, EV_SORT);
-    t.describe = ms(EV_SORT, EV_DESCRIBE);
+    t.describe = ms(EV_DESC_START, EV_DESCRIBE);
     t.pack = ms(EV_DESCRIBE, EV_PACK);
     t.d2h = ms(EV_PACK, EV_END);
     t.total = ms(EV_START, EV_END);
@@ -672,6 +717,16 @@ int surf_create(const surf_params *params, int device, int max_width, int max_he
     cudaEventCreateWithFlags(&e->ev_free_cur, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&e->ev_free_next, cudaEventDisableTiming);
     cudaStreamCreateWithFlags(&e->upload_stream, cudaStreamNonBlocking);
+    // Default priority on purpose.  Measured (64 frames, 640x480): with a high-priority look-ahead stream and
+    // descriptor CTAs that turn over every 8-128 keypoints the Hessian kernels run at full speed but stretch the
+    // descriptor stage by more than they save (8.24k frames/s); queued behind the persistent descriptor CTAs they
+    // fill the slots those leave free (8.60k frames/s against 8.24k without look-ahead).
+    cudaStreamCreateWithFlags(&e->la_stream, cudaStreamNonBlocking);
+    for (int i = 0; i < EV_COUNT; i++) cudaEventCreate(&e->la_ev[i]);
+    cudaEventCreateWithFlags(&e->ev_detect_done, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&e->ev_la_done, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&e->ev_set_free, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&e->alt.ev_free, cudaEventDisableTiming);
     upload_tables();
     rc = alloc_workspace(e);
     if (rc == SURF_OK && cudaGetLastError() != cudaSuccess) rc = SURF_ERR_CUDA;
@@ -712,6 +767,16 @@ void surf_destroy(surf_engine *e)
         cudaStreamSynchronize(e->upload_stream);
         cudaStreamDestroy(e->upload_stream);
     }
+    if (e->la_stream) {
+        cudaStreamSynchronize(e->la_stream);
+        cudaStreamDestroy(e->la_stream);
+    }
+    for (int i = 0; i < EV_COUNT; i++)
+        if (e->la_ev[i]) cudaEventDestroy(e->la_ev[i]);
+    if (e->ev_detect_done) cudaEventDestroy(e->ev_detect_done);
+    if (e->ev_la_done) cudaEventDestroy(e->ev_la_done);
+    if (e->ev_set_free) cudaEventDestroy(e->ev_set_free);
+    if (e->alt.ev_free) cudaEventDestroy(e->alt.ev_free);
     if (e->stream) cudaStreamDestroy(e->stream);
     delete e;
 }
@@ -722,9 +787,12 @@ int surf_set_params(surf_engine *e, const surf_params *params)
     int rc = check_params(e, params);
     if (rc) return rc;
     if ((rc = ensure_device(e))) return rc;
+    CU(e, cudaStreamSynchronize(e->la_stream));
+    e->la.valid = false;
     CU(e, cudaStreamSynchronize(e->stream));
     e->params = *params;
     e->tmap_w = 0;  // layer tables depend on the parameters
+    e->alt.tmap_w = 0;
     return alloc_det_and_desc(e);
 }
 
@@ -768,13 +836,31 @@ int surf_submit_batch(surf_engine *e, const uint8_t *images, int in_mem, int bat
     e->pending.active = false;
     e->launches = 0;
     const FrameGeo geo = make_geo(width, height);
-    rec(e, EV_START);
     ImageRef img;
-    if ((rc = stage_images(e, in, &img))) return rc;
-    const uint32_t *msum = nullptr;
-    if ((rc = stage_mask(e, in, geo, &msum))) return rc;
-    rec(e, EV_H2D);
-    if ((rc = run_detect(e, img, msum, geo, batch))) return rc;
+    const surf_engine::LookAhead &la = e->la;
+    if (la.valid && la.images == images && la.in_mem == in_mem && la.batch == batch && la.width == width && la.height == height &&
+        la.pitch == pitch && la.frame_stride == frame_stride && la.mask == mask && la.mask_pitch == mask_pitch) {
+        // stages 1-3 of these frames already ran (or are running) on the look-ahead stream: adopt their detect set,
+        // their stage events and, for host frames, the frame buffer they were uploaded into
+        e->la.valid = false;
+        swap_detect_sets(e);
+        for (int i = 0; i < EV_COUNT; i++) std::swap(e->ev[i], e->la_ev[i]);
+        if (in_mem == SURF_MEM_HOST) {
+            std::swap(e->d_img, e->d_img_next);
+            std::swap(e->ev_free_cur, e->ev_free_next);
+            std::swap(e->free_cur_recorded, e->free_next_recorded);
+        }
+        img = la.img;
+        e->launches = la.launches;
+        CU(e, cudaStreamWaitEvent(e->stream, e->ev_la_done, 0));
+    } else {
+        rec(e, EV_START);
+        if ((rc = stage_images(e, in, &img))) return rc;
+        const uint32_t *msum = nullptr;
+        if ((rc = stage_mask(e, in, geo, &msum))) return rc;
+        rec(e, EV_H2D);
+        if ((rc = run_detect(e, img, msum, geo, batch))) return rc;
+    }
     if ((rc = run_describe_pack(e, img, geo, batch, want_descriptors != 0, nullptr, true))) return rc;
     if ((rc = fetch_counts(e, batch))) return rc;
     if (in_mem == SURF_MEM_HOST) {  // the staged frames (d_img) are free again after these kernels
@@ -795,6 +881,11 @@ int surf_prefetch_batch(surf_engine *e, const uint8_t *images, int batch, int wi
     if (rc) return rc;
     if ((rc = ensure_device(e))) return rc;
     if (!e->d_img_next) CU(e, cudaMalloc(&e->d_img_next, e->img_pitch * e->max_h * e->max_b));
+    if (e->la.valid) {  // a pending look-ahead may own the second frame buffer: it is given up
+        e->la.valid = false;
+        CU(e, cudaStreamWaitEvent(e->upload_stream, e->ev_la_done, 0));
+        CU(e, cudaStreamWaitEvent(e->stream, e->ev_la_done, 0));
+    }
     // the upload may start as soon as the last kernels that read this buffer (two batches ago) have ended; it
     // overlaps the kernels of the batch in flight, which read the other buffer.  The host does not wait.
     if (e->free_next_recorded) CU(e, cudaStreamWaitEvent(e->upload_stream, e->ev_free_next, 0));
@@ -803,6 +894,76 @@ int surf_prefetch_batch(surf_engine *e, const uint8_t *images, int batch, int wi
     surf_engine::Prefetched &pf = e->prefetched;
     pf.images = images; pf.batch = batch; pf.width = width; pf.height = height; pf.pitch = pitch;
     pf.frame_stride = frame_stride; pf.valid = true;
+    return SURF_OK;
+}
+
+int surf_lookahead_batch(surf_engine *e, const uint8_t *images, int in_mem, int batch, int width, int height, size_t pitch,
+                         size_t frame_stride, const uint8_t *mask, size_t mask_pitch)
+{
+    BatchIn in{images, in_mem, batch, width, height, pitch, frame_stride, mask, mask_pitch};
+    int rc = check_frame_args(e, in);
+    if (rc) return rc;
+    if ((rc = ensure_device(e))) return rc;
+    if (e->la.valid) {  // replaces an unused look-ahead: same stream, so it simply queues behind it
+        e->la.valid = false;
+    }
+    e->prefetched.valid = false;  // the second frame buffer is about to be overwritten
+    surf_engine::DetectSet &a = e->alt;
+    if (!a.d_sum) {
+        const FrameGeo g = make_geo(e->max_w, e->max_h);
+        const size_t nk = (size_t)e->max_b * e->cap;
+        CU(e, cudaMalloc(&a.d_sum, g.sum_frame * sizeof(uint32_t) * e->max_b));
+        CU(e, cudaMalloc(&a.d_kp_a, nk * sizeof(surf_keypoint)));
+        CU(e, cudaMalloc(&a.d_kp_b, nk * sizeof(surf_keypoint)));
+        CU(e, cudaMalloc(&a.d_counts, sizeof(int) * (e->max_b + 1)));
+    }
+    if (in_mem == SURF_MEM_HOST && !e->d_img_next) CU(e, cudaMalloc(&e->d_img_next, e->img_pitch * e->max_h * e->max_b));
+    cudaStream_t ls = e->la_stream;
+    // Ordering: after stages 1-3 of the batch in flight (the determinant pyramid, band sums and mask integral are
+    // shared scratch; it is also the overlap wanted: these kernels run beside that batch's descriptor stage), after
+    // the stage-4 kernels that last read the alternate set, and after the last readers of the second frame buffer.
+    if (e->detect_done_recorded) CU(e, cudaStreamWaitEvent(ls, e->ev_detect_done, 0));
+    if (a.free_recorded) CU(e, cudaStreamWaitEvent(ls, a.ev_free, 0));
+    if (in_mem == SURF_MEM_HOST && e->free_next_recorded) CU(e, cudaStreamWaitEvent(ls, e->ev_free_next, 0));
+    // run stages 1-3 with the alternate set, the look-ahead stream and the look-ahead's own stage events in place
+    const int launches0 = e->launches;
+    e->launches = 0;
+    swap_detect_sets(e);
+    std::swap(e->stream, e->la_stream);
+    for (int i = 0; i < EV_COUNT; i++) std::swap(e->ev[i], e->la_ev[i]);
+    const FrameGeo geo = make_geo(width, height);
+    ImageRef img;
+    rec(e, EV_START);
+    if (in_mem == SURF_MEM_DEVICE) {
+        img.ptr = images;
+        img.pitch = pitch;
+        img.frame_stride = frame_stride;
+    } else {
+        rc = upload_frames(e, in, e->d_img_next, e->stream);
+        img.ptr = e->d_img_next;
+        img.pitch = e->img_pitch;
+        img.frame_stride = e->img_pitch * height;
+    }
+    const uint32_t *msum = nullptr;
+    if (!rc) rc = stage_mask(e, in, geo, &msum);
+    if (!rc) {
+        rec(e, EV_H2D);
+        rc = run_detect(e, img, msum, geo, batch);
+    }
+    // run_detect recorded ev_detect_done on the look-ahead stream: that is this look-ahead's completion; the main
+    // stream's own marker must be recorded again by its next run_detect
+    std::swap(e->ev_detect_done, e->ev_la_done);
+    e->detect_done_recorded = false;
+    for (int i = 0; i < EV_COUNT; i++) std::swap(e->ev[i], e->la_ev[i]);
+    std::swap(e->stream, e->la_stream);
+    swap_detect_sets(e);
+    const int la_launches = e->launches;
+    e->launches = launches0;
+    if (rc) return rc;
+    surf_engine::LookAhead &la = e->la;
+    la.images = images; la.mask = mask; la.in_mem = in_mem; la.batch = batch; la.width = width; la.height = height;
+    la.pitch = pitch; la.frame_stride = frame_stride; la.mask_pitch = mask_pitch; la.img = img; la.launches = la_launches;
+    la.valid = true;
     return SURF_OK;
 }
 

@@ -13,7 +13,7 @@
 
 using namespace surfb200;  // private header of the library's own translation units
 
-enum Ev { EV_START, EV_H2D, EV_INTEGRAL, EV_HESSIAN_NMS, EV_SORT, EV_DESCRIBE, EV_PACK, EV_END, EV_COUNT };
+enum Ev { EV_START, EV_H2D, EV_INTEGRAL, EV_HESSIAN_NMS, EV_SORT, EV_DESC_START, EV_DESCRIBE, EV_PACK, EV_END, EV_COUNT };
 
 struct Pending {
     bool active = false;
@@ -53,6 +53,35 @@ struct surf_engine {
         size_t pitch = 0, frame_stride = 0;
         bool valid = false;
     } prefetched;
+    // surf_lookahead_batch: stages 1-3 of the NEXT batch run on their own stream, into the second detect set, while
+    // the submitted batch is in its descriptor stage.  A detect set is what stages 1-3 write and stage 4 reads:
+    // integral images, the two keypoint buffers, the per-frame counters, and the TMA maps of the integral images.
+    // The members below (d_sum, d_kp_a, d_kp_b, d_counts, sorted, tmap*) are the CURRENT set; `alt` holds the other one.
+    struct DetectSet {
+        uint32_t *d_sum = nullptr;
+        surf_keypoint *d_kp_a = nullptr, *d_kp_b = nullptr, *sorted = nullptr;
+        int *d_counts = nullptr;
+        CUtensorMap tmap[2];
+        TileOctave tile_oct[2];
+        int tmap_w = 0, tmap_h = 0, tmap_b = 0, tmap_layers = 0;
+        bool tmap_ok[2] = {false, false};
+        cudaEvent_t ev_free = nullptr;   // end of the stage-4 kernels that last read this set
+        bool free_recorded = false;
+    } alt;
+    cudaEvent_t ev_set_free = nullptr;   // the current set's ev_free
+    bool set_free_recorded = false;
+    cudaStream_t la_stream = nullptr;
+    cudaEvent_t la_ev[EV_COUNT]{};       // stage events of the look-ahead (swapped with ev[] while it is recorded / used)
+    cudaEvent_t ev_detect_done = nullptr, ev_la_done = nullptr;
+    bool detect_done_recorded = false;
+    struct LookAhead {
+        bool valid = false;
+        const uint8_t *images = nullptr, *mask = nullptr;
+        int in_mem = 0, batch = 0, width = 0, height = 0;
+        size_t pitch = 0, frame_stride = 0, mask_pitch = 0;
+        ImageRef img{};                  // device view of the frames the look-ahead ran on
+        int launches = 0;
+    } la;
     uint8_t *d_mask = nullptr;
     uint32_t *d_sum = nullptr, *d_msum = nullptr, *d_bandsum = nullptr;
     float *d_det = nullptr;     size_t det_words = 0;

@@ -32,7 +32,7 @@ MEM_HOST, MEM_DEVICE = 0, 1
 ABI_SYMBOLS = [
     "surf_create", "surf_destroy", "surf_set_params", "surf_get_params", "surf_last_error", "surf_required_capacity",
     "surf_descriptor_size", "surf_get_timings", "surf_stream", "surf_detect", "surf_compute", "surf_detect_and_compute",
-    "surf_detect_and_compute_batch", "surf_submit_batch", "surf_prefetch_batch", "surf_collect_batch", "surf_device_results", "surf_sync",
+    "surf_detect_and_compute_batch", "surf_submit_batch", "surf_prefetch_batch", "surf_lookahead_batch", "surf_collect_batch", "surf_device_results", "surf_sync",
     "surf_integral", "surf_hessian_layer", "surf_raw_keypoints", "surf_describe_keypoints", "surf_match_knn",
     "surf_match_ratio", "surf_merge_topk", "surf_version", "surf_match_prev", "surf_stream_reset",
     "surf_device_matches", "surf_set_match_mode", "surf_match_redo_count", "surf_set_async_outputs",
@@ -104,6 +104,7 @@ def load_library():
     L.surf_submit_batch.argtypes = [vp, vp, i32, i32, i32, i32, sz, sz, vp, sz, i32]
     L.surf_collect_batch.argtypes = [vp, vp, vp, i32, lng, vp]
     L.surf_prefetch_batch.argtypes = [vp, vp, i32, i32, i32, sz, sz]
+    L.surf_lookahead_batch.argtypes = [vp, vp, i32, i32, i32, i32, sz, sz, vp, sz]
     L.surf_rand_create.argtypes = [C.c_uint32, C.POINTER(vp)]
     L.surf_rand_destroy.argtypes = [vp]
     L.surf_rand_destroy.restype = None
@@ -310,6 +311,13 @@ class SURF:
         """Starts the upload of the NEXT batch's host frames while the submitted batch computes; the following
         submit() of the same pointer and geometry uses them (surf_prefetch_batch)."""
         self._check(self._lib.surf_prefetch_batch(self._h, images_ptr, B, W, H, pitch, frame_stride))
+
+    def lookahead(self, images_ptr: int, in_mem: int, B: int, W: int, H: int, pitch: int, frame_stride: int,
+                  mask_ptr: int = 0, mask_pitch: int = 0):
+        """Uploads the NEXT batch (host frames) and runs its stages 1-3 beside the submitted batch's descriptor stage;
+        the following submit() with the same arguments continues from there (surf_lookahead_batch)."""
+        self._check(self._lib.surf_lookahead_batch(self._h, images_ptr, in_mem, B, W, H, pitch, frame_stride,
+                                                   mask_ptr or None, mask_pitch))
 
     def collect(self, kps_ptr: int, desc_ptr: int, out_mem: int, capacity: int, offsets: np.ndarray):
         self._check(self._lib.surf_collect_batch(self._h, kps_ptr or None, desc_ptr or None, out_mem, capacity,

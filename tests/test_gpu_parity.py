@@ -586,6 +586,61 @@ def test_prefetched_upload_gives_identical_results():
         e.close()
 
 
+@pytest.mark.parametrize("in_mem_name,use_mask", [("host", False), ("device", False), ("host", True), ("device", True)])
+def test_lookahead_detect_gives_identical_results(in_mem_name, use_mask):
+    """surf_lookahead_batch runs stages 1-3 of batch i+1 on a second stream and buffer set while batch i is in its
+    descriptor stage; results must be the bytes of the plain path, over several batches, and a submit of OTHER frames
+    must discard the look-ahead."""
+    import torch
+
+    from surffeatures_b200 import KEYPOINT_DTYPE, MEM_DEVICE, MEM_HOST, SURF
+
+    frames = speckle.speckle_stream(10, 240, 320, seed=23, fresh=0.0)
+    mask = np.zeros((240, 320), np.uint8)
+    mask[30:200, 40:300] = 255
+    e = SURF(100, 4, 3, max_width=320, max_height=240, max_batch=2, max_keypoints=4096)
+    try:
+        ref = [e.detectAndComputeBatchPacked(frames[2 * i:2 * i + 2], mask=mask if use_mask else None) for i in range(5)]
+        ref = [(k.copy(), d.copy(), o.copy()) for k, d, o in ref]
+        if in_mem_name == "host":
+            store, mstore, mem = torch.from_numpy(frames).pin_memory(), torch.from_numpy(mask).pin_memory(), MEM_HOST
+        else:
+            store, mstore, mem = torch.from_numpy(frames).cuda(), torch.from_numpy(mask).cuda(), MEM_DEVICE
+        torch.cuda.synchronize()
+        mptr, mpitch = (mstore.data_ptr(), 320) if use_mask else (0, 0)
+        cap = 2 * 4096
+        k = torch.zeros((cap, 7), dtype=torch.float32).pin_memory()
+        d = torch.zeros((cap, 64), dtype=torch.float32).pin_memory()
+        off = np.zeros(3, np.int32)
+
+        def ptr(i):
+            return store[2 * i:2 * i + 2].data_ptr()
+
+        # 0 -> 1 -> 2 -> 3 each looked ahead; then look ahead at 0 but submit 4 (discard); then 1 without look-ahead
+        plan = [(0, 1), (1, 2), (2, 3), (3, 0), (4, None), (1, None)]
+        for cur, nxt in plan:
+            e.submit(ptr(cur), mem, 2, 320, 240, 320, 320 * 240, True, mptr, mpitch)
+            if nxt is not None:
+                e.lookahead(ptr(nxt), mem, 2, 320, 240, 320, 320 * 240, mptr, mpitch)
+            e.collect(k.data_ptr(), d.data_ptr(), MEM_HOST, cap, off)
+            rk, rd, ro = ref[cur]
+            n = int(off[-1])
+            assert np.array_equal(off, ro), (cur, off, ro)
+            assert k.numpy()[:n].copy().view(KEYPOINT_DTYPE).reshape(-1).tobytes() == rk.tobytes()
+            assert np.array_equal(d.numpy()[:n], rd)
+            t = e.timings()
+            assert t["hessian"] > 0 and t["describe"] > 0
+        # single-frame calls after a pending look-ahead still work (it is discarded, the scratch is ordered)
+        e.submit(ptr(0), mem, 2, 320, 240, 320, 320 * 240, True, mptr, mpitch)
+        e.lookahead(ptr(1), mem, 2, 320, 240, 320, 320 * 240, mptr, mpitch)
+        e.collect(k.data_ptr(), d.data_ptr(), MEM_HOST, cap, off)
+        kk, dd = e.detectAndCompute(frames[5], mask=mask if use_mask else None)
+        k5, d5, o5 = ref[2]
+        assert kk.tobytes() == k5[o5[1]:o5[2]].tobytes() and np.array_equal(dd, d5[o5[1]:o5[2]])
+    finally:
+        e.close()
+
+
 @pytest.mark.parametrize("shape,thr,octaves,layers", [((251, 333), 100, 4, 3), ((333, 251), 200, 3, 1),
                                                       ((480, 640), 300, 4, 4), ((200, 1000), 100, 2, 2),
                                                       ((640, 480), 100, 5, 2)])
