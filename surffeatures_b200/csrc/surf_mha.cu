@@ -34,7 +34,7 @@ struct surf_mha {
     std::vector<std::string> names;      // kept "<dir><frame field name>.png"
     std::vector<uint8_t> validity;       // flags of frames first..last
     std::vector<long> frame_offset;      // file offset of every kept frame
-    uint8_t *stage[2] = {nullptr, nullptr};  // pinned staging buffers of the sweep driver
+    uint8_t *stage[3] = {nullptr, nullptr, nullptr};  // pinned staging buffers of the sweep driver
     size_t stage_bytes = 0;
     char err[256] = "";
 };
@@ -333,18 +333,30 @@ int surf_sweep_mha(surf_engine *e, surf_mha *m, const float crop_ratios[4], cons
             if (f.valid()) f.get();
         pending.clear();
     };
-    // chunk c is read from the file while chunk c-1 is on the GPU (two pinned buffers)
-    if (n > 0) start_chunk(0, n < B ? n : B, m->stage[0]);
+    // Three pinned buffers: while chunk c is in its descriptor stage, chunk c+1 (already read) is uploaded and run
+    // through stages 1-3 by surf_lookahead_batch, and chunk c+2 is read from the file.
+    auto chunk_count = [&](int c) {
+        const long s0 = (long)c * B;
+        return s0 >= n ? 0 : (int)(n - s0 < B ? n - s0 : B);
+    };
+    auto chunk_view = [&](int c) { return m->stage[c % 3] + rect[0]; };  // cropData: the roi of every frame (rows already selected)
+    if (n > 0) {
+        start_chunk(0, chunk_count(0), m->stage[0]);
+        wait_chunk();
+        if (chunk_count(1)) start_chunk(B, chunk_count(1), m->stage[1]);
+    }
     std::vector<int32_t> off((size_t)B + 1);
     for (int start = 0, c = 0; start < n; start += B, c++) {
-        const int cnt = n - start < B ? n - start : B;
-        wait_chunk();
-        if (start + B < n) {
-            const int nxt = n - (start + B) < B ? n - (start + B) : B;
-            start_chunk(start + B, nxt, m->stage[(c + 1) & 1]);
-        }
-        const uint8_t *view = m->stage[c & 1] + rect[0];  // cropData: the roi of every frame (rows already selected)
+        const int cnt = chunk_count(c);
+        const uint8_t *view = chunk_view(c);
         rc = surf_submit_batch(e, view, SURF_MEM_HOST, cnt, rect[2], rect[3], (size_t)m->width, band_bytes, cmask, mask_pitch, 1);
+        if (!rc && chunk_count(c + 1)) {
+            wait_chunk();  // chunk c+1 is in its buffer
+            rc = surf_lookahead_batch(e, chunk_view(c + 1), SURF_MEM_HOST, chunk_count(c + 1), rect[2], rect[3], (size_t)m->width,
+                                      band_bytes, cmask, mask_pitch);
+            // chunk c-1's buffer is free: its upload ended before its results were collected
+            if (!rc && chunk_count(c + 2)) start_chunk((c + 2) * B, chunk_count(c + 2), m->stage[(c + 2) % 3]);
+        }
         if (!rc) {
             if (keypoints || descriptors)
                 rc = surf_collect_batch(e, keypoints ? keypoints + total : nullptr, descriptors ? descriptors + (size_t)total * D : nullptr,
