@@ -564,34 +564,47 @@ struct TileC {
     static constexpr int tile_bytes = tile_p * tile_h * 4;
 };
 
-template <int OCT, int LPO>
-__device__ __forceinline__ void layer_responses_c(const int *__restrict__ o, int l, float &dx, float &dy, float &dc)
+// Filter geometry and weights of layer L as compile-time constants.  cvRound(size / 9.f * k) for the sizes that
+// occur (multiples of 3) never meets a tie -- the fraction is 0, 1/3 or 2/3 -- so it equals the integer expression
+// below; the weights are IEEE fp32 quotients evaluated by the compiler (left in the kernel, nvcc emits a full
+// division sequence for each of them: they are not folded).
+template <int OCT, int L>
+struct LayerK {
+    static constexpr int size = (9 + 6 * L) << OCT;
+    __host__ __device__ static constexpr int r(int k) { return (2 * size * k + 9) / 18; }
+    static constexpr float xx0 = 1 / ((float)(r(3) - r(0)) * (r(7) - r(2)));
+    static constexpr float xx1 = -2 / ((float)(r(6) - r(3)) * (r(7) - r(2)));
+    static constexpr float xx2 = 1 / ((float)(r(9) - r(6)) * (r(7) - r(2)));
+    static constexpr float yy0 = 1 / ((float)(r(7) - r(2)) * (r(3) - r(0)));
+    static constexpr float yy1 = -2 / ((float)(r(7) - r(2)) * (r(6) - r(3)));
+    static constexpr float yy2 = 1 / ((float)(r(7) - r(2)) * (r(9) - r(6)));
+    static constexpr float xy0 = 1 / ((float)(r(4) - r(1)) * (r(4) - r(1)));
+    static constexpr float xy1 = -1 / ((float)(r(8) - r(5)) * (r(4) - r(1)));
+    static constexpr float xy2 = -1 / ((float)(r(4) - r(1)) * (r(8) - r(5)));
+    static constexpr float xy3 = 1 / ((float)(r(8) - r(5)) * (r(8) - r(5)));
+};
+
+template <int OCT, int LPO, int L>
+__device__ __forceinline__ void layer_responses_k(const int *__restrict__ o, float &dx, float &dy, float &dc)
 {
+    using K = LayerK<OCT, L>;
     constexpr int P = TileC<OCT, LPO>::tile_p;
-    const int size = (9 + 6 * l) << OCT;
-    const float ratio = (float)size / 9;
-    const int r0 = __float2int_rn(ratio * 0), r1 = __float2int_rn(ratio * 1), r2 = __float2int_rn(ratio * 2);
-    const int r3 = __float2int_rn(ratio * 3), r4 = __float2int_rn(ratio * 4), r5 = __float2int_rn(ratio * 5);
-    const int r6 = __float2int_rn(ratio * 6), r7 = __float2int_rn(ratio * 7), r8 = __float2int_rn(ratio * 8);
-    const int r9 = __float2int_rn(ratio * 9);
+    constexpr int r0 = K::r(0), r1 = K::r(1), r2 = K::r(2), r3 = K::r(3), r4 = K::r(4);
+    constexpr int r5 = K::r(5), r6 = K::r(6), r7 = K::r(7), r8 = K::r(8), r9 = K::r(9);
     {   // Dxx: rows r2, r7; columns r0, r3, r6, r9
         const int c0 = o[r7 * P + r0] - o[r2 * P + r0], c1 = o[r7 * P + r3] - o[r2 * P + r3];
         const int c2 = o[r7 * P + r6] - o[r2 * P + r6], c3 = o[r7 * P + r9] - o[r2 * P + r9];
-        const float w0 = 1 / ((float)(r3 - r0) * (r7 - r2)), w1 = -2 / ((float)(r6 - r3) * (r7 - r2));
-        const float w2 = 1 / ((float)(r9 - r6) * (r7 - r2));
-        double d = (double)((float)(c1 - c0) * w0);
-        d += (double)((float)(c2 - c1) * w1);
-        d += (double)((float)(c3 - c2) * w2);
+        double d = (double)((float)(c1 - c0) * K::xx0);
+        d += (double)((float)(c2 - c1) * K::xx1);
+        d += (double)((float)(c3 - c2) * K::xx2);
         dx = (float)d;
     }
     {   // Dyy: rows r0, r3, r6, r9; columns r2, r7
         const int q0 = o[r0 * P + r7] - o[r0 * P + r2], q1 = o[r3 * P + r7] - o[r3 * P + r2];
         const int q2 = o[r6 * P + r7] - o[r6 * P + r2], q3 = o[r9 * P + r7] - o[r9 * P + r2];
-        const float w0 = 1 / ((float)(r7 - r2) * (r3 - r0)), w1 = -2 / ((float)(r7 - r2) * (r6 - r3));
-        const float w2 = 1 / ((float)(r7 - r2) * (r9 - r6));
-        double d = (double)((float)(q1 - q0) * w0);
-        d += (double)((float)(q2 - q1) * w1);
-        d += (double)((float)(q3 - q2) * w2);
+        double d = (double)((float)(q1 - q0) * K::yy0);
+        d += (double)((float)(q2 - q1) * K::yy1);
+        d += (double)((float)(q3 - q2) * K::yy2);
         dy = (float)d;
     }
     {   // Dxy: rows / columns r1, r4, r5, r8
@@ -599,13 +612,26 @@ __device__ __forceinline__ void layer_responses_c(const int *__restrict__ o, int
         const int b1 = o[r1 * P + r5] + o[r4 * P + r8] - o[r4 * P + r5] - o[r1 * P + r8];
         const int b2 = o[r5 * P + r1] + o[r8 * P + r4] - o[r8 * P + r1] - o[r5 * P + r4];
         const int b3 = o[r5 * P + r5] + o[r8 * P + r8] - o[r8 * P + r5] - o[r5 * P + r8];
-        const float w0 = 1 / ((float)(r4 - r1) * (r4 - r1)), w1 = -1 / ((float)(r8 - r5) * (r4 - r1));
-        const float w2 = -1 / ((float)(r4 - r1) * (r8 - r5)), w3 = 1 / ((float)(r8 - r5) * (r8 - r5));
-        double d = (double)((float)b0 * w0);
-        d += (double)((float)b1 * w1);
-        d += (double)((float)b2 * w2);
-        d += (double)((float)b3 * w3);
+        double d = (double)((float)b0 * K::xy0);
+        d += (double)((float)b1 * K::xy1);
+        d += (double)((float)b2 * K::xy2);
+        d += (double)((float)b3 * K::xy3);
         dc = (float)d;
+    }
+}
+
+// run-time layer index -> the compile-time instance (called from fully unrolled loops: the switch folds away)
+template <int OCT, int LPO>
+__device__ __forceinline__ void layer_responses_c(const int *__restrict__ o, int l, float &dx, float &dy, float &dc)
+{
+    static_assert(LPO <= 6, "extend the dispatch");
+    switch (l) {
+        case 0: layer_responses_k<OCT, LPO, 0>(o, dx, dy, dc); break;
+        case 1: layer_responses_k<OCT, LPO, 1>(o, dx, dy, dc); break;
+        case 2: layer_responses_k<OCT, LPO, 2>(o, dx, dy, dc); break;
+        case 3: layer_responses_k<OCT, LPO, 3>(o, dx, dy, dc); break;
+        case 4: layer_responses_k<OCT, LPO, 4>(o, dx, dy, dc); break;
+        default: layer_responses_k<OCT, LPO, 5>(o, dx, dy, dc); break;
     }
 }
 
