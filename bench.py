@@ -332,21 +332,25 @@ def run_ours(args):
     dom = max(stage_key, key=lambda k: stage_ms[k])
     dom_bytes = (alg["hessian"] + alg["nms"] if dom == "hessian" else alg[dom]) * B
     achieved = dom_bytes / (stage_ms[dom] * 1e-3) / 1e9
-    # dram__bytes_read+write of the describe-stage kernels from one `ncu --set full` capture of this very
-    # command at batch 64 (profiles/r1/describe_stage_v10_ncu_summary.txt): 189.9 MB read + 38.9 MB written
-    traffic = 228.8e6 if (dom == "describe" and B == 64) else None
+    # dram__bytes_read+write and smsp__inst_executed of the describe-stage kernels (k_orient, four window kernels, four
+    # k_patch_descriptor) from one `ncu --set full` capture of this very command at batch 64
+    # (profiles/r1/describe_stage_v17_ncu_summary.txt): 323.3 MB read + 77.0 MB written, 4.63 G warp instructions
+    NCU_DESCRIBE_TRAFFIC, NCU_DESCRIBE_INST = 400.4e6, 4.63e9
+    traffic = NCU_DESCRIBE_TRAFFIC if (dom == "describe" and B == 64) else None
     roofline = {"bound": "hbm", "kernel": {"integral": "k_band_colsum+k_band_integral",
                                            "hessian": "k_hessian_nms_tma_c<0|1>+k_hessian+k_nms",
-                                           "describe": "k_orient+k_descriptor<5 size classes>"}[dom],
+                                           "describe": "k_orient+k_descriptor<0..2>+k_descriptor_big+k_patch_descriptor"}[dom],
                 "achieved": achieved, "peak": peak, "peak_source": how + " (MEASURED_PEAKS.json hbm_gbs)",
                 "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                "limiter": "instruction issue, not HBM: smsp__issue_active 68-86 % in the descriptor kernels "
-                           "(~6300 exact bilinear taps per keypoint); see profiles/r1/",
+                "limiter": "instruction issue, not HBM: smsp__issue_active 68-86 % in the window kernels "
+                           "(~6300 exact bilinear taps per keypoint at 33 instructions each); see profiles/r1/",
                 "peak_kind": "burst copy peak; the stage is timed inside a long step",
-                # the stage's real limiter: warp instructions issued (ncu smsp__inst_executed.sum of the describe
-                # kernels at batch 64, profiles/r1/) / stage time, against 148 SMs x 4 schedulers x SM clock
-                "issue_slots": ({"warp_inst_per_step": 6.52e9, "achieved_ginst_s": 6.52e9 / (stage_ms[dom] * 1e-3) / 1e9,
-                                 "peak_ginst_s": 148 * 4 * 1.965, "frac": 6.52e9 / (stage_ms[dom] * 1e-3) / (148 * 4 * 1.965e9)}
+                # the stage's real limiter: warp instructions issued (ncu, see above) / stage time, against
+                # 148 SMs x 4 schedulers x SM clock
+                "issue_slots": ({"warp_inst_per_step": NCU_DESCRIBE_INST,
+                                 "achieved_ginst_s": NCU_DESCRIBE_INST / (stage_ms[dom] * 1e-3) / 1e9,
+                                 "peak_ginst_s": 148 * 4 * 1.965,
+                                 "frac": NCU_DESCRIBE_INST / (stage_ms[dom] * 1e-3) / (148 * 4 * 1.965e9)}
                                 if (dom == "describe" and B == 64) else None),
                 "algorithmic_bytes_per_launch": dom_bytes, "ms_per_launch": stage_ms[dom],
                 "stage_ms_per_step": stage_ms,
