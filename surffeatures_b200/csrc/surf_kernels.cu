@@ -635,19 +635,58 @@ __device__ __forceinline__ void layer_responses_c(const int *__restrict__ o, int
     }
 }
 
+#ifndef SURF_HESS_MINB
+#define SURF_HESS_MINB 3
+#endif
+// Determinant of layer L at tile sample (ti, tj), or 0 where the reference leaves the layer's grid empty.
+template <int OCT, int LPO, int L>
+__device__ __forceinline__ float tile_det(const int *__restrict__ s_tile, int ti, int tj, int i0, int j0, int rows, int cols,
+                                          int W, int H, int xshift)
+{
+    using C = TileC<OCT, LPO>;
+    constexpr int step = C::step;
+    constexpr int size = (9 + 6 * L) << OCT;
+    constexpr int m = (size / 2) >> OCT;
+    const int i = i0 - 1 + ti, j = j0 - 1 + tj;
+    const int ni = 1 + (H - size) / step, nj = 1 + (W - size) / step;  // only used when the layer fits
+    const int ii = i - m, jj = j - m;
+    if (!(i >= 0 && j >= 0 && i < rows && j < cols && size <= H && size <= W && ii >= 0 && ii < ni && jj >= 0 && jj < nj)) return 0.f;
+    const int *o = s_tile + ((ti + C::m_max - m) * step) * C::tile_p + (tj + C::m_max - m) * step + xshift;
+    float dx, dy, dc;
+    layer_responses_k<OCT, LPO, L>(o, dx, dy, dc);
+    return dx * dy - 0.81f * dc * dc;
+}
+
+// Candidates of one middle layer whose lower (or upper) neighbour layer was not computed for the whole tile.
+constexpr int kLazyCap = 128;  // strict in-plane maxima cannot touch: at most 7 x 15 of them in the inner 14 x 30
+struct LazyList {
+    int count;
+    unsigned short pos[kLazyCap];   // ti << 8 | tj
+    float extra[kLazyCap][9];       // the missing layer's 3 x 3 determinants around the candidate
+};
+
+// The outermost layers (0 and LPO-1) only ever serve as the lower / upper neighbours of maxima candidates of layers
+// 1 and LPO-2.  They are NOT computed for the whole tile: phase 1 computes the middle layers, phase 2 finds the
+// samples of layers 1 and LPO-2 that beat the threshold, their 8 in-plane neighbours and the 9 of their computed
+// neighbour layer (1-2 % of the samples), phase 3 evaluates the missing layer at the 9 positions around each of
+// them (one thread per position), phase 4 finishes the comparison and refines.  Same determinant function, same
+// comparisons: the keypoints are those of the eager kernel, for 3/5 (LPO = 5) of the box filters.
 template <int OCT, int LPO>
-__global__ void __launch_bounds__(kTileThreads, 1024 / kTileThreads) k_hessian_nms_tma_c(const __grid_constant__ CUtensorMap tmap, int W, int H,
+__global__ void __launch_bounds__(kTileThreads, SURF_HESS_MINB) k_hessian_nms_tma_c(const __grid_constant__ CUtensorMap tmap, int W, int H,
                                                                     const uint32_t *__restrict__ msum, int SP, float thr,
                                                                     surf_keypoint *__restrict__ raw,
                                                                     int *__restrict__ counts, int cap)
 {
+    static_assert(LPO >= 4, "every middle layer must have at least one computed neighbour layer");
     using C = TileC<OCT, LPO>;
     constexpr int step = C::step;
+    constexpr int NM = LPO - 2;  // middle layers 1 .. LPO-2, stored at index l - 1
     extern __shared__ __align__(128) unsigned char tile_smem_raw[];
     unsigned char *tile_smem = tile_smem_raw + ((128u - (smem_u32(tile_smem_raw) & 127u)) & 127u);
     int *s_tile = reinterpret_cast<int *>(tile_smem);
     float *s_det = reinterpret_cast<float *>(tile_smem + C::tile_bytes);
     __shared__ __align__(8) uint64_t s_bar;
+    __shared__ LazyList s_lazy[2];  // [0]: candidates of layer 1 (layer 0 missing), [1]: of layer LPO-2 (layer LPO-1 missing)
 
     const int tid = threadIdx.x;
     const int tj = tid & (kTileW - 1), ti = tid / kTileW;
@@ -658,6 +697,8 @@ __global__ void __launch_bounds__(kTileThreads, 1024 / kTileThreads) k_hessian_n
     if (tid == 0) {
         mbar_init(bar, 1);
         mbar_init_fence();
+        s_lazy[0].count = 0;
+        s_lazy[1].count = 0;
     }
     __syncthreads();
     if (tid == 0) {
@@ -672,48 +713,72 @@ __global__ void __launch_bounds__(kTileThreads, 1024 / kTileThreads) k_hessian_n
     }
     const int i = i0 - 1 + ti, j = j0 - 1 + tj;
     const bool in_grid = i >= 0 && j >= 0 && i < rows && j < cols;
-#pragma unroll
-    for (int l = 0; l < LPO; l++) {
-        const int size = (9 + 6 * l) << OCT;
-        const int m = (size / 2) >> OCT;
-        const int ni = 1 + (H - size) / step, nj = 1 + (W - size) / step;  // only used when the layer fits
-        float v = 0.f;
-        const int ii = i - m, jj = j - m;
-        if (in_grid && size <= H && size <= W && ii >= 0 && ii < ni && jj >= 0 && jj < nj) {
-            const int *o = s_tile + ((ti + C::m_max - m) * step) * C::tile_p + (tj + C::m_max - m) * step + xshift;
-            float dx, dy, dc;
-            layer_responses_c<OCT, LPO>(o, l, dx, dy, dc);
-            v = dx * dy - 0.81f * dc * dc;
+
+    // ---- phase 1: middle layers for the whole tile ----
+    {
+        float v1 = tile_det<OCT, LPO, 1>(s_tile, ti, tj, i0, j0, rows, cols, W, H, xshift);
+        s_det[(0 * kTileH + ti) * kTileW + tj] = v1;
+        float v2 = tile_det<OCT, LPO, 2>(s_tile, ti, tj, i0, j0, rows, cols, W, H, xshift);
+        s_det[(1 * kTileH + ti) * kTileW + tj] = v2;
+        if (NM > 2) {
+            float v3 = tile_det<OCT, LPO, (NM > 2 ? 3 : 1)>(s_tile, ti, tj, i0, j0, rows, cols, W, H, xshift);
+            s_det[(2 * kTileH + ti) * kTileW + tj] = v3;
         }
-        s_det[(l * kTileH + ti) * kTileW + tj] = v;
+        static_assert(NM <= 3, "extend phase 1");
     }
     __syncthreads();
 
     const bool inner = ti >= 1 && ti < kTileH - 1 && tj >= 1 && tj < kTileW - 1 && in_grid;
+    const int lane = tid & 31;
+    // keypoint of a confirmed maximum of layer l with its 27 determinants in N; appended warp-aggregated
+    auto emit = [&](bool is_max, int l, const float (&N)[3][9], int ci, int cj, int cti, int ctj) {
+        bool found = false;
+        surf_keypoint kp;
+        if (is_max) {
+            const int size = (9 + 6 * l) << OCT, size_dn = (9 + 6 * (l - 1)) << OCT;
+            const int m = (size / 2) >> OCT;
+            const int si = step * (ci - (size / 2) / step), sj = step * (cj - (size / 2) / step);
+            kp.x = sj + (size - 1) * 0.5f;
+            kp.y = si + (size - 1) * 0.5f;
+            kp.size = (float)size;
+            kp.angle = -1.f;
+            kp.response = N[1][4];
+            kp.octave = OCT;
+            const int *o = s_tile + ((cti + C::m_max - m) * step) * C::tile_p + (ctj + C::m_max - m) * step + xshift;
+            float dx, dy, dc;
+            layer_responses_c<OCT, LPO>(o, l, dx, dy, dc);
+            const float tr = dx + dy;
+            kp.class_id = (tr > 0) - (tr < 0);
+            found = refine_maximum(N, step, size - size_dn, kp);
+        }
+        const unsigned mk = __ballot_sync(FULL_MASK, found);
+        if (mk) {
+            const int leader = __ffs(mk) - 1;
+            int base = 0;
+            if (lane == leader) base = atomicAdd(counts + b, __popc(mk));
+            base = __shfl_sync(FULL_MASK, base, leader);
+            const int pos = base + __popc(mk & ((1u << lane) - 1));
+            if (found && pos < cap) raw[(size_t)b * cap + pos] = kp;
+        }
+    };
+
+    // ---- phase 2: candidates of every middle layer against what is computed ----
 #pragma unroll
     for (int l = 1; l <= LPO - 2; l++) {
         const int size = (9 + 6 * l) << OCT;
-        const int m = (size / 2) >> OCT;
-        const int size_up = (9 + 6 * (l + 1)) << OCT, size_dn = (9 + 6 * (l - 1)) << OCT;
+        const int size_up = (9 + 6 * (l + 1)) << OCT;
         const int margin = (size_up / 2) / step + 1;
-        bool found = false;
-        surf_keypoint kp;
+        const bool has_dn = l - 1 >= 1, has_up = l + 1 <= LPO - 2;
+        bool cand = false;
+        float N[3][9];
         if (inner && i >= margin && i < rows - margin && j >= margin && j < cols - margin) {
-            const float *d1 = s_det + (l * kTileH + ti) * kTileW + tj;
+            const float *d1 = s_det + ((l - 1) * kTileH + ti) * kTileW + tj;
             const float v = *d1;
             if (v > thr) {
-                float N[3][9];
-#pragma unroll
-                for (int k = 0; k < 3; k++)
-#pragma unroll
-                    for (int r = 0; r < 3; r++)
-#pragma unroll
-                        for (int q = 0; q < 3; q++) N[k][r * 3 + q] = d1[(k - 1) * (kTileH * kTileW) + (r - 1) * kTileW + (q - 1)];
-                const int si = step * (i - (size / 2) / step);
-                const int sj = step * (j - (size / 2) / step);
                 bool keep = true;
                 if (msum) {
                     // (0,0,9,9) pattern resized: corners at cvRound(ratio * 0) and cvRound(ratio * 9)
+                    const int si = step * (i - (size / 2) / step), sj = step * (j - (size / 2) / step);
                     const float ratio = (float)size / 9;
                     const int e = __float2int_rn(ratio * 9);
                     const int *mo = reinterpret_cast<const int *>(msum) + (size_t)si * SP + sj;
@@ -722,38 +787,98 @@ __global__ void __launch_bounds__(kTileThreads, 1024 / kTileThreads) k_hessian_n
                     keep = !(mv < 0.5f);
                 }
                 if (keep) {
-                    bool is_max = true;
+                    cand = true;
 #pragma unroll
-                    for (int k = 0; k < 3; k++)
+                    for (int k = 0; k < 3; k++) {
+                        if ((k == 0 && !has_dn) || (k == 2 && !has_up)) continue;
 #pragma unroll
-                        for (int q = 0; q < 9; q++)
-                            if (!(k == 1 && q == 4)) is_max = is_max && (v > N[k][q]);
-                    if (is_max) {
-                        kp.x = sj + (size - 1) * 0.5f;
-                        kp.y = si + (size - 1) * 0.5f;
-                        kp.size = (float)size;
-                        kp.angle = -1.f;
-                        kp.response = v;
-                        kp.octave = OCT;
-                        const int *o = s_tile + ((ti + C::m_max - m) * step) * C::tile_p + (tj + C::m_max - m) * step + xshift;
-                        float dx, dy, dc;
-                        layer_responses_c<OCT, LPO>(o, l, dx, dy, dc);
-                        const float tr = dx + dy;
-                        kp.class_id = (tr > 0) - (tr < 0);
-                        found = refine_maximum(N, step, size - size_dn, kp);
+                        for (int r = 0; r < 3; r++)
+#pragma unroll
+                            for (int q = 0; q < 3; q++) {
+                                const float nv = d1[(k - 1) * (kTileH * kTileW) + (r - 1) * kTileW + (q - 1)];
+                                N[k][r * 3 + q] = nv;
+                                if (!(k == 1 && r == 1 && q == 1)) cand = cand && (v > nv);
+                            }
                     }
                 }
             }
         }
-        const unsigned mk = __ballot_sync(FULL_MASK, found);
-        if (mk) {
-            const int lane = tid & 31;
-            const int leader = __ffs(mk) - 1;
-            int base = 0;
-            if (lane == leader) base = atomicAdd(counts + b, __popc(mk));
-            base = __shfl_sync(FULL_MASK, base, leader);
-            const int pos = base + __popc(mk & ((1u << lane) - 1));
-            if (found && pos < cap) raw[(size_t)b * cap + pos] = kp;
+        if (has_dn && has_up) {
+            emit(cand, l, N, i, j, ti, tj);  // complete: all 26 neighbours were available
+        } else if (cand) {
+            LazyList &L = s_lazy[has_up ? 0 : 1];
+            const int slot = atomicAdd(&L.count, 1);
+            if (slot < kLazyCap) L.pos[slot] = (unsigned short)(ti << 8 | tj);
+        }
+    }
+    __syncthreads();
+
+    // ---- phase 3: the missing layer at the 9 positions around every listed candidate ----
+    const int c0 = min(s_lazy[0].count, kLazyCap), c1 = min(s_lazy[1].count, kLazyCap);
+    if ((s_lazy[0].count > kLazyCap || s_lazy[1].count > kLazyCap) && tid == 0) atomicOr(counts + gridDim.z, 1);  // cannot happen
+    const int n0 = (9 * c0 + 31) & ~31;  // list 1 starts at a warp boundary: each warp evaluates one layer
+    for (int t = tid; t < n0 + 9 * c1; t += kTileThreads) {
+        const int which = t >= n0;
+        const int u = which ? t - n0 : t;
+        if (!which && u >= 9 * c0) continue;
+        const int sidx = u / 9, n = u - sidx * 9;
+        LazyList &L = s_lazy[which];
+        const int p = L.pos[sidx];
+        const int nti = (p >> 8) + n / 3 - 1, ntj = (p & 255) + n % 3 - 1;
+        L.extra[sidx][n] = which ? tile_det<OCT, LPO, LPO - 1>(s_tile, nti, ntj, i0, j0, rows, cols, W, H, xshift)
+                                 : tile_det<OCT, LPO, 0>(s_tile, nti, ntj, i0, j0, rows, cols, W, H, xshift);
+    }
+    __syncthreads();
+
+    // ---- phase 4: finish the comparison; one thread per listed candidate.  List 0 takes threads [0, c0), list 1
+    //      starts at the next warp boundary, so a warp handles one list (emit() votes per warp) ----
+    const int c0r = (c0 + 31) & ~31;
+    for (int base = 0; base < c0r + c1; base += kTileThreads) {
+        const int t = base + tid;
+        float N[3][9];
+        if (t < c0r) {  // candidate of layer 1: the lower neighbours come from the list
+            const bool active = t < c0;
+            const LazyList &L = s_lazy[0];
+            const int cti = active ? L.pos[t] >> 8 : 1, ctj = active ? L.pos[t] & 255 : 1;
+            const float *d1 = s_det + (0 * kTileH + cti) * kTileW + ctj;
+            const float v = *d1;
+            bool is_max = active;
+#pragma unroll
+            for (int q = 0; q < 9; q++) {
+                const float ev = active ? L.extra[t][q] : 0.f;
+                N[0][q] = ev;
+                is_max = is_max && (v > ev);
+            }
+#pragma unroll
+            for (int r = 0; r < 3; r++)
+#pragma unroll
+                for (int q = 0; q < 3; q++) {
+                    N[1][r * 3 + q] = d1[(r - 1) * kTileW + (q - 1)];
+                    N[2][r * 3 + q] = d1[kTileH * kTileW + (r - 1) * kTileW + (q - 1)];
+                }
+            emit(is_max, 1, N, i0 - 1 + cti, j0 - 1 + ctj, cti, ctj);
+        } else {        // candidate of layer LPO-2: the upper neighbours come from the list
+            const int u = t - c0r;
+            const bool active = u < c1;
+            const LazyList &L = s_lazy[1];
+            const int cti = active ? L.pos[u] >> 8 : 1, ctj = active ? L.pos[u] & 255 : 1;
+            const float *d1 = s_det + ((LPO - 3) * kTileH + cti) * kTileW + ctj;
+            const float v = *d1;
+            bool is_max = active;
+#pragma unroll
+            for (int q = 0; q < 9; q++) {
+                const float ev = active ? L.extra[u][q] : 0.f;
+                N[2][q] = ev;
+                is_max = is_max && (v > ev);
+            }
+#pragma unroll
+            for (int r = 0; r < 3; r++)
+#pragma unroll
+                for (int q = 0; q < 3; q++) {
+                    N[1][r * 3 + q] = d1[(r - 1) * kTileW + (q - 1)];
+                    N[0][r * 3 + q] = d1[-(kTileH * kTileW) + (r - 1) * kTileW + (q - 1)];
+                }
+            emit(is_max, LPO - 2, N, i0 - 1 + cti, j0 - 1 + ctj, cti, ctj);
         }
     }
 }
@@ -763,7 +888,7 @@ static void launch_tma_c(const CUtensorMap &tmap, const TileOctave &oct, const u
                          surf_keypoint *raw, int *counts, int cap, int B, cudaStream_t st)
 {
     using C = TileC<OCT, LPO>;
-    const size_t smem = (size_t)C::tile_bytes + (size_t)LPO * kTileH * kTileW * sizeof(float) + 128;
+    const size_t smem = (size_t)C::tile_bytes + (size_t)(LPO - 2) * kTileH * kTileW * sizeof(float) + 128;
     static bool attr_set[64] = {};
     int dev = 0;
     cudaGetDevice(&dev);
