@@ -25,8 +25,8 @@ namespace surfb200 {
 // ------------------------------------------------------------------------------------------------
 // constant tables (fixed by the algorithm, not by engine parameters)
 // ------------------------------------------------------------------------------------------------
-__constant__ signed char c_ori_x[kOriSamples];
-__constant__ signed char c_ori_y[kOriSamples];
+__constant__ float c_ori_x[kOriSamples];  // sample offsets -6..6, kept as floats (an I2F per use sat on the slow conversion pipe)
+__constant__ float c_ori_y[kOriSamples];
 __constant__ float c_ori_w[kOriSamples];
 __constant__ float c_desc_w[400];
 
@@ -45,15 +45,15 @@ static void gaussian_taps(int n, double sigma, float *out)
 
 void upload_tables()
 {
-    signed char px[kOriSamples], py[kOriSamples];
+    float px[kOriSamples], py[kOriSamples];
     float pw[kOriSamples], dw[400], g[13], gd[20];
     gaussian_taps(13, 2.5, g);
     int n = 0;
     for (int i = -6; i <= 6; i++)
         for (int j = -6; j <= 6; j++)
             if (i * i + j * j <= 36) {
-                px[n] = (signed char)i;  // the outer loop variable is the x offset
-                py[n] = (signed char)j;
+                px[n] = (float)i;  // the outer loop variable is the x offset
+                py[n] = (float)j;
                 pw[n++] = g[i + 6] * g[j + 6];
             }
     gaussian_taps(20, 3.3, gd);
