@@ -743,7 +743,9 @@ void surf_destroy(surf_engine *e)
 {
     if (!e) return;
     cudaSetDevice(e->device);
-    if (e->stream) cudaStreamSynchronize(e->stream);
+    // every stream that may still touch the workspace drains before it is freed
+    for (cudaStream_t st : {e->la_stream, e->upload_stream, e->match_stream, e->copy_stream, e->stream})
+        if (st) cudaStreamSynchronize(st);
     free_workspace(e);
     if (e->ev_valid)
         for (int i = 0; i < EV_COUNT; i++) cudaEventDestroy(e->ev[i]);
