@@ -205,3 +205,77 @@ def test_oracle_reproduces_golden_vectors(oracle):
         assert int(oracle.integral(img).astype(np.int64).sum()) == spec["integral_checksum"]
         assert k.tobytes() == z[name + "_kp"].tobytes(), name
         assert np.array_equal(d, z[name + "_desc"]), name
+
+
+def _np_refine(N, step, ds, x, y, size):
+    """interpolateKeypoint (SURVEY A3.4): central differences, Matx33f::solve by the closed-form 3x3 Cramer rule in fp32
+    (OpenCV's Matx_FastSolveOp<float, 3, 1>), written here a second time in numpy scalars."""
+    f = np.float32
+    N0, N1, N2 = N
+    b = [f(-(f(N1[5] - N1[3]) / f(2))), f(-(f(N1[7] - N1[1]) / f(2))), f(-(f(N2[4] - N0[4]) / f(2)))]
+    dxx = f(f(N1[3] - f(f(2) * N1[4])) + N1[5])
+    dxy = f(f(f(f(N1[8] - N1[6]) - N1[2]) + N1[0]) / f(4))
+    dxs = f(f(f(f(N2[5] - N2[3]) - N0[5]) + N0[3]) / f(4))
+    dyy = f(f(N1[1] - f(f(2) * N1[4])) + N1[7])
+    dys = f(f(f(f(N2[7] - N2[1]) - N0[7]) + N0[1]) / f(4))
+    dss = f(f(N0[4] - f(f(2) * N1[4])) + N2[4])
+    a = [[dxx, dxy, dxs], [dxy, dyy, dys], [dxs, dys, dss]]
+
+    def m2(p, q, r, s):
+        return f(f(p * q) - f(r * s))
+
+    det = f(f(f(a[0][0] * m2(a[1][1], a[2][2], a[2][1], a[1][2])) - f(a[0][1] * m2(a[1][0], a[2][2], a[2][0], a[1][2])))
+            + f(a[0][2] * m2(a[1][0], a[2][1], a[2][0], a[1][1])))
+    if det == 0:
+        return None
+    d = f(f(1) / det)
+    x0 = f(d * f(f(f(b[0] * m2(a[1][1], a[2][2], a[1][2], a[2][1])) - f(a[0][1] * m2(b[1], a[2][2], a[1][2], b[2])))
+                 + f(a[0][2] * m2(b[1], a[2][1], a[1][1], b[2]))))
+    x1 = f(d * f(f(f(a[0][0] * m2(b[1], a[2][2], a[1][2], b[2])) - f(b[0] * m2(a[1][0], a[2][2], a[1][2], a[2][0])))
+                 + f(a[0][2] * m2(a[1][0], b[2], b[1], a[2][0]))))
+    x2 = f(d * f(f(f(a[0][0] * m2(a[1][1], b[2], b[1], a[2][1])) - f(a[0][1] * m2(a[1][0], b[2], b[1], a[2][0])))
+                 + f(b[0] * m2(a[1][0], a[2][1], a[1][1], a[2][0]))))
+    if (x0 == 0 and x1 == 0 and x2 == 0) or abs(x0) > 1 or abs(x1) > 1 or abs(x2) > 1:
+        return None
+    return (f(x + f(x0 * f(step))), f(y + f(x1 * f(step))), f(np.rint(f(size + f(x2 * f(ds))))))
+
+
+def test_raw_keypoints_equal_numpy_restatement_of_stage3(oracle):
+    """Maxima search, sub-pixel / scale interpolation and the final sort, restated in numpy on the oracle's own layers
+    (which test_hessian_layer_vs_numpy_restatement pins): the raw keypoints must come out byte for byte."""
+    img = speckle.speckle_frame(200, 260, 13, blobs=3)
+    S = oracle.integral(img)
+    thr, O, L = 250.0, 3, 3
+    raw = oracle.raw_keypoints(img, oracle.params(thr, O, L))
+    mine = []
+    for o in range(O):
+        step = 1 << o
+        sizes = [(9 + 6 * l) << o for l in range(L + 2)]
+        layers = [oracle.hessian_layer(S, s, step) for s in sizes]
+        dets = [t[0] for t in layers]
+        traces = [t[1] for t in layers]
+        for l in range(1, L + 1):
+            size = sizes[l]
+            if sizes[l + 1] > min(img.shape):       # a layer that does not fit leaves nothing to compare with
+                continue
+            margin = (sizes[l + 1] // 2) // step + 1
+            rows, cols = dets[l].shape
+            for i in range(margin, rows - margin):
+                for j in range(margin, cols - margin):
+                    v = dets[l][i, j]
+                    if not v > np.float32(thr):
+                        continue
+                    N = [dets[k][i - 1:i + 2, j - 1:j + 2].reshape(-1) for k in (l - 1, l, l + 1)]
+                    if not all(v > N[k][q] for k in range(3) for q in range(9) if not (k == 1 and q == 4)):
+                        continue
+                    si, sj = step * (i - (size // 2) // step), step * (j - (size // 2) // step)
+                    x0, y0 = np.float32(sj + (size - 1) * 0.5), np.float32(si + (size - 1) * 0.5)
+                    r = _np_refine(N, step, size - sizes[l - 1], x0, y0, np.float32(size))
+                    if r is None:
+                        continue
+                    tr = traces[l][i, j]
+                    mine.append((float(r[0]), float(r[1]), float(r[2]), -1.0, float(v), o, int(tr > 0) - int(tr < 0)))
+    mine.sort(key=lambda k: (-k[4], -k[2], -k[5], -k[1], k[0]))
+    got = np.array(mine, dtype=oracle.KEYPOINT_DTYPE)
+    assert len(got) == len(raw) > 50
+    assert got.tobytes() == raw.tobytes()
