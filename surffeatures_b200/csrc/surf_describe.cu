@@ -295,7 +295,7 @@ struct AreaTab {  // one destination cell of the INTER_AREA table (same for x an
 struct DescShared {  // static shared state of one descriptor CTA
     AreaTab tab;
     __align__(4) unsigned char patch[kPatchPx + 3];
-    int work;
+    int next;     // the following queue item, fetched while the current keypoint is tapped
     int inexact;  // a row start of this window is not a multiple of 2^-32: fp64 tap coordinates
 };
 
@@ -746,17 +746,14 @@ __global__ void __launch_bounds__(ClassT<CLS>::threads) k_descriptor(const __gri
     if (tid == 0) {
         mbar_init(bar, 1);
         mbar_init_fence();
+        S.next = atomicAdd(A.misc + kMiscClassHead + CLS, 1);
     }
 
     for (;;) {
-        __syncthreads();  // everyone is done with the previous keypoint's shared state
-        if (tid == 0) {
-            S.work = atomicAdd(A.misc + kMiscClassHead + CLS, 1);
-            S.inexact = 0;
-        }
-        __syncthreads();
-        const int work = S.work;
+        __syncthreads();  // everyone is done with the previous keypoint's shared state; S.next is visible
+        const int work = S.next;
         if (work >= count) break;
+        if (tid == 0) S.inexact = 0;  // set again (same warp, later) by the row-start chains
         const int kidx = list[work];
         const int b = kidx / A.cap;
         const surf_keypoint *kpp = A.kps + kidx;
@@ -805,7 +802,11 @@ __global__ void __launch_bounds__(ClassT<CLS>::threads) k_descriptor(const __gri
         // the class tile is an upper bound by construction (ClassT); a violation would be a bug, reported
         // through the status word instead of corrupting memory
         if (tx1 - tx0a + 1 > tp || th_rows > CT::tr) {
-            if (tid == 0) atomicOr(A.misc + kMiscStatus, 2);
+            __syncthreads();  // every thread has read S.next
+            if (tid == 0) {
+                atomicOr(A.misc + kMiscStatus, 2);
+                S.next = atomicAdd(A.misc + kMiscClassHead + CLS, 1);
+            }
             continue;
         }
         // ---- the window's bounding box -> shared memory: one TMA box load (issued now, awaited below) ----
@@ -842,6 +843,11 @@ __global__ void __launch_bounds__(ClassT<CLS>::threads) k_descriptor(const __gri
         }
         __syncthreads();
 
+        // The next queue item is fetched now (every thread has read S.next: a barrier lies behind us) and published
+        // after the taps, so the atomic's round trip hides under them.
+        int next_item = 0;
+        if (tid == THREADS - 32) next_item = atomicAdd(A.misc + kMiscClassHead + CLS, 1);
+
         // ---- window pixels ----
         auto SRC = [&](int o) -> unsigned { return (unsigned)s_tile[o]; };
         if (A.upright) {
@@ -873,6 +879,7 @@ __global__ void __launch_bounds__(ClassT<CLS>::threads) k_descriptor(const __gri
                     wrow[j] = (unsigned char)rotated_tap(fx, fy, W, H, tx0a, ty0, tp, SRC);
             }
         }
+        if (tid == THREADS - 32) S.next = next_item;
         __syncthreads();
         // the image tile is no longer needed: its space holds the row sums of the resize
         descriptor_tail<THREADS, CT::max_cell>(A, kidx, n, s_win, reinterpret_cast<float *>(s_tile), win_addr, tile_addr, S, int_scale, isc);
@@ -908,17 +915,14 @@ __global__ void __launch_bounds__(BigT::threads) k_descriptor_big(const __grid_c
         mbar_init(bar0, 1);
         mbar_init(bar0 + 8, 1);
         mbar_init_fence();
+        S.next = atomicAdd(A.misc + kMiscClassHead + CLS, 1);
     }
 
     for (;;) {
-        __syncthreads();
-        if (tid == 0) {
-            S.work = atomicAdd(A.misc + kMiscClassHead + CLS, 1);
-            S.inexact = 0;
-        }
-        __syncthreads();
-        const int work = S.work;
+        __syncthreads();  // S.next is visible
+        const int work = S.next;
         if (work >= count) break;
+        if (tid == 0) S.inexact = 0;
         const int kidx = list[work];
         const int b = kidx / A.cap;
         const surf_keypoint *kpp = A.kps + kidx;
@@ -955,6 +959,8 @@ __global__ void __launch_bounds__(BigT::threads) k_descriptor_big(const __grid_c
         const bool int_scale = fabs(scale - isc) < DBL_EPSILON;
         if (!int_scale && warp == NW - 1 && lane < kPatch) area_tab_entry(S.tab, lane, n, scale);
         __syncthreads();  // row starts visible
+        int next_item = 0;    // fetched under the taps, published after them (see k_descriptor)
+        if (tid == THREADS - 32) next_item = atomicAdd(A.misc + kMiscClassHead + CLS, 1);
 
         // ---- sub-windows of at most kSubSide x kSubSide taps, each with its own image tile ----
         const int q = (n + kSubSide - 1) / kSubSide;
@@ -1057,6 +1063,7 @@ __global__ void __launch_bounds__(BigT::threads) k_descriptor_big(const __grid_c
             __syncthreads();  // this buffer may be refilled (two iterations ahead) and g_win rows are complete
         }
         if (bad && tid == 0) atomicOr(A.misc + kMiscStatus, 2);
+        if (tid == THREADS - 32) S.next = next_item;
         descriptor_tail<THREADS, 0>(A, kidx, n, g_win, g_buf, 0, 0, S, int_scale, isc);
     }
 }
