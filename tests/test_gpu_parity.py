@@ -134,6 +134,29 @@ def test_orientation_patches_descriptors_given_keypoints(eng, oracle, frame640):
     assert (err == 0).mean() >= 0.99
 
 
+def test_axis_aligned_directions_take_the_fp64_tap_path(eng, oracle):
+    """Keypoints whose direction is within 0.11 degrees of an axis have a sine or cosine that is not a multiple of
+    2^-32: their windows are tapped with fp64 coordinates instead of the 32.32 fixed-point ones.  Collected from several
+    frames (about 0.3 % of the keypoints), both small and large windows; patches must be identical, byte for byte."""
+    p = oracle.params(100, 4, 3)
+    picked = 0
+    for seed in (1, 2, 3, 4):
+        img = speckle.speckle_frame(480, 640, 40 + seed, blobs=6)
+        raw = oracle.raw_keypoints(img, p)
+        okp, odesc, opatch = oracle.describe(img, p, raw, want_patches=True)
+        th = np.deg2rad(okp["angle"].astype(np.float64))
+        near_axis = (okp["size"] > 0) & (np.minimum(np.abs(np.cos(th)), np.abs(np.sin(th))) < 2.0 ** -9)
+        if not near_axis.any():
+            continue
+        sel = raw[near_axis]
+        gkp, gdesc, gpatch = eng.describe_keypoints(img, sel, want_patches=True)
+        assert np.array_equal(gkp["angle"], okp["angle"][near_axis])
+        assert np.array_equal(gpatch, opatch[near_axis])
+        assert np.abs(gdesc - odesc[near_axis]).max() <= 1e-6
+        picked += int(near_axis.sum())
+    assert picked >= 8, picked
+
+
 def test_big_keypoints_unstaged_window_path(eng, oracle):
     img = speckle.speckle_frame(480, 640, 21, blobs=8)
     p = oracle.params(100, 4, 3)
