@@ -541,6 +541,59 @@ def test_async_output_mode_gives_identical_results():
         e.close()
 
 
+def test_stream_loop_with_lookahead_async_outputs_and_matching():
+    """The loop bench.py times end to end -- submit, look-ahead of the next batch, asynchronous result copies and the
+    frame-to-frame matcher -- must deliver the bytes of the plain synchronous calls."""
+    import torch
+
+    from surffeatures_b200 import MEM_HOST, SURF
+
+    frames = speckle.speckle_stream(8, 240, 320, seed=29, fresh=0.0)
+    e = SURF(100, 4, 3, max_width=320, max_height=240, max_batch=2, max_keypoints=4096)
+    try:
+        ref = []
+        for i in range(4):
+            k, d, off = e.detectAndComputeBatchPacked(frames[2 * i:2 * i + 2])
+            m, g = e.match_prev(0.8, n_total=int(off[-1]))
+            ref.append((k.copy(), d.copy(), off.copy(), m.copy(), g.copy()))
+        e.stream_reset()
+        e.set_async_outputs(True)
+        cap = 2 * 4096
+        pinned = torch.from_numpy(frames).pin_memory()
+        bufs = [dict(k=torch.zeros((cap, 7), dtype=torch.float32).pin_memory(), d=torch.zeros((cap, 64)).pin_memory(),
+                     m=torch.zeros((cap * 2, 4), dtype=torch.int32).pin_memory(),
+                     g=torch.zeros((cap,), dtype=torch.uint8).pin_memory()) for _ in range(2)]
+        offs = [np.zeros(3, np.int32) for _ in range(4)]
+        got = []
+
+        def snapshot(i):
+            pb, n = bufs[i & 1], int(offs[i][-1])
+            got.append((pb["k"].numpy()[:n].copy().view(np.uint8).reshape(-1), pb["d"].numpy()[:n].copy(),
+                        pb["m"].numpy()[:2 * n].copy(), pb["g"].numpy()[:n].copy()))
+
+        for i in range(4):
+            hb = bufs[i & 1]
+            e.submit(pinned[2 * i:2 * i + 2].data_ptr(), MEM_HOST, 2, 320, 240, 320, 320 * 240, True)
+            if i + 1 < 4:
+                e.lookahead(pinned[2 * i + 2:2 * i + 4].data_ptr(), MEM_HOST, 2, 320, 240, 320, 320 * 240)
+            e.wait_outputs()
+            if i >= 1:
+                snapshot(i - 1)
+            e.collect(hb["k"].data_ptr(), hb["d"].data_ptr(), MEM_HOST, cap, offs[i])
+            e.match_prev_to(0.8, hb["m"].data_ptr(), hb["g"].data_ptr(), MEM_HOST, cap)
+        e.wait_outputs()
+        snapshot(3)
+        for i in range(4):
+            k, d, off, m, g = ref[i]
+            assert np.array_equal(offs[i], off)
+            assert got[i][0].tobytes() == k.tobytes()
+            assert np.array_equal(got[i][1], d)
+            assert got[i][2].tobytes() == m.tobytes()
+            assert np.array_equal(got[i][3].astype(bool), g)
+    finally:
+        e.close()
+
+
 def test_device_frames_with_unaligned_pitch_take_the_fallback_path(oracle):
     """Frames handed over as device pointers with a pitch that is not a multiple of 16 cannot use TMA:
     the 4-byte cp.async tile path must give the same bytes."""
