@@ -296,6 +296,10 @@ struct DescShared {  // static shared state of one descriptor CTA
     AreaTab tab;
     __align__(4) unsigned char patch[kPatchPx + 3];
     int next;     // the following queue item, fetched while the current keypoint is tapped
+    struct Geo {  // window geometry of the current keypoint: written by warp 0 (isc / int_scale by the last warp)
+        int n, b, ux0, uy0, tx0a, ty0, interior, bad, isc, int_scale;
+        float sd, cd;
+    } geo;
     int inexact;  // a row start of this window is not a multiple of 2^-32: fp64 tap coordinates
 };
 
@@ -753,95 +757,117 @@ __global__ void __launch_bounds__(ClassT<CLS>::threads) k_descriptor(const __gri
         __syncthreads();  // everyone is done with the previous keypoint's shared state; S.next is visible
         const int work = S.next;
         if (work >= count) break;
-        if (tid == 0) S.inexact = 0;  // set again (same warp, later) by the row-start chains
         const int kidx = list[work];
-        const int b = kidx / A.cap;
         const surf_keypoint *kpp = A.kps + kidx;
-        const float cx = kpp->x, cy = kpp->y, size = kpp->size;
-        const uint8_t *img = A.img.ptr + (size_t)b * A.img.frame_stride;
 
-        const float s = size * 1.2f / 9.0f;
-        const int n = (int)(21 * s);
-        const float off = -(float)(n - 1) / 2;
-
-        // ---- window geometry ----
-        float sd = 1.f, cd = 0.f;
-        int ux0 = 0, uy0 = 0;  // upright: integer window origin
-        int tx0, tx1, ty0, ty1;
-        bool interior = false;  // every tap has its four neighbours inside the frame
-        if (A.upright) {
-            ux0 = __float2int_rn(cx + off);
-            uy0 = __float2int_rn(cy - off);
-            tx0 = min(max(ux0, 0), W - 1);
-            tx1 = min(max(ux0 + n - 1, 0), W - 1);
-            ty1 = min(max(uy0, 0), H - 1);
-            ty0 = min(max(uy0 - n + 1, 0), H - 1);
-        } else {
-            const float2 sc = A.sincos[kidx];
-            sd = sc.x;
-            cd = sc.y;
-            // Bounding box of all taps from the closed-form window corners.  The true row starts come from
-            // sequential fp32 additions (computed below, overlapped with the tile load) and drift from the
-            // closed form by far less than the 1-pixel margin taken here.
-            const float sx0 = cx + off * cd + off * sd, sy0 = cy - off * sd + off * cd;
-            const float ext = (float)(n - 1);
-            const float xa = sx0, xb = sx0 + ext * sd, xc2 = sx0 + ext * cd, xd = xb + ext * cd;
-            const float ya = sy0, yb = sy0 + ext * cd, yc2 = sy0 - ext * sd, yd = yb - ext * sd;
-            const float minx = fminf(fminf(xa, xb), fminf(xc2, xd)) - 1.f, maxx = fmaxf(fmaxf(xa, xb), fmaxf(xc2, xd)) + 1.f;
-            const float miny = fminf(fminf(ya, yb), fminf(yc2, yd)) - 1.f, maxy = fmaxf(fmaxf(ya, yb), fmaxf(yc2, yd)) + 1.f;
-            const int bx0 = __float2int_rd(minx), bx1 = __float2int_rd(maxx) + 1;
-            const int by0 = __float2int_rd(miny), by1 = __float2int_rd(maxy) + 1;
-            interior = bx0 >= 0 && by0 >= 0 && bx1 <= W - 1 && by1 <= H - 1;
-            tx0 = min(max(bx0, 0), W - 1);
-            tx1 = min(max(bx1, 0), W - 1);
-            ty0 = min(max(by0, 0), H - 1);
-            ty1 = min(max(by1, 0), H - 1);
+        // ---- prologue.  Only warp 0 works out the window geometry (about 250 instructions that every warp used to
+        //      repeat), issues the tile load and walks the row-start chains; the last warp builds the resize table;
+        //      the others go straight to the barrier and read the result from shared memory.  Without TMA the tile
+        //      copy needs every warp, so all of them take the lead role. ----
+        const bool lead = warp == 0 || !use_tma;
+        if (lead) {
+            const float cx = kpp->x, cy = kpp->y, size = kpp->size;
+            const float s = size * 1.2f / 9.0f;
+            const int n = (int)(21 * s);
+            const float off = -(float)(n - 1) / 2;
+            const int b = kidx / A.cap;
+            float sd = 1.f, cd = 0.f;
+            int ux0 = 0, uy0 = 0;  // upright: integer window origin
+            int tx0, tx1, ty0, ty1;
+            bool interior = false;  // every tap has its four neighbours inside the frame
+            if (A.upright) {
+                ux0 = __float2int_rn(cx + off);
+                uy0 = __float2int_rn(cy - off);
+                tx0 = min(max(ux0, 0), W - 1);
+                tx1 = min(max(ux0 + n - 1, 0), W - 1);
+                ty1 = min(max(uy0, 0), H - 1);
+                ty0 = min(max(uy0 - n + 1, 0), H - 1);
+            } else {
+                const float2 sc = A.sincos[kidx];
+                sd = sc.x;
+                cd = sc.y;
+                // Bounding box of all taps from the closed-form window corners.  The true row starts come from
+                // sequential fp32 additions (computed below, overlapped with the tile load) and drift from the
+                // closed form by far less than the 1-pixel margin taken here.
+                const float sx0 = cx + off * cd + off * sd, sy0 = cy - off * sd + off * cd;
+                const float ext = (float)(n - 1);
+                const float xa = sx0, xb = sx0 + ext * sd, xc2 = sx0 + ext * cd, xd = xb + ext * cd;
+                const float ya = sy0, yb = sy0 + ext * cd, yc2 = sy0 - ext * sd, yd = yb - ext * sd;
+                const float minx = fminf(fminf(xa, xb), fminf(xc2, xd)) - 1.f, maxx = fmaxf(fmaxf(xa, xb), fmaxf(xc2, xd)) + 1.f;
+                const float miny = fminf(fminf(ya, yb), fminf(yc2, yd)) - 1.f, maxy = fmaxf(fmaxf(ya, yb), fmaxf(yc2, yd)) + 1.f;
+                const int bx0 = __float2int_rd(minx), bx1 = __float2int_rd(maxx) + 1;
+                const int by0 = __float2int_rd(miny), by1 = __float2int_rd(maxy) + 1;
+                interior = bx0 >= 0 && by0 >= 0 && bx1 <= W - 1 && by1 <= H - 1;
+                tx0 = min(max(bx0, 0), W - 1);
+                tx1 = min(max(bx1, 0), W - 1);
+                ty0 = min(max(by0, 0), H - 1);
+                ty1 = min(max(by1, 0), H - 1);
+            }
+            const int tx0a = tx0 & ~15;              // tile origin aligned down to 16 bytes (TMA / vector copies)
+            const int th_rows = ty1 - ty0 + 1;
+            // the class tile is an upper bound by construction (ClassT); a violation would be a bug, reported
+            // through the status word instead of corrupting memory
+            const bool bad = tx1 - tx0a + 1 > tp || th_rows > CT::tr;
+            if (tid == 0) {
+                S.inexact = 0;  // set again (same warp, later) by the row-start chains
+                S.geo.n = n; S.geo.b = b; S.geo.ux0 = ux0; S.geo.uy0 = uy0; S.geo.tx0a = tx0a; S.geo.ty0 = ty0;
+                S.geo.interior = interior; S.geo.bad = bad; S.geo.sd = sd; S.geo.cd = cd;
+                // ---- the window's bounding box -> shared memory: one TMA box load (issued now, awaited below) ----
+                if (use_tma && !bad)
+                    tma_load_tile(&imap, (uint32_t)__cvta_generic_to_shared(s_tile), tx0a, ty0, b, bar, (uint32_t)(tp * CT::tr));
+            }
+            if (!use_tma && !bad) {
+                const uint8_t *img = A.img.ptr + (size_t)b * A.img.frame_stride;
+                copy_tile_fallback<NW, tp>(A, img, pitch, s_tile, tx0a, tx1, ty0, th_rows);
+            }
+            if (!A.upright && tid < 2 && !bad) {
+                // row starts advance by sequential fp32 additions (x chain on lane 0, y chain on lane 1 of the same
+                // warp: one instruction stream for both); runs while the tile is in flight
+                float v = tid == 0 ? cx + off * cd + off * sd : cy - off * sd + off * cd;
+                const float inc = tid == 0 ? sd : cd;
+                float *dst = tid == 0 ? s_rsx : s_rsy;
+                // every row start must be a multiple of 2^-32 for the fixed-point taps: branch-free running minimum
+                // of fix32_key (see there)
+                uint32_t key = 0xffffffffu;
+                for (int i = 0; i < n; i++, v += inc) {
+                    dst[i] = v;
+                    key = min(key, fix32_key(v));
+                }
+                if (key < kFix32KeyMin) S.inexact = 1;
+            }
         }
-        const int tx0a = tx0 & ~15;              // tile origin aligned down to 16 bytes (TMA / vector copies)
-        const int th_rows = ty1 - ty0 + 1;
-        // the class tile is an upper bound by construction (ClassT); a violation would be a bug, reported
-        // through the status word instead of corrupting memory
-        if (tx1 - tx0a + 1 > tp || th_rows > CT::tr) {
-            __syncthreads();  // every thread has read S.next
+        if (warp == NW - 1) {
+            // ---- INTER_AREA table for this window size ----
+            const float s = kpp->size * 1.2f / 9.0f;
+            const int n = (int)(21 * s);
+            const double inv = (double)kPatch / n;
+            const double scale = 1. / inv;
+            const int isc = __double2int_rn(scale);
+            const bool int_scale = fabs(scale - isc) < DBL_EPSILON;
+            if (lane == 31) {
+                S.geo.isc = isc;
+                S.geo.int_scale = int_scale;
+            }
+            if (!int_scale && lane < kPatch) area_tab_entry(S.tab, lane, n, scale);
+        }
+        __syncthreads();  // geometry, row starts and the resize table are visible
+        const int n = S.geo.n, b = S.geo.b, ux0 = S.geo.ux0, uy0 = S.geo.uy0, tx0a = S.geo.tx0a, ty0 = S.geo.ty0;
+        const bool interior = S.geo.interior != 0, int_scale = S.geo.int_scale != 0;
+        const int isc = S.geo.isc;
+        const float sd = S.geo.sd, cd = S.geo.cd;
+        (void)b;
+        if (S.geo.bad) {
+            __syncthreads();  // every thread has read S.next and the geometry
             if (tid == 0) {
                 atomicOr(A.misc + kMiscStatus, 2);
                 S.next = atomicAdd(A.misc + kMiscClassHead + CLS, 1);
             }
             continue;
         }
-        // ---- the window's bounding box -> shared memory: one TMA box load (issued now, awaited below) ----
-        if (use_tma && tid == 0)
-            tma_load_tile(&imap, (uint32_t)__cvta_generic_to_shared(s_tile), tx0a, ty0, b, bar, (uint32_t)(tp * CT::tr));
-
-        // ---- INTER_AREA table for this window size (one warp) ----
-        const double inv = (double)kPatch / n;
-        const double scale = 1. / inv;
-        const int isc = __double2int_rn(scale);
-        const bool int_scale = fabs(scale - isc) < DBL_EPSILON;
-        if (!int_scale && warp == NW - 1 && lane < kPatch) area_tab_entry(S.tab, lane, n, scale);
-
-        if (!use_tma) copy_tile_fallback<NW, tp>(A, img, pitch, s_tile, tx0a, tx1, ty0, th_rows);
-        if (!A.upright && tid < 2) {
-            // row starts advance by sequential fp32 additions (x chain on lane 0, y chain on lane 1 of the same
-            // warp: one instruction stream for both), stored as doubles for the tap loop; runs while the tile
-            // is in flight
-            float v = tid == 0 ? cx + off * cd + off * sd : cy - off * sd + off * cd;
-            const float inc = tid == 0 ? sd : cd;
-            float *dst = tid == 0 ? s_rsx : s_rsy;
-            // every row start must be a multiple of 2^-32 for the fixed-point taps: branch-free running minimum
-            // of fix32_key (see there)
-            uint32_t key = 0xffffffffu;
-            for (int i = 0; i < n; i++, v += inc) {
-                dst[i] = v;
-                key = min(key, fix32_key(v));
-            }
-            if (key < kFix32KeyMin) S.inexact = 1;
-        }
         if (use_tma) {
             if (!mbar_wait_bounded(bar, tma_phase) && tid == 0) atomicOr(A.misc + kMiscStatus, 4);  // reported by the host
             tma_phase ^= 1;
         }
-        __syncthreads();
 
         // The next queue item is fetched now (every thread has read S.next: a barrier lies behind us) and published
         // after the taps, so the atomic's round trip hides under them.
