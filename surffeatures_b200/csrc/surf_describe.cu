@@ -926,6 +926,7 @@ __global__ void __launch_bounds__(BigT::threads) k_descriptor_big(const __grid_c
     const uint32_t tile0_addr = pin_reg(smem_u32(s_tile0));
     __shared__ __align__(8) uint64_t s_bar[2];
     __shared__ DescShared S;
+    __shared__ int4 s_sub[(kMaxWindow / kSubSide) * (kMaxWindow / kSubSide)];  // per sub-window: tile origin x, y, flags
     uint32_t phase[2] = {0, 0};
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -1028,28 +1029,31 @@ __global__ void __launch_bounds__(BigT::threads) k_descriptor_big(const __grid_c
             tx0a = tx0 & ~15;
             fits = (tx1 - tx0a + 1 <= tp) && (ty1 - ty0 + 1 <= tr);
         };
-        bool bad = false;
-        if (use_tma && tid == 0) {  // prologue: first tile
+        // every sub-window's tile origin, once per keypoint: thread t works out sub-window t (fp64 extremes of its taps)
+        // and the tap loops below only read three words per sub-window
+        if (tid < n_sub) {
             int i0, i1, j0, j1, tx0a, ty0;
             bool fits, inside;
-            sub_box(0, i0, i1, j0, j1, tx0a, ty0, fits, inside);
-            tma_load_tile(&imap, (uint32_t)__cvta_generic_to_shared(s_tile0), tx0a, ty0, b, bar0, BigT::tile_bytes);
+            sub_box(tid, i0, i1, j0, j1, tx0a, ty0, fits, inside);
+            s_sub[tid] = make_int4(tx0a, ty0, (fits ? 1 : 0) | (inside ? 2 : 0), 0);
         }
+        __syncthreads();
+        bool bad = false;
+        if (use_tma && tid == 0)  // prologue: first tile
+            tma_load_tile(&imap, (uint32_t)__cvta_generic_to_shared(s_tile0), s_sub[0].x, s_sub[0].y, b, bar0, BigT::tile_bytes);
         for (int sub = 0; sub < n_sub; sub++) {
             const int cur = sub & 1;
             unsigned char *tile = s_tile0 + cur * BigT::tile_stride;
-            int i0, i1, j0, j1, tx0a, ty0;
-            bool fits, interior;
-            sub_box(sub, i0, i1, j0, j1, tx0a, ty0, fits, interior);
+            const int si = sub / q, sj = sub - si * q;
+            const int i0 = si * sw, i1 = min(n, i0 + sw), j0 = sj * sw, j1 = min(n, j0 + sw);
+            const int4 sb = s_sub[sub];
+            const int tx0a = sb.x, ty0 = sb.y;
+            const bool fits = (sb.z & 1) != 0, interior = (sb.z & 2) != 0;
             bad = bad || !fits;
             if (use_tma) {
-                if (tid == 0 && sub + 1 < n_sub) {  // prefetch the next sub-window's tile into the other buffer
-                    int a0, a1, c0, c1, nx, ny;
-                    bool nf, ni;
-                    sub_box(sub + 1, a0, a1, c0, c1, nx, ny, nf, ni);
-                    tma_load_tile(&imap, (uint32_t)__cvta_generic_to_shared(s_tile0 + (cur ^ 1) * BigT::tile_stride), nx, ny, b,
-                                  bar0 + 8 * (cur ^ 1), BigT::tile_bytes);
-                }
+                if (tid == 0 && sub + 1 < n_sub)  // prefetch the next sub-window's tile into the other buffer
+                    tma_load_tile(&imap, (uint32_t)__cvta_generic_to_shared(s_tile0 + (cur ^ 1) * BigT::tile_stride), s_sub[sub + 1].x,
+                                  s_sub[sub + 1].y, b, bar0 + 8 * (cur ^ 1), BigT::tile_bytes);
                 if (!mbar_wait_bounded(bar0 + 8 * cur, phase[cur]) && tid == 0) atomicOr(A.misc + kMiscStatus, 4);
                 phase[cur] ^= 1;
             } else {
