@@ -492,8 +492,7 @@ template <int THREADS, int MAXC>
 __device__ __forceinline__ void descriptor_tail(const DescribeArgs &A, int kidx, int n, const unsigned char *win, float *buf,
                                                 uint32_t win_addr, uint32_t buf_addr, DescShared &S, bool int_scale, int isc)
 {
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int D = A.extended ? 128 : 64;
+    const int tid = threadIdx.x;
     // Fractional scales run the reference's two passes: row sums buf[sy][dx] = sum_x win[sy][x] * alpha (fp32,
     // table order), then the column pass.  Thread = (row group, dx): the dx entry of the table stays in registers.
     if (!int_scale && MAXC > 0) {
