@@ -334,8 +334,8 @@ def run_ours(args):
     achieved = dom_bytes / (stage_ms[dom] * 1e-3) / 1e9
     # dram__bytes_read+write and smsp__inst_executed of the describe-stage kernels (k_orient, four window kernels, four
     # k_patch_descriptor) from one `ncu --set full` capture of this very command at batch 64
-    # (profiles/r1/describe_stage_v23_ncu_summary.txt): 324.0 MB read + 112.0 MB written, 4.65 G warp instructions
-    NCU_DESCRIBE_TRAFFIC, NCU_DESCRIBE_INST = 436.0e6, 4.65e9
+    # (profiles/r1/describe_stage_v25_ncu_summary.txt): 323.9 MB read + 105.0 MB written, 4.42 G warp instructions
+    NCU_DESCRIBE_TRAFFIC, NCU_DESCRIBE_INST = 428.9e6, 4.42e9
     traffic = NCU_DESCRIBE_TRAFFIC if (dom == "describe" and B == 64) else None
     roofline = {"bound": "hbm", "kernel": {"integral": "k_band_colsum+k_band_integral",
                                            "hessian": "k_hessian_nms_tma_c<0|1>+k_hessian+k_nms",
