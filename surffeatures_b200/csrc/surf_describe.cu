@@ -142,6 +142,15 @@ __global__ void __launch_bounds__(kOriWarps * 32) k_orient(const __grid_constant
 {
     __shared__ OriSample s_smp[kOriWarps][kOriSamples + 3];
     __shared__ unsigned char s_m2[kOriWarps][kOriSamples + 3];  // membership in windows 64..71
+    // window membership of every rounded angle 0..360, built once per CTA (window_mask is ~40 integer instructions
+    // with 64-bit shifts; the table makes it one 16-byte shared-memory read per sample)
+    __shared__ uint4 s_wmask[361];
+    for (int a = threadIdx.x; a <= 360; a += kOriWarps * 32) {
+        unsigned m0, m1, m2;
+        window_mask(a, m0, m1, m2);
+        s_wmask[a] = make_uint4(m0, m1, m2, 0u);
+    }
+    __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int W = A.geo.W, H = A.geo.H, SP = A.geo.SP;
     const int total = A.offsets[A.B];
@@ -195,7 +204,10 @@ __global__ void __launch_bounds__(kOriWarps * 32) k_orient(const __grid_constant
                 if (valid) {
                     OriSample o;
                     unsigned m2;
-                    window_mask(__float2int_rn(fast_atan2_deg(Y, X)), o.m0, o.m1, m2);
+                    const uint4 wm = s_wmask[__float2int_rn(fast_atan2_deg(Y, X))];
+                    o.m0 = wm.x;
+                    o.m1 = wm.y;
+                    m2 = wm.z;
                     o.X = X;
                     o.Y = Y;
                     const int pos = na + __popc(bal & ((1u << lane) - 1));
