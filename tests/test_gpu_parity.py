@@ -594,6 +594,46 @@ def test_stream_loop_with_lookahead_async_outputs_and_matching():
         e.close()
 
 
+@pytest.mark.parametrize("extended,upright,shape", [(True, False, (200, 264)), (False, True, (251, 333)), (True, True, (240, 320))])
+def test_lookahead_variants_and_pending_lookahead_at_destroy(extended, upright, shape):
+    """Look-ahead with the other descriptor variants and odd frame sizes (device frames, no TMA alignment for 333 px
+    rows), a batch smaller than max_batch, and an engine destroyed while a look-ahead is still pending."""
+    import torch
+
+    from surffeatures_b200 import KEYPOINT_DTYPE, MEM_DEVICE, MEM_HOST, SURF
+
+    H, W = shape
+    frames = speckle.speckle_stream(7, H, W, seed=31, fresh=0.0)
+    D = 128 if extended else 64
+    e = SURF(150, 3, 2, extended, upright, max_width=W, max_height=H, max_batch=3, max_keypoints=4096)
+    try:
+        batches = [frames[0:3], frames[3:6], frames[6:7]]          # the last batch has one frame
+        ref = [e.detectAndComputeBatchPacked(b) for b in batches]
+        ref = [(k.copy(), d.copy(), o.copy()) for k, d, o in ref]
+        dev = [torch.from_numpy(np.ascontiguousarray(b)).cuda() for b in batches]
+        torch.cuda.synchronize()
+        cap = 3 * 4096
+        k = torch.zeros((cap, 7), dtype=torch.float32).pin_memory()
+        d = torch.zeros((cap, D), dtype=torch.float32).pin_memory()
+        for i, b in enumerate(batches):
+            nb = len(b)
+            off = np.zeros(nb + 1, np.int32)
+            e.submit(dev[i].data_ptr(), MEM_DEVICE, nb, W, H, W, W * H, True)
+            if i + 1 < len(batches):
+                e.lookahead(dev[i + 1].data_ptr(), MEM_DEVICE, len(batches[i + 1]), W, H, W, W * H)
+            e.collect(k.data_ptr(), d.data_ptr(), MEM_HOST, cap, off)
+            rk, rd, ro = ref[i]
+            n = int(off[-1])
+            assert np.array_equal(off, ro)
+            assert k.numpy()[:n].copy().view(KEYPOINT_DTYPE).reshape(-1).tobytes() == rk.tobytes()
+            assert np.array_equal(d.numpy()[:n], rd)
+        # leave a look-ahead pending and destroy the engine: close() must drain it
+        e.submit(dev[0].data_ptr(), MEM_DEVICE, 3, W, H, W, W * H, True)
+        e.lookahead(dev[1].data_ptr(), MEM_DEVICE, 3, W, H, W, W * H)
+    finally:
+        e.close()
+
+
 def test_device_frames_with_unaligned_pitch_take_the_fallback_path(oracle):
     """Frames handed over as device pointers with a pitch that is not a multiple of 16 cannot use TMA:
     the 4-byte cp.async tile path must give the same bytes."""
