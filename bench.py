@@ -1,15 +1,24 @@
 #!/usr/bin/env python
-"""bench.py -- SURF detect+describe frames/sec @640x480 (BASELINE.json metric), config 2:
-a stream of 640x480 speckle frames, detect + describe every frame and BF L2 ratio-match it to the
-previous frame.  One step = one batch of BATCH consecutive frames of the stream.
+"""bench.py -- SURF detect+describe frames/sec @640x480 (BASELINE.json metric).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+Headline workload = BASELINE config 2: a stream of 640x480 speckle frames, detect + describe every frame and BF L2
+ratio-match it to the previous frame.  One step = one batch of BATCH consecutive frames of the stream.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config 2|3|4|5] [--no-extras]
 
 value   : whole-job frames/s with the frames already resident in HBM (device pointers in/out)
 e2e     : the same through the host-buffer API (pinned host frames -> H2D, packed keypoints,
           descriptors and matches -> D2H inside the timed region)
-roofline: dominant kernel's algorithmic bytes / its CUDA-event time, against MEASURED_PEAKS.json
+roofline: dominant stage's algorithmic bytes / its CUDA-event time, against MEASURED_PEAKS.json;
+          roofline_stages: the same for every stage (integral, Hessian+maxima, describe, matcher), timed in a pass
+          where no other stream runs beside the stage
+latency : host-in/host-out milliseconds per call at batch 1, 4, 16 (the reference's one-frame-per-tick loop)
+configs : BASELINE configs 3 (1024^2, 128-d upright, 256 frames), 4 (sweep of 512^2 slices sharded by frame,
+          results gathered to rank 0 by NCCL) and 5 (1M-row database sharded by row, NCCL all-gather of top-2
+          records) measured in the same run; under torchrun 4 and 5 use all ranks (strong scaling)
 cpu_baseline: the CPU oracle (restatement of OpenCV 2.4.5 SURF + BFMatcher) on the box's host cores
+
+All device times are CUDA events recorded by the engine on its own stream (surf_mark), max over ranks.
 """
 from __future__ import annotations
 
@@ -20,6 +29,7 @@ import subprocess
 import sys
 import threading
 import time
+from concurrent.futures import ThreadPoolExecutor
 
 import numpy as np
 
@@ -38,12 +48,30 @@ def _metric():
     return "SURF detect+describe frames/sec @640x480 (1/2/4/8 GPU); HBM GB/s vs peak"
 
 
+def workload_config(B: int) -> dict:
+    """The `config` object -- identical in both arms (--impl ours / reference)."""
+    return {"workload": "config2: 640x480 speckle stream, detect+describe (thr=100, 4 octaves, 3 layers, 64-d) "
+                        "+ BF L2 k=2 ratio(0.8) match to previous frame",
+            "frames_per_step": B, "frame": "640x480 u8", "ratio": RATIO,
+            "l2": f"inputs cycle through {POOL_BATCHES} batches (no L2 flush needed): per-step working set "
+                  f"(integral images + det pyramid of {B} frames) > 126 MB L2"}
+
+
 def _peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         d = json.load(open(p))
-        return float(d["hbm_gbs"]), "measured"
-    return 6650.0, "fallback"
+        return {"hbm": float(d["hbm_gbs"]), "bf16_burst": float(d.get("bf16_tflops", 1590.0)),
+                "bf16_sustained": float(d.get("bf16_tflops_sustained", 1400.0)), "source": "measured (MEASURED_PEAKS.json)"}
+    return {"hbm": 6650.0, "bf16_burst": 1590.0, "bf16_sustained": 1400.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+def host_threads() -> int:
+    """Threads this process may use: the affinity mask, not OMP_NUM_THREADS (torchrun exports OMP_NUM_THREADS=1)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
 
 
 class ClockSampler:
@@ -134,63 +162,83 @@ class ClockSampler:
                 "source": "nvidia-smi"}
 
 
-def make_stream(n_frames: int, seed: int) -> np.ndarray:
+def make_stream(n_frames: int, seed: int, h: int = H_, w: int = W_) -> np.ndarray:
     from surffeatures_b200 import speckle
 
-    return speckle.speckle_stream(n_frames, H_, W_, seed=seed)
+    return speckle.speckle_stream(n_frames, h, w, seed=seed)
 
 
-def algorithmic_bytes_per_frame(n_kp: float, D: int = 64, L: int = 3, O: int = 4):
-    """B1..B4 per 640x480 frame."""
-    A = 4 * (W_ + 1) * (H_ + 1)
-    P = sum((H_ >> o) * (W_ >> o) for o in range(O))
-    b1 = W_ * H_ + A
+def make_frames_parallel(n: int, h: int, w: int, seed0: int) -> np.ndarray:
+    """n independent speckle frames (seeds seed0...), generated on a few host threads (numpy releases the GIL)."""
+    from surffeatures_b200 import speckle
+
+    with ThreadPoolExecutor(max_workers=min(8, host_threads())) as ex:
+        return np.stack(list(ex.map(lambda i: speckle.speckle_frame(h, w, seed0 + i), range(n))))
+
+
+def algorithmic_bytes_per_frame(n_kp: float, D: int = 64, L: int = 3, O: int = 4, W: int = W_, H: int = H_):
+    """B1..B4 per frame."""
+    A = 4 * (W + 1) * (H + 1)
+    P = sum((H >> o) * (W >> o) for o in range(O))
+    b1 = W * H + A
     b2 = O * A + 4 * (L + 2) * P
     b3 = 4 * (L + 2) * P + 28 * n_kp
-    b4 = W_ * H_ + A + n_kp * (28 + 4 + 4 * D)
-    return {"integral": b1, "hessian": b2, "nms": b3, "describe": b4, "total": b1 + b2 + b3 + b4}
+    b4 = W * H + A + n_kp * (28 + 4 + 4 * D)
+    return {"integral": b1, "hessian": b2, "nms": b3, "hessian_nms_fused": O * A + 28 * n_kp, "describe": b4,
+            "total": b1 + b2 + b3 + b4}
 
 
 # ------------------------------------------------------------------------------------------------
+def _cpu_stream_pass(so, frames, p, threads):
+    """One pass of the config-2 workload on the CPU oracle: detect+describe every frame of `frames[1:]`, match each to
+    its predecessor.  Returns keypoints seen."""
+    res = so.detect_and_compute_batch(frames[1:], p, cap=CAP, n_threads=threads)
+    prev = so.detect_and_compute(frames[0], p)[1]
+    for _, d in res:
+        so.knn_match(d, prev, 2, n_threads=threads)
+        prev = d
+    return sum(len(k) for k, _ in res)
+
+
 def run_reference(args):
-    """--impl reference: the reference's CPU implementation of the path.  Genuine OpenCV 2.4.5
-    nonfree cannot be built offline, so this times the oracle port (all host threads, frame-parallel),
-    each step a bounded sample of the same stream."""
+    """--impl reference: the reference's CPU implementation of the path.  Genuine OpenCV 2.4.5 nonfree cannot be
+    built offline, so this times the oracle port (all host threads, frame-parallel).  Same `config` as the GPU arm;
+    each step is a bounded sample of that step's 64 frames so that the whole run ends within a few minutes."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
+    threads = host_threads()
+    os.environ["OMP_NUM_THREADS"] = str(threads)   # torchrun exports 1; the oracle also gets num_threads explicitly
     from oracle import surf_oracle as so
 
-    threads = so.max_threads()
-    sample = max(threads, 8)
-    frames = make_stream(sample + 1, seed=1)
+    B = args.batch
     p = so.params(**PARAMS)
-
-    def step():
-        res = so.detect_and_compute_batch(frames[1:], p, cap=CAP, n_threads=threads)
-        prev = so.detect_and_compute(frames[0], p)[1]
-        for _, d in res:
-            so.knn_match(d, prev, 2, n_threads=threads)
-            prev = d
-        return sum(len(k) for k, _ in res)
-
+    probe = make_stream(3, seed=1)
+    t0 = time.perf_counter()
+    so.detect_and_compute_batch(probe[1:], p, cap=CAP, n_threads=min(threads, 2))
+    per_frame_1t = (time.perf_counter() - t0) / 2 * min(threads, 2)       # thread-seconds per frame, roughly
+    # bound the run: about 150 s of wall clock over warm-up + timed steps
+    n_steps = max(1, args.steps + args.warmup)
+    est = per_frame_1t / threads * 1.4
+    sample = int(max(min(B, 150.0 / (n_steps * est)), min(B, threads)))
+    frames = make_stream(sample + 1, seed=1)
     for _ in range(args.warmup):
-        step()
+        _cpu_stream_pass(so, frames, p, threads)
     t0 = time.perf_counter()
     nk = 0
     for _ in range(args.steps):
-        nk += step()
+        nk += _cpu_stream_pass(so, frames, p, threads)
     dt = time.perf_counter() - t0
     fps = sample * args.steps / dt
     line = {
         "impl": "reference", "metric": _metric(), "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "u8/int32/f32", "data": "synthetic",
-        "config": {"workload": "config2: 640x480 speckle stream, detect+describe (thr=100, 4 octaves, 3 layers, 64-d) "
-                               "+ BF L2 k=2 ratio match to previous frame", "frames_per_step": sample},
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps * (B / sample),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/int32/f32", "data": "synthetic",
+        "config": workload_config(B),
         "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port",
-                         "sample": f"{sample} frames/step x {args.steps} steps, oracle port of OpenCV 2.4.5 SURF "
-                                   f"(genuine nonfree not installable offline)"},
+                         "sample": f"{sample} of the step's {B} frames per timed step x {args.steps} steps, detect+describe+"
+                                   f"match, oracle port of OpenCV 2.4.5 SURF (genuine nonfree not installable offline), "
+                                   f"frame-parallel on {threads} threads; ms_per_step is scaled to {B} frames"},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "keypoints_per_frame": nk / (sample * args.steps),
     }
@@ -199,209 +247,470 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------
-def run_ours(args):
-    import torch
-    import torch.distributed as dist
+class Ctx:
+    """Process-wide state of the GPU arm."""
 
-    from surffeatures_b200 import DMATCH_DTYPE, KEYPOINT_DTYPE, MEM_DEVICE, MEM_HOST, SURF
+    def __init__(self):
+        import torch
+        import torch.distributed as dist
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device: the engine has no CPU path")
-    torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    dev = torch.device("cuda", local)
-    B = args.batch
-    D = 64
+        self.torch, self.dist = torch, dist
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py needs a CUDA device: the engine has no CPU path")
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device("cuda", self.local)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=self.dev)
 
-    # ---- synthetic stream: each rank owns its own contiguous shard of the sweep (weak scaling) ----
-    pool = make_stream(POOL_BATCHES * B, seed=1 + rank)
-    h_pool = torch.from_numpy(pool).pin_memory()
-    d_pool = h_pool.to(dev)
+    def barrier(self):
+        self.torch.cuda.synchronize()
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
 
-    eng = SURF(**PARAMS, device=local, max_width=W_, max_height=H_, max_batch=B, max_keypoints=CAP)
-    stream = torch.cuda.ExternalStream(eng.cuda_stream, device=dev)
-    cap_total = B * CAP
-    offsets = np.zeros(B + 1, np.int32)
-    launches = [0]
-    kp_seen = [0]
-    look = {"on": LOOKAHEAD}
+    def max_over_ranks(self, v: float) -> float:
+        if self.world == 1:
+            return float(v)
+        t = self.torch.tensor([v], device=self.dev, dtype=self.torch.float64)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
 
-    def step_device(i, _):
-        src = d_pool[(i % POOL_BATCHES) * B:(i % POOL_BATCHES + 1) * B]
-        eng.submit(src.data_ptr(), MEM_DEVICE, B, W_, H_, W_, W_ * H_, True)
-        if look["on"]:   # stages 1-3 of the next batch run beside this batch's descriptor stage
-            nxt = d_pool[((i + 1) % POOL_BATCHES) * B:((i + 1) % POOL_BATCHES + 1) * B]
-            eng.lookahead(nxt.data_ptr(), MEM_DEVICE, B, W_, H_, W_, W_ * H_)
-        eng.collect(0, 0, MEM_DEVICE, cap_total, offsets)   # waits for the counts; copies nothing
-        launches[0] += eng.timings()["launches"]
-        kp_seen[0] += int(offsets[B])
-        eng.match_prev_device(RATIO)                         # frame t vs t-1 for the whole batch, on the device
-        launches[0] += 7
-        return 0
+    def sum_over_ranks(self, v: float) -> float:
+        if self.world == 1:
+            return float(v)
+        t = self.torch.tensor([v], device=self.dev, dtype=self.torch.float64)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+        return float(t.item())
 
-    # host-buffer API: pinned frames in, packed keypoints/descriptors/matches out.  Two sets of pinned
-    # output buffers alternate so that the device->host copies of step i overlap the kernels of step i+1.
-    hbuf = [dict(kps=torch.empty((cap_total, 7), dtype=torch.float32).pin_memory(),
-                 desc=torch.empty((cap_total, D), dtype=torch.float32).pin_memory(),
-                 matches=torch.empty((cap_total * 2, 4), dtype=torch.int32).pin_memory(),
-                 good=torch.empty((cap_total,), dtype=torch.uint8).pin_memory()) for _ in range(2)]
-    bytes_io = {"h2d": 0, "d2h": 0}
 
-    def step_e2e(i, _):
-        hb = hbuf[i & 1]
-        src = h_pool[(i % POOL_BATCHES) * B:(i % POOL_BATCHES + 1) * B]
-        eng.submit(src.data_ptr(), MEM_HOST, B, W_, H_, W_, W_ * H_, True)
-        nxt = h_pool[((i + 1) % POOL_BATCHES) * B:((i + 1) % POOL_BATCHES + 1) * B]
-        if look["on"]:   # next step's H2D and stages 1-3 run under this step's descriptor kernels
-            eng.lookahead(nxt.data_ptr(), MEM_HOST, B, W_, H_, W_, W_ * H_)
+class StreamBench:
+    """detect+describe(+match to the previous frame) over batches of B frames cycled from a pool (configs 2 and 3)."""
+
+    def __init__(self, ctx: Ctx, eng, pool: np.ndarray, B: int, D: int, cap: int, match: bool):
+        from surffeatures_b200 import MEM_DEVICE, MEM_HOST
+
+        torch = ctx.torch
+        self.ctx, self.eng, self.B, self.D, self.cap, self.match = ctx, eng, B, D, cap, match
+        self.MEM_DEVICE, self.MEM_HOST = MEM_DEVICE, MEM_HOST
+        self.n_pool = len(pool) // B
+        self.H, self.W = pool.shape[1:]
+        self.h_pool = torch.from_numpy(pool).pin_memory()
+        self.d_pool = self.h_pool.to(ctx.dev)
+        self.cap_total = B * cap
+        self.offsets = np.zeros(B + 1, np.int32)
+        self.launches = 0
+        self.kp_seen = 0
+        self.lookahead = LOOKAHEAD
+        self.hbuf = None
+        self.bytes_io = {"h2d": 0, "d2h": 0}
+
+    def _slice(self, pool, i):
+        j = i % self.n_pool
+        return pool[j * self.B:(j + 1) * self.B]
+
+    def step_device(self, i):
+        e, B, W, H = self.eng, self.B, self.W, self.H
+        e.submit(self._slice(self.d_pool, i).data_ptr(), self.MEM_DEVICE, B, W, H, W, W * H, True)
+        if self.lookahead:   # stages 1-3 of the next batch run beside this batch's descriptor stage
+            e.lookahead(self._slice(self.d_pool, i + 1).data_ptr(), self.MEM_DEVICE, B, W, H, W, W * H)
+        e.collect(0, 0, self.MEM_DEVICE, self.cap_total, self.offsets)   # waits for the counts; copies nothing
+        self.launches += e.timings()["launches"]
+        self.kp_seen += int(self.offsets[B])
+        if self.match:
+            e.match_prev_device(RATIO)       # frame t vs t-1 for the whole batch, on the device, own stream
+
+    def alloc_host_outputs(self):
+        """Two sets of pinned output buffers alternate so that the device->host copies of step i overlap the kernels
+        of step i+1."""
+        torch = self.ctx.torch
+        n = self.cap_total
+        self.hbuf = [dict(kps=torch.empty((n, 7), dtype=torch.float32).pin_memory(),
+                          desc=torch.empty((n, self.D), dtype=torch.float32).pin_memory(),
+                          matches=torch.empty((n * 2, 4), dtype=torch.int32).pin_memory() if self.match else None,
+                          good=torch.empty((n,), dtype=torch.uint8).pin_memory() if self.match else None) for _ in range(2)]
+
+    def step_e2e(self, i):
+        e, B, W, H = self.eng, self.B, self.W, self.H
+        hb = self.hbuf[i & 1]
+        e.submit(self._slice(self.h_pool, i).data_ptr(), self.MEM_HOST, B, W, H, W, W * H, True)
+        nxt = self._slice(self.h_pool, i + 1)
+        if self.lookahead:   # next step's H2D and stages 1-3 run under this step's descriptor kernels
+            e.lookahead(nxt.data_ptr(), self.MEM_HOST, B, W, H, W, W * H)
         else:
-            eng.prefetch(nxt.data_ptr(), B, W_, H_, W_, W_ * H_)   # next step's H2D runs under this step's kernels
-        eng.wait_outputs()      # copies of step i-1 (other buffer set) have landed; this set is free again
-        eng.collect(hb["kps"].data_ptr(), hb["desc"].data_ptr(), MEM_HOST, cap_total, offsets)
-        n = int(offsets[B])
-        eng.match_prev_to(RATIO, hb["matches"].data_ptr(), hb["good"].data_ptr(), MEM_HOST, cap_total)
-        bytes_io["h2d"] = B * W_ * H_
-        bytes_io["d2h"] = n * (28 + 4 * D) + 2 * n * 16 + n + (B + 1) * 4
-        return 0
+            e.prefetch(nxt.data_ptr(), B, W, H, W, W * H)
+        e.wait_outputs()      # copies of step i-1 (other buffer set) have landed; this set is free again
+        e.collect(hb["kps"].data_ptr(), hb["desc"].data_ptr(), self.MEM_HOST, self.cap_total, self.offsets)
+        n = int(self.offsets[B])
+        self.kp_seen += n
+        d2h = n * (28 + 4 * self.D) + (B + 1) * 4
+        if self.match:
+            e.match_prev_to(RATIO, hb["matches"].data_ptr(), hb["good"].data_ptr(), self.MEM_HOST, self.cap_total)
+            d2h += 2 * n * 16 + n
+        self.bytes_io = {"h2d": B * W * H, "d2h": d2h}
 
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def timed(step_fn, steps, warmup, sample_clocks=False):
-        n_prev = 0
-        eng.stream_reset()
+    def timed(self, step_fn, steps, warmup, sample_clocks=False):
+        e, ctx = self.eng, self.ctx
+        e.stream_reset()
         for i in range(warmup):
-            n_prev = step_fn(i, n_prev)
-        sampler = ClockSampler(local) if sample_clocks else None
-        barrier()
+            step_fn(i)
+        sampler = ClockSampler(ctx.local) if sample_clocks else None
+        ctx.barrier()
         if sampler:
             sampler.start()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        launches[0] = 0
-        kp_seen[0] = 0
-        stage = {k: 0.0 for k in ("integral", "hessian", "sort", "describe", "pack")}
-        e0.record(stream)
+        self.launches = 0
+        self.kp_seen = 0
+        n_match = 0
+        e.mark(0)
         for i in range(steps):
-            n_prev = step_fn(warmup + i, n_prev)
-            t = eng.timings()
-            for k in stage:
-                stage[k] += t[k]
-        eng.wait_outputs()
-        eng.sync()               # compute stream and the matcher's own stream
-        e1.record(stream)
-        barrier()
-        ms = e0.elapsed_time(e1)
+            step_fn(warmup + i)
+            if self.match:
+                n_match += 1
+        e.wait_outputs()
+        e.sync()               # compute stream and the matcher's own stream
+        e.mark(1)
+        ms = e.mark_elapsed(0, 1)
+        if self.match and n_match:
+            self.launches += n_match * e.match_prev_time()[1]
         clocks = sampler.stop() if sampler else None
-        if world > 1:
-            t = torch.tensor([ms], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-        return ms, {k: v / steps for k, v in stage.items()}, clocks
+        ctx.barrier()
+        return ctx.max_over_ranks(ms), clocks
 
+    def stage_pass(self, steps, warmup):
+        """Every stage timed with nothing else on the GPU: no look-ahead, the matcher drained before the next submit."""
+        e, B, W, H = self.eng, self.B, self.W, self.H
+        e.stream_reset()
+        acc = {k: 0.0 for k in ("integral", "hessian", "sort", "describe", "pack", "match")}
+        for i in range(warmup + steps):
+            e.sync()
+            e.submit(self._slice(self.d_pool, i).data_ptr(), self.MEM_DEVICE, B, W, H, W, W * H, True)
+            e.collect(0, 0, self.MEM_DEVICE, self.cap_total, self.offsets)
+            t = e.timings()
+            mt = 0.0
+            if self.match:
+                e.match_prev_device(RATIO)
+                mt = e.match_prev_time()[0]
+            if i >= warmup:
+                for k in ("integral", "hessian", "sort", "describe", "pack"):
+                    acc[k] += t[k]
+                acc["match"] += mt
+        e.sync()
+        return {k: v / steps for k, v in acc.items()}
+
+
+def measure_latency(ctx: Ctx, eng, frames: np.ndarray, D: int, reps: int = 30):
+    """Host-in / host-out wall-clock per call at small batches (blocking API, pinned buffers): the one-frame-per-tick
+    use of computeNext (vtkSlicerSurfFeaturesLogic.cxx:1392-1406)."""
+    from surffeatures_b200 import MEM_HOST
+
+    torch = ctx.torch
+    out = {}
+    H, W = frames.shape[1:]
+    for nb in (1, 4, 16):
+        if nb > len(frames) or nb > eng.max_batch:
+            continue
+        h_in = torch.from_numpy(frames[:nb].copy()).pin_memory()
+        kps = torch.empty((nb * CAP, 7), dtype=torch.float32).pin_memory()
+        desc = torch.empty((nb * CAP, D), dtype=torch.float32).pin_memory()
+        off = np.zeros(nb + 1, np.int32)
+        ts = []
+        for r in range(reps + 5):
+            t0 = time.perf_counter()
+            eng.submit(h_in.data_ptr(), MEM_HOST, nb, W, H, W, W * H, True)
+            eng.collect(kps.data_ptr(), desc.data_ptr(), MEM_HOST, nb * CAP, off)
+            ts.append((time.perf_counter() - t0) * 1e3)
+        ts = np.array(ts[5:])
+        out[f"batch{nb}"] = {"ms_per_call_median": float(np.median(ts)), "ms_p10": float(np.quantile(ts, 0.1)),
+                             "ms_p90": float(np.quantile(ts, 0.9)), "ms_per_frame": float(np.median(ts) / nb),
+                             "frames_per_s": float(nb / np.median(ts) * 1e3), "keypoints": int(off[nb]),
+                             "launches_per_call": int(eng.timings()["launches"])}
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+def run_config3(ctx: Ctx, steps_frames: int = 256):
+    """BASELINE config 3: extended 128-d upright SURF on 1024x1024 frames, 256 frames (batches of 32), one GPU per rank."""
+    from surffeatures_b200 import SURF
+
+    B, cap, D, S = 32, 32768, 128, 1024
+    pool = make_frames_parallel(B, S, S, 100 + 1000 * ctx.rank)      # 32 distinct frames, cycled 8x = 256 frames
+    eng = SURF(100.0, 4, 3, True, True, device=ctx.local, max_width=S, max_height=S, max_batch=B, max_keypoints=cap)
+    try:
+        sb = StreamBench(ctx, eng, pool, B, D, cap, match=False)
+        steps = steps_frames // B
+        ms, _ = sb.timed(sb.step_device, steps, 2)
+        kp = sb.kp_seen / (steps * B)
+        sb.alloc_host_outputs()
+        eng.set_async_outputs(True)
+        ms_e2e, _ = sb.timed(sb.step_e2e, steps, 2)
+        eng.set_async_outputs(False)
+        return {"workload": "config3: 256 frames 1024x1024, extended (128-d) upright, thr=100, 4 octaves, 3 layers; batches "
+                            "of 32 (32 distinct frames cycled)", "frames": steps * B * ctx.world,
+                "value": ctx.world * steps * B / (ms * 1e-3), "unit": "frames/s", "ms_per_256_frames": ms * 256 / (steps * B),
+                "keypoints_per_frame": kp,
+                "e2e": {"value": ctx.world * steps * B / (ms_e2e * 1e-3), "unit": "frames/s",
+                        "h2d_bytes_per_step": sb.bytes_io["h2d"], "d2h_bytes_per_step": sb.bytes_io["d2h"]},
+                "scaling": "weak (one replica per GPU)"}
+    finally:
+        eng.close()
+
+
+def run_config4(ctx: Ctx, comm_factory, n_total: int = 4096, reps: int = 2):
+    """BASELINE config 4: a sweep of n_total 512x512 slices sharded by frame over the ranks; every batch's keypoints and
+    descriptors go to rank 0 by NCCL (surf_sweep_sharded) while the next batch computes.  Strong scaling."""
+    from surffeatures_b200 import SURF, shard_range
+
+    torch = ctx.torch
+    S, B, cap, D = 512, 64, 8192, 64
+    lo, hi = shard_range(n_total, ctx.rank, ctx.world)
+    n_local = hi - lo
+    n_pool = 128
+    pool = make_stream(n_pool, seed=2 + ctx.rank, h=S, w=S)           # 128 correlated slices, cycled over the shard
+    reps_pool = (n_local + n_pool - 1) // n_pool
+    d_frames = torch.from_numpy(pool).to(ctx.dev).repeat(reps_pool, 1, 1)[:n_local].contiguous()
+    eng = SURF(100.0, 4, 3, False, False, device=ctx.local, max_width=S, max_height=S, max_batch=B, max_keypoints=cap)
+    comm = comm_factory(eng) if ctx.world > 1 else None
+    try:
+        per_frame = 5000                                             # output capacity on rank 0 (~3.9k keypoints / slice)
+        cap_rows = n_total * per_frame if ctx.rank == 0 else 0
+        d_kps = torch.empty((max(cap_rows, 1), 7), dtype=torch.float32, device=ctx.dev)
+        d_desc = torch.empty((max(cap_rows, 1), D), dtype=torch.float32, device=ctx.dev)
+        off = np.zeros(n_total + 1, np.int64) if ctx.rank == 0 else None
+        best = None
+        for r in range(reps + 1):
+            ctx.barrier()
+            st = eng.sweep_sharded_device(comm, d_frames.data_ptr(), n_total, S, S, S, S * S, 0, d_kps.data_ptr(),
+                                          d_desc.data_ptr(), cap_rows, off)
+            ms = ctx.max_over_ranks(st["total_ms"])
+            if r > 0 and (best is None or ms < best[0]):
+                best = (ms, st)
+        ms, st = best
+        total_kp = int(off[-1]) if ctx.rank == 0 else 0
+        res = {"workload": f"config4: sweep of {n_total} slices 512x512 sharded by frame over {ctx.world} GPU(s), thr=100, 4 "
+                           f"octaves, 3 layers, 64-d; keypoints + descriptors gathered to rank 0 in frame order "
+                           f"(NCCL send/recv per batch, overlapped with the next batch); 128 distinct slices per rank cycled",
+               "frames": n_total, "value": n_total / (ms * 1e-3), "unit": "frames/s", "ms_per_sweep": ms,
+               "scaling": "strong", "keypoints_gathered": total_kp,
+               "nccl": {"bytes_into_rank0": int(st["bytes_received"]) if ctx.rank == 0 else None,
+                        "exchange_ms_rank0": st["exchange_ms"], "assemble_ms_rank0": st["assemble_ms"],
+                        "chunks_per_rank": st["chunks"],
+                        "ingress_gbs": (st["bytes_received"] / (st["exchange_ms"] * 1e-3) / 1e9
+                                        if ctx.rank == 0 and st["exchange_ms"] > 0 else None)},
+               "data_path": "device-resident frames in, device-resident gathered results out (rank 0)"}
+        return res
+    finally:
+        if comm is not None:
+            comm.close()
+        eng.close()
+
+
+def run_config5(ctx: Ctx, comm_factory, n_rows: int = 1 << 20, nq: int = 4096, reps: int = 10):
+    """BASELINE config 5: knnMatch(k=2) + ratio test of 4096 queries against a 1M x 64 database sharded by row over the
+    ranks; per-rank tensor-core candidates + exact rescoring, NCCL all-gather of the 16 B x 2 x Nq records, merge."""
+    from surffeatures_b200 import SURF, DescriptorDB, MEM_DEVICE, shard_range
+
+    torch = ctx.torch
+    D, k = 64, 2
+    lo, hi = shard_range(n_rows, ctx.rank, ctx.world)
+    rng = np.random.default_rng(3 + 17 * ctx.rank)
+    rows = np.abs(rng.standard_normal((hi - lo, D), dtype=np.float32))
+    rows *= rng.choice(np.array([-1.0, 1.0], np.float32), size=rows.shape, p=[0.35, 0.65])
+    rows /= np.linalg.norm(rows, axis=1, keepdims=True)
+    q = rows[rng.integers(0, len(rows), nq)] + 0.05 * rng.standard_normal((nq, D), dtype=np.float32)
+    q /= np.linalg.norm(q, axis=1, keepdims=True)
+    eng = SURF(100.0, 4, 3, False, False, device=ctx.local, max_width=64, max_height=64, max_batch=1, max_keypoints=1024)
+    comm = comm_factory(eng) if ctx.world > 1 else None
+    db = DescriptorDB(eng, D, max_rows=hi - lo, max_images=1)
+    try:
+        d_rows = torch.from_numpy(rows).to(ctx.dev)
+        db.add_device(d_rows.data_ptr(), 0, np.array([0, hi - lo], np.int32))
+        d_q = torch.from_numpy(q).to(ctx.dev)            # rank 0's rows are broadcast to everybody (query_root = 0)
+        d_out = torch.empty((nq * k, 4), dtype=torch.int32, device=ctx.dev)
+        times, nccl = [], []
+        for r in range(reps + 3):
+            ctx.barrier()
+            eng.mark(2)
+            db.knn_sharded_device(comm, d_q.data_ptr(), nq, k, d_out.data_ptr(), 0 if comm is not None else -1)
+            eng.mark(3)
+            if r >= 3:
+                times.append(ctx.max_over_ranks(eng.mark_elapsed(2, 3)))
+                nccl.append(comm.last_times()["nccl_ms"] if comm is not None else 0.0)
+        ms = float(np.median(times))
+        out = d_out.cpu().numpy().view(np.dtype([("q", "<i4"), ("t", "<i4"), ("img", "<i4"), ("d", "<f4")])).reshape(nq, k)
+        passed = float(np.mean(out["d"][:, 0] < RATIO * out["d"][:, 1]))
+        flops = 2.0 * nq * n_rows * D
+        pk = _peaks()
+        return {"workload": f"config5: knnMatch(k=2) + ratio(0.8) of {nq} queries against a {n_rows} x 64 database sharded by "
+                            f"row over {ctx.world} GPU(s); tcgen05 candidates + exact fp32 rescoring per rank, NCCL all-gather "
+                            f"of 16 B x 2 x Nq records per rank, merge (ties -> lower global row)",
+                "value": nq / (ms * 1e-3), "unit": "queries/s", "ms_per_query_batch": ms, "nccl_ms": float(np.median(nccl)),
+                "nccl_bytes_per_rank": 16 * k * nq + 4, "scaling": "strong", "ratio_test_pass_fraction": passed,
+                "useful_tflops": flops / (ms * 1e-3) / 1e12,
+                "tensor_frac_of_burst_peak": flops / (ms * 1e-3) / 1e12 / (pk["bf16_burst"] * ctx.world),
+                "note": "the BF16 hi/lo split issues 3 MMAs per useful product: the tensor pipe does 3x the useful flops"}
+    finally:
+        db.close()
+        if comm is not None:
+            comm.close()
+        eng.close()
+
+
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    ctx = Ctx()
+    torch = ctx.torch
+    from surffeatures_b200 import SURF, Comm
+
+    if os.environ.get("SURF_B200_LIB") and not args.dev_lib:
+        raise SystemExit("SURF_B200_LIB is a development knob (A/B builds); pass --dev-lib to measure another library")
+    B, D = args.batch, 64
     steps, warmup = args.steps, max(args.warmup, 3)
-    ms_dev, stage_overlapped, clocks = timed(step_device, steps, warmup, sample_clocks=True)
-    n_launch = launches[0]
-    kp_per_frame = kp_seen[0] / (steps * B)
-    # Per-stage durations for the roofline come from a pass of the same steps WITHOUT the look-ahead: with it, stages
-    # 1-3 of batch i+1 share the GPU with stage 4 of batch i and no stage has a duration of its own.
-    stage_ms = stage_overlapped
-    ms_serial = ms_dev
-    if look["on"]:
-        look["on"] = False
-        ms_serial, stage_ms, _ = timed(step_device, max(5, steps // 3), warmup)
-        ms_serial *= steps / max(5, steps // 3)
-        look["on"] = True
+    peaks = _peaks()
+
+    pool = make_stream(POOL_BATCHES * B, seed=1 + ctx.rank)   # each rank owns its own shard of the stream (weak scaling)
+    eng = SURF(**PARAMS, device=ctx.local, max_width=W_, max_height=H_, max_batch=B, max_keypoints=CAP)
+    sb = StreamBench(ctx, eng, pool, B, D, CAP, match=True)
+
+    ms_dev, clocks = sb.timed(sb.step_device, steps, warmup, sample_clocks=True)
+    n_launch = sb.launches
+    kp_per_frame = sb.kp_seen / (steps * B)
+    sb.alloc_host_outputs()
     eng.set_async_outputs(True)
-    ms_e2e, _, _ = timed(step_e2e, steps, warmup)
+    ms_e2e, _ = sb.timed(sb.step_e2e, steps, warmup)
     eng.set_async_outputs(False)
+    stage_ms = sb.stage_pass(max(5, steps // 3), 2)
+    fps = ctx.world * B * steps / (ms_dev * 1e-3)
+    fps_e2e = ctx.world * B * steps / (ms_e2e * 1e-3)
 
-    fps = world * B * steps / (ms_dev * 1e-3)
-    fps_e2e = world * B * steps / (ms_e2e * 1e-3)
-
-    # ---- roofline of the dominant kernel (by measured stage time) ----
-    peak, how = _peaks()
+    # ---- roofline: every stage, then the dominant one in the contract's `roofline` object ----
     alg = algorithmic_bytes_per_frame(kp_per_frame, D)
-    stage_key = {"integral": "integral", "hessian": "hessian", "describe": "describe"}
-    dom = max(stage_key, key=lambda k: stage_ms[k])
-    dom_bytes = (alg["hessian"] + alg["nms"] if dom == "hessian" else alg[dom]) * B
-    achieved = dom_bytes / (stage_ms[dom] * 1e-3) / 1e9
-    # dram__bytes_read+write and smsp__inst_executed of the describe-stage kernels (k_orient, four window kernels, four
-    # k_patch_descriptor) from one `ncu --set full` capture of this very command at batch 64
-    # (profiles/r1/describe_stage_v25_ncu_summary.txt): 323.9 MB read + 105.0 MB written, 4.42 G warp instructions
-    NCU_DESCRIBE_TRAFFIC, NCU_DESCRIBE_INST = 428.9e6, 4.42e9
-    traffic = NCU_DESCRIBE_TRAFFIC if (dom == "describe" and B == 64) else None
-    roofline = {"bound": "hbm", "kernel": {"integral": "k_band_colsum+k_band_integral",
-                                           "hessian": "k_hessian_nms_tma_c<0|1>+k_hessian+k_nms",
-                                           "describe": "k_orient+k_descriptor<0..2>+k_descriptor_big+k_patch_descriptor"}[dom],
-                "achieved": achieved, "peak": peak, "peak_source": how + " (MEASURED_PEAKS.json hbm_gbs)",
-                "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                "limiter": "instruction issue, not HBM: smsp__issue_active 68-86 % in the window kernels "
-                           "(~6300 exact bilinear taps per keypoint at 33 instructions each); see profiles/r1/",
-                "peak_kind": "burst copy peak; the stage is timed inside a long step",
-                # the stage's real limiter: warp instructions issued (ncu, see above) / stage time, against
-                # 148 SMs x 4 schedulers x SM clock
+    match_flops = 2.0 * kp_per_frame * kp_per_frame * D * B
+    stages = [
+        {"stage": "integral", "kernels": "k_band_colsum+k_band_integral", "bound": "hbm",
+         "algorithmic_bytes": alg["integral"] * B, "ms": stage_ms["integral"]},
+        {"stage": "hessian+maxima", "kernels": "k_hessian_nms_tma_c<0|1>+k_hessian+k_nms", "bound": "hbm",
+         "algorithmic_bytes": alg["hessian_nms_fused"] * B, "algorithmic_bytes_unfused": (alg["hessian"] + alg["nms"]) * B,
+         "ms": stage_ms["hessian"]},
+        {"stage": "sort", "kernels": "k_sort_chunks+k_merge_pass", "bound": "hbm",
+         "algorithmic_bytes": 2 * 28 * kp_per_frame * B, "ms": stage_ms["sort"]},
+        {"stage": "describe", "kernels": "k_orient+k_descriptor<0..2>+k_descriptor_big+k_patch_descriptor", "bound": "hbm",
+         "algorithmic_bytes": alg["describe"] * B, "ms": stage_ms["describe"]},
+    ]
+    for s in stages:
+        s["achieved"] = s["algorithmic_bytes"] / (s["ms"] * 1e-3) / 1e9 if s["ms"] > 0 else None
+        s["peak"], s["unit"] = peaks["hbm"], "GB/s"
+        s["frac"] = s["achieved"] / peaks["hbm"] if s["achieved"] else None
+        if "algorithmic_bytes_unfused" in s and s["ms"] > 0:
+            s["frac_unfused_accounting"] = s["algorithmic_bytes_unfused"] / (s["ms"] * 1e-3) / 1e9 / peaks["hbm"]
+    stages.append({"stage": "match", "kernels": "k_tc_prep+k_tc_candidates+k_tc_rescore+k_tc_redo", "bound": "tensor",
+                   "algorithmic_flops": match_flops, "ms": stage_ms["match"],
+                   "achieved": match_flops / (stage_ms["match"] * 1e-3) / 1e12 if stage_ms["match"] > 0 else None,
+                   "peak": peaks["bf16_burst"], "unit": "TFLOP/s",
+                   "frac": match_flops / (stage_ms["match"] * 1e-3) / 1e12 / peaks["bf16_burst"] if stage_ms["match"] > 0 else None,
+                   "note": "useful flops 2*Nq*Nt*D; the BF16 hi/lo split issues 3 MMAs per useful product"})
+    dom = max(stages[:4], key=lambda s: s["ms"])
+    # dram__bytes_read+write and smsp__inst_executed of the describe-stage kernels from one `ncu --set full` capture of this
+    # very command at batch 64 (profiles/: see NCU_* below)
+    traffic = NCU_DESCRIBE_TRAFFIC if (dom["stage"] == "describe" and B == 64) else None
+    roofline = {"bound": "hbm", "kernel": dom["kernels"], "achieved": dom["achieved"], "peak": peaks["hbm"],
+                "peak_source": peaks["source"] + " hbm_gbs, burst copy peak", "unit": "GB/s", "frac": dom["frac"],
+                "traffic": traffic, "traffic_source": NCU_SOURCE if traffic else None,
+                "limiter": "instruction issue, not HBM: the window kernels sit at 80-85 % issue-slot utilisation "
+                           "(about 6300 exact bilinear taps per keypoint); see profiles/",
                 "issue_slots": ({"warp_inst_per_step": NCU_DESCRIBE_INST,
-                                 "achieved_ginst_s": NCU_DESCRIBE_INST / (stage_ms[dom] * 1e-3) / 1e9,
+                                 "achieved_ginst_s": NCU_DESCRIBE_INST / (dom["ms"] * 1e-3) / 1e9,
                                  "peak_ginst_s": 148 * 4 * 1.965,
-                                 "frac": NCU_DESCRIBE_INST / (stage_ms[dom] * 1e-3) / (148 * 4 * 1.965e9)}
-                                if (dom == "describe" and B == 64) else None),
-                "algorithmic_bytes_per_launch": dom_bytes, "ms_per_launch": stage_ms[dom],
-                "stage_ms_per_step": stage_ms,
-                "stage_ms_note": ("stages timed in a pass without the look-ahead (serialized, "
-                                  f"{ms_serial / steps:.3f} ms per step); the headline value overlaps stages 1-3 of the "
-                                  "next batch with stage 4" if look["on"] else "stages run back to back"),
-                "stage_ms_per_step_overlapped": stage_overlapped if look["on"] else None,
-                "whole_path_frac": alg["total"] * B * steps / (ms_dev * 1e-3) / 1e9 / peak}
+                                 "frac": NCU_DESCRIBE_INST / (dom["ms"] * 1e-3) / (148 * 4 * 1.965e9)}
+                                if traffic else None),
+                "algorithmic_bytes_per_launch": dom["algorithmic_bytes"], "ms_per_launch": dom["ms"],
+                "whole_path_frac": alg["total"] * B * steps / (ms_dev * 1e-3) / 1e9 / peaks["hbm"]}
+
+    latency = None
+    if ctx.rank == 0 and not args.no_extras:
+        latency = measure_latency(ctx, eng, pool[:16], D)
+    ctx.barrier()
+
+    extras = {}
+    if not args.no_extras:
+        comm_factory = Comm.from_torch
+        for name, fn in (("config3", lambda: run_config3(ctx)),
+                         ("config4", lambda: run_config4(ctx, comm_factory, args.sweep_frames)),
+                         ("config5", lambda: run_config5(ctx, comm_factory))):
+            if args.only_extra and name != args.only_extra:
+                continue
+            try:
+                extras[name] = fn()
+            except Exception as ex:   # an extra must not take the headline down with it (recorded, not hidden)
+                extras[name] = {"error": f"{type(ex).__name__}: {ex}"}
+                # a failed collective cannot be resynchronised: leave the remaining multi-rank extras alone
+                if ctx.world > 1:
+                    break
+            ctx.barrier()
 
     cpu_baseline = None
-    if rank == 0 and world == 1 and not args.no_cpu:
-        from oracle import surf_oracle as so
+    if ctx.rank == 0 and ctx.world == 1 and not args.no_cpu:
+        cpu_baseline = cpu_baseline_leg(pool)
 
-        threads = so.max_threads()
-        ns = max(threads, 8)
-        p = so.params(**PARAMS)
-        so.detect_and_compute(pool[0], p)
-        t0 = time.perf_counter()
-        res = so.detect_and_compute_batch(pool[:ns], p, cap=CAP, n_threads=threads)
-        for a, b_ in zip(res[1:], res[:-1]):
-            so.knn_match(a[1], b_[1], 2, n_threads=threads)
-        dt = time.perf_counter() - t0
-        cpu_baseline = {"value": ns / dt, "unit": "frames/s", "cores": threads, "kind": "port",
-                        "sample": f"{ns} frames of the same stream, detect+describe+match, oracle port of OpenCV 2.4.5 "
-                                  f"SURF (genuine nonfree not installable offline), {threads} threads frame-parallel"}
-
-    if rank == 0:
+    if ctx.rank == 0:
         line = {
-            "metric": _metric(), "value": fps, "unit": "frames/s", "n_gpus": world, "steps": steps, "warmup": warmup,
+            "metric": _metric(), "value": fps, "unit": "frames/s", "n_gpus": ctx.world, "steps": steps, "warmup": warmup,
             "ms_per_step": ms_dev / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u8/int32/f32", "data": "synthetic",
-            "config": {"workload": "config2: 640x480 speckle stream, detect+describe (thr=100, 4 octaves, 3 layers, "
-                                   "64-d) + BF L2 k=2 ratio(0.8) match to previous frame",
-                       "frames_per_step": B, "frames_per_step_all_gpus": B * world,
-                       "l2": f"inputs cycle through {POOL_BATCHES} batches (no L2 flush needed): per-step working set "
-                             f"(integral+det pyramid, {B} frames) > 126 MB L2",
-                       "sharding": "frames sharded by rank, no data-path collective",
-                       "lookahead": bool(look["on"])},
-            "e2e": {"value": fps_e2e, "unit": "frames/s", "h2d_bytes_per_step": bytes_io["h2d"],
-                    "d2h_bytes_per_step": bytes_io["d2h"], "ms_per_step": ms_e2e / steps},
+            "config": workload_config(B),
+            "notes": {"frames_per_step_all_gpus": B * ctx.world, "sharding": "frames sharded by rank, no data-path collective "
+                      "(config 2 does not shard below a frame: replicas); configs 4 and 5 below use NCCL",
+                      "lookahead": bool(sb.lookahead), "library": os.environ.get("SURF_B200_LIB", "surffeatures_b200/libsurf_b200.so")},
+            "e2e": {"value": fps_e2e, "unit": "frames/s", "h2d_bytes_per_step": sb.bytes_io["h2d"],
+                    "d2h_bytes_per_step": sb.bytes_io["d2h"], "ms_per_step": ms_e2e / steps},
             "gpu_launches": n_launch, "keypoints_per_frame": kp_per_frame,
-            "roofline": roofline, "cpu_baseline": cpu_baseline, "clocks": clocks,
+            "roofline": roofline, "roofline_stages": stages,
+            "stage_ms_note": "stages timed in a separate pass with nothing else on the GPU (no look-ahead, matcher drained "
+                             "before the next submit); the headline overlaps stages 1-3 of the next batch and the matcher "
+                             "with stage 4",
+            "latency": latency, "latency_ms_batch1": latency["batch1"]["ms_per_call_median"] if latency else None,
+            "configs": extras, "cpu_baseline": cpu_baseline, "clocks": clocks,
         }
         print(json.dumps(line), flush=True)
+    # orderly shutdown: engine first (its streams and events), then the process group; no os._exit
+    eng.close()
     torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
-    # the engine's stream is wrapped by a torch ExternalStream: leave both to process teardown
-    sys.stdout.flush()
-    os._exit(0)
+    if ctx.world > 1:
+        ctx.dist.barrier()
+        ctx.dist.destroy_process_group()
+    return 0
+
+
+# from profiles/r1/describe_stage_v25_ncu_summary.txt (ncu --set full of this command, batch 64): 323.9 MB read + 105.0 MB
+# written by k_orient + the four window kernels + four k_patch_descriptor launches, 4.42 G warp instructions
+NCU_DESCRIBE_TRAFFIC, NCU_DESCRIBE_INST = 428.9e6, 4.42e9
+NCU_SOURCE = "profiles/r1/describe_stage_v25_ncu_summary.txt"
+
+
+def cpu_baseline_leg(pool: np.ndarray):
+    """The oracle port on the box's host cores, on a bounded sample of the same stream (about 10-30 s of CPU work):
+    T-thread frame-parallel passes (median of the repetitions that fit the budget) and a 1-thread row."""
+    from oracle import surf_oracle as so
+
+    threads = host_threads()
+    p = so.params(**PARAMS)
+    ns = max(threads, 8)
+    frames = pool[:ns + 1]
+    _cpu_stream_pass(so, frames[:3], p, threads)       # warm-up
+    reps, t_all = [], time.perf_counter()
+    while len(reps) < 20 and (time.perf_counter() - t_all < 15.0 or len(reps) < 3):
+        t0 = time.perf_counter()
+        _cpu_stream_pass(so, frames, p, threads)
+        reps.append(ns / (time.perf_counter() - t0))
+    t0 = time.perf_counter()
+    _cpu_stream_pass(so, frames[:3], p, 1)
+    one = 2 / (time.perf_counter() - t0)
+    return {"value": float(np.median(reps)), "unit": "frames/s", "cores": threads, "kind": "port",
+            "p10": float(np.quantile(reps, 0.1)), "p90": float(np.quantile(reps, 0.9)), "repetitions": len(reps),
+            "single_thread_frames_per_s": one,
+            "sample": f"{ns} frames of the same stream per repetition, detect+describe+match, oracle port of OpenCV 2.4.5 "
+                      f"SURF (genuine nonfree not installable offline), {threads} threads frame-parallel; 1-thread row on 2 frames"}
 
 
 def main():
@@ -412,6 +721,10 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-extras", action="store_true", help="headline only: no latency table, no configs 3/4/5")
+    ap.add_argument("--only-extra", default="", help="run only this extra (config3|config4|config5)")
+    ap.add_argument("--sweep-frames", type=int, default=4096, help="slices of the config-4 sweep")
+    ap.add_argument("--dev-lib", action="store_true", help="allow SURF_B200_LIB (development A/B builds)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

@@ -315,6 +315,66 @@ int surf_estimate_pose(surf_rand *rng, const double *query_points, const double 
 int surf_mean_plane_distance(const uint8_t *mask, int rows, int cols, size_t pitch, int step, const double ground_truth[16],
                              const double estimate[16], double *out);
 
+/* ---- timing marks: CUDA events on the engine's own stream (what bench.py times with) ---- */
+#define SURF_MAX_MARKS 8
+int surf_mark(surf_engine *e, int slot);                                  /* records mark `slot` (0..7) now */
+int surf_mark_elapsed(surf_engine *e, int from_slot, int to_slot, float *ms); /* waits for `to_slot` */
+/* Device time and kernel launches of the last surf_match_prev (waits for it). */
+int surf_match_prev_time(surf_engine *e, float *ms, int *launches);
+
+/* ---- multi-GPU: one process per GPU, NCCL on device buffers --------------------
+ * Frames are independent (computeNext touches only images[index], vtkSlicerSurfFeaturesLogic.cxx:1392-1406),
+ * so a sweep is sharded by contiguous frame blocks with no collective on the compute path; NCCL carries only
+ *   - the gather of the variable-length keypoint / descriptor blocks to one rank, in frame order
+ *     (surf_sweep_sharded; BASELINE config 4), and
+ *   - the all-gather of per-rank top-k records of a row-sharded train database, merged with ties going to
+ *     the lower global row as BFMatcher's single scan does (surf_db_knn_sharded; BASELINE config 5; the
+ *     matcher calls being distributed are matchDescriptorsKNN :635-643 / :1457-1458).
+ * libnccl.so.2 is resolved at run time (the copy already loaded in the process, e.g. torch's, else the system
+ * one); a missing library is SURF_ERR_NCCL from surf_comm_*, never a load failure of libsurf_b200.so. */
+typedef struct surf_comm surf_comm;
+#define SURF_COMM_ID_BYTES 128
+/* ncclGetUniqueId: call on one rank and hand the 128 bytes to every rank (any transport). */
+int surf_comm_unique_id(void *id);
+/* ncclCommInitRank on the engine's device; collective over the n_ranks processes. */
+int surf_comm_init(surf_engine *e, const void *id, int rank, int n_ranks, surf_comm **out);
+void surf_comm_destroy(surf_comm *c);
+int surf_comm_info(const surf_comm *c, int *rank, int *n_ranks, int *nccl_version);
+/* Contiguous block [lo, hi) of `rank`: the first n_items % n_ranks ranks get one item more. */
+int surf_shard_range(long n_items, int rank, int n_ranks, long *lo, long *hi);
+
+typedef struct surf_sweep_stats {
+    float total_ms;        /* device time from the first kernel to the last copy into the output arrays */
+    float exchange_ms;     /* device time of the NCCL operations (they overlap the compute of later chunks) */
+    float assemble_ms;     /* destination rank: frame-order assembly of the gathered blocks */
+    int64_t bytes_sent;    /* payload this rank sent */
+    int64_t bytes_received;/* payload this rank received (destination rank) */
+    int32_t chunks;        /* batches per rank (every rank runs the same number) */
+    int32_t launches;      /* kernels launched by this rank's engine */
+} surf_sweep_stats;
+
+/* computeNext over a whole sweep, sharded by frame: this rank holds frames [lo, hi) = surf_shard_range(
+ * n_frames_total, rank, n_ranks) at images_local (frame_stride apart); it runs them in batches of the engine's
+ * max_batch and sends every batch's packed keypoints / descriptors to dst_rank while the next batch computes
+ * (per-frame counts by ncclAllGather, payload by grouped ncclSend / ncclRecv straight from the device results).
+ * On dst_rank keypoints / descriptors (out_mem host or device, `capacity` rows) receive ALL frames in frame
+ * order and offsets[n_frames_total + 1] (host) the row offsets; other ranks may pass NULL for the three.
+ * comm == NULL runs the same code on one GPU.  Collective: every rank of the communicator must call it. */
+int surf_sweep_sharded(surf_engine *e, surf_comm *comm, const uint8_t *images_local, int in_mem, long n_frames_total,
+                       int width, int height, size_t pitch, size_t frame_stride, const uint8_t *mask, size_t mask_pitch,
+                       int want_descriptors, int dst_rank, surf_keypoint *keypoints, float *descriptors, int out_mem,
+                       long capacity, int64_t *offsets, surf_sweep_stats *stats);
+
+/* knnMatch(query, k) against a train database whose rows are sharded over the ranks (rank r holds the r-th
+ * contiguous block in its own surf_db).  query_root >= 0: that rank's query rows are broadcast first (the other
+ * ranks pass a buffer of the same size that is overwritten when mem is device, or ignored when host);
+ * query_root < 0: every rank already passes the same rows.  Every rank receives the merged result: train_idx
+ * is the GLOBAL row (rank-order concatenation), img_idx 0, ties -> lower global row.  Collective. */
+int surf_db_knn_sharded(surf_db *db_shard, surf_comm *comm, const float *query, int n_query, int k, int query_root,
+                        surf_dmatch *out, int mem);
+/* Device time of the last surf_db_knn_sharded on this rank: whole call, and the NCCL part of it. */
+int surf_comm_last_times(const surf_comm *c, float *total_ms, float *nccl_ms);
+
 const char *surf_version(void);
 
 #ifdef __cplusplus

@@ -6,9 +6,9 @@ hand-written sm_100a CUDA kernels (csrc/, include/surf_b200.h) plus this thin ho
 the cv::Feature2D / DescriptorMatcher interface.  No CPU fallback.
 """
 from .engine import (  # noqa: F401
-    ABI_SYMBOLS, BFMatcher, DMATCH_DTYPE, KEYPOINT_DTYPE, LIB_PATH, MEM_DEVICE, MEM_HOST, SURF, SurfError,
-    load_library, to_cv2_keypoints,
+    ABI_SYMBOLS, BFMatcher, Comm, DescriptorDB, DMATCH_DTYPE, KEYPOINT_DTYPE, LIB_PATH, MEM_DEVICE, MEM_HOST, SURF,
+    SurfError, load_library, shard_range, to_cv2_keypoints,
 )
 
 __all__ = ["SURF", "BFMatcher", "SurfError", "KEYPOINT_DTYPE", "DMATCH_DTYPE", "load_library", "LIB_PATH",
-           "ABI_SYMBOLS", "MEM_HOST", "MEM_DEVICE", "to_cv2_keypoints"]
+           "ABI_SYMBOLS", "MEM_HOST", "MEM_DEVICE", "to_cv2_keypoints", "Comm", "DescriptorDB", "shard_range"]

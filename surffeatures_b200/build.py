@@ -22,6 +22,7 @@ UNITS = [
     ("surf_match_tc.cu", []),
     ("surf_engine.cu", []),
     ("surf_db.cu", []),
+    ("surf_comm.cu", []),
     ("surf_vote.cu", ["-fmad=false"]),
     ("surf_mha.cu", ["-fmad=false"]),
     ("surf_pose.cu", ["-fmad=false"]),
@@ -66,7 +67,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
             sys.stderr.write(out)
         if p.returncode:
             raise RuntimeError("nvcc failed: " + " ".join(cmd))
-    cmd = [nvcc, "-ccbin", host, *ARCH, "-shared", "-o", LIB, *objs, "-lcudart"]
+    cmd = [nvcc, "-ccbin", host, *ARCH, "-shared", "-o", LIB, *objs, "-lcudart", "-ldl"]
     subprocess.check_call(cmd, env=env)
     return LIB
 

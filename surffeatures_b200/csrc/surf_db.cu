@@ -11,25 +11,7 @@
 
 #include "surf_engine_priv.h"
 
-struct surf_db {
-    surf_engine *e = nullptr;
-    int dim = 64;
-    long max_rows = 0;
-    int max_images = 0;
-    TcPool pool{};                  // one slot of slot_rows >= max_rows rows
-    float *rows = nullptr;          // fp32 [max_rows][dim]
-    surf_keypoint *kps = nullptr;   // [max_rows]
-    int *d_img_off = nullptr;       // [max_images + 1]
-    TcSegment *d_seg = nullptr;     // one table entry for the append being prepared
-    std::vector<int> img_off;       // host copy, img_off[0] = 0
-    bool has_kps = true;            // false once an add() came without keypoints
-    void *vote_ws = nullptr;        // scratch of surf_correspond (owned by the train database)
-    size_t vote_ws_cap = 0;
-};
-
 namespace {
-
-long db_rows(const surf_db *db) { return db->img_off.empty() ? 0 : db->img_off.back(); }
 
 // Device buffers of a host-memory call: [query rows | out records], reusing the engine's match staging area.
 int reserve_io(surf_engine *e, size_t bytes)
@@ -50,7 +32,7 @@ int reserve_io(surf_engine *e, size_t bytes)
 namespace surfb200 {
 
 // k-NN of device-resident query rows against a database, records with (img_idx, local train_idx).
-int db_knn_device(surf_db *db, const float *dq, int n_query, int k, surf_dmatch *dout, int *launches)
+int db_knn_device(surf_db *db, const float *dq, int n_query, int k, surf_dmatch *dout, int *launches, bool localize)
 {
     surf_engine *e = db->e;
     const long n_train = db_rows(db);
@@ -82,7 +64,7 @@ int db_knn_device(surf_db *db, const float *dq, int n_query, int k, surf_dmatch 
         launch_tc_match(a, e->stream, launches);
         e->last_tc_ws = 2;
     }
-    launch_db_localize(dout, (long)n_query * k, db->d_img_off, (int)db->img_off.size() - 1, e->stream, launches);
+    if (localize) launch_db_localize(dout, (long)n_query * k, db->d_img_off, (int)db->img_off.size() - 1, e->stream, launches);
     CU(e, cudaGetLastError());
     return SURF_OK;
 }

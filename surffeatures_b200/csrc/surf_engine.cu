@@ -47,10 +47,12 @@ int tc_reserve(surf_engine *e, surf_engine::TcWs &w, int slots, int slot_rows, i
         return SURF_OK;
     }
     CU(e, cudaStreamSynchronize(e->stream));
+    CU(e, cudaStreamSynchronize(e->match_stream));
+    const int old_slot_rows = w.pool.hi ? w.pool.slot_rows : 0;
     cudaFree(w.pool.hi); cudaFree(w.pool.lo); cudaFree(w.pool.norm); cudaFree(w.pool.max_norm); cudaFree(w.pool.count);
     w.pool = TcPool();
     if (slots < w.slots) slots = w.slots;
-    if (slot_rows < w.pool.slot_rows) slot_rows = w.pool.slot_rows;
+    if (slot_rows < old_slot_rows) slot_rows = old_slot_rows;
     if (dim < w.dim) dim = w.dim;
     const size_t rows = (size_t)slots * slot_rows;
     CU(e, cudaMalloc(&w.pool.hi, rows * dim * sizeof(uint16_t)));
@@ -708,6 +710,8 @@ int surf_create(const surf_params *params, int device, int max_width, int max_he
     e->ev_valid = true;
     cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking);
     cudaStreamCreateWithFlags(&e->match_stream, cudaStreamNonBlocking);
+    cudaEventCreate(&e->ev_match_t0);
+    cudaEventCreate(&e->ev_match_t1);
     cudaEventCreateWithFlags(&e->ev_batch_done, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&e->ev_match_done, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&e->ev_copy_done, cudaEventDisableTiming);
@@ -746,6 +750,10 @@ void surf_destroy(surf_engine *e)
     // every stream that may still touch the workspace drains before it is freed
     for (cudaStream_t st : {e->la_stream, e->upload_stream, e->match_stream, e->copy_stream, e->stream})
         if (st) cudaStreamSynchronize(st);
+    if (e->solo) {
+        surf_comm_destroy(e->solo);
+        e->solo = nullptr;
+    }
     free_workspace(e);
     if (e->ev_valid)
         for (int i = 0; i < EV_COUNT; i++) cudaEventDestroy(e->ev[i]);
@@ -757,6 +765,10 @@ void surf_destroy(surf_engine *e)
         cudaStreamSynchronize(e->match_stream);
         cudaStreamDestroy(e->match_stream);
     }
+    if (e->ev_match_t0) cudaEventDestroy(e->ev_match_t0);
+    if (e->ev_match_t1) cudaEventDestroy(e->ev_match_t1);
+    for (cudaEvent_t m : e->marks)
+        if (m) cudaEventDestroy(m);
     if (e->ev_batch_done) cudaEventDestroy(e->ev_batch_done);
     if (e->ev_match_done) cudaEventDestroy(e->ev_match_done);
     if (e->ev_copy_done) cudaEventDestroy(e->ev_copy_done);
@@ -789,9 +801,15 @@ int surf_set_params(surf_engine *e, const surf_params *params)
     int rc = check_params(e, params);
     if (rc) return rc;
     if ((rc = ensure_device(e))) return rc;
-    CU(e, cudaStreamSynchronize(e->la_stream));
+    // every stream that may still touch buffers about to be re-allocated drains first
+    for (cudaStream_t st : {e->la_stream, e->upload_stream, e->match_stream, e->copy_stream, e->stream})
+        CU(e, cudaStreamSynchronize(st));
     e->la.valid = false;
-    CU(e, cudaStreamSynchronize(e->stream));
+    e->match_in_flight = e->copies_in_flight = e->match_copies_in_flight = false;
+    // a pending batch and the stream matcher's predecessor frame were produced with the old parameters
+    // (descriptor length, thresholds): neither is carried over
+    e->pending.active = false;
+    e->stream_primed = false;
     e->params = *params;
     e->tmap_w = 0;  // layer tables depend on the parameters
     e->alt.tmap_w = 0;
@@ -870,6 +888,7 @@ int surf_submit_batch(surf_engine *e, const uint8_t *images, int in_mem, int bat
         e->free_cur_recorded = true;
     }
     e->pending.active = true;
+    e->pending.matched = false;
     e->pending.batch = batch;
     e->pending.want_desc = want_descriptors != 0;
     return SURF_OK;
@@ -1376,9 +1395,17 @@ int surf_match_prev(surf_engine *e, float ratio, surf_dmatch *out, uint8_t *good
     if (!e) return SURF_ERR_BAD_ARG;
     if (!e->pending.active || !e->pending.want_desc)
         return fail(e, SURF_ERR_BAD_ARG, "surf_match_prev needs a submitted and collected batch with descriptors");
+    if (e->pending.matched)
+        return fail(e, SURF_ERR_BAD_ARG, "surf_match_prev was already called for this batch");
     int rc = ensure_device(e);
     if (rc) return rc;
     const int B = e->pending.batch, D = e->params.extended ? 128 : 64;
+    const long total = e->h_pin[2 * B + B];  // offsets[B] fetched by surf_collect_batch
+    if ((out || good) && total > capacity) {  // nothing launched, stream state untouched: the caller may retry
+        e->required = total;
+        return fail(e, SURF_ERR_CAPACITY, "%ld keypoints in the batch; the match arrays hold %ld", total, capacity);
+    }
+    e->pending.matched = true;
     const int slots = e->max_b + 1, rows = (e->cap + 255) & ~255;
     surf_engine::TcWs &w = e->tc[1];
     if ((rc = tc_reserve(e, w, slots, rows, D))) return rc;
@@ -1400,6 +1427,7 @@ int surf_match_prev(surf_engine *e, float ratio, surf_dmatch *out, uint8_t *good
         launch_zero(e->d_prev_off, 2, ms, nullptr);
     }
     int launches = 0;
+    CU(e, cudaEventRecord(e->ev_match_t0, ms));
     launch_tc_stream_tables(w.segs, w.probs, B, slots, e->tc_prev_slot, e->d_out_desc, e->d_off_out, e->d_prev_desc,
                             e->d_prev_off, ms, &launches);
     const int prev = (e->tc_prev_slot + B) % slots;
@@ -1413,19 +1441,16 @@ int surf_match_prev(surf_engine *e, float ratio, surf_dmatch *out, uint8_t *good
     e->last_tc_ws = 1;
     // keep the last frame (fp32 rows + its slot) as the next batch's predecessor
     launch_copy_rows(e->d_out_desc, e->d_off_out + B - 1, D, e->d_prev_desc, e->cap, e->d_prev_off, ms, &launches);
+    CU(e, cudaEventRecord(e->ev_match_t1, ms));
     CU(e, cudaEventRecord(e->ev_match_done, ms));
     e->match_in_flight = true;
+    e->match_launches = launches;
     e->launches = launches;
     e->timings.launches = launches;
     CU(e, cudaGetLastError());
     e->tc_prev_slot = prev;
     e->stream_primed = true;
-    const long total = e->h_pin[2 * B + B];  // offsets[B] fetched by surf_collect_batch
     if (out || good) {
-        if (total > capacity) {
-            e->required = total;
-            return fail(e, SURF_ERR_CAPACITY, "%ld keypoints in the batch; the match arrays hold %ld", total, capacity);
-        }
         const cudaMemcpyKind kind = out_mem == SURF_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
         cudaStream_t cs = ms;
         if (e->async_outputs) {  // copy stream waits for the match kernels, the host does not
@@ -1441,6 +1466,41 @@ int surf_match_prev(surf_engine *e, float ratio, surf_dmatch *out, uint8_t *good
             CU(e, cudaStreamSynchronize(ms));
         }
     }
+    return SURF_OK;
+}
+
+int surf_match_prev_time(surf_engine *e, float *ms, int *launches)
+{
+    if (!e || !ms) return SURF_ERR_BAD_ARG;
+    *ms = 0.f;
+    if (launches) *launches = e->match_launches;
+    if (!e->stream_primed) return SURF_OK;  // no surf_match_prev since the last reset
+    int rc = ensure_device(e);
+    if (rc) return rc;
+    CU(e, cudaEventSynchronize(e->ev_match_t1));
+    CU(e, cudaEventElapsedTime(ms, e->ev_match_t0, e->ev_match_t1));
+    return SURF_OK;
+}
+
+int surf_mark(surf_engine *e, int slot)
+{
+    if (!e || slot < 0 || slot >= SURF_MAX_MARKS) return SURF_ERR_BAD_ARG;
+    int rc = ensure_device(e);
+    if (rc) return rc;
+    if (!e->marks[slot]) CU(e, cudaEventCreate(&e->marks[slot]));
+    CU(e, cudaEventRecord(e->marks[slot], e->stream));
+    return SURF_OK;
+}
+
+int surf_mark_elapsed(surf_engine *e, int from_slot, int to_slot, float *ms)
+{
+    if (!e || !ms || from_slot < 0 || from_slot >= SURF_MAX_MARKS || to_slot < 0 || to_slot >= SURF_MAX_MARKS)
+        return SURF_ERR_BAD_ARG;
+    if (!e->marks[from_slot] || !e->marks[to_slot]) return fail(e, SURF_ERR_BAD_ARG, "mark not recorded");
+    int rc = ensure_device(e);
+    if (rc) return rc;
+    CU(e, cudaEventSynchronize(e->marks[to_slot]));
+    CU(e, cudaEventElapsedTime(ms, e->marks[from_slot], e->marks[to_slot]));
     return SURF_OK;
 }
 

@@ -17,6 +17,7 @@ enum Ev { EV_START, EV_H2D, EV_INTEGRAL, EV_HESSIAN_NMS, EV_SORT, EV_DESC_START,
 
 struct Pending {
     bool active = false;
+    bool matched = false;   // surf_match_prev already ran on this batch
     int batch = 0;
     bool want_desc = false;
 };
@@ -29,6 +30,9 @@ struct surf_engine {
     cudaStream_t copy_stream = nullptr;  // device->host result copies in asynchronous-output mode
     cudaStream_t match_stream = nullptr; // surf_match_prev runs here, concurrently with the next batch's kernels
     cudaEvent_t ev_batch_done = nullptr, ev_match_done = nullptr;
+    cudaEvent_t ev_match_t0 = nullptr, ev_match_t1 = nullptr;  // timed: the last surf_match_prev on match_stream
+    int match_launches = 0;
+    cudaEvent_t marks[SURF_MAX_MARKS]{};                       // surf_mark
     bool match_in_flight = false;
     cudaEvent_t ev_copy_done = nullptr, ev_match_copy_done = nullptr, ev_ready = nullptr;
     bool match_copies_in_flight = false;
@@ -124,6 +128,7 @@ struct surf_engine {
     surf_dmatch *d_stream_matches = nullptr;
     uint8_t *d_stream_good = nullptr;
 
+    struct surf_comm *solo = nullptr;  // single-GPU context of surf_sweep_sharded (surf_comm.cu), destroyed with the engine
     surf_keypoint *sorted = nullptr;  // which of d_kp_a / d_kp_b holds the current keypoints
     Pending pending;
     surf_timings timings{};
@@ -133,7 +138,28 @@ struct surf_engine {
 };
 
 
+struct surf_db {
+    surf_engine *e = nullptr;
+    int dim = 64;
+    long max_rows = 0;
+    int max_images = 0;
+    TcPool pool{};                  // one slot of slot_rows >= max_rows rows
+    float *rows = nullptr;          // fp32 [max_rows][dim]
+    surf_keypoint *kps = nullptr;   // [max_rows]
+    int *d_img_off = nullptr;       // [max_images + 1]
+    TcSegment *d_seg = nullptr;     // one table entry for the append being prepared
+    std::vector<int> img_off;       // host copy, img_off[0] = 0
+    bool has_kps = true;            // false once an add() came without keypoints
+    void *vote_ws = nullptr;        // scratch of surf_correspond (owned by the train database)
+    size_t vote_ws_cap = 0;
+};
+
 namespace surfb200 {
+
+inline long db_rows(const surf_db *db) { return db->img_off.empty() ? 0 : db->img_off.back(); }
+// k-NN of device-resident query rows against a database on the engine stream; records carry (img_idx, row within
+// the image) when `localize`, else (0, row within the database)
+int db_knn_device(surf_db *db, const float *dq, int n_query, int k, surf_dmatch *dout, int *launches, bool localize = true);
 
 int fail(surf_engine *e, int code, const char *fmt, ...);
 int ensure_device(surf_engine *e);

@@ -41,6 +41,8 @@ ABI_SYMBOLS = [
     "surf_wait_outputs", "surf_db_create", "surf_db_destroy", "surf_db_clear", "surf_db_add", "surf_db_size",
     "surf_db_knn", "surf_correspond", "surf_mha_open", "surf_mha_close", "surf_mha_last_error", "surf_mha_transforms",
     "surf_mha_validity", "surf_mha_frame_name", "surf_mha_read", "surf_crop_rect", "surf_mask_centroid", "surf_sweep_mha",
+    "surf_mark", "surf_mark_elapsed", "surf_match_prev_time", "surf_comm_unique_id", "surf_comm_init", "surf_comm_destroy",
+    "surf_comm_info", "surf_shard_range", "surf_sweep_sharded", "surf_db_knn_sharded", "surf_comm_last_times",
 ]
 
 
@@ -65,6 +67,14 @@ class Timings(C.Structure):
 
 class VoteParams(C.Structure):
     _fields_ = [("bogus_ratio", C.c_float), ("ref_x", C.c_int32), ("ref_y", C.c_int32)]
+
+
+class SweepStats(C.Structure):
+    _fields_ = [("total_ms", C.c_float), ("exchange_ms", C.c_float), ("assemble_ms", C.c_float),
+                ("bytes_sent", C.c_int64), ("bytes_received", C.c_int64), ("chunks", C.c_int32), ("launches", C.c_int32)]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
 
 
 VOTE_RESULT_DTYPE = np.dtype([("n_matches", "<i4"), ("hough_count", "<i4"), ("best_image", "<i4"),
@@ -137,6 +147,19 @@ def load_library():
     L.surf_db_size.argtypes = [vp, C.POINTER(lng), C.POINTER(i32)]
     L.surf_db_knn.argtypes = [vp, vp, i32, i32, vp, i32]
     L.surf_correspond.argtypes = [vp, vp, vp, vp, vp, i32, C.POINTER(VoteParams), vp, vp, i32]
+    L.surf_mark.argtypes = [vp, i32]
+    L.surf_mark_elapsed.argtypes = [vp, i32, i32, C.POINTER(C.c_float)]
+    L.surf_match_prev_time.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(i32)]
+    L.surf_comm_unique_id.argtypes = [vp]
+    L.surf_comm_init.argtypes = [vp, vp, i32, i32, C.POINTER(vp)]
+    L.surf_comm_destroy.argtypes = [vp]
+    L.surf_comm_destroy.restype = None
+    L.surf_comm_info.argtypes = [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]
+    L.surf_shard_range.argtypes = [lng, i32, i32, C.POINTER(lng), C.POINTER(lng)]
+    L.surf_sweep_sharded.argtypes = [vp, vp, vp, i32, lng, i32, i32, sz, sz, vp, sz, i32, i32, vp, vp, i32, lng, vp,
+                                     C.POINTER(SweepStats)]
+    L.surf_db_knn_sharded.argtypes = [vp, vp, vp, i32, i32, i32, vp, i32]
+    L.surf_comm_last_times.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_float)]
     L.surf_version.argtypes = []
     L.surf_version.restype = C.c_char_p
     for name in ABI_SYMBOLS:
@@ -289,6 +312,8 @@ class SURF:
             raise SurfError(-1, "images must be (B, H, W) uint8")
         B, H, W = images.shape
         m = None if mask is None else _u8(mask, "mask")
+        if m is not None and m.shape != (H, W):
+            raise SurfError(-1, "mask must have the frames' size")
         D = self.descriptorSize()
         cap = int(capacity) if capacity else B * self.max_keypoints
         kps = np.zeros(cap, KEYPOINT_DTYPE)
@@ -439,6 +464,128 @@ class SURF:
     def merge_topk_device(self, in_ptr: int, n_ranks: int, nq: int, k: int, out_ptr: int):
         self._check(self._lib.surf_merge_topk(self._h, in_ptr, n_ranks, nq, k, out_ptr))
 
+    # ---- timing marks on the engine's stream ----
+    def mark(self, slot: int):
+        self._check(self._lib.surf_mark(self._h, slot))
+
+    def mark_elapsed(self, a: int, b: int) -> float:
+        ms = C.c_float(0)
+        self._check(self._lib.surf_mark_elapsed(self._h, a, b, C.byref(ms)))
+        return float(ms.value)
+
+    def match_prev_time(self):
+        """(device ms, kernel launches) of the last match_prev* call; waits for it."""
+        ms, n = C.c_float(0), C.c_int(0)
+        self._check(self._lib.surf_match_prev_time(self._h, C.byref(ms), C.byref(n)))
+        return float(ms.value), int(n.value)
+
+    # ---- frame-sharded sweep (BASELINE config 4) ----
+    def sweep_sharded(self, comm, frames_local: np.ndarray, n_frames_total: int, mask=None, want_descriptors=True,
+                      dst: int = 0, capacity: Optional[int] = None):
+        """computeNext over a sweep sharded by frame (surf_sweep_sharded): `frames_local` is this rank's contiguous
+        block (shard_range(n_frames_total, rank, world)), host memory.  Returns (kps, desc, offsets[int64], stats)
+        on rank `dst` and (None, None, None, stats) elsewhere.  comm=None: one GPU."""
+        fr = np.ascontiguousarray(frames_local, dtype=np.uint8)
+        if fr.ndim != 3:
+            raise SurfError(-1, "frames_local must be (n, H, W) uint8")
+        n, H, W = fr.shape
+        rank, world = (comm.rank, comm.world) if comm is not None else (0, 1)
+        m = None if mask is None else _u8(mask, "mask")
+        if m is not None and m.shape != (H, W):
+            raise SurfError(-1, "mask must have the frames' size")
+        D = self.descriptorSize()
+        st = SweepStats()
+        kps = desc = off = None
+        cap = 0
+        if rank == dst:
+            cap = int(capacity) if capacity else n_frames_total * self.max_keypoints
+            kps = np.zeros(cap, KEYPOINT_DTYPE)
+            desc = np.zeros((cap, D), np.float32) if want_descriptors else None
+            off = np.zeros(n_frames_total + 1, np.int64)
+        self._check(self._lib.surf_sweep_sharded(
+            self._h, None if comm is None else comm._h, _ptr(fr) if n else None, MEM_HOST, n_frames_total, W, H, W, W * H,
+            _ptr(m), 0 if m is None else m.strides[0], int(want_descriptors), dst, _ptr(kps), _ptr(desc), MEM_HOST, cap,
+            _ptr(off), C.byref(st)))
+        if rank != dst:
+            return None, None, None, st.as_dict()
+        nk = int(off[-1])
+        return kps[:nk], (None if desc is None else desc[:nk]), off, st.as_dict()
+
+    def sweep_sharded_device(self, comm, images_ptr: int, n_frames_total: int, W: int, H: int, pitch: int,
+                             frame_stride: int, dst: int, kps_ptr: int, desc_ptr: int, capacity: int,
+                             offsets: Optional[np.ndarray], want_descriptors: bool = True):
+        """Raw-pointer form: device-resident frames in, device-resident gathered results out (on `dst`)."""
+        st = SweepStats()
+        self._check(self._lib.surf_sweep_sharded(
+            self._h, None if comm is None else comm._h, images_ptr or None, MEM_DEVICE, n_frames_total, W, H, pitch,
+            frame_stride, None, 0, int(want_descriptors), dst, kps_ptr or None, desc_ptr or None, MEM_DEVICE, capacity,
+            _ptr(offsets), C.byref(st)))
+        return st.as_dict()
+
+
+def shard_range(n_items: int, rank: int, world: int):
+    """Contiguous block [lo, hi) of rank `rank` (surf_shard_range): the first n_items % world ranks get one more."""
+    lo, hi = C.c_long(0), C.c_long(0)
+    rc = load_library().surf_shard_range(n_items, rank, world, C.byref(lo), C.byref(hi))
+    if rc != SURF_OK:
+        raise SurfError(rc, "bad shard_range arguments")
+    return lo.value, hi.value
+
+
+class Comm:
+    """NCCL communicator of the engine's device (surf_comm_*): one process per GPU.  The 128-byte id comes from
+    Comm.unique_id() on one rank and reaches the others by any transport (bench.py: torch.distributed broadcast)."""
+
+    def __init__(self, engine: SURF, unique_id: bytes, rank: int, world: int):
+        if len(unique_id) != 128:
+            raise SurfError(-1, "unique_id must be 128 bytes")
+        self._engine, self._lib = engine, engine._lib
+        self.rank, self.world = rank, world
+        h = C.c_void_p()
+        buf = C.create_string_buffer(bytes(unique_id), 128)
+        engine._check(self._lib.surf_comm_init(engine._h, buf, rank, world, C.byref(h)))
+        self._h = h
+
+    @staticmethod
+    def unique_id() -> bytes:
+        buf = C.create_string_buffer(128)
+        rc = load_library().surf_comm_unique_id(buf)
+        if rc != SURF_OK:
+            raise SurfError(rc, "ncclGetUniqueId failed (is libnccl.so.2 loadable?)")
+        return buf.raw
+
+    @classmethod
+    def from_torch(cls, engine: SURF):
+        """Rendezvous over an initialised torch.distributed process group (plumbing only)."""
+        import torch
+        import torch.distributed as dist
+
+        rank, world = dist.get_rank(), dist.get_world_size()
+        t = torch.zeros(128, dtype=torch.uint8)
+        if rank == 0:
+            t = torch.frombuffer(bytearray(cls.unique_id()), dtype=torch.uint8).clone()
+        if dist.get_backend() == "nccl":
+            t = t.cuda()
+        dist.broadcast(t, 0)
+        return cls(engine, bytes(t.cpu().numpy().tobytes()), rank, world)
+
+    def info(self):
+        r, n, v = C.c_int(0), C.c_int(0), C.c_int(0)
+        self._engine._check(self._lib.surf_comm_info(self._h, C.byref(r), C.byref(n), C.byref(v)))
+        return {"rank": r.value, "world": n.value, "nccl_version": v.value}
+
+    def last_times(self):
+        a, b = C.c_float(0), C.c_float(0)
+        self._engine._check(self._lib.surf_comm_last_times(self._h, C.byref(a), C.byref(b)))
+        return {"total_ms": float(a.value), "nccl_ms": float(b.value)}
+
+    def close(self):
+        if getattr(self, "_h", None) and getattr(self._engine, "_h", None):
+            self._lib.surf_comm_destroy(self._h)
+        self._h = None
+
+    __del__ = close
+
 
 class DescriptorDB:
     """Device-resident train database (surf_db_*): what cv::DescriptorMatcher::add(vector<Mat>) builds at
@@ -491,6 +638,19 @@ class DescriptorDB:
         out = np.zeros((q.shape[0], k), DMATCH_DTYPE)
         self._engine._check(self._lib.surf_db_knn(self._h, _ptr(q), q.shape[0], k, _ptr(out), MEM_HOST))
         return out
+
+    def knnMatchSharded(self, comm, queryDescriptors, k=2, query_root: int = -1) -> np.ndarray:
+        """knnMatch against a database whose rows are sharded over the ranks of `comm` (this object holds this
+        rank's block).  trainIdx is the global row; every rank gets the merged result (surf_db_knn_sharded)."""
+        q = np.ascontiguousarray(queryDescriptors, np.float32)
+        out = np.zeros((q.shape[0], k), DMATCH_DTYPE)
+        self._engine._check(self._lib.surf_db_knn_sharded(self._h, None if comm is None else comm._h, _ptr(q), q.shape[0], k,
+                                                          query_root, _ptr(out), MEM_HOST))
+        return out
+
+    def knn_sharded_device(self, comm, q_ptr: int, nq: int, k: int, out_ptr: int, query_root: int = -1):
+        self._engine._check(self._lib.surf_db_knn_sharded(self._h, None if comm is None else comm._h, q_ptr, nq, k,
+                                                          query_root, out_ptr, MEM_DEVICE))
 
 
 def correspond(train: DescriptorDB, bogus: DescriptorDB, query_descriptors: Sequence[np.ndarray],

@@ -7,8 +7,11 @@ frame blocks with NO collective on the data path; the only exchange steps are
                     order (BASELINE config 4), and
   * match_sharded : all-gather of the per-rank top-k candidate records of a row-sharded keyframe
                     database followed by a merge (BASELINE config 5; ties -> lower global row).
-`compute` / `match` / `merge` are callables so that the same plumbing runs on the B200 engine (NCCL) and,
-in the CPU tests, on a stand-in over gloo.
+On a B200 both exchange steps are product code behind the C ABI (surf_sweep_sharded, surf_db_knn_sharded in
+csrc/surf_comm.cu: NCCL on device buffers; Python mirror SURF.sweep_sharded / DescriptorDB.knnMatchSharded).  This
+module restates the same protocol over torch.distributed with `compute` / `match` / `merge` as callables, so that the
+host-side logic (shard ranges, frame order, global row indices, tie rule) is covered on the CPU over gloo with
+world_size 2; it is not on the GPU path.
 """
 from __future__ import annotations
 
@@ -67,7 +70,7 @@ def sweep_sharded(frames_local: np.ndarray, compute: Callable, group=None, dst: 
             all_d.append(d_t)
         elif nk:
             kr = torch.empty((nk, 7), dtype=torch.int32, device=dev)
-            dr = torch.empty((nk, D), dtype=torch.float32, device=dev)
+            dr = torch.empty((nk, int(metas[r][2])), dtype=torch.float32, device=dev)   # the SENDER's descriptor length
             dist.recv(kr, r, group=group)
             dist.recv(dr, r, group=group)
             all_k.append(kr)
