@@ -66,7 +66,8 @@ typedef struct surf_params {
 
 typedef struct surf_engine surf_engine;
 
-/* Per-stage device times of the last batch call, milliseconds (CUDA events on the engine stream). */
+/* Per-stage device times of the batch collected last, milliseconds (CUDA events on the engine's streams).  d2h is
+ * the fetch of the per-frame counters; total ends there (result copies run on a separate copy stream). */
 typedef struct surf_timings {
     float h2d, integral, hessian, nms, sort, describe, pack, d2h, total;
     int32_t launches; /* kernels launched by the last call */
@@ -118,8 +119,13 @@ int surf_detect_and_compute_batch(surf_engine *e, const uint8_t *images, int in_
                                   size_t mask_pitch, surf_keypoint *keypoints, float *descriptors, int out_mem,
                                   long capacity, int32_t *offsets);
 
-/* Asynchronous halves of the call above, for double-buffered streams (two engines, alternate):
- * submit enqueues upload + all kernels; collect waits and copies the packed results out. */
+/* Asynchronous halves of the call above: submit enqueues upload + all kernels; collect waits for the batch and
+ * copies the packed results out.  TWO batches may be in flight: surf_submit_batch(i+1) may precede
+ * surf_collect_batch(i) (collect always takes the oldest submitted batch), so the GPU never idles while the host
+ * reads counters and enqueues copies; a third submit without a collect is SURF_ERR_BAD_ARG.
+ * Sizing the outputs: a collect whose arrays are too small returns SURF_ERR_CAPACITY with offsets[] filled and leaves
+ * the batch collectable; with no batch in flight, a further collect repeats the copy of the batch collected last (a
+ * counts-only call with NULL arrays first, then the real one). */
 int surf_submit_batch(surf_engine *e, const uint8_t *images, int in_mem, int batch, int width, int height,
                       size_t pitch, size_t frame_stride, const uint8_t *mask, size_t mask_pitch, int want_descriptors);
 int surf_collect_batch(surf_engine *e, surf_keypoint *keypoints, float *descriptors, int out_mem, long capacity,
@@ -137,9 +143,9 @@ int surf_prefetch_batch(surf_engine *e, const uint8_t *images, int batch, int wi
  * the look-ahead.  Frames and mask must stay unchanged until that submit's results are collected. */
 int surf_lookahead_batch(surf_engine *e, const uint8_t *images, int in_mem, int batch, int width, int height, size_t pitch,
                          size_t frame_stride, const uint8_t *mask, size_t mask_pitch);
-/* Device-resident results of the last submitted batch (valid until the next submit): packed
- * keypoints, packed descriptors, device int32 offsets[batch+1]. Requires surf_collect_batch or
- * surf_sync first if the host needs the counts. */
+/* Device-resident results of the batch collected last (valid until the second submit after that batch's own):
+ * packed keypoints, packed descriptors, device int32 offsets[batch+1].  Before any collect: of the batch
+ * submitted last (surf_sync first if the host needs them complete). */
 int surf_device_results(surf_engine *e, const surf_keypoint **keypoints, const float **descriptors,
                         const int32_t **offsets);
 int surf_sync(surf_engine *e);
@@ -175,7 +181,7 @@ int surf_match_knn(surf_engine *e, const float *query, int n_query, const float 
 int surf_match_ratio(surf_engine *e, const float *query, int n_query, const float *train, int n_train, int dim,
                      float ratio, surf_dmatch *out, uint8_t *good, int mem);
 
-/* Live-stream matching (BASELINE config 2): every frame of the batch last submitted AND collected
+/* Live-stream matching (BASELINE config 2): every frame of the batch collected last
  * on this engine is matched (k = 2 + ratio test) against its predecessor -- the first frame against
  * the last frame of the previous batch (no matches on the very first call or after
  * surf_stream_reset).  Results are packed like the keypoints: 2 records per keypoint, row

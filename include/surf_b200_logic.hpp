@@ -19,7 +19,8 @@
 //
 // Differences that are deliberate: a computeNext*() call advances by one engine batch instead of one frame (the
 // progress getters still run 0..100); the descriptors stay on the device (train / bogus databases) unless asked
-// for; RANSAC / plane fitting / simulateAll (row f4) are not part of this library.
+// for; simulateAll and the overlay drawing are not part of this library (ransac() and the pose estimate, row f4, are:
+// see below).  The start / stop frame defaults are the reference constructor's (.cxx:1021-1026).
 #ifndef SURF_B200_LOGIC_HPP
 #define SURF_B200_LOGIC_HPP
 
@@ -39,8 +40,8 @@ public:
           maskData_(0), maskW_(0), maskH_(0), maskStep_(0), batch_(batch), dbRows_(db_rows), dbImages_(db_images)
     {
         cropRatios[0] = 1 / 5.; cropRatios[1] = 3. / 3.9; cropRatios[2] = 1 / 6.; cropRatios[3] = 3. / 4.;  // .cxx:1008-1009
-        bogusStartFrame = trainStartFrame = 0;
-        bogusStopFrame = trainStopFrame = -1;
+        bogusStartFrame = trainStartFrame = 0;                                                             // .cxx:1021-1024
+        bogusStopFrame = trainStopFrame = 2;
         queryStartFrame = 3; queryStopFrame = 5;                                                           // .cxx:1025-1026
         // the reference's effective parameters: detector (minHessian, 4, 2), default-constructed extractor
         surf_params p = {(double)minHessian, 4, 2, 1, 0};
@@ -186,7 +187,8 @@ private:
         std::vector<float> desc;
         std::vector<int32_t> offsets;
         std::vector<unsigned char> stage;
-        Sweep() : seq(0), info(), done(0) {}
+        int32_t rect[4];               // cropData's rectangle for THIS file's frame size (cv::Rect x, y, w, h)
+        Sweep() : seq(0), info(), done(0) { rect[0] = rect[1] = rect[2] = rect[3] = 0; }
     };
 
     void check(int rc) const
@@ -217,10 +219,10 @@ private:
         last = w.info.last_frame;
         surf_params p = {(double)minHessian, 4, 2, 1, 0};
         check(surf_set_params(e_, &p));
-        check(surf_crop_rect(w.info.width, w.info.height, cropRatios, rect_));
+        check(surf_crop_rect(w.info.width, w.info.height, cropRatios, w.rect));   // every file is cropped by its own size
         if (maskData_) {
             if (maskW_ != w.info.width || maskH_ != w.info.height) throw Error(SURF_ERR_BAD_ARG, "mask size differs from the frames");
-            check(surf_mask_centroid(maskData_ + (size_t)rect_[1] * maskStep_ + rect_[0], rect_[2], rect_[3], maskStep_, &xcentroid,
+            check(surf_mask_centroid(maskData_ + (size_t)w.rect[1] * maskStep_ + w.rect[0], w.rect[2], w.rect[3], maskStep_, &xcentroid,
                                      &ycentroid));
         }
         if (s == TRAIN) check(surf_db_clear(trainDb_));
@@ -235,9 +237,10 @@ private:
         const int cnt = w.info.n_frames - w.done < batch_ ? w.info.n_frames - w.done : batch_;
         const size_t fb = (size_t)w.info.width * w.info.height;
         check(surf_mha_read(w.seq, w.done, cnt, w.stage.data(), fb));
-        const unsigned char *view = w.stage.data() + (size_t)rect_[1] * w.info.width + rect_[0];
-        const unsigned char *cmask = maskData_ ? maskData_ + (size_t)rect_[1] * maskStep_ + rect_[0] : 0;
-        check(surf_submit_batch(e_, view, SURF_MEM_HOST, cnt, rect_[2], rect_[3], (size_t)w.info.width, fb, cmask, maskStep_, 1));
+        const int32_t *rect = w.rect;
+        const unsigned char *view = w.stage.data() + (size_t)rect[1] * w.info.width + rect[0];
+        const unsigned char *cmask = maskData_ ? maskData_ + (size_t)rect[1] * maskStep_ + rect[0] : 0;
+        check(surf_submit_batch(e_, view, SURF_MEM_HOST, cnt, rect[2], rect[3], (size_t)w.info.width, fb, cmask, maskStep_, 1));
         std::vector<int32_t> off(cnt + 1);
         if (s == QUERY) {
             // counts first (a collect without outputs), then a second collect into the grown host arrays
@@ -267,7 +270,6 @@ private:
     int batch_;
     long dbRows_;
     int dbImages_;
-    int32_t rect_[4];
     Sweep sweep_[3];
 };
 

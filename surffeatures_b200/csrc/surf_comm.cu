@@ -409,32 +409,49 @@ int surf_sweep_sharded(surf_engine *e, surf_comm *comm, const uint8_t *images_lo
 
     CU(e, cudaEventRecord(c->ev_t[0], e->stream));
     size_t local_rows = 0;
-    bool lookahead_issued = false;
+    auto chunk_frames = [&](int x) {
+        const long f0 = (long)x * B;
+        return (int)(n_local - f0 < 0 ? 0 : (n_local - f0 > B ? B : n_local - f0));
+    };
+    auto chunk_ptr = [&](int x) { return images_local + (size_t)x * B * frame_stride; };
+    auto note_error = [&](int r) {
+        if (r && first_error == SURF_OK) {  // keep the collective protocol going with empty chunks; report at the end
+            first_error = r;
+            snprintf(first_msg, sizeof(first_msg), "%s", e->err);
+        }
+    };
+    // Two batches in flight: chunk x+1 is submitted (continuing from its look-ahead) and chunk x+2's stages 1-3 are
+    // started before the host waits for chunk x, so the GPU always has the next descriptor stage queued.
+    bool submitted_next = false;
+    if (chunk_frames(0) > 0) {
+        note_error(surf_submit_batch(e, chunk_ptr(0), in_mem, chunk_frames(0), width, height, pitch, frame_stride, mask, mask_pitch,
+                                     want_descriptors));
+        launches += e->launches;
+        if (first_error == SURF_OK && chunk_frames(1) > 0)
+            note_error(surf_lookahead_batch(e, chunk_ptr(1), in_mem, chunk_frames(1), width, height, pitch, frame_stride, mask,
+                                            mask_pitch));
+    }
     for (int x = 0; x < n_chunks; x++) {
         const int s = x & 1;
-        const long f0 = (long)x * B;
-        const int nb = (int)(n_local - f0 < 0 ? 0 : (n_local - f0 > B ? B : n_local - f0));
+        const int nb = chunk_frames(x);
         chunk_row0[x] = local_rows;
         memset(c->h_cnt_local[s], 0, sizeof(int) * B);
         if (nb > 0 && first_error == SURF_OK) {
-            const uint8_t *src = images_local + (size_t)f0 * frame_stride;
-            rc = surf_submit_batch(e, src, in_mem, nb, width, height, pitch, frame_stride, mask, mask_pitch, want_descriptors);
-            launches += e->launches;
-            const long f1 = f0 + B;
-            const int nb2 = (int)(n_local - f1 < 0 ? 0 : (n_local - f1 > B ? B : n_local - f1));
-            lookahead_issued = false;
-            if (!rc && nb2 > 0) {  // stages 1-3 of the next batch run beside this batch's descriptor stage
-                rc = surf_lookahead_batch(e, images_local + (size_t)f1 * frame_stride, in_mem, nb2, width, height, pitch,
-                                          frame_stride, mask, mask_pitch);
-                lookahead_issued = !rc;
+            submitted_next = false;
+            if (chunk_frames(x + 1) > 0) {
+                rc = surf_submit_batch(e, chunk_ptr(x + 1), in_mem, chunk_frames(x + 1), width, height, pitch, frame_stride, mask,
+                                       mask_pitch, want_descriptors);
+                launches += e->launches;
+                submitted_next = !rc;
+                if (!rc && chunk_frames(x + 2) > 0)
+                    rc = surf_lookahead_batch(e, chunk_ptr(x + 2), in_mem, chunk_frames(x + 2), width, height, pitch, frame_stride,
+                                              mask, mask_pitch);
+                note_error(rc);
             }
-            if (!rc)
-                rc = surf_collect_batch(e, own_kp + local_rows, own_desc ? own_desc + local_rows * D : nullptr, SURF_MEM_DEVICE,
-                                        (long)(region_rows[rank] - local_rows), off32.data());
-            if (rc) {  // keep the collective protocol going with empty chunks; report at the end
-                first_error = rc;
-                snprintf(first_msg, sizeof(first_msg), "%s", e->err);
-            } else {
+            rc = surf_collect_batch(e, own_kp + local_rows, own_desc ? own_desc + local_rows * D : nullptr, SURF_MEM_DEVICE,
+                                    (long)(region_rows[rank] - local_rows), off32.data());
+            note_error(rc);
+            if (!rc) {
                 for (int i = 0; i < nb; i++) c->h_cnt_local[s][i] = off32[i + 1] - off32[i];
                 local_rows += (size_t)off32[nb];
             }
@@ -447,7 +464,7 @@ int surf_sweep_sharded(surf_engine *e, surf_comm *comm, const uint8_t *images_lo
         CU(e, cudaEventRecord(c->ev_cnt[s], c->stream));
         if (x > 0 && (rc = exchange(x - 1))) return rc;
     }
-    (void)lookahead_issued;
+    (void)submitted_next;
     chunk_row0[n_chunks] = local_rows;
     if (n_chunks > 0 && (rc = exchange(n_chunks - 1))) return rc;
     CU(e, cudaStreamSynchronize(c->stream));
@@ -497,6 +514,9 @@ int surf_sweep_sharded(surf_engine *e, surf_comm *comm, const uint8_t *images_lo
     }
     cudaGetLastError();
     if (first_error != SURF_OK) {
+        // leave no batch behind: whatever was submitted and not collected is collected into nowhere
+        while (surf_collect_batch(e, nullptr, nullptr, SURF_MEM_DEVICE, 1L << 40, off32.data()) != SURF_ERR_BAD_ARG) {
+        }
         snprintf(e->err, sizeof(e->err), "%s", first_msg);
         return first_error;
     }

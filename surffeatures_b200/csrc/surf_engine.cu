@@ -316,12 +316,48 @@ int check_params(surf_engine *e, const surf_params *p)
     return SURF_OK;
 }
 
+// The buffers named d_out_kp / d_out_desc / d_off_out / h_pin are those of output set s from here on.
+void bind_out(surf_engine *e, int s)
+{
+    e->out_bound = s;
+    e->d_out_kp = e->out[s].d_kp;
+    e->d_out_desc = e->out[s].d_desc;
+    e->d_off_out = e->out[s].d_off;
+    e->h_pin = e->out[s].h_pin;
+}
+
+// A stage-event array no batch in flight is using.
+cudaEvent_t *next_ev_array(surf_engine *e)
+{
+    for (int t = 0; t < surf_engine::kEvSets; t++) {
+        cudaEvent_t *a = e->evpool[e->ev_next];
+        e->ev_next = (e->ev_next + 1) % surf_engine::kEvSets;
+        bool used = (e->la.valid && e->la_ev == a);
+        for (const OutSet &o : e->out) used = used || ((o.active || o.collected) && o.ev == a);
+        if (!used) return a;
+    }
+    return e->evpool[0];
+}
+
+// The single-shot calls (surf_detect, surf_integral, ...) abandon batches that were submitted and not collected.
+void drop_batches(surf_engine *e)
+{
+    for (OutSet &o : e->out) o.active = o.collected = false;
+    e->out_collected = -1;
+}
+
 void free_workspace(surf_engine *e)
 {
     cudaFree(e->d_img); cudaFree(e->d_img_next); cudaFree(e->d_mask); cudaFree(e->d_sum); cudaFree(e->d_msum); cudaFree(e->d_bandsum);
-    cudaFree(e->d_det); cudaFree(e->d_kp_a); cudaFree(e->d_kp_b); cudaFree(e->d_out_kp); cudaFree(e->d_desc);
-    cudaFree(e->d_out_desc); cudaFree(e->d_patches); cudaFree(e->d_counts); cudaFree(e->d_ndel);
-    cudaFree(e->d_off_in); cudaFree(e->d_off_out); cudaFree(e->d_misc); cudaFree(e->d_deleted);
+    cudaFree(e->d_det); cudaFree(e->d_kp_a); cudaFree(e->d_kp_b); cudaFree(e->d_desc);
+    cudaFree(e->d_patches); cudaFree(e->d_counts); cudaFree(e->d_ndel);
+    cudaFree(e->d_off_in); cudaFree(e->d_misc); cudaFree(e->d_deleted);
+    for (OutSet &o : e->out) {
+        cudaFree(o.d_kp); cudaFree(o.d_desc); cudaFree(o.d_off);
+        if (o.h_pin) cudaFreeHost(o.h_pin);
+        o.d_kp = nullptr; o.d_desc = nullptr; o.d_off = nullptr; o.h_pin = nullptr;
+        o.active = o.collected = false;
+    }
     cudaFree(e->d_match_part); cudaFree(e->d_match_io); cudaFree(e->d_class_list); cudaFree(e->d_win_scratch); cudaFree(e->d_sincos); cudaFree(e->d_patch_ws);
     for (auto &w : e->tc) {
         cudaFree(w.pool.hi); cudaFree(w.pool.lo); cudaFree(w.pool.norm); cudaFree(w.pool.max_norm);
@@ -335,7 +371,6 @@ void free_workspace(surf_engine *e)
     e->alt.d_sum = nullptr; e->alt.d_kp_a = e->alt.d_kp_b = e->alt.sorted = nullptr; e->alt.d_counts = nullptr;
     e->alt.tmap_w = 0; e->alt.free_recorded = false;
     e->la.valid = false;
-    if (e->h_pin) cudaFreeHost(e->h_pin);
     e->d_img = e->d_img_next = e->d_mask = nullptr; e->prefetched.valid = false; e->d_sum = e->d_msum = e->d_bandsum = nullptr; e->d_det = nullptr;
     e->d_kp_a = e->d_kp_b = e->d_out_kp = nullptr; e->d_desc = e->d_out_desc = nullptr; e->d_patches = nullptr;
     e->d_counts = e->d_ndel = e->d_off_in = e->d_off_out = e->d_misc = e->d_deleted = nullptr;
@@ -359,12 +394,16 @@ int alloc_det_and_desc(surf_engine *e)
     const int D = e->params.extended ? 128 : 64;
     if (D > e->desc_dim) {
         cudaFree(e->d_desc);
-        cudaFree(e->d_out_desc);
-        e->d_desc = e->d_out_desc = nullptr;
+        e->d_desc = nullptr;
         const size_t n = (size_t)e->max_b * e->cap * D;
         CU(e, cudaMalloc(&e->d_desc, n * sizeof(float)));
-        CU(e, cudaMalloc(&e->d_out_desc, n * sizeof(float)));
+        for (OutSet &o : e->out) {
+            cudaFree(o.d_desc);
+            o.d_desc = nullptr;
+            CU(e, cudaMalloc(&o.d_desc, n * sizeof(float)));
+        }
         e->desc_dim = D;
+        bind_out(e, e->out_bound);
     }
     return SURF_OK;
 }
@@ -382,19 +421,23 @@ int alloc_workspace(surf_engine *e)
     const size_t nk = (size_t)B * cap;
     CU(e, cudaMalloc(&e->d_kp_a, nk * sizeof(surf_keypoint)));
     CU(e, cudaMalloc(&e->d_kp_b, nk * sizeof(surf_keypoint)));
-    CU(e, cudaMalloc(&e->d_out_kp, nk * sizeof(surf_keypoint)));
+    for (OutSet &o : e->out) {
+        CU(e, cudaMalloc(&o.d_kp, nk * sizeof(surf_keypoint)));
+        CU(e, cudaMalloc(&o.d_off, sizeof(int) * (B + 1)));
+        CU(e, cudaMallocHost(&o.h_pin, sizeof(int) * (3 * (size_t)B + 8 + kMiscWords)));
+    }
     CU(e, cudaMalloc(&e->d_deleted, nk * sizeof(int)));
     CU(e, cudaMalloc(&e->d_counts, sizeof(int) * (B + 1)));  // + status word of the TMA kernel
     CU(e, cudaMalloc(&e->d_ndel, sizeof(int) * B));
     CU(e, cudaMalloc(&e->d_off_in, sizeof(int) * (B + 1)));
-    CU(e, cudaMalloc(&e->d_off_out, sizeof(int) * (B + 1)));
     CU(e, cudaMalloc(&e->d_misc, sizeof(int) * kMiscWords));
     CU(e, cudaMalloc(&e->d_class_list, nk * kNumClasses * sizeof(int)));
     CU(e, cudaMalloc(&e->d_win_scratch, describe_scratch_bytes()));
     CU(e, cudaMalloc(&e->d_sincos, nk * sizeof(float2)));
     CU(e, cudaMalloc(&e->d_patch_ws, nk * (size_t)kPatchStride));
-    CU(e, cudaMallocHost(&e->h_pin, sizeof(int) * (3 * (size_t)B + 8 + kMiscWords)));
-    return alloc_det_and_desc(e);
+    int rc = alloc_det_and_desc(e);
+    bind_out(e, 0);
+    return rc;
 }
 
 struct BatchIn {
@@ -531,7 +574,7 @@ int stage_mask(surf_engine *e, const BatchIn &in, const FrameGeo &geo, const uin
     return SURF_OK;
 }
 
-void rec(surf_engine *e, Ev which) { cudaEventRecord(e->ev[which], e->stream); }
+void rec(surf_engine *e, Ev which) { cudaEventRecord(e->ev[which], e->stream); }  // e->ev: the batch's event array
 
 // integral -> Hessian pyramid -> maxima -> sort.  Leaves sorted raw keypoints in e->sorted.
 int run_detect(surf_engine *e, const ImageRef &img, const uint32_t *msum, const FrameGeo &geo, int B)
@@ -602,9 +645,12 @@ int run_describe_pack(surf_engine *e, const ImageRef &img, const FrameGeo &geo, 
     launch_describe(a, e->imap, e->imap_ok ? 1 : 0, e->stream, &e->launches);
     rec(e, EV_DESCRIBE);
     if (pack) {
-        if (e->copies_in_flight) CU(e, cudaStreamWaitEvent(e->stream, e->ev_copy_done, 0));
-        // the stream matcher of the previous batch (on its own stream) still reads the packed descriptors
-        if (e->match_in_flight) CU(e, cudaStreamWaitEvent(e->stream, e->ev_match_done, 0));
+        // the output set being written: its previous batch's result copies, stream matcher (own stream) and match
+        // copies may still be reading it
+        OutSet &o = e->out[e->out_bound];
+        if (o.copies_in_flight) CU(e, cudaStreamWaitEvent(e->stream, o.ev_copy_done, 0));
+        if (o.match_in_flight) CU(e, cudaStreamWaitEvent(e->stream, o.ev_match_done, 0));
+        o.copies_in_flight = o.match_in_flight = false;
         launch_offsets(e->d_counts, e->d_ndel, e->cap, B, e->d_off_out, e->stream, &e->launches);
         launch_pack(e->sorted, want_desc ? e->d_desc : nullptr, p.extended ? 128 : 64, e->cap, B, e->d_off_in, e->d_ndel,
                     e->d_deleted, e->d_off_out, e->d_out_kp, want_desc ? e->d_out_desc : nullptr, e->stream,
@@ -627,6 +673,9 @@ int fetch_counts(surf_engine *e, int B)
     CU(e, cudaMemcpyAsync(h + 2 * B, e->d_off_out, sizeof(int) * (B + 1), cudaMemcpyDeviceToHost, e->stream));
     CU(e, cudaMemcpyAsync(h + 3 * B + 1, e->d_misc, sizeof(int) * kMiscWords, cudaMemcpyDeviceToHost, e->stream));
     CU(e, cudaMemcpyAsync(h + 3 * B + 1 + kMiscWords, e->d_counts + B, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+    // these copies read the detect set's counters: a look-ahead may overwrite the set only after them
+    CU(e, cudaEventRecord(e->ev_set_free, e->stream));
+    e->set_free_recorded = true;
     return SURF_OK;
 }
 
@@ -651,11 +700,14 @@ int check_counts(surf_engine *e, int B)
     return SURF_OK;
 }
 
-void collect_timings(surf_engine *e)
+void collect_timings(surf_engine *e, cudaEvent_t *ev, int launches)
 {
     auto ms = [&](Ev a, Ev b) {
         float t = 0;
-        cudaEventElapsedTime(&t, e->ev[a], e->ev[b]);
+        if (cudaEventElapsedTime(&t, ev[a], ev[b]) != cudaSuccess) {
+            cudaGetLastError();
+            t = 0;
+        }
         return t;
     };
     surf_timings &t = e->timings;
@@ -668,7 +720,7 @@ void collect_timings(surf_engine *e)
     t.pack = ms(EV_DESCRIBE, EV_PACK);
     t.d2h = ms(EV_PACK, EV_END);
     t.total = ms(EV_START, EV_END);
-    t.launches = e->launches;
+    t.launches = launches;
 }
 
 }  // namespace
@@ -706,17 +758,20 @@ int surf_create(const surf_params *params, int device, int max_width, int max_he
         delete e;
         return SURF_ERR_CUDA;
     }
-    for (int i = 0; i < EV_COUNT; i++) cudaEventCreate(&e->ev[i]);
+    for (auto &arr : e->evpool)
+        for (int i = 0; i < EV_COUNT; i++) cudaEventCreate(&arr[i]);
+    e->ev = e->evpool[0];
     e->ev_valid = true;
     cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking);
     cudaStreamCreateWithFlags(&e->match_stream, cudaStreamNonBlocking);
     cudaEventCreate(&e->ev_match_t0);
     cudaEventCreate(&e->ev_match_t1);
-    cudaEventCreateWithFlags(&e->ev_batch_done, cudaEventDisableTiming);
-    cudaEventCreateWithFlags(&e->ev_match_done, cudaEventDisableTiming);
-    cudaEventCreateWithFlags(&e->ev_copy_done, cudaEventDisableTiming);
+    for (OutSet &o : e->out) {
+        cudaEventCreateWithFlags(&o.ev_ready, cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&o.ev_copy_done, cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&o.ev_match_done, cudaEventDisableTiming);
+    }
     cudaEventCreateWithFlags(&e->ev_match_copy_done, cudaEventDisableTiming);
-    cudaEventCreateWithFlags(&e->ev_ready, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&e->ev_upload_done, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&e->ev_free_cur, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&e->ev_free_next, cudaEventDisableTiming);
@@ -726,7 +781,6 @@ int surf_create(const surf_params *params, int device, int max_width, int max_he
     // descriptor stage by more than they save (8.24k frames/s); queued behind the persistent descriptor CTAs they
     // fill the slots those leave free (8.60k frames/s against 8.24k without look-ahead).
     cudaStreamCreateWithFlags(&e->la_stream, cudaStreamNonBlocking);
-    for (int i = 0; i < EV_COUNT; i++) cudaEventCreate(&e->la_ev[i]);
     cudaEventCreateWithFlags(&e->ev_detect_done, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&e->ev_la_done, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&e->ev_set_free, cudaEventDisableTiming);
@@ -756,7 +810,8 @@ void surf_destroy(surf_engine *e)
     }
     free_workspace(e);
     if (e->ev_valid)
-        for (int i = 0; i < EV_COUNT; i++) cudaEventDestroy(e->ev[i]);
+        for (auto &arr : e->evpool)
+            for (int i = 0; i < EV_COUNT; i++) cudaEventDestroy(arr[i]);
     if (e->copy_stream) {
         cudaStreamSynchronize(e->copy_stream);
         cudaStreamDestroy(e->copy_stream);
@@ -769,11 +824,10 @@ void surf_destroy(surf_engine *e)
     if (e->ev_match_t1) cudaEventDestroy(e->ev_match_t1);
     for (cudaEvent_t m : e->marks)
         if (m) cudaEventDestroy(m);
-    if (e->ev_batch_done) cudaEventDestroy(e->ev_batch_done);
-    if (e->ev_match_done) cudaEventDestroy(e->ev_match_done);
-    if (e->ev_copy_done) cudaEventDestroy(e->ev_copy_done);
+    for (OutSet &o : e->out)
+        for (cudaEvent_t ev : {o.ev_ready, o.ev_copy_done, o.ev_match_done})
+            if (ev) cudaEventDestroy(ev);
     if (e->ev_match_copy_done) cudaEventDestroy(e->ev_match_copy_done);
-    if (e->ev_ready) cudaEventDestroy(e->ev_ready);
     if (e->ev_upload_done) cudaEventDestroy(e->ev_upload_done);
     if (e->ev_free_cur) cudaEventDestroy(e->ev_free_cur);
     if (e->ev_free_next) cudaEventDestroy(e->ev_free_next);
@@ -785,8 +839,6 @@ void surf_destroy(surf_engine *e)
         cudaStreamSynchronize(e->la_stream);
         cudaStreamDestroy(e->la_stream);
     }
-    for (int i = 0; i < EV_COUNT; i++)
-        if (e->la_ev[i]) cudaEventDestroy(e->la_ev[i]);
     if (e->ev_detect_done) cudaEventDestroy(e->ev_detect_done);
     if (e->ev_la_done) cudaEventDestroy(e->ev_la_done);
     if (e->ev_set_free) cudaEventDestroy(e->ev_set_free);
@@ -805,10 +857,11 @@ int surf_set_params(surf_engine *e, const surf_params *params)
     for (cudaStream_t st : {e->la_stream, e->upload_stream, e->match_stream, e->copy_stream, e->stream})
         CU(e, cudaStreamSynchronize(st));
     e->la.valid = false;
-    e->match_in_flight = e->copies_in_flight = e->match_copies_in_flight = false;
-    // a pending batch and the stream matcher's predecessor frame were produced with the old parameters
+    for (OutSet &o : e->out) o.match_in_flight = o.copies_in_flight = false;
+    e->match_copies_in_flight = false;
+    // pending batches and the stream matcher's predecessor frame were produced with the old parameters
     // (descriptor length, thresholds): neither is carried over
-    e->pending.active = false;
+    drop_batches(e);
     e->stream_primed = false;
     e->params = *params;
     e->tmap_w = 0;  // layer tables depend on the parameters
@@ -842,7 +895,7 @@ int surf_sync(surf_engine *e)
     if (rc) return rc;
     CU(e, cudaStreamSynchronize(e->stream));
     CU(e, cudaStreamSynchronize(e->match_stream));
-    e->match_in_flight = false;
+    for (OutSet &o : e->out) o.match_in_flight = false;
     return SURF_OK;
 }
 
@@ -853,7 +906,14 @@ int surf_submit_batch(surf_engine *e, const uint8_t *images, int in_mem, int bat
     int rc = check_frame_args(e, in);
     if (rc) return rc;
     if ((rc = ensure_device(e))) return rc;
-    e->pending.active = false;
+    // two batches may be in flight: this one takes the output set the batch before the previous one used
+    const int s = e->out_next;
+    OutSet &o = e->out[s];
+    if (o.active)
+        return fail(e, SURF_ERR_BAD_ARG, "two batches are already submitted: collect one before submitting a third");
+    if (e->out_collected == s) e->out_collected = -1;   // its buffers are about to be overwritten
+    o.collected = false;
+    bind_out(e, s);
     e->launches = 0;
     const FrameGeo geo = make_geo(width, height);
     ImageRef img;
@@ -864,7 +924,7 @@ int surf_submit_batch(surf_engine *e, const uint8_t *images, int in_mem, int bat
         // their stage events and, for host frames, the frame buffer they were uploaded into
         e->la.valid = false;
         swap_detect_sets(e);
-        for (int i = 0; i < EV_COUNT; i++) std::swap(e->ev[i], e->la_ev[i]);
+        e->ev = e->la_ev;
         if (in_mem == SURF_MEM_HOST) {
             std::swap(e->d_img, e->d_img_next);
             std::swap(e->ev_free_cur, e->ev_free_next);
@@ -874,6 +934,7 @@ int surf_submit_batch(surf_engine *e, const uint8_t *images, int in_mem, int bat
         e->launches = la.launches;
         CU(e, cudaStreamWaitEvent(e->stream, e->ev_la_done, 0));
     } else {
+        e->ev = next_ev_array(e);
         rec(e, EV_START);
         if ((rc = stage_images(e, in, &img))) return rc;
         const uint32_t *msum = nullptr;
@@ -883,14 +944,19 @@ int surf_submit_batch(surf_engine *e, const uint8_t *images, int in_mem, int bat
     }
     if ((rc = run_describe_pack(e, img, geo, batch, want_descriptors != 0, nullptr, true))) return rc;
     if ((rc = fetch_counts(e, batch))) return rc;
+    rec(e, EV_END);
+    CU(e, cudaEventRecord(o.ev_ready, e->stream));
     if (in_mem == SURF_MEM_HOST) {  // the staged frames (d_img) are free again after these kernels
         CU(e, cudaEventRecord(e->ev_free_cur, e->stream));
         e->free_cur_recorded = true;
     }
-    e->pending.active = true;
-    e->pending.matched = false;
-    e->pending.batch = batch;
-    e->pending.want_desc = want_descriptors != 0;
+    o.ev = e->ev;
+    o.active = true;
+    o.matched = false;
+    o.batch = batch;
+    o.want_desc = want_descriptors != 0;
+    o.launches = e->launches;
+    e->out_next = s ^ 1;
     return SURF_OK;
 }
 
@@ -951,7 +1017,9 @@ int surf_lookahead_batch(surf_engine *e, const uint8_t *images, int in_mem, int 
     e->launches = 0;
     swap_detect_sets(e);
     std::swap(e->stream, e->la_stream);
-    for (int i = 0; i < EV_COUNT; i++) std::swap(e->ev[i], e->la_ev[i]);
+    cudaEvent_t *const main_ev = e->ev;
+    e->la_ev = next_ev_array(e);   // (la.valid is false here: a replaced look-ahead's array may be taken again)
+    e->ev = e->la_ev;
     const FrameGeo geo = make_geo(width, height);
     ImageRef img;
     rec(e, EV_START);
@@ -975,7 +1043,7 @@ int surf_lookahead_batch(surf_engine *e, const uint8_t *images, int in_mem, int 
     // stream's own marker must be recorded again by its next run_detect
     std::swap(e->ev_detect_done, e->ev_la_done);
     e->detect_done_recorded = false;
-    for (int i = 0; i < EV_COUNT; i++) std::swap(e->ev[i], e->la_ev[i]);
+    e->ev = main_ev;
     std::swap(e->stream, e->la_stream);
     swap_detect_sets(e);
     const int la_launches = e->launches;
@@ -992,45 +1060,57 @@ int surf_collect_batch(surf_engine *e, surf_keypoint *keypoints, float *descript
                        int32_t *offsets)
 {
     if (!e) return SURF_ERR_BAD_ARG;
-    if (!e->pending.active) return fail(e, SURF_ERR_BAD_ARG, "no submitted batch to collect");
+    // the OLDEST submitted batch: with two in flight that is the one the next submit would overwrite
+    int s = e->out_next;
+    if (!e->out[s].active) s ^= 1;
+    // nothing in flight: the batch collected last may be collected again (counts-only call first, then a second call
+    // into arrays sized from the counts) until the next submit
+    if (!e->out[s].active && e->out_collected >= 0 && e->out[e->out_collected].collected) s = e->out_collected;
+    OutSet &o = e->out[s];
+    if (!o.active && !o.collected) return fail(e, SURF_ERR_BAD_ARG, "no submitted batch to collect");
     if (!offsets) return fail(e, SURF_ERR_BAD_ARG, "offsets is null");
     int rc = ensure_device(e);
     if (rc) return rc;
-    const int B = e->pending.batch;
-    CU(e, cudaStreamSynchronize(e->stream));
-    if ((rc = check_counts(e, B))) return rc;
+    const int B = o.batch;
+    CU(e, cudaEventSynchronize(o.ev_ready));   // this batch only: a batch submitted after it keeps the GPU busy meanwhile
+    const int bound = e->out_bound;
+    bind_out(e, s);
+    rc = check_counts(e, B);
     const int *off = e->h_pin + 2 * B;
     const long total = off[B];
-    for (int b = 0; b <= B; b++) offsets[b] = off[b];
-    if (total > capacity) {
-        e->required = total;
-        return fail(e, SURF_ERR_CAPACITY, "%ld keypoints in the batch; the output arrays hold %ld", total, capacity);
+    if (!rc) {
+        for (int b = 0; b <= B; b++) offsets[b] = off[b];
+        if (total > capacity) {
+            e->required = total;
+            rc = fail(e, SURF_ERR_CAPACITY, "%ld keypoints in the batch; the output arrays hold %ld", total, capacity);
+        }
     }
+    if (rc) {   // the batch stays collectable (e.g. with larger arrays after SURF_ERR_CAPACITY)
+        bind_out(e, bound);
+        return rc;
+    }
+    collect_timings(e, o.ev, o.launches);
     const cudaMemcpyKind kind = out_mem == SURF_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
     const int D = e->params.extended ? 128 : 64;
-    // Asynchronous-output mode: the copies go to the copy stream (the compute stream is idle here, so no
-    // event is needed) and overlap the next batch's kernels; surf_wait_outputs() completes them.
-    // EV_END is recorded BEFORE the copies are enqueued: the stream's last operations were small D2H
-    // copies, so a timed event recorded after the big copies would queue behind them on the copy engine.
-    if (e->async_outputs) {
-        rec(e, EV_END);
-        CU(e, cudaEventSynchronize(e->ev[EV_END]));
-        collect_timings(e);
-        if (total > 0 && keypoints)
-            CU(e, cudaMemcpyAsync(keypoints, e->d_out_kp, sizeof(surf_keypoint) * total, kind, e->copy_stream));
-        if (total > 0 && descriptors && e->pending.want_desc)
-            CU(e, cudaMemcpyAsync(descriptors, e->d_out_desc, sizeof(float) * D * total, kind, e->copy_stream));
-        CU(e, cudaEventRecord(e->ev_copy_done, e->copy_stream));
-        e->copies_in_flight = true;
-        return SURF_OK;
+    // The result copies go to the copy stream (the batch's kernels have ended: ev_ready) so that they neither wait
+    // for nor delay a batch submitted after this one.  Asynchronous-output mode returns without waiting for them:
+    // they overlap the following kernels and surf_wait_outputs() completes them.
+    const bool any = total > 0 && (keypoints || (descriptors && o.want_desc));
+    if (any) {
+        if (keypoints) CU(e, cudaMemcpyAsync(keypoints, o.d_kp, sizeof(surf_keypoint) * total, kind, e->copy_stream));
+        if (descriptors && o.want_desc)
+            CU(e, cudaMemcpyAsync(descriptors, o.d_desc, sizeof(float) * D * total, kind, e->copy_stream));
+        CU(e, cudaEventRecord(o.ev_copy_done, e->copy_stream));
+        o.copies_in_flight = true;
+        if (!e->async_outputs) {
+            CU(e, cudaStreamSynchronize(e->copy_stream));
+            o.copies_in_flight = false;
+        }
     }
-    if (total > 0 && keypoints)
-        CU(e, cudaMemcpyAsync(keypoints, e->d_out_kp, sizeof(surf_keypoint) * total, kind, e->stream));
-    if (total > 0 && descriptors && e->pending.want_desc)
-        CU(e, cudaMemcpyAsync(descriptors, e->d_out_desc, sizeof(float) * D * total, kind, e->stream));
-    rec(e, EV_END);
-    CU(e, cudaStreamSynchronize(e->stream));
-    collect_timings(e);
+    o.active = false;
+    o.collected = true;
+    e->out_collected = s;
+    bind_out(e, bound);
     return SURF_OK;
 }
 
@@ -1040,6 +1120,8 @@ int surf_set_async_outputs(surf_engine *e, int enable)
     int rc = ensure_device(e);
     if (rc) return rc;
     CU(e, cudaStreamSynchronize(e->copy_stream));
+    for (OutSet &o : e->out) o.copies_in_flight = false;
+    e->match_copies_in_flight = false;
     e->async_outputs = enable ? 1 : 0;
     return SURF_OK;
 }
@@ -1050,7 +1132,7 @@ int surf_wait_outputs(surf_engine *e)
     int rc = ensure_device(e);
     if (rc) return rc;
     CU(e, cudaStreamSynchronize(e->copy_stream));
-    e->copies_in_flight = false;
+    for (OutSet &o : e->out) o.copies_in_flight = false;
     e->match_copies_in_flight = false;
     return SURF_OK;
 }
@@ -1059,10 +1141,16 @@ int surf_device_results(surf_engine *e, const surf_keypoint **keypoints, const f
                         const int32_t **offsets)
 {
     if (!e) return SURF_ERR_BAD_ARG;
-    if (!e->pending.active) return fail(e, SURF_ERR_BAD_ARG, "no submitted batch");
-    if (keypoints) *keypoints = e->d_out_kp;
-    if (descriptors) *descriptors = e->pending.want_desc ? e->d_out_desc : nullptr;
-    if (offsets) *offsets = e->d_off_out;
+    // the batch collected last; before any collect, the batch submitted last
+    int s = e->out_collected;
+    if (s < 0) {
+        s = e->out_next ^ 1;
+        if (!e->out[s].active) return fail(e, SURF_ERR_BAD_ARG, "no submitted batch");
+    }
+    const OutSet &o = e->out[s];
+    if (keypoints) *keypoints = o.d_kp;
+    if (descriptors) *descriptors = o.want_desc ? o.d_desc : nullptr;
+    if (offsets) *offsets = o.d_off;
     return SURF_OK;
 }
 
@@ -1112,7 +1200,9 @@ static int describe_given(surf_engine *e, const uint8_t *image, int width, int h
         return fail(e, SURF_ERR_CAPACITY, "%d keypoints given; the engine was created for %d per frame", n, e->cap);
     }
     if ((rc = ensure_device(e))) return rc;
-    e->pending.active = false;
+    drop_batches(e);
+    bind_out(e, e->out_next);
+    e->ev = next_ev_array(e);
     e->launches = 0;
     const FrameGeo geo = make_geo(width, height);
     const int D = e->params.extended ? 128 : 64;
@@ -1150,7 +1240,7 @@ static int describe_given(surf_engine *e, const uint8_t *image, int width, int h
     }
     rec(e, EV_END);
     CU(e, cudaStreamSynchronize(e->stream));
-    collect_timings(e);
+    collect_timings(e, e->ev, e->launches);
     return SURF_OK;
 }
 
@@ -1186,7 +1276,9 @@ int surf_integral(surf_engine *e, const uint8_t *image, int width, int height, s
     if (rc) return rc;
     if (!sum) return fail(e, SURF_ERR_BAD_ARG, "sum is null");
     if ((rc = ensure_device(e))) return rc;
-    e->pending.active = false;
+    drop_batches(e);
+    bind_out(e, e->out_next);
+    e->ev = next_ev_array(e);
     e->launches = 0;
     const FrameGeo geo = make_geo(width, height);
     ImageRef img;
@@ -1209,7 +1301,9 @@ int surf_hessian_layer(surf_engine *e, const uint8_t *image, int width, int heig
     if (!det || octave < 0 || octave >= e->params.n_octaves || layer < 0 || layer >= lpo)
         return fail(e, SURF_ERR_BAD_ARG, "bad octave/layer or null output");
     if ((rc = ensure_device(e))) return rc;
-    e->pending.active = false;
+    drop_batches(e);
+    bind_out(e, e->out_next);
+    e->ev = next_ev_array(e);
     e->launches = 0;
     const FrameGeo geo = make_geo(width, height);
     ImageRef img;
@@ -1236,7 +1330,9 @@ int surf_raw_keypoints(surf_engine *e, const uint8_t *image, int width, int heig
     if (rc) return rc;
     if (!keypoints || !n_out) return fail(e, SURF_ERR_BAD_ARG, "null output");
     if ((rc = ensure_device(e))) return rc;
-    e->pending.active = false;
+    drop_batches(e);
+    bind_out(e, e->out_next);
+    e->ev = next_ev_array(e);
     e->launches = 0;
     const FrameGeo geo = make_geo(width, height);
     rec(e, EV_START);
@@ -1393,19 +1489,19 @@ int surf_device_matches(surf_engine *e, const surf_dmatch **matches, const uint8
 int surf_match_prev(surf_engine *e, float ratio, surf_dmatch *out, uint8_t *good, int out_mem, long capacity)
 {
     if (!e) return SURF_ERR_BAD_ARG;
-    if (!e->pending.active || !e->pending.want_desc)
+    const int s = e->out_collected;
+    if (s < 0 || !e->out[s].collected || !e->out[s].want_desc)
         return fail(e, SURF_ERR_BAD_ARG, "surf_match_prev needs a submitted and collected batch with descriptors");
-    if (e->pending.matched)
-        return fail(e, SURF_ERR_BAD_ARG, "surf_match_prev was already called for this batch");
+    OutSet &o = e->out[s];
+    if (o.matched) return fail(e, SURF_ERR_BAD_ARG, "surf_match_prev was already called for this batch");
     int rc = ensure_device(e);
     if (rc) return rc;
-    const int B = e->pending.batch, D = e->params.extended ? 128 : 64;
-    const long total = e->h_pin[2 * B + B];  // offsets[B] fetched by surf_collect_batch
+    const int B = o.batch, D = e->params.extended ? 128 : 64;
+    const long total = o.h_pin[2 * B + B];  // offsets[B] fetched by surf_collect_batch
     if ((out || good) && total > capacity) {  // nothing launched, stream state untouched: the caller may retry
         e->required = total;
         return fail(e, SURF_ERR_CAPACITY, "%ld keypoints in the batch; the match arrays hold %ld", total, capacity);
     }
-    e->pending.matched = true;
     const int slots = e->max_b + 1, rows = (e->cap + 255) & ~255;
     surf_engine::TcWs &w = e->tc[1];
     if ((rc = tc_reserve(e, w, slots, rows, D))) return rc;
@@ -1417,21 +1513,21 @@ int surf_match_prev(surf_engine *e, float ratio, surf_dmatch *out, uint8_t *good
         CU(e, cudaMalloc(&e->d_stream_matches, nk * 2 * sizeof(surf_dmatch)));
         CU(e, cudaMalloc(&e->d_stream_good, nk));
     }
-    // The matcher runs on its own stream: it only depends on the batch just collected, so the caller can
-    // submit the next batch right away and its kernels overlap the (latency-bound) match kernels.
+    o.matched = true;
+    // The matcher runs on its own stream: it only depends on the batch just collected (whose kernels have ended:
+    // the collect waited for ev_ready), so batches submitted meanwhile overlap the (latency-bound) match kernels.
     cudaStream_t ms = e->match_stream;
-    CU(e, cudaEventRecord(e->ev_batch_done, e->stream));
-    CU(e, cudaStreamWaitEvent(ms, e->ev_batch_done, 0));
+    CU(e, cudaStreamWaitEvent(ms, o.ev_ready, 0));
     if (!e->stream_primed) {  // forget the previous frame: an empty predecessor slot
         launch_zero(w.pool.count + e->tc_prev_slot, 1, ms, nullptr);
         launch_zero(e->d_prev_off, 2, ms, nullptr);
     }
     int launches = 0;
     CU(e, cudaEventRecord(e->ev_match_t0, ms));
-    launch_tc_stream_tables(w.segs, w.probs, B, slots, e->tc_prev_slot, e->d_out_desc, e->d_off_out, e->d_prev_desc,
-                            e->d_prev_off, ms, &launches);
+    launch_tc_stream_tables(w.segs, w.probs, B, slots, e->tc_prev_slot, o.d_desc, o.d_off, e->d_prev_desc, e->d_prev_off, ms,
+                            &launches);
     const int prev = (e->tc_prev_slot + B) % slots;
-    // the previous step's match results may still be on their way to the host
+    // the previous batch's match results (d_stream_matches is one buffer) may still be on their way to the host
     if (e->match_copies_in_flight) CU(e, cudaStreamWaitEvent(ms, e->ev_match_copy_done, 0));
     TcMatchArgs a{};
     a.pool = w.pool; a.segs = w.segs; a.n_segs = B; a.probs = w.probs; a.n_probs = B; a.n_splits = 1;
@@ -1440,10 +1536,10 @@ int surf_match_prev(surf_engine *e, float ratio, surf_dmatch *out, uint8_t *good
     launch_tc_match(a, ms, &launches);
     e->last_tc_ws = 1;
     // keep the last frame (fp32 rows + its slot) as the next batch's predecessor
-    launch_copy_rows(e->d_out_desc, e->d_off_out + B - 1, D, e->d_prev_desc, e->cap, e->d_prev_off, ms, &launches);
+    launch_copy_rows(o.d_desc, o.d_off + B - 1, D, e->d_prev_desc, e->cap, e->d_prev_off, ms, &launches);
     CU(e, cudaEventRecord(e->ev_match_t1, ms));
-    CU(e, cudaEventRecord(e->ev_match_done, ms));
-    e->match_in_flight = true;
+    CU(e, cudaEventRecord(o.ev_match_done, ms));
+    o.match_in_flight = true;
     e->match_launches = launches;
     e->launches = launches;
     e->timings.launches = launches;
@@ -1454,7 +1550,7 @@ int surf_match_prev(surf_engine *e, float ratio, surf_dmatch *out, uint8_t *good
         const cudaMemcpyKind kind = out_mem == SURF_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
         cudaStream_t cs = ms;
         if (e->async_outputs) {  // copy stream waits for the match kernels, the host does not
-            CU(e, cudaStreamWaitEvent(e->copy_stream, e->ev_match_done, 0));
+            CU(e, cudaStreamWaitEvent(e->copy_stream, o.ev_match_done, 0));
             cs = e->copy_stream;
         }
         if (out && total) CU(e, cudaMemcpyAsync(out, e->d_stream_matches, sizeof(surf_dmatch) * 2 * total, kind, cs));

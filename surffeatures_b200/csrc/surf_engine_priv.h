@@ -15,11 +15,23 @@ using namespace surfb200;  // private header of the library's own translation un
 
 enum Ev { EV_START, EV_H2D, EV_INTEGRAL, EV_HESSIAN_NMS, EV_SORT, EV_DESC_START, EV_DESCRIBE, EV_PACK, EV_END, EV_COUNT };
 
-struct Pending {
-    bool active = false;
-    bool matched = false;   // surf_match_prev already ran on this batch
+// Results of one submitted batch.  There are two sets, used alternately, so that surf_submit_batch of batch i+1 may
+// precede surf_collect_batch of batch i: the host then never keeps the GPU waiting for its own wake-up.
+struct OutSet {
+    surf_keypoint *d_kp = nullptr;   // packed keypoints
+    float *d_desc = nullptr;         // packed descriptors [rows][D]
+    int *d_off = nullptr;            // offsets[B + 1]
+    int *h_pin = nullptr;            // pinned: counts[B], ndel[B], off_out[B+1], misc, status
+    cudaEvent_t ev_ready = nullptr;  // this batch's kernels and counter copies have ended (main stream)
+    cudaEvent_t ev_copy_done = nullptr, ev_match_done = nullptr;   // readers of this set: result copies, stream matcher
+    bool copies_in_flight = false, match_in_flight = false;
+    cudaEvent_t *ev = nullptr;       // stage events of the batch (one array of the engine's pool)
+    bool active = false;             // submitted, not yet collected
+    bool collected = false;          // collected: surf_match_prev / surf_device_results refer to it
+    bool matched = false;            // surf_match_prev already ran on this batch
     int batch = 0;
     bool want_desc = false;
+    int launches = 0;
 };
 
 struct surf_engine {
@@ -29,17 +41,23 @@ struct surf_engine {
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;  // device->host result copies in asynchronous-output mode
     cudaStream_t match_stream = nullptr; // surf_match_prev runs here, concurrently with the next batch's kernels
-    cudaEvent_t ev_batch_done = nullptr, ev_match_done = nullptr;
     cudaEvent_t ev_match_t0 = nullptr, ev_match_t1 = nullptr;  // timed: the last surf_match_prev on match_stream
     int match_launches = 0;
     cudaEvent_t marks[SURF_MAX_MARKS]{};                       // surf_mark
-    bool match_in_flight = false;
-    cudaEvent_t ev_copy_done = nullptr, ev_match_copy_done = nullptr, ev_ready = nullptr;
-    bool match_copies_in_flight = false;
     int async_outputs = 0;
-    bool copies_in_flight = false;
-    cudaEvent_t ev[EV_COUNT]{};
+    cudaEvent_t ev_match_copy_done = nullptr;   // the match results (one device buffer) are on their way to the host
+    bool match_copies_in_flight = false;
+    // stage events: a pool of arrays, one per batch in flight (two submitted + one look-ahead at most); `ev` is the
+    // array the launch sequence being enqueued records into
+    static constexpr int kEvSets = 4;
+    cudaEvent_t evpool[kEvSets][EV_COUNT]{};
+    int ev_next = 0;
+    cudaEvent_t *ev = nullptr;
     bool ev_valid = false;
+    OutSet out[2];
+    int out_next = 0;        // set the next surf_submit_batch writes
+    int out_bound = 0;       // set whose buffers d_out_kp / d_out_desc / d_off_out / h_pin currently alias
+    int out_collected = -1;  // set of the batch collected last
 
     // workspace
     uint8_t *d_img = nullptr;   size_t img_pitch = 0;
@@ -75,7 +93,7 @@ struct surf_engine {
     cudaEvent_t ev_set_free = nullptr;   // the current set's ev_free
     bool set_free_recorded = false;
     cudaStream_t la_stream = nullptr;
-    cudaEvent_t la_ev[EV_COUNT]{};       // stage events of the look-ahead (swapped with ev[] while it is recorded / used)
+    cudaEvent_t *la_ev = nullptr;        // stage-event array of the pending look-ahead
     cudaEvent_t ev_detect_done = nullptr, ev_la_done = nullptr;
     bool detect_done_recorded = false;
     struct LookAhead {
@@ -97,7 +115,7 @@ struct surf_engine {
     uint8_t *d_win_scratch = nullptr;
     float2 *d_sincos = nullptr;
     uint8_t *d_patch_ws = nullptr;  // [max_b][cap][kPatchStride]
-    int *h_pin = nullptr;  // pinned: counts[B], ndel[B], off_out[B+1], misc[4]
+    int *h_pin = nullptr;  // alias of out[out_bound].h_pin (as are d_out_kp, d_out_desc, d_off_out)
     surf_dmatch *d_match_part = nullptr;  size_t match_part_cap = 0;
     void *d_match_io = nullptr;           size_t match_io_cap = 0;
     int match_exact_only = 0;
@@ -130,7 +148,6 @@ struct surf_engine {
 
     struct surf_comm *solo = nullptr;  // single-GPU context of surf_sweep_sharded (surf_comm.cu), destroyed with the engine
     surf_keypoint *sorted = nullptr;  // which of d_kp_a / d_kp_b holds the current keypoints
-    Pending pending;
     surf_timings timings{};
     int launches = 0;
     long required = 0;
