@@ -29,6 +29,8 @@ __constant__ float c_ori_x[kOriSamples];  // sample offsets -6..6, kept as float
 __constant__ float c_ori_y[kOriSamples];
 __constant__ float c_ori_w[kOriSamples];
 __constant__ float c_desc_w[400];
+// 1.0f twice, opaque to ptxas (see tap_fixed2)
+__constant__ float2 c_one2 = {1.f, 1.f};
 
 static void gaussian_taps(int n, double sigma, float *out)
 {
@@ -420,6 +422,69 @@ __device__ __forceinline__ uint32_t tap_fixed(long long X, long long Y)
     return __float_as_uint(__fmaf_rn(t, 5.421010862427522e-20f, 12582912.0f));  // low byte = cvRound(value)
 }
 
+// ---- two taps per thread on Blackwell's packed fp32 pipe (FMUL2 / FADD2 / FFMA2: mul / add / fma.rn.f32x2) ----
+// Each lane of a packed operation is the IEEE single operation, so the results are those of tap_fixed bit for bit;
+// 14 packed instructions replace 28 scalar ones per pair of taps.  One catch, measured on ptxas 12.9: a
+// mul.rn.f32x2 feeding an add.rn.f32x2 is contracted into FFMA2 even under --fmad=false (the scalar forms are
+// not).  The sums are therefore written as fma(x, 1, y) with the two ones read from constant memory: that is
+// round(x + y) exactly, it already is a fused multiply-add (nothing left to contract) and ptxas cannot fold a
+// multiplier it does not know.
+#ifndef SURF_TAP_F32X2
+#define SURF_TAP_F32X2 1
+#endif
+__device__ __forceinline__ uint64_t f2_pack(float lo, float hi)
+{
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void f2_unpack(uint64_t v, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ uint64_t f2_mul(uint64_t a, uint64_t b)
+{
+    uint64_t r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ uint64_t f2_sub(uint64_t a, uint64_t b)
+{
+    uint64_t r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ uint64_t f2_fma(uint64_t a, uint64_t b, uint64_t c)
+{
+    uint64_t r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+
+// Two interior taps at once (same contract as tap_fixed for each of them).  `one` = (1.0f, 1.0f) from c_one2.
+template <int TP>
+__device__ __forceinline__ void tap_fixed2(long long X0, long long Y0, long long X1, long long Y1, uint64_t one, uint32_t &v0,
+                                           uint32_t &v1)
+{
+    const uint64_t a = f2_pack(__uint2float_rn((uint32_t)X0), __uint2float_rn((uint32_t)X1));  // fractions * 2^32
+    const uint64_t b = f2_pack(__uint2float_rn((uint32_t)Y0), __uint2float_rn((uint32_t)Y1));
+    const uint64_t c32 = f2_pack(4294967296.f, 4294967296.f);
+    const uint64_t na = f2_sub(c32, a), nb = f2_sub(c32, b);
+    const uint32_t q0 = (uint32_t)((int)(Y0 >> 32) * TP + (int)(X0 >> 32));
+    const uint32_t q1 = (uint32_t)((int)(Y1 >> 32) * TP + (int)(X1 >> 32));
+    const uint64_t p00 = f2_pack(tap_u8f(lds_u8<0>(q0)), tap_u8f(lds_u8<0>(q1)));
+    const uint64_t p01 = f2_pack(tap_u8f(lds_u8<1>(q0)), tap_u8f(lds_u8<1>(q1)));
+    const uint64_t p10 = f2_pack(tap_u8f(lds_u8<TP>(q0)), tap_u8f(lds_u8<TP>(q1)));
+    const uint64_t p11 = f2_pack(tap_u8f(lds_u8<TP + 1>(q0)), tap_u8f(lds_u8<TP + 1>(q1)));
+    // p00 * na * nb + p01 * a * nb + p10 * na * b + p11 * a * b, left to right, every product and sum rounded
+    uint64_t t = f2_mul(f2_mul(p00, na), nb);
+    t = f2_fma(t, one, f2_mul(f2_mul(p01, a), nb));
+    t = f2_fma(t, one, f2_mul(f2_mul(p10, na), b));
+    t = f2_fma(t, one, f2_mul(f2_mul(p11, a), b));                                             // value * 2^64
+    t = f2_fma(t, f2_pack(5.421010862427522e-20f, 5.421010862427522e-20f), f2_pack(12582912.0f, 12582912.0f));
+    float r0, r1;
+    f2_unpack(t, r0, r1);
+    v0 = __float_as_uint(r0);  // low byte = cvRound(value)
+    v1 = __float_as_uint(r1);
+}
+
 // Tap of a window that may leave the interpolable area: X, Y are the true coordinates.
 template <int TP>
 __device__ __forceinline__ uint32_t tap_fixed_checked(long long X, long long Y, int W1, int H1, int x0, int y0, uint32_t tile)
@@ -457,6 +522,9 @@ __device__ __forceinline__ void window_taps_fixed(int n, int i0, int i1, int j0,
     const long long ybias = CHECK ? 0ll : ((long long)(-y0)) << 32;
     const long long lane_x = (long long)(j0 + lj) * cdq + xbias, lane_y = (long long)(j0 + lj) * sdq - ybias;
     const int W1 = W - 1, H1 = H - 1;
+#if SURF_TAP_F32X2
+    const uint64_t one2 = f2_pack(c_one2.x, c_one2.y);
+#endif
     for (int i = i0 + warp * 4 + li; i < i1; i += NW * 4) {
         long long X = fix32(rsx[i]) + lane_x, Y = fix32(rsy[i]) - lane_y;
         int j = j0 + lj;
@@ -467,8 +535,12 @@ __device__ __forceinline__ void window_taps_fixed(int n, int i0, int i1, int j0,
                 v0 = tap_fixed_checked<TP>(X, Y, W1, H1, x0, y0, tile);
                 v1 = tap_fixed_checked<TP>(X + sx8, Y - sy8, W1, H1, x0, y0, tile);
             } else {
+#if SURF_TAP_F32X2
+                tap_fixed2<TP>(X, Y, X + sx8, Y - sy8, one2, v0, v1);
+#else
                 v0 = tap_fixed<TP>(X, Y);
                 v1 = tap_fixed<TP>(X + sx8, Y - sy8);
+#endif
             }
             if (GLOBAL) {
                 win_g[o + j] = (unsigned char)v0;
