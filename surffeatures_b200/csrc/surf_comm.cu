@@ -304,6 +304,7 @@ int surf_sweep_sharded(surf_engine *e, surf_comm *comm, const uint8_t *images_lo
                        long capacity, int64_t *offsets, surf_sweep_stats *stats)
 {
     if (!e) return SURF_ERR_BAD_ARG;
+    NvtxRange nvtx("surf_sweep_sharded");
     if (comm && comm->e != e) return fail(e, SURF_ERR_BAD_ARG, "the communicator belongs to another engine");
     int rc = ensure_device(e);
     if (rc) return rc;
@@ -527,6 +528,7 @@ int surf_db_knn_sharded(surf_db *db, surf_comm *c, const float *query, int n_que
                         int mem)
 {
     if (!db) return SURF_ERR_BAD_ARG;
+    NvtxRange nvtx("surf_db_knn_sharded");
     surf_engine *e = db->e;
     if (!c) return surf_db_knn(db, query, n_query, k, out, mem);  // one GPU: the whole database is local
     if (c->e != e) return fail(e, SURF_ERR_BAD_ARG, "database and communicator belong to different engines");

@@ -308,7 +308,6 @@ struct AreaTab {  // one destination cell of the INTER_AREA table (same for x an
 
 struct DescShared {  // static shared state of one descriptor CTA
     AreaTab tab;
-    __align__(4) unsigned char patch[kPatchPx + 3];
     int next;     // the following queue item, fetched while the current keypoint is tapped
     struct Geo {  // window geometry of the current keypoint: written by warp 0 (isc / int_scale by the last warp)
         int n, b, ux0, uy0, tx0a, ty0, interior, bad, isc, int_scale;
@@ -574,7 +573,8 @@ __device__ __forceinline__ void cell_weights(const AreaTab &t, int d, float (&w)
 // the resize table touches more than MAXC source pixels; MAXC == 0: any window (global scratch), generic loops.
 template <int THREADS, int MAXC>
 __device__ __forceinline__ void descriptor_tail(const DescribeArgs &A, int kidx, int n, const unsigned char *win, float *buf,
-                                                uint32_t win_addr, uint32_t buf_addr, DescShared &S, bool int_scale, int isc)
+                                                uint32_t win_addr, uint32_t buf_addr, DescShared &S, bool int_scale, int isc,
+                                                unsigned char *patch)
 {
     const int tid = threadIdx.x;
     // Fractional scales run the reference's two passes: row sums buf[sy][dx] = sum_x win[sy][x] * alpha (fp32,
@@ -591,6 +591,29 @@ __device__ __forceinline__ void descriptor_tail(const DescribeArgs &A, int kidx,
             cell_weights<M>(S.tab, dx, w);
             uint32_t ra = win_addr + g * n + S.tab.start[dx], ba = buf_addr + (g * kPatch + dx) * 4;
             const uint32_t rstep = G * n;
+#if SURF_TAP_F32X2
+            // Two source rows per iteration on the packed fp32 pipe: lane 0 of every pair is row sy, lane 1 row sy + G.
+            // `b += p * w` is a rounded product and a rounded sum in the reference: FMUL2, then the sum as
+            // fma(b, 1, product) (see tap_fixed2 for why the one comes from constant memory).
+            const uint64_t one2 = f2_pack(c_one2.x, c_one2.y);
+            uint64_t w2[M];
+#pragma unroll
+            for (int k = 0; k < M; k++) w2[k] = f2_pack(w[k], w[k]);
+            for (int sy = g; sy < n; sy += 2 * G, ra += 2 * rstep, ba += 2 * G * kPatch * 4) {
+                const bool has_b = sy + G < n;
+                const uint32_t rb = has_b ? ra + rstep : ra;   // no second row: the first one twice, result dropped
+                uint64_t b2 = f2_mul(f2_pack(tap_u8f(lds_u8<0>(ra)), tap_u8f(lds_u8<0>(rb))), w2[0]);
+#define SURF_ROW_STEP(K)                                                                                              \
+    if (M > K) b2 = f2_fma(b2, one2, f2_mul(f2_pack(tap_u8f(lds_u8<K % M>(ra)), tap_u8f(lds_u8<K % M>(rb))), w2[K % M]));
+                SURF_ROW_STEP(1) SURF_ROW_STEP(2) SURF_ROW_STEP(3) SURF_ROW_STEP(4) SURF_ROW_STEP(5) SURF_ROW_STEP(6) SURF_ROW_STEP(7)
+#undef SURF_ROW_STEP
+                static_assert(M <= 8, "extend the unrolled row pass");
+                float ba_v, bb_v;
+                f2_unpack(b2, ba_v, bb_v);
+                sts_f32(ba, ba_v);
+                if (has_b) sts_f32(ba + G * kPatch * 4, bb_v);
+            }
+#else
 #pragma unroll 2
             for (int sy = g; sy < n; sy += G, ra += rstep, ba += G * kPatch * 4) {
                 float b = tap_u8f(lds_u8<0>(ra)) * w[0];
@@ -604,6 +627,7 @@ __device__ __forceinline__ void descriptor_tail(const DescribeArgs &A, int kidx,
                 static_assert(M <= 8, "extend the unrolled row pass");
                 sts_f32(ba, b);
             }
+#endif
         }
         __syncthreads();
     } else if (!int_scale) {
@@ -667,87 +691,86 @@ __device__ __forceinline__ void descriptor_tail(const DescribeArgs &A, int kidx,
             }
             outv = sat_u8(acc);
         }
-        S.patch[p] = (unsigned char)outv;
+        patch[p] = (unsigned char)outv;
     }
-    __syncthreads();
+    __syncthreads();  // the patch (a slot of the CTA's ring) is complete
     if (A.patches) {
         unsigned char *po = A.patches + (size_t)kidx * kPatchPx;
-        for (int p = tid; p < kPatchPx; p += THREADS) po[p] = S.patch[p];
+        for (int p = tid; p < kPatchPx; p += THREADS) po[p] = patch[p];
     }
-    if (!A.desc) return;
-    // the patch goes to the workspace slot of this keypoint (16-byte aligned); k_patch_descriptor finishes it
-    uint32_t *pw = reinterpret_cast<uint32_t *>(A.patch_ws + (size_t)kidx * kPatchStride);
-    const uint32_t *ps = reinterpret_cast<const uint32_t *>(S.patch);
-    for (int t = tid; t < (kPatchPx + 3) / 4; t += THREADS) pw[t] = ps[t];
 }
 
 // ------------------------------------------------------------------------------------------------
-// K4c: from the 21 x 21 patch to the descriptor.  One warp per keypoint of a size class's work list, no block
-// barriers: lane = (sub-region, dx-or-dy half).  Every output component is one sequential fp32 sum over the
-// sub-region's 5 x 5 samples in (y, x) order, as the reference accumulates it.
+// K4c: from the 21 x 21 patch to the descriptor, inside the window kernels.  A CTA parks the patches of its last
+// kRing keypoints in shared memory; when the ring is full every warp finishes one (or two) of them, one warp per
+// keypoint, no block barrier inside: lane = (sub-region, dx-or-dy half).  Every output component is one
+// sequential fp32 sum over the sub-region's 5 x 5 samples in (y, x) order, as the reference accumulates it.
 //   64-d : half 0 -> sum dx, sum |dx| (components 0, 2 of the region); half 1 -> sum dy, sum |dy| (1, 3)
 //   128-d: half 0 -> dx and |dx| split by the sign of dy (0..3);       half 1 -> dy and |dy| split by the sign of dx (4..7)
+// (Round 1 wrote the patches to a global workspace and finished them in a second kernel: 122 MB per 64-frame
+// batch written and read back, and four more launches.  Finishing them in batches keeps every warp of the CTA busy
+// at the same time, which finishing each keypoint's 25-step chains right after its window did not.)
 // ------------------------------------------------------------------------------------------------
-constexpr int kPdWarps = 8;
+constexpr int kRing = 8;
 
-__global__ void __launch_bounds__(kPdWarps * 32) k_patch_descriptor(const __grid_constant__ DescribeArgs A, int cls)
+__device__ __forceinline__ void patch_descriptor_warp(const DescribeArgs &A, const unsigned char *P, int kidx, const float *s_w)
 {
-    __shared__ __align__(16) unsigned char s_patch[kPdWarps][kPatchStride];
-    __shared__ float s_w[400];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int t = threadIdx.x; t < 400; t += kPdWarps * 32) s_w[t] = c_desc_w[t];
-    __syncthreads();
-    const int count = A.misc[kMiscClassCount + cls];
-    const int *list = A.class_list + (size_t)cls * A.list_stride;
+    const int lane = threadIdx.x & 31;
     const int region = lane >> 1, half = lane & 1;
     const int y0 = (region >> 2) * 5, x0 = (region & 3) * 5;
-    unsigned char *P = s_patch[warp];
-    for (int w = blockIdx.x * kPdWarps + warp; w < count; w += gridDim.x * kPdWarps) {
-        const int kidx = list[w];
-        const uint4 *src = reinterpret_cast<const uint4 *>(A.patch_ws + (size_t)kidx * kPatchStride);
-        if (lane < kPatchStride / 16) reinterpret_cast<uint4 *>(P)[lane] = src[lane];
-        __syncwarp();
-        float a0 = 0, a1 = 0, a2 = 0, a3 = 0;
-        for (int y = y0; y < y0 + 5; y++) {
-            const unsigned char *r0 = P + y * kPatch + x0, *r1 = r0 + kPatch;
-            int p00 = r0[0], p10 = r1[0];
+    float a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+    for (int y = y0; y < y0 + 5; y++) {
+        const unsigned char *r0 = P + y * kPatch + x0, *r1 = r0 + kPatch;
+        int p00 = r0[0], p10 = r1[0];
 #pragma unroll
-            for (int x = 0; x < 5; x++) {
-                const int p01 = r0[x + 1], p11 = r1[x + 1];
-                const float wgt = s_w[y * 20 + x0 + x];
-                const float tx = (p01 - p00 + p11 - p10) * wgt, ty = (p10 - p00 + p11 - p01) * wgt;
-                const float u = half ? ty : tx, o = half ? tx : ty;
-                if (A.extended) {
-                    if (o >= 0) {
-                        a0 += u;
-                        a1 += fabsf(u);
-                    } else {
-                        a2 += u;
-                        a3 += fabsf(u);
-                    }
-                } else {
+        for (int x = 0; x < 5; x++) {
+            const int p01 = r0[x + 1], p11 = r1[x + 1];
+            const float wgt = s_w[y * 20 + x0 + x];
+            const float tx = (p01 - p00 + p11 - p10) * wgt, ty = (p10 - p00 + p11 - p01) * wgt;
+            const float u = half ? ty : tx, o = half ? tx : ty;
+            if (A.extended) {
+                if (o >= 0) {
                     a0 += u;
                     a1 += fabsf(u);
+                } else {
+                    a2 += u;
+                    a3 += fabsf(u);
                 }
-                p00 = p01;
-                p10 = p11;
+            } else {
+                a0 += u;
+                a1 += fabsf(u);
             }
+            p00 = p01;
+            p10 = p11;
         }
-        double mag = (double)(a0 * a0) + (double)(a1 * a1);
-        if (A.extended) mag += (double)(a2 * a2) + (double)(a3 * a3);
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) mag += __shfl_xor_sync(FULL_MASK, mag, d);
-        const float scale = (float)(1. / (sqrt(mag) + DBL_EPSILON));
-        if (A.extended) {
-            float4 *vo = reinterpret_cast<float4 *>(A.desc + (size_t)kidx * 128 + region * 8 + half * 4);
-            *vo = make_float4(a0 * scale, a1 * scale, a2 * scale, a3 * scale);
-        } else {
-            float *vo = A.desc + (size_t)kidx * 64 + region * 4 + half;
-            vo[0] = a0 * scale;
-            vo[2] = a1 * scale;
-        }
-        __syncwarp();  // the next keypoint overwrites the patch
     }
+    double mag = (double)(a0 * a0) + (double)(a1 * a1);
+    if (A.extended) mag += (double)(a2 * a2) + (double)(a3 * a3);
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) mag += __shfl_xor_sync(FULL_MASK, mag, d);
+    const float scale = (float)(1. / (sqrt(mag) + DBL_EPSILON));
+    if (A.extended) {
+        float4 *vo = reinterpret_cast<float4 *>(A.desc + (size_t)kidx * 128 + region * 8 + half * 4);
+        *vo = make_float4(a0 * scale, a1 * scale, a2 * scale, a3 * scale);
+    } else {
+        float *vo = A.desc + (size_t)kidx * 64 + region * 4 + half;
+        vo[0] = a0 * scale;
+        vo[2] = a1 * scale;
+    }
+}
+
+struct PatchRing {
+    __align__(16) unsigned char patch[kRing][kPatchStride];
+    int kidx[kRing];
+    float w[400];  // Gaussian weights of the 20 x 20 gradient samples (divergent index: shared, not constant memory)
+};
+
+// Every warp finishes the ring entries warp, warp + NW, ...  The caller guarantees the entries are visible (a block
+// barrier lies between the last patch write and this call).
+template <int NW>
+__device__ __forceinline__ void ring_flush(const DescribeArgs &A, const PatchRing &R, int pending)
+{
+    for (int w = threadIdx.x >> 5; w < pending; w += NW) patch_descriptor_warp(A, R.patch[w], R.kidx[w], R.w);
 }
 
 // Per-class compile-time geometry.  The image tile of a class has a FIXED pitch and row count (the largest
@@ -822,7 +845,9 @@ __global__ void __launch_bounds__(ClassT<CLS>::threads) k_descriptor(const __gri
     const uint32_t tile_addr = pin_reg(smem_u32(s_tile)), win_addr = pin_reg(smem_u32(s_win));
     __shared__ __align__(8) uint64_t s_bar;
     __shared__ DescShared S;
+    __shared__ PatchRing ring;
     uint32_t tma_phase = 0;
+    int pending = 0;  // patches parked in the ring (uniform across the CTA)
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int W = A.geo.W, H = A.geo.H;
@@ -835,6 +860,7 @@ __global__ void __launch_bounds__(ClassT<CLS>::threads) k_descriptor(const __gri
         mbar_init_fence();
         S.next = atomicAdd(A.misc + kMiscClassHead + CLS, 1);
     }
+    for (int t = tid; t < 400; t += THREADS) ring.w[t] = c_desc_w[t];
 
     for (;;) {
         __syncthreads();  // everyone is done with the previous keypoint's shared state; S.next is visible
@@ -991,8 +1017,15 @@ __global__ void __launch_bounds__(ClassT<CLS>::threads) k_descriptor(const __gri
         if (tid == THREADS - 32) S.next = next_item;
         __syncthreads();
         // the image tile is no longer needed: its space holds the row sums of the resize
-        descriptor_tail<THREADS, CT::max_cell>(A, kidx, n, s_win, reinterpret_cast<float *>(s_tile), win_addr, tile_addr, S, int_scale, isc);
+        if (tid == 0) ring.kidx[pending] = kidx;
+        descriptor_tail<THREADS, CT::max_cell>(A, kidx, n, s_win, reinterpret_cast<float *>(s_tile), win_addr, tile_addr, S, int_scale, isc,
+                                               ring.patch[pending]);
+        if (A.desc && ++pending == kRing) {  // (the tail ended with a block barrier: the ring is visible)
+            ring_flush<NW>(A, ring, pending);
+            pending = 0;
+        }
     }
+    ring_flush<NW>(A, ring, pending);  // the loop left through its barrier
 }
 
 __global__ void __launch_bounds__(BigT::threads) k_descriptor_big(const __grid_constant__ DescribeArgs A,
@@ -1009,6 +1042,8 @@ __global__ void __launch_bounds__(BigT::threads) k_descriptor_big(const __grid_c
     const uint32_t tile0_addr = pin_reg(smem_u32(s_tile0));
     __shared__ __align__(8) uint64_t s_bar[2];
     __shared__ DescShared S;
+    __shared__ PatchRing ring;
+    int pending = 0;
     __shared__ int4 s_sub[(kMaxWindow / kSubSide) * (kMaxWindow / kSubSide)];  // per sub-window: tile origin x, y, flags
     uint32_t phase[2] = {0, 0};
 
@@ -1027,6 +1062,7 @@ __global__ void __launch_bounds__(BigT::threads) k_descriptor_big(const __grid_c
         mbar_init_fence();
         S.next = atomicAdd(A.misc + kMiscClassHead + CLS, 1);
     }
+    for (int t = tid; t < 400; t += THREADS) ring.w[t] = c_desc_w[t];
 
     for (;;) {
         __syncthreads();  // S.next is visible
@@ -1177,8 +1213,14 @@ __global__ void __launch_bounds__(BigT::threads) k_descriptor_big(const __grid_c
         }
         if (bad && tid == 0) atomicOr(A.misc + kMiscStatus, 2);
         if (tid == THREADS - 32) S.next = next_item;
-        descriptor_tail<THREADS, 0>(A, kidx, n, g_win, g_buf, 0, 0, S, int_scale, isc);
+        if (tid == 0) ring.kidx[pending] = kidx;
+        descriptor_tail<THREADS, 0>(A, kidx, n, g_win, g_buf, 0, 0, S, int_scale, isc, ring.patch[pending]);
+        if (A.desc && ++pending == kRing) {
+            ring_flush<NW>(A, ring, pending);
+            pending = 0;
+        }
     }
+    ring_flush<NW>(A, ring, pending);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1192,7 +1234,7 @@ struct ClassCfg {
 
 struct DevCfg {
     bool ready = false;
-    int ori_grid = 0, pd_grid = 0;
+    int ori_grid = 0;
     ClassCfg cls[kNumClasses];
     cudaStream_t side[kNumClasses - 1];
     cudaEvent_t fork, join[kNumClasses - 1];
@@ -1233,7 +1275,6 @@ DevCfg &dev_cfg()
         int per_sm = 4;
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_orient, kOriWarps * 32, 0);
         c.ori_grid = sms * (per_sm < 1 ? 1 : per_sm);
-        c.pd_grid = sms * 4;
         setup_class<0>(c.cls[0], sms);
         setup_class<1>(c.cls[1], sms);
         setup_class<2>(c.cls[2], sms);
@@ -1271,21 +1312,16 @@ void launch_describe(const DescribeArgs &a, const CUtensorMap *imaps, int use_tm
     // tails of the short launches overlap the long ones; join back on `st`.
     cudaEventRecord(c.fork, st);
     for (int k = 0; k < kNumClasses - 1; k++) cudaStreamWaitEvent(c.side[k], c.fork, 0);
-    // each class: windows -> 21 x 21 patches, then (same stream) patches -> descriptors, one warp per keypoint
-    const int pd_grid = c.pd_grid;
+    // each class: windows -> 21 x 21 patches -> descriptors, in one kernel
     k_descriptor_big<<<c.cls[3].grid, BigT::threads, c.cls[3].smem, st>>>(a, imaps[3], use_tma);
-    if (a.desc) k_patch_descriptor<<<pd_grid / 4, kPdWarps * 32, 0, st>>>(a, 3);
     k_descriptor<1><<<c.cls[1].grid, ClassT<1>::threads, c.cls[1].smem, c.side[0]>>>(a, imaps[1], use_tma);
-    if (a.desc) k_patch_descriptor<<<pd_grid, kPdWarps * 32, 0, c.side[0]>>>(a, 1);
     k_descriptor<2><<<c.cls[2].grid, ClassT<2>::threads, c.cls[2].smem, c.side[1]>>>(a, imaps[2], use_tma);
-    if (a.desc) k_patch_descriptor<<<pd_grid / 2, kPdWarps * 32, 0, c.side[1]>>>(a, 2);
     k_descriptor<0><<<c.cls[0].grid, ClassT<0>::threads, c.cls[0].smem, c.side[2]>>>(a, imaps[0], use_tma);
-    if (a.desc) k_patch_descriptor<<<pd_grid, kPdWarps * 32, 0, c.side[2]>>>(a, 0);
     for (int k = 0; k < kNumClasses - 1; k++) {
         cudaEventRecord(c.join[k], c.side[k]);
         cudaStreamWaitEvent(st, c.join[k], 0);
     }
-    *launches += a.desc ? 8 : 4;
+    *launches += 4;
 }
 
 }  // namespace surfb200

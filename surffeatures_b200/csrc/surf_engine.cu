@@ -358,7 +358,7 @@ void free_workspace(surf_engine *e)
         o.d_kp = nullptr; o.d_desc = nullptr; o.d_off = nullptr; o.h_pin = nullptr;
         o.active = o.collected = false;
     }
-    cudaFree(e->d_match_part); cudaFree(e->d_match_io); cudaFree(e->d_class_list); cudaFree(e->d_win_scratch); cudaFree(e->d_sincos); cudaFree(e->d_patch_ws);
+    cudaFree(e->d_match_part); cudaFree(e->d_match_io); cudaFree(e->d_class_list); cudaFree(e->d_win_scratch); cudaFree(e->d_sincos);
     for (auto &w : e->tc) {
         cudaFree(w.pool.hi); cudaFree(w.pool.lo); cudaFree(w.pool.norm); cudaFree(w.pool.max_norm);
         cudaFree(w.pool.count); cudaFree(w.cand); cudaFree(w.redo); cudaFree(w.counters); cudaFree(w.segs);
@@ -375,7 +375,7 @@ void free_workspace(surf_engine *e)
     e->d_kp_a = e->d_kp_b = e->d_out_kp = nullptr; e->d_desc = e->d_out_desc = nullptr; e->d_patches = nullptr;
     e->d_counts = e->d_ndel = e->d_off_in = e->d_off_out = e->d_misc = e->d_deleted = nullptr;
     e->d_match_part = nullptr; e->d_match_io = nullptr; e->h_pin = nullptr; e->d_class_list = nullptr;
-    e->d_win_scratch = nullptr; e->d_sincos = nullptr; e->d_patch_ws = nullptr;
+    e->d_win_scratch = nullptr; e->d_sincos = nullptr;
     e->match_part_cap = e->match_io_cap = 0;
 }
 
@@ -434,7 +434,6 @@ int alloc_workspace(surf_engine *e)
     CU(e, cudaMalloc(&e->d_class_list, nk * kNumClasses * sizeof(int)));
     CU(e, cudaMalloc(&e->d_win_scratch, describe_scratch_bytes()));
     CU(e, cudaMalloc(&e->d_sincos, nk * sizeof(float2)));
-    CU(e, cudaMalloc(&e->d_patch_ws, nk * (size_t)kPatchStride));
     int rc = alloc_det_and_desc(e);
     bind_out(e, 0);
     return rc;
@@ -579,6 +578,7 @@ void rec(surf_engine *e, Ev which) { cudaEventRecord(e->ev[which], e->stream); }
 // integral -> Hessian pyramid -> maxima -> sort.  Leaves sorted raw keypoints in e->sorted.
 int run_detect(surf_engine *e, const ImageRef &img, const uint32_t *msum, const FrameGeo &geo, int B)
 {
+    NvtxRange nvtx("surf:stages1-3 integral+hessian+maxima+sort");
     const surf_params &p = e->params;
     launch_zero(e->d_counts, B + 1, e->stream, &e->launches);  // per-frame counters + status word
     launch_integral(img, B, geo, e->d_sum, e->d_bandsum, 0, e->stream, &e->launches);
@@ -614,6 +614,7 @@ int run_detect(surf_engine *e, const ImageRef &img, const uint32_t *msum, const 
 int run_describe_pack(surf_engine *e, const ImageRef &img, const FrameGeo &geo, int B, bool want_desc,
                       uint8_t *patches, bool pack)
 {
+    NvtxRange nvtx("surf:stage4 orientation+descriptor+pack");
     const surf_params &p = e->params;
     rec(e, EV_DESC_START);
     launch_zero(e->d_ndel, B, e->stream, &e->launches);
@@ -629,7 +630,6 @@ int run_describe_pack(surf_engine *e, const ImageRef &img, const FrameGeo &geo, 
     a.B = B;
     a.desc = want_desc ? e->d_desc : nullptr;
     a.patches = patches;
-    a.patch_ws = e->d_patch_ws;
     a.extended = p.extended;
     a.upright = p.upright;
     a.img_aligned4 = ((reinterpret_cast<uintptr_t>(img.ptr) | img.pitch | img.frame_stride) & 3) == 0;
@@ -902,6 +902,7 @@ int surf_sync(surf_engine *e)
 int surf_submit_batch(surf_engine *e, const uint8_t *images, int in_mem, int batch, int width, int height, size_t pitch,
                       size_t frame_stride, const uint8_t *mask, size_t mask_pitch, int want_descriptors)
 {
+    NvtxRange nvtx("surf_submit_batch");
     BatchIn in{images, in_mem, batch, width, height, pitch, frame_stride, mask, mask_pitch};
     int rc = check_frame_args(e, in);
     if (rc) return rc;
@@ -987,6 +988,7 @@ int surf_prefetch_batch(surf_engine *e, const uint8_t *images, int batch, int wi
 int surf_lookahead_batch(surf_engine *e, const uint8_t *images, int in_mem, int batch, int width, int height, size_t pitch,
                          size_t frame_stride, const uint8_t *mask, size_t mask_pitch)
 {
+    NvtxRange nvtx("surf_lookahead_batch");
     BatchIn in{images, in_mem, batch, width, height, pitch, frame_stride, mask, mask_pitch};
     int rc = check_frame_args(e, in);
     if (rc) return rc;
@@ -1060,6 +1062,7 @@ int surf_collect_batch(surf_engine *e, surf_keypoint *keypoints, float *descript
                        int32_t *offsets)
 {
     if (!e) return SURF_ERR_BAD_ARG;
+    NvtxRange nvtx("surf_collect_batch");
     // the OLDEST submitted batch: with two in flight that is the one the next submit would overwrite
     int s = e->out_next;
     if (!e->out[s].active) s ^= 1;
@@ -1489,6 +1492,7 @@ int surf_device_matches(surf_engine *e, const surf_dmatch **matches, const uint8
 int surf_match_prev(surf_engine *e, float ratio, surf_dmatch *out, uint8_t *good, int out_mem, long capacity)
 {
     if (!e) return SURF_ERR_BAD_ARG;
+    NvtxRange nvtx("surf_match_prev (stage 5)");
     const int s = e->out_collected;
     if (s < 0 || !e->out[s].collected || !e->out[s].want_desc)
         return fail(e, SURF_ERR_BAD_ARG, "surf_match_prev needs a submitted and collected batch with descriptors");

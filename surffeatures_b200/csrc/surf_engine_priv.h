@@ -8,8 +8,17 @@
 #include <vector>
 
 #include <cuda.h>
+#include <nvtx3/nvToolsExt.h>   // header-only NVTX v3: ranges show up in Nsight Systems / ncu --nvtx, cost nothing otherwise
 
 #include "surf_internal.h"
+
+// Host-side NVTX range around a phase of the C ABI (tracing).
+struct NvtxRange {
+    explicit NvtxRange(const char *name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+    NvtxRange(const NvtxRange &) = delete;
+    NvtxRange &operator=(const NvtxRange &) = delete;
+};
 
 using namespace surfb200;  // private header of the library's own translation units
 
@@ -114,7 +123,6 @@ struct surf_engine {
     int *d_deleted = nullptr, *d_class_list = nullptr;
     uint8_t *d_win_scratch = nullptr;
     float2 *d_sincos = nullptr;
-    uint8_t *d_patch_ws = nullptr;  // [max_b][cap][kPatchStride]
     int *h_pin = nullptr;  // alias of out[out_bound].h_pin (as are d_out_kp, d_out_desc, d_off_out)
     surf_dmatch *d_match_part = nullptr;  size_t match_part_cap = 0;
     void *d_match_io = nullptr;           size_t match_io_cap = 0;

@@ -13,7 +13,7 @@ constexpr int kMaxLayersPerOctave = 8;  // nOctaveLayers + 2 <= 8
 constexpr int kMaxOctaves = 8;
 constexpr int kPatch = 21;              // PATCH_SZ + 1 (OpenCV nonfree/surf.cpp)
 constexpr int kPatchPx = kPatch * kPatch;
-constexpr int kPatchStride = 448;        // patch workspace slot (441 bytes, rounded up to 16)
+constexpr int kPatchStride = 448;        // a 21 x 21 patch in a descriptor CTA's shared-memory ring (441 bytes, rounded up to 16)
 constexpr int kOriSamples = 113;        // integer points with i^2 + j^2 <= 36
 constexpr int kOriWindows = 72;         // 0, 5, ..., 355 degrees
 constexpr int kMaxWindow = 768;         // largest descriptor window side handled (size 264 -> 739)
@@ -104,7 +104,6 @@ struct DescribeArgs {
     int B;
     float *desc;          // [B][cap][D] or nullptr (orientation only)
     uint8_t *patches;     // optional [B][cap][441]
-    uint8_t *patch_ws;    // [B][cap][kPatchStride]: 21 x 21 patches between the window kernels and k_patch_descriptor
     int extended, upright;
     int *misc;            // status word, class counters and queue heads (kMisc*)
     int *ndeleted;        // [B]
