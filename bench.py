@@ -247,6 +247,43 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------
+def _parse_cpulist(txt: str):
+    cpus = []
+    for part in txt.strip().split(","):
+        if not part:
+            continue
+        a, _, b = part.partition("-")
+        cpus.extend(range(int(a), int(b or a) + 1))
+    return cpus
+
+
+def bind_rank_to_gpu_numa(torch, local: int, world: int):
+    """One process per GPU on a shared host: give every rank a private slice of the cores of its GPU's NUMA node, before
+    any pinned buffer is allocated (first touch decides where the pages live).  Returns a note for the JSON line."""
+    if world == 1:
+        return "single process: affinity left alone"
+    try:
+        props = torch.cuda.get_device_properties(local)
+        bdf = f"{props.pci_domain_id:04x}:{props.pci_bus_id:02x}:{props.pci_device_id:02x}.0"
+        node_cpus = _parse_cpulist(open(f"/sys/bus/pci/devices/{bdf}/local_cpulist").read())
+        allowed = sorted(set(node_cpus) & set(os.sched_getaffinity(0))) or sorted(os.sched_getaffinity(0))
+        # ranks whose GPUs share this CPU list split it evenly (rank order = local rank order)
+        n_local = int(os.environ.get("LOCAL_WORLD_SIZE", world))
+        sharing = []
+        for r in range(n_local):
+            pr = torch.cuda.get_device_properties(r)
+            f = f"/sys/bus/pci/devices/{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0/local_cpulist"
+            if _parse_cpulist(open(f).read()) == node_cpus:
+                sharing.append(r)
+        k, n = sharing.index(local), len(sharing)
+        per = max(1, len(allowed) // n)
+        mine = allowed[k * per:(k + 1) * per] or allowed
+        os.sched_setaffinity(0, mine)
+        return f"rank bound to cpus {mine[0]}-{mine[-1]} ({len(mine)} of the {len(allowed)} cores local to GPU {bdf}, shared by {n} ranks)"
+    except Exception as ex:   # containers without sysfs PCI topology: run unbound
+        return f"unbound ({type(ex).__name__})"
+
+
 class Ctx:
     """Process-wide state of the GPU arm."""
 
@@ -262,6 +299,7 @@ class Ctx:
             raise SystemExit("bench.py needs a CUDA device: the engine has no CPU path")
         torch.cuda.set_device(self.local)
         self.dev = torch.device("cuda", self.local)
+        self.affinity = bind_rank_to_gpu_numa(torch, self.local, self.world)
         if self.world > 1:
             dist.init_process_group("nccl", device_id=self.dev)
 
@@ -682,7 +720,7 @@ def run_ours(args):
             "config": workload_config(B),
             "notes": {"frames_per_step_all_gpus": B * ctx.world, "sharding": "frames sharded by rank, no data-path collective "
                       "(config 2 does not shard below a frame: replicas); configs 4 and 5 below use NCCL",
-                      "lookahead": bool(sb.lookahead), "library": os.environ.get("SURF_B200_LIB", "surffeatures_b200/libsurf_b200.so")},
+                      "lookahead": bool(sb.lookahead), "two_batches_in_flight": True, "host_affinity": ctx.affinity, "library": os.environ.get("SURF_B200_LIB", "surffeatures_b200/libsurf_b200.so")},
             "e2e": {"value": fps_e2e, "unit": "frames/s", "h2d_bytes_per_step": sb.bytes_io["h2d"],
                     "d2h_bytes_per_step": sb.bytes_io["d2h"], "ms_per_step": ms_e2e / steps},
             "gpu_launches": n_launch, "keypoints_per_frame": kp_per_frame,

@@ -516,8 +516,8 @@ int surf_sweep_sharded(surf_engine *e, surf_comm *comm, const uint8_t *images_lo
     cudaGetLastError();
     if (first_error != SURF_OK) {
         // leave no batch behind: whatever was submitted and not collected is collected into nowhere
-        while (surf_collect_batch(e, nullptr, nullptr, SURF_MEM_DEVICE, 1L << 40, off32.data()) != SURF_ERR_BAD_ARG) {
-        }
+        while (e->out[0].active || e->out[1].active)
+            if (surf_collect_batch(e, nullptr, nullptr, SURF_MEM_DEVICE, 1L << 40, off32.data()) != SURF_OK) break;
         snprintf(e->err, sizeof(e->err), "%s", first_msg);
         return first_error;
     }

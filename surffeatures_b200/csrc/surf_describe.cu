@@ -89,6 +89,39 @@ __device__ __forceinline__ float fast_atan2_deg(float y, float x)
     return a;
 }
 
+// ---- packed fp32 (Blackwell FADD2 / FMUL2 / FFMA2): two IEEE single operations per instruction ----
+__device__ __forceinline__ uint64_t f2_pack(float lo, float hi)
+{
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void f2_unpack(uint64_t v, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ uint64_t f2_mul(uint64_t a, uint64_t b)
+{
+    uint64_t r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ uint64_t f2_sub(uint64_t a, uint64_t b)
+{
+    uint64_t r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ uint64_t f2_fma(uint64_t a, uint64_t b, uint64_t c)
+{
+    uint64_t r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ uint64_t f2_add(uint64_t a, uint64_t b)
+{
+    uint64_t r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+
 // uchar -> float without a conversion instruction: 2^23 + v is exact, minus 2^23 gives v.
 __device__ __forceinline__ float u8f(unsigned v) { return __uint_as_float(0x4B000000u | v) - 8388608.0f; }
 
@@ -229,15 +262,20 @@ __global__ void __launch_bounds__(kOriWarps * 32) k_orient(const __grid_constant
                 float bmod = 0, bx = 0, by = 0;
                 int bi = 1 << 30;
                 {
-                    float sx0 = 0, sy0 = 0, sx1 = 0, sy1 = 0, sx2 = 0, sy2 = 0;
+                    // (sum x, sum y) of a window advance together: one packed add (FADD2) per member sample
+                    uint64_t s0 = 0, s1 = 0, s2 = 0;  // (+0.0f, +0.0f)
 #pragma unroll 4
                     for (int k = 0; k < na; k++) {
-                        const OriSample o = smp[k];
+                        const ulonglong2 o = *reinterpret_cast<const ulonglong2 *>(&smp[k]);  // (X, Y) | (m0, m1)
                         const unsigned m2 = smp2[k];
-                        if (o.m0 & lanebit) { sx0 += o.X; sy0 += o.Y; }
-                        if (o.m1 & lanebit) { sx1 += o.X; sy1 += o.Y; }
-                        if (m2 & lanebit) { sx2 += o.X; sy2 += o.Y; }
+                        if ((unsigned)o.y & lanebit) s0 = f2_add(s0, o.x);
+                        if ((unsigned)(o.y >> 32) & lanebit) s1 = f2_add(s1, o.x);
+                        if (m2 & lanebit) s2 = f2_add(s2, o.x);
                     }
+                    float sx0, sy0, sx1, sy1, sx2, sy2;
+                    f2_unpack(s0, sx0, sy0);
+                    f2_unpack(s1, sx1, sy1);
+                    f2_unpack(s2, sx2, sy2);
                     const float q0 = sx0 * sx0 + sy0 * sy0, q1 = sx1 * sx1 + sy1 * sy1, q2 = sx2 * sx2 + sy2 * sy2;
                     if (q0 > bmod) { bmod = q0; bx = sx0; by = sy0; bi = lane; }
                     if (q1 > bmod) { bmod = q1; bx = sx1; by = sy1; bi = lane + 32; }
@@ -431,32 +469,6 @@ __device__ __forceinline__ uint32_t tap_fixed(long long X, long long Y)
 #ifndef SURF_TAP_F32X2
 #define SURF_TAP_F32X2 1
 #endif
-__device__ __forceinline__ uint64_t f2_pack(float lo, float hi)
-{
-    uint64_t r;
-    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-    return r;
-}
-__device__ __forceinline__ void f2_unpack(uint64_t v, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
-__device__ __forceinline__ uint64_t f2_mul(uint64_t a, uint64_t b)
-{
-    uint64_t r;
-    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-    return r;
-}
-__device__ __forceinline__ uint64_t f2_sub(uint64_t a, uint64_t b)
-{
-    uint64_t r;
-    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-    return r;
-}
-__device__ __forceinline__ uint64_t f2_fma(uint64_t a, uint64_t b, uint64_t c)
-{
-    uint64_t r;
-    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
-    return r;
-}
-
 // Two interior taps at once (same contract as tap_fixed for each of them).  `one` = (1.0f, 1.0f) from c_one2.
 template <int TP>
 __device__ __forceinline__ void tap_fixed2(long long X0, long long Y0, long long X1, long long Y1, uint64_t one, uint32_t &v0,

@@ -348,7 +348,8 @@ void drop_batches(surf_engine *e)
 
 void free_workspace(surf_engine *e)
 {
-    cudaFree(e->d_img); cudaFree(e->d_img_next); cudaFree(e->d_mask); cudaFree(e->d_sum); cudaFree(e->d_msum); cudaFree(e->d_bandsum);
+    for (auto &p : e->imgbuf) { cudaFree(p); p = nullptr; }
+    cudaFree(e->d_mask); cudaFree(e->d_sum); cudaFree(e->d_msum); cudaFree(e->d_bandsum);
     cudaFree(e->d_det); cudaFree(e->d_kp_a); cudaFree(e->d_kp_b); cudaFree(e->d_desc);
     cudaFree(e->d_patches); cudaFree(e->d_counts); cudaFree(e->d_ndel);
     cudaFree(e->d_off_in); cudaFree(e->d_misc); cudaFree(e->d_deleted);
@@ -371,7 +372,7 @@ void free_workspace(surf_engine *e)
     e->alt.d_sum = nullptr; e->alt.d_kp_a = e->alt.d_kp_b = e->alt.sorted = nullptr; e->alt.d_counts = nullptr;
     e->alt.tmap_w = 0; e->alt.free_recorded = false;
     e->la.valid = false;
-    e->d_img = e->d_img_next = e->d_mask = nullptr; e->prefetched.valid = false; e->d_sum = e->d_msum = e->d_bandsum = nullptr; e->d_det = nullptr;
+    e->d_mask = nullptr; e->prefetched.valid = false; e->buf_staged = -1; e->d_sum = e->d_msum = e->d_bandsum = nullptr; e->d_det = nullptr;
     e->d_kp_a = e->d_kp_b = e->d_out_kp = nullptr; e->d_desc = e->d_out_desc = nullptr; e->d_patches = nullptr;
     e->d_counts = e->d_ndel = e->d_off_in = e->d_off_out = e->d_misc = e->d_deleted = nullptr;
     e->d_match_part = nullptr; e->d_match_io = nullptr; e->h_pin = nullptr; e->d_class_list = nullptr;
@@ -413,7 +414,7 @@ int alloc_workspace(surf_engine *e)
     const int W = e->max_w, H = e->max_h, B = e->max_b, cap = e->cap;
     const FrameGeo g = make_geo(W, H);
     e->img_pitch = (size_t)((W + 15) & ~15);
-    CU(e, cudaMalloc(&e->d_img, e->img_pitch * H * B));
+    CU(e, cudaMalloc(&e->imgbuf[0], e->img_pitch * H * B));  // the other two on first use (prefetch / look-ahead)
     CU(e, cudaMalloc(&e->d_mask, e->img_pitch * H));
     CU(e, cudaMalloc(&e->d_sum, g.sum_frame * sizeof(uint32_t) * B));
     CU(e, cudaMalloc(&e->d_msum, g.sum_frame * sizeof(uint32_t)));
@@ -460,6 +461,18 @@ int check_frame_args(surf_engine *e, const BatchIn &in)
                     in.batch, e->max_w, e->max_h, e->max_b);
     if (in.in_mem != SURF_MEM_HOST && in.in_mem != SURF_MEM_DEVICE) return fail(e, SURF_ERR_BAD_ARG, "bad in_mem");
     if (in.mask && in.mask_pitch < (size_t)in.width) return fail(e, SURF_ERR_BAD_ARG, "mask pitch smaller than width");
+    return SURF_OK;
+}
+
+// Host frames are staged in a rotation of three device buffers: the batch in its descriptor stage reads one, the batch
+// submitted after it (continuing from its look-ahead) the second, and the upload of the batch after that goes to the
+// third -- the buffer whose batch ended two submits ago -- so it starts at once instead of waiting for the batch in
+// flight.  Returns the next buffer of the rotation (allocated on first use).
+int next_frame_buffer(surf_engine *e, int *out)
+{
+    const int b = (e->buf_cur + 1) % 3;
+    if (!e->imgbuf[b]) CU(e, cudaMalloc(&e->imgbuf[b], e->img_pitch * e->max_h * e->max_b));
+    *out = b;
     return SURF_OK;
 }
 
@@ -531,23 +544,20 @@ int stage_images(surf_engine *e, const BatchIn &in, ImageRef *ref)
     surf_engine::Prefetched &pf = e->prefetched;
     if (pf.valid && pf.images == in.images && pf.batch == in.batch && pf.width == in.width && pf.height == in.height &&
         pf.pitch == in.pitch && pf.frame_stride == in.frame_stride) {
-        // these frames are already on their way (surf_prefetch_batch): swap the buffers, wait on the device only
-        uint8_t *t = e->d_img;
-        e->d_img = e->d_img_next;
-        e->d_img_next = t;
-        cudaEvent_t te = e->ev_free_cur;
-        e->ev_free_cur = e->ev_free_next;
-        e->ev_free_next = te;
-        const bool tr = e->free_cur_recorded;
-        e->free_cur_recorded = e->free_next_recorded;
-        e->free_next_recorded = tr;
+        // these frames are already on their way (surf_prefetch_batch): take their buffer, wait on the device only
+        e->buf_cur = e->buf_staged;
         CU(e, cudaStreamWaitEvent(e->stream, e->ev_upload_done, 0));
     } else {
-        int rc = upload_frames(e, in, e->d_img, e->stream);
+        int b = 0;
+        int rc = next_frame_buffer(e, &b);
         if (rc) return rc;
+        if (e->buf_free_rec[b]) CU(e, cudaStreamWaitEvent(e->stream, e->ev_buf_free[b], 0));
+        if ((rc = upload_frames(e, in, e->imgbuf[b], e->stream))) return rc;
+        e->buf_cur = b;
     }
     pf.valid = false;
-    ref->ptr = e->d_img;
+    e->buf_staged = -1;
+    ref->ptr = e->imgbuf[e->buf_cur];
     ref->pitch = e->img_pitch;
     ref->frame_stride = e->img_pitch * in.height;
     return SURF_OK;
@@ -773,8 +783,7 @@ int surf_create(const surf_params *params, int device, int max_width, int max_he
     }
     cudaEventCreateWithFlags(&e->ev_match_copy_done, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&e->ev_upload_done, cudaEventDisableTiming);
-    cudaEventCreateWithFlags(&e->ev_free_cur, cudaEventDisableTiming);
-    cudaEventCreateWithFlags(&e->ev_free_next, cudaEventDisableTiming);
+    for (auto &ev : e->ev_buf_free) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
     cudaStreamCreateWithFlags(&e->upload_stream, cudaStreamNonBlocking);
     // Default priority on purpose.  Measured (64 frames, 640x480): with a high-priority look-ahead stream and
     // descriptor CTAs that turn over every 8-128 keypoints the Hessian kernels run at full speed but stretch the
@@ -829,8 +838,8 @@ void surf_destroy(surf_engine *e)
             if (ev) cudaEventDestroy(ev);
     if (e->ev_match_copy_done) cudaEventDestroy(e->ev_match_copy_done);
     if (e->ev_upload_done) cudaEventDestroy(e->ev_upload_done);
-    if (e->ev_free_cur) cudaEventDestroy(e->ev_free_cur);
-    if (e->ev_free_next) cudaEventDestroy(e->ev_free_next);
+    for (cudaEvent_t ev : e->ev_buf_free)
+        if (ev) cudaEventDestroy(ev);
     if (e->upload_stream) {
         cudaStreamSynchronize(e->upload_stream);
         cudaStreamDestroy(e->upload_stream);
@@ -927,9 +936,8 @@ int surf_submit_batch(surf_engine *e, const uint8_t *images, int in_mem, int bat
         swap_detect_sets(e);
         e->ev = e->la_ev;
         if (in_mem == SURF_MEM_HOST) {
-            std::swap(e->d_img, e->d_img_next);
-            std::swap(e->ev_free_cur, e->ev_free_next);
-            std::swap(e->free_cur_recorded, e->free_next_recorded);
+            e->buf_cur = e->buf_staged;
+            e->buf_staged = -1;
         }
         img = la.img;
         e->launches = la.launches;
@@ -947,9 +955,9 @@ int surf_submit_batch(surf_engine *e, const uint8_t *images, int in_mem, int bat
     if ((rc = fetch_counts(e, batch))) return rc;
     rec(e, EV_END);
     CU(e, cudaEventRecord(o.ev_ready, e->stream));
-    if (in_mem == SURF_MEM_HOST) {  // the staged frames (d_img) are free again after these kernels
-        CU(e, cudaEventRecord(e->ev_free_cur, e->stream));
-        e->free_cur_recorded = true;
+    if (in_mem == SURF_MEM_HOST) {  // the staged frames are free again after these kernels
+        CU(e, cudaEventRecord(e->ev_buf_free[e->buf_cur], e->stream));
+        e->buf_free_rec[e->buf_cur] = true;
     }
     o.ev = e->ev;
     o.active = true;
@@ -968,17 +976,19 @@ int surf_prefetch_batch(surf_engine *e, const uint8_t *images, int batch, int wi
     int rc = check_frame_args(e, in);
     if (rc) return rc;
     if ((rc = ensure_device(e))) return rc;
-    if (!e->d_img_next) CU(e, cudaMalloc(&e->d_img_next, e->img_pitch * e->max_h * e->max_b));
-    if (e->la.valid) {  // a pending look-ahead may own the second frame buffer: it is given up
+    if (e->la.valid) {  // a pending look-ahead owns the staged frame buffer: it is given up
         e->la.valid = false;
         CU(e, cudaStreamWaitEvent(e->upload_stream, e->ev_la_done, 0));
         CU(e, cudaStreamWaitEvent(e->stream, e->ev_la_done, 0));
     }
-    // the upload may start as soon as the last kernels that read this buffer (two batches ago) have ended; it
-    // overlaps the kernels of the batch in flight, which read the other buffer.  The host does not wait.
-    if (e->free_next_recorded) CU(e, cudaStreamWaitEvent(e->upload_stream, e->ev_free_next, 0));
-    if ((rc = upload_frames(e, in, e->d_img_next, e->upload_stream))) return rc;
+    int b = 0;
+    if ((rc = next_frame_buffer(e, &b))) return rc;
+    // the upload may start as soon as the last kernels that read this buffer (three batches ago) have ended; it
+    // overlaps the kernels of the batches in flight, which read the other buffers.  The host does not wait.
+    if (e->buf_free_rec[b]) CU(e, cudaStreamWaitEvent(e->upload_stream, e->ev_buf_free[b], 0));
+    if ((rc = upload_frames(e, in, e->imgbuf[b], e->upload_stream))) return rc;
     CU(e, cudaEventRecord(e->ev_upload_done, e->upload_stream));
+    e->buf_staged = b;
     surf_engine::Prefetched &pf = e->prefetched;
     pf.images = images; pf.batch = batch; pf.width = width; pf.height = height; pf.pitch = pitch;
     pf.frame_stride = frame_stride; pf.valid = true;
@@ -1006,14 +1016,24 @@ int surf_lookahead_batch(surf_engine *e, const uint8_t *images, int in_mem, int 
         CU(e, cudaMalloc(&a.d_kp_b, nk * sizeof(surf_keypoint)));
         CU(e, cudaMalloc(&a.d_counts, sizeof(int) * (e->max_b + 1)));
     }
-    if (in_mem == SURF_MEM_HOST && !e->d_img_next) CU(e, cudaMalloc(&e->d_img_next, e->img_pitch * e->max_h * e->max_b));
+    int fb = 0;
+    if (in_mem == SURF_MEM_HOST) {
+        // the frames go up on the upload stream right away (third buffer of the rotation: its batch ended two submits
+        // ago); only stages 1-3 wait for the detect set
+        if ((rc = next_frame_buffer(e, &fb))) return rc;
+        if (e->la_done_recorded) CU(e, cudaStreamWaitEvent(e->upload_stream, e->ev_la_done, 0));  // a replaced look-ahead
+        if (e->buf_free_rec[fb]) CU(e, cudaStreamWaitEvent(e->upload_stream, e->ev_buf_free[fb], 0));
+        if ((rc = upload_frames(e, in, e->imgbuf[fb], e->upload_stream))) return rc;
+        CU(e, cudaEventRecord(e->ev_upload_done, e->upload_stream));
+        e->buf_staged = fb;
+    }
     cudaStream_t ls = e->la_stream;
     // Ordering: after stages 1-3 of the batch in flight (the determinant pyramid, band sums and mask integral are
     // shared scratch; it is also the overlap wanted: these kernels run beside that batch's descriptor stage), after
     // the stage-4 kernels that last read the alternate set, and after the last readers of the second frame buffer.
     if (e->detect_done_recorded) CU(e, cudaStreamWaitEvent(ls, e->ev_detect_done, 0));
     if (a.free_recorded) CU(e, cudaStreamWaitEvent(ls, a.ev_free, 0));
-    if (in_mem == SURF_MEM_HOST && e->free_next_recorded) CU(e, cudaStreamWaitEvent(ls, e->ev_free_next, 0));
+    if (in_mem == SURF_MEM_HOST) CU(e, cudaStreamWaitEvent(ls, e->ev_upload_done, 0));
     // run stages 1-3 with the alternate set, the look-ahead stream and the look-ahead's own stage events in place
     const int launches0 = e->launches;
     e->launches = 0;
@@ -1030,8 +1050,7 @@ int surf_lookahead_batch(surf_engine *e, const uint8_t *images, int in_mem, int 
         img.pitch = pitch;
         img.frame_stride = frame_stride;
     } else {
-        rc = upload_frames(e, in, e->d_img_next, e->stream);
-        img.ptr = e->d_img_next;
+        img.ptr = e->imgbuf[fb];
         img.pitch = e->img_pitch;
         img.frame_stride = e->img_pitch * height;
     }
@@ -1045,6 +1064,7 @@ int surf_lookahead_batch(surf_engine *e, const uint8_t *images, int in_mem, int 
     // stream's own marker must be recorded again by its next run_detect
     std::swap(e->ev_detect_done, e->ev_la_done);
     e->detect_done_recorded = false;
+    e->la_done_recorded = true;
     e->ev = main_ev;
     std::swap(e->stream, e->la_stream);
     swap_detect_sets(e);

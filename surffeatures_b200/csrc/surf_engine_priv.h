@@ -69,15 +69,15 @@ struct surf_engine {
     int out_collected = -1;  // set of the batch collected last
 
     // workspace
-    uint8_t *d_img = nullptr;   size_t img_pitch = 0;
-    // surf_prefetch_batch: the next batch's frames are uploaded on their own stream into the second frame buffer
-    // while the current batch computes; surf_submit_batch of the same host frames then swaps the buffers
-    uint8_t *d_img_next = nullptr;
-    cudaStream_t upload_stream = nullptr;
+    // Host frames are staged in a rotation of three device buffers (see next_frame_buffer): buf_cur holds the frames of
+    // the batch submitted last, buf_staged those of a prefetch / look-ahead not yet adopted (-1: none).
+    uint8_t *imgbuf[3] = {nullptr, nullptr, nullptr};   size_t img_pitch = 0;
+    int buf_cur = 0, buf_staged = -1;
+    cudaEvent_t ev_buf_free[3] = {nullptr, nullptr, nullptr};  // end of the last kernels that read the buffer
+    bool buf_free_rec[3] = {false, false, false};
+    cudaStream_t upload_stream = nullptr;   // uploads of surf_prefetch_batch / surf_lookahead_batch
     cudaEvent_t ev_upload_done = nullptr;
-    // end of the last kernels that read d_img / d_img_next (swapped together with the buffers)
-    cudaEvent_t ev_free_cur = nullptr, ev_free_next = nullptr;
-    bool free_cur_recorded = false, free_next_recorded = false;
+    bool la_done_recorded = false;
     struct Prefetched {
         const uint8_t *images = nullptr;
         int batch = 0, width = 0, height = 0;

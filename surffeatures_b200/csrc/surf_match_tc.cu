@@ -207,6 +207,232 @@ __device__ __forceinline__ void cand_replace_worst(Cand<KC> &c, float dist, int 
 
 constexpr int kCandThreads = 512;  // 16 warps: warp w owns TMEM lanes 32*(w%4).. and the column quarter w/4
 
+#ifndef SURF_TC_PIPE
+#define SURF_TC_PIPE 1
+#endif
+#if SURF_TC_PIPE
+// Software-pipelined candidate search: train tiles of kTC = 128 rows, TWO accumulators of 128 TMEM columns in the CTA's
+// 256 and two operand stages in shared memory.  While the 16 epilogue warps scan accumulator (t & 1), the tensor core
+// already computes tile t + 1 into the other one (issued by thread 0 at the top of iteration t) and the bulk copies of
+// tile t + 2 land in the stage tile t's MMA has just released:
+//     iteration t :  [thread 0] wait operands(t+1) -> MMA(t+1) -> commit          (accumulator and stage (t+1) & 1)
+//                    [all]      wait MMA(t)                                        (issued one iteration earlier)
+//                    [thread 0] bulk copies of tile t+2 -> stage t & 1             (|t|^2 rows: three slots, see below)
+//                    [all]      epilogue(t): tcgen05.ld, filter, candidate lists
+//                    [all]      tcgen05 fence, block barrier                       (accumulator t & 1 drained)
+// Round 1 ran MMA(t) -> epilogue(t) back to back in a CTA (one 256-column accumulator) and relied on the second CTA
+// of the SM for overlap: 55 % issue-active, tensor pipe 12 %.
+constexpr int kTC = 128;
+
+template <int D, int KC>
+__global__ void __launch_bounds__(kCandThreads, (D == 64 && KC <= 4) ? 2 : 1) k_tc_candidates(TcPool pool, TcPool tpool, const TcProblem *__restrict__ probs,
+                                                       int n_probs, int mt_per_prob, int n_splits, int cand_stride,
+                                                       TcCand *__restrict__ cand_out, int *__restrict__ work_head)
+{
+    constexpr int KSTEPS = D / 16;
+    constexpr uint32_t SBO = (D / 8) * 128;        // bytes between 8-row groups
+    constexpr uint32_t A_BYTES = kTM * D * 2;      // one of hi / lo
+    constexpr uint32_t B_BYTES = kTC * D * 2;      // one of hi / lo of one stage
+    extern __shared__ __align__(1024) unsigned char sm[];
+    unsigned char *sA_hi = sm, *sA_lo = sm + A_BYTES;
+    unsigned char *sB = sm + 2 * A_BYTES;          // stage s: hi at sB + s * 2 * B_BYTES, lo right behind it
+    // |t|^2 of the train tiles: THREE slots, because the slot of tile t is still read by epilogue(t) when the copies
+    // of tile t + 2 are issued (the operand stage itself is free by then: MMA(t) has completed)
+    float *sTn = reinterpret_cast<float *>(sB + 4 * B_BYTES);
+    __shared__ __align__(8) uint64_t s_bar[4];  // [0], [1] MMA done per accumulator; [2], [3] operands landed per stage
+    __shared__ uint32_t s_tmem;
+    __shared__ int s_item;
+    __shared__ float s_thr[4][kTM];  // filter threshold published by each column quarter of a query row
+
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int quarter = warp >> 2, qrow = (warp & 3) * 32 + (tid & 31);
+    volatile float *my_thr = &s_thr[quarter][qrow];
+    const volatile float *row_thr = &s_thr[0][qrow];  // the four quarters' thresholds of this row, kTM apart
+    const uint32_t bar_mma = smem_u32(&s_bar[0]), bar_ld = smem_u32(&s_bar[2]);  // + 8 * (accumulator | stage)
+    if (tid == 0) {
+        for (int i = 0; i < 4; i++) mbar_init(smem_u32(&s_bar[i]), 1);
+        mbar_init_fence();
+    }
+    __syncwarp();
+    if (warp == 0) tmem_alloc(smem_u32(&s_tmem), kTmemCols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = s_tmem;
+    const uint32_t idesc = umma_idesc(kTM, kTC);
+    uint32_t ph_mma = 0, ph_ld = 0;  // bit s = parity of barrier s (ph_ld is only used by thread 0)
+    const int total_items = n_probs * mt_per_prob * n_splits;
+
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) s_item = atomicAdd(work_head, 1);
+        __syncthreads();
+        const int item = s_item;
+        if (item >= total_items) break;
+        const int p = item / (mt_per_prob * n_splits);
+        const int rem = item - p * (mt_per_prob * n_splits);
+        const int mt = rem / n_splits, split = rem - mt * n_splits;
+        const TcProblem pr = probs[p];
+        const int nq = pool.count[pr.q_slot], nt = tpool.count[pr.t_slot];
+        const int q0 = mt * kTM;
+        if (q0 >= nq) continue;
+        // train tiles of this split
+        const int n_tiles = (nt + kTC - 1) / kTC;
+        const int per = (n_tiles + n_splits - 1) / n_splits;
+        const int tile0 = split * per, tile1 = min(n_tiles, tile0 + per);
+
+        Cand<KC> best;
+#pragma unroll
+        for (int r = 0; r < KC; r++) {
+            best.d[r] = INFINITY;
+            best.i[r] = -1;
+        }
+        best.worst = INFINITY;
+        best.wslot = 0;
+        float thr = INFINITY;
+        *my_thr = INFINITY;  // read by the partners only after the tile loop's first block barrier (or the merge's)
+        const size_t trow_base = (size_t)pr.t_slot * tpool.slot_rows;
+        // operands arrive by TMA bulk copies (contiguous runs of core matrices), counted on the stage's barrier
+        auto load_train_tile = [&](int tile, int k) {  // k = tile - tile0
+            const int st = k & 1;
+            const size_t row0 = trow_base + (size_t)tile * kTC;
+            const uint32_t bar = bar_ld + 8 * st;
+            unsigned char *hi = sB + (size_t)st * 2 * B_BYTES;
+            bulk_g2s(smem_u32(hi), tpool.hi + row0 * D, B_BYTES, bar);
+            bulk_g2s(smem_u32(hi + B_BYTES), tpool.lo + row0 * D, B_BYTES, bar);
+            bulk_g2s(smem_u32(sTn + (k % 3) * kTC), tpool.norm + row0, kTC * sizeof(float), bar);
+        };
+        auto issue_mma = [&](int k) {  // thread 0: operands of stage k & 1 have landed; accumulator k & 1 is drained
+            const int st = k & 1;
+            mbar_wait(bar_ld + 8 * st, (ph_ld >> st) & 1);
+            ph_ld ^= 1u << st;
+            tc_fence_after();
+            const uint32_t a_hi = smem_u32(sA_hi), a_lo = smem_u32(sA_lo);
+            const uint32_t b_hi = smem_u32(sB + (size_t)st * 2 * B_BYTES), b_lo = b_hi + B_BYTES;
+            const uint32_t acc = tmem + (uint32_t)st * kTC;
+#pragma unroll
+            for (int ks = 0; ks < KSTEPS; ks++) {
+                const uint32_t ko = ks * 256;  // two core matrices (16 K-elements) per step
+                umma_bf16(acc, umma_desc(a_hi + ko, 128, SBO), umma_desc(b_hi + ko, 128, SBO), idesc, ks > 0);
+            }
+#pragma unroll
+            for (int ks = 0; ks < KSTEPS; ks++) {
+                const uint32_t ko = ks * 256;
+                umma_bf16(acc, umma_desc(a_hi + ko, 128, SBO), umma_desc(b_lo + ko, 128, SBO), idesc, 1);
+                umma_bf16(acc, umma_desc(a_lo + ko, 128, SBO), umma_desc(b_hi + ko, 128, SBO), idesc, 1);
+            }
+            umma_commit(bar_mma + 8 * st);
+        };
+        if (tid == 0 && tile0 < tile1) {
+            const size_t e0 = ((size_t)pr.q_slot * pool.slot_rows + q0) * D;
+            mbar_expect_tx(bar_ld, 2 * A_BYTES + 2 * B_BYTES + kTC * sizeof(float));
+            bulk_g2s(smem_u32(sA_hi), pool.hi + e0, A_BYTES, bar_ld);
+            bulk_g2s(smem_u32(sA_lo), pool.lo + e0, A_BYTES, bar_ld);
+            load_train_tile(tile0, 0);
+            if (tile0 + 1 < tile1) {
+                mbar_expect_tx(bar_ld + 8, 2 * B_BYTES + kTC * sizeof(float));
+                load_train_tile(tile0 + 1, 1);
+            }
+            issue_mma(0);
+        }
+
+        for (int tile = tile0; tile < tile1; tile++) {
+            const int k = tile - tile0, cur = k & 1;
+            const int t0 = tile * kTC;
+            if (tid == 0 && tile + 1 < tile1) issue_mma(k + 1);  // runs under this tile's epilogue
+            mbar_wait(bar_mma + 8 * cur, (ph_mma >> cur) & 1);    // accumulator `cur` complete; its operand stage is free
+            ph_mma ^= 1u << cur;
+            tc_fence_after();
+            if (tid == 0 && tile + 2 < tile1) {
+                mbar_expect_tx(bar_ld + 8 * cur, 2 * B_BYTES + kTC * sizeof(float));
+                load_train_tile(tile + 2, k + 2);
+            }
+
+            // ---- epilogue: 16 warps; warp w reads TMEM lanes 32*(w%4).. (its query rows) and the column
+            //      quarter w/4, so four threads share a query row and each keeps its own list.  The filter
+            //      threshold `thr` is the smallest of the four lists' worst kept values: each of them is >= the
+            //      KC-th smallest value of the whole row, so nothing that belongs to the row's KC smallest is
+            //      ever rejected, and every value a list rejects or evicts is >= the final thr.
+            const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)cur * kTC;
+            const float *tn = sTn + (k % 3) * kTC;
+            const int lim = min(kTC, nt - t0);
+            const int c0 = quarter * (kTC / 4);
+            {
+                float v[32];
+                tmem_ld32(lane_addr + c0, v);
+                thr = fminf(fminf(thr, row_thr[0]), fminf(row_thr[kTM], fminf(row_thr[2 * kTM], row_thr[3 * kTM])));
+                if (c0 < lim) {
+#pragma unroll
+                    for (int c = 0; c < 32; c += 4) {
+                        const float4 t4 = *reinterpret_cast<const float4 *>(tn + c0 + c);
+                        // |t|^2 - 2 q.t  (+ |q|^2 later); padded train rows carry |t|^2 = inf
+                        const float d0 = fmaf(-2.f, v[c], t4.x), d1 = fmaf(-2.f, v[c + 1], t4.y);
+                        const float d2 = fmaf(-2.f, v[c + 2], t4.z), d3 = fmaf(-2.f, v[c + 3], t4.w);
+                        if (fminf(fminf(d0, d1), fminf(d2, d3)) < thr) {  // one test per four columns
+                            const int idx = t0 + c0 + c;
+                            if (d0 < thr) { cand_replace_worst(best, d0, idx); thr = fminf(thr, best.worst); }
+                            if (d1 < thr) { cand_replace_worst(best, d1, idx + 1); thr = fminf(thr, best.worst); }
+                            if (d2 < thr) { cand_replace_worst(best, d2, idx + 2); thr = fminf(thr, best.worst); }
+                            if (d3 < thr) { cand_replace_worst(best, d3, idx + 3); thr = fminf(thr, best.worst); }
+                        }
+                    }
+                }
+                *my_thr = thr;
+            }
+            tc_fence_before();
+            __syncthreads();  // every warp has drained accumulator `cur` before MMA(t + 2) overwrites it
+        }
+        // ---- merge the four quarter lists of every query row into one list of the KC smallest values.  The
+        //      scratch aliases the operand stages: every MMA that read them has completed (bar_mma), no copy is in
+        //      flight, and the next item's bulk copies are issued only after the proxy fence and the barrier at the
+        //      loop top.
+        struct Ent {
+            float d;
+            int i;
+        };
+        static_assert(sizeof(Ent) * kTM * 4 * KC <= 4 * B_BYTES, "merge scratch must fit the operand stages");
+        Ent *s_merge = reinterpret_cast<Ent *>(sB);  // [row][quarter][KC]
+#pragma unroll
+        for (int r = 0; r < KC; r++) s_merge[(qrow * 4 + quarter) * KC + r] = Ent{best.d[r], best.i[r]};
+        *my_thr = thr;
+        __syncthreads();
+        if (tid < kTM) {
+            const int row = tid;
+            Cand<KC> m;
+#pragma unroll
+            for (int r = 0; r < KC; r++) {
+                m.d[r] = INFINITY;
+                m.i[r] = -1;
+            }
+            m.worst = INFINITY;
+            m.wslot = 0;
+            for (int e = 0; e < 4 * KC; e++) {
+                const Ent en = s_merge[row * 4 * KC + e];
+                if (en.i >= 0 && en.d < m.worst) cand_replace_worst(m, en.d, en.i);
+            }
+            if (q0 + row < nq) {
+                TcCand o;
+#pragma unroll
+                for (int r = 0; r < kCand; r++) {
+                    o.d[r] = r < KC ? m.d[r < KC ? r : 0] : INFINITY;
+                    o.i[r] = r < KC ? m.i[r < KC ? r : 0] : -1;
+                }
+                // lower bound of every value of this split that is not in the list: what the quarter lists
+                // rejected or evicted (>= their final thresholds) and what the merge dropped (>= the list's worst)
+                const float bound = fminf(fminf(s_thr[0][row], s_thr[1][row]), fminf(s_thr[2][row], s_thr[3][row]));
+                o.worst = fminf(bound, m.worst);
+                cand_out[(size_t)(p * n_splits + split) * cand_stride + q0 + row] = o;
+            }
+        }
+        fence_async_smem();  // generic-proxy accesses to the stages before the next bulk copy overwrites them
+    }
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, kTmemCols);
+}
+
+size_t tc_candidates_smem(int dim) { return (size_t)(2 * kTM + 4 * kTC) * dim * 2 + 3 * kTC * sizeof(float) + 1024; }
+#else
+
 template <int D, int KC>
 __global__ void __launch_bounds__(kCandThreads, (D == 64 && KC <= 4) ? 2 : 1) k_tc_candidates(TcPool pool, TcPool tpool, const TcProblem *__restrict__ probs,
                                                        int n_probs, int mt_per_prob, int n_splits, int cand_stride,
@@ -401,6 +627,10 @@ __global__ void __launch_bounds__(kCandThreads, (D == 64 && KC <= 4) ? 2 : 1) k_
     __syncthreads();
     if (warp == 0) tmem_dealloc(tmem, kTmemCols);
 }
+
+
+size_t tc_candidates_smem(int dim) { return (size_t)(2 * kTM + 2 * kTN) * dim * 2 + 2 * kTN * sizeof(float) + 1024; }
+#endif
 
 // ------------------------------------------------------------------------------------------------
 // K5c: exact rescoring of the candidates, top-k, margin test.  LPQ lanes per query, one per
@@ -644,8 +874,6 @@ __global__ void __launch_bounds__(256) k_tc_redo(TcPool tpool, const TcProblem *
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
-size_t tc_candidates_smem(int dim) { return (size_t)(2 * kTM + 2 * kTN) * dim * 2 + 2 * kTN * sizeof(float) + 1024; }
-
 void launch_tc_prep(const TcPool &pool, const TcSegment *segs, int n_segs, int max_rows, int dim, bool reset_norms,
                     cudaStream_t st, int *launches)
 {
