@@ -41,6 +41,7 @@ PARAMS = dict(hessianThreshold=100.0, nOctaves=4, nOctaveLayers=3, extended=Fals
 RATIO = 0.8
 CAP = 8192          # raw keypoints per frame the workspace holds
 LOOKAHEAD = os.environ.get("SURF_BENCH_LOOKAHEAD", "1") != "0"   # surf_lookahead_batch in the throughput loops
+E2E_DIAG = os.environ.get("SURF_BENCH_E2E_DIAG", "")   # "no_d2h" / "no_h2d": diagnosis runs of the end-to-end loop, never a reported number
 POOL_BATCHES = 4    # distinct batches cycled through; the per-step working set (integral + det pyramid of 64 frames, ~600 MB) exceeds the 126 MB L2
 
 
@@ -397,8 +398,13 @@ class StreamBench:
     def step_e2e(self, i):
         e, B, W, H = self.eng, self.B, self.W, self.H
         hb = self.hbuf[i & 1]
-        self._submit(i + 1, self.MEM_HOST)
+        self._submit(i + 1, self.MEM_DEVICE if E2E_DIAG == "no_h2d" else self.MEM_HOST)
         e.wait_outputs()      # copies of step i-1 (other buffer set) have landed; this set is free again
+        if E2E_DIAG == "no_d2h":   # diagnosis only: the end-to-end loop without its result copies
+            e.collect(0, 0, self.MEM_DEVICE, self.cap_total, self.offsets)
+            if self.match:
+                e.match_prev_device(RATIO)
+            return
         e.collect(hb["kps"].data_ptr(), hb["desc"].data_ptr(), self.MEM_HOST, self.cap_total, self.offsets)
         n = int(self.offsets[B])
         self.kp_seen += n
@@ -411,7 +417,10 @@ class StreamBench:
     def timed(self, step_fn, steps, warmup, sample_clocks=False):
         e, ctx = self.eng, self.ctx
         e.stream_reset()
-        (self.prime_e2e if step_fn == self.step_e2e else self.prime_device)()   # batch 0 in flight before step 0
+        if step_fn == self.step_e2e and E2E_DIAG != "no_h2d":   # batch 0 in flight before step 0
+            self.prime_e2e()
+        else:
+            self.prime_device()
         for i in range(warmup):
             step_fn(i)
         sampler = ClockSampler(ctx.local) if sample_clocks else None
@@ -720,7 +729,7 @@ def run_ours(args):
             "config": workload_config(B),
             "notes": {"frames_per_step_all_gpus": B * ctx.world, "sharding": "frames sharded by rank, no data-path collective "
                       "(config 2 does not shard below a frame: replicas); configs 4 and 5 below use NCCL",
-                      "lookahead": bool(sb.lookahead), "two_batches_in_flight": True, "host_affinity": ctx.affinity, "library": os.environ.get("SURF_B200_LIB", "surffeatures_b200/libsurf_b200.so")},
+                      "lookahead": bool(sb.lookahead), "two_batches_in_flight": True, "e2e_diag": E2E_DIAG or None, "host_affinity": ctx.affinity, "library": os.environ.get("SURF_B200_LIB", "surffeatures_b200/libsurf_b200.so")},
             "e2e": {"value": fps_e2e, "unit": "frames/s", "h2d_bytes_per_step": sb.bytes_io["h2d"],
                     "d2h_bytes_per_step": sb.bytes_io["d2h"], "ms_per_step": ms_e2e / steps},
             "gpu_launches": n_launch, "keypoints_per_frame": kp_per_frame,

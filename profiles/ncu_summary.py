@@ -26,7 +26,17 @@ WANT = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "la
         "smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio",
         "smsp__average_warps_issue_stalled_dispatch_stall_per_issue_active.ratio",
         "smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio",
-        "smsp__thread_inst_executed_per_inst_executed.ratio"]
+        "smsp__thread_inst_executed_per_inst_executed.ratio",
+        # tensor pipe (stage 5): cycles the tensor cores / the tensor memory path are busy, TMEM instructions
+        "TPC.TriageCompute.sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed",
+        "TPC.TriageCompute.sm__pipe_tensor_subpipe_hmma_cycles_active_realtime.avg",
+        "sm__mem_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed",
+        "sm__inst_executed_pipe_tensor_subpipe_hmma.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_tmem.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active"]
 
 out = subprocess.run(["ncu", "-i", sys.argv[1], "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines()))

@@ -28,7 +28,7 @@ namespace surfb200 {
 __constant__ float c_ori_x[kOriSamples];  // sample offsets -6..6, kept as floats (an I2F per use sat on the slow conversion pipe)
 __constant__ float c_ori_y[kOriSamples];
 __constant__ float c_ori_w[kOriSamples];
-__constant__ float c_desc_w[400];
+__constant__ float c_desc_g[20];   // getGaussianKernel(20, 3.3) as floats; the sample weight is the float product g[y] * g[x]
 // 1.0f twice, opaque to ptxas (see tap_fixed2)
 __constant__ float2 c_one2 = {1.f, 1.f};
 
@@ -48,7 +48,7 @@ static void gaussian_taps(int n, double sigma, float *out)
 void upload_tables()
 {
     float px[kOriSamples], py[kOriSamples];
-    float pw[kOriSamples], dw[400], g[13], gd[20];
+    float pw[kOriSamples], g[13], gd[20];
     gaussian_taps(13, 2.5, g);
     int n = 0;
     for (int i = -6; i <= 6; i++)
@@ -59,12 +59,10 @@ void upload_tables()
                 pw[n++] = g[i + 6] * g[j + 6];
             }
     gaussian_taps(20, 3.3, gd);
-    for (int i = 0; i < 20; i++)
-        for (int j = 0; j < 20; j++) dw[i * 20 + j] = gd[i] * gd[j];
     cudaMemcpyToSymbol(c_ori_x, px, sizeof(px));
     cudaMemcpyToSymbol(c_ori_y, py, sizeof(py));
     cudaMemcpyToSymbol(c_ori_w, pw, sizeof(pw));
-    cudaMemcpyToSymbol(c_desc_w, dw, sizeof(dw));
+    cudaMemcpyToSymbol(c_desc_g, gd, sizeof(gd));
 }
 
 __device__ __forceinline__ float fast_atan2_deg(float y, float x)
@@ -90,6 +88,13 @@ __device__ __forceinline__ float fast_atan2_deg(float y, float x)
 }
 
 // ---- packed fp32 (Blackwell FADD2 / FMUL2 / FFMA2): two IEEE single operations per instruction ----
+// compile-time switches of the three places that use it (A/B builds: tools/build_variant.sh)
+#ifndef SURF_TAP_F32X2
+#define SURF_TAP_F32X2 1
+#endif
+#ifndef SURF_ROW_F32X2
+#define SURF_ROW_F32X2 0   // packed INTER_AREA row pass: two weights per cell entry cost registers
+#endif
 __device__ __forceinline__ uint64_t f2_pack(float lo, float hi)
 {
     uint64_t r;
@@ -113,12 +118,6 @@ __device__ __forceinline__ uint64_t f2_fma(uint64_t a, uint64_t b, uint64_t c)
 {
     uint64_t r;
     asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
-    return r;
-}
-__device__ __forceinline__ uint64_t f2_add(uint64_t a, uint64_t b)
-{
-    uint64_t r;
-    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
     return r;
 }
 
@@ -262,20 +261,15 @@ __global__ void __launch_bounds__(kOriWarps * 32) k_orient(const __grid_constant
                 float bmod = 0, bx = 0, by = 0;
                 int bi = 1 << 30;
                 {
-                    // (sum x, sum y) of a window advance together: one packed add (FADD2) per member sample
-                    uint64_t s0 = 0, s1 = 0, s2 = 0;  // (+0.0f, +0.0f)
+                    float sx0 = 0, sy0 = 0, sx1 = 0, sy1 = 0, sx2 = 0, sy2 = 0;
 #pragma unroll 4
                     for (int k = 0; k < na; k++) {
-                        const ulonglong2 o = *reinterpret_cast<const ulonglong2 *>(&smp[k]);  // (X, Y) | (m0, m1)
+                        const OriSample o = smp[k];
                         const unsigned m2 = smp2[k];
-                        if ((unsigned)o.y & lanebit) s0 = f2_add(s0, o.x);
-                        if ((unsigned)(o.y >> 32) & lanebit) s1 = f2_add(s1, o.x);
-                        if (m2 & lanebit) s2 = f2_add(s2, o.x);
+                        if (o.m0 & lanebit) { sx0 += o.X; sy0 += o.Y; }
+                        if (o.m1 & lanebit) { sx1 += o.X; sy1 += o.Y; }
+                        if (m2 & lanebit) { sx2 += o.X; sy2 += o.Y; }
                     }
-                    float sx0, sy0, sx1, sy1, sx2, sy2;
-                    f2_unpack(s0, sx0, sy0);
-                    f2_unpack(s1, sx1, sy1);
-                    f2_unpack(s2, sx2, sy2);
                     const float q0 = sx0 * sx0 + sy0 * sy0, q1 = sx1 * sx1 + sy1 * sy1, q2 = sx2 * sx2 + sy2 * sy2;
                     if (q0 > bmod) { bmod = q0; bx = sx0; by = sy0; bi = lane; }
                     if (q1 > bmod) { bmod = q1; bx = sx1; by = sy1; bi = lane + 32; }
@@ -466,9 +460,7 @@ __device__ __forceinline__ uint32_t tap_fixed(long long X, long long Y)
 // not).  The sums are therefore written as fma(x, 1, y) with the two ones read from constant memory: that is
 // round(x + y) exactly, it already is a fused multiply-add (nothing left to contract) and ptxas cannot fold a
 // multiplier it does not know.
-#ifndef SURF_TAP_F32X2
-#define SURF_TAP_F32X2 1
-#endif
+
 // Two interior taps at once (same contract as tap_fixed for each of them).  `one` = (1.0f, 1.0f) from c_one2.
 template <int TP>
 __device__ __forceinline__ void tap_fixed2(long long X0, long long Y0, long long X1, long long Y1, uint64_t one, uint32_t &v0,
@@ -603,7 +595,7 @@ __device__ __forceinline__ void descriptor_tail(const DescribeArgs &A, int kidx,
             cell_weights<M>(S.tab, dx, w);
             uint32_t ra = win_addr + g * n + S.tab.start[dx], ba = buf_addr + (g * kPatch + dx) * 4;
             const uint32_t rstep = G * n;
-#if SURF_TAP_F32X2
+#if SURF_ROW_F32X2
             // Two source rows per iteration on the packed fp32 pipe: lane 0 of every pair is row sy, lane 1 row sy + G.
             // `b += p * w` is a rounded product and a rounded sum in the reference: FMUL2, then the sum as
             // fma(b, 1, product) (see tap_fixed2 for why the one comes from constant memory).
@@ -723,21 +715,26 @@ __device__ __forceinline__ void descriptor_tail(const DescribeArgs &A, int kidx,
 // batch written and read back, and four more launches.  Finishing them in batches keeps every warp of the CTA busy
 // at the same time, which finishing each keypoint's 25-step chains right after its window did not.)
 // ------------------------------------------------------------------------------------------------
-constexpr int kRing = 8;
+constexpr int kRing = 4;  // (8 patches + the 400-entry weight table in shared memory cost a CTA per SM in two classes)
 
-__device__ __forceinline__ void patch_descriptor_warp(const DescribeArgs &A, const unsigned char *P, int kidx, const float *s_w)
+__device__ __forceinline__ void patch_descriptor_warp(const DescribeArgs &A, const unsigned char *P, int kidx)
 {
     const int lane = threadIdx.x & 31;
     const int region = lane >> 1, half = lane & 1;
     const int y0 = (region >> 2) * 5, x0 = (region & 3) * 5;
+    // Gaussian weights of this lane's 5 x 5 samples: the table upstream builds is the float product g[y] * g[x]
+    float gx[5];
+#pragma unroll
+    for (int x = 0; x < 5; x++) gx[x] = c_desc_g[x0 + x];
     float a0 = 0, a1 = 0, a2 = 0, a3 = 0;
     for (int y = y0; y < y0 + 5; y++) {
         const unsigned char *r0 = P + y * kPatch + x0, *r1 = r0 + kPatch;
+        const float gy = c_desc_g[y];
         int p00 = r0[0], p10 = r1[0];
 #pragma unroll
         for (int x = 0; x < 5; x++) {
             const int p01 = r0[x + 1], p11 = r1[x + 1];
-            const float wgt = s_w[y * 20 + x0 + x];
+            const float wgt = __fmul_rn(gy, gx[x]);
             const float tx = (p01 - p00 + p11 - p10) * wgt, ty = (p10 - p00 + p11 - p01) * wgt;
             const float u = half ? ty : tx, o = half ? tx : ty;
             if (A.extended) {
@@ -774,7 +771,6 @@ __device__ __forceinline__ void patch_descriptor_warp(const DescribeArgs &A, con
 struct PatchRing {
     __align__(16) unsigned char patch[kRing][kPatchStride];
     int kidx[kRing];
-    float w[400];  // Gaussian weights of the 20 x 20 gradient samples (divergent index: shared, not constant memory)
 };
 
 // Every warp finishes the ring entries warp, warp + NW, ...  The caller guarantees the entries are visible (a block
@@ -782,7 +778,7 @@ struct PatchRing {
 template <int NW>
 __device__ __forceinline__ void ring_flush(const DescribeArgs &A, const PatchRing &R, int pending)
 {
-    for (int w = threadIdx.x >> 5; w < pending; w += NW) patch_descriptor_warp(A, R.patch[w], R.kidx[w], R.w);
+    for (int w = threadIdx.x >> 5; w < pending; w += NW) patch_descriptor_warp(A, R.patch[w], R.kidx[w]);
 }
 
 // Per-class compile-time geometry.  The image tile of a class has a FIXED pitch and row count (the largest
@@ -792,6 +788,8 @@ struct ClassT {
     static constexpr int max_n = CLS == 0 ? kClassMaxN0 : CLS == 1 ? kClassMaxN1 : kClassMaxN2;
     // measured (describe stage, 64 frames): 128/256/256 threads 6.43 ms, 128/128/256 6.28 ms, 256/256/256 7.46 ms
     static constexpr int threads = CLS == 2 ? 256 : 128;
+    // resident CTAs per SM the register allocation must allow (class 0 is register-limited: 10 x 128 threads x 48)
+    static constexpr int min_ctas = CLS == 0 ? 10 : CLS == 1 ? 6 : 3;
     // bounding box side of a rotated n x n window: n (|cos| + |sin|) + 3 <= 1.4143 n + 3, plus the 1-pixel
     // margin on both sides of the closed-form box; origin aligned down / pitch rounded up to 16 bytes
     static constexpr int side = (int)(1.4143 * max_n) + 4 + 2;
@@ -840,7 +838,7 @@ __device__ __forceinline__ void copy_tile_fallback(const DescribeArgs &A, const 
 }
 
 template <int CLS>
-__global__ void __launch_bounds__(ClassT<CLS>::threads) k_descriptor(const __grid_constant__ DescribeArgs A,
+__global__ void __launch_bounds__(ClassT<CLS>::threads, ClassT<CLS>::min_ctas) k_descriptor(const __grid_constant__ DescribeArgs A,
                                                                      const __grid_constant__ CUtensorMap imap, int use_tma)
 {
     using CT = ClassT<CLS>;
@@ -872,7 +870,6 @@ __global__ void __launch_bounds__(ClassT<CLS>::threads) k_descriptor(const __gri
         mbar_init_fence();
         S.next = atomicAdd(A.misc + kMiscClassHead + CLS, 1);
     }
-    for (int t = tid; t < 400; t += THREADS) ring.w[t] = c_desc_w[t];
 
     for (;;) {
         __syncthreads();  // everyone is done with the previous keypoint's shared state; S.next is visible
@@ -1074,7 +1071,6 @@ __global__ void __launch_bounds__(BigT::threads) k_descriptor_big(const __grid_c
         mbar_init_fence();
         S.next = atomicAdd(A.misc + kMiscClassHead + CLS, 1);
     }
-    for (int t = tid; t < 400; t += THREADS) ring.w[t] = c_desc_w[t];
 
     for (;;) {
         __syncthreads();  // S.next is visible

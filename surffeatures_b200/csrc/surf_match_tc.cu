@@ -207,8 +207,17 @@ __device__ __forceinline__ void cand_replace_worst(Cand<KC> &c, float dist, int 
 
 constexpr int kCandThreads = 512;  // 16 warps: warp w owns TMEM lanes 32*(w%4).. and the column quarter w/4
 
+// Two candidate kernels, selected at compile time.  SURF_TC_PIPE = 0 (default): one 256-column accumulator per CTA,
+// MMA(t) -> epilogue(t) back to back, two CTAs per SM overlap each other.  SURF_TC_PIPE = 1: the software-pipelined
+// variant below.  Measured on a B200 (round 2, 64 frame pairs of ~4230 x 4230 x 64, profiles/r2/): pipelined 0.902 ms
+// against 0.862 ms serial, 1M-row database query 3.07 ms against 2.42 ms.  The pipeline does what it should -- the
+// long-scoreboard stall (waiting for the accumulator) falls from 2.6 to 0.4 per issue -- but the tiles are half as
+// wide, so the block barrier that recycles an accumulator comes twice as often, and the epilogue's work per warp is
+// very uneven (divergent list updates: 15 of 32 lanes active on average): barrier stalls double (2.1 -> 4.2 per issue),
+// issue-slot utilisation stays at 55 % and the tensor pipe at 20 %.  The kernel is bound by the epilogue's
+// instructions, not by the MMA / epilogue serialisation; kept for reference, not built by default.
 #ifndef SURF_TC_PIPE
-#define SURF_TC_PIPE 1
+#define SURF_TC_PIPE 0
 #endif
 #if SURF_TC_PIPE
 // Software-pipelined candidate search: train tiles of kTC = 128 rows, TWO accumulators of 128 TMEM columns in the CTA's
