@@ -764,6 +764,7 @@ int surf_create(const surf_params *params, int device, int max_width, int max_he
     e->max_b = max_batch;
     e->cap = (max_keypoints + 127) & ~127;
     if (getenv("SURF_B200_NO_TMA")) e->use_tma = 0;
+    if (const char *v = getenv("SURF_B200_EARLY_UPLOAD")) e->early_upload = atoi(v);
     if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess) {
         delete e;
         return SURF_ERR_CUDA;
@@ -1017,23 +1018,34 @@ int surf_lookahead_batch(surf_engine *e, const uint8_t *images, int in_mem, int 
         CU(e, cudaMalloc(&a.d_counts, sizeof(int) * (e->max_b + 1)));
     }
     int fb = 0;
+    cudaStream_t ls = e->la_stream;
     if (in_mem == SURF_MEM_HOST) {
-        // the frames go up on the upload stream right away (third buffer of the rotation: its batch ended two submits
-        // ago); only stages 1-3 wait for the detect set
         if ((rc = next_frame_buffer(e, &fb))) return rc;
-        if (e->la_done_recorded) CU(e, cudaStreamWaitEvent(e->upload_stream, e->ev_la_done, 0));  // a replaced look-ahead
-        if (e->buf_free_rec[fb]) CU(e, cudaStreamWaitEvent(e->upload_stream, e->ev_buf_free[fb], 0));
-        if ((rc = upload_frames(e, in, e->imgbuf[fb], e->upload_stream))) return rc;
-        CU(e, cudaEventRecord(e->ev_upload_done, e->upload_stream));
+        if (e->early_upload) {
+            // the frames go up on the upload stream right away (third buffer of the rotation: its batch ended two
+            // submits ago); only stages 1-3 wait for the detect set
+            if (e->la_done_recorded) CU(e, cudaStreamWaitEvent(e->upload_stream, e->ev_la_done, 0));  // a replaced look-ahead
+            if (e->buf_free_rec[fb]) CU(e, cudaStreamWaitEvent(e->upload_stream, e->ev_buf_free[fb], 0));
+            if ((rc = upload_frames(e, in, e->imgbuf[fb], e->upload_stream))) return rc;
+            CU(e, cudaEventRecord(e->ev_upload_done, e->upload_stream));
+        }
         e->buf_staged = fb;
     }
-    cudaStream_t ls = e->la_stream;
     // Ordering: after stages 1-3 of the batch in flight (the determinant pyramid, band sums and mask integral are
     // shared scratch; it is also the overlap wanted: these kernels run beside that batch's descriptor stage), after
-    // the stage-4 kernels that last read the alternate set, and after the last readers of the second frame buffer.
+    // the stage-4 kernels that last read the alternate set, and after the last readers of the frame buffer.
     if (e->detect_done_recorded) CU(e, cudaStreamWaitEvent(ls, e->ev_detect_done, 0));
     if (a.free_recorded) CU(e, cudaStreamWaitEvent(ls, a.ev_free, 0));
-    if (in_mem == SURF_MEM_HOST) CU(e, cudaStreamWaitEvent(ls, e->ev_upload_done, 0));
+    if (in_mem == SURF_MEM_HOST) {
+        if (e->early_upload) {
+            CU(e, cudaStreamWaitEvent(ls, e->ev_upload_done, 0));
+        } else {
+            // the upload leads the look-ahead's own stream: it starts when the batch two submits back has left its
+            // descriptor stage, together with that batch's result copies in the other direction
+            if (e->buf_free_rec[fb]) CU(e, cudaStreamWaitEvent(ls, e->ev_buf_free[fb], 0));
+            if ((rc = upload_frames(e, in, e->imgbuf[fb], ls))) return rc;
+        }
+    }
     // run stages 1-3 with the alternate set, the look-ahead stream and the look-ahead's own stage events in place
     const int launches0 = e->launches;
     e->launches = 0;

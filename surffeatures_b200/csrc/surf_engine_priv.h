@@ -78,6 +78,7 @@ struct surf_engine {
     cudaStream_t upload_stream = nullptr;   // uploads of surf_prefetch_batch / surf_lookahead_batch
     cudaEvent_t ev_upload_done = nullptr;
     bool la_done_recorded = false;
+    int early_upload = 0;   // look-ahead uploads on the upload stream at once (1) or at the head of the look-ahead stream (0)
     struct Prefetched {
         const uint8_t *images = nullptr;
         int batch = 0, width = 0, height = 0;
