@@ -92,9 +92,6 @@ __device__ __forceinline__ float fast_atan2_deg(float y, float x)
 #ifndef SURF_TAP_F32X2
 #define SURF_TAP_F32X2 1
 #endif
-#ifndef SURF_ROW_F32X2
-#define SURF_ROW_F32X2 0   // packed INTER_AREA row pass: two weights per cell entry cost registers
-#endif
 __device__ __forceinline__ uint64_t f2_pack(float lo, float hi)
 {
     uint64_t r;
@@ -573,8 +570,8 @@ __device__ __forceinline__ void cell_weights(const AreaTab &t, int d, float (&w)
     for (int k = 0; k < MAXC; k++) w[k] = k >= c ? 0.f : ((k == 0 && hf) ? af : ((k == c - 1 && hl) ? al : am));
 }
 
-// MAXC > 0: the window and the row sums live in shared memory (addresses win_addr / buf_addr) and no cell of
-// the resize table touches more than MAXC source pixels; MAXC == 0: any window (global scratch), generic loops.
+// The window and the row sums live in shared memory (addresses win_addr / buf_addr) and no cell of the resize table
+// touches more than MAXC source pixels.
 template <int THREADS, int MAXC>
 __device__ __forceinline__ void descriptor_tail(const DescribeArgs &A, int kidx, int n, const unsigned char *win, float *buf,
                                                 uint32_t win_addr, uint32_t buf_addr, DescShared &S, bool int_scale, int isc,
@@ -583,11 +580,12 @@ __device__ __forceinline__ void descriptor_tail(const DescribeArgs &A, int kidx,
     const int tid = threadIdx.x;
     // Fractional scales run the reference's two passes: row sums buf[sy][dx] = sum_x win[sy][x] * alpha (fp32,
     // table order), then the column pass.  Thread = (row group, dx): the dx entry of the table stays in registers.
-    if (!int_scale && MAXC > 0) {
+    static_assert(MAXC > 0, "windows beyond the staged classes go through k_descriptor_big's streaming resize");
+    if (!int_scale) {
         // Fixed trip count: weights beyond the cell's pixel count are 0 and `b + p * 0 == b` exactly (the extra
         // reads stay inside the CTA's shared memory; any byte is a finite number).
         constexpr int G = THREADS / kPatch;
-        constexpr int M = MAXC > 0 ? MAXC : 1;
+        constexpr int M = MAXC;
         if (tid < G * kPatch) {
             const int g = tid / kPatch, dx = tid - g * kPatch;
             if (S.tab.count[dx] > M) atomicOr(A.misc + kMiscStatus, 2);  // table bound violated: reported by the host
@@ -595,29 +593,6 @@ __device__ __forceinline__ void descriptor_tail(const DescribeArgs &A, int kidx,
             cell_weights<M>(S.tab, dx, w);
             uint32_t ra = win_addr + g * n + S.tab.start[dx], ba = buf_addr + (g * kPatch + dx) * 4;
             const uint32_t rstep = G * n;
-#if SURF_ROW_F32X2
-            // Two source rows per iteration on the packed fp32 pipe: lane 0 of every pair is row sy, lane 1 row sy + G.
-            // `b += p * w` is a rounded product and a rounded sum in the reference: FMUL2, then the sum as
-            // fma(b, 1, product) (see tap_fixed2 for why the one comes from constant memory).
-            const uint64_t one2 = f2_pack(c_one2.x, c_one2.y);
-            uint64_t w2[M];
-#pragma unroll
-            for (int k = 0; k < M; k++) w2[k] = f2_pack(w[k], w[k]);
-            for (int sy = g; sy < n; sy += 2 * G, ra += 2 * rstep, ba += 2 * G * kPatch * 4) {
-                const bool has_b = sy + G < n;
-                const uint32_t rb = has_b ? ra + rstep : ra;   // no second row: the first one twice, result dropped
-                uint64_t b2 = f2_mul(f2_pack(tap_u8f(lds_u8<0>(ra)), tap_u8f(lds_u8<0>(rb))), w2[0]);
-#define SURF_ROW_STEP(K)                                                                                              \
-    if (M > K) b2 = f2_fma(b2, one2, f2_mul(f2_pack(tap_u8f(lds_u8<K % M>(ra)), tap_u8f(lds_u8<K % M>(rb))), w2[K % M]));
-                SURF_ROW_STEP(1) SURF_ROW_STEP(2) SURF_ROW_STEP(3) SURF_ROW_STEP(4) SURF_ROW_STEP(5) SURF_ROW_STEP(6) SURF_ROW_STEP(7)
-#undef SURF_ROW_STEP
-                static_assert(M <= 8, "extend the unrolled row pass");
-                float ba_v, bb_v;
-                f2_unpack(b2, ba_v, bb_v);
-                sts_f32(ba, ba_v);
-                if (has_b) sts_f32(ba + G * kPatch * 4, bb_v);
-            }
-#else
 #pragma unroll 2
             for (int sy = g; sy < n; sy += G, ra += rstep, ba += G * kPatch * 4) {
                 float b = tap_u8f(lds_u8<0>(ra)) * w[0];
@@ -630,30 +605,6 @@ __device__ __forceinline__ void descriptor_tail(const DescribeArgs &A, int kidx,
                 if (M > 7) b += tap_u8f(lds_u8<7 % M>(ra)) * w[7 % M];
                 static_assert(M <= 8, "extend the unrolled row pass");
                 sts_f32(ba, b);
-            }
-#endif
-        }
-        __syncthreads();
-    } else if (!int_scale) {
-        constexpr int G = THREADS / kPatch;
-        if (tid < G * kPatch) {
-            const int g = tid / kPatch, dx = tid - g * kPatch;
-            const int xs = S.tab.start[dx], xc = S.tab.count[dx];
-            const bool xhf = S.tab.has_first[dx], xhl = S.tab.has_last[dx];
-            const float xaf = S.tab.a_first[dx], xam = S.tab.a_mid[dx], xal = S.tab.a_last[dx];
-            const int fend = xc - (xhl ? 1 : 0);
-            for (int sy = g; sy < n; sy += G) {
-                const unsigned char *row = win + sy * n + xs;
-                float b = 0;
-                int f = 0;
-                if (xhf) {
-                    b += u8f(row[0]) * xaf;
-                    f = 1;
-                }
-#pragma unroll 4
-                for (; f < fend; f++) b += u8f(row[f]) * xam;
-                if (xhl) b += u8f(row[xc - 1]) * xal;
-                buf[sy * kPatch + dx] = b;
             }
         }
         __syncthreads();
@@ -672,8 +623,8 @@ __device__ __forceinline__ void descriptor_tail(const DescribeArgs &A, int kidx,
             }
             const float wgt = 1.f / (isc * isc);
             outv = sat_u8(acc * wgt);
-        } else if (MAXC > 0) {
-            constexpr int M = MAXC > 0 ? MAXC : 1;
+        } else {
+            constexpr int M = MAXC;
             float v[M];
             cell_weights<M>(S.tab, dy, v);
             const int ys = S.tab.start[dy];
@@ -681,18 +632,6 @@ __device__ __forceinline__ void descriptor_tail(const DescribeArgs &A, int kidx,
 #pragma unroll
             for (int e = 0; e < M; e++)  // rows past the window are clamped: their weight is 0, the value finite
                 acc += v[e] * lds_f32(buf_addr + (min(ys + e, n - 1) * kPatch + dx) * 4);
-            outv = sat_u8(acc);
-        } else {
-            const int ys = S.tab.start[dy], yc = S.tab.count[dy];
-            const bool yhf = S.tab.has_first[dy], yhl = S.tab.has_last[dy];
-            const float yaf = S.tab.a_first[dy], yam = S.tab.a_mid[dy], yal = S.tab.a_last[dy];
-            const float *col = buf + ys * kPatch + dx;
-            float acc = 0;
-            for (int e = 0; e < yc; e++) {
-                const float beta = (e == 0 && yhf) ? yaf : ((e == yc - 1 && yhl) ? yal : yam);
-                const float bv = col[e * kPatch];
-                if (e == 0) acc = beta * bv; else acc += beta * bv;
-            }
             outv = sat_u8(acc);
         }
         patch[p] = (unsigned char)outv;
@@ -808,7 +747,11 @@ struct BigT {
     static constexpr int tp = ClassT<1>::tp, tr = ClassT<1>::tr;
     static constexpr int tile_bytes = tp * tr;
     static constexpr int tile_stride = (tile_bytes + 127) & ~127;  // TMA destinations are 128-byte aligned
-    static constexpr int smem = 128 + 2 * tile_stride + kMaxWindow * 8;
+    // one sub-window of taps (kSubSide x kSubSide bytes) and its INTER_AREA row sums (kSubSide rows x 21 cells)
+    static constexpr int blk_bytes = kSubSide * kSubSide;
+    static constexpr int rows_bytes = kSubSide * kPatch * 4;
+    static constexpr int smem = 128 + 2 * tile_stride + kMaxWindow * 8 + blk_bytes + rows_bytes;
+    static constexpr int max_sub = 96;  // sub-windows per keypoint: <= 8 row blocks x <= 11 cell groups
 };
 
 // frame-tile fallback when the frames are not 16-byte aligned (no TMA): asynchronous 4-byte copies
@@ -1037,7 +980,15 @@ __global__ void __launch_bounds__(ClassT<CLS>::threads, ClassT<CLS>::min_ctas) k
     ring_flush<NW>(A, ring, pending);  // the loop left through its barrier
 }
 
-__global__ void __launch_bounds__(BigT::threads) k_descriptor_big(const __grid_constant__ DescribeArgs A,
+// Windows wider than 128 pixels (keypoint sizes above 46).  The window is never materialised: it is cut into
+// sub-windows of at most kSubSide x kSubSide taps -- row blocks of equal height, column groups that hold whole cells of
+// the 21-cell INTER_AREA table (neighbouring groups share the one boundary pixel two cells share) -- and every sub-window
+// goes  TMA tile -> taps (shared memory) -> row sums of its cells (shared memory).  When a row block is complete its row
+// sums are folded into the 21 x 21 column accumulators, in source-row order as the reference's vertical pass adds them
+// (two cells per thread, in registers across the row blocks).  Round 1 kept the whole window and its row sums in a
+// per-CTA global scratch: 52 MB written and 24 MB read back per 64-frame batch, a generic resize pass over global
+// memory, and 390 MB of workspace.
+__global__ void __launch_bounds__(BigT::threads, 3) k_descriptor_big(const __grid_constant__ DescribeArgs A,
                                                                   const __grid_constant__ CUtensorMap imap, int use_tma)
 {
     constexpr int THREADS = BigT::threads, NW = THREADS / 32;
@@ -1048,12 +999,14 @@ __global__ void __launch_bounds__(BigT::threads) k_descriptor_big(const __grid_c
     unsigned char *s_tile0 = dyn;                       // two tile buffers
     float *s_rsx = reinterpret_cast<float *>(dyn + 2 * BigT::tile_stride);
     float *s_rsy = s_rsx + kMaxWindow;
-    const uint32_t tile0_addr = pin_reg(smem_u32(s_tile0));
+    unsigned char *s_blk = reinterpret_cast<unsigned char *>(s_rsy + kMaxWindow);   // taps of the current sub-window, pitch kSubSide
+    float *s_rows = reinterpret_cast<float *>(s_blk + BigT::blk_bytes);             // row sums of the current row block [row][21]
+    const uint32_t tile0_addr = pin_reg(smem_u32(s_tile0)), blk_addr = pin_reg(smem_u32(s_blk));
     __shared__ __align__(8) uint64_t s_bar[2];
     __shared__ DescShared S;
     __shared__ PatchRing ring;
     int pending = 0;
-    __shared__ int4 s_sub[(kMaxWindow / kSubSide) * (kMaxWindow / kSubSide)];  // per sub-window: tile origin x, y, flags
+    __shared__ int4 s_sub[BigT::max_sub];  // per sub-window: tile origin x, y, flags
     uint32_t phase[2] = {0, 0};
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -1061,9 +1014,6 @@ __global__ void __launch_bounds__(BigT::threads) k_descriptor_big(const __grid_c
     const int pitch = (int)A.img.pitch;
     const int count = A.misc[kMiscClassCount + CLS];
     const int *list = A.class_list + (size_t)CLS * A.list_stride;
-    // per-CTA global scratch: the n x n window, then the n x 21 row sums
-    unsigned char *g_win = A.win_scratch + (size_t)blockIdx.x * kBigScratchBytes;
-    float *g_buf = reinterpret_cast<float *>(g_win + (size_t)kMaxWindow * kMaxWindow);
     const uint32_t bar0 = (uint32_t)__cvta_generic_to_shared(&s_bar[0]);
     if (tid == 0) {
         mbar_init(bar0, 1);
@@ -1112,23 +1062,38 @@ __global__ void __launch_bounds__(BigT::threads) k_descriptor_big(const __grid_c
         const int isc = __double2int_rn(scale);
         const bool int_scale = fabs(scale - isc) < DBL_EPSILON;
         if (!int_scale && warp == NW - 1 && lane < kPatch) area_tab_entry(S.tab, lane, n, scale);
-        __syncthreads();  // row starts visible
+        __syncthreads();  // row starts and the resize table are visible
         int next_item = 0;    // fetched under the taps, published after them (see k_descriptor)
         if (tid == THREADS - 32) next_item = atomicAdd(A.misc + kMiscClassHead + CLS, 1);
 
-        // ---- sub-windows of at most kSubSide x kSubSide taps, each with its own image tile ----
-        const int q = (n + kSubSide - 1) / kSubSide;
-        const int sw = (n + q - 1) / q;
-        const int n_sub = q * q;
-        // bounding box (tile origin) of sub-window `sub`; exact row starts are known here
+        // ---- sub-window grid: qy row blocks of sh rows, qx column groups of cpg cells ----
+        const int qy = (n + kSubSide - 1) / kSubSide;
+        const int sh = (n + qy - 1) / qy;
+        // a group of c cells spans at most c * scale + 2 source pixels (integer scales: exactly c * isc)
+        const int cpg = int_scale ? max(1, kSubSide / isc) : max(1, (int)((kSubSide - 2) / scale));
+        const int qx = (kPatch + cpg - 1) / cpg;
+        const int n_sub = qy * qx;
+        auto group_cols = [&](int gj, int &d0, int &d1, int &j0, int &j1) {  // cells [d0, d1) = source columns [j0, j1)
+            d0 = gj * cpg;
+            d1 = min(kPatch, d0 + cpg);
+            if (int_scale) {
+                j0 = d0 * isc;
+                j1 = d1 * isc;
+            } else {
+                j0 = S.tab.start[d0];
+                j1 = S.tab.start[d1 - 1] + S.tab.count[d1 - 1];
+            }
+        };
         const bool fixed_ok = !A.upright && !S.inexact && fix32_exact(cd) && fix32_exact(sd);
         const long long cdq = fixed_ok ? fix32(cd) : 0, sdq = fixed_ok ? fix32(sd) : 0;
-        auto sub_box = [&](int sub, int &i0, int &i1, int &j0, int &j1, int &tx0a, int &ty0, bool &fits, bool &interior) {
-            const int si = sub / q, sj = sub - si * q;
-            i0 = si * sw; i1 = min(n, i0 + sw);
-            j0 = sj * sw; j1 = min(n, j0 + sw);
-            int tx0, tx1, ty1;
-            interior = false;
+        // every sub-window's tile origin, once per keypoint: thread t works out sub-window t (fp64 extremes of its taps)
+        if (tid < n_sub && tid < BigT::max_sub) {
+            const int si = tid / qx, gj = tid - si * qx;
+            const int i0 = si * sh, i1 = min(n, i0 + sh);
+            int d0, d1, j0, j1;
+            group_cols(gj, d0, d1, j0, j1);
+            int tx0, tx1, ty0, ty1;
+            bool inside = false;
             if (A.upright) {
                 // window pixel (i, j) = frame (clamp(ux0 + i), clamp(uy0 - j))
                 tx0 = min(max(ux0 + i0, 0), W - 1);
@@ -1147,32 +1112,33 @@ __global__ void __launch_bounds__(BigT::threads) k_descriptor_big(const __grid_c
                 // four neighbours inside the frame
                 const int bx0 = __double2int_rd(minx), bx1 = __double2int_rd(maxx) + 1;
                 const int by0 = __double2int_rd(miny), by1 = __double2int_rd(maxy) + 1;
-                interior = bx0 >= 0 && by0 >= 0 && bx1 <= W - 1 && by1 <= H - 1;
+                inside = bx0 >= 0 && by0 >= 0 && bx1 <= W - 1 && by1 <= H - 1;
                 tx0 = min(max(bx0, 0), W - 1);
                 tx1 = min(max(bx1, 0), W - 1);
                 ty0 = min(max(by0, 0), H - 1);
                 ty1 = min(max(by1, 0), H - 1);
             }
-            tx0a = tx0 & ~15;
-            fits = (tx1 - tx0a + 1 <= tp) && (ty1 - ty0 + 1 <= tr);
-        };
-        // every sub-window's tile origin, once per keypoint: thread t works out sub-window t (fp64 extremes of its taps)
-        // and the tap loops below only read three words per sub-window
-        if (tid < n_sub) {
-            int i0, i1, j0, j1, tx0a, ty0;
-            bool fits, inside;
-            sub_box(tid, i0, i1, j0, j1, tx0a, ty0, fits, inside);
+            const int tx0a = tx0 & ~15;
+            const bool fits = (tx1 - tx0a + 1 <= tp) && (ty1 - ty0 + 1 <= tr) && (j1 - j0 <= kSubSide) && (i1 - i0 <= kSubSide);
             s_sub[tid] = make_int4(tx0a, ty0, (fits ? 1 : 0) | (inside ? 2 : 0), 0);
         }
         __syncthreads();
-        bool bad = false;
-        if (use_tma && tid == 0)  // prologue: first tile
+        const bool too_many = n_sub > BigT::max_sub;  // cannot happen for n <= kMaxWindow; reported, nothing loaded
+        bool bad = too_many;
+        // the two cells of the 21 x 21 output this thread owns: p0 = tid, p1 = tid + THREADS
+        float acc0 = 0.f, acc1 = 0.f;
+        int iacc0 = 0, iacc1 = 0;
+        if (use_tma && tid == 0 && !too_many)  // prologue: first tile
             tma_load_tile(&imap, (uint32_t)__cvta_generic_to_shared(s_tile0), s_sub[0].x, s_sub[0].y, b, bar0, BigT::tile_bytes);
-        for (int sub = 0; sub < n_sub; sub++) {
+        // (a sub-window that does not fit its tile is skipped but the loop goes on: every tile that was requested is
+        // awaited, or the barrier phases of the next keypoint would be off by one)
+        for (int sub = 0; sub < (too_many ? 0 : n_sub); sub++) {
             const int cur = sub & 1;
             unsigned char *tile = s_tile0 + cur * BigT::tile_stride;
-            const int si = sub / q, sj = sub - si * q;
-            const int i0 = si * sw, i1 = min(n, i0 + sw), j0 = sj * sw, j1 = min(n, j0 + sw);
+            const int si = sub / qx, gj = sub - si * qx;
+            const int i0 = si * sh, i1 = min(n, i0 + sh);
+            int d0, d1, j0, j1;
+            group_cols(gj, d0, d1, j0, j1);
             const int4 sb = s_sub[sub];
             const int tx0a = sb.x, ty0 = sb.y;
             const bool fits = (sb.z & 1) != 0, interior = (sb.z & 2) != 0;
@@ -1188,6 +1154,7 @@ __global__ void __launch_bounds__(BigT::threads) k_descriptor_big(const __grid_c
                 copy_tile_fallback<NW, tp>(A, img, pitch, tile, tx0a, tx1, ty0, min(tr, H - ty0));
                 __syncthreads();
             }
+            // ---- taps of rows [i0, i1) x columns [j0, j1) -> s_blk[(i - i0) * kSubSide + (j - j0)] ----
             auto SRC = [&](int o) -> unsigned { return (unsigned)tile[o]; };
             if (fits) {
                 if (A.upright) {
@@ -1195,15 +1162,17 @@ __global__ void __launch_bounds__(BigT::threads) k_descriptor_big(const __grid_c
                         const int x = min(max(ux0 + i, 0), W - 1) - tx0a;
                         for (int j = j0 + lane; j < j1; j += 32) {
                             const int y = min(max(uy0 - j, 0), H - 1) - ty0;
-                            g_win[i * n + j] = (unsigned char)SRC(y * tp + x);
+                            s_blk[(i - i0) * kSubSide + (j - j0)] = (unsigned char)SRC(y * tp + x);
                         }
                     }
                 } else if (fixed_ok) {
                     const uint32_t tile_addr = tile0_addr + cur * BigT::tile_stride;
+                    // the tap routine addresses its output as base + i * pitch + j: bias the base by the block origin
+                    const uint32_t out_addr = blk_addr - (uint32_t)(i0 * kSubSide + j0);
                     if (interior)
-                        window_taps_fixed<tp, NW, false, true>(n, i0, i1, j0, j1, s_rsx, s_rsy, cdq, sdq, tile_addr, tx0a, ty0, W, H, 0, g_win);
+                        window_taps_fixed<tp, NW, false, false>(kSubSide, i0, i1, j0, j1, s_rsx, s_rsy, cdq, sdq, tile_addr, tx0a, ty0, W, H, out_addr, nullptr);
                     else
-                        window_taps_fixed<tp, NW, true, true>(n, i0, i1, j0, j1, s_rsx, s_rsy, cdq, sdq, tile_addr, tx0a, ty0, W, H, 0, g_win);
+                        window_taps_fixed<tp, NW, true, false>(kSubSide, i0, i1, j0, j1, s_rsx, s_rsy, cdq, sdq, tile_addr, tx0a, ty0, W, H, out_addr, nullptr);
                 } else {
                     const int lj = lane & 7, li = lane >> 3;  // 4 rows x 8 columns per warp
                     const double lane_dx = (double)(j0 + lj) * (double)cd, lane_dy = (double)(j0 + lj) * (double)sd;
@@ -1211,18 +1180,96 @@ __global__ void __launch_bounds__(BigT::threads) k_descriptor_big(const __grid_c
                     for (int i = i0 + warp * 4 + li; i < i1; i += NW * 4) {
                         double fx = (double)s_rsx[i] + lane_dx;
                         double fy = (double)s_rsy[i] - lane_dy;
-                        unsigned char *wrow = g_win + (size_t)i * n;
+                        unsigned char *wrow = s_blk + (i - i0) * kSubSide - j0;
                         for (int j = j0 + lj; j < j1; j += 8, fx += step_x, fy -= step_y)
                             wrow[j] = (unsigned char)rotated_tap(fx, fy, W, H, tx0a, ty0, tp, SRC);
                     }
                 }
             }
-            __syncthreads();  // this buffer may be refilled (two iterations ahead) and g_win rows are complete
+            __syncthreads();  // the sub-window's taps are complete; this tile buffer may be refilled (two iterations ahead)
+            // ---- row sums of the cells [d0, d1) over the block's rows (the reference's horizontal pass) ----
+            const int nr = i1 - i0, nc = d1 - d0;
+            for (int t = tid; t < nr * nc; t += THREADS) {
+                const int r = t / nc, d = d0 + (t - r * nc);
+                if (int_scale) {
+                    const unsigned char *row = s_blk + r * kSubSide + (d * isc - j0);
+                    int a = 0;
+                    for (int u = 0; u < isc; u++) a += row[u];
+                    reinterpret_cast<int *>(s_rows)[r * kPatch + d] = a;
+                } else {
+                    const int xs = S.tab.start[d], xc = S.tab.count[d];
+                    const bool xhf = S.tab.has_first[d], xhl = S.tab.has_last[d];
+                    const float xaf = S.tab.a_first[d], xam = S.tab.a_mid[d], xal = S.tab.a_last[d];
+                    const unsigned char *row = s_blk + r * kSubSide + (xs - j0);
+                    const int fend = xc - (xhl ? 1 : 0);
+                    float bsum = 0;
+                    int f = 0;
+                    if (xhf) {
+                        bsum += u8f(row[0]) * xaf;
+                        f = 1;
+                    }
+#pragma unroll 4
+                    for (; f < fend; f++) bsum += u8f(row[f]) * xam;
+                    if (xhl) bsum += u8f(row[xc - 1]) * xal;
+                    s_rows[r * kPatch + d] = bsum;
+                }
+            }
+            if (gj == qx - 1) {
+                // ---- the row block is complete: fold its rows into the column accumulators, rows in increasing order ----
+                __syncthreads();
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    const int p = tid + h * THREADS;
+                    if (p < kPatchPx) {
+                        const int dy = p / kPatch, dx = p - dy * kPatch;
+                        if (int_scale) {
+                            int a = h ? iacc1 : iacc0;
+                            const int lo = max(dy * isc, i0), hi = min(dy * isc + isc, i1);
+                            for (int sy = lo; sy < hi; sy++) a += reinterpret_cast<const int *>(s_rows)[(sy - i0) * kPatch + dx];
+                            if (h) iacc1 = a; else iacc0 = a;
+                        } else {
+                            const int ys = S.tab.start[dy], yc = S.tab.count[dy];
+                            const bool yhf = S.tab.has_first[dy], yhl = S.tab.has_last[dy];
+                            const float yaf = S.tab.a_first[dy], yam = S.tab.a_mid[dy], yal = S.tab.a_last[dy];
+                            float a = h ? acc1 : acc0;
+                            const int lo = max(ys, i0), hi = min(ys + yc, i1);
+                            for (int sy = lo; sy < hi; sy++) {
+                                const int e = sy - ys;
+                                const float beta = (e == 0 && yhf) ? yaf : ((e == yc - 1 && yhl) ? yal : yam);
+                                const float bv = s_rows[(sy - i0) * kPatch + dx];
+                                if (e == 0) a = beta * bv; else a += beta * bv;
+                            }
+                            if (h) acc1 = a; else acc0 = a;
+                        }
+                    }
+                }
+            }
+            __syncthreads();  // s_blk / s_rows may be overwritten by the next sub-window
         }
         if (bad && tid == 0) atomicOr(A.misc + kMiscStatus, 2);
         if (tid == THREADS - 32) S.next = next_item;
         if (tid == 0) ring.kidx[pending] = kidx;
-        descriptor_tail<THREADS, 0>(A, kidx, n, g_win, g_buf, 0, 0, S, int_scale, isc, ring.patch[pending]);
+        // ---- the 21 x 21 patch ----
+        unsigned char *patch = ring.patch[pending];
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const int p = tid + h * THREADS;
+            if (p < kPatchPx) {
+                int outv;
+                if (int_scale) {
+                    const float wgt = 1.f / (isc * isc);
+                    outv = sat_u8((h ? iacc1 : iacc0) * wgt);
+                } else {
+                    outv = sat_u8(h ? acc1 : acc0);
+                }
+                patch[p] = (unsigned char)outv;
+            }
+        }
+        __syncthreads();  // the patch (a slot of the CTA's ring) is complete
+        if (A.patches) {
+            unsigned char *po = A.patches + (size_t)kidx * kPatchPx;
+            for (int p = tid; p < kPatchPx; p += THREADS) po[p] = patch[p];
+        }
         if (A.desc && ++pending == kRing) {
             ring_flush<NW>(A, ring, pending);
             pending = 0;
@@ -1268,7 +1315,6 @@ void setup_big(ClassCfg &c, int sms)
     int per_sm = 1;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_descriptor_big, BigT::threads, c.smem);
     if (per_sm < 1) per_sm = 1;
-    if (per_sm > kClassDGridPerSm) per_sm = kClassDGridPerSm;  // bounds the global window scratch
     c.grid = sms * per_sm;
 }
 
@@ -1307,8 +1353,6 @@ void describe_tile_box(int cls, int *pitch_bytes, int *rows)
     *pitch_bytes = tp[cls];
     *rows = tr[cls];
 }
-
-size_t describe_scratch_bytes() { return (size_t)dev_cfg().cls[kNumClasses - 1].grid * kBigScratchBytes; }
 
 void launch_describe(const DescribeArgs &a, const CUtensorMap *imaps, int use_tma, cudaStream_t st, int *launches)
 {

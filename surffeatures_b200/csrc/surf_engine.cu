@@ -359,7 +359,7 @@ void free_workspace(surf_engine *e)
         o.d_kp = nullptr; o.d_desc = nullptr; o.d_off = nullptr; o.h_pin = nullptr;
         o.active = o.collected = false;
     }
-    cudaFree(e->d_match_part); cudaFree(e->d_match_io); cudaFree(e->d_class_list); cudaFree(e->d_win_scratch); cudaFree(e->d_sincos);
+    cudaFree(e->d_match_part); cudaFree(e->d_match_io); cudaFree(e->d_class_list); cudaFree(e->d_sincos);
     for (auto &w : e->tc) {
         cudaFree(w.pool.hi); cudaFree(w.pool.lo); cudaFree(w.pool.norm); cudaFree(w.pool.max_norm);
         cudaFree(w.pool.count); cudaFree(w.cand); cudaFree(w.redo); cudaFree(w.counters); cudaFree(w.segs);
@@ -376,7 +376,7 @@ void free_workspace(surf_engine *e)
     e->d_kp_a = e->d_kp_b = e->d_out_kp = nullptr; e->d_desc = e->d_out_desc = nullptr; e->d_patches = nullptr;
     e->d_counts = e->d_ndel = e->d_off_in = e->d_off_out = e->d_misc = e->d_deleted = nullptr;
     e->d_match_part = nullptr; e->d_match_io = nullptr; e->h_pin = nullptr; e->d_class_list = nullptr;
-    e->d_win_scratch = nullptr; e->d_sincos = nullptr;
+    e->d_sincos = nullptr;
     e->match_part_cap = e->match_io_cap = 0;
 }
 
@@ -433,7 +433,6 @@ int alloc_workspace(surf_engine *e)
     CU(e, cudaMalloc(&e->d_off_in, sizeof(int) * (B + 1)));
     CU(e, cudaMalloc(&e->d_misc, sizeof(int) * kMiscWords));
     CU(e, cudaMalloc(&e->d_class_list, nk * kNumClasses * sizeof(int)));
-    CU(e, cudaMalloc(&e->d_win_scratch, describe_scratch_bytes()));
     CU(e, cudaMalloc(&e->d_sincos, nk * sizeof(float2)));
     int rc = alloc_det_and_desc(e);
     bind_out(e, 0);
@@ -649,7 +648,6 @@ int run_describe_pack(surf_engine *e, const ImageRef &img, const FrameGeo &geo, 
     a.deleted_slots = e->d_deleted;
     a.class_list = e->d_class_list;
     a.list_stride = (size_t)e->max_b * e->cap;
-    a.win_scratch = e->d_win_scratch;
     a.sincos = e->d_sincos;
     ensure_image_maps(e, img, geo, B);
     launch_describe(a, e->imap, e->imap_ok ? 1 : 0, e->stream, &e->launches);

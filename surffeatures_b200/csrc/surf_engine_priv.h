@@ -122,7 +122,6 @@ struct surf_engine {
     uint8_t *d_patches = nullptr;
     int *d_counts = nullptr, *d_ndel = nullptr, *d_off_in = nullptr, *d_off_out = nullptr, *d_misc = nullptr;
     int *d_deleted = nullptr, *d_class_list = nullptr;
-    uint8_t *d_win_scratch = nullptr;
     float2 *d_sincos = nullptr;
     int *h_pin = nullptr;  // alias of out[out_bound].h_pin (as are d_out_kp, d_out_desc, d_off_out)
     surf_dmatch *d_match_part = nullptr;  size_t match_part_cap = 0;

@@ -80,11 +80,9 @@ struct ImageRef {
 // Descriptor windows are handled by size class (window side n = (int)(21 * size * 1.2 / 9)).  Classes 0-2
 // (n <= 64 / 96 / 128) stage the rotated window's whole bounding box and the window itself in shared memory;
 // the last class (n > 128) cuts the window into sub-windows of at most 96 x 96 taps, each with its own
-// image tile, and keeps the window in a per-CTA global scratch buffer.
+// image tile, and streams their INTER_AREA row sums through shared memory (the window is never materialised).
 constexpr int kNumClasses = 4;
 constexpr int kClassMaxN0 = 64, kClassMaxN1 = 96, kClassMaxN2 = 128;  // last class: up to kMaxWindow
-constexpr int kClassDGridPerSm = 4;  // persistent CTAs per SM of the sub-window kernel (measured: 2 -> 5.01 ms, 3 -> 4.93, 4 -> 4.90 per describe stage)
-constexpr size_t kBigScratchBytes = (size_t)kMaxWindow * kMaxWindow + (size_t)kMaxWindow * kPatch * sizeof(float);
 
 // d_misc word layout
 constexpr int kMiscStatus = 1;
@@ -110,11 +108,9 @@ struct DescribeArgs {
     int *deleted_slots;   // [B][cap]
     int *class_list;      // [kNumClasses][list_stride]: keypoint index b * cap + slot
     size_t list_stride;
-    uint8_t *win_scratch; // class D windows: [grid][kMaxWindow * kMaxWindow]
     float2 *sincos;       // [B][cap]: (-sin, cos) of the dominant angle, written by k_orient
 };
 
-size_t describe_scratch_bytes();  // size of win_scratch for the current device
 
 // ---- launchers (surf_kernels.cu) ----
 int integral_band_rows(int W);

@@ -170,6 +170,41 @@ def test_big_keypoints_unstaged_window_path(eng, oracle):
     assert np.abs(gdesc - odesc).max() <= 1e-6
 
 
+@pytest.mark.parametrize("upright", [False, True])
+def test_big_windows_every_resize_path(oracle, upright):
+    """Windows wider than 128 pixels are streamed: sub-windows of taps -> row sums of whole INTER_AREA cells -> column
+    accumulators.  Given keypoints whose window sides cover the integer scales (multiples of 21), fractional scales up to
+    the largest window (739), cell groups of every width, and centres in the frame's interior, on its border and in its
+    corners (clamped taps); patches byte for byte, angles bit for bit."""
+    from surffeatures_b200 import KEYPOINT_DTYPE, SURF
+
+    img = speckle.speckle_frame(480, 640, 77, blobs=8)
+    sides = [129, 130, 146, 147, 148, 160, 168, 189, 191, 192, 193, 210, 231, 255, 288, 289, 300, 336, 384, 385, 420, 441,
+             500, 577, 640, 700, 739]
+    centres = [(320.3, 240.6), (30.2, 40.9), (600.7, 441.1), (12.5, 300.0), (333.3, 470.2)]
+    kps = np.zeros(len(sides) * len(centres), KEYPOINT_DTYPE)
+    i = 0
+    for n in sides:
+        for (x, y) in centres:
+            kps[i] = (x, y, (n + 0.4) * 9.0 / (21 * 1.2), -1.0, 500.0, 2, 1)
+            i += 1
+    got_sides = (np.float32(21) * (kps["size"] * np.float32(1.2) / np.float32(9.0))).astype(np.int32)
+    assert set(sides) <= set(got_sides.tolist())          # the sizes hit the intended window sides, 147 = 7 * 21 etc.
+    p = oracle.params(100, 4, 3, False, upright)
+    okp, odesc, opatch = oracle.describe(img, p, kps, want_patches=True)
+    e = SURF(100, 4, 3, False, upright, max_width=640, max_height=480, max_keypoints=4096)
+    try:
+        gkp, gdesc, gpatch = e.describe_keypoints(img, kps, want_patches=True)
+    finally:
+        e.close()
+    alive = okp["size"] > 0
+    assert alive.sum() >= 0.8 * len(kps)
+    assert np.array_equal(gkp["size"] > 0, alive)
+    assert np.array_equal(gkp["angle"][alive], okp["angle"][alive])
+    assert np.array_equal(gpatch[alive], opatch[alive])
+    assert np.abs(gdesc[alive] - odesc[alive]).max() <= 1e-6
+
+
 @pytest.mark.parametrize("extended,upright", [(False, False), (True, False), (False, True), (True, True)])
 def test_detect_and_compute_variants(oracle, frame640, extended, upright):
     from surffeatures_b200 import SURF
