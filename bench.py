@@ -663,7 +663,7 @@ def run_ours(args):
          "ms": stage_ms["hessian"]},
         {"stage": "sort", "kernels": "k_sort_chunks+k_merge_pass", "bound": "hbm",
          "algorithmic_bytes": 2 * 28 * kp_per_frame * B, "ms": stage_ms["sort"]},
-        {"stage": "describe", "kernels": "k_orient+k_descriptor<0..2>+k_descriptor_big+k_patch_descriptor", "bound": "hbm",
+        {"stage": "describe", "kernels": "k_orient+k_descriptor<0..2>+k_descriptor_big", "bound": "hbm",
          "algorithmic_bytes": alg["describe"] * B, "ms": stage_ms["describe"]},
     ]
     for s in stages:
@@ -750,10 +750,11 @@ def run_ours(args):
     return 0
 
 
-# from profiles/r1/describe_stage_v25_ncu_summary.txt (ncu --set full of this command, batch 64): 323.9 MB read + 105.0 MB
-# written by k_orient + the four window kernels + four k_patch_descriptor launches, 4.42 G warp instructions
-NCU_DESCRIBE_TRAFFIC, NCU_DESCRIBE_INST = 428.9e6, 4.42e9
-NCU_SOURCE = "profiles/r1/describe_stage_v25_ncu_summary.txt"
+# from profiles/r2/describe_stage_v4_ncu_summary.txt (ncu --set full of this command, batch 64, same kernels as HEAD):
+# k_orient + the four window kernels (the patch -> descriptor step now runs inside them): 189.0 MB read + 14.4 MB written,
+# 4.24 G warp instructions.  Round 1: 428.9 MB and 4.42 G.
+NCU_DESCRIBE_TRAFFIC, NCU_DESCRIBE_INST = 203.4e6, 4.243e9
+NCU_SOURCE = "profiles/r2/describe_stage_v4_ncu_summary.txt"
 
 
 def cpu_baseline_leg(pool: np.ndarray):

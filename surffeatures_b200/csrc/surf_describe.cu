@@ -1189,8 +1189,9 @@ __global__ void __launch_bounds__(BigT::threads, 3) k_descriptor_big(const __gri
             __syncthreads();  // the sub-window's taps are complete; this tile buffer may be refilled (two iterations ahead)
             // ---- row sums of the cells [d0, d1) over the block's rows (the reference's horizontal pass) ----
             const int nr = i1 - i0, nc = d1 - d0;
+            const unsigned nc_inv = (65536u + nc - 1) / nc;  // t / nc == (t * nc_inv) >> 16 for t <= 96 * 21 (checked exhaustively)
             for (int t = tid; t < nr * nc; t += THREADS) {
-                const int r = t / nc, d = d0 + (t - r * nc);
+                const int r = (int)(((unsigned)t * nc_inv) >> 16), d = d0 + (t - r * nc);
                 if (int_scale) {
                     const unsigned char *row = s_blk + r * kSubSide + (d * isc - j0);
                     int a = 0;
@@ -1205,12 +1206,12 @@ __global__ void __launch_bounds__(BigT::threads, 3) k_descriptor_big(const __gri
                     float bsum = 0;
                     int f = 0;
                     if (xhf) {
-                        bsum += u8f(row[0]) * xaf;
+                        bsum += tap_u8f(row[0]) * xaf;
                         f = 1;
                     }
 #pragma unroll 4
-                    for (; f < fend; f++) bsum += u8f(row[f]) * xam;
-                    if (xhl) bsum += u8f(row[xc - 1]) * xal;
+                    for (; f < fend; f++) bsum += tap_u8f(row[f]) * xam;
+                    if (xhl) bsum += tap_u8f(row[xc - 1]) * xal;
                     s_rows[r * kPatch + d] = bsum;
                 }
             }

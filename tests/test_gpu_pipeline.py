@@ -313,3 +313,43 @@ def test_one_rank_nccl_communicator_runs_the_exchange_code(sweep_setup):
             db.close()
     finally:
         comm.close()
+
+
+def test_results_do_not_depend_on_batch_composition_or_repetition():
+    """compute-sanitizer is closed on the GPU pool (profiles/r2/compute_sanitizer_closed.log), so races are hunted the
+    other way round: a frame's bytes must not depend on which batch it rides in, on its position in the batch, on what
+    else the GPU is doing (look-ahead of another batch, matcher on its own stream), or on how often the call is
+    repeated.  Shared-memory races in the fused Hessian tiles, the descriptor CTAs' ring and the atomic work queues
+    would show up as a keypoint order or a descriptor bit that differs between runs."""
+    import torch
+
+    from surffeatures_b200 import MEM_DEVICE, SURF
+
+    W, H = 320, 240
+    frames = np.stack([speckle.speckle_frame(H, W, 50 + i, blobs=4 if i % 3 == 0 else 0) for i in range(12)])
+    e = SURF(100, 4, 3, max_width=W, max_height=H, max_batch=12, max_keypoints=4096)
+    try:
+        single = [e.detectAndCompute(f) for f in frames]
+        for rep in range(6):
+            order = np.random.default_rng(rep).permutation(12)
+            B = (12, 6, 4, 3, 5, 7)[rep]
+            for lo in range(0, 12, B):
+                idx = order[lo:lo + B]
+                d_frames = torch.from_numpy(frames[idx]).cuda()
+                nxt = torch.from_numpy(frames[order[:len(idx)]]).cuda()
+                e.submit(d_frames.data_ptr(), MEM_DEVICE, len(idx), W, H, W, W * H, True)
+                e.lookahead(nxt.data_ptr(), MEM_DEVICE, len(idx), W, H, W, W * H)   # competing work on the look-ahead stream
+                cap = len(idx) * 4096
+                k = torch.zeros((cap, 7), dtype=torch.float32).pin_memory()
+                d = torch.zeros((cap, 64)).pin_memory()
+                off = np.zeros(len(idx) + 1, np.int32)
+                e.collect(k.data_ptr(), d.data_ptr(), 0, cap, off)
+                e.match_prev_device(0.8)
+                for j, f in enumerate(idx):
+                    sk, sd = single[f]
+                    assert off[j + 1] - off[j] == len(sk), (rep, f)
+                    assert k.numpy()[off[j]:off[j + 1]].tobytes() == sk.tobytes(), (rep, f)
+                    assert np.array_equal(d.numpy()[off[j]:off[j + 1]], sd), (rep, f)
+        e.sync()
+    finally:
+        e.close()
