@@ -493,7 +493,9 @@ def measure_latency(ctx: Ctx, eng, frames: np.ndarray, D: int, reps: int = 30):
         out[f"batch{nb}"] = {"ms_per_call_median": float(np.median(ts)), "ms_p10": float(np.quantile(ts, 0.1)),
                              "ms_p90": float(np.quantile(ts, 0.9)), "ms_per_frame": float(np.median(ts) / nb),
                              "frames_per_s": float(nb / np.median(ts) * 1e3), "keypoints": int(off[nb]),
-                             "launches_per_call": int(eng.timings()["launches"])}
+                             "launches_per_call": int(eng.timings()["launches"]),
+                             "device_stage_ms": {k: round(float(v), 4) for k, v in eng.timings().items()
+                                                 if k in ("h2d", "integral", "hessian", "sort", "describe", "pack", "d2h", "total")}}
     return out
 
 
@@ -700,36 +702,17 @@ def run_ours(args):
         latency = measure_latency(ctx, eng, pool[:16], D)
     ctx.barrier()
 
-    extras = {}
-    if not args.no_extras:
-        comm_factory = Comm.from_torch
-        for name, fn in (("config3", lambda: run_config3(ctx)),
-                         ("config4", lambda: run_config4(ctx, comm_factory, args.sweep_frames)),
-                         ("config5", lambda: run_config5(ctx, comm_factory))):
-            if args.only_extra and name != args.only_extra:
-                continue
-            try:
-                extras[name] = fn()
-            except Exception as ex:   # an extra must not take the headline down with it (recorded, not hidden)
-                extras[name] = {"error": f"{type(ex).__name__}: {ex}"}
-                # a failed collective cannot be resynchronised: leave the remaining multi-rank extras alone
-                if ctx.world > 1:
-                    break
-            ctx.barrier()
-
-    cpu_baseline = None
-    if ctx.rank == 0 and ctx.world == 1 and not args.no_cpu:
-        cpu_baseline = cpu_baseline_leg(pool)
-
-    if ctx.rank == 0:
-        line = {
+    def make_line(extras, cpu_baseline):
+        return {
             "metric": _metric(), "value": fps, "unit": "frames/s", "n_gpus": ctx.world, "steps": steps, "warmup": warmup,
             "ms_per_step": ms_dev / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u8/int32/f32", "data": "synthetic",
             "config": workload_config(B),
             "notes": {"frames_per_step_all_gpus": B * ctx.world, "sharding": "frames sharded by rank, no data-path collective "
                       "(config 2 does not shard below a frame: replicas); configs 4 and 5 below use NCCL",
-                      "lookahead": bool(sb.lookahead), "two_batches_in_flight": True, "e2e_diag": E2E_DIAG or None, "host_affinity": ctx.affinity, "library": os.environ.get("SURF_B200_LIB", "surffeatures_b200/libsurf_b200.so")},
+                      "lookahead": bool(sb.lookahead), "two_batches_in_flight": True, "e2e_diag": E2E_DIAG or None,
+                      "host_affinity": ctx.affinity,
+                      "library": os.environ.get("SURF_B200_LIB", "surffeatures_b200/libsurf_b200.so")},
             "e2e": {"value": fps_e2e, "unit": "frames/s", "h2d_bytes_per_step": sb.bytes_io["h2d"],
                     "d2h_bytes_per_step": sb.bytes_io["d2h"], "ms_per_step": ms_e2e / steps},
             "gpu_launches": n_launch, "keypoints_per_frame": kp_per_frame,
@@ -740,7 +723,51 @@ def run_ours(args):
             "latency": latency, "latency_ms_batch1": latency["batch1"]["ms_per_call_median"] if latency else None,
             "configs": extras, "cpu_baseline": cpu_baseline, "clocks": clocks,
         }
-        print(json.dumps(line), flush=True)
+
+    extras = {}
+    if not args.no_extras:
+        comm_factory = Comm.from_torch
+        # The extras run collectives; a rank that fails inside one would leave the others waiting forever and take the
+        # headline down with it.  A watchdog bounds them: when it fires, rank 0 prints the line with what is done so far
+        # and every rank leaves at once (the one case in which the process does not shut down in order).
+        done = threading.Event()
+
+        def bail():
+            if done.is_set():
+                return
+            if ctx.rank == 0:
+                extras.setdefault("error", f"extras did not finish within {args.extras_timeout} s")
+                print(json.dumps(make_line(extras, None)), flush=True)
+            os._exit(0)
+
+        dog = threading.Timer(args.extras_timeout, bail)
+        dog.daemon = True
+        dog.start()
+        for name, fn in (("config3", lambda: run_config3(ctx)),
+                         ("config4", lambda: run_config4(ctx, comm_factory, args.sweep_frames)),
+                         ("config5", lambda: run_config5(ctx, comm_factory))):
+            if args.only_extra and name != args.only_extra:
+                continue
+            failed = 0.0
+            try:
+                extras[name] = fn()
+            except Exception as ex:   # an extra must not take the headline down with it (recorded, not hidden)
+                extras[name] = {"error": f"{type(ex).__name__}: {ex}"}
+                failed = 1.0
+            # every rank learns whether any rank failed: the remaining multi-rank extras are skipped by all or by none
+            if ctx.max_over_ranks(failed) > 0:
+                extras.setdefault(name, {"error": "another rank failed"})
+                break
+            ctx.barrier()
+        done.set()
+        dog.cancel()
+
+    cpu_baseline = None
+    if ctx.rank == 0 and ctx.world == 1 and not args.no_cpu:
+        cpu_baseline = cpu_baseline_leg(pool)
+
+    if ctx.rank == 0:
+        print(json.dumps(make_line(extras, cpu_baseline)), flush=True)
     # orderly shutdown: engine first (its streams and events), then the process group; no os._exit
     eng.close()
     torch.cuda.synchronize()
@@ -793,6 +820,7 @@ def main():
     ap.add_argument("--no-extras", action="store_true", help="headline only: no latency table, no configs 3/4/5")
     ap.add_argument("--only-extra", default="", help="run only this extra (config3|config4|config5)")
     ap.add_argument("--sweep-frames", type=int, default=4096, help="slices of the config-4 sweep")
+    ap.add_argument("--extras-timeout", type=float, default=420.0, help="watchdog of the configs 3/4/5 section, seconds")
     ap.add_argument("--dev-lib", action="store_true", help="allow SURF_B200_LIB (development A/B builds)")
     args = ap.parse_args()
     if args.impl == "reference":
