@@ -26,29 +26,58 @@ import numpy as np
 import cv2
 d = np.load(sys.argv[1])
 mats = [d[k] for k in sorted(d.files) if k.startswith("m")]
-bf = cv2.BFMatcher(cv2.NORM_L2)
-bf.add(mats)
-ref = bf.knnMatch(d["q"], k=3)
-print(json.dumps([[(m.imgIdx, m.trainIdx, float(m.distance)) for m in row] for row in ref]))
+q = d["q"]
+cv2.setNumThreads(1)
+
+
+def self_consistent(ref):
+    # every (imgIdx, trainIdx, distance) cv2 reports must describe a row at that distance
+    for i, row in enumerate(ref):
+        for m in row:
+            if not (0 <= m.imgIdx < len(mats) and 0 <= m.trainIdx < len(mats[m.imgIdx])):
+                return False
+            true = float(np.sqrt(((q[i].astype(np.float64) - mats[m.imgIdx][m.trainIdx]) ** 2).sum()))
+            if abs(true - m.distance) > 1e-5:
+                return False
+    return True
+
+
+for attempt in range(20):
+    bf = cv2.BFMatcher(cv2.NORM_L2)
+    bf.add(mats)
+    ref = bf.knnMatch(q, k=3)
+    if self_consistent(ref):
+        print(json.dumps([[(m.imgIdx, m.trainIdx, float(m.distance)) for m in row] for row in ref]))
+        break
+else:
+    print(json.dumps(None))
 """
 
 
 def test_db_knn_equals_cv2_bfmatcher_add(oracle, tmp_path):
     """Genuine cv2.BFMatcher.add(list) + knnMatch.  cv2 runs in a fresh interpreter: with torch imported first in
     the same process (as other tests of this suite do) cv2 4.13's multi-image knnMatch returns wrong neighbours
-    here -- a library clash that has nothing to do with either side of this comparison."""
+    here -- a library clash that has nothing to do with either side of this comparison.  cv2 4.13's multi-image knnMatch
+    is also not repeatable on its own: about every other identical call reports, for one or two of the 200 queries,
+    the right distance with an (imgIdx, trainIdx) that is not the row at that distance (measured here, one thread or
+    eight).  The script therefore accepts a cv2 answer only if it is self-consistent -- every reported index is the
+    row at the reported distance -- and asks again otherwise.  Train images with fewer than k rows are left out of this
+    case: cv2 4.13 fills the missing neighbours of such an image from uninitialised memory (query 1 of a 1-row image came
+    back as distance 0.0 / row 0 in every call here); the oracle's handling of short images is covered below."""
     pytest.importorskip("cv2")
     import json
     import subprocess
     import sys
 
     rng = np.random.default_rng(0)
-    mats = [_unit_rows(rng, n) for n in (120, 1, 333, 64)]
+    mats = [_unit_rows(rng, n) for n in (120, 3, 333, 64)]  # every image >= k rows: see the docstring
     q = _unit_rows(rng, 200)
     npz = tmp_path / "case.npz"
     np.savez(npz, q=q, **{f"m{i}": m for i, m in enumerate(mats)})
     out = subprocess.run([sys.executable, "-c", _CV2_SCRIPT, str(npz)], capture_output=True, text=True, check=True).stdout
     ref = json.loads(out.strip().splitlines()[-1])
+    if ref is None:
+        pytest.skip("cv2's multi-image knnMatch contradicted itself in 20 of 20 calls on this machine")
     got = oracle.db_knn(q, mats, 3)
     for i, row in enumerate(ref):
         assert [m[0] for m in row] == list(got["imgIdx"][i])
@@ -62,6 +91,23 @@ def test_db_knn_ties_follow_add_order(oracle):
     b[3] = a[4]
     m = oracle.db_knn(a[4:5], [a, b], 2)
     assert list(zip(m["imgIdx"][0], m["trainIdx"][0])) == [(0, 4), (1, 3)]
+
+
+def test_db_knn_with_images_shorter_than_k(oracle):
+    """Images with fewer than k rows (the case cv2 4.13 cannot arbitrate): the database is the concatenation of its
+    images, so the k nearest rows are those of a stable fp64 argsort over all rows, whichever image they sit in."""
+    rng = np.random.default_rng(2)
+    mats = [_unit_rows(rng, n) for n in (120, 1, 333, 2, 64)]
+    q = _unit_rows(rng, 200)
+    got = oracle.db_knn(q, mats, 3)
+    allm = np.concatenate(mats).astype(np.float64)
+    d = ((q[:, None, :].astype(np.float64) - allm[None]) ** 2).sum(-1)
+    idx = np.argsort(d, axis=1, kind="stable")[:, :3]
+    off = np.cumsum([0] + [len(m) for m in mats])
+    img = np.searchsorted(off, idx, side="right") - 1
+    assert np.array_equal(got["imgIdx"], img)
+    assert np.array_equal(got["trainIdx"], idx - off[img])
+    assert np.allclose(got["distance"], np.sqrt(np.take_along_axis(d, idx, 1)), rtol=1e-6)
 
 
 # ---- literal transcription of the reference's Hough code (every variable a numpy float32 / python float = double)
