@@ -389,9 +389,52 @@ static inline uint8_t sat_u8(float v)
 /* cv::resize(win, patch, Size(21,21), 0, 0, INTER_AREA) for an n x n 8-bit window, n >= 21.
  * Three code paths of imgwarp.cpp: 2x integer (ResizeAreaFastVec), k x integer (ResizeAreaFast_),
  * fractional table (ResizeArea_).  SURVEY A5.4. */
+/* n < 21 (keypoints smaller than 7.9 px handed to compute()): cv::resize does not have a true area mode for
+ * enlargement; INTER_AREA then runs the bilinear code with its own coefficients (`area_mode` in imgwarp.cpp
+ * resize(): sx = floor(dx * scale), fx = (dx + 1) - (sx + 1) * inv_scale, fx <= 0 ? 0 : fx - floor(fx)), the 8-bit
+ * fixed-point kernels HResizeLinear (coefficients * 2048, int rows) and VResizeLinear
+ * ((b0 * (S0 >> 4) >> 16) + (b1 * (S1 >> 4) >> 16) + 2) >> 2.  Pinned against cv2 4.13 for every n = 1..20. */
+static void area_up_coef(int d, int n, double scale, double inv, int *s0, int *c0, int *c1)
+{
+    int sx = ifloor(d * scale);
+    float fx = (float)((d + 1) - (sx + 1) * inv);
+    fx = fx <= 0 ? 0.f : fx - (float)ifloor(fx);
+    if (sx >= n - 1) { /* sx + ksize/2 >= ssize: the last source pixel alone */
+        fx = 0;
+        sx = n - 1;
+    }
+    *s0 = sx;
+    *c0 = rnd((1.f - fx) * 2048);
+    *c1 = rnd(fx * 2048);
+}
+
+static void resize_area_up_21(const uint8_t *win, int n, uint8_t *patch)
+{
+    const double inv = (double)PATCH_W / n;
+    const double scale = 1. / inv;
+    int xs[PATCH_W], xa[PATCH_W], xb[PATCH_W];
+    for (int dx = 0; dx < PATCH_W; dx++) area_up_coef(dx, n, scale, inv, &xs[dx], &xa[dx], &xb[dx]);
+    for (int dy = 0; dy < PATCH_W; dy++) {
+        int sy, b0, b1;
+        area_up_coef(dy, n, scale, inv, &sy, &b0, &b1);
+        const uint8_t *r0 = win + (size_t)sy * n;
+        const uint8_t *r1 = win + (size_t)(sy + 1 < n ? sy + 1 : n - 1) * n;
+        for (int dx = 0; dx < PATCH_W; dx++) {
+            const int x0 = xs[dx], x1 = x0 + 1 < n ? x0 + 1 : x0; /* weight of x1 is 0 when it is clamped */
+            const int h0 = r0[x0] * xa[dx] + r0[x1] * xb[dx];
+            const int h1 = r1[x0] * xa[dx] + r1[x1] * xb[dx];
+            patch[dy * PATCH_W + dx] = (uint8_t)((((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2);
+        }
+    }
+}
+
 int orc_resize_area_21(const uint8_t *win, int n, uint8_t *patch)
 {
-    if (n < PATCH_W) return -1;
+    if (n < 1) return -1;
+    if (n < PATCH_W) {
+        resize_area_up_21(win, n, patch);
+        return 0;
+    }
     const double inv = (double)PATCH_W / n;
     const double scale = 1. / inv;
     const int isc = (int)lrint(scale);
@@ -532,7 +575,7 @@ static void describe_one(const uint8_t *img, int H, int W, int pitch, const int3
     if (!vec && !patch_out) return;
 
     const int n = (int)((PATCH_SZ + 1) * s);
-    if (n < PATCH_W) { /* up-scaling INTER_AREA is outside the restated path */
+    if (n < 1) { /* size < 0.36: upstream builds an empty window and cv::resize raises; the keypoint is deleted here */
         kp->size = -1;
         return;
     }

@@ -129,7 +129,7 @@ def resize_area_21(win):
     out = np.empty((21, 21), np.uint8)
     rc = lib().orc_resize_area_21(_ptr(win), win.shape[0], _ptr(out))
     if rc:
-        raise ValueError("window smaller than 21")
+        raise ValueError("empty window")
     return out
 
 

@@ -6,12 +6,19 @@ import sys
 
 rep = sys.argv[1]
 top = int(sys.argv[2]) if len(sys.argv) > 2 else 40
+only = sys.argv[3] if len(sys.argv) > 3 else ""  # substring of the kernel's function name, e.g. "k_descriptor<(int)0>"
 out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--print-source", "cuda,sass", "--csv"],
                      capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
 hdr = None
 data = {}
+fn_ok = True
 for r in rows:
+    if r and r[0] == "Function Name":
+        fn_ok = only in r[1]
+        continue
+    if not fn_ok:
+        continue
     if r and r[0] == "Line No":
         hdr = r
         ie, smp = hdr.index("Instructions Executed"), hdr.index("# Samples")

@@ -291,8 +291,8 @@ __global__ void __launch_bounds__(kOriWarps * 32) k_orient(const __grid_constant
         }
 
         const int n = (int)(21 * s);
-        if (!dead && want_desc && (n < kPatch || n > kMaxWindow)) {
-            // n < 21: up-scaling INTER_AREA is outside the restated path (the oracle deletes it too);
+        if (!dead && want_desc && (n < 1 || n > kMaxWindow)) {
+            // n < 1 (size < 0.36): upstream builds an empty window and cv::resize raises; deleted here, as the oracle does;
             // n > kMaxWindow: unsupported window, reported through the status word.
             if (n > kMaxWindow && lane == 0) atomicOr(A.misc + kMiscStatus, 1);
             dead = true;
@@ -433,9 +433,7 @@ __device__ __forceinline__ float tap_u8f(uint32_t v) { return __uint2float_rn(v)
 // float (multiple of 2^-32, |v| < 2^31) -> signed 32.32 fixed point, exact
 __device__ __forceinline__ long long fix32(float v) { return __double2ll_rn((double)v * 4294967296.0); }
 __device__ __forceinline__ bool fix32_exact(float v) { return v == 0.f || fabsf(v) >= 0.001953125f; }
-// the same test as an order-preserving key: (bits << 1) - 2 wraps 0 to the top, so fix32_exact(v) <=> key >= kFix32KeyMin
-__device__ __forceinline__ uint32_t fix32_key(float v) { return (__float_as_uint(v) << 1) - 2u; }
-constexpr uint32_t kFix32KeyMin = (0x3b000000u << 1) - 2u;  // 2^-9
+constexpr float kFix32Min = 0.001953125f;  // 2^-9
 
 // Interior tap: X's high word already carries (tile address - x0), Y's high word (-y0).
 template <int TP>
@@ -507,6 +505,24 @@ __device__ __forceinline__ uint32_t tap_fixed_checked(long long X, long long Y, 
     return lds_u8<0>(tile + (uint32_t)((y - y0) * TP + (x - x0)));
 }
 
+// Enlarging INTER_AREA (source axis of n < 21 pixels -> 21): cv::resize has no area mode for enlargement and runs its
+// bilinear code with the area-mode coefficients (imgwarp.cpp resize(): sx = floor(d * scale), fx = (d + 1) - (sx + 1) *
+// inv_scale, fx <= 0 ? 0 : fx - floor(fx)) in 8-bit fixed point: coefficients * 2048 (HResizeLinear), then
+// ((b0 * (S0 >> 4) >> 16) + (b1 * (S1 >> 4) >> 16) + 2) >> 2 (VResizeLinear).  The oracle pins this against cv2.
+__device__ __forceinline__ void area_up_coef(int d, int n, double scale, double inv, int &s0, int &c0, int &c1)
+{
+    int sx = __double2int_rd(d * scale);
+    float fx = (float)((d + 1) - (sx + 1) * inv);
+    fx = fx <= 0 ? 0.f : fx - floorf(fx);
+    if (sx >= n - 1) {  // the last source pixel alone
+        fx = 0;
+        sx = n - 1;
+    }
+    s0 = sx;
+    c0 = __float2int_rn((1.f - fx) * 2048.f);
+    c1 = __float2int_rn(fx * 2048.f);
+}
+
 // Rows [i0, i1) x columns [j0, j1) of the rotated window from the shared-memory frame tile at `tile`
 // (origin (x0, y0), pitch TP).  A warp covers 4 rows x 8 columns per step.  The window goes to shared memory
 // (win_s, GLOBAL = false) or to the per-CTA global scratch (win_g).
@@ -525,11 +541,18 @@ __device__ __forceinline__ void window_taps_fixed(int n, int i0, int i1, int j0,
 #if SURF_TAP_F32X2
     const uint64_t one2 = f2_pack(c_one2.x, c_one2.y);
 #endif
+    // Column groups of 16 (two taps per lane, 8 columns apart).  The last group may hold 9..15 columns: every lane
+    // still has its first tap, only lanes lj < rem - 8 a second one.  That group runs the pair code once for the whole
+    // warp (lanes without a second tap repeat their first one and drop it) instead of the pair code for some lanes
+    // and then the single-tap code for the others.
+    const int full_end = j0 + ((j1 - j0) & ~15);  // columns [j0, full_end) in whole groups
+    const int rem = j1 - full_end;                // 0..15 columns left
+    const bool ok2 = lj < rem - 8;
     for (int i = i0 + warp * 4 + li; i < i1; i += NW * 4) {
         long long X = fix32(rsx[i]) + lane_x, Y = fix32(rsy[i]) - lane_y;
         int j = j0 + lj;
         const int o = i * n;
-        for (; j + 8 < j1; j += 16, X += 2 * sx8, Y -= 2 * sy8) {
+        for (; j < full_end; j += 16, X += 2 * sx8, Y -= 2 * sy8) {
             uint32_t v0, v1;
             if (CHECK) {
                 v0 = tap_fixed_checked<TP>(X, Y, W1, H1, x0, y0, tile);
@@ -550,7 +573,27 @@ __device__ __forceinline__ void window_taps_fixed(int n, int i0, int i1, int j0,
                 sts_u8(win_s + o + j + 8, v1);
             }
         }
-        if (j < j1) {
+        if (rem > 8) {
+            uint32_t v0, v1 = 0;
+            if (CHECK) {
+                v0 = tap_fixed_checked<TP>(X, Y, W1, H1, x0, y0, tile);
+                if (ok2) v1 = tap_fixed_checked<TP>(X + sx8, Y - sy8, W1, H1, x0, y0, tile);
+            } else {
+#if SURF_TAP_F32X2
+                tap_fixed2<TP>(X, Y, ok2 ? X + sx8 : X, ok2 ? Y - sy8 : Y, one2, v0, v1);
+#else
+                v0 = tap_fixed<TP>(X, Y);
+                if (ok2) v1 = tap_fixed<TP>(X + sx8, Y - sy8);
+#endif
+            }
+            if (GLOBAL) {
+                win_g[o + j] = (unsigned char)v0;
+                if (ok2) win_g[o + j + 8] = (unsigned char)v1;
+            } else {
+                sts_u8(win_s + o + j, v0);
+                if (ok2) sts_u8(win_s + o + j + 8, v1);
+            }
+        } else if (lj < rem) {
             const uint32_t v0 = CHECK ? tap_fixed_checked<TP>(X, Y, W1, H1, x0, y0, tile) : tap_fixed<TP>(X, Y);
             if (GLOBAL) win_g[o + j] = (unsigned char)v0; else sts_u8(win_s + o + j, v0);
         }
@@ -609,32 +652,57 @@ __device__ __forceinline__ void descriptor_tail(const DescribeArgs &A, int kidx,
         }
         __syncthreads();
     }
-    for (int p = tid; p < kPatchPx; p += THREADS) {
-        const int dy = p / kPatch, dx = p - dy * kPatch;
-        int outv;
-        if (int_scale && isc == 2) {
-            const unsigned char *r0 = win + (2 * dy) * n + 2 * dx, *r1 = r0 + n;
-            outv = (r0[0] + r0[1] + r1[0] + r1[1] + 2) >> 2;
-        } else if (int_scale) {
-            int acc = 0;
-            for (int v = 0; v < isc; v++) {
-                const unsigned char *r0 = win + (dy * isc + v) * n + dx * isc;
-                for (int u = 0; u < isc; u++) acc += r0[u];
-            }
-            const float wgt = 1.f / (isc * isc);
-            outv = sat_u8(acc * wgt);
-        } else {
-            constexpr int M = MAXC;
+    if (!int_scale) {
+        // Column pass.  Thread = (dy, every G-th dx): the dy entry of the table -- its weights and the addresses of its
+        // source rows -- is worked out once per thread and serves its 21 / G outputs (it used to be re-derived for every
+        // output: about half of this pass's instructions).
+        constexpr int G = THREADS / kPatch;
+        constexpr int M = MAXC;
+        if (tid < G * kPatch) {
+            const int dy = tid / G, c = tid - dy * G;
             float v[M];
             cell_weights<M>(S.tab, dy, v);
             const int ys = S.tab.start[dy];
-            float acc = 0;
+            uint32_t ra[M];
 #pragma unroll
             for (int e = 0; e < M; e++)  // rows past the window are clamped: their weight is 0, the value finite
-                acc += v[e] * lds_f32(buf_addr + (min(ys + e, n - 1) * kPatch + dx) * 4);
-            outv = sat_u8(acc);
+                ra[e] = buf_addr + (uint32_t)(min(ys + e, n - 1) * kPatch + c) * 4;
+            for (int dx = c; dx < kPatch; dx += G) {
+                float acc = 0;
+#pragma unroll
+                for (int e = 0; e < M; e++) acc += v[e] * lds_f32(ra[e] + (uint32_t)(dx - c) * 4);
+                patch[dy * kPatch + dx] = (unsigned char)sat_u8(acc);
+            }
         }
-        patch[p] = (unsigned char)outv;
+    } else {
+        for (int p = tid; p < kPatchPx; p += THREADS) {
+            const int dy = p / kPatch, dx = p - dy * kPatch;
+            int outv;
+            if (isc == 2) {
+                const unsigned char *r0 = win + (2 * dy) * n + 2 * dx, *r1 = r0 + n;
+                outv = (r0[0] + r0[1] + r1[0] + r1[1] + 2) >> 2;
+            } else if (isc == 0) {
+                // n < 21 (only keypoints handed to compute() with size < 7.9): cv::resize's fixed-point bilinear code
+                // with the area-mode coefficients (see area_up_coef)
+                const double inv = (double)kPatch / n, scale = 1. / inv;
+                int x0, xa, xb, y0, ya, yb;
+                area_up_coef(dx, n, scale, inv, x0, xa, xb);
+                area_up_coef(dy, n, scale, inv, y0, ya, yb);
+                const int x1 = min(x0 + 1, n - 1);
+                const unsigned char *r0 = win + y0 * n, *r1 = win + min(y0 + 1, n - 1) * n;
+                const int h0 = r0[x0] * xa + r0[x1] * xb, h1 = r1[x0] * xa + r1[x1] * xb;
+                outv = (((ya * (h0 >> 4)) >> 16) + ((yb * (h1 >> 4)) >> 16) + 2) >> 2;
+            } else {
+                int acc = 0;
+                for (int v = 0; v < isc; v++) {
+                    const unsigned char *r0 = win + (dy * isc + v) * n + dx * isc;
+                    for (int u = 0; u < isc; u++) acc += r0[u];
+                }
+                const float wgt = 1.f / (isc * isc);
+                outv = sat_u8(acc * wgt);
+            }
+            patch[p] = (unsigned char)outv;
+        }
     }
     __syncthreads();  // the patch (a slot of the CTA's ring) is complete
     if (A.patches) {
@@ -656,6 +724,7 @@ __device__ __forceinline__ void descriptor_tail(const DescribeArgs &A, int kidx,
 // ------------------------------------------------------------------------------------------------
 constexpr int kRing = 4;  // (8 patches + the 400-entry weight table in shared memory cost a CTA per SM in two classes)
 
+template <bool EXT>
 __device__ __forceinline__ void patch_descriptor_warp(const DescribeArgs &A, const unsigned char *P, int kidx)
 {
     const int lane = threadIdx.x & 31;
@@ -674,9 +743,11 @@ __device__ __forceinline__ void patch_descriptor_warp(const DescribeArgs &A, con
         for (int x = 0; x < 5; x++) {
             const int p01 = r0[x + 1], p11 = r1[x + 1];
             const float wgt = __fmul_rn(gy, gx[x]);
-            const float tx = (p01 - p00 + p11 - p10) * wgt, ty = (p10 - p00 + p11 - p01) * wgt;
-            const float u = half ? ty : tx, o = half ? tx : ty;
-            if (A.extended) {
+            // dx = p01 - p00 + p11 - p10, dy = p10 - p00 + p11 - p01 (integers: any order of the terms is the same value)
+            const int da = p11 - p00, db = p01 - p10;
+            if (EXT) {
+                const float tx = (da + db) * wgt, ty = (da - db) * wgt;
+                const float u = half ? ty : tx, o = half ? tx : ty;
                 if (o >= 0) {
                     a0 += u;
                     a1 += fabsf(u);
@@ -685,6 +756,7 @@ __device__ __forceinline__ void patch_descriptor_warp(const DescribeArgs &A, con
                     a3 += fabsf(u);
                 }
             } else {
+                const float u = (half ? da - db : da + db) * wgt;
                 a0 += u;
                 a1 += fabsf(u);
             }
@@ -693,11 +765,11 @@ __device__ __forceinline__ void patch_descriptor_warp(const DescribeArgs &A, con
         }
     }
     double mag = (double)(a0 * a0) + (double)(a1 * a1);
-    if (A.extended) mag += (double)(a2 * a2) + (double)(a3 * a3);
+    if (EXT) mag += (double)(a2 * a2) + (double)(a3 * a3);
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) mag += __shfl_xor_sync(FULL_MASK, mag, d);
     const float scale = (float)(1. / (sqrt(mag) + DBL_EPSILON));
-    if (A.extended) {
+    if (EXT) {
         float4 *vo = reinterpret_cast<float4 *>(A.desc + (size_t)kidx * 128 + region * 8 + half * 4);
         *vo = make_float4(a0 * scale, a1 * scale, a2 * scale, a3 * scale);
     } else {
@@ -707,17 +779,27 @@ __device__ __forceinline__ void patch_descriptor_warp(const DescribeArgs &A, con
     }
 }
 
-struct PatchRing {
-    __align__(16) unsigned char patch[kRing][kPatchStride];
-    int kidx[kRing];
+template <int R>
+struct PatchRingT {
+    __align__(16) unsigned char patch[R][kPatchStride];
+    int kidx[R];
 };
+
+using PatchRing = PatchRingT<kRing>;
+// the sub-window kernel parks two: its shared memory is sized to the byte for three CTAs per SM, and its keypoints are
+// few and long (a flush every second keypoint costs nothing against > 16 000 taps each)
+constexpr int kRingBig = 2;
 
 // Every warp finishes the ring entries warp, warp + NW, ...  The caller guarantees the entries are visible (a block
 // barrier lies between the last patch write and this call).
-template <int NW>
-__device__ __forceinline__ void ring_flush(const DescribeArgs &A, const PatchRing &R, int pending)
+template <int NW, class Ring>
+__device__ __forceinline__ void ring_flush(const DescribeArgs &A, const Ring &R, int pending)
 {
-    for (int w = threadIdx.x >> 5; w < pending; w += NW) patch_descriptor_warp(A, R.patch[w], R.kidx[w]);
+    if (A.extended) {
+        for (int w = threadIdx.x >> 5; w < pending; w += NW) patch_descriptor_warp<true>(A, R.patch[w], R.kidx[w]);
+    } else {
+        for (int w = threadIdx.x >> 5; w < pending; w += NW) patch_descriptor_warp<false>(A, R.patch[w], R.kidx[w]);
+    }
 }
 
 // Per-class compile-time geometry.  The image tile of a class has a FIXED pitch and row count (the largest
@@ -732,7 +814,14 @@ struct ClassT {
     // bounding box side of a rotated n x n window: n (|cos| + |sin|) + 3 <= 1.4143 n + 3, plus the 1-pixel
     // margin on both sides of the closed-form box; origin aligned down / pitch rounded up to 16 bytes
     static constexpr int side = (int)(1.4143 * max_n) + 4 + 2;
-    static constexpr int tp = (side + 15 + 15) & ~15;
+    // Pitch: room for the 0..15 columns of the aligned-down origin, a multiple of 16 bytes (TMA box), and an ODD
+    // multiple of 16: the bank of a tile byte is (x / 4 + y * tp / 4) mod 32, so with tp / 4 = 4 (mod 8) eight
+    // consecutive rows start in eight different groups of four banks and the ~9 x 9 pixel footprint of a warp's
+    // 4 x 8 rotated taps is nearly conflict-free.  Class 1 (and the sub-window kernel) had tp = 160 = 40 words:
+    // rows four apart shared their banks, 91 M shared-memory bank conflicts per batch against 33 - 52 M in the
+    // classes whose pitch happened to be odd (profiles/r2/describe_stage_v5_ncu_summary.txt).
+    static constexpr int tp_min = (side + 15 + 15) & ~15;
+    static constexpr int tp = (tp_min & 16) ? tp_min : tp_min + 16;
     static constexpr int tr = side;
     static constexpr int win_bytes = (max_n * max_n + 127) & ~127;
     static constexpr int smem = 128 + max_n * 8 + win_bytes + tp * tr;
@@ -887,14 +976,14 @@ __global__ void __launch_bounds__(ClassT<CLS>::threads, ClassT<CLS>::min_ctas) k
                 float v = tid == 0 ? cx + off * cd + off * sd : cy - off * sd + off * cd;
                 const float inc = tid == 0 ? sd : cd;
                 float *dst = tid == 0 ? s_rsx : s_rsy;
-                // every row start must be a multiple of 2^-32 for the fixed-point taps: branch-free running minimum
-                // of fix32_key (see there)
-                uint32_t key = 0xffffffffu;
+                // every row start must be a multiple of 2^-32 for the fixed-point taps: running minimum of |v| (a row
+                // start of exactly 0 would be fine but is sent to the fp64 taps as well: one FMNMX per step)
+                float lo = INFINITY;
                 for (int i = 0; i < n; i++, v += inc) {
                     dst[i] = v;
-                    key = min(key, fix32_key(v));
+                    lo = fminf(lo, fabsf(v));
                 }
-                if (key < kFix32KeyMin) S.inexact = 1;
+                if (lo < kFix32Min) S.inexact = 1;
             }
         }
         if (warp == NW - 1) {
@@ -903,8 +992,10 @@ __global__ void __launch_bounds__(ClassT<CLS>::threads, ClassT<CLS>::min_ctas) k
             const int n = (int)(21 * s);
             const double inv = (double)kPatch / n;
             const double scale = 1. / inv;
-            const int isc = __double2int_rn(scale);
-            const bool int_scale = fabs(scale - isc) < DBL_EPSILON;
+            // n < 21: the window is enlarged (descriptor_tail's bilinear path), flagged as "integer scale 0"
+            const bool enlarge = n < kPatch;
+            const int isc = enlarge ? 0 : __double2int_rn(scale);
+            const bool int_scale = enlarge || fabs(scale - isc) < DBL_EPSILON;
             if (lane == 31) {
                 S.geo.isc = isc;
                 S.geo.int_scale = int_scale;
@@ -1004,7 +1095,7 @@ __global__ void __launch_bounds__(BigT::threads, 3) k_descriptor_big(const __gri
     const uint32_t tile0_addr = pin_reg(smem_u32(s_tile0)), blk_addr = pin_reg(smem_u32(s_blk));
     __shared__ __align__(8) uint64_t s_bar[2];
     __shared__ DescShared S;
-    __shared__ PatchRing ring;
+    __shared__ PatchRingT<kRingBig> ring;
     int pending = 0;
     __shared__ int4 s_sub[BigT::max_sub];  // per sub-window: tile origin x, y, flags
     uint32_t phase[2] = {0, 0};
@@ -1049,12 +1140,12 @@ __global__ void __launch_bounds__(BigT::threads, 3) k_descriptor_big(const __gri
                 float v = tid == 0 ? cx + off * cd + off * sd : cy - off * sd + off * cd;
                 const float inc = tid == 0 ? sd : cd;
                 float *dst = tid == 0 ? s_rsx : s_rsy;
-                uint32_t key = 0xffffffffu;
+                float lo = INFINITY;
                 for (int i = 0; i < n; i++, v += inc) {
                     dst[i] = v;
-                    key = min(key, fix32_key(v));
+                    lo = fminf(lo, fabsf(v));
                 }
-                if (key < kFix32KeyMin) S.inexact = 1;
+                if (lo < kFix32Min) S.inexact = 1;
             }
         }
         const double inv = (double)kPatch / n;
@@ -1271,7 +1362,7 @@ __global__ void __launch_bounds__(BigT::threads, 3) k_descriptor_big(const __gri
             unsigned char *po = A.patches + (size_t)kidx * kPatchPx;
             for (int p = tid; p < kPatchPx; p += THREADS) po[p] = patch[p];
         }
-        if (A.desc && ++pending == kRing) {
+        if (A.desc && ++pending == kRingBig) {
             ring_flush<NW>(A, ring, pending);
             pending = 0;
         }

@@ -327,6 +327,43 @@ def test_provided_keypoints_deletion_and_filter(eng, oracle, frame640):
     assert np.linalg.norm(gd - od, axis=1).max() <= 1e-4
 
 
+@pytest.mark.parametrize("upright", [False, True])
+def test_small_provided_keypoints_enlarging_resize(oracle, frame640, upright):
+    """DescriptorExtractor::compute() on keypoints smaller than any the detector emits (size < 7.9: window of 1..20
+    pixels, enlarged to 21 x 21 by cv::resize's bilinear fixed-point code).  Sizes sweep every window side 1..20,
+    positions include the frame border; the tiniest (Haar side 0, window 0) follow the oracle's reading of upstream
+    (angle 0 / deleted)."""
+    from surffeatures_b200 import SURF
+
+    p = oracle.params(100, 4, 3, False, upright)
+    rng = np.random.default_rng(5)
+    base = oracle.raw_keypoints(frame640, oracle.params(100, 4, 3))[:400].copy()
+    kps = np.concatenate([base, base])
+    n_small = len(kps)
+    # window side n = (int)(21 * size * 1.2 / 9): sizes 0.2 .. 7.9 cover n = 0 .. 20 several times over
+    kps["size"] = np.linspace(0.2, 7.85, n_small).astype(np.float32)[rng.permutation(n_small)]
+    kps["x"][:40] = rng.uniform(-2, 6, 40).astype(np.float32)          # left border
+    kps["y"][40:80] = rng.uniform(474, 482, 40).astype(np.float32)     # bottom border
+    kps["x"][80:120] = rng.uniform(634, 642, 40).astype(np.float32)    # right border
+    eng = SURF(100, 4, 3, False, upright, max_width=640, max_height=480, max_batch=1, max_keypoints=8192)
+    try:
+        okp, odesc, opatch = oracle.describe(frame640, p, kps, want_patches=True)
+        gkp, gdesc, gpatch = eng.describe_keypoints(frame640, kps, want_patches=True)
+    finally:
+        eng.close()
+    assert np.array_equal(gkp["size"], okp["size"])
+    live = okp["size"] > 0
+    side = (21 * (kps["size"] * np.float32(1.2) / np.float32(9.0))).astype(np.int32)
+    assert set(range(1, 21)) <= set(side[live].tolist()), "every enlarging window side must be exercised"
+    assert (~live).sum() > 0 and (side[~live] < 1).any()
+    assert np.array_equal(gkp["angle"][live], okp["angle"][live])
+    same_patch = (gpatch[live] == opatch[live]).all(axis=(1, 2))
+    assert same_patch.mean() >= 0.999, f"{(~same_patch).sum()} patches differ"
+    err = np.linalg.norm(gdesc[live] - odesc[live], axis=1)
+    assert np.nanmax(err) <= 1e-4, float(np.nanmax(err))
+    assert np.array_equal(np.isnan(gdesc[live]), np.isnan(odesc[live]))
+
+
 def test_capacity_overflow_is_reported(frame640):
     from surffeatures_b200 import SURF, SurfError
 

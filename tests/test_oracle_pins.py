@@ -60,6 +60,17 @@ def test_resize_area_bit_exact_vs_cv2(oracle, n):
     assert np.array_equal(oracle.resize_area_21(w), cv2.resize(w, (21, 21), interpolation=cv2.INTER_AREA))
 
 
+@pytest.mark.parametrize("n", range(1, 21))
+def test_resize_area_enlarging_bit_exact_vs_cv2(oracle, n):
+    """Windows narrower than 21 px (keypoint size < 7.9 handed to compute()): INTER_AREA runs cv::resize's bilinear
+    fixed-point code with the area-mode coefficients.  Several seeds, plus flat and extreme inputs."""
+    rng = np.random.default_rng(1000 + n)
+    wins = [rng.integers(0, 256, (n, n), dtype=np.uint8) for _ in range(8)]
+    wins += [np.zeros((n, n), np.uint8), np.full((n, n), 255, np.uint8), (np.indices((n, n)).sum(0) % 2 * 255).astype(np.uint8)]
+    for w in wins:
+        assert np.array_equal(oracle.resize_area_21(w), cv2.resize(w, (21, 21), interpolation=cv2.INTER_AREA))
+
+
 def test_knn_match_vs_cv2_bfmatcher(oracle):
     rng = np.random.default_rng(0)
     t = rng.standard_normal((400, 64)).astype(np.float32)

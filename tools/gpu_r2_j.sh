@@ -1,0 +1,23 @@
+#!/bin/bash
+# round 2, GPU call J: full GPU suite after the enlarging-resize path and the odd tile pitch; A/B against the HEAD library
+cd "$(dirname "$0")/.."
+mkdir -p gpurun_out
+timeout 1500 python -m pytest tests -m gpu -q --timeout=600 -rf -p no:cacheprovider > gpurun_out/r2j_pytest_gpu.log 2>&1; echo "pytest exit $?" >> gpurun_out/r2j_pytest_gpu.log
+tail -6 gpurun_out/r2j_pytest_gpu.log
+B="python bench.py --no-extras --no-cpu --steps 30 --warmup 3"
+for r in 1 2; do
+  timeout 300 $B > gpurun_out/r2j_bench_new$r.json 2> gpurun_out/r2j_bench_new$r.err; echo "new$r exit $?"
+  SURF_B200_LIB=$PWD/scratch_ab/lib_head.so timeout 300 $B --dev-lib > gpurun_out/r2j_bench_head$r.json 2>/dev/null; echo "head$r exit $?"
+done
+python - <<'PY'
+import json
+for n in ("new1","head1","new2","head2"):
+    try:
+        d=json.load(open(f"gpurun_out/r2j_bench_{n}.json"))
+        st={s["stage"]:round(s["ms"],3) for s in d["roofline_stages"]}
+        print(n, round(d["value"]), round(d["e2e"]["value"]), st)
+    except Exception as e: print(n, "failed", e)
+PY
+CMD="python bench.py --no-extras --no-cpu --steps 2 --warmup 3"
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k_orient|k_descriptor' -s 15 -c 5 -o gpurun_out/r2j_describe $CMD > gpurun_out/r2j_ncu_describe.log 2>&1; echo "ncu describe exit $?"
+ls -la gpurun_out | grep r2j
