@@ -687,8 +687,9 @@ def run_ours(args):
     roofline = {"bound": "hbm", "kernel": dom["kernels"], "achieved": dom["achieved"], "peak": peaks["hbm"],
                 "peak_source": peaks["source"] + " hbm_gbs, burst copy peak", "unit": "GB/s", "frac": dom["frac"],
                 "traffic": traffic, "traffic_source": NCU_SOURCE if traffic else None,
-                "limiter": "instruction issue, not HBM: the window kernels sit at 80-85 % issue-slot utilisation "
-                           "(about 6300 exact bilinear taps per keypoint); see profiles/",
+                "limiter": "instruction issue, not HBM: the window kernels sit at 74-84 % issue-slot utilisation "
+                           "(about 6300 exact bilinear taps per keypoint, 56-74 % of their instructions); see "
+                           "profiles/r2/describe_stage_v5_sections.txt",
                 "issue_slots": ({"warp_inst_per_step": NCU_DESCRIBE_INST,
                                  "achieved_ginst_s": NCU_DESCRIBE_INST / (dom["ms"] * 1e-3) / 1e9,
                                  "peak_ginst_s": 148 * 4 * 1.965,
@@ -777,11 +778,11 @@ def run_ours(args):
     return 0
 
 
-# from profiles/r2/describe_stage_v4_ncu_summary.txt (ncu --set full of this command, batch 64, same kernels as HEAD):
-# k_orient + the four window kernels (the patch -> descriptor step now runs inside them): 189.0 MB read + 14.4 MB written,
-# 4.24 G warp instructions.  Round 1: 428.9 MB and 4.42 G.
-NCU_DESCRIBE_TRAFFIC, NCU_DESCRIBE_INST = 203.4e6, 4.243e9
-NCU_SOURCE = "profiles/r2/describe_stage_v4_ncu_summary.txt"
+# from profiles/r2/describe_stage_v5_ncu_summary.txt (ncu --set full of this command, batch 64, same kernels as HEAD):
+# k_orient + the four window kernels (the patch -> descriptor step runs inside them): 188.9 MB read + 14.3 MB written,
+# 3.93 G warp instructions.  Round 1: 428.9 MB and 4.42 G; round 2 before the resize / tap-tail changes: 4.24 G.
+NCU_DESCRIBE_TRAFFIC, NCU_DESCRIBE_INST = 203.2e6, 3.930e9
+NCU_SOURCE = "profiles/r2/describe_stage_v5_ncu_summary.txt"
 
 
 def cpu_baseline_leg(pool: np.ndarray):
