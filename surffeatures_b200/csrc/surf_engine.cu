@@ -88,14 +88,17 @@ int tc_reserve_work(surf_engine *e, surf_engine::TcWs &w, int n_probs, int split
         CU(e, cudaMalloc(&w.redo, need_redo * 2 * sizeof(int)));
         w.redo_cap = need_redo;
     }
-    if (!w.counters) CU(e, cudaMalloc(&w.counters, 4 * sizeof(int)));
     const int tab = n_probs > n_segs ? n_probs : n_segs;
     if (tab > w.table_cap) {
         CU(e, cudaStreamSynchronize(e->stream));
         cudaFree(w.segs);
         cudaFree(w.probs);
+        cudaFree(w.counters);
         w.segs = nullptr;
         w.probs = nullptr;
+        w.counters = nullptr;
+        CU(e, cudaMalloc(&w.counters, (2 + (size_t)tab) * sizeof(int)));  // work head, redo total, redo entries per problem
+        CU(e, cudaMemset(w.counters, 0, (2 + (size_t)tab) * sizeof(int)));
         CU(e, cudaMalloc(&w.segs, tab * sizeof(TcSegment)));
         CU(e, cudaMalloc(&w.probs, tab * sizeof(TcProblem)));
         w.table_cap = tab;

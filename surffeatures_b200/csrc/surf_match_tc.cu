@@ -17,6 +17,7 @@
 #include <cuda_bf16.h>
 
 #include <cfloat>
+#include <cstdlib>
 
 #include "surf_internal.h"
 #include "surf_ptx.cuh"
@@ -642,6 +643,237 @@ size_t tc_candidates_smem(int dim) { return (size_t)(2 * kTM + 2 * kTN) * dim * 
 #endif
 
 // ------------------------------------------------------------------------------------------------
+// K5b', the candidate kernel for k <= 2 and train splits of at most 2^14 rows (a frame's keypoints): the epilogue is
+// BRANCH-FREE.  With 32 query rows in a warp, "some lane has a value under its row's threshold" is true for almost
+// every group of columns when the train set is a frame (a few thousand rows), so the filtered list updates of
+// k_tc_candidates run for the whole warp almost every time (12.6 instructions per score, measured).  Here a score is
+// turned into ONE sortable 32-bit key and pushed through a sorted three-entry list with unsigned min / max only:
+//   u    = sigma * (|t|^2 - 2 q.t + off)  in [0, 1)           sigma, off from the slots' largest norms
+//   t'   = 2^(s-9) + u                    one FFMA: fma(acc, -2 sigma, tnB[col]), tnB = 2^(s-9) + sigma (|t|^2 + off)
+//   key  = bits(t') << s  |  row of the train split (s bits)  one IMAD: the shift drops sign, exponent and the s - 9
+//                                                             mantissa bits that are zero in [2^(s-9), 2^(s-9) + 1)
+// i.e. the FFMA's own rounding quantises u to 32 - s bits (18 bits for 16 384 rows: 4e-6 of the value range) and the
+// low s bits are free for the index.  Two keys are sorted, then merged into (m1 <= m2 <= m3): 8 min / max
+// instructions per PAIR of scores (three-input VIMNMX3 where two mins follow each other).  m3 bounds everything the
+// thread did not keep.  Four threads share a query row (column quarters); at the end of an item their lists are
+// merged: the four smallest keys are the candidates, min(fifth, the four m3) decoded and lowered by the quantisation
+// slack is the bound the margin test of k_tc_rescore uses.  Padded train rows get the largest value of the range.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void key_insert_pair(uint32_t &m1, uint32_t &m2, uint32_t &m3, uint32_t x, uint32_t y)
+{
+    const uint32_t lo = min(x, y), hi = max(x, y);
+    const uint32_t a = max(m1, lo), b = max(m2, lo), c = max(m1, hi);
+    m3 = min(m3, min(b, c));
+    m2 = min(m2, min(a, hi));
+    m1 = min(m1, lo);
+}
+
+size_t tc_candidates3_smem(int dim) { return (size_t)(2 * kTM + 2 * kTN) * dim * 2 + 4 * kTN * sizeof(float) + 1024; }
+
+template <int D>
+__global__ void __launch_bounds__(kCandThreads, D == 64 ? 2 : 1) k_tc_candidates3(TcPool pool, TcPool tpool, const TcProblem *__restrict__ probs,
+                                                        int n_probs, int mt_per_prob, int n_splits, int cand_stride,
+                                                        TcCand *__restrict__ cand_out, int *__restrict__ work_head, int idx_bits, uint32_t key_mul)
+{
+    constexpr int KSTEPS = D / 16;
+    constexpr uint32_t SBO = (D / 8) * 128;        // bytes between 8-row groups
+    constexpr uint32_t A_BYTES = kTM * D * 2;      // one of hi / lo
+    constexpr uint32_t B_BYTES = kTN * D * 2;
+    extern __shared__ __align__(1024) unsigned char sm[];
+    unsigned char *sA_hi = sm, *sA_lo = sm + A_BYTES;
+    unsigned char *sB_hi = sm + 2 * A_BYTES, *sB_lo = sB_hi + B_BYTES;
+    float *sTn = reinterpret_cast<float *>(sB_lo + B_BYTES);  // |t|^2 of the train tile, two stages (bulk copies)
+    float *sTnB = sTn + 2 * kTN;                               // 2^(s-9) + sigma (|t|^2 + off), two stages (generic)
+    __shared__ __align__(8) uint64_t s_bar[2];  // [0] MMA done (tcgen05.commit), [1] operands landed (bulk copies)
+    __shared__ uint32_t s_tmem;
+    __shared__ int s_item;
+
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int quarter = warp >> 2, qrow = (warp & 3) * 32 + (tid & 31);
+    const uint32_t bar_mma = smem_u32(&s_bar[0]), bar_ld = smem_u32(&s_bar[1]);
+    if (tid == 0) {
+        mbar_init(bar_mma, 1);
+        mbar_init(bar_ld, 1);
+        mbar_init_fence();
+    }
+    __syncwarp();
+    if (warp == 0) tmem_alloc(smem_u32(&s_tmem), kTmemCols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = s_tmem;
+    const uint32_t idesc = umma_idesc(kTM, kTN);
+    uint32_t ph_mma = 0, ph_ld = 0;
+    const int total_items = n_probs * mt_per_prob * n_splits;
+    const int vbits = 32 - idx_bits;                                  // bits of the quantised value
+    const uint32_t pad_field = (1u << vbits) - 1u;                    // value field of a padded train row and of an empty entry
+    const float base2 = __uint_as_float((uint32_t)(127 + idx_bits - 9) << 23);          // 2^(s-9)
+    const float pad_val = __uint_as_float(((uint32_t)(127 + idx_bits - 8) << 23) - 1);   // just under 2^(s-8)
+    const float grid = __uint_as_float((uint32_t)(127 - vbits) << 23);                   // 2^-vbits
+
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) s_item = atomicAdd(work_head, 1);
+        __syncthreads();
+        const int item = s_item;
+        if (item >= total_items) break;
+        const int p = item / (mt_per_prob * n_splits);
+        const int rem = item - p * (mt_per_prob * n_splits);
+        const int mt = rem / n_splits, split = rem - mt * n_splits;
+        const TcProblem pr = probs[p];
+        const int nq = pool.count[pr.q_slot], nt = tpool.count[pr.t_slot];
+        const int q0 = mt * kTM;
+        if (q0 >= nq) continue;
+        const int n_tiles = (nt + kTN - 1) / kTN;
+        const int per = (n_tiles + n_splits - 1) / n_splits;
+        const int tile0 = split * per, tile1 = min(n_tiles, tile0 + per);
+        // value range of |t|^2 - 2 q.t over the two slots: [-max|q|^2, 2 max|t|^2 + max|q|^2]
+        const float nsum = pool.max_norm[pr.q_slot] + tpool.max_norm[pr.t_slot];
+        const float off = pool.max_norm[pr.q_slot] + 0.01f * nsum;
+        const float sigma = 1.f / (2.04f * nsum + 1e-30f);
+        const float m2sigma = -2.f * sigma;
+
+        // the lists hold keys whose index field is RELATIVE to the chunk being scanned and counts downwards
+        // (31 - column for the chunk's own columns, more for earlier chunks), so a new key is bits * 2^s + constant
+        // with no index register; the three entries are moved along by the chunk distance once per chunk
+        uint32_t m1 = pad_field << idx_bits, m2 = m1, m3 = m1;  // empty entries: the value field of a padded row
+        int pos = -1;                                            // first split row of the last chunk scanned
+        const size_t trow_base = (size_t)pr.t_slot * tpool.slot_rows;
+        auto load_train_tile = [&](int tile, int stage) {
+            const size_t row0 = trow_base + (size_t)tile * kTN;
+            bulk_g2s(smem_u32(sB_hi), tpool.hi + row0 * D, B_BYTES, bar_ld);
+            bulk_g2s(smem_u32(sB_lo), tpool.lo + row0 * D, B_BYTES, bar_ld);
+            bulk_g2s(smem_u32(sTn + stage * kTN), tpool.norm + row0, kTN * sizeof(float), bar_ld);
+        };
+        if (tid == 0 && tile0 < tile1) {
+            const size_t e0 = ((size_t)pr.q_slot * pool.slot_rows + q0) * D;
+            mbar_expect_tx(bar_ld, 2 * A_BYTES + 2 * B_BYTES + kTN * sizeof(float));
+            bulk_g2s(smem_u32(sA_hi), pool.hi + e0, A_BYTES, bar_ld);
+            bulk_g2s(smem_u32(sA_lo), pool.lo + e0, A_BYTES, bar_ld);
+            load_train_tile(tile0, 0);
+        }
+
+        for (int tile = tile0; tile < tile1; tile++) {
+            const int stage = (tile - tile0) & 1;
+            mbar_wait(bar_ld, ph_ld);  // operands of this tile are in shared memory
+            ph_ld ^= 1;
+            if (tid < kTN) {
+                const float tn = sTn[stage * kTN + tid];
+                sTnB[stage * kTN + tid] = tn < INFINITY ? fmaf(tn + off, sigma, base2) : pad_val;
+            }
+            __syncthreads();  // everyone has observed this phase before the next one can be armed; sTnB is written
+            if (tid == 0) {
+                tc_fence_after();
+                const uint32_t a_hi = smem_u32(sA_hi), a_lo = smem_u32(sA_lo);
+                const uint32_t b_hi = smem_u32(sB_hi), b_lo = smem_u32(sB_lo);
+#pragma unroll
+                for (int ks = 0; ks < KSTEPS; ks++) {
+                    const uint32_t ko = ks * 256;  // two core matrices (16 K-elements) per step
+                    umma_bf16(tmem, umma_desc(a_hi + ko, 128, SBO), umma_desc(b_hi + ko, 128, SBO), idesc, ks > 0);
+                }
+#pragma unroll
+                for (int ks = 0; ks < KSTEPS; ks++) {
+                    const uint32_t ko = ks * 256;
+                    umma_bf16(tmem, umma_desc(a_hi + ko, 128, SBO), umma_desc(b_lo + ko, 128, SBO), idesc, 1);
+                    umma_bf16(tmem, umma_desc(a_lo + ko, 128, SBO), umma_desc(b_hi + ko, 128, SBO), idesc, 1);
+                }
+                umma_commit(bar_mma);
+            }
+            mbar_wait(bar_mma, ph_mma);  // accumulators complete; the train tile in shared memory is free
+            ph_mma ^= 1;
+            tc_fence_after();
+            if (tid == 0 && tile + 1 < tile1) {  // prefetch the next train tile under this tile's epilogue
+                mbar_expect_tx(bar_ld, 2 * B_BYTES + kTN * sizeof(float));
+                load_train_tile(tile + 1, stage ^ 1);
+            }
+
+            // ---- epilogue: warp w reads TMEM lanes 32*(w%4).. (its query rows) and the column quarter w/4
+            const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+            const float *tn = sTnB + stage * kTN;
+            const int cbeg = quarter * (kTN / 4);
+            const int lim = min(kTN, nt - tile * kTN);
+#pragma unroll 1
+            for (int c0 = cbeg; c0 < cbeg + kTN / 4; c0 += 32) {
+                float v[32];
+                tmem_ld32(lane_addr + c0, v);
+                if (c0 < lim) {  // a chunk of padding rows only: nothing to keep
+                    const int idx0 = (tile - tile0) * kTN + c0;
+                    const uint32_t delta = pos < 0 ? 0u : (uint32_t)(idx0 - pos);
+                    pos = idx0;
+                    m1 += delta;
+                    m2 += delta;
+                    m3 += delta;
+#pragma unroll
+                    for (int c = 0; c < 32; c += 4) {
+                        const float4 t4 = *reinterpret_cast<const float4 *>(tn + c0 + c);
+                        const uint32_t k0 = __float_as_uint(fmaf(v[c], m2sigma, t4.x)) * key_mul + (31 - c);
+                        const uint32_t k1 = __float_as_uint(fmaf(v[c + 1], m2sigma, t4.y)) * key_mul + (30 - c);
+                        const uint32_t k2 = __float_as_uint(fmaf(v[c + 2], m2sigma, t4.z)) * key_mul + (29 - c);
+                        const uint32_t k3 = __float_as_uint(fmaf(v[c + 3], m2sigma, t4.w)) * key_mul + (28 - c);
+                        key_insert_pair(m1, m2, m3, k0, k1);
+                        key_insert_pair(m1, m2, m3, k2, k3);
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncthreads();  // every warp has drained TMEM before the next tile's MMA overwrites it
+        }
+        // ---- merge the four quarter lists of every query row.  The scratch aliases the train-tile buffer: every MMA
+        //      that read it has completed (bar_mma), and the next item's bulk copies are issued only after the proxy
+        //      fence and the barrier at the loop top.
+        uint32_t *s_merge = reinterpret_cast<uint32_t *>(sB_hi);  // [row][quarter][3]
+        const uint32_t idx_mask = (1u << idx_bits) - 1u;
+        auto absolute = [&](uint32_t m) {  // relative, descending index field -> row of the split
+            return (m & ~idx_mask) | (((uint32_t)(pos + 31) - (m & idx_mask)) & idx_mask);
+        };
+        s_merge[(qrow * 4 + quarter) * 3 + 0] = absolute(m1);
+        s_merge[(qrow * 4 + quarter) * 3 + 1] = absolute(m2);
+        s_merge[(qrow * 4 + quarter) * 3 + 2] = absolute(m3);
+        __syncthreads();
+        if (tid < kTM && q0 + tid < nq) {
+            const int row = tid;
+            uint32_t best[5] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
+            uint32_t third = 0xffffffffu;  // smallest of the four lists' third entries
+#pragma unroll
+            for (int e = 0; e < 12; e++) {
+                uint32_t x = s_merge[row * 12 + e];
+                if (e % 3 == 2) third = min(third, x);
+#pragma unroll
+                for (int r = 0; r < 5; r++) {  // sorted insertion, branch-free
+                    const uint32_t lo = min(best[r], x);
+                    x = max(best[r], x);
+                    best[r] = lo;
+                }
+            }
+            const float inv_sigma = 2.04f * nsum + 1e-30f;
+            TcCand o;
+#pragma unroll
+            for (int r = 0; r < kCand; r++) {
+                o.d[r] = INFINITY;
+                o.i[r] = -1;
+            }
+#pragma unroll
+            for (int r = 0; r < 4; r++) {
+                const uint32_t field = best[r] >> idx_bits;
+                if (field != pad_field) {
+                    o.d[r] = (float)field * grid * inv_sigma - off;
+                    o.i[r] = tile0 * kTN + (int)(best[r] & idx_mask);
+                }
+            }
+            // lower bound of every value of this split that is not among the four candidates: what the quarter lists
+            // dropped (>= their third entries) and what the merge dropped (>= the fifth key), less the quantisation
+            // slack (two roundings to the grid of 2^-vbits, the decode's own fp32 roundings)
+            const uint32_t bfield = min(third, best[4]) >> idx_bits;
+            o.worst = bfield != pad_field ? ((float)bfield - 2.5f) * grid * inv_sigma - off - 2e-6f * nsum : INFINITY;
+            cand_out[(size_t)(p * n_splits + split) * cand_stride + q0 + row] = o;
+        }
+        fence_async_smem();  // generic-proxy accesses to the tile buffer before the next bulk copy overwrites it
+    }
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, kTmemCols);
+}
+
+// ------------------------------------------------------------------------------------------------
 // K5c: exact rescoring of the candidates, top-k, margin test.  LPQ lanes per query, one per
 // candidate slot of a list (4 when the lists keep 4 entries, else 8).
 // ------------------------------------------------------------------------------------------------
@@ -727,10 +959,12 @@ __global__ void __launch_bounds__(256) k_tc_rescore(TcPool pool, TcPool tpool, c
     }
     if (good && k >= 2)
         good[out_row0 + gq] = (bi[0] >= 0 && bi[1] >= 0 && sqrtf(bd[0]) < ratio * sqrtf(bd[1])) ? 1 : 0;
-    if (!proven) {
-        const int pos = atomicAdd(redo_count, 1);
-        redo_list[2 * pos] = p;
-        redo_list[2 * pos + 1] = gq;
+    if (!proven) {  // redo_count[0] = total (reported), redo_count[1 + p] = entries of problem p's list
+        atomicAdd(redo_count, 1);
+        const int pos = atomicAdd(redo_count + 1 + p, 1);
+        int *e = redo_list + 2 * ((size_t)p * cand_stride + pos);
+        e[0] = p;
+        e[1] = gq;
     }
 }
 
@@ -852,32 +1086,30 @@ __device__ void redo_scan(const TcProblem &pr, int nt, const int *__restrict__ e
 
 constexpr int kRedoGroup = 8;
 
+// The unproven queries are listed PER PROBLEM (k_tc_rescore), so a CTA takes up to kRedoGroup queries of one problem and
+// reads every train row once for all of them: with the three-entry key lists 0.1-0.2 % of a frame's queries are unproven
+// (a handful per frame pair), and one scan of the train frame per group is what bounds this kernel.
 template <int D>
-__global__ void __launch_bounds__(256) k_tc_redo(TcPool tpool, const TcProblem *__restrict__ probs, int k, float ratio,
+__global__ void __launch_bounds__(256) k_tc_redo(TcPool tpool, const TcProblem *__restrict__ probs, int list_stride, int k, float ratio,
                                                  surf_dmatch *__restrict__ out, uint8_t *__restrict__ good,
-                                                 const int *__restrict__ redo_list, const int *__restrict__ redo_count)
+                                                 const int *__restrict__ redo_list, const int *__restrict__ prob_count)
 {
     __shared__ float s_d[kRedoGroup][8][4];
     __shared__ int s_i[kRedoGroup][8][4];
     __shared__ __align__(16) float s_q[kRedoGroup][D];
-    const int n = *redo_count;
-    // few entries: one per CTA (a lone query is latency-critical); many: groups of kRedoGroup share every train row
-    const int group = n > (int)gridDim.x ? kRedoGroup : 1;
-    for (int w0 = blockIdx.x * group; w0 < n; w0 += gridDim.x * group) {
-        const int ng = min(group, n - w0);
-        const int *entries = redo_list + 2 * w0;
-        bool same = ng > 1;
-        for (int g = 1; g < ng; g++) same = same && entries[2 * g] == entries[0];
-        if (same) {
-            const TcProblem pr = probs[entries[0]];
-            redo_scan<D, kRedoGroup>(pr, tpool.count[pr.t_slot], entries, ng, k, ratio, out, good, s_q, s_d, s_i);
-        } else {
-            for (int g = 0; g < ng; g++) {
-                const TcProblem pr = probs[entries[2 * g]];
-                redo_scan<D, 1>(pr, tpool.count[pr.t_slot], entries + 2 * g, 1, k, ratio, out, good, s_q, s_d, s_i);
-            }
-        }
+    const int p = blockIdx.y;
+    const int n = prob_count[p];
+    const bool single = n <= (int)gridDim.x;  // few entries and CTAs to spare: one query per CTA (latency)
+    if ((int)blockIdx.x * (single ? 1 : kRedoGroup) >= n) return;
+    const TcProblem pr = probs[p];
+    const int nt = tpool.count[pr.t_slot];
+    const int *list = redo_list + 2 * (size_t)p * list_stride;
+    if (single) {
+        redo_scan<D, 1>(pr, nt, list + 2 * blockIdx.x, 1, k, ratio, out, good, s_q, s_d, s_i);
+        return;
     }
+    for (int w0 = blockIdx.x * kRedoGroup; w0 < n; w0 += gridDim.x * kRedoGroup)
+        redo_scan<D, kRedoGroup>(pr, nt, list + 2 * w0, min(kRedoGroup, n - w0), k, ratio, out, good, s_q, s_d, s_i);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -902,7 +1134,7 @@ void launch_tc_match(const TcMatchArgs &a, cudaStream_t st, int *launches)
     const TcPool &tp = a.tpool.hi ? a.tpool : a.pool;
     // ---- prep every segment (rows -> bf16 hi/lo tiles + norms) ----
     launch_tc_prep(a.pool, a.segs, a.n_segs, a.pool.slot_rows, D, true, st, nullptr);
-    launch_zero(a.counters, 2, st, nullptr);  // [0] work head, [1] redo count
+    launch_zero(a.counters, 2 + a.n_probs, st, nullptr);  // [0] work head, [1] redo count, [2 + p] redo entries of problem p
 
     static bool attr_set[64] = {};
     int dev = 0;
@@ -919,6 +1151,26 @@ void launch_tc_match(const TcMatchArgs &a, cudaStream_t st, int *launches)
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int mt_per_prob = a.max_q_rows / kTM;
     const bool small_k = a.k <= 2;
+    // k <= 2 against train splits of at most 2^14 rows (frame against frame): the branch-free key kernel
+    const int tiles_cap = tp.slot_rows / kTN;
+    const int rows_per_split = (tiles_cap + a.n_splits - 1) / a.n_splits * kTN;
+    static const bool keys_off = getenv("SURF_TC_NO_KEYS") != nullptr;  // measurement knob: the filtered-list kernel
+    if (small_k && rows_per_split <= (1 << 14) && !keys_off) {
+        int idx_bits = 9;
+        while ((1 << idx_bits) < rows_per_split) idx_bits++;
+        static bool attr3_set[64] = {};
+        if (!attr3_set[dev & 63]) {
+            cudaFuncSetAttribute(k_tc_candidates3<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_candidates3_smem(64));
+            cudaFuncSetAttribute(k_tc_candidates3<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_candidates3_smem(128));
+            attr3_set[dev & 63] = true;
+        }
+        if (D == 64)
+            k_tc_candidates3<64><<<2 * sms, kCandThreads, tc_candidates3_smem(64), st>>>(
+                a.pool, tp, a.probs, a.n_probs, mt_per_prob, a.n_splits, a.max_q_rows, a.cand, a.counters, idx_bits, 1u << idx_bits);
+        else
+            k_tc_candidates3<128><<<sms, kCandThreads, tc_candidates3_smem(128), st>>>(
+                a.pool, tp, a.probs, a.n_probs, mt_per_prob, a.n_splits, a.max_q_rows, a.cand, a.counters, idx_bits, 1u << idx_bits);
+    } else {
 // persistent CTAs: 256 TMEM columns each, so at most two share an SM's 512; the D = 64 / 4-entry variant fits two
 // (2 x 101 KB of shared memory, 64 registers x 512 threads), the others run one per SM
 #define SURF_TC_LAUNCH(DD, KK)                                                                              \
@@ -930,17 +1182,19 @@ void launch_tc_match(const TcMatchArgs &a, cudaStream_t st, int *launches)
         if (small_k) SURF_TC_LAUNCH(128, 4); else SURF_TC_LAUNCH(128, 8);
     }
 #undef SURF_TC_LAUNCH
+    }
     const int lpq = small_k ? 4 : kCand;  // lists of the small-k candidate kernel hold 4 entries
     dim3 gres(((size_t)a.max_q_rows * lpq + 255) / 256, a.n_probs);
+    dim3 gredo(a.n_probs == 1 ? 2 * sms : (2 * sms / a.n_probs > 2 ? 2 * sms / a.n_probs : 2), a.n_probs);
 #define SURF_TC_RESCORE(DD, LL)                                                                                        \
     k_tc_rescore<DD, LL><<<gres, 256, 0, st>>>(a.pool, tp, a.probs, a.n_splits, a.max_q_rows, a.cand, a.k, a.ratio, a.out, \
                                                a.good, a.redo_list, a.counters + 1)
     if (D == 64) {
         if (small_k) SURF_TC_RESCORE(64, 4); else SURF_TC_RESCORE(64, kCand);
-        k_tc_redo<64><<<sms * 2, 256, 0, st>>>(tp, a.probs, a.k, a.ratio, a.out, a.good, a.redo_list, a.counters + 1);
+        k_tc_redo<64><<<gredo, 256, 0, st>>>(tp, a.probs, a.max_q_rows, a.k, a.ratio, a.out, a.good, a.redo_list, a.counters + 2);
     } else {
         if (small_k) SURF_TC_RESCORE(128, 4); else SURF_TC_RESCORE(128, kCand);
-        k_tc_redo<128><<<sms * 2, 256, 0, st>>>(tp, a.probs, a.k, a.ratio, a.out, a.good, a.redo_list, a.counters + 1);
+        k_tc_redo<128><<<gredo, 256, 0, st>>>(tp, a.probs, a.max_q_rows, a.k, a.ratio, a.out, a.good, a.redo_list, a.counters + 2);
     }
 #undef SURF_TC_RESCORE
     *launches += 6;

