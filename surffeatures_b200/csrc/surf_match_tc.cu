@@ -62,6 +62,26 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
         : "memory");
 }
 
+// the same with the accumulate flag fixed at compile time (no predicate computed from a register)
+__device__ __forceinline__ void umma_bf16_first(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, 0, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc)
+        : "memory");
+}
+__device__ __forceinline__ void umma_bf16_acc(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.eq.b32 p, 0, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc)
+        : "memory");
+}
+
 __device__ __forceinline__ void umma_commit(uint32_t bar)
 {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
@@ -208,241 +228,9 @@ __device__ __forceinline__ void cand_replace_worst(Cand<KC> &c, float dist, int 
 
 constexpr int kCandThreads = 512;  // 16 warps: warp w owns TMEM lanes 32*(w%4).. and the column quarter w/4
 
-// Two candidate kernels, selected at compile time.  SURF_TC_PIPE = 0 (default): one 256-column accumulator per CTA,
-// MMA(t) -> epilogue(t) back to back, two CTAs per SM overlap each other.  SURF_TC_PIPE = 1: the software-pipelined
-// variant below.  Measured on a B200 (round 2, 64 frame pairs of ~4230 x 4230 x 64, profiles/r2/): pipelined 0.902 ms
-// against 0.862 ms serial, 1M-row database query 3.07 ms against 2.42 ms.  The pipeline does what it should -- the
-// long-scoreboard stall (waiting for the accumulator) falls from 2.6 to 0.4 per issue -- but the tiles are half as
-// wide, so the block barrier that recycles an accumulator comes twice as often, and the epilogue's work per warp is
-// very uneven (divergent list updates: 15 of 32 lanes active on average): barrier stalls double (2.1 -> 4.2 per issue),
-// issue-slot utilisation stays at 55 % and the tensor pipe at 20 %.  The kernel is bound by the epilogue's
-// instructions, not by the MMA / epilogue serialisation; kept for reference, not built by default.
-#ifndef SURF_TC_PIPE
-#define SURF_TC_PIPE 0
-#endif
-#if SURF_TC_PIPE
-// Software-pipelined candidate search: train tiles of kTC = 128 rows, TWO accumulators of 128 TMEM columns in the CTA's
-// 256 and two operand stages in shared memory.  While the 16 epilogue warps scan accumulator (t & 1), the tensor core
-// already computes tile t + 1 into the other one (issued by thread 0 at the top of iteration t) and the bulk copies of
-// tile t + 2 land in the stage tile t's MMA has just released:
-//     iteration t :  [thread 0] wait operands(t+1) -> MMA(t+1) -> commit          (accumulator and stage (t+1) & 1)
-//                    [all]      wait MMA(t)                                        (issued one iteration earlier)
-//                    [thread 0] bulk copies of tile t+2 -> stage t & 1             (|t|^2 rows: three slots, see below)
-//                    [all]      epilogue(t): tcgen05.ld, filter, candidate lists
-//                    [all]      tcgen05 fence, block barrier                       (accumulator t & 1 drained)
-// Round 1 ran MMA(t) -> epilogue(t) back to back in a CTA (one 256-column accumulator) and relied on the second CTA
-// of the SM for overlap: 55 % issue-active, tensor pipe 12 %.
-constexpr int kTC = 128;
-
-template <int D, int KC>
-__global__ void __launch_bounds__(kCandThreads, (D == 64 && KC <= 4) ? 2 : 1) k_tc_candidates(TcPool pool, TcPool tpool, const TcProblem *__restrict__ probs,
-                                                       int n_probs, int mt_per_prob, int n_splits, int cand_stride,
-                                                       TcCand *__restrict__ cand_out, int *__restrict__ work_head)
-{
-    constexpr int KSTEPS = D / 16;
-    constexpr uint32_t SBO = (D / 8) * 128;        // bytes between 8-row groups
-    constexpr uint32_t A_BYTES = kTM * D * 2;      // one of hi / lo
-    constexpr uint32_t B_BYTES = kTC * D * 2;      // one of hi / lo of one stage
-    extern __shared__ __align__(1024) unsigned char sm[];
-    unsigned char *sA_hi = sm, *sA_lo = sm + A_BYTES;
-    unsigned char *sB = sm + 2 * A_BYTES;          // stage s: hi at sB + s * 2 * B_BYTES, lo right behind it
-    // |t|^2 of the train tiles: THREE slots, because the slot of tile t is still read by epilogue(t) when the copies
-    // of tile t + 2 are issued (the operand stage itself is free by then: MMA(t) has completed)
-    float *sTn = reinterpret_cast<float *>(sB + 4 * B_BYTES);
-    __shared__ __align__(8) uint64_t s_bar[4];  // [0], [1] MMA done per accumulator; [2], [3] operands landed per stage
-    __shared__ uint32_t s_tmem;
-    __shared__ int s_item;
-    __shared__ float s_thr[4][kTM];  // filter threshold published by each column quarter of a query row
-
-    const int tid = threadIdx.x, warp = tid >> 5;
-    const int quarter = warp >> 2, qrow = (warp & 3) * 32 + (tid & 31);
-    volatile float *my_thr = &s_thr[quarter][qrow];
-    const volatile float *row_thr = &s_thr[0][qrow];  // the four quarters' thresholds of this row, kTM apart
-    const uint32_t bar_mma = smem_u32(&s_bar[0]), bar_ld = smem_u32(&s_bar[2]);  // + 8 * (accumulator | stage)
-    if (tid == 0) {
-        for (int i = 0; i < 4; i++) mbar_init(smem_u32(&s_bar[i]), 1);
-        mbar_init_fence();
-    }
-    __syncwarp();
-    if (warp == 0) tmem_alloc(smem_u32(&s_tmem), kTmemCols);
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem = s_tmem;
-    const uint32_t idesc = umma_idesc(kTM, kTC);
-    uint32_t ph_mma = 0, ph_ld = 0;  // bit s = parity of barrier s (ph_ld is only used by thread 0)
-    const int total_items = n_probs * mt_per_prob * n_splits;
-
-    for (;;) {
-        __syncthreads();
-        if (tid == 0) s_item = atomicAdd(work_head, 1);
-        __syncthreads();
-        const int item = s_item;
-        if (item >= total_items) break;
-        const int p = item / (mt_per_prob * n_splits);
-        const int rem = item - p * (mt_per_prob * n_splits);
-        const int mt = rem / n_splits, split = rem - mt * n_splits;
-        const TcProblem pr = probs[p];
-        const int nq = pool.count[pr.q_slot], nt = tpool.count[pr.t_slot];
-        const int q0 = mt * kTM;
-        if (q0 >= nq) continue;
-        // train tiles of this split
-        const int n_tiles = (nt + kTC - 1) / kTC;
-        const int per = (n_tiles + n_splits - 1) / n_splits;
-        const int tile0 = split * per, tile1 = min(n_tiles, tile0 + per);
-
-        Cand<KC> best;
-#pragma unroll
-        for (int r = 0; r < KC; r++) {
-            best.d[r] = INFINITY;
-            best.i[r] = -1;
-        }
-        best.worst = INFINITY;
-        best.wslot = 0;
-        float thr = INFINITY;
-        *my_thr = INFINITY;  // read by the partners only after the tile loop's first block barrier (or the merge's)
-        const size_t trow_base = (size_t)pr.t_slot * tpool.slot_rows;
-        // operands arrive by TMA bulk copies (contiguous runs of core matrices), counted on the stage's barrier
-        auto load_train_tile = [&](int tile, int k) {  // k = tile - tile0
-            const int st = k & 1;
-            const size_t row0 = trow_base + (size_t)tile * kTC;
-            const uint32_t bar = bar_ld + 8 * st;
-            unsigned char *hi = sB + (size_t)st * 2 * B_BYTES;
-            bulk_g2s(smem_u32(hi), tpool.hi + row0 * D, B_BYTES, bar);
-            bulk_g2s(smem_u32(hi + B_BYTES), tpool.lo + row0 * D, B_BYTES, bar);
-            bulk_g2s(smem_u32(sTn + (k % 3) * kTC), tpool.norm + row0, kTC * sizeof(float), bar);
-        };
-        auto issue_mma = [&](int k) {  // thread 0: operands of stage k & 1 have landed; accumulator k & 1 is drained
-            const int st = k & 1;
-            mbar_wait(bar_ld + 8 * st, (ph_ld >> st) & 1);
-            ph_ld ^= 1u << st;
-            tc_fence_after();
-            const uint32_t a_hi = smem_u32(sA_hi), a_lo = smem_u32(sA_lo);
-            const uint32_t b_hi = smem_u32(sB + (size_t)st * 2 * B_BYTES), b_lo = b_hi + B_BYTES;
-            const uint32_t acc = tmem + (uint32_t)st * kTC;
-#pragma unroll
-            for (int ks = 0; ks < KSTEPS; ks++) {
-                const uint32_t ko = ks * 256;  // two core matrices (16 K-elements) per step
-                umma_bf16(acc, umma_desc(a_hi + ko, 128, SBO), umma_desc(b_hi + ko, 128, SBO), idesc, ks > 0);
-            }
-#pragma unroll
-            for (int ks = 0; ks < KSTEPS; ks++) {
-                const uint32_t ko = ks * 256;
-                umma_bf16(acc, umma_desc(a_hi + ko, 128, SBO), umma_desc(b_lo + ko, 128, SBO), idesc, 1);
-                umma_bf16(acc, umma_desc(a_lo + ko, 128, SBO), umma_desc(b_hi + ko, 128, SBO), idesc, 1);
-            }
-            umma_commit(bar_mma + 8 * st);
-        };
-        if (tid == 0 && tile0 < tile1) {
-            const size_t e0 = ((size_t)pr.q_slot * pool.slot_rows + q0) * D;
-            mbar_expect_tx(bar_ld, 2 * A_BYTES + 2 * B_BYTES + kTC * sizeof(float));
-            bulk_g2s(smem_u32(sA_hi), pool.hi + e0, A_BYTES, bar_ld);
-            bulk_g2s(smem_u32(sA_lo), pool.lo + e0, A_BYTES, bar_ld);
-            load_train_tile(tile0, 0);
-            if (tile0 + 1 < tile1) {
-                mbar_expect_tx(bar_ld + 8, 2 * B_BYTES + kTC * sizeof(float));
-                load_train_tile(tile0 + 1, 1);
-            }
-            issue_mma(0);
-        }
-
-        for (int tile = tile0; tile < tile1; tile++) {
-            const int k = tile - tile0, cur = k & 1;
-            const int t0 = tile * kTC;
-            if (tid == 0 && tile + 1 < tile1) issue_mma(k + 1);  // runs under this tile's epilogue
-            mbar_wait(bar_mma + 8 * cur, (ph_mma >> cur) & 1);    // accumulator `cur` complete; its operand stage is free
-            ph_mma ^= 1u << cur;
-            tc_fence_after();
-            if (tid == 0 && tile + 2 < tile1) {
-                mbar_expect_tx(bar_ld + 8 * cur, 2 * B_BYTES + kTC * sizeof(float));
-                load_train_tile(tile + 2, k + 2);
-            }
-
-            // ---- epilogue: 16 warps; warp w reads TMEM lanes 32*(w%4).. (its query rows) and the column
-            //      quarter w/4, so four threads share a query row and each keeps its own list.  The filter
-            //      threshold `thr` is the smallest of the four lists' worst kept values: each of them is >= the
-            //      KC-th smallest value of the whole row, so nothing that belongs to the row's KC smallest is
-            //      ever rejected, and every value a list rejects or evicts is >= the final thr.
-            const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)cur * kTC;
-            const float *tn = sTn + (k % 3) * kTC;
-            const int lim = min(kTC, nt - t0);
-            const int c0 = quarter * (kTC / 4);
-            {
-                float v[32];
-                tmem_ld32(lane_addr + c0, v);
-                thr = fminf(fminf(thr, row_thr[0]), fminf(row_thr[kTM], fminf(row_thr[2 * kTM], row_thr[3 * kTM])));
-                if (c0 < lim) {
-#pragma unroll
-                    for (int c = 0; c < 32; c += 4) {
-                        const float4 t4 = *reinterpret_cast<const float4 *>(tn + c0 + c);
-                        // |t|^2 - 2 q.t  (+ |q|^2 later); padded train rows carry |t|^2 = inf
-                        const float d0 = fmaf(-2.f, v[c], t4.x), d1 = fmaf(-2.f, v[c + 1], t4.y);
-                        const float d2 = fmaf(-2.f, v[c + 2], t4.z), d3 = fmaf(-2.f, v[c + 3], t4.w);
-                        if (fminf(fminf(d0, d1), fminf(d2, d3)) < thr) {  // one test per four columns
-                            const int idx = t0 + c0 + c;
-                            if (d0 < thr) { cand_replace_worst(best, d0, idx); thr = fminf(thr, best.worst); }
-                            if (d1 < thr) { cand_replace_worst(best, d1, idx + 1); thr = fminf(thr, best.worst); }
-                            if (d2 < thr) { cand_replace_worst(best, d2, idx + 2); thr = fminf(thr, best.worst); }
-                            if (d3 < thr) { cand_replace_worst(best, d3, idx + 3); thr = fminf(thr, best.worst); }
-                        }
-                    }
-                }
-                *my_thr = thr;
-            }
-            tc_fence_before();
-            __syncthreads();  // every warp has drained accumulator `cur` before MMA(t + 2) overwrites it
-        }
-        // ---- merge the four quarter lists of every query row into one list of the KC smallest values.  The
-        //      scratch aliases the operand stages: every MMA that read them has completed (bar_mma), no copy is in
-        //      flight, and the next item's bulk copies are issued only after the proxy fence and the barrier at the
-        //      loop top.
-        struct Ent {
-            float d;
-            int i;
-        };
-        static_assert(sizeof(Ent) * kTM * 4 * KC <= 4 * B_BYTES, "merge scratch must fit the operand stages");
-        Ent *s_merge = reinterpret_cast<Ent *>(sB);  // [row][quarter][KC]
-#pragma unroll
-        for (int r = 0; r < KC; r++) s_merge[(qrow * 4 + quarter) * KC + r] = Ent{best.d[r], best.i[r]};
-        *my_thr = thr;
-        __syncthreads();
-        if (tid < kTM) {
-            const int row = tid;
-            Cand<KC> m;
-#pragma unroll
-            for (int r = 0; r < KC; r++) {
-                m.d[r] = INFINITY;
-                m.i[r] = -1;
-            }
-            m.worst = INFINITY;
-            m.wslot = 0;
-            for (int e = 0; e < 4 * KC; e++) {
-                const Ent en = s_merge[row * 4 * KC + e];
-                if (en.i >= 0 && en.d < m.worst) cand_replace_worst(m, en.d, en.i);
-            }
-            if (q0 + row < nq) {
-                TcCand o;
-#pragma unroll
-                for (int r = 0; r < kCand; r++) {
-                    o.d[r] = r < KC ? m.d[r < KC ? r : 0] : INFINITY;
-                    o.i[r] = r < KC ? m.i[r < KC ? r : 0] : -1;
-                }
-                // lower bound of every value of this split that is not in the list: what the quarter lists
-                // rejected or evicted (>= their final thresholds) and what the merge dropped (>= the list's worst)
-                const float bound = fminf(fminf(s_thr[0][row], s_thr[1][row]), fminf(s_thr[2][row], s_thr[3][row]));
-                o.worst = fminf(bound, m.worst);
-                cand_out[(size_t)(p * n_splits + split) * cand_stride + q0 + row] = o;
-            }
-        }
-        fence_async_smem();  // generic-proxy accesses to the stages before the next bulk copy overwrites them
-    }
-    __syncthreads();
-    if (warp == 0) tmem_dealloc(tmem, kTmemCols);
-}
-
-size_t tc_candidates_smem(int dim) { return (size_t)(2 * kTM + 4 * kTC) * dim * 2 + 3 * kTC * sizeof(float) + 1024; }
-#else
-
+// The filtered-list candidate kernel (any k <= 4, any number of train rows): one 256-column accumulator per CTA,
+// MMA(t) -> epilogue(t) back to back, two CTAs per SM overlap each other.  It serves k = 3, 4 and train sets of more
+// than 2^14 rows per split (a database); for k <= 2 against a frame's keypoints the key kernels below replace it.
 template <int D, int KC>
 __global__ void __launch_bounds__(kCandThreads, (D == 64 && KC <= 4) ? 2 : 1) k_tc_candidates(TcPool pool, TcPool tpool, const TcProblem *__restrict__ probs,
                                                        int n_probs, int mt_per_prob, int n_splits, int cand_stride,
@@ -640,7 +428,6 @@ __global__ void __launch_bounds__(kCandThreads, (D == 64 && KC <= 4) ? 2 : 1) k_
 
 
 size_t tc_candidates_smem(int dim) { return (size_t)(2 * kTM + 2 * kTN) * dim * 2 + 2 * kTN * sizeof(float) + 1024; }
-#endif
 
 // ------------------------------------------------------------------------------------------------
 // K5b', the candidate kernel for k <= 2 and train splits of at most 2^14 rows (a frame's keypoints): the epilogue is
@@ -871,6 +658,326 @@ __global__ void __launch_bounds__(kCandThreads, D == 64 ? 2 : 1) k_tc_candidates
     }
     __syncthreads();
     if (warp == 0) tmem_dealloc(tmem, kTmemCols);
+}
+
+constexpr int kTP = 128;  // train rows per tile of the warp-specialised kernel
+
+// Warp-specialised form of the key kernel, ONE CTA per SM with the whole TMEM: 16 epilogue warps, an MMA warp and a copy
+// warp; no block barrier inside an item.  What the earlier pipelined forms showed (profiles/r2): (1) with two operand
+// stages the bulk copy of tile k + 1 can only start when MMA(k - 1) has released its stage and takes longer than MMA(k);
+// (2) ONE producer warp doing waits, biased norms, descriptor arithmetic, 12 MMAs and the copies of a tile executes
+// ~400 dependent instructions per tile, ~1 us, which is longer than the epilogue of a tile: the epilogue warps waited
+// for the tensor core (30 % of the stall samples at the mma_done wait) while the tensor pipe was 21-26 % busy.  Here
+//   * NS operand stages (4 for 64-d rows: copies run up to four tiles ahead) and NA = 4 accumulators of 128 TMEM columns;
+//   * the MMA warp does nothing but: operands landed, accumulator drained -> 3 * KSTEPS tcgen05.mma (descriptors are
+//     one base per operand plus constants) -> commit; the copy warp does the bulk copies and the biased |t|^2;
+//   * an epilogue warp gives its part of an accumulator back as soon as tcgen05.ld has put it into registers, BEFORE
+//     the key arithmetic, and has the tcgen05.ld of the next tile in flight under the arithmetic of the current one
+//     (two register buffers of 32 columns).
+// Barriers (mbarrier, parity kept per thread):
+//     ld_done[s]   operands of a tile have landed            (bulk copies, expect_tx)        MMA warp, copy warp wait
+//     tnb_ready[q] biased |t|^2 of the tile are written      (copy warp, one arrival)        epilogue warps wait
+//     mma_done[a]  accumulator complete, operand stage free  (tcgen05.commit)                epilogue warps, copy warp wait
+//     drained[a]   accumulator is in registers               (16 arrivals)                   MMA warp waits
+// s = tile % NS, a = tile % NA, q = tile % 16.  sTnB has sixteen slots: the copy warp writes slot q of tile k after it
+// has seen MMA(k - 1) complete; that MMA was issued after drained(k - 1 - NA), i.e. after every epilogue warp had loaded
+// accumulator k - 1 - NA and therefore finished the arithmetic of tile k - 2 - NA >= k - 16.
+constexpr int kEpiWarps = 16;
+constexpr int kWsThreads = (kEpiWarps + 2) * 32;  // + the MMA warp and the copy warp
+constexpr int kWsAcc = 4;       // accumulators (x 128 columns = the SM's 512 TMEM columns)
+constexpr int kWsSlots = 16;    // sTnB slots
+
+__host__ __device__ constexpr int ws_stages(int dim) { return dim == 64 ? 4 : 2; }
+size_t tc_candidates3w_smem(int dim)
+{
+    return (size_t)(2 * kTM + 2 * ws_stages(dim) * kTP) * dim * 2 + (ws_stages(dim) + kWsSlots) * kTP * sizeof(float) + 1024;
+}
+
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&r)[32])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+// completes every tcgen05.ld of this thread; the registers pass through the asm so that no use is scheduled above it
+__device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[32])
+{
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                   "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]),
+                   "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]),
+                   "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+                 :
+                 : "memory");
+}
+
+template <int D>
+__global__ void __launch_bounds__(kWsThreads, 1) k_tc_candidates3w(TcPool pool, TcPool tpool, const TcProblem *__restrict__ probs,
+                                                         int n_probs, int mt_per_prob, int n_splits, int cand_stride,
+                                                         TcCand *__restrict__ cand_out, int *__restrict__ work_head, int idx_bits, uint32_t key_mul)
+{
+    constexpr int NS = ws_stages(D), NA = kWsAcc, NQ = kWsSlots;
+    constexpr int KSTEPS = D / 16;
+    constexpr uint32_t SBO = (D / 8) * 128;        // bytes between 8-row groups
+    constexpr uint32_t A_BYTES = kTM * D * 2;      // one of hi / lo
+    constexpr uint32_t B_BYTES = kTP * D * 2;      // one of hi / lo of one stage
+    extern __shared__ __align__(1024) unsigned char sm[];
+    unsigned char *sA_hi = sm, *sA_lo = sm + A_BYTES;
+    unsigned char *sB = sm + 2 * A_BYTES;          // stage s: hi at sB + s * 2 * B_BYTES, lo right behind it
+    float *sTn = reinterpret_cast<float *>(sB + 2 * NS * B_BYTES);  // |t|^2 of the train tiles, one slot per stage (bulk copies)
+    float *sTnB = sTn + NS * kTP;                                    // 2^(s-9) + sigma (|t|^2 + off), NQ slots
+    __shared__ __align__(8) uint64_t s_bar[2 * NA + NS + NQ];
+    __shared__ uint32_t s_tmem;
+    __shared__ int s_item;
+
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // provably warp-uniform: the producer's code stays on the uniform datapath
+    const bool producer = warp >= kEpiWarps;
+    const int quarter = warp >> 2, qrow = (warp & 3) * 32 + lane;
+    const uint32_t bar_mma = smem_u32(&s_bar[0]), bar_dr = smem_u32(&s_bar[NA]);   // + 8 * accumulator
+    const uint32_t bar_ld = smem_u32(&s_bar[2 * NA]);                               // + 8 * stage
+    const uint32_t bar_tnb = smem_u32(&s_bar[2 * NA + NS]);                         // + 8 * slot
+    if (tid == 0) {
+        for (int i = 0; i < NA; i++) {
+            mbar_init(bar_mma + 8 * i, 1);
+            mbar_init(bar_dr + 8 * i, kEpiWarps);
+        }
+        for (int i = 0; i < NS; i++) mbar_init(bar_ld + 8 * i, 1);
+        for (int i = 0; i < NQ; i++) mbar_init(bar_tnb + 8 * i, 1);
+        mbar_init_fence();
+    }
+    __syncwarp();
+    if (warp == 0) tmem_alloc(smem_u32(&s_tmem), NA * kTP);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = s_tmem;
+    const uint32_t idesc = umma_idesc(kTM, kTP);
+    // parities of the next phase to wait for, one word: bits 0-3 mma_done[a], bits 8-23 ld_done[s] (MMA and copy warp)
+    // or tnb_ready[q] (epilogue), bits 16-19 drained[a] (MMA warp)
+    uint32_t ph = 0;
+    const int total_items = n_probs * mt_per_prob * n_splits;
+    const int vbits = 32 - idx_bits;                                  // bits of the quantised value
+    const uint32_t pad_field = (1u << vbits) - 1u;                    // value field of a padded train row and of an empty entry
+    const uint32_t idx_mask = (1u << idx_bits) - 1u;
+    const float base2 = __uint_as_float((uint32_t)(127 + idx_bits - 9) << 23);          // 2^(s-9)
+    const float pad_val = __uint_as_float(((uint32_t)(127 + idx_bits - 8) << 23) - 1);   // just under 2^(s-8)
+    const float grid = __uint_as_float((uint32_t)(127 - vbits) << 23);                   // 2^-vbits
+
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) s_item = atomicAdd(work_head, 1);
+        __syncthreads();
+        const int item = s_item;
+        if (item >= total_items) break;
+        const int p = item / (mt_per_prob * n_splits);
+        const int rem = item - p * (mt_per_prob * n_splits);
+        const int mt = rem / n_splits, split = rem - mt * n_splits;
+        const TcProblem pr = probs[p];
+        const int nq = pool.count[pr.q_slot], nt = tpool.count[pr.t_slot];
+        const int q0 = mt * kTM;
+        if (q0 >= nq) continue;
+        const int n_tiles = (nt + kTP - 1) / kTP;
+        const int per = (n_tiles + n_splits - 1) / n_splits;
+        const int tile0 = split * per, tile1 = min(n_tiles, tile0 + per);
+        const int nk = max(tile1 - tile0, 0);
+        // value range of |t|^2 - 2 q.t over the two slots: [-max|q|^2, 2 max|t|^2 + max|q|^2]
+        const float nsum = pool.max_norm[pr.q_slot] + tpool.max_norm[pr.t_slot];
+        const float off = pool.max_norm[pr.q_slot] + 0.01f * nsum;
+        const float sigma = 1.f / (2.04f * nsum + 1e-30f);
+
+        uint32_t m1 = pad_field << idx_bits, m2 = m1, m3 = m1;  // empty entries: the value field of a padded row
+        int pos = -1;                                            // first split row of the last chunk scanned
+        if (warp == kEpiWarps) {
+            // ---- MMA warp: operands landed + accumulator drained -> 3 * KSTEPS tcgen05.mma and the commit
+            const uint64_t da_hi = umma_desc(smem_u32(sA_hi), 128, SBO), da_lo = umma_desc(smem_u32(sA_lo), 128, SBO);
+            const uint64_t db0 = umma_desc(smem_u32(sB), 128, SBO);
+            for (int k = 0; k < nk; k++) {
+                const int st = k % NS, ac = k % NA;
+                mbar_wait(bar_ld + 8 * st, (ph >> (8 + st)) & 1);  // operands of tile k have landed
+                ph ^= 256u << st;
+                if (k >= NA) {  // accumulator ac was last used by tile k - NA
+                    mbar_wait(bar_dr + 8 * ac, (ph >> (16 + ac)) & 1);
+                    ph ^= 65536u << ac;
+                }
+                // descriptors differ by constants only: +16 (256 bytes) per K step, + st * 2 * B_BYTES per stage
+                const uint64_t db_hi = db0 + (uint64_t)((uint32_t)st * (2 * B_BYTES >> 4)), db_lo = db_hi + (B_BYTES >> 4);
+                const uint32_t acc = tmem + (uint32_t)ac * kTP;
+                if (lane == 0) {
+                    tc_fence_after();
+#pragma unroll
+                    for (int ks = 0; ks < KSTEPS; ks++) {
+                        if (ks == 0) umma_bf16_first(acc, da_hi, db_hi, idesc);
+                        else umma_bf16_acc(acc, da_hi + 16 * ks, db_hi + 16 * ks, idesc);
+                    }
+#pragma unroll
+                    for (int ks = 0; ks < KSTEPS; ks++) {
+                        umma_bf16_acc(acc, da_hi + 16 * ks, db_lo + 16 * ks, idesc);
+                        umma_bf16_acc(acc, da_lo + 16 * ks, db_hi + 16 * ks, idesc);
+                    }
+                    umma_commit(bar_mma + 8 * ac);
+                }
+                __syncwarp();
+            }
+            for (int k = max(nk - NA, 0); k < nk; k++) {  // every completion is waited for exactly once: the last NA drains
+                const int ac = k % NA;
+                mbar_wait(bar_dr + 8 * ac, (ph >> (16 + ac)) & 1);
+                ph ^= 65536u << ac;
+            }
+        } else if (warp == kEpiWarps + 1) {
+            // ---- copy warp: bulk copies NS tiles ahead, biased |t|^2 of every tile that lands
+            const size_t trow_base = (size_t)pr.t_slot * tpool.slot_rows;
+            auto load_train_tile = [&](int k) {  // lane 0: arms the stage's barrier and starts the three copies
+                const int st = k % NS;
+                const size_t row0 = trow_base + (size_t)(tile0 + k) * kTP;
+                const uint32_t bar = bar_ld + 8 * st;
+                unsigned char *hi = sB + (size_t)st * 2 * B_BYTES;
+                mbar_expect_tx(bar, 2 * B_BYTES + kTP * sizeof(float) + (k == 0 ? 2 * A_BYTES : 0));
+                bulk_g2s(smem_u32(hi), tpool.hi + row0 * D, B_BYTES, bar);
+                bulk_g2s(smem_u32(hi + B_BYTES), tpool.lo + row0 * D, B_BYTES, bar);
+                bulk_g2s(smem_u32(sTn + st * kTP), tpool.norm + row0, kTP * sizeof(float), bar);
+            };
+            if (lane == 0 && nk > 0) {
+                const size_t e0 = ((size_t)pr.q_slot * pool.slot_rows + q0) * D;
+                load_train_tile(0);  // its barrier also counts the query tile
+                bulk_g2s(smem_u32(sA_hi), pool.hi + e0, A_BYTES, bar_ld);
+                bulk_g2s(smem_u32(sA_lo), pool.lo + e0, A_BYTES, bar_ld);
+                for (int k = 1; k < min(NS, nk); k++) load_train_tile(k);
+            }
+            for (int k = 0; k < nk; k++) {
+                const int st = k % NS, q = k % NQ;
+                mbar_wait(bar_ld + 8 * st, (ph >> (8 + st)) & 1);  // |t|^2 of tile k have landed
+                ph ^= 256u << st;
+                {
+                    const float4 t4 = *reinterpret_cast<const float4 *>(sTn + st * kTP + lane * 4);
+                    float4 o4;
+                    o4.x = t4.x < INFINITY ? fmaf(t4.x + off, sigma, base2) : pad_val;
+                    o4.y = t4.y < INFINITY ? fmaf(t4.y + off, sigma, base2) : pad_val;
+                    o4.z = t4.z < INFINITY ? fmaf(t4.z + off, sigma, base2) : pad_val;
+                    o4.w = t4.w < INFINITY ? fmaf(t4.w + off, sigma, base2) : pad_val;
+                    *reinterpret_cast<float4 *>(sTnB + q * kTP + lane * 4) = o4;
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_tnb + 8 * q);
+                const int ao = k % NA;  // MMA(k) complete: its operand stage (and sTn slot, read above) takes tile k + NS
+                mbar_wait(bar_mma + 8 * ao, (ph >> ao) & 1);
+                ph ^= 1u << ao;
+                fence_async_smem();  // the generic reads of sTn[st] above, before the copy that overwrites it
+                if (lane == 0 && k + NS < nk) load_train_tile(k + NS);
+            }
+        } else if (nk > 0) {
+            const float m2sigma = -2.f * sigma;
+            const int c0 = quarter * (kTP / 4);
+            const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)c0;
+            auto start_load = [&](int k, uint32_t (&r)[32]) {  // accumulator of tile k -> registers (asynchronous)
+                const int ac = k % NA;
+                mbar_wait(bar_mma + 8 * ac, (ph >> ac) & 1);
+                ph ^= 1u << ac;
+                tc_fence_after();
+                tmem_ld32_nowait(lane_addr + (uint32_t)(ac * kTP), r);
+            };
+            auto finish_load = [&](int k, uint32_t (&r)[32]) {  // the registers are valid; hand the accumulator back
+                tmem_ld_wait(r);
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_dr + 8 * (k % NA));
+            };
+            auto keys = [&](int k, const uint32_t (&r)[32]) {
+                const int q = k % NQ;
+                mbar_wait(bar_tnb + 8 * q, (ph >> (8 + q)) & 1);  // (long since complete: it precedes the MMA's issue)
+                ph ^= 256u << q;
+                if (c0 < min(kTP, nt - (tile0 + k) * kTP)) {  // else a chunk of padding rows only: nothing to keep
+                    const float *tn = sTnB + q * kTP + c0;
+                    const int idx0 = k * kTP + c0;
+                    const uint32_t delta = pos < 0 ? 0u : (uint32_t)(idx0 - pos);
+                    pos = idx0;
+                    m1 += delta;
+                    m2 += delta;
+                    m3 += delta;
+#pragma unroll
+                    for (int c = 0; c < 32; c += 4) {
+                        const float4 t4 = *reinterpret_cast<const float4 *>(tn + c);
+                        const uint32_t k0 = __float_as_uint(fmaf(__uint_as_float(r[c]), m2sigma, t4.x)) * key_mul + (31 - c);
+                        const uint32_t k1 = __float_as_uint(fmaf(__uint_as_float(r[c + 1]), m2sigma, t4.y)) * key_mul + (30 - c);
+                        const uint32_t k2 = __float_as_uint(fmaf(__uint_as_float(r[c + 2]), m2sigma, t4.z)) * key_mul + (29 - c);
+                        const uint32_t k3 = __float_as_uint(fmaf(__uint_as_float(r[c + 3]), m2sigma, t4.w)) * key_mul + (28 - c);
+                        key_insert_pair(m1, m2, m3, k0, k1);
+                        key_insert_pair(m1, m2, m3, k2, k3);
+                    }
+                }
+            };
+            uint32_t va[32], vb[32];
+            start_load(0, va);
+            for (int k = 0; k < nk; k += 2) {  // two tiles per trip: the register buffers keep their names
+                finish_load(k, va);
+                if (k + 1 < nk) start_load(k + 1, vb);
+                keys(k, va);
+                if (k + 1 < nk) {
+                    finish_load(k + 1, vb);
+                    if (k + 2 < nk) start_load(k + 2, va);
+                    keys(k + 1, vb);
+                }
+            }
+        }
+        // ---- merge the four quarter lists of every query row.  The scratch aliases the operand stages: every MMA that
+        //      read them has completed, no copy is in flight (the producer has waited for everything it started), and the
+        //      next item's bulk copies are issued only after the proxy fence and the barrier at the loop top.
+        uint32_t *s_merge = reinterpret_cast<uint32_t *>(sB);  // [row][quarter][3]
+        if (!producer) {  // (an epilogue warp has itself seen the last MMA complete)
+            auto absolute = [&](uint32_t m) {  // relative, descending index field -> row of the split
+                return (m & ~idx_mask) | (((uint32_t)(pos + 31) - (m & idx_mask)) & idx_mask);
+            };
+            s_merge[(qrow * 4 + quarter) * 3 + 0] = absolute(m1);
+            s_merge[(qrow * 4 + quarter) * 3 + 1] = absolute(m2);
+            s_merge[(qrow * 4 + quarter) * 3 + 2] = absolute(m3);
+        }
+        __syncthreads();
+        if (tid < kTM && q0 + tid < nq) {
+            const int row = tid;
+            uint32_t best[5] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
+            uint32_t third = 0xffffffffu;  // smallest of the four lists' third entries
+#pragma unroll
+            for (int e = 0; e < 12; e++) {
+                uint32_t x = s_merge[row * 12 + e];
+                if (e % 3 == 2) third = min(third, x);
+#pragma unroll
+                for (int r = 0; r < 5; r++) {  // sorted insertion, branch-free
+                    const uint32_t lo = min(best[r], x);
+                    x = max(best[r], x);
+                    best[r] = lo;
+                }
+            }
+            const float inv_sigma = 2.04f * nsum + 1e-30f;
+            TcCand o;
+#pragma unroll
+            for (int r = 0; r < kCand; r++) {
+                o.d[r] = INFINITY;
+                o.i[r] = -1;
+            }
+#pragma unroll
+            for (int r = 0; r < 4; r++) {
+                const uint32_t field = best[r] >> idx_bits;
+                if (field != pad_field) {
+                    o.d[r] = (float)field * grid * inv_sigma - off;
+                    o.i[r] = tile0 * kTP + (int)(best[r] & idx_mask);
+                }
+            }
+            // lower bound of every value of this split that is not among the four candidates (see k_tc_candidates3)
+            const uint32_t bfield = min(third, best[4]) >> idx_bits;
+            o.worst = bfield != pad_field ? ((float)bfield - 2.5f) * grid * inv_sigma - off - 2e-6f * nsum : INFINITY;
+            cand_out[(size_t)(p * n_splits + split) * cand_stride + q0 + row] = o;
+        }
+        fence_async_smem();  // generic-proxy accesses to the stages before the next bulk copy overwrites them
+    }
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, NA * kTP);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1152,9 +1259,12 @@ void launch_tc_match(const TcMatchArgs &a, cudaStream_t st, int *launches)
     const int mt_per_prob = a.max_q_rows / kTM;
     const bool small_k = a.k <= 2;
     // k <= 2 against train splits of at most 2^14 rows (frame against frame): the branch-free key kernel
-    const int tiles_cap = tp.slot_rows / kTN;
-    const int rows_per_split = (tiles_cap + a.n_splits - 1) / a.n_splits * kTN;
-    static const bool keys_off = getenv("SURF_TC_NO_KEYS") != nullptr;  // measurement knob: the filtered-list kernel
+    static const bool keys_off = getenv("SURF_TC_NO_KEYS") != nullptr;         // measurement knobs: the filtered-list kernel,
+    static const bool keys_serial = getenv("SURF_TC_KEYS_SERIAL") != nullptr;  // the key kernel with MMA and epilogue back to back
+    const bool ws = D == 64 && !keys_serial;  // 128-d rows leave room for two operand stages only: serial key kernel
+    const int tile_rows = ws ? kTP : kTN;
+    const int tiles_cap = (tp.slot_rows + tile_rows - 1) / tile_rows;
+    const int rows_per_split = (tiles_cap + a.n_splits - 1) / a.n_splits * tile_rows;
     if (small_k && rows_per_split <= (1 << 14) && !keys_off) {
         int idx_bits = 9;
         while ((1 << idx_bits) < rows_per_split) idx_bits++;
@@ -1162,9 +1272,13 @@ void launch_tc_match(const TcMatchArgs &a, cudaStream_t st, int *launches)
         if (!attr3_set[dev & 63]) {
             cudaFuncSetAttribute(k_tc_candidates3<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_candidates3_smem(64));
             cudaFuncSetAttribute(k_tc_candidates3<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_candidates3_smem(128));
+            cudaFuncSetAttribute(k_tc_candidates3w<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_candidates3w_smem(64));
             attr3_set[dev & 63] = true;
         }
-        if (D == 64)
+        if (ws)  // one CTA per SM (all 512 TMEM columns)
+            k_tc_candidates3w<64><<<sms, kWsThreads, tc_candidates3w_smem(64), st>>>(
+                a.pool, tp, a.probs, a.n_probs, mt_per_prob, a.n_splits, a.max_q_rows, a.cand, a.counters, idx_bits, 1u << idx_bits);
+        else if (D == 64)
             k_tc_candidates3<64><<<2 * sms, kCandThreads, tc_candidates3_smem(64), st>>>(
                 a.pool, tp, a.probs, a.n_probs, mt_per_prob, a.n_splits, a.max_q_rows, a.cand, a.counters, idx_bits, 1u << idx_bits);
         else

@@ -25,6 +25,12 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
 
+// one arrival (release: this thread's earlier writes are visible to whoever sees the phase complete)
+__device__ __forceinline__ void mbar_arrive(uint32_t bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
 // Spins on the barrier's phase `parity`; false if it has not completed after ~2^24 polls.
 __device__ __forceinline__ bool mbar_wait_bounded(uint32_t bar, uint32_t parity)
 {
