@@ -483,16 +483,24 @@ def measure_latency(ctx: Ctx, eng, frames: np.ndarray, D: int, reps: int = 30):
         kps = torch.empty((nb * CAP, 7), dtype=torch.float32).pin_memory()
         desc = torch.empty((nb * CAP, D), dtype=torch.float32).pin_memory()
         off = np.zeros(nb + 1, np.int32)
-        ts = []
-        for r in range(reps + 5):
-            t0 = time.perf_counter()
-            eng.submit(h_in.data_ptr(), MEM_HOST, nb, W, H, W, W * H, True)
-            eng.collect(kps.data_ptr(), desc.data_ptr(), MEM_HOST, nb * CAP, off)
-            ts.append((time.perf_counter() - t0) * 1e3)
-        ts = np.array(ts[5:])
+        def calls(graphs: bool):
+            eng.set_graphs(graphs)
+            ts = []
+            for r in range(reps + 8):
+                t0 = time.perf_counter()
+                eng.submit(h_in.data_ptr(), MEM_HOST, nb, W, H, W, W * H, True)
+                eng.collect(kps.data_ptr(), desc.data_ptr(), MEM_HOST, nb * CAP, off)
+                ts.append((time.perf_counter() - t0) * 1e3)
+            return np.array(ts[8:])
+
+        ts_eager = calls(False)
+        r0 = eng.graph_replays()
+        ts = calls(True)   # the default: the launch sequence replayed as a CUDA graph
         out[f"batch{nb}"] = {"ms_per_call_median": float(np.median(ts)), "ms_p10": float(np.quantile(ts, 0.1)),
                              "ms_p90": float(np.quantile(ts, 0.9)), "ms_per_frame": float(np.median(ts) / nb),
                              "frames_per_s": float(nb / np.median(ts) * 1e3), "keypoints": int(off[nb]),
+                             "graph_replays": int(eng.graph_replays() - r0), "calls": int(reps + 8),
+                             "eager_ms_per_call_median": float(np.median(ts_eager)),
                              "launches_per_call": int(eng.timings()["launches"]),
                              "device_stage_ms": {k: round(float(v), 4) for k, v in eng.timings().items()
                                                  if k in ("h2d", "integral", "hessian", "sort", "describe", "pack", "d2h", "total")}}

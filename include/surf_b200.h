@@ -194,6 +194,12 @@ int surf_device_matches(surf_engine *e, const surf_dmatch **matches, const uint8
 /* 0: tensor-core candidate search + exact rescoring (default); 1: exact CUDA-core kernel only.
  * Both return identical results. */
 int surf_set_match_mode(surf_engine *e, int exact_only);
+/* Small batches (<= max_batch frames, default 16; 0 keeps the current value): the launch sequence of one submit is
+ * captured into a CUDA graph the second time the same buffers and sizes come round and replayed afterwards (the live,
+ * one-frame-per-tick use of vtkSlicerSurfFeaturesLogic.cxx:1392-1406).  Same kernels, same arguments: identical results.
+ * On by default; surf_graph_replays counts the submits served by a replay. */
+int surf_set_graphs(surf_engine *e, int enable, int max_batch);
+int surf_graph_replays(const surf_engine *e, long *replays);
 /* Number of queries of the last tensor-core match call whose candidate set could not be proven and
  * that were redone by the exact kernel (diagnostic; synchronises the engine stream). */
 int surf_match_redo_count(surf_engine *e, int *count);

@@ -349,10 +349,13 @@ void drop_batches(surf_engine *e)
     e->out_collected = -1;
 }
 
+void drop_graphs(surf_engine *e);
+
 void free_workspace(surf_engine *e)
 {
+    drop_graphs(e);  // they hold the addresses of the buffers freed below
     for (auto &p : e->imgbuf) { cudaFree(p); p = nullptr; }
-    cudaFree(e->d_mask); cudaFree(e->d_sum); cudaFree(e->d_msum); cudaFree(e->d_bandsum);
+    cudaFree(e->d_mask); cudaFree(e->d_sum); cudaFree(e->d_msum); cudaFree(e->d_bandsum); cudaFree(e->d_bandflags);
     cudaFree(e->d_det); cudaFree(e->d_kp_a); cudaFree(e->d_kp_b); cudaFree(e->d_desc);
     cudaFree(e->d_patches); cudaFree(e->d_counts); cudaFree(e->d_ndel);
     cudaFree(e->d_off_in); cudaFree(e->d_misc); cudaFree(e->d_deleted);
@@ -375,7 +378,7 @@ void free_workspace(surf_engine *e)
     e->alt.d_sum = nullptr; e->alt.d_kp_a = e->alt.d_kp_b = e->alt.sorted = nullptr; e->alt.d_counts = nullptr;
     e->alt.tmap_w = 0; e->alt.free_recorded = false;
     e->la.valid = false;
-    e->d_mask = nullptr; e->prefetched.valid = false; e->buf_staged = -1; e->d_sum = e->d_msum = e->d_bandsum = nullptr; e->d_det = nullptr;
+    e->d_mask = nullptr; e->prefetched.valid = false; e->buf_staged = -1; e->d_sum = e->d_msum = e->d_bandsum = nullptr; e->d_bandflags = nullptr; e->d_det = nullptr;
     e->d_kp_a = e->d_kp_b = e->d_out_kp = nullptr; e->d_desc = e->d_out_desc = nullptr; e->d_patches = nullptr;
     e->d_counts = e->d_ndel = e->d_off_in = e->d_off_out = e->d_misc = e->d_deleted = nullptr;
     e->d_match_part = nullptr; e->d_match_io = nullptr; e->h_pin = nullptr; e->d_class_list = nullptr;
@@ -422,6 +425,8 @@ int alloc_workspace(surf_engine *e)
     CU(e, cudaMalloc(&e->d_sum, g.sum_frame * sizeof(uint32_t) * B));
     CU(e, cudaMalloc(&e->d_msum, g.sum_frame * sizeof(uint32_t)));
     CU(e, cudaMalloc(&e->d_bandsum, integral_bandsum_words(W, H, B) * sizeof(uint32_t)));
+    CU(e, cudaMalloc(&e->d_bandflags, integral_flag_words(H, B) * sizeof(int)));
+    CU(e, cudaMemset(e->d_bandflags, 0, integral_flag_words(H, B) * sizeof(int)));
     const size_t nk = (size_t)B * cap;
     CU(e, cudaMalloc(&e->d_kp_a, nk * sizeof(surf_keypoint)));
     CU(e, cudaMalloc(&e->d_kp_b, nk * sizeof(surf_keypoint)));
@@ -580,12 +585,18 @@ int stage_mask(surf_engine *e, const BatchIn &in, const FrameGeo &geo, const uin
         m.pitch = e->img_pitch;
     }
     m.frame_stride = 0;
-    launch_integral(m, 1, geo, e->d_msum, e->d_bandsum, 1, e->stream, &e->launches);
+    launch_integral(m, 1, geo, e->d_msum, e->d_bandsum, e->d_bandflags, 1, e->stream, &e->launches);
     *msum = e->d_msum;
     return SURF_OK;
 }
 
-void rec(surf_engine *e, Ev which) { cudaEventRecord(e->ev[which], e->stream); }  // e->ev: the batch's event array
+// e->ev: the batch's event array.  Inside a stream capture the record is an "external" node: the event is really
+// recorded when the graph runs, so the stage timings and the cross-stream waits on these events keep working.
+void rec_event(surf_engine *e, cudaEvent_t ev)
+{
+    cudaEventRecordWithFlags(ev, e->stream, e->capturing ? cudaEventRecordExternal : cudaEventRecordDefault);
+}
+void rec(surf_engine *e, Ev which) { rec_event(e, e->ev[which]); }
 
 // integral -> Hessian pyramid -> maxima -> sort.  Leaves sorted raw keypoints in e->sorted.
 int run_detect(surf_engine *e, const ImageRef &img, const uint32_t *msum, const FrameGeo &geo, int B)
@@ -593,7 +604,7 @@ int run_detect(surf_engine *e, const ImageRef &img, const uint32_t *msum, const 
     NvtxRange nvtx("surf:stages1-3 integral+hessian+maxima+sort");
     const surf_params &p = e->params;
     launch_zero(e->d_counts, B + 1, e->stream, &e->launches);  // per-frame counters + status word
-    launch_integral(img, B, geo, e->d_sum, e->d_bandsum, 0, e->stream, &e->launches);
+    launch_integral(img, B, geo, e->d_sum, e->d_bandsum, e->d_bandflags, 0, e->stream, &e->launches);
     rec(e, EV_INTEGRAL);
     const float thr = (float)p.hessian_threshold;
     float *det = e->d_det;
@@ -616,9 +627,20 @@ int run_detect(surf_engine *e, const ImageRef &img, const uint32_t *msum, const 
     rec(e, EV_HESSIAN_NMS);
     e->sorted = launch_sort(e->d_kp_a, e->d_kp_b, e->d_counts, e->cap, B, e->stream, &e->launches);
     rec(e, EV_SORT);
-    CU(e, cudaEventRecord(e->ev_detect_done, e->stream));
+    rec_event(e, e->ev_detect_done);
     e->detect_done_recorded = true;
     CU(e, cudaGetLastError());
+    return SURF_OK;
+}
+
+// The output set about to be written: its previous batch's result copies, stream matcher (own stream) and match copies
+// may still be reading it.  (Run before a stream capture begins: these are events of work outside the graph.)
+int wait_out_set_readers(surf_engine *e)
+{
+    OutSet &o = e->out[e->out_bound];
+    if (o.copies_in_flight) CU(e, cudaStreamWaitEvent(e->stream, o.ev_copy_done, 0));
+    if (o.match_in_flight) CU(e, cudaStreamWaitEvent(e->stream, o.ev_match_done, 0));
+    o.copies_in_flight = o.match_in_flight = false;
     return SURF_OK;
 }
 
@@ -658,10 +680,7 @@ int run_describe_pack(surf_engine *e, const ImageRef &img, const FrameGeo &geo, 
     if (pack) {
         // the output set being written: its previous batch's result copies, stream matcher (own stream) and match
         // copies may still be reading it
-        OutSet &o = e->out[e->out_bound];
-        if (o.copies_in_flight) CU(e, cudaStreamWaitEvent(e->stream, o.ev_copy_done, 0));
-        if (o.match_in_flight) CU(e, cudaStreamWaitEvent(e->stream, o.ev_match_done, 0));
-        o.copies_in_flight = o.match_in_flight = false;
+        if (int rcw = wait_out_set_readers(e)) return rcw;
         launch_offsets(e->d_counts, e->d_ndel, e->cap, B, e->d_off_out, e->stream, &e->launches);
         launch_pack(e->sorted, want_desc ? e->d_desc : nullptr, p.extended ? 128 : 64, e->cap, B, e->d_off_in, e->d_ndel,
                     e->d_deleted, e->d_off_out, e->d_out_kp, want_desc ? e->d_out_desc : nullptr, e->stream,
@@ -669,7 +688,7 @@ int run_describe_pack(surf_engine *e, const ImageRef &img, const FrameGeo &geo, 
     }
     rec(e, EV_PACK);
     // the detect set (integral images, keypoints, counters) is free for a look-ahead once these kernels end
-    CU(e, cudaEventRecord(e->ev_set_free, e->stream));
+    rec_event(e, e->ev_set_free);
     e->set_free_recorded = true;
     CU(e, cudaGetLastError());
     return SURF_OK;
@@ -685,7 +704,88 @@ int fetch_counts(surf_engine *e, int B)
     CU(e, cudaMemcpyAsync(h + 3 * B + 1, e->d_misc, sizeof(int) * kMiscWords, cudaMemcpyDeviceToHost, e->stream));
     CU(e, cudaMemcpyAsync(h + 3 * B + 1 + kMiscWords, e->d_counts + B, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
     // these copies read the detect set's counters: a look-ahead may overwrite the set only after them
-    CU(e, cudaEventRecord(e->ev_set_free, e->stream));
+    rec_event(e, e->ev_set_free);
+    e->set_free_recorded = true;
+    return SURF_OK;
+}
+
+void drop_graphs(surf_engine *e)
+{
+    for (surf_engine::GraphEntry &g : e->graphs)
+        if (g.exec) cudaGraphExecDestroy(g.exec);
+    e->graphs.clear();
+}
+
+// Stages 1-4 and the count copies of one submitted batch (everything between the upload and the result copies).  For
+// small batches the host cost of ~25 launches and ~15 event records is a quarter of the call: the second time the same
+// buffers, sizes and events come round the sequence is captured into a CUDA graph and replayed from then on.  The
+// graph holds exactly the nodes the eager path enqueues (same kernels, same arguments), so results are byte-identical.
+int run_stages(surf_engine *e, const ImageRef &img, const uint32_t *msum, const FrameGeo &geo, int B, bool want_desc)
+{
+    auto eager = [&]() -> int {
+        int rc;
+        if ((rc = run_detect(e, img, msum, geo, B))) return rc;
+        if ((rc = run_describe_pack(e, img, geo, B, want_desc, nullptr, true))) return rc;
+        if ((rc = fetch_counts(e, B))) return rc;
+        rec(e, EV_END);
+        return SURF_OK;
+    };
+    if (!e->use_graphs || B > e->graph_max_batch) return eager();
+    surf_engine::GraphKey key;
+    memset(&key, 0, sizeof(key));
+    key.img = img.ptr; key.msum = msum; key.d_sum = e->d_sum; key.d_kp_a = e->d_kp_a; key.d_kp_b = e->d_kp_b;
+    key.d_counts = e->d_counts; key.ev = e->ev; key.h_pin = e->h_pin; key.pitch = img.pitch; key.fstride = img.frame_stride;
+    key.W = geo.W; key.H = geo.H; key.B = B; key.want_desc = want_desc; key.out_set = e->out_bound; key.cap = e->cap;
+    surf_engine::GraphEntry *g = nullptr;
+    for (surf_engine::GraphEntry &c : e->graphs)
+        if (!memcmp(&c.key, &key, sizeof(key))) g = &c;
+    if (!g) {
+        if (e->graphs.size() >= 32) {  // replace the least recently used entry
+            size_t lru = 0;
+            for (size_t i = 1; i < e->graphs.size(); i++)
+                if (e->graphs[i].last_use < e->graphs[lru].last_use) lru = i;
+            if (e->graphs[lru].exec) cudaGraphExecDestroy(e->graphs[lru].exec);
+            e->graphs.erase(e->graphs.begin() + lru);
+        }
+        e->graphs.emplace_back();
+        g = &e->graphs.back();
+        g->key = key;
+    }
+    g->last_use = ++e->graph_clock;
+    g->seen++;
+    if (g->failed || g->seen < 2) return eager();  // first sighting: eager (one-time allocations and attributes happen here)
+    int rc;
+    if ((rc = wait_out_set_readers(e))) return rc;  // events of work outside the graph: ordered before it on the stream
+    if (!g->exec) {
+        const int launches0 = e->launches;
+        cudaGraph_t graph = nullptr;
+        if (cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeRelaxed) != cudaSuccess) {
+            cudaGetLastError();
+            g->failed = true;
+            return eager();
+        }
+        e->capturing = true;
+        rc = eager();
+        e->capturing = false;
+        const cudaError_t ce = cudaStreamEndCapture(e->stream, &graph);
+        if (rc || ce != cudaSuccess || !graph || cudaGraphInstantiate(&g->exec, graph, 0) != cudaSuccess) {
+            cudaGetLastError();
+            if (graph) cudaGraphDestroy(graph);
+            g->exec = nullptr;
+            g->failed = true;
+            e->launches = launches0;
+            return eager();  // nothing of the capture ran
+        }
+        cudaGraphDestroy(graph);
+        g->sorted = e->sorted;
+        g->launches = e->launches - launches0;
+        e->launches = launches0;
+    }
+    CU(e, cudaGraphLaunch(g->exec, e->stream));
+    e->graph_replays++;
+    e->sorted = g->sorted;
+    e->launches += g->launches;
+    e->detect_done_recorded = true;
     e->set_free_recorded = true;
     return SURF_OK;
 }
@@ -765,6 +865,7 @@ int surf_create(const surf_params *params, int device, int max_width, int max_he
     e->max_b = max_batch;
     e->cap = (max_keypoints + 127) & ~127;
     if (getenv("SURF_B200_NO_TMA")) e->use_tma = 0;
+    if (getenv("SURF_B200_NO_GRAPHS")) e->use_graphs = 0;
     if (const char *v = getenv("SURF_B200_EARLY_UPLOAD")) e->early_upload = atoi(v);
     if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess) {
         delete e;
@@ -873,6 +974,7 @@ int surf_set_params(surf_engine *e, const surf_params *params)
     // pending batches and the stream matcher's predecessor frame were produced with the old parameters
     // (descriptor length, thresholds): neither is carried over
     drop_batches(e);
+    drop_graphs(e);  // thresholds, layer tables and descriptor length are baked into the captured launches
     e->stream_primed = false;
     e->params = *params;
     e->tmap_w = 0;  // layer tables depend on the parameters
@@ -929,11 +1031,13 @@ int surf_submit_batch(surf_engine *e, const uint8_t *images, int in_mem, int bat
     e->launches = 0;
     const FrameGeo geo = make_geo(width, height);
     ImageRef img;
+    bool adopted = false;
     const surf_engine::LookAhead &la = e->la;
     if (la.valid && la.images == images && la.in_mem == in_mem && la.batch == batch && la.width == width && la.height == height &&
         la.pitch == pitch && la.frame_stride == frame_stride && la.mask == mask && la.mask_pitch == mask_pitch) {
         // stages 1-3 of these frames already ran (or are running) on the look-ahead stream: adopt their detect set,
         // their stage events and, for host frames, the frame buffer they were uploaded into
+        adopted = true;
         e->la.valid = false;
         swap_detect_sets(e);
         e->ev = e->la_ev;
@@ -951,11 +1055,13 @@ int surf_submit_batch(surf_engine *e, const uint8_t *images, int in_mem, int bat
         const uint32_t *msum = nullptr;
         if ((rc = stage_mask(e, in, geo, &msum))) return rc;
         rec(e, EV_H2D);
-        if ((rc = run_detect(e, img, msum, geo, batch))) return rc;
+        if ((rc = run_stages(e, img, msum, geo, batch, want_descriptors != 0))) return rc;
     }
-    if ((rc = run_describe_pack(e, img, geo, batch, want_descriptors != 0, nullptr, true))) return rc;
-    if ((rc = fetch_counts(e, batch))) return rc;
-    rec(e, EV_END);
+    if (adopted) {
+        if ((rc = run_describe_pack(e, img, geo, batch, want_descriptors != 0, nullptr, true))) return rc;
+        if ((rc = fetch_counts(e, batch))) return rc;
+        rec(e, EV_END);
+    }
     CU(e, cudaEventRecord(o.ev_ready, e->stream));
     if (in_mem == SURF_MEM_HOST) {  // the staged frames are free again after these kernels
         CU(e, cudaEventRecord(e->ev_buf_free[e->buf_cur], e->stream));
@@ -1249,7 +1355,7 @@ static int describe_given(surf_engine *e, const uint8_t *image, int width, int h
     CU(e, cudaMemcpyAsync(e->d_counts, &n, sizeof(int), cudaMemcpyHostToDevice, e->stream));
     e->sorted = e->d_kp_a;
     rec(e, EV_H2D);
-    launch_integral(img, 1, geo, e->d_sum, e->d_bandsum, 0, e->stream, &e->launches);
+    launch_integral(img, 1, geo, e->d_sum, e->d_bandsum, e->d_bandflags, 0, e->stream, &e->launches);
     rec(e, EV_INTEGRAL);
     rec(e, EV_HESSIAN_NMS);
     rec(e, EV_SORT);
@@ -1319,7 +1425,7 @@ int surf_integral(surf_engine *e, const uint8_t *image, int width, int height, s
     const FrameGeo geo = make_geo(width, height);
     ImageRef img;
     if ((rc = stage_images(e, in, &img))) return rc;
-    launch_integral(img, 1, geo, e->d_sum, e->d_bandsum, clamp01, e->stream, &e->launches);
+    launch_integral(img, 1, geo, e->d_sum, e->d_bandsum, e->d_bandflags, clamp01, e->stream, &e->launches);
     CU(e, cudaGetLastError());
     CU(e, cudaMemcpy2DAsync(sum, sizeof(int32_t) * (width + 1), e->d_sum, sizeof(uint32_t) * geo.SP,
                             sizeof(int32_t) * (width + 1), height + 1, cudaMemcpyDeviceToHost, e->stream));
@@ -1344,7 +1450,7 @@ int surf_hessian_layer(surf_engine *e, const uint8_t *image, int width, int heig
     const FrameGeo geo = make_geo(width, height);
     ImageRef img;
     if ((rc = stage_images(e, in, &img))) return rc;
-    launch_integral(img, 1, geo, e->d_sum, e->d_bandsum, 0, e->stream, &e->launches);
+    launch_integral(img, 1, geo, e->d_sum, e->d_bandsum, e->d_bandflags, 0, e->stream, &e->launches);
     const OctavePat pat = make_octave(octave, lpo, width, height);
     const size_t det_frame = (size_t)pat.lpo * pat.rows * pat.cols;
     launch_hessian(e->d_sum, geo, pat, e->d_det, det_frame, 1, e->stream, &e->launches);
@@ -1489,6 +1595,25 @@ int surf_set_match_mode(surf_engine *e, int exact_only)
 {
     if (!e) return SURF_ERR_BAD_ARG;
     e->match_exact_only = exact_only ? 1 : 0;
+    return SURF_OK;
+}
+
+int surf_set_graphs(surf_engine *e, int enable, int max_batch)
+{
+    if (!e || max_batch < 0) return SURF_ERR_BAD_ARG;
+    e->use_graphs = enable ? 1 : 0;
+    if (max_batch > 0) e->graph_max_batch = max_batch;
+    if (!enable) {
+        cudaStreamSynchronize(e->stream);
+        drop_graphs(e);
+    }
+    return SURF_OK;
+}
+
+int surf_graph_replays(const surf_engine *e, long *replays)
+{
+    if (!e || !replays) return SURF_ERR_BAD_ARG;
+    *replays = (long)e->graph_replays;
     return SURF_OK;
 }
 

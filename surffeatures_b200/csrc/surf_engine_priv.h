@@ -116,6 +116,7 @@ struct surf_engine {
     } la;
     uint8_t *d_mask = nullptr;
     uint32_t *d_sum = nullptr, *d_msum = nullptr, *d_bandsum = nullptr;
+    int *d_bandflags = nullptr;  // ticket / exit counters and per-band flags of the integral kernel
     float *d_det = nullptr;     size_t det_words = 0;
     surf_keypoint *d_kp_a = nullptr, *d_kp_b = nullptr, *d_out_kp = nullptr;
     float *d_desc = nullptr, *d_out_desc = nullptr;  int desc_dim = 0;
@@ -127,6 +128,27 @@ struct surf_engine {
     surf_dmatch *d_match_part = nullptr;  size_t match_part_cap = 0;
     void *d_match_io = nullptr;           size_t match_io_cap = 0;
     int match_exact_only = 0;
+    // CUDA graphs of the small-batch path: the launch sequence of stages 1-4 + the count copies of one submit, keyed on
+    // every pointer and size it bakes in; captured the second time a key is seen, replayed afterwards
+    struct GraphKey {
+        const void *img, *msum, *d_sum, *d_kp_a, *d_kp_b, *d_counts, *ev, *h_pin;
+        size_t pitch, fstride;
+        int W, H, B, want_desc, out_set, cap;
+    };
+    struct GraphEntry {
+        GraphKey key;
+        cudaGraphExec_t exec = nullptr;
+        surf_keypoint *sorted = nullptr;
+        int launches = 0;
+        int seen = 0;
+        bool failed = false;
+        unsigned long last_use = 0;
+    };
+    std::vector<GraphEntry> graphs;
+    int use_graphs = 1;
+    int graph_max_batch = 16;
+    bool capturing = false;
+    unsigned long graph_clock = 0, graph_replays = 0;
     int use_tma = 1;                 // fused TMA-staged Hessian + maxima kernel for octaves 0-1
     CUtensorMap tmap[2];             // integral-image tile maps of octaves 0 and 1
     TileOctave tile_oct[2];

@@ -115,7 +115,8 @@ struct DescribeArgs {
 // ---- launchers (surf_kernels.cu) ----
 int integral_band_rows(int W);
 size_t integral_bandsum_words(int W, int H, int B);
-void launch_integral(const ImageRef &img, int B, const FrameGeo &geo, uint32_t *sum, uint32_t *bandsum, int clamp01,
+size_t integral_flag_words(int H, int B);
+void launch_integral(const ImageRef &img, int B, const FrameGeo &geo, uint32_t *sum, uint32_t *bandsum, int *bandflags, int clamp01,
                      cudaStream_t st, int *launches);
 void launch_hessian(const uint32_t *sum, const FrameGeo &geo, const OctavePat &pat, float *det, size_t det_frame, int B,
                     cudaStream_t st, int *launches);

@@ -36,6 +36,7 @@ ABI_SYMBOLS = [
     "surf_integral", "surf_hessian_layer", "surf_raw_keypoints", "surf_describe_keypoints", "surf_match_knn",
     "surf_match_ratio", "surf_merge_topk", "surf_version", "surf_match_prev", "surf_stream_reset",
     "surf_device_matches", "surf_set_match_mode", "surf_match_redo_count", "surf_set_async_outputs",
+    "surf_set_graphs", "surf_graph_replays",
     "surf_rand_create", "surf_rand_destroy", "surf_rand_next", "surf_match_points", "surf_ransac_plane",
     "surf_estimate_pose", "surf_mean_plane_distance",
     "surf_wait_outputs", "surf_db_create", "surf_db_destroy", "surf_db_clear", "surf_db_add", "surf_db_size",
@@ -138,6 +139,8 @@ def load_library():
     L.surf_set_match_mode.argtypes = [vp, i32]
     L.surf_match_redo_count.argtypes = [vp, C.POINTER(i32)]
     L.surf_set_async_outputs.argtypes = [vp, i32]
+    L.surf_set_graphs.argtypes = [vp, i32, i32]
+    L.surf_graph_replays.argtypes = [vp, C.POINTER(C.c_long)]
     L.surf_wait_outputs.argtypes = [vp]
     L.surf_db_create.argtypes = [vp, i32, lng, i32, C.POINTER(vp)]
     L.surf_db_destroy.argtypes = [vp]
@@ -431,6 +434,15 @@ class SURF:
     def set_match_mode(self, exact_only: bool):
         """False (default): tensor-core candidate search + exact rescoring; True: exact CUDA-core kernel."""
         self._check(self._lib.surf_set_match_mode(self._h, int(bool(exact_only))))
+
+    def set_graphs(self, enable: bool, max_batch: int = 0):
+        """CUDA-graph replay of the launch sequence of small batches (<= max_batch frames; 0 keeps the current limit)."""
+        self._check(self._lib.surf_set_graphs(self._h, int(bool(enable)), int(max_batch)))
+
+    def graph_replays(self) -> int:
+        n = C.c_long(0)
+        self._check(self._lib.surf_graph_replays(self._h, C.byref(n)))
+        return n.value
 
     def match_redo_count(self) -> int:
         n = C.c_int(0)

@@ -353,3 +353,44 @@ def test_results_do_not_depend_on_batch_composition_or_repetition():
         e.sync()
     finally:
         e.close()
+
+
+def test_graph_replays_are_byte_identical_to_the_eager_launches():
+    """Small batches are served by CUDA-graph replays from the second time a (buffers, size) key comes round
+    (surf_set_graphs): same kernels, same arguments, so keypoints, descriptors and stage timings must not change."""
+    from surffeatures_b200 import SURF
+
+    W, H = 320, 240
+    frames = speckle.speckle_stream(6, H, W, seed=23, fresh=0.0)
+    mask = np.zeros((H, W), np.uint8)
+    mask[30:200, 40:300] = 255
+    e = SURF(100, 4, 3, max_width=W, max_height=H, max_batch=4, max_keypoints=4096)
+    try:
+        e.set_graphs(False)
+        eager = [e.detectAndCompute(f) for f in frames]
+        eager_mask = [e.detectAndCompute(f, mask) for f in frames[:2]]
+        eager_batch = e.detectAndComputeBatchPacked(frames[:4])
+        assert e.graph_replays() == 0
+        e.set_graphs(True)
+        for rep in range(4):
+            for f, (kp, de) in zip(frames, eager):
+                k2, d2 = e.detectAndCompute(f)
+                assert k2.tobytes() == kp.tobytes() and d2.tobytes() == de.tobytes()
+            t = e.timings()
+            assert t["total"] > 0 and t["describe"] > 0          # the stage events are recorded by the graph, too
+            for f, (kp, de) in zip(frames[:2], eager_mask):
+                k2, d2 = e.detectAndCompute(f, mask)
+                assert k2.tobytes() == kp.tobytes() and d2.tobytes() == de.tobytes()
+            kb, db, ob = e.detectAndComputeBatchPacked(frames[:4])
+            assert kb.tobytes() == eager_batch[0].tobytes() and db.tobytes() == eager_batch[1].tobytes()
+            assert np.array_equal(ob, eager_batch[2])
+        assert e.graph_replays() >= 12, e.graph_replays()         # most of the 4 x 9 submits were replays
+        # new parameters drop the graphs: the next calls run (and are captured) with the new thresholds
+        e.hessianThreshold = 400.0
+        a = e.detectAndCompute(frames[0])
+        b = e.detectAndCompute(frames[0])
+        c = e.detectAndCompute(frames[0])
+        assert len(a[0]) < len(eager[0][0])
+        assert a[0].tobytes() == b[0].tobytes() == c[0].tobytes() and a[1].tobytes() == c[1].tobytes()
+    finally:
+        e.close()
