@@ -666,7 +666,7 @@ def run_ours(args):
     alg = algorithmic_bytes_per_frame(kp_per_frame, D)
     match_flops = 2.0 * kp_per_frame * kp_per_frame * D * B
     stages = [
-        {"stage": "integral", "kernels": "k_band_colsum+k_band_integral", "bound": "hbm",
+        {"stage": "integral", "kernels": "k_integral_band", "bound": "hbm",
          "algorithmic_bytes": alg["integral"] * B, "ms": stage_ms["integral"]},
         {"stage": "hessian+maxima", "kernels": "k_hessian_nms_tma_c<0|1>+k_hessian+k_nms", "bound": "hbm",
          "algorithmic_bytes": alg["hessian_nms_fused"] * B, "algorithmic_bytes_unfused": (alg["hessian"] + alg["nms"]) * B,
@@ -682,7 +682,7 @@ def run_ours(args):
         s["frac"] = s["achieved"] / peaks["hbm"] if s["achieved"] else None
         if "algorithmic_bytes_unfused" in s and s["ms"] > 0:
             s["frac_unfused_accounting"] = s["algorithmic_bytes_unfused"] / (s["ms"] * 1e-3) / 1e9 / peaks["hbm"]
-    stages.append({"stage": "match", "kernels": "k_tc_prep+k_tc_candidates+k_tc_rescore+k_tc_redo", "bound": "tensor",
+    stages.append({"stage": "match", "kernels": "k_tc_prep+k_tc_candidates3w+k_tc_rescore+k_tc_redo", "bound": "tensor",
                    "algorithmic_flops": match_flops, "ms": stage_ms["match"],
                    "achieved": match_flops / (stage_ms["match"] * 1e-3) / 1e12 if stage_ms["match"] > 0 else None,
                    "peak": peaks["bf16_burst"], "unit": "TFLOP/s",
