@@ -143,13 +143,20 @@ __device__ __forceinline__ void find_frame(const int *offsets, int B, int w, int
 }
 
 // ------------------------------------------------------------------------------------------------
-// K4a: orientation.  One warp per keypoint.
+// K4a: orientation.  A warp takes FOUR keypoints at a time.  The 113 Haar samples of each are gathered by the whole
+// warp (one keypoint after the other, 32 samples per round, compacted in sample order); the 72 sliding windows of the
+// four keypoints are then summed together: lane l owns the nine windows (l % 8) + 8 s, s = 0..8, of keypoint l / 8, so
+// all 288 (keypoint, window) pairs are busy (one keypoint per warp left 24 of 96 window slots idle and spent 12
+// instructions per sample; here 31 per sample serve four keypoints).  Sums run in sample order in fp32, the first strict
+// maximum over increasing window index wins: the same arithmetic in the same order as before, bit-identical angles.
+// The per-keypoint tail (correctly rounded sin / cos in double, class lists) runs on four lanes at once.
 // ------------------------------------------------------------------------------------------------
-constexpr int kOriWarps = 8;
+constexpr int kOriWarps = 4;
+constexpr int kOriPerWarp = 4;
 
 struct __align__(16) OriSample {
     float X, Y;          // Gaussian-weighted Haar responses
-    unsigned m0, m1;     // membership of the sample in windows 0..31 / 32..63 (bit w = window w)
+    unsigned m0, m1;     // membership of the sample in windows 0..31 / 32..63 (bit w = window w); 0 for padding
 };
 
 // The 72 sliding windows (0, 5, ..., 355 degrees; a sample with rounded angle a belongs to window w iff
@@ -171,8 +178,11 @@ __device__ __forceinline__ void window_mask(int a, unsigned &m0, unsigned &m1, u
 
 __global__ void __launch_bounds__(kOriWarps * 32) k_orient(const __grid_constant__ DescribeArgs A)
 {
-    __shared__ OriSample s_smp[kOriWarps][kOriSamples + 3];
-    __shared__ unsigned char s_m2[kOriWarps][kOriSamples + 3];  // membership in windows 64..71
+    // 117 slots: the four lists of a warp are 468 words apart, i.e. 20 banks: the four 16-byte reads of a warp (one
+    // per keypoint, same sample index) fall into four different bank groups
+    constexpr int kSlots = kOriSamples + 4;
+    __shared__ OriSample s_smp[kOriWarps][kOriPerWarp][kSlots];
+    __shared__ unsigned char s_m2[kOriWarps][kOriPerWarp][kSlots + 3];  // membership in windows 64..71
     // window membership of every rounded angle 0..360, built once per CTA (window_mask is ~40 integer instructions
     // with 64-bit shifts; the table makes it one 16-byte shared-memory read per sample)
     __shared__ uint4 s_wmask[361];
@@ -183,121 +193,168 @@ __global__ void __launch_bounds__(kOriWarps * 32) k_orient(const __grid_constant
     }
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int grp = lane >> 3, l8 = lane & 7;  // window phase: keypoint of the four, window residue
     const int W = A.geo.W, H = A.geo.H, SP = A.geo.SP;
     const int total = A.offsets[A.B];
     const bool want_desc = (A.desc != nullptr) || (A.patches != nullptr);
-    OriSample *smp = s_smp[warp];
-    unsigned char *smp2 = s_m2[warp];
-    const unsigned lanebit = 1u << lane;
-
-    for (int w = blockIdx.x * kOriWarps + warp; w < total; w += gridDim.x * kOriWarps) {
-        int b, slot;
-        find_frame(A.offsets, A.B, w, b, slot);
-        surf_keypoint *kpp = A.kps + (size_t)b * A.cap + slot;
-        const float cx = kpp->x, cy = kpp->y, size = kpp->size;
-        const int *S = reinterpret_cast<const int *>(A.sum) + (size_t)b * A.geo.sum_frame;
-
-        const float s = size * 1.2f / 9.0f;
-        const int g = 2 * __float2int_rn(2 * s);
-        bool dead = (H + 1 < g) || (W + 1 < g);
-        float dir = 360.f - 90.f;
-
-        if (!dead && !A.upright) {
-            // ---- 113 samples, 4 rounds of 32, compacted in sample order ----
-            int na = 0;
-            const float hg = (float)(g - 1) / 2;
-            const int h = g / 2;
-            const float wa = 1 / ((float)h * g), wn = -1 / ((float)h * g);
-            for (int r = 0; r < 4; r++) {
-                const int k = r * 32 + lane;
-                bool valid = false;
-                float X = 0, Y = 0;
-                if (k < kOriSamples) {
-                    const int x = __float2int_rn(cx + c_ori_x[k] * s - hg);
-                    const int y = __float2int_rn(cy + c_ori_y[k] * s - hg);
-                    if (!(y < 0 || y >= (H + 1) - g || x < 0 || x >= (W + 1) - g)) {
-                        valid = true;
-                        const int *o = S + (size_t)y * SP + x;
-                        const int *oh = o + (size_t)h * SP, *og = o + (size_t)g * SP;
-                        const int p00 = __ldg(o), p0h = __ldg(o + h), p0g = __ldg(o + g);
-                        const int ph0 = __ldg(oh), phg = __ldg(oh + g);
-                        const int pg0 = __ldg(og), pgh = __ldg(og + h), pgg = __ldg(og + g);
-                        // x gradient: right half minus left half; y gradient: top half minus bottom half
-                        const int left = p00 + pgh - pg0 - p0h, right = p0h + pgg - pgh - p0g;
-                        const int top = p00 + phg - ph0 - p0g, bottom = ph0 + pgg - pg0 - phg;
-                        const float vx = (float)((double)((float)left * wn) + (double)((float)right * wa));
-                        const float vy = (float)((double)((float)top * wa) + (double)((float)bottom * wn));
-                        X = vx * c_ori_w[k];
-                        Y = vy * c_ori_w[k];
-                    }
-                }
-                const unsigned bal = __ballot_sync(FULL_MASK, valid);
-                if (valid) {
-                    OriSample o;
-                    unsigned m2;
-                    const uint4 wm = s_wmask[__float2int_rn(fast_atan2_deg(Y, X))];
-                    o.m0 = wm.x;
-                    o.m1 = wm.y;
-                    m2 = wm.z;
-                    o.X = X;
-                    o.Y = Y;
-                    const int pos = na + __popc(bal & ((1u << lane) - 1));
-                    smp[pos] = o;
-                    smp2[pos] = (unsigned char)m2;
-                }
-                na += __popc(bal);
-            }
-            __syncwarp();
-            if (na == 0) {
-                dead = true;
-            } else {
-                // ---- 72 sliding windows (lane handles windows lane, lane+32, lane+64), fp32 sums in
-                //      sample order; first strict maximum over increasing window index ----
-                // lane owns windows lane, lane + 32 and (lanes 0..7) lane + 64: one pass over the samples feeds
-                // all three; membership is one bit test per window (masks built with the samples)
-                float bmod = 0, bx = 0, by = 0;
-                int bi = 1 << 30;
-                {
-                    float sx0 = 0, sy0 = 0, sx1 = 0, sy1 = 0, sx2 = 0, sy2 = 0;
-#pragma unroll 4
-                    for (int k = 0; k < na; k++) {
-                        const OriSample o = smp[k];
-                        const unsigned m2 = smp2[k];
-                        if (o.m0 & lanebit) { sx0 += o.X; sy0 += o.Y; }
-                        if (o.m1 & lanebit) { sx1 += o.X; sy1 += o.Y; }
-                        if (m2 & lanebit) { sx2 += o.X; sy2 += o.Y; }
-                    }
-                    const float q0 = sx0 * sx0 + sy0 * sy0, q1 = sx1 * sx1 + sy1 * sy1, q2 = sx2 * sx2 + sy2 * sy2;
-                    if (q0 > bmod) { bmod = q0; bx = sx0; by = sy0; bi = lane; }
-                    if (q1 > bmod) { bmod = q1; bx = sx1; by = sy1; bi = lane + 32; }
-                    if (lane < 8 && q2 > bmod) { bmod = q2; bx = sx2; by = sy2; bi = lane + 64; }
-                }
+    const unsigned bit0 = 1u << l8, bit1 = bit0 << 8, bit2 = bit0 << 16, bit3 = bit0 << 24;
+    // a lane always gathers the same four samples (lane, lane + 32, ...): their offsets and weights live in registers (indexed
+    // per lane the constant bank served one address at a time: the top stall of the gather)
+    float kx[4], ky[4], kw[4];
 #pragma unroll
-                for (int d = 16; d > 0; d >>= 1) {
-                    const float om = __shfl_xor_sync(FULL_MASK, bmod, d);
-                    const float ox = __shfl_xor_sync(FULL_MASK, bx, d);
-                    const float oy = __shfl_xor_sync(FULL_MASK, by, d);
-                    const int oi = __shfl_xor_sync(FULL_MASK, bi, d);
-                    if (om > bmod || (om == bmod && oi < bi)) {
-                        bmod = om;
-                        bx = ox;
-                        by = oy;
-                        bi = oi;
-                    }
-                }
-                dir = fast_atan2_deg(-by, bx);
-            }
-            __syncwarp();  // the next keypoint overwrites smp
-        }
+    for (int r = 0; r < 4; r++) {
+        const int k = min(r * 32 + lane, kOriSamples - 1);
+        kx[r] = c_ori_x[k];
+        ky[r] = c_ori_y[k];
+        kw[r] = c_ori_w[k];
+    }
+    int fb = 0;  // frame of the last keypoint: keypoints come in frame order, so the next one is almost always in it too
 
-        const int n = (int)(21 * s);
-        if (!dead && want_desc && (n < 1 || n > kMaxWindow)) {
-            // n < 1 (size < 0.36): upstream builds an empty window and cv::resize raises; deleted here, as the oracle does;
-            // n > kMaxWindow: unsupported window, reported through the status word.
-            if (n > kMaxWindow && lane == 0) atomicOr(A.misc + kMiscStatus, 1);
-            dead = true;
+    for (int w0 = (blockIdx.x * kOriWarps + warp) * kOriPerWarp; w0 < total; w0 += gridDim.x * kOriWarps * kOriPerWarp) {
+        // this lane's keypoint of the four (window phase and tail): filled in while the warp gathers the samples
+        int my_b = 0, my_slot = 0, my_na = 0;
+        float my_s = 0.f;
+        bool my_live = false, my_dead = false;
+        int na_max = 0;
+        for (int j = 0; j < kOriPerWarp; j++) {
+            const int w = w0 + j;
+            if (w >= total) {  // (uniform) no keypoint: an all-padding list, so the joint walk below reads valid entries
+                for (int k = lane; k < kSlots; k += 32) {
+                    s_smp[warp][j][k] = OriSample{0.f, 0.f, 0u, 0u};
+                    s_m2[warp][j][k] = 0;
+                }
+                continue;
+            }
+            int b, slot;
+            if (w >= A.offsets[fb] && w < A.offsets[fb + 1]) {
+                b = fb;
+                slot = w - A.offsets[fb];
+            } else {
+                find_frame(A.offsets, A.B, w, b, slot);
+                fb = b;
+            }
+            const surf_keypoint *kpp = A.kps + (size_t)b * A.cap + slot;
+            const float cx = kpp->x, cy = kpp->y, size = kpp->size;
+            const int *S = reinterpret_cast<const int *>(A.sum) + (size_t)b * A.geo.sum_frame;
+            const float s = size * 1.2f / 9.0f;
+            const int g = 2 * __float2int_rn(2 * s);
+            bool dead = (H + 1 < g) || (W + 1 < g);
+            int na = 0;
+            OriSample *smp = s_smp[warp][j];
+            unsigned char *smp2 = s_m2[warp][j];
+            if (!dead && !A.upright) {
+                // ---- 113 samples, 4 rounds of 32, compacted in sample order ----
+                const float hg = (float)(g - 1) / 2;
+                const int h = g / 2;
+                const float wa = 1 / ((float)h * g), wn = -1 / ((float)h * g);
+#pragma unroll
+                for (int r = 0; r < 4; r++) {
+                    const int k = r * 32 + lane;
+                    bool valid = false;
+                    float X = 0, Y = 0;
+                    if (k < kOriSamples) {
+                        const int x = __float2int_rn(cx + kx[r] * s - hg);
+                        const int y = __float2int_rn(cy + ky[r] * s - hg);
+                        if (!(y < 0 || y >= (H + 1) - g || x < 0 || x >= (W + 1) - g)) {
+                            valid = true;
+                            const int *o = S + (size_t)y * SP + x;
+                            const int *oh = o + (size_t)h * SP, *og = o + (size_t)g * SP;
+                            const int p00 = __ldg(o), p0h = __ldg(o + h), p0g = __ldg(o + g);
+                            const int ph0 = __ldg(oh), phg = __ldg(oh + g);
+                            const int pg0 = __ldg(og), pgh = __ldg(og + h), pgg = __ldg(og + g);
+                            // x gradient: right half minus left half; y gradient: top half minus bottom half
+                            const int left = p00 + pgh - pg0 - p0h, right = p0h + pgg - pgh - p0g;
+                            const int top = p00 + phg - ph0 - p0g, bottom = ph0 + pgg - pg0 - phg;
+                            const float vx = (float)((double)((float)left * wn) + (double)((float)right * wa));
+                            const float vy = (float)((double)((float)top * wa) + (double)((float)bottom * wn));
+                            X = vx * kw[r];
+                            Y = vy * kw[r];
+                        }
+                    }
+                    const unsigned bal = __ballot_sync(FULL_MASK, valid);
+                    if (valid) {
+                        const uint4 wm = s_wmask[__float2int_rn(fast_atan2_deg(Y, X))];
+                        const int pos = na + __popc(bal & ((1u << lane) - 1));
+                        smp[pos] = OriSample{X, Y, wm.x, wm.y};
+                        smp2[pos] = (unsigned char)wm.z;
+                    }
+                    na += __popc(bal);
+                }
+                if (na == 0) dead = true;
+            }
+            // padding up to the end of the list: samples that belong to no window (the four lists are walked together)
+            for (int k = na + lane; k < kSlots; k += 32) {
+                smp[k] = OriSample{0.f, 0.f, 0u, 0u};
+                smp2[k] = 0;
+            }
+            if (grp == j) {
+                my_b = b; my_slot = slot; my_na = na; my_s = s;
+                my_live = true;
+                my_dead = dead;
+            }
+            na_max = max(na_max, na);
         }
-        if (lane == 0) {
+        __syncwarp();
+
+        float dir = 360.f - 90.f;
+        if (!A.upright && na_max > 0) {
+            // ---- 72 sliding windows per keypoint, fp32 sums in sample order; lane owns windows l8 + 8 s of keypoint grp ----
+            const OriSample *smp = s_smp[warp][grp];
+            const unsigned char *smp2 = s_m2[warp][grp];
+            float sx[9], sy[9];
+#pragma unroll
+            for (int q = 0; q < 9; q++) sx[q] = sy[q] = 0.f;
+#pragma unroll 2
+            for (int k = 0; k < na_max; k++) {
+                const OriSample o = smp[k];
+                const unsigned m2 = smp2[k];
+                if (o.m0 & bit0) { sx[0] += o.X; sy[0] += o.Y; }
+                if (o.m0 & bit1) { sx[1] += o.X; sy[1] += o.Y; }
+                if (o.m0 & bit2) { sx[2] += o.X; sy[2] += o.Y; }
+                if (o.m0 & bit3) { sx[3] += o.X; sy[3] += o.Y; }
+                if (o.m1 & bit0) { sx[4] += o.X; sy[4] += o.Y; }
+                if (o.m1 & bit1) { sx[5] += o.X; sy[5] += o.Y; }
+                if (o.m1 & bit2) { sx[6] += o.X; sy[6] += o.Y; }
+                if (o.m1 & bit3) { sx[7] += o.X; sy[7] += o.Y; }
+                if (m2 & bit0) { sx[8] += o.X; sy[8] += o.Y; }
+            }
+            // first strict maximum over increasing window index: inside the lane (s ascending), then over the 8 lanes
+            float bmod = 0, bx = 0, by = 0;
+            int bi = 1 << 30;
+#pragma unroll
+            for (int q = 0; q < 9; q++) {
+                const float qq = sx[q] * sx[q] + sy[q] * sy[q];
+                if (qq > bmod) { bmod = qq; bx = sx[q]; by = sy[q]; bi = l8 + 8 * q; }
+            }
+#pragma unroll
+            for (int d = 4; d > 0; d >>= 1) {
+                const float om = __shfl_xor_sync(FULL_MASK, bmod, d);
+                const float ox = __shfl_xor_sync(FULL_MASK, bx, d);
+                const float oy = __shfl_xor_sync(FULL_MASK, by, d);
+                const int oi = __shfl_xor_sync(FULL_MASK, bi, d);
+                if (om > bmod || (om == bmod && oi < bi)) {
+                    bmod = om;
+                    bx = ox;
+                    by = oy;
+                    bi = oi;
+                }
+            }
+            if (my_na > 0) dir = fast_atan2_deg(-by, bx);
+        }
+        __syncwarp();  // the next four keypoints overwrite the sample lists
+
+        // ---- tail: lane 0 of each group finishes its keypoint
+        if (my_live && l8 == 0) {
+            const int b = my_b, slot = my_slot;
+            surf_keypoint *kpp = A.kps + (size_t)b * A.cap + slot;
+            bool dead = my_dead;
+            const int n = (int)(21 * my_s);
+            if (!dead && want_desc && (n < 1 || n > kMaxWindow)) {
+                // n < 1 (size < 0.36): upstream builds an empty window and cv::resize raises; deleted here, as the oracle
+                // does; n > kMaxWindow: unsupported window, reported through the status word.
+                if (n > kMaxWindow) atomicOr(A.misc + kMiscStatus, 1);
+                dead = true;
+            }
             if (dead) {
                 kpp->size = -1.f;
                 const int pos = atomicAdd(A.ndeleted + b, 1);

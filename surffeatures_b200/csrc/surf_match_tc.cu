@@ -1110,9 +1110,17 @@ __device__ void redo_scan(const TcProblem &pr, int nt, const int *__restrict__ e
         float acc[NG];
 #pragma unroll
         for (int g = 0; g < NG; g++) acc[g] = 0.f;
-#pragma unroll 4
-        for (int d = 0; d < D / 4; d++) {  // same element order as k_match_exact
-            const float4 b4 = __ldg(tv + d);
+        // the scan is bound by the latency of the row loads: a whole 64-d row (16 loads) is in flight per thread
+        float4 row[D / 4 < 16 ? D / 4 : 16];
+        constexpr int RB = D / 4 < 16 ? D / 4 : 16;
+#pragma unroll
+        for (int d0 = 0; d0 < D / 4; d0 += RB) {
+#pragma unroll
+        for (int d = 0; d < RB; d++) row[d] = __ldg(tv + d0 + d);
+#pragma unroll
+        for (int dd = 0; dd < RB; dd++) {  // same element order as k_match_exact
+            const int d = d0 + dd;
+            const float4 b4 = row[dd];
 #pragma unroll
             for (int g = 0; g < NG; g++) {
                 const float4 a4 = *reinterpret_cast<const float4 *>(&s_q[g][4 * d]);
@@ -1121,6 +1129,7 @@ __device__ void redo_scan(const TcProblem &pr, int nt, const int *__restrict__ e
                 df = a4.z - b4.z; acc[g] = fmaf(df, df, acc[g]);
                 df = a4.w - b4.w; acc[g] = fmaf(df, df, acc[g]);
             }
+        }
         }
 #pragma unroll
         for (int g = 0; g < NG; g++) {
@@ -1206,17 +1215,19 @@ __global__ void __launch_bounds__(256) k_tc_redo(TcPool tpool, const TcProblem *
     __shared__ __align__(16) float s_q[kRedoGroup][D];
     const int p = blockIdx.y;
     const int n = prob_count[p];
-    const bool single = n <= (int)gridDim.x;  // few entries and CTAs to spare: one query per CTA (latency)
-    if ((int)blockIdx.x * (single ? 1 : kRedoGroup) >= n) return;
+    if (n <= 0) return;
     const TcProblem pr = probs[p];
     const int nt = tpool.count[pr.t_slot];
     const int *list = redo_list + 2 * (size_t)p * list_stride;
-    if (single) {
-        redo_scan<D, 1>(pr, nt, list + 2 * blockIdx.x, 1, k, ratio, out, good, s_q, s_d, s_i);
-        return;
+    // few entries and CTAs to spare: one query per CTA; else groups of kRedoGroup share every train row.  (Measured: sizing
+    // the groups 1 / 2 / 4 to spread a problem's handful of entries over more CTAs is slower, 171 against 134 us -- a scan
+    // is bound by the latency of its row loads, not by the flops of the queries that share them.)
+    const int group = n <= (int)gridDim.x ? 1 : kRedoGroup;
+    for (int w0 = blockIdx.x * group; w0 < n; w0 += gridDim.x * group) {
+        const int ng = min(group, n - w0);
+        if (group == 1) redo_scan<D, 1>(pr, nt, list + 2 * w0, ng, k, ratio, out, good, s_q, s_d, s_i);
+        else redo_scan<D, kRedoGroup>(pr, nt, list + 2 * w0, ng, k, ratio, out, good, s_q, s_d, s_i);
     }
-    for (int w0 = blockIdx.x * kRedoGroup; w0 < n; w0 += gridDim.x * kRedoGroup)
-        redo_scan<D, kRedoGroup>(pr, nt, list + 2 * w0, min(kRedoGroup, n - w0), k, ratio, out, good, s_q, s_d, s_i);
 }
 
 // ------------------------------------------------------------------------------------------------
