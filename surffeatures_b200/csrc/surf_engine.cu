@@ -734,7 +734,8 @@ int run_stages(surf_engine *e, const ImageRef &img, const uint32_t *msum, const 
     surf_engine::GraphKey key;
     memset(&key, 0, sizeof(key));
     key.img = img.ptr; key.msum = msum; key.d_sum = e->d_sum; key.d_kp_a = e->d_kp_a; key.d_kp_b = e->d_kp_b;
-    key.d_counts = e->d_counts; key.ev = e->ev; key.h_pin = e->h_pin; key.pitch = img.pitch; key.fstride = img.frame_stride;
+    key.d_counts = e->d_counts; key.ev = e->ev; key.h_pin = e->h_pin; key.ev_detect_done = e->ev_detect_done;
+    key.ev_set_free = e->ev_set_free; key.pitch = img.pitch; key.fstride = img.frame_stride;
     key.W = geo.W; key.H = geo.H; key.B = B; key.want_desc = want_desc; key.out_set = e->out_bound; key.cap = e->cap;
     surf_engine::GraphEntry *g = nullptr;
     for (surf_engine::GraphEntry &c : e->graphs)

@@ -132,6 +132,7 @@ struct surf_engine {
     // every pointer and size it bakes in; captured the second time a key is seen, replayed afterwards
     struct GraphKey {
         const void *img, *msum, *d_sum, *d_kp_a, *d_kp_b, *d_counts, *ev, *h_pin;
+        const void *ev_detect_done, *ev_set_free;  // handles the look-ahead logic swaps around: baked into the graph, too
         size_t pitch, fstride;
         int W, H, B, want_desc, out_set, cap;
     };
