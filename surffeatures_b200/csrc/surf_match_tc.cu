@@ -455,9 +455,26 @@ __device__ __forceinline__ void key_insert_pair(uint32_t &m1, uint32_t &m2, uint
     m1 = min(m1, lo);
 }
 
+// Four keys at a time: a tournament finds the smallest, which alone goes through the sorted list; the other three are
+// only folded into `bnd`, a lower bound of everything the thread dropped without listing (their minimum is the quad's
+// second smallest).  13 min / max per four scores instead of 16.  A true neighbour that loses its quad to a better one
+// (3 of 4 352 columns share a quad with the best) is then not a candidate, the bound says so, and the query is redone.
+__device__ __forceinline__ void key_insert_quad(uint32_t &m1, uint32_t &m2, uint32_t &m3, uint32_t &bnd, uint32_t k0, uint32_t k1,
+                                                uint32_t k2, uint32_t k3)
+{
+    const uint32_t lo1 = min(k0, k1), hi1 = max(k0, k1), lo2 = min(k2, k3), hi2 = max(k2, k3);
+    const uint32_t L = min(lo1, lo2), M = max(lo1, lo2);
+    bnd = min(min(bnd, hi1), min(hi2, M));
+    const uint32_t t1 = max(m1, L);
+    m1 = min(m1, L);
+    const uint32_t t2 = max(m2, t1);
+    m2 = min(m2, t1);
+    m3 = min(m3, t2);
+}
+
 size_t tc_candidates3_smem(int dim) { return (size_t)(2 * kTM + 2 * kTN) * dim * 2 + 4 * kTN * sizeof(float) + 1024; }
 
-template <int D>
+template <int D, bool QUAD>
 __global__ void __launch_bounds__(kCandThreads, D == 64 ? 2 : 1) k_tc_candidates3(TcPool pool, TcPool tpool, const TcProblem *__restrict__ probs,
                                                         int n_probs, int mt_per_prob, int n_splits, int cand_stride,
                                                         TcCand *__restrict__ cand_out, int *__restrict__ work_head, int idx_bits, uint32_t key_mul)
@@ -524,6 +541,7 @@ __global__ void __launch_bounds__(kCandThreads, D == 64 ? 2 : 1) k_tc_candidates
         // (31 - column for the chunk's own columns, more for earlier chunks), so a new key is bits * 2^s + constant
         // with no index register; the three entries are moved along by the chunk distance once per chunk
         uint32_t m1 = pad_field << idx_bits, m2 = m1, m3 = m1;  // empty entries: the value field of a padded row
+        uint32_t bnd = 0xffffffffu;                             // QUAD: lower bound of the keys dropped without listing
         int pos = -1;                                            // first split row of the last chunk scanned
         const size_t trow_base = (size_t)pr.t_slot * tpool.slot_rows;
         auto load_train_tile = [&](int tile, int stage) {
@@ -597,8 +615,12 @@ __global__ void __launch_bounds__(kCandThreads, D == 64 ? 2 : 1) k_tc_candidates
                         const uint32_t k1 = __float_as_uint(fmaf(v[c + 1], m2sigma, t4.y)) * key_mul + (30 - c);
                         const uint32_t k2 = __float_as_uint(fmaf(v[c + 2], m2sigma, t4.z)) * key_mul + (29 - c);
                         const uint32_t k3 = __float_as_uint(fmaf(v[c + 3], m2sigma, t4.w)) * key_mul + (28 - c);
-                        key_insert_pair(m1, m2, m3, k0, k1);
-                        key_insert_pair(m1, m2, m3, k2, k3);
+                        if (QUAD) {
+                            key_insert_quad(m1, m2, m3, bnd, k0, k1, k2, k3);
+                        } else {
+                            key_insert_pair(m1, m2, m3, k0, k1);
+                            key_insert_pair(m1, m2, m3, k2, k3);
+                        }
                     }
                 }
             }
@@ -608,23 +630,24 @@ __global__ void __launch_bounds__(kCandThreads, D == 64 ? 2 : 1) k_tc_candidates
         // ---- merge the four quarter lists of every query row.  The scratch aliases the train-tile buffer: every MMA
         //      that read it has completed (bar_mma), and the next item's bulk copies are issued only after the proxy
         //      fence and the barrier at the loop top.
-        uint32_t *s_merge = reinterpret_cast<uint32_t *>(sB_hi);  // [row][quarter][3]
+        uint32_t *s_merge = reinterpret_cast<uint32_t *>(sB_hi);  // [row][quarter][m1, m2, m3, bound]
         const uint32_t idx_mask = (1u << idx_bits) - 1u;
         auto absolute = [&](uint32_t m) {  // relative, descending index field -> row of the split
             return (m & ~idx_mask) | (((uint32_t)(pos + 31) - (m & idx_mask)) & idx_mask);
         };
-        s_merge[(qrow * 4 + quarter) * 3 + 0] = absolute(m1);
-        s_merge[(qrow * 4 + quarter) * 3 + 1] = absolute(m2);
-        s_merge[(qrow * 4 + quarter) * 3 + 2] = absolute(m3);
+        *reinterpret_cast<uint4 *>(s_merge + (qrow * 4 + quarter) * 4) = make_uint4(absolute(m1), absolute(m2), absolute(m3), min(m3, bnd));
         __syncthreads();
         if (tid < kTM && q0 + tid < nq) {
             const int row = tid;
             uint32_t best[5] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
-            uint32_t third = 0xffffffffu;  // smallest of the four lists' third entries
+            uint32_t third = 0xffffffffu;  // smallest of the four threads' bounds (third entry, dropped quad members)
 #pragma unroll
-            for (int e = 0; e < 12; e++) {
-                uint32_t x = s_merge[row * 12 + e];
-                if (e % 3 == 2) third = min(third, x);
+            for (int e = 0; e < 16; e++) {
+                uint32_t x = s_merge[row * 16 + e];
+                if (e % 4 == 3) {
+                    third = min(third, x);
+                    continue;
+                }
 #pragma unroll
                 for (int r = 0; r < 5; r++) {  // sorted insertion, branch-free
                     const uint32_t lo = min(best[r], x);
@@ -718,7 +741,7 @@ __device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[32])
                  : "memory");
 }
 
-template <int D>
+template <int D, bool QUAD>
 __global__ void __launch_bounds__(kWsThreads, 1) k_tc_candidates3w(TcPool pool, TcPool tpool, const TcProblem *__restrict__ probs,
                                                          int n_probs, int mt_per_prob, int n_splits, int cand_stride,
                                                          TcCand *__restrict__ cand_out, int *__restrict__ work_head, int idx_bits, uint32_t key_mul)
@@ -794,6 +817,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) k_tc_candidates3w(TcPool pool, 
         const float sigma = 1.f / (2.04f * nsum + 1e-30f);
 
         uint32_t m1 = pad_field << idx_bits, m2 = m1, m3 = m1;  // empty entries: the value field of a padded row
+        uint32_t bnd = 0xffffffffu;                             // QUAD: lower bound of the keys dropped without listing
         int pos = -1;                                            // first split row of the last chunk scanned
         if (warp == kEpiWarps) {
             // ---- MMA warp: operands landed + accumulator drained -> 3 * KSTEPS tcgen05.mma and the commit
@@ -908,8 +932,12 @@ __global__ void __launch_bounds__(kWsThreads, 1) k_tc_candidates3w(TcPool pool, 
                         const uint32_t k1 = __float_as_uint(fmaf(__uint_as_float(r[c + 1]), m2sigma, t4.y)) * key_mul + (30 - c);
                         const uint32_t k2 = __float_as_uint(fmaf(__uint_as_float(r[c + 2]), m2sigma, t4.z)) * key_mul + (29 - c);
                         const uint32_t k3 = __float_as_uint(fmaf(__uint_as_float(r[c + 3]), m2sigma, t4.w)) * key_mul + (28 - c);
-                        key_insert_pair(m1, m2, m3, k0, k1);
-                        key_insert_pair(m1, m2, m3, k2, k3);
+                        if (QUAD) {
+                            key_insert_quad(m1, m2, m3, bnd, k0, k1, k2, k3);
+                        } else {
+                            key_insert_pair(m1, m2, m3, k0, k1);
+                            key_insert_pair(m1, m2, m3, k2, k3);
+                        }
                     }
                 }
             };
@@ -929,24 +957,25 @@ __global__ void __launch_bounds__(kWsThreads, 1) k_tc_candidates3w(TcPool pool, 
         // ---- merge the four quarter lists of every query row.  The scratch aliases the operand stages: every MMA that
         //      read them has completed, no copy is in flight (the producer has waited for everything it started), and the
         //      next item's bulk copies are issued only after the proxy fence and the barrier at the loop top.
-        uint32_t *s_merge = reinterpret_cast<uint32_t *>(sB);  // [row][quarter][3]
+        uint32_t *s_merge = reinterpret_cast<uint32_t *>(sB);  // [row][quarter][m1, m2, m3, bound]
         if (!producer) {  // (an epilogue warp has itself seen the last MMA complete)
             auto absolute = [&](uint32_t m) {  // relative, descending index field -> row of the split
                 return (m & ~idx_mask) | (((uint32_t)(pos + 31) - (m & idx_mask)) & idx_mask);
             };
-            s_merge[(qrow * 4 + quarter) * 3 + 0] = absolute(m1);
-            s_merge[(qrow * 4 + quarter) * 3 + 1] = absolute(m2);
-            s_merge[(qrow * 4 + quarter) * 3 + 2] = absolute(m3);
+            *reinterpret_cast<uint4 *>(s_merge + (qrow * 4 + quarter) * 4) = make_uint4(absolute(m1), absolute(m2), absolute(m3), min(m3, bnd));
         }
         __syncthreads();
         if (tid < kTM && q0 + tid < nq) {
             const int row = tid;
             uint32_t best[5] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
-            uint32_t third = 0xffffffffu;  // smallest of the four lists' third entries
+            uint32_t third = 0xffffffffu;  // smallest of the four threads' bounds (third entry, dropped quad members)
 #pragma unroll
-            for (int e = 0; e < 12; e++) {
-                uint32_t x = s_merge[row * 12 + e];
-                if (e % 3 == 2) third = min(third, x);
+            for (int e = 0; e < 16; e++) {
+                uint32_t x = s_merge[row * 16 + e];
+                if (e % 4 == 3) {
+                    third = min(third, x);
+                    continue;
+                }
 #pragma unroll
                 for (int r = 0; r < 5; r++) {  // sorted insertion, branch-free
                     const uint32_t lo = min(best[r], x);
@@ -1281,20 +1310,23 @@ void launch_tc_match(const TcMatchArgs &a, cudaStream_t st, int *launches)
         while ((1 << idx_bits) < rows_per_split) idx_bits++;
         static bool attr3_set[64] = {};
         if (!attr3_set[dev & 63]) {
-            cudaFuncSetAttribute(k_tc_candidates3<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_candidates3_smem(64));
-            cudaFuncSetAttribute(k_tc_candidates3<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_candidates3_smem(128));
-            cudaFuncSetAttribute(k_tc_candidates3w<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_candidates3w_smem(64));
+            cudaFuncSetAttribute(k_tc_candidates3<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_candidates3_smem(64));
+            cudaFuncSetAttribute(k_tc_candidates3<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_candidates3_smem(128));
+            cudaFuncSetAttribute(k_tc_candidates3w<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_candidates3w_smem(64));
+            cudaFuncSetAttribute(k_tc_candidates3w<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_candidates3w_smem(64));
             attr3_set[dev & 63] = true;
         }
-        if (ws)  // one CTA per SM (all 512 TMEM columns)
-            k_tc_candidates3w<64><<<sms, kWsThreads, tc_candidates3w_smem(64), st>>>(
-                a.pool, tp, a.probs, a.n_probs, mt_per_prob, a.n_splits, a.max_q_rows, a.cand, a.counters, idx_bits, 1u << idx_bits);
-        else if (D == 64)
-            k_tc_candidates3<64><<<2 * sms, kCandThreads, tc_candidates3_smem(64), st>>>(
-                a.pool, tp, a.probs, a.n_probs, mt_per_prob, a.n_splits, a.max_q_rows, a.cand, a.counters, idx_bits, 1u << idx_bits);
-        else
-            k_tc_candidates3<128><<<sms, kCandThreads, tc_candidates3_smem(128), st>>>(
-                a.pool, tp, a.probs, a.n_probs, mt_per_prob, a.n_splits, a.max_q_rows, a.cand, a.counters, idx_bits, 1u << idx_bits);
+        static const bool keys_pairs = getenv("SURF_TC_KEYS_PAIRS") != nullptr;  // every key listed (no quad tournament)
+#define SURF_KEYS_ARGS a.pool, tp, a.probs, a.n_probs, mt_per_prob, a.n_splits, a.max_q_rows, a.cand, a.counters, idx_bits, 1u << idx_bits
+        if (ws) {  // one CTA per SM (all 512 TMEM columns)
+            if (keys_pairs) k_tc_candidates3w<64, false><<<sms, kWsThreads, tc_candidates3w_smem(64), st>>>(SURF_KEYS_ARGS);
+            else k_tc_candidates3w<64, true><<<sms, kWsThreads, tc_candidates3w_smem(64), st>>>(SURF_KEYS_ARGS);
+        } else if (D == 64) {
+            k_tc_candidates3<64, true><<<2 * sms, kCandThreads, tc_candidates3_smem(64), st>>>(SURF_KEYS_ARGS);
+        } else {
+            k_tc_candidates3<128, true><<<sms, kCandThreads, tc_candidates3_smem(128), st>>>(SURF_KEYS_ARGS);
+        }
+#undef SURF_KEYS_ARGS
     } else {
 // persistent CTAs: 256 TMEM columns each, so at most two share an SM's 512; the D = 64 / 4-entry variant fits two
 // (2 x 101 KB of shared memory, 64 registers x 512 threads), the others run one per SM

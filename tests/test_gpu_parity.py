@@ -504,7 +504,9 @@ def test_tensor_core_matcher_equals_exact_and_rarely_redoes(eng, oracle, nq, nt,
     want = oracle.knn_match(q, t, k)
     assert np.array_equal(got["trainIdx"], want["trainIdx"])
     # the tensor-core candidates must be good enough to prove almost every query
-    assert redo <= max(2, nq // 200), f"{redo} of {nq} queries fell back to the exact kernel"
+    # (k <= 2: three-entry key lists behind a quad tournament -- a neighbour that shares its quad of train rows with a
+    # better one is redone: 3 / nt of the queries on top of the 0.1-0.2 % whose third neighbour lies within the margin)
+    assert redo <= max(4, nq // 100), f"{redo} of {nq} queries fell back to the exact kernel"
 
 
 def test_tensor_core_matcher_near_ties_fall_back_correctly(eng, oracle):
@@ -541,7 +543,7 @@ def test_match_prev_stream_equals_pairwise_exact(oracle):
         for lo, hi in ((0, 4), (4, 7)):   # two batches: the second one's first frame matches across the call
             kps, desc, off = e.detectAndComputeBatchPacked(frames[lo:hi])
             m, good = e.match_prev(0.8, n_total=int(off[-1]))
-            assert e.match_redo_count() <= max(3, int(off[-1]) // 200)   # three-entry key lists: 0.1-0.2 % unproven
+            assert e.match_redo_count() <= max(4, int(off[-1]) // 100)   # key lists + quad tournament: <= 1 % unproven at ~1 100 rows
             for b in range(hi - lo):
                 d = desc[off[b]:off[b + 1]]
                 mm, gg = m[off[b]:off[b + 1]], good[off[b]:off[b + 1]]
