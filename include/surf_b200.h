@@ -77,7 +77,8 @@ typedef struct surf_timings {
 
 /* Creates an engine on `device` with workspace for `max_batch` frames of up to max_width x
  * max_height and `max_keypoints` raw keypoints per frame.  Mirrors `explicit SURF(double
- * hessianThreshold, int nOctaves, int nOctaveLayers, bool extended, bool upright)`. */
+ * hessianThreshold, int nOctaves, int nOctaveLayers, bool extended, bool upright)`.  max_width is limited to 7 224
+ * pixels (SURF_ERR_UNSUPPORTED beyond: a band of the integral-image kernel holds whole rows in shared memory). */
 int surf_create(const surf_params *params, int device, int max_width, int max_height, int max_batch,
                 int max_keypoints, surf_engine **out);
 void surf_destroy(surf_engine *e);

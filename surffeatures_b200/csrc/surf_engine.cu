@@ -847,6 +847,7 @@ int surf_create(const surf_params *params, int device, int max_width, int max_he
     if (!out) return SURF_ERR_BAD_ARG;
     *out = nullptr;
     if (max_width <= 0 || max_height <= 0 || max_batch <= 0 || max_keypoints <= 0) return SURF_ERR_BAD_ARG;
+    if (max_width > integral_max_width()) return SURF_ERR_UNSUPPORTED;  // a band of the integral kernel holds whole rows
     int rc = check_params(nullptr, params);
     if (rc) return rc;
     int ndev = 0;

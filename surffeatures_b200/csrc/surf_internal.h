@@ -114,6 +114,7 @@ struct DescribeArgs {
 
 // ---- launchers (surf_kernels.cu) ----
 int integral_band_rows(int W);
+int integral_max_width();
 size_t integral_bandsum_words(int W, int H, int B);
 size_t integral_flag_words(int H, int B);
 void launch_integral(const ImageRef &img, int B, const FrameGeo &geo, uint32_t *sum, uint32_t *bandsum, int *bandflags, int clamp01,

@@ -61,6 +61,9 @@ size_t integral_bandsum_words(int W, int H, int B)
     return (size_t)B * nb * ((W + 3) & ~3);
 }
 
+// widest frame whose 4-row bands still fit the 227 KB of shared memory a CTA can have (32 bytes per column)
+int integral_max_width() { return ((227 * 1024 - 1024) / 32 - 8) & ~3; }
+
 // one flag per band of the largest batch (bands have >= 4 rows); zero when allocated
 size_t integral_flag_words(int H, int B) { return (size_t)B * ((H + 3) / 4); }
 
@@ -254,7 +257,7 @@ void launch_integral(const ImageRef &img, int B, const FrameGeo &geo, uint32_t *
     int dev = 0;
     cudaGetDevice(&dev);
     if (!attr_set[dev & 63]) {
-        cudaFuncSetAttribute(k_integral_band, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+        cudaFuncSetAttribute(k_integral_band, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024);
         attr_set[dev & 63] = true;
     }
     // a flag carries the number of the launch that set it: one counter for the process, never 0, so a flag buffer

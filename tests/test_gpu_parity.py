@@ -59,6 +59,26 @@ def test_integral_strided_input(eng, oracle):
     assert np.array_equal(eng.integral(view), oracle.integral(np.ascontiguousarray(view)))
 
 
+@pytest.mark.parametrize("shape", [(70, 1400), (37, 2049), (9, 4100), (3, 1299), (5, 7224)])
+def test_integral_wide_frames_take_the_short_band_path(oracle, shape):
+    """Frames wider than ~1 100 px do not fit 32-row bands in shared memory: the band height shrinks (R = 28 ... 4), the
+    row groups are no longer eight rows and the generic vertical-sum loop runs; many bands per frame also exercise the
+    flag / carry step of k_integral_band.  Batched, too: the bands of several frames are in flight together."""
+    from surffeatures_b200 import SURF
+
+    H, W = shape
+    rng = np.random.default_rng(H * 31 + W)
+    e = SURF(100, 1, 2, max_width=W, max_height=H, max_batch=3, max_keypoints=256)
+    try:
+        for rep in range(3):   # epoch flags: nothing is cleared between launches
+            img = rng.integers(0, 256, shape, dtype=np.uint8)
+            assert np.array_equal(e.integral(img), oracle.integral(img))
+        m = rng.integers(0, 2, shape, dtype=np.uint8) * 255
+        assert np.array_equal(e.integral(m, clamp01=True), oracle.integral(m, clamp01=True))
+    finally:
+        e.close()
+
+
 # ---------------------------------------------------------------- stage 2
 def test_hessian_layers(eng, oracle, frame640):
     S = oracle.integral(frame640)

@@ -69,6 +69,8 @@ def test_bad_arguments_are_status_codes_not_crashes():
     assert lib.surf_create(ctypes.byref(p), 0, 640, 480, 1, 1024, ctypes.byref(h)) == -1
     p = sb.engine.Params(100.0, 4, 3, 0, 0)
     assert lib.surf_create(ctypes.byref(p), 0, 0, 480, 1, 1024, ctypes.byref(h)) == -1
+    # a band of the integral-image kernel holds whole rows in shared memory: frames wider than 7 224 px are refused
+    assert lib.surf_create(ctypes.byref(p), 0, 7225, 480, 1, 1024, ctypes.byref(h)) == -2
     assert lib.surf_sync(None) == -1
     assert lib.surf_last_error(None) == b"null engine"
 
