@@ -41,7 +41,7 @@ PARAMS = dict(hessianThreshold=100.0, nOctaves=4, nOctaveLayers=3, extended=Fals
 RATIO = 0.8
 CAP = 8192          # raw keypoints per frame the workspace holds
 LOOKAHEAD = os.environ.get("SURF_BENCH_LOOKAHEAD", "1") != "0"   # surf_lookahead_batch in the throughput loops
-E2E_DIAG = os.environ.get("SURF_BENCH_E2E_DIAG", "")   # "no_d2h" / "no_h2d": diagnosis runs of the end-to-end loop, never a reported number
+E2E_DIAG = os.environ.get("SURF_BENCH_E2E_DIAG", "")   # "no_d2h" / "no_h2d" / "no_desc": diagnosis runs of the end-to-end loop, never a reported number
 POOL_BATCHES = 4    # distinct batches cycled through; the per-step working set (integral + det pyramid of 64 frames, ~600 MB) exceeds the 126 MB L2
 
 
@@ -405,7 +405,8 @@ class StreamBench:
             if self.match:
                 e.match_prev_device(RATIO)
             return
-        e.collect(hb["kps"].data_ptr(), hb["desc"].data_ptr(), self.MEM_HOST, self.cap_total, self.offsets)
+        e.collect(hb["kps"].data_ptr(), 0 if E2E_DIAG == "no_desc" else hb["desc"].data_ptr(), self.MEM_HOST, self.cap_total,
+                  self.offsets)
         n = int(self.offsets[B])
         self.kp_seen += n
         d2h = n * (28 + 4 * self.D) + (B + 1) * 4
@@ -656,7 +657,7 @@ def run_ours(args):
     kp_per_frame = sb.kp_seen / (steps * B)
     sb.alloc_host_outputs()
     eng.set_async_outputs(True)
-    ms_e2e, _ = sb.timed(sb.step_e2e, steps, warmup)
+    ms_e2e, clocks_e2e = sb.timed(sb.step_e2e, steps, warmup, sample_clocks=True)
     eng.set_async_outputs(False)
     stage_ms = sb.stage_pass(max(5, steps // 3), 2)
     fps = ctx.world * B * steps / (ms_dev * 1e-3)
@@ -723,7 +724,7 @@ def run_ours(args):
                       "host_affinity": ctx.affinity,
                       "library": os.environ.get("SURF_B200_LIB", "surffeatures_b200/libsurf_b200.so")},
             "e2e": {"value": fps_e2e, "unit": "frames/s", "h2d_bytes_per_step": sb.bytes_io["h2d"],
-                    "d2h_bytes_per_step": sb.bytes_io["d2h"], "ms_per_step": ms_e2e / steps},
+                    "d2h_bytes_per_step": sb.bytes_io["d2h"], "ms_per_step": ms_e2e / steps, "clocks": clocks_e2e},
             "gpu_launches": n_launch, "keypoints_per_frame": kp_per_frame,
             "roofline": roofline, "roofline_stages": stages,
             "stage_ms_note": "stages timed in a separate pass with nothing else on the GPU (no look-ahead, matcher drained "
