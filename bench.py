@@ -787,12 +787,11 @@ def run_ours(args):
     return 0
 
 
-# from profiles/r2/describe_stage_v5_ncu_summary.txt (ncu --set full of this command, batch 64: the four window kernels
-# are those of HEAD) and profiles/r2/k_orient_v9_ncu_summary.txt (k_orient of HEAD, four keypoints per warp: 0.470 G warp
-# instructions against 0.695 G, same DRAM traffic): k_orient + the four window kernels (the patch -> descriptor step runs
-# inside them) 188.9 MB read + 13.4 MB written, 3.71 G warp instructions.  Round 1: 428.9 MB and 4.42 G.
-NCU_DESCRIBE_TRAFFIC, NCU_DESCRIBE_INST = 202.3e6, 3.705e9
-NCU_SOURCE = "profiles/r2/describe_stage_v5_ncu_summary.txt + profiles/r2/k_orient_v9_ncu_summary.txt"
+# from profiles/r2/describe_stage_v11_ncu_summary.txt (ncu --set full of this command, batch 64, the kernels of HEAD): k_orient +
+# the four window kernels (the patch -> descriptor step runs inside them): 188.9 MB read + 13.0 MB written, 3.704 G warp
+# instructions.  Round 1: 428.9 MB and 4.42 G; first half of round 2: 203.2 MB and 3.93 G.
+NCU_DESCRIBE_TRAFFIC, NCU_DESCRIBE_INST = 201.9e6, 3.704e9
+NCU_SOURCE = "profiles/r2/describe_stage_v11_ncu_summary.txt"
 
 
 def cpu_baseline_leg(pool: np.ndarray):
