@@ -1541,10 +1541,13 @@ static int match_common(surf_engine *e, const float *query, int n_query, const f
         dq = q2;
         dt = t2;
     }
-    if (e->match_exact_only || n_train == 0) {
+    // (a train set of a few rows: the key lists' quad tournament would send 3 / n_train of the queries to the exact redo
+    // anyway, and the exact kernel is as fast there)
+    if (e->match_exact_only || n_train < 128) {
         if ((rc = reserve_match_part(e, n_query, n_train, k))) return rc;
         launch_match_knn(dq, n_query, dt, n_train, dim, k, dout, 0, e->d_match_part, e->stream, &e->launches);
         if (good) launch_ratio_test(dout, n_query, ratio, dgood, e->stream, &e->launches);
+        e->last_tc_ws = -1;  // no candidate search ran: surf_match_redo_count reports 0
     } else {
         // tensor-core candidate search + exact rescoring: slot 0 = queries, slot 1 = train rows
         const int rows = ((n_query > n_train ? n_query : n_train) + 255) & ~255;
