@@ -440,11 +440,13 @@ size_t tc_candidates_smem(int dim) { return (size_t)(2 * kTM + 2 * kTN) * dim * 
 //   key  = bits(t') << s  |  row of the train split (s bits)  one IMAD: the shift drops sign, exponent and the s - 9
 //                                                             mantissa bits that are zero in [2^(s-9), 2^(s-9) + 1)
 // i.e. the FFMA's own rounding quantises u to 32 - s bits (18 bits for 16 384 rows: 4e-6 of the value range) and the
-// low s bits are free for the index.  Two keys are sorted, then merged into (m1 <= m2 <= m3): 8 min / max
-// instructions per PAIR of scores (three-input VIMNMX3 where two mins follow each other).  m3 bounds everything the
-// thread did not keep.  Four threads share a query row (column quarters); at the end of an item their lists are
-// merged: the four smallest keys are the candidates, min(fifth, the four m3) decoded and lowered by the quantisation
-// slack is the bound the margin test of k_tc_rescore uses.  Padded train rows get the largest value of the range.
+// low s bits are free for the index.  The keys go into a sorted list (m1 <= m2 <= m3) either pair by pair (QUAD =
+// false: two keys are sorted, then merged, 8 min / max per pair, three-input VIMNMX3 where two mins follow each other;
+// m3 bounds everything the thread did not keep) or, the default, four at a time through a tournament
+// (key_insert_quad).  Four threads share a query row (column quarters); at the end of an item their lists are merged:
+// the four smallest keys are the candidates, min(fifth, the four threads' bounds) decoded and lowered by the
+// quantisation slack is the bound the margin test of k_tc_rescore uses.  Padded train rows get the largest value of
+// the range.  tests/test_match_keys_model.py restates the arithmetic and the bound in numpy and checks both.
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void key_insert_pair(uint32_t &m1, uint32_t &m2, uint32_t &m3, uint32_t x, uint32_t y)
 {
