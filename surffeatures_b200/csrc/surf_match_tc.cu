@@ -10,10 +10,14 @@
 // queries that fail the test are redone by the exact kernel, so results equal the exact path.
 //
 //   k_tc_prep        fp32 rows -> BF16 hi / lo in the UMMA canonical K-major layout + |row|^2
-//   k_tc_candidates  128 x 256 output tiles: operands copied to shared memory, one elected thread
-//                    issues tcgen05.mma, accumulators read back with tcgen05.ld, per-row running
-//                    top-kCand kept in registers across the train tiles
-//   k_tc_rescore     exact fp32 distances of the candidates, top-k, margin test
+//   k_tc_candidates    128 x 256 output tiles: operands copied to shared memory, one elected thread
+//                      issues tcgen05.mma, accumulators read back with tcgen05.ld, per-row running
+//                      top-kCand kept in registers across the train tiles (filtered lists: k = 3, 4, databases)
+//   k_tc_candidates3w  k <= 2 against a frame: warp-specialised (MMA warp, copy warp, 16 epilogue warps), four
+//                      operand stages and four TMEM accumulators, scores as sortable 32-bit keys, branch-free lists
+//   k_tc_candidates3   the same key epilogue with MMA and epilogue back to back (128-d rows, A/B)
+//   k_tc_rescore       exact fp32 distances of the candidates, top-k, margin test
+//   k_tc_redo          exact scan for the queries the margin test could not prove
 #include <cuda_bf16.h>
 
 #include <cfloat>
