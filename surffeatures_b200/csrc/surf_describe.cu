@@ -1,9 +1,9 @@
 // surf_describe.cu -- stage 4 of the SURF path (SURFInvoker in OpenCV 2.4.5 nonfree/surf.cpp; SURVEY.md A4,
 // A5; rows a7/a8), reached from SurfFeatures/Logic/vtkSlicerSurfFeaturesLogic.cxx:1384-1389.
 //
-//   k_orient      one warp per keypoint: 113 Haar samples from the integral image, 72 sliding 60-degree
-//                 windows, dominant angle; classifies the keypoint by descriptor-window size and appends
-//                 it to that class's work list.
+//   k_orient      four keypoints per warp: 113 Haar samples from the integral image each, 72 sliding 60-degree
+//                 windows (lane = keypoint x window residue), dominant angle; classifies the keypoint by
+//                 descriptor-window size and appends it to that class's work list.
 //   k_descriptor  one CTA per keypoint, persistent CTAs on an atomic queue per size class.  The rotated
 //                 n x n window's bounding box in the 8-bit image is staged in shared memory, every window
 //                 pixel is a bilinear tap rounded to uchar, the window is reduced to 21 x 21 with
