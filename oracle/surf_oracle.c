@@ -495,6 +495,31 @@ typedef struct {
     float dw[PATCH_SZ * PATCH_SZ];
 } surf_tables;
 
+/* Named reading choices of SURVEY Appendix C as run-time switches, so that a genuine OpenCV -- if one with nonfree
+ * SURF ever is at hand (tests/test_opencv_probe.py) -- can arbitrate between the readings.  All zero = the 2.4.5
+ * reading the CUDA path implements.  Process-wide; test infrastructure only.
+ *   angle_pre244   C-2: 0 = 2.4.4+ convention, kp.angle = fastAtan2(-sum_y, sum_x), sin_dir = -sin(dir), upright 270;
+ *                       1 = the convention before 2.4.4: kp.angle = fastAtan2(sum_y, sum_x), sin_dir = sin(dir),
+ *                       upright 90 (the same physical direction, reported mirrored)
+ *   libm_sincos    0 = sin / cos of the dominant angle correctly rounded to fp32; 1 = this platform's sinf / cosf
+ *                       (what upstream literally calls)
+ *   desc_gauss     C-4: when set, the 20 taps of the descriptor's Gaussian (PATCH_SZ, sigma 3.3) are taken from here
+ *                       instead of the closed form (e.g. the installed cv2.getGaussianKernel(20, 3.3, CV_32F), whose two
+ *                       centre taps differ by ~1 % since the bit-exact even-length kernel of OpenCV 4.x) */
+static struct {
+    int angle_pre244, libm_sincos, have_desc_gauss;
+    float desc_gauss[PATCH_SZ];
+} g_sw;
+
+void orc_set_switches(int angle_pre244, int libm_sincos, const float *desc_gauss20)
+{
+    g_sw.angle_pre244 = angle_pre244;
+    g_sw.libm_sincos = libm_sincos;
+    g_sw.have_desc_gauss = desc_gauss20 != 0;
+    if (desc_gauss20)
+        for (int i = 0; i < PATCH_SZ; i++) g_sw.desc_gauss[i] = desc_gauss20[i];
+}
+
 static void build_tables(surf_tables *t)
 {
     float g[2 * ORI_RADIUS + 1], gd[PATCH_SZ];
@@ -508,6 +533,8 @@ static void build_tables(surf_tables *t)
                 t->pw[t->npts++] = g[i + ORI_RADIUS] * g[j + ORI_RADIUS];
             }
     orc_gaussian_kernel(PATCH_SZ, DESC_SIGMA, gd);
+    if (g_sw.have_desc_gauss)
+        for (int i = 0; i < PATCH_SZ; i++) gd[i] = g_sw.desc_gauss[i];
     for (int i = 0; i < PATCH_SZ; i++)
         for (int j = 0; j < PATCH_SZ; j++) t->dw[i * PATCH_SZ + j] = gd[i] * gd[j];
 }
@@ -525,7 +552,7 @@ static void describe_one(const uint8_t *img, int H, int W, int pitch, const int3
         kp->size = -1;
         return;
     }
-    float dir = 360.f - 90.f;
+    float dir = g_sw.angle_pre244 ? 90.f : 360.f - 90.f;
     if (!p->upright) {
         box_t hx[2], hy[2];
         float X[ORI_BOUND], Y[ORI_BOUND], ang[ORI_BOUND];
@@ -569,7 +596,7 @@ static void describe_one(const uint8_t *img, int H, int W, int pitch, const int3
                 by = sy;
             }
         }
-        dir = orc_fast_atan2(-by, bx);
+        dir = g_sw.angle_pre244 ? orc_fast_atan2(by, bx) : orc_fast_atan2(-by, bx);
     }
     kp->angle = dir;
     if (!vec && !patch_out) return;
@@ -586,8 +613,9 @@ static void describe_one(const uint8_t *img, int H, int W, int pitch, const int3
     uint8_t *win = *winbuf;
     if (!p->upright) {
         float th = dir * (float)(3.1415926535897932384626433832795 / 180);
-        float sd = -(float)sin((double)th);
-        float cd = (float)cos((double)th);
+        float sd = g_sw.libm_sincos ? sinf(th) : (float)sin((double)th);
+        float cd = g_sw.libm_sincos ? cosf(th) : (float)cos((double)th);
+        if (!g_sw.angle_pre244) sd = -sd;
         float off = -(float)(n - 1) / 2;
         float sx0 = cx + off * cd + off * sd;
         float sy0 = cy - off * sd + off * cd;

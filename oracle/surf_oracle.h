@@ -49,6 +49,10 @@ typedef struct {
     int32_t upright;
 } orc_params;
 
+/* Named reading choices as process-wide run-time switches; all zero / null = the 2.4.5 reading the CUDA
+ * path implements.  See surf_oracle.c. */
+void orc_set_switches(int angle_pre244, int libm_sincos, const float *desc_gauss20);
+
 /* ---- sub-steps (exported so tests can pin each one) ---- */
 
 /* sum is (H+1) x (W+1) int32, dense.  clamp01 != 0 applies min(pixel,1) first (mask integral). */

@@ -81,8 +81,31 @@ def lib():
         L.orc_mask_centroid.restype = None
         L.orc_max_threads.argtypes = []
         L.orc_max_threads.restype = i32
+        L.orc_set_switches.argtypes = [i32, i32, vp]
+        L.orc_set_switches.restype = None
         _lib = L
     return _lib
+
+
+class switches:
+    """Context manager for the named reading choices of SURVEY Appendix C (process-wide in the C oracle; all off = the
+    2.4.5 reading the CUDA path implements).  angle_pre244: kp.angle = fastAtan2(sum_y, sum_x), upright 90 (C-2, the
+    convention before 2.4.4); libm_sincos: this platform's sinf / cosf for the dominant angle instead of the correctly
+    rounded values; desc_gauss: the 20 taps of the descriptor's Gaussian, e.g. cv2.getGaussianKernel(20, 3.3, cv2.CV_32F)
+    of the installed OpenCV (C-4)."""
+
+    def __init__(self, angle_pre244=False, libm_sincos=False, desc_gauss=None):
+        self.a, self.l = int(bool(angle_pre244)), int(bool(libm_sincos))
+        self.g = None if desc_gauss is None else np.ascontiguousarray(np.asarray(desc_gauss, np.float32).reshape(-1))
+        assert self.g is None or self.g.size == 20
+
+    def __enter__(self):
+        lib().orc_set_switches(self.a, self.l, _ptr(self.g))
+        return self
+
+    def __exit__(self, *exc):
+        lib().orc_set_switches(0, 0, None)
+        return False
 
 
 def _img(a):

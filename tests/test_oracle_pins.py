@@ -290,3 +290,44 @@ def test_raw_keypoints_equal_numpy_restatement_of_stage3(oracle):
     got = np.array(mine, dtype=oracle.KEYPOINT_DTYPE)
     assert len(got) == len(raw) > 50
     assert got.tobytes() == raw.tobytes()
+
+
+# ---------------------------------------------------------------- Appendix-C reading choices as named switches
+def test_oracle_switches_change_what_they_name_and_nothing_else():
+    """every doubtful upstream detail is a named run-time switch of the oracle so that a genuine
+    OpenCV (tests/test_opencv_probe.py) can arbitrate.  All off = the 2.4.5 reading the CUDA path implements."""
+    import cv2
+
+    from oracle import surf_oracle as so
+    from surffeatures_b200 import speckle
+
+    img = speckle.speckle_frame(240, 320, 11)
+    p = so.params(100, 4, 3, False, False)
+    kp0, d0 = so.detect_and_compute(img, p)
+    assert len(kp0) > 300
+    # C-2: the convention before 2.4.4 reports the mirrored angle; the sampled window is the same physical one
+    with so.switches(angle_pre244=True):
+        kp1, d1 = so.detect_and_compute(img, p)
+        kpu, _ = so.detect_and_compute(img, so.params(100, 4, 3, False, True))
+    assert np.array_equal(kp0["x"], kp1["x"]) and np.array_equal(kp0["size"], kp1["size"])
+    mirrored = np.mod(360.0 - kp1["angle"].astype(np.float64), 360.0)
+    assert np.abs(((kp0["angle"] - mirrored + 180.0) % 360.0) - 180.0).max() < 1e-3
+    e1 = np.linalg.norm(d0 - d1, axis=1)      # sin / cos of the mirrored angle: last-bit effects (a tap rounds the other way)
+    assert np.median(e1) == 0 and np.quantile(e1, 0.95) < 1e-3
+    assert (kpu["angle"] == 90.0).all()
+    # C-4: the installed OpenCV's even-length Gaussian differs from the 2.4.5 closed form on the centre taps
+    g_cv = cv2.getGaussianKernel(20, 3.3, cv2.CV_32F).reshape(-1)
+    with so.switches(desc_gauss=g_cv):
+        kp2, d2 = so.detect_and_compute(img, p)
+    assert np.array_equal(kp0["angle"], kp2["angle"])                       # orientation does not use that kernel
+    e = np.linalg.norm(d0 - d2, axis=1)
+    assert (g_cv != so.gaussian_kernel(20, 3.3)).any() and 0 < np.median(e) < 0.05
+    # libm sinf / cosf for the dominant angle: the platform-dependent last bit
+    with so.switches(libm_sincos=True):
+        kp3, d3 = so.detect_and_compute(img, p)
+    assert np.array_equal(kp0["angle"], kp3["angle"])
+    e3 = np.linalg.norm(d0 - d3, axis=1)
+    assert np.median(e3) == 0 and np.quantile(e3, 0.95) < 1e-3
+    # back to the defaults
+    kp4, d4 = so.detect_and_compute(img, p)
+    assert kp4.tobytes() == kp0.tobytes() and d4.tobytes() == d0.tobytes()
